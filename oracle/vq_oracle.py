@@ -1,0 +1,400 @@
+"""CPU oracle for the codebook hot path -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and the ``cpu_baseline`` /
+``--impl reference`` legs of ``bench.py`` may import this module.  The product
+path (``vqb200``) never does; it fails loudly when the CUDA library is missing.
+
+What this is
+------------
+A restatement, in plain torch-on-CPU, of the arithmetic the reference
+(`MisterBourbaki/vector-quantization-by-ml`, a pure-Python torch library)
+performs on the codebook path.  The reference's arithmetic lives in third-party
+torch ops (``torch.cdist`` -> ATen ``_euclidean_dist`` -> SGEMM, ``einsum`` ->
+``bmm``, ``argmax``, ``F.one_hot``, ``lerp_``, ``mse_loss``, ``F.normalize``;
+reference lock pins torch 2.4.0, this image has torch 2.11), so the oracle calls
+the *same* torch ops in the *same* order -- that is what makes it bit-faithful
+and also what makes it a fair CPU timing baseline.
+
+Pinning
+-------
+The reference's own tests pin no numeric value on this path (shape assertions
+only: reference ``tests/test_vector_quantize_pytorch.py:30-31``).  The oracle is
+therefore pinned against outputs of the reference itself, run in the build
+container: ``tests/golden/make_golden.py`` imports ``/root/reference`` and
+writes fixtures under ``tests/golden/*.pt``; ``tests/test_oracle_golden.py``
+checks this file against them bit-for-bit (indices, quantize, loss,
+cluster_size) / to 1e-6 (embed_avg, embeddings).
+
+Reference lines followed (relative to /root/reference/vector_quantization):
+  codebooks.py:350-435   Codebook.forward
+  codebooks.py:230-255   replace_codes / expire_codes_
+  utils/general.py:41-89 sample_vectors / batched_sample_vectors
+  utils/general.py:92-98 ema_inplace (lerp_)
+  utils/general.py:112-136 gumbel_sample deterministic branch (argmax + one_hot)
+  utils/general.py:154-163 laplace_smoothing / batched_embedding
+  utils/losses.py:5-19   l2norm
+  vector_quantize_pytorch.py:182-430 VectorQuantize.forward (layout glue, ST, commit loss)
+  residual_vq.py:134-269 ResidualVQ.forward
+  utils/kmeans.py:38-120 kmeans (first-forward init)
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Callable, List, Optional, Tuple
+
+import torch
+import torch.nn.functional as F
+
+
+# --------------------------------------------------------------------------- #
+# small helpers
+# --------------------------------------------------------------------------- #
+
+def l2norm(t: torch.Tensor) -> torch.Tensor:
+    """utils/losses.py:19 -- F.normalize(p=2, dim=-1), eps 1e-12."""
+    return F.normalize(t, p=2, dim=-1)
+
+
+def default_init(num_codebooks: int, codebook_size: int, dim: int) -> torch.Tensor:
+    """utils/general.py:101-104 -- kaiming_uniform_ on a fresh (H,K,d) tensor."""
+    t = torch.empty(num_codebooks, codebook_size, dim)
+    torch.nn.init.kaiming_uniform_(t)
+    return t
+
+
+def similarities(flat: torch.Tensor, emb: torch.Tensor, use_cosine_sim: bool) -> torch.Tensor:
+    """codebooks.py:122-123 (dot) / :128-129 (-cdist).  (H,N,d),(H,K,d)->(H,N,K)."""
+    if use_cosine_sim:
+        return torch.einsum("hnd,hcd->hnc", flat, emb)
+    return -torch.cdist(flat, emb)
+
+
+def pick_rows(n_rows: int, m: int, device) -> torch.Tensor:
+    """utils/general.py:62-66 -- which batch rows replace m dead codes.
+
+    Consumes the global torch generator exactly as the reference does."""
+    if n_rows >= m:
+        return torch.randperm(n_rows, device=device)[:m]
+    return torch.randint(0, n_rows, (m,), device=device)
+
+
+# --------------------------------------------------------------------------- #
+# codebook state + parameters
+# --------------------------------------------------------------------------- #
+
+@dataclass
+class CodebookState:
+    """The three persistent buffers of reference Codebook (codebooks.py:183-190)."""
+    embeddings: torch.Tensor     # (H,K,d) fp32
+    embed_avg: torch.Tensor      # (H,K,d) fp32
+    cluster_size: torch.Tensor   # (H,K)   fp32
+    is_initialized: bool = True
+
+    @staticmethod
+    def fresh(num_codebooks: int, codebook_size: int, dim: int,
+              weights_l2norm: bool = False, kmeans_init: bool = False) -> "CodebookState":
+        """codebooks.py:136-139,182-190."""
+        emb = (torch.zeros(num_codebooks, codebook_size, dim) if kmeans_init
+               else default_init(num_codebooks, codebook_size, dim))
+        if weights_l2norm:
+            emb = l2norm(emb)
+        return CodebookState(emb, emb.clone(), torch.zeros(num_codebooks, codebook_size),
+                             is_initialized=not kmeans_init)
+
+    def clone(self) -> "CodebookState":
+        return CodebookState(self.embeddings.clone(), self.embed_avg.clone(),
+                             self.cluster_size.clone(), self.is_initialized)
+
+
+@dataclass
+class CodebookOpts:
+    """Subset of reference CodebookParams (codebooks.py:58-78) on the hot path."""
+    decay: float = 0.8
+    eps: float = 1e-5
+    threshold_ema_dead_code: int = 2
+    reset_cluster_size: Optional[int] = None
+    use_cosine_sim: bool = False
+    weights_l2norm: bool = False          # weights_regularization == "l2norm"
+    ema_update: bool = True
+    kmeans_iters: int = 10
+
+    @property
+    def reset(self) -> float:
+        return float(self.threshold_ema_dead_code if self.reset_cluster_size is None
+                     else self.reset_cluster_size)
+
+
+# --------------------------------------------------------------------------- #
+# kmeans init (utils/kmeans.py:38-120)
+# --------------------------------------------------------------------------- #
+
+def kmeans_init(vectors: torch.Tensor, num_clusters: int, iters: int, use_cosine_sim: bool,
+                all_reduce: Callable[[torch.Tensor], None] = lambda t: None
+                ) -> Tuple[torch.Tensor, torch.Tensor]:
+    H, N, d = vectors.shape
+    cents = torch.stack([v[pick_rows(N, num_clusters, v.device)] for v in vectors.unbind(0)], 0)
+    counts = None
+    for _ in range(iters):
+        if use_cosine_sim:
+            sim = vectors @ cents.transpose(1, 2)
+        else:
+            sim = -torch.cdist(vectors, cents)
+        labels = sim.argmax(-1)
+        counts = torch.zeros(H, num_clusters, dtype=labels.dtype)
+        counts.scatter_add_(-1, labels, torch.ones_like(labels))
+        all_reduce(counts)
+        empty = counts == 0
+        denom = counts.masked_fill(empty, 1)
+        sums = torch.zeros(H, num_clusters, d, dtype=vectors.dtype)
+        sums.scatter_add_(1, labels[..., None].expand(-1, -1, d), vectors)
+        means = sums / denom[..., None]
+        all_reduce(means)
+        if use_cosine_sim:
+            means = l2norm(means)
+        cents = torch.where(empty[..., None], cents, means)
+    return cents, counts
+
+
+# --------------------------------------------------------------------------- #
+# Codebook.forward  (codebooks.py:350-435)
+# --------------------------------------------------------------------------- #
+
+def codebook_forward(state: CodebookState, x: torch.Tensor, opts: CodebookOpts, *,
+                     training: bool = True, mask: Optional[torch.Tensor] = None,
+                     freeze_codebook: bool = False, row_chunk: Optional[int] = None,
+                     all_reduce: Callable[[torch.Tensor], None] = lambda t: None,
+                     want_gap: bool = False):
+    """One forward of the reference Codebook on CPU.
+
+    x: (B,n,d) or (H,B,n,d), any float dtype.  Mutates ``state`` in place when
+    training with EMA.  Returns (quantize fp32 like x, indices int64, extras) where
+    extras has 'top2_rel_gap' (H,N) when ``want_gap`` -- the reference's own fp32
+    top-2 distance gap, relative, used for the north-star index exemption.
+
+    ``row_chunk``: evaluate search/gather/statistics on row chunks (the reference
+    cannot hold N x K at the big configs; cdist on row chunks is bitwise identical
+    to the unchunked call).  EMA statistics are accumulated across
+    chunks with the same einsum per chunk, so embed_sum differs from the unchunked
+    SGEMM only by fp32 summation order.
+    """
+    needs_h = x.ndim < 4
+    x = x.float()                                          # :354
+    if needs_h:
+        x = x.unsqueeze(0)                                 # :356-357
+    H, d = x.shape[0], x.shape[-1]
+    lead = x.shape[1:-1]
+    flat = x.reshape(H, -1, d)                             # :359
+    N = flat.shape[1]
+    K = state.embeddings.shape[1]
+
+    flat_mask = None
+    if mask is not None:                                   # :361-367
+        rep = N // (mask.shape[0] * mask.shape[1])
+        flat_mask = mask[:, None, :].expand(mask.shape[0], rep, mask.shape[1]).reshape(1, -1).expand(H, -1)
+
+    if not state.is_initialized:                           # :368-370, :208-228
+        data = flat
+        if flat_mask is not None:
+            data = flat[flat_mask].reshape(H, -1, d)
+        cents, counts = kmeans_init(data, K, opts.kmeans_iters, opts.use_cosine_sim, all_reduce)
+        state.embeddings.copy_(cents)
+        state.embed_avg.copy_(cents * counts[..., None])
+        state.cluster_size.copy_(counts)
+        state.is_initialized = True
+
+    emb = state.embeddings
+    do_ema = training and opts.ema_update and not freeze_codebook
+
+    chunk = N if row_chunk is None else max(1, int(row_chunk))
+    ind = torch.empty(H, N, dtype=torch.long)
+    quant = torch.empty(H, N, d)
+    counts = torch.zeros(H, K)
+    sums = torch.zeros(H, K, d)
+    gap = torch.empty(H, N) if want_gap else None
+
+    for lo in range(0, N, chunk):
+        hi = min(N, lo + chunk)
+        part = flat[:, lo:hi]
+        sim = similarities(part, emb, opts.use_cosine_sim)            # :386
+        idx = sim.argmax(-1)                                         # general.py:128
+        onehot = F.one_hot(idx, K).type(sim.dtype)                   # general.py:129
+        ind[:, lo:hi] = idx
+        if training:
+            quant[:, lo:hi] = torch.einsum("hnc,hcd->hnd", onehot, emb)   # :395
+        else:
+            quant[:, lo:hi] = emb.gather(1, idx[..., None].expand(-1, -1, d))  # :397
+        if want_gap and K > 1:
+            top2 = sim.topk(2, dim=-1).values
+            denom = top2[..., 0].abs().clamp_min(1e-30)
+            gap[:, lo:hi] = (top2[..., 0] - top2[..., 1]).abs() / denom
+        elif want_gap:
+            gap[:, lo:hi] = float("inf")
+        if do_ema:
+            if flat_mask is not None:
+                onehot[~flat_mask[:, lo:hi]] = 0.0                   # :405-406
+            counts += onehot.sum(dim=1)                              # :408
+            sums += torch.einsum("hnd,hnc->hcd", part, onehot)       # :413
+
+    if do_ema:
+        w = 1 - opts.decay
+        all_reduce(counts)                                           # :410
+        state.cluster_size.lerp_(counts, w)                          # :411
+        sums = sums.contiguous()
+        all_reduce(sums)                                             # :415
+        state.embed_avg.lerp_(sums, w)                               # :417
+        total = state.cluster_size.sum(dim=-1, keepdim=True)
+        smoothed = (state.cluster_size + opts.eps) / (total + K * opts.eps) * total   # :419-421
+        new_emb = state.embed_avg / smoothed[..., None]              # :423
+        if opts.weights_l2norm:
+            new_emb = l2norm(new_emb)                                # :424
+        state.embeddings.copy_(new_emb)                              # :425
+        expire_codes(state, x, opts)                                 # :426
+
+    quant = quant.reshape(H, *lead, d)
+    ind = ind.reshape(H, *lead)
+    if needs_h:
+        quant, ind = quant[0], ind[0]
+    extras = {}
+    if want_gap:
+        extras["top2_rel_gap"] = gap
+    return quant, ind, extras
+
+
+def expire_codes(state: CodebookState, x: torch.Tensor, opts: CodebookOpts,
+                 sample_fn: Optional[Callable[[torch.Tensor, int], torch.Tensor]] = None) -> None:
+    """codebooks.py:245-255 + :230-243.  x is the (H,...,d) input handed to forward."""
+    if opts.threshold_ema_dead_code == 0:
+        return
+    dead = state.cluster_size < opts.threshold_ema_dead_code
+    if not bool(torch.any(dead)):
+        return
+    H, d = x.shape[0], x.shape[-1]
+    rows = x.reshape(H, -1, d)
+    if opts.weights_l2norm:
+        rows = l2norm(rows)                                 # :231
+    for h in range(H):
+        m = int(dead[h].sum().item())                       # :234
+        if sample_fn is None:
+            picked = rows[h][pick_rows(rows.shape[1], m, rows.device)]
+        else:
+            picked = sample_fn(rows[h], m)
+        state.embeddings[h][dead[h]] = picked               # :241
+        state.cluster_size[h][dead[h]] = opts.reset         # :242
+        state.embed_avg[h][dead[h]] = picked * opts.reset   # :243
+
+
+# --------------------------------------------------------------------------- #
+# VectorQuantize.forward (vector_quantize_pytorch.py:182-430), EMA path only
+# --------------------------------------------------------------------------- #
+
+@dataclass
+class VQOpts:
+    heads: int = 1
+    separate_codebook_per_head: bool = False
+    channel_last: bool = True
+    commitment_weight: float = 1.0
+    input_l2norm: bool = False            # transform_input == "l2norm"
+    codebook: CodebookOpts = field(default_factory=CodebookOpts)
+
+
+def vq_forward(state: CodebookState, x: torch.Tensor, opts: VQOpts, *, training: bool = True,
+               mask: Optional[torch.Tensor] = None, freeze_codebook: bool = False,
+               row_chunk: Optional[int] = None, want_gap: bool = False,
+               all_reduce: Callable[[torch.Tensor], None] = lambda t: None):
+    """Returns (quantize, indices, loss[1], extras) like the reference forward."""
+    orig = x
+    only_one = x.ndim == 2
+    if only_one:
+        x = x[:, None, :]                                   # :194-196
+    heads = opts.heads
+    multi = heads > 1
+    B = x.shape[0]
+    if not opts.channel_last:                               # :210-211
+        x = x.movedim(1, -1)
+    spatial = None
+    if x.ndim >= 4:                                         # :212-213
+        spatial = x.shape[1:-1]
+        x = x.reshape(B, -1, x.shape[-1])
+    if multi:                                               # :217-219
+        n = x.shape[1]
+        dh = x.shape[-1] // heads
+        xh = x.reshape(B, n, heads, dh)
+        if opts.separate_codebook_per_head:
+            x = xh.permute(2, 0, 1, 3)                      # h b n d
+        else:
+            x = xh.permute(0, 2, 1, 3).reshape(1, B * heads, n, dh)   # 1 (b h) n d
+    if opts.input_l2norm:                                   # :221
+        x = l2norm(x)
+
+    quant, ind, extras = codebook_forward(state, x, opts.codebook, training=training, mask=mask,
+                                          freeze_codebook=freeze_codebook, row_chunk=row_chunk,
+                                          want_gap=want_gap, all_reduce=all_reduce)
+    commit_q = quant
+    if training:
+        quant = x + (quant - x)                             # :273 (values; detach is autograd-only)
+
+    if multi:                                               # :303-307
+        if opts.separate_codebook_per_head:
+            ind = ind.permute(1, 2, 0)
+        else:
+            ind = ind.reshape(B, heads, -1).permute(0, 2, 1)
+    if spatial is not None:                                 # :309-312
+        ind = ind.reshape(B, *spatial, *ind.shape[2:])
+    if only_one:
+        ind = ind[:, 0]                                     # :314-315
+
+    loss = torch.tensor([0.0])                              # :319
+    if training and opts.commitment_weight > 0:
+        if mask is not None:                                # :347-360
+            per = F.mse_loss(commit_q, x.float(), reduction="none")
+            lm = mask
+            if multi:
+                lm = mask[None, :, None, :].expand(per.shape[0], mask.shape[0],
+                                                   per.shape[1] // mask.shape[0], mask.shape[1]
+                                                   ).reshape(per.shape[0], per.shape[1], mask.shape[1])
+            commit = per[lm].mean()
+        else:
+            commit = F.mse_loss(commit_q, x.float())        # :362
+        loss = loss + commit * opts.commitment_weight       # :364
+
+    if multi:                                               # :394-398
+        if opts.separate_codebook_per_head:
+            quant = quant.permute(1, 2, 0, 3).reshape(B, quant.shape[2], -1)
+        else:
+            n = quant.shape[2]
+            quant = quant.reshape(B, heads, n, -1).permute(0, 2, 1, 3).reshape(B, n, -1)
+    if spatial is not None:                                 # :406-407
+        quant = quant.reshape(B, *spatial, quant.shape[-1])
+    if not opts.channel_last:                               # :408-409
+        quant = quant.movedim(-1, 1)
+    if only_one:
+        quant = quant[:, 0]                                 # :410-411
+    if mask is not None:                                    # :415-418
+        quant = torch.where(mask[..., None], quant, orig)
+    return quant, ind, loss, extras
+
+
+# --------------------------------------------------------------------------- #
+# ResidualVQ.forward (residual_vq.py:134-269), no quantize-dropout
+# --------------------------------------------------------------------------- #
+
+def rvq_forward(states: List[CodebookState], x: torch.Tensor, opts: VQOpts, *, training: bool = True,
+                mask: Optional[torch.Tensor] = None, freeze_codebook: bool = False,
+                row_chunk: Optional[int] = None, want_gap: bool = False,
+                all_reduce: Callable[[torch.Tensor], None] = lambda t: None):
+    """states: one CodebookState per level (the same object repeated for shared_codebook).
+
+    Returns (quantized_out, indices (...,Q), losses (1,Q), extras-per-level)."""
+    out = 0.0                                               # :154
+    residual = x                                            # :155
+    all_ind, all_loss, all_extras = [], [], []
+    for st in states:                                       # :212
+        q, ind, loss, ex = vq_forward(st, residual, opts, training=training, mask=mask,
+                                      freeze_codebook=freeze_codebook, row_chunk=row_chunk,
+                                      want_gap=want_gap, all_reduce=all_reduce)
+        residual = residual - q                             # :232
+        out = out + q                                       # :233
+        all_ind.append(ind)
+        all_loss.append(loss)
+        all_extras.append(ex)
+    return out, torch.stack(all_ind, -1), torch.stack(all_loss, -1), all_extras

@@ -1,0 +1,39 @@
+"""Shared helpers: load a golden fixture and map its cfg onto oracle opts / vqb200 modules."""
+import glob
+import os
+
+import torch
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def fixture_names():
+    return sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.pt")))
+
+
+def load(name):
+    return torch.load(os.path.join(GOLDEN_DIR, name + ".pt"), weights_only=False)
+
+
+def oracle_opts(cfg):
+    from oracle.vq_oracle import CodebookOpts, VQOpts
+    cb = CodebookOpts(threshold_ema_dead_code=cfg["thr"], use_cosine_sim=cfg.get("cosine", False),
+                      weights_l2norm=bool(cfg.get("l2w")))
+    return VQOpts(heads=cfg.get("heads", 1), separate_codebook_per_head=cfg.get("separate", False),
+                  channel_last=cfg.get("channel_last", True), input_l2norm=bool(cfg.get("l2in")), codebook=cb)
+
+
+def oracle_states(fx):
+    from oracle.vq_oracle import CodebookState
+    cfg = fx["cfg"]
+    sts = [CodebookState(s["embeddings"].clone(), s["embed_avg"].clone(), s["cluster_size"].clone(),
+                         is_initialized=not cfg.get("kmeans", False)) for s in fx["init"]]
+    if cfg.get("shared"):
+        sts = [sts[0]] * len(sts)
+    return sts
+
+
+def rel_err(a, b):
+    """max |a-b| relative to max |b| (buffer-level relative error)."""
+    a, b = a.double(), b.double()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))

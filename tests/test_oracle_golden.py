@@ -1,0 +1,53 @@
+"""Pins the CPU oracle against fixtures produced by the live reference (tests/golden/make_golden.py).
+
+No GPU.  Bit-exact: indices, quantize, loss, cluster_size.  embed_avg/embeddings: 1e-6 relative
+(the oracle accumulates embed_sum with the same einsum, so these are normally bit-exact too).
+"""
+import pytest
+import torch
+
+import golden_util as gu
+from oracle import vq_oracle as O
+
+
+@pytest.mark.parametrize("name", gu.fixture_names())
+def test_oracle_matches_reference_fixture(name):
+    fx = gu.load(name)
+    cfg = fx["cfg"]
+    opts = gu.oracle_opts(cfg)
+    states = gu.oracle_states(fx)
+    training = cfg.get("training", True)
+    for s, step in enumerate(fx["steps"]):
+        x = fx["x"] + 0.01 * s
+        torch.manual_seed(fx["rng_seed"] + s)
+        if cfg["kind"] == "vq":
+            q, ind, loss, ex = O.vq_forward(states[0], x, opts, training=training, mask=fx["mask"], want_gap=True)
+            gaps = [ex["top2_rel_gap"]]
+        else:
+            q, ind, loss, exs = O.rvq_forward(states, x, opts, training=training, mask=fx["mask"], want_gap=True)
+            gaps = [e["top2_rel_gap"] for e in exs]
+        assert torch.equal(ind, step["indices"]), f"{name} step {s}: indices differ"
+        assert torch.equal(q, step["quantize"]), f"{name} step {s}: quantize not bit-exact"
+        assert q.dtype == step["quantize"].dtype and ind.dtype == torch.int64
+        assert loss.shape == step["loss"].shape
+        assert torch.equal(loss, step["loss"]), f"{name} step {s}: loss {loss} vs {step['loss']}"
+        for lvl, after in enumerate(step["after"]):
+            st = states[lvl]
+            assert torch.equal(st.cluster_size, after["cluster_size"]), f"{name} step {s} lvl {lvl} cluster_size"
+            assert gu.rel_err(st.embed_avg, after["embed_avg"]) <= 1e-6
+            assert gu.rel_err(st.embeddings, after["embeddings"]) <= 1e-6
+        for g_or, g_ref in zip(gaps, step["top2_rel_gap"]):
+            assert torch.allclose(g_or.reshape(-1), g_ref.reshape(-1), rtol=1e-4, atol=1e-9)
+
+
+def test_row_chunked_oracle_equals_unchunked():
+    """The big configs need a row-chunked oracle: chunking must not change indices/quantize."""
+    fx = gu.load("c1_noexpire")
+    opts = gu.oracle_opts(fx["cfg"])
+    a, b = gu.oracle_states(fx)[0], gu.oracle_states(fx)[0]
+    qa, ia, la, _ = O.vq_forward(a, fx["x"], opts)
+    qb, ib, lb, _ = O.vq_forward(b, fx["x"], opts, row_chunk=100)
+    assert torch.equal(ia, ib) and torch.equal(qa, qb) and torch.equal(la, lb)
+    assert torch.equal(a.cluster_size, b.cluster_size)
+    assert gu.rel_err(b.embed_avg, a.embed_avg) <= 1e-6
+    assert gu.rel_err(b.embeddings, a.embeddings) <= 1e-6
