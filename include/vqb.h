@@ -1,0 +1,166 @@
+/*
+ * vqb.h -- C ABI of libvqb200.so: the B200 (sm_100a) codebook hot path behind the
+ * module API of MisterBourbaki/vector-quantization-by-ml (a pure-Python torch library).
+ *
+ * The reference has no FFI/plugin layer: its "operators" are torch library calls made
+ * from Codebook.forward / VectorQuantize.forward / ResidualVQ.forward.  Every entry
+ * point below names the reference call site (file:line under
+ * /root/reference/vector_quantization/) whose torch ops it replaces.  A maintainer of
+ * the reference binds these with ctypes.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless named host_*.
+ *   - all work is enqueued asynchronously on `stream` (a cudaStream_t passed as void*);
+ *     no entry point synchronises the device.
+ *   - the library owns no memory: buffers, caches and workspaces are allocated by the caller
+ *     (sizes from the *_bytes() helpers) and only borrowed for the duration of the call.
+ *   - return 0 on success, negative VQB_ERR_* otherwise; message via vqb_last_error()
+ *     (thread-local).  Never throws, never exits.
+ *   - there is no CPU implementation behind these symbols.
+ *
+ * Shapes: H codebooks (heads), N latent rows per codebook, K codes, d dims; row-major,
+ * contiguous: latents (H,N,d), codebook (H,K,d), indices (H,N) int64.
+ */
+#ifndef VQB_H_
+#define VQB_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VQB_VERSION 100
+
+#define VQB_OK               0
+#define VQB_ERR_INVALID     -1   /* bad argument */
+#define VQB_ERR_CUDA        -2   /* a CUDA runtime/driver call failed */
+#define VQB_ERR_WORKSPACE   -3   /* workspace / cache too small */
+#define VQB_ERR_UNSUPPORTED -4   /* shape outside what the kernels handle */
+
+/* latent element types accepted for x */
+#define VQB_F32  0
+#define VQB_BF16 1
+#define VQB_F16  2
+
+/* similarity: reference codebooks.py:128-129 (-cdist) / :122-123 (einsum dot) */
+#define VQB_EUCLID 0
+#define VQB_DOT    1
+
+/* vqb_search flags */
+#define VQB_SEARCH_LATENTS_PREPARED 1  /* ws already holds bf16 latents + row stats (written by vqb_rvq_level) */
+#define VQB_SEARCH_FORCE_EXACT      2  /* skip the tensor-core pass: fp32/fp64 CUDA-core scan of every code */
+
+int         vqb_version(void);
+const char* vqb_last_error(void);
+
+/* ---- derived codebook cache ---------------------------------------------------------
+ * bf16 (negated, padded) copy of the codebook for the tensor-core pass + per-code norms and
+ * rounding-error bounds.  Derived from `embeddings`; must be rebuilt whenever embeddings
+ * change (EMA refresh codebooks.py:425, expiry :241, kmeans init :226, load_state_dict). */
+size_t vqb_codebook_cache_bytes(int64_t H, int K, int d);
+int    vqb_prepare_codebook(const float* codebook, int64_t H, int K, int d, int metric,
+                            void* cache, size_t cache_bytes, void* stream);
+
+/* ---- nearest-code search ------------------------------------------------------------
+ * Replaces codebooks.py:386 (similarity_fn: -cdist / einsum, N x K fp32 materialised) +
+ * utils/general.py:128-129 (argmax + one_hot).  bf16 tcgen05 GEMM with a fused per-row
+ * top-2 epilogue produces candidates; candidates are re-ranked with fp64-accumulated
+ * fp32 scores (sqrt(clamp(|x|^2+|c|^2-2x.c)) resp. x.c), lowest index wins ties, like
+ * torch argmax.  Rows whose candidate set cannot be proven complete are rescanned exactly.
+ *   idx_out   (H,N) int64  code index + idx_offset
+ *   score_out (H,N) fp32, nullable: the exact score of the winner (euclid: distance,
+ *             dot: -similarity; smaller is better) -- used by the sharded-codebook merge.
+ *   codebook  (H,K,d) fp32 master copy (re-rank reads it), cache from vqb_prepare_codebook. */
+size_t vqb_search_workspace_bytes(int64_t H, int64_t N, int K, int d);
+int    vqb_search(const void* x, int x_dtype, const float* codebook, const void* cache,
+                  int metric, int64_t H, int64_t N, int K, int d, int64_t idx_offset,
+                  int64_t* idx_out, float* score_out, int flags,
+                  void* ws, size_t ws_bytes, void* stream);
+/* debug/statistics of the last vqb_search on this ws: host_out[0]=rows re-ranked,
+ * [1]=rows rescanned exactly, [2]=tensor-core pass used (0/1).  Synchronises `stream`. */
+int    vqb_search_stats(const void* ws, int64_t* host_out3, void* stream);
+
+/* ---- l2 normalisation of rows (transform_input="l2norm") ------------------------------
+ * Replaces vector_quantize_pytorch.py:221 -> utils/losses.py:19 (F.normalize, eps 1e-12). */
+int vqb_l2norm_rows(const void* x, int x_dtype, float* out, int64_t rows, int d, void* stream);
+
+/* ---- gather + straight-through + commitment loss --------------------------------------
+ * Replaces codebooks.py:393-397 (one-hot einsum / batched_embedding gather),
+ * vector_quantize_pytorch.py:273 (x + (q - x).detach()) and :347-364 (mse commitment loss).
+ *   q_out (H,N,d) fp32: training ? fl(x + fl(c - x)) : c        (bit-exact given idx)
+ *   loss_out[0] = mean((c - x)^2) over rows with mask!=0 (all rows if mask NULL), [1] = #rows used
+ *   mask (N) uint8 per row, shared by all H, nullable.  want_loss=0 skips the loss. */
+size_t vqb_gather_workspace_bytes(int64_t H, int64_t N, int d);
+int    vqb_gather_st_loss(const void* x, int x_dtype, const float* codebook, const int64_t* idx,
+                          const uint8_t* mask, int training, int want_loss,
+                          float* q_out, float* loss_out,
+                          int64_t H, int64_t N, int K, int d,
+                          void* ws, size_t ws_bytes, void* stream);
+/* backward of the two lines above: grad_x = grad_q + coef * (x - c) * grad_loss[0]
+ * with coef = commitment_weight * 2 / (rows_used * d); rows with mask==0 get grad_q only. */
+int    vqb_st_commit_backward(const float* grad_q, const float* grad_loss, const void* x, int x_dtype,
+                              const float* codebook, const int64_t* idx, const uint8_t* mask,
+                              float coef, float* grad_x,
+                              int64_t H, int64_t N, int K, int d, void* stream);
+
+/* ---- EMA statistics: deterministic sort-and-segment reduction -------------------------
+ * Replaces codebooks.py:405-408 (masked one-hot column sums) and :413 (x^T . onehot SGEMM).
+ *   stats (H,K,d+1) fp32: [..., :d] = sum of rows assigned to the code, [..., d] = count.
+ * Stable counting sort of rows by code, fixed-order segmented sums: bitwise reproducible. */
+size_t vqb_ema_workspace_bytes(int64_t H, int64_t N, int K, int d);
+/* absmax_bound2: nullable device pointer to two floats (a, b) with a + b >= max|x_j| over the batch
+ * (the first 8 bytes of a search workspace after vqb_search on the same x hold exactly that);
+ * when NULL the bound is computed with one extra pass over x.  It only sizes the fixed-point scale. */
+int    vqb_ema_reduce(const void* x, int x_dtype, const int64_t* idx, const uint8_t* mask,
+                      const float* absmax_bound2,
+                      int64_t H, int64_t N, int K, int d, float* stats,
+                      void* ws, size_t ws_bytes, void* stream);
+/* Replaces codebooks.py:411,417 (lerp_), :419-421 (laplace smoothing), :423-425 (divide,
+ * optional l2norm, copy into embeddings).  weight = 1 - decay.  ws: >= 4*H bytes of scratch
+ * (an EMA workspace is fine; its contents are dead once stats has been written). */
+int    vqb_ema_apply(const float* stats, float* cluster_size, float* embed_avg, float* embeddings,
+                     float weight, double eps, int l2norm, int64_t H, int K, int d,
+                     void* ws, size_t ws_bytes, void* stream);
+
+/* ---- dead-code expiry scatter ---------------------------------------------------------
+ * Replaces codebooks.py:241-243 for one codebook h: the j-th dead code (ascending index,
+ * dead = cluster_size < threshold) takes row sample_rows[j] of x (l2-normalised first when
+ * l2norm, codebooks.py:231).  The RNG draw (utils/general.py:62-66) stays in torch host code.
+ *   x (N,d) rows of codebook h; sample_rows (m) int64; m = number of dead codes (host-known,
+ *   the reference syncs for it too: codebooks.py:234).  cluster_size/embed_avg/embeddings point
+ *   at codebook h's slices. */
+int    vqb_expire_scatter(const void* x, int x_dtype, const int64_t* sample_rows, int64_t m,
+                          float threshold, float reset, int l2norm,
+                          float* cluster_size, float* embed_avg, float* embeddings,
+                          int64_t N, int K, int d, void* stream);
+
+/* ---- ResidualVQ level step ------------------------------------------------------------
+ * Replaces, for one level, codebooks.py:393-397 + vector_quantize_pytorch.py:273,362 +
+ * residual_vq.py:232-233, and prepares the next level's search operand in the same pass:
+ *   q        = training ? fl(r + fl(c - r)) : c      (rows with mask==0: q = r, as torch.where does at :415-418)
+ *   out      = first_level ? fl(0.0f + q) : fl(out + q)
+ *   r_next   = fl(r - q)                  (residual_out; may alias residual_in, but the caller normally
+ *                                          ping-pongs two buffers so the level input survives for expiry sampling)
+ *   loss_out = [mean((c - r)^2) over rows with mask!=0, rows used]   (as vqb_gather_st_loss)
+ *   next_ws  : bf16 copy + row stats of r_next, laid out exactly as vqb_search expects with
+ *              VQB_SEARCH_LATENTS_PREPARED (NULL on the last level).
+ *   q_out    : nullable, per-level quantized output (needed only for return_all_codes). */
+int    vqb_rvq_level(const float* residual_in, float* residual_out, const float* codebook, const int64_t* idx,
+                     const uint8_t* mask, int training, int first_level, float* quantized_out, float* q_out,
+                     float* loss_out, int64_t N, int K, int d,
+                     void* gather_ws, size_t gather_ws_bytes,
+                     void* next_ws, size_t next_ws_bytes, void* stream);
+
+/* ---- sharded-codebook merge (K >= 64K split across GPUs) ------------------------------
+ * No reference counterpart.  key = (orderable(score) << 32) | index, so an
+ * all_reduce(MIN) over uint64 (as int64 with the sign bit clear) picks the smallest score and,
+ * on ties, the lowest global index -- torch argmax semantics. */
+int    vqb_minkey_pack(const float* score, const int64_t* idx, int64_t n, int64_t* keys, void* stream);
+int    vqb_minkey_unpack(const int64_t* keys, int64_t n, int64_t* idx, float* score, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VQB_H_ */

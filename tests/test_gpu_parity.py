@@ -1,0 +1,269 @@
+"""GPU parity tests: the CUDA path (through the C ABI, via the vqb200 modules) against
+(a) the golden fixtures recorded from the live reference and (b) the CPU oracle on seeded inputs.
+
+Bars (BASELINE.json north_star): indices identical except rows whose REFERENCE fp32 top-2 gap is
+< 1e-6 relative; quantize bit-exact given the indices; loss and EMA buffers within 1e-5 relative
+(relative to the buffer's max magnitude); cluster_size exact.
+"""
+import pytest
+import torch
+
+import golden_util as gu
+
+pytestmark = pytest.mark.gpu
+
+REL = 1e-5
+
+
+def _dev():
+    return torch.device("cuda:0")
+
+
+def _cpu_draw(num_rows, m, device):
+    """Draw replacement/kmeans rows from the CPU generator exactly like the oracle/reference-on-CPU did."""
+    if num_rows >= m:
+        return torch.randperm(num_rows)[:m].to(device)
+    return torch.randint(0, num_rows, (m,)).to(device)
+
+
+@pytest.fixture(autouse=True)
+def _patch_draw(monkeypatch):
+    from vqb200 import codebook
+    monkeypatch.setattr(codebook.Codebook, "_draw_rows", staticmethod(_cpu_draw))
+
+
+def build_module(cfg):
+    from vqb200 import CodebookParams, KmeansParameters, ResidualVQ, VectorQuantize
+    cb_dim = cfg.get("cb_dim", cfg["dim"])
+    cp = CodebookParams(dim=cb_dim, codebook_size=cfg["K"], threshold_ema_dead_code=cfg["thr"],
+                        use_cosine_sim=cfg.get("cosine", False),
+                        transform_input="l2norm" if cfg.get("l2in") else "identity",
+                        weights_regularization="l2norm" if cfg.get("l2w") else "identity",
+                        initialization_by_kmeans=cfg.get("kmeans", False),
+                        kmeans_params=KmeansParameters() if cfg.get("kmeans") else None)
+    if cfg["kind"] == "vq":
+        mod = VectorQuantize(dim=cfg["dim"], codebook_params=cp, codebook_dim=cfg.get("cb_dim"),
+                             heads=cfg.get("heads", 1), separate_codebook_per_head=cfg.get("separate", False),
+                             channel_last=cfg.get("channel_last", True), sync_codebook=False)
+        books = [mod._codebook]
+    else:
+        mod = ResidualVQ(dim=cfg["dim"], num_quantizers=cfg["Q"], codebook_params=cp,
+                         shared_codebook=cfg.get("shared", False), sync_codebook=False)
+        books = [l._codebook for l in mod.layers]
+    return mod, books
+
+
+def load_state(books, fx):
+    seen = set()
+    for cb, init in zip(books, fx["init"]):
+        if id(cb) in seen:
+            continue
+        seen.add(id(cb))
+        cb.embeddings.copy_(init["embeddings"])
+        cb.embed_avg.copy_(init["embed_avg"])
+        cb.cluster_size.copy_(init["cluster_size"])
+        cb.invalidate_cache()
+
+
+def run_fixture(name, fused):
+    fx = gu.load(name)
+    cfg = fx["cfg"]
+    mod, books = build_module(cfg)
+    mod = mod.to(_dev())
+    load_state(books, fx)
+    training = cfg.get("training", True)
+    mod.train(training)
+    if cfg["kind"] == "rvq":
+        mod.use_fused_levels = fused
+    l2 = bool(cfg.get("l2in"))
+    mask = fx["mask"].to(_dev()) if fx["mask"] is not None else None
+    for s, step in enumerate(fx["steps"]):
+        x = (fx["x"] + 0.01 * s).to(_dev())
+        torch.manual_seed(fx["rng_seed"] + s)
+        with torch.no_grad():
+            q, ind, loss = mod(x, mask=mask)
+        torch.cuda.synchronize()
+        q, ind, loss = q.cpu(), ind.cpu(), loss.cpu()
+        ref_ind = step["indices"]
+        assert ind.shape == ref_ind.shape and ind.dtype == torch.int64
+        assert q.shape == step["quantize"].shape and q.dtype == torch.float32
+        assert loss.shape == step["loss"].shape
+        diff = ind != ref_ind
+        if bool(diff.any()):
+            # only rows inside the reference's own fp32 tie zone may differ
+            gaps = step["top2_rel_gap"]
+            if cfg["kind"] == "vq" and len(gaps) == 1 and gaps[0].numel() == ind.numel() and cfg.get("heads", 1) == 1:
+                g = gaps[0].reshape(ind.shape)
+                assert bool((g[diff] < 1e-6).all()), f"{name} step {s}: index mismatch outside the tie exemption"
+                pytest.skip(f"{name}: {int(diff.sum())} exempt tie rows changed the trajectory; later values not comparable")
+            raise AssertionError(f"{name} step {s}: {int(diff.sum())} index mismatches")
+        if l2:
+            assert gu.rel_err(q, step["quantize"]) <= 1e-6
+        else:
+            assert torch.equal(q, step["quantize"]), f"{name} step {s}: quantize not bit-exact"
+        ref_loss = step["loss"]
+        assert torch.allclose(loss, ref_loss, rtol=REL, atol=1e-12), f"{name} step {s}: loss {loss} vs {ref_loss}"
+        for lvl, after in enumerate(step["after"]):
+            cb = books[lvl]
+            assert torch.equal(cb.cluster_size.cpu(), after["cluster_size"]), f"{name} step {s} lvl {lvl}: cluster_size"
+            assert gu.rel_err(cb.embed_avg.cpu(), after["embed_avg"]) <= REL, f"{name} step {s} lvl {lvl}: embed_avg"
+            assert gu.rel_err(cb.embeddings.cpu(), after["embeddings"]) <= REL, f"{name} step {s} lvl {lvl}: embeddings"
+
+
+@pytest.mark.parametrize("name", gu.fixture_names())
+def test_module_matches_reference_fixture(name):
+    run_fixture(name, fused=True)
+
+
+@pytest.mark.parametrize("name", [n for n in gu.fixture_names() if n.startswith("rvq")])
+def test_rvq_generic_loop_matches_reference_fixture(name):
+    run_fixture(name, fused=False)
+
+
+# ------------------------------------------------------------------------------------------------
+# op level: search (tensor-core path) vs exact scan vs oracle, many shapes incl. ragged / padded
+# ------------------------------------------------------------------------------------------------
+SEARCH_SHAPES = [
+    # H, N, K, d, cosine, codebook scale (None = reference default kaiming-uniform scale)
+    (1, 1, 1, 1, False, 0.5),
+    (1, 7, 3, 5, False, 0.5),
+    (1, 128, 256, 64, False, 0.5),
+    (1, 1024, 512, 256, False, 0.5),
+    (1, 1024, 512, 256, False, None),
+    (1, 1000, 300, 100, False, 0.5),
+    (3, 333, 260, 72, False, 0.5),
+    (2, 777, 520, 96, True, 0.5),
+    (1, 2048, 1024, 512, False, 0.5),
+    (1, 2048, 1024, 512, True, 0.5),
+    (1, 513, 2050, 64, False, 0.5),
+    (1, 300, 64, 640, False, 0.5),       # d_pad > 512: exact-scan path
+]
+
+
+@pytest.mark.parametrize("H,N,K,d,cos,scale", SEARCH_SHAPES)
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_search_matches_oracle(H, N, K, d, cos, scale, dtype):
+    from oracle import vq_oracle as O
+    from vqb200 import ops
+    g = torch.Generator().manual_seed(1000 * N + K + d)
+    x = torch.randn(H, N, d, generator=g).to(dtype)
+    if scale is None:
+        c = (torch.rand(H, K, d, generator=g) * 2 - 1) * (6.0 / (K * d)) ** 0.5
+    else:
+        c = torch.randn(H, K, d, generator=g) * scale
+    xd, cd = x.to(_dev()), c.to(_dev())
+    cache = ops.prepare_codebook(cd, cos)
+    idx, score, ws = ops.search(xd, cd, cache, cos, want_score=True)
+    idx_ex, score_ex, _ = ops.search(xd, cd, cache, cos, force_exact=True, want_score=True)
+    torch.cuda.synchronize()
+    stats = ops.search_stats(ws)
+    if ((d + 63) // 64) * 64 <= 512:
+        assert stats["tensor_core_pass"] == 1
+    # the two CUDA paths use the same fp64-accumulated score: they must agree exactly
+    assert torch.equal(idx, idx_ex), f"tc vs exact: {int((idx != idx_ex).sum())} mismatches, stats {stats}"
+    assert torch.equal(score, score_ex)
+    sim = O.similarities(x.float(), c, cos)
+    ref = sim.argmax(-1)
+    if K > 1:
+        top2 = sim.topk(2, -1).values
+        gap = (top2[..., 0] - top2[..., 1]).abs() / top2[..., 0].abs().clamp_min(1e-30)
+    else:
+        gap = torch.full(ref.shape, float("inf"))
+    bad = (idx.cpu() != ref) & (gap >= 1e-6)
+    assert not bool(bad.any()), f"{int(bad.sum())} mismatches outside the tie exemption"
+    # score: distance (euclid) or -similarity (dot) of the winner
+    ref_score = -sim.gather(-1, idx.cpu()[..., None])[..., 0]
+    assert torch.allclose(score.cpu(), ref_score, rtol=2e-5, atol=2e-5 * float(ref_score.abs().max()) + 1e-7)
+
+
+def test_search_duplicate_codes_and_ties():
+    """Exact duplicates in the codebook (expiry copies batch rows): the lowest index must win, as torch.argmax."""
+    from vqb200 import ops
+    g = torch.Generator().manual_seed(5)
+    c = torch.randn(1, 512, 64, generator=g)
+    c[0, 100] = c[0, 7]
+    c[0, 300] = c[0, 7]
+    c[0, 301] = c[0, 7]
+    c[0, 411] = c[0, 7]
+    x = torch.randn(1, 256, 64, generator=g)
+    x[0, :64] = c[0, 7] + 1e-3 * torch.randn(64, 64, generator=g)
+    xd, cd = x.to(_dev()), c.to(_dev())
+    idx, _, ws = ops.search(xd, cd, ops.prepare_codebook(cd, False), False)
+    ref = (-torch.cdist(x, c)).argmax(-1)
+    assert torch.equal(idx.cpu()[0, :64], torch.full((64,), 7))
+    assert torch.equal(idx.cpu(), ref)
+
+
+def test_gather_st_loss_and_backward_match_torch():
+    from vqb200 import ops
+    g = torch.Generator().manual_seed(3)
+    H, N, K, d = 2, 300, 50, 40
+    x = torch.randn(H, N, d, generator=g)
+    c = torch.randn(H, K, d, generator=g)
+    idx = torch.randint(0, K, (H, N), generator=g)
+    mask = torch.rand(N, generator=g) > 0.3
+    xd = x.to(_dev()).requires_grad_(True)
+    q, commit = ops.quantize_training(xd, c.to(_dev()), idx.to(_dev()), mask.to(torch.uint8).to(_dev()), True)
+    gq = torch.randn(H, N, d, generator=g)
+    (q * gq.to(_dev())).sum().add(commit * 0.7).backward()
+    xr = x.clone().requires_grad_(True)
+    cq = torch.stack([c[h][idx[h]] for h in range(H)])
+    qr = xr + (cq - xr).detach()
+    lr = torch.nn.functional.mse_loss(cq, xr, reduction="none")[:, mask].mean()
+    (qr * gq).sum().add(lr * 0.7).backward()
+    assert torch.equal(q.detach().cpu(), qr.detach())
+    assert torch.allclose(commit.detach().cpu(), lr.detach(), rtol=1e-6)
+    assert torch.allclose(xd.grad.cpu(), xr.grad, rtol=1e-5, atol=1e-7)
+
+
+def test_ema_reduce_is_deterministic_and_exact():
+    from vqb200 import ops
+    g = torch.Generator().manual_seed(11)
+    H, N, K, d = 2, 5000, 97, 72
+    x = torch.randn(H, N, d, generator=g)
+    idx = torch.randint(0, K, (H, N), generator=g)
+    idx[:, :2000] = 3                      # one very long segment
+    mask = torch.rand(N, generator=g) > 0.2
+    xd, idd, md = x.to(_dev()), idx.to(_dev()), mask.to(torch.uint8).to(_dev())
+    a = ops.ema_reduce(xd, idd, md, K).cpu()
+    b = ops.ema_reduce(xd, idd, md, K).cpu()
+    assert torch.equal(a, b), "EMA statistics must be bitwise reproducible"
+    onehot = torch.nn.functional.one_hot(idx, K).double()
+    onehot[:, ~mask] = 0
+    ref_cnt = onehot.sum(1)
+    ref_sum = torch.einsum("hnd,hnc->hcd", x.double(), onehot)
+    assert torch.equal(a[..., d].double(), ref_cnt)
+    assert float((a[..., :d].double() - ref_sum).abs().max()) <= 1e-6 * float(ref_sum.abs().max())
+
+
+def test_minkey_roundtrip_and_order():
+    from vqb200 import ops
+    g = torch.Generator().manual_seed(2)
+    score = torch.randn(1000, generator=g) * 10
+    score[:10] = 0.0
+    score[10:20] = -0.0
+    idx = torch.randint(0, 1 << 20, (1000,), generator=g)
+    keys = ops.minkey_pack(score.to(_dev()), idx.to(_dev()))
+    i2, s2 = ops.minkey_unpack(keys, want_score=True)
+    assert torch.equal(i2.cpu(), idx)
+    assert torch.equal(s2.cpu().abs(), score.abs()) and torch.equal(s2.cpu()[20:], score[20:])
+    k = keys.cpu()
+    order = torch.argsort(k, stable=True)
+    s_sorted = score[order]
+    assert bool((s_sorted[1:] >= s_sorted[:-1]).all())
+
+
+def test_state_dict_roundtrip_and_cache_invalidation():
+    from vqb200 import CodebookParams, VectorQuantize
+    vq = VectorQuantize(dim=32, codebook_params=CodebookParams(dim=32, codebook_size=64, threshold_ema_dead_code=0)).to(_dev())
+    x = torch.randn(2, 50, 32, device=_dev())
+    vq.eval()
+    _, i0, _ = vq(x)
+    sd = {k: v.clone() for k, v in vq.state_dict().items()}
+    assert set(sd) == {"_codebook.cluster_size", "_codebook.embed_avg", "_codebook.embeddings"}
+    new = torch.randn(1, 64, 32, device=_dev())
+    sd["_codebook.embeddings"] = new
+    vq.load_state_dict(sd)
+    _, i1, _ = vq(x)
+    ref = (-torch.cdist(x.reshape(1, -1, 32).cpu(), new.cpu())).argmax(-1).reshape(2, 50)
+    assert torch.equal(i1.cpu(), ref), "search must see embeddings written through load_state_dict"

@@ -1,0 +1,116 @@
+"""CPU-only checks: the C-ABI library loads and exports every symbol include/vqb.h declares (no compute calls),
+the module API mirrors the reference (signatures, buffers, state_dict keys), unsupported options and CPU tensors
+fail loudly (there is no fallback)."""
+import inspect
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    text = open(os.path.join(ROOT, "include", "vqb.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(vqb_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_header_symbol():
+    from vqb200 import _lib
+    handle = _lib.lib()
+    names = _header_symbols()
+    assert len(names) >= 18
+    for n in names:
+        assert hasattr(handle, n), f"libvqb200.so does not export {n}"
+        assert n in _lib.SIGNATURES, f"{n} has no ctypes signature"
+    assert sorted(_lib.SIGNATURES) == names
+    assert handle.vqb_version() == 100
+
+
+def test_size_helpers_and_argument_errors_without_gpu():
+    from vqb200 import _lib
+    h = _lib.lib()
+    assert h.vqb_codebook_cache_bytes(1, 8192, 256) >= 8192 * 256 * 2
+    assert h.vqb_search_workspace_bytes(1, 1024, 512, 256) > 1024 * 256 * 2
+    assert h.vqb_ema_workspace_bytes(1, 1024, 512, 256) >= 512 * 256 * 8
+    assert h.vqb_gather_workspace_bytes(1, 1024, 256) > 0
+    # argument validation happens before any CUDA call
+    rc = h.vqb_search(None, 0, None, None, 0, 1, 1, 1, 1, 0, None, None, 0, None, 0, None)
+    assert rc == -1 and b"null" in h.vqb_last_error()
+    with pytest.raises(ValueError):
+        _lib.check(rc, "vqb_search")
+
+
+def test_signatures_match_reference_api():
+    from vqb200 import Codebook, ResidualVQ, VectorQuantize
+    cb = list(inspect.signature(Codebook.__init__).parameters)
+    assert cb[1:] == ["dim", "codebook_size", "num_codebooks", "initialization_by_kmeans", "kmeans_params", "decay",
+                      "eps_for_smoothing", "threshold_ema_dead_code", "reset_cluster_size", "use_ddp",
+                      "distributed_replace_codes", "learnable_codebook", "gumbel_params", "ema_update", "use_affine",
+                      "affine_params", "transform_input", "use_cosine_sim", "weights_regularization"]
+    vq = list(inspect.signature(VectorQuantize.__init__).parameters)
+    assert vq[1:] == ["dim", "codebook_params", "codebook_dim", "heads", "separate_codebook_per_head",
+                      "layernorm_after_project_in", "channel_last", "commitment_weight",
+                      "commitment_use_cross_entropy_loss", "orthogonal_reg_weight", "orthogonal_reg_active_codes_only",
+                      "orthogonal_reg_max_codes", "codebook_diversity_loss_weight", "codebook_diversity_temperature",
+                      "sync_codebook", "in_place_codebook_optimizer", "sync_update_v"]
+    assert list(inspect.signature(VectorQuantize.forward).parameters)[1:] == \
+        ["x", "indices", "mask", "freeze_codebook", "return_loss_breakdown"]
+    assert list(inspect.signature(ResidualVQ.forward).parameters)[1:] == \
+        ["x", "mask", "indices", "return_all_codes", "freeze_codebook", "rand_quantize_dropout_fixed_seed"]
+    assert list(inspect.signature(Codebook.forward).parameters)[1:] == ["x", "mask", "freeze_codebook"]
+
+
+def test_buffers_and_state_dict_keys_match_reference():
+    from vqb200 import CodebookParams, ResidualVQ, VectorQuantize
+    vq = VectorQuantize(dim=256, codebook_params=CodebookParams(dim=256, codebook_size=512))
+    sd = vq.state_dict()
+    assert list(sd) == ["_codebook.cluster_size", "_codebook.embed_avg", "_codebook.embeddings"]
+    assert sd["_codebook.embeddings"].shape == (1, 512, 256) and sd["_codebook.embeddings"].dtype == torch.float32
+    assert sd["_codebook.cluster_size"].shape == (1, 512) and float(sd["_codebook.cluster_size"].abs().sum()) == 0.0
+    assert torch.equal(sd["_codebook.embed_avg"], sd["_codebook.embeddings"])
+    bound = (6.0 / (512 * 256)) ** 0.5            # kaiming-uniform on (1,K,d): fan_in = K*d
+    assert float(sd["_codebook.embeddings"].abs().max()) <= bound
+    rvq = ResidualVQ(dim=32, num_quantizers=3, codebook_params=CodebookParams(dim=32, codebook_size=64))
+    assert rvq.codebooks.shape == (3, 64, 32)
+    assert "layers.2._codebook.embed_avg" in rvq.state_dict()
+    shared = ResidualVQ(dim=32, num_quantizers=3, shared_codebook=True,
+                        codebook_params=CodebookParams(dim=32, codebook_size=64))
+    assert shared.layers[0]._codebook is shared.layers[2]._codebook
+    mh = VectorQuantize(dim=32, heads=4, codebook_dim=8, separate_codebook_per_head=True,
+                        codebook_params=CodebookParams(dim=8, codebook_size=16))
+    assert mh._codebook.embeddings.shape == (4, 16, 8)
+    cos = VectorQuantize(dim=16, codebook_params=CodebookParams(dim=16, codebook_size=8, use_cosine_sim=True,
+                                                                weights_regularization="l2norm"))
+    assert torch.allclose(cos._codebook.embeddings.norm(dim=-1), torch.ones(1, 8), atol=1e-6)
+
+
+def test_no_cpu_fallback_and_unsupported_options_fail_loudly():
+    from vqb200 import Codebook, CodebookParams, GumbelParams, VectorQuantize
+    vq = VectorQuantize(dim=8, codebook_params=CodebookParams(dim=8, codebook_size=4))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        vq(torch.randn(1, 3, 8))
+    with pytest.raises(NotImplementedError):
+        Codebook(8, 4, learnable_codebook=True)
+    with pytest.raises(NotImplementedError):
+        Codebook(8, 4, use_affine=True)
+    with pytest.raises(NotImplementedError):
+        Codebook(8, 4, gumbel_params=GumbelParams(stochastic=True))
+    with pytest.raises(ValueError):
+        Codebook(8, 4, transform_input="tanh")
+    for kw in (dict(codebook_diversity_loss_weight=0.1), dict(orthogonal_reg_weight=1.0),
+               dict(commitment_use_cross_entropy_loss=True), dict(sync_update_v=0.5)):
+        with pytest.raises(NotImplementedError):
+            VectorQuantize(dim=8, codebook_params=CodebookParams(dim=8, codebook_size=4), **kw)
+
+
+def test_product_code_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "vector-quantization-by-ml_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in text, \
+                    f"{f} mentions the oracle; the product path must not depend on it"

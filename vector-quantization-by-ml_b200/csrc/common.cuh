@@ -1,0 +1,155 @@
+// common.cuh -- shared helpers for libvqb200 (sm_100a only).
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/vqb.h"
+
+namespace vqb {
+
+// ---- error plumbing (thread-local message, C return codes) --------------------------------
+void set_error(const char* fmt, ...);
+
+#define VQB_CUDA_TRY(expr)                                                              \
+  do {                                                                                  \
+    cudaError_t _e = (expr);                                                            \
+    if (_e != cudaSuccess) {                                                            \
+      vqb::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+      return VQB_ERR_CUDA;                                                              \
+    }                                                                                   \
+  } while (0)
+
+#define VQB_REQUIRE(cond, code, ...)                                                    \
+  do {                                                                                  \
+    if (!(cond)) {                                                                      \
+      vqb::set_error(__VA_ARGS__);                                                      \
+      return (code);                                                                    \
+    }                                                                                   \
+  } while (0)
+
+#define VQB_LAUNCH_CHECK() VQB_CUDA_TRY(cudaGetLastError())
+
+// ---- geometry shared by prepare / search / resolve ----------------------------------------
+constexpr int kBlockM = 128;   // latent rows per CTA tile (TMEM lanes)
+constexpr int kBlockN = 256;   // codes per N tile (UMMA N)
+constexpr int kBlockK = 64;    // bf16 elements per k-block = one 128B swizzle atom
+constexpr int kNumCand = 24;   // candidates kept per row: 2 column-halves x 4 classes x top-3
+constexpr float kPadBias = 3.0e38f;
+
+__host__ __device__ inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
+__host__ __device__ inline int64_t round_up64(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
+inline int k_pad(int K) { return round_up(K, kBlockN); }
+inline int d_pad(int d) { return round_up(d, kBlockK); }
+inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+// Derived codebook cache layout (one caller-owned buffer).
+struct CacheLayout {
+  int Kp, dp;
+  size_t off_cb;     // bf16 [H][Kp][dp]  = bf16(-c), zero padded
+  size_t off_cn2h;   // f32  [H][Kp]      = |c|^2 / 2   (0 for the dot metric)
+  size_t off_cn;     // f32  [H][Kp]      = |c|
+  size_t off_dcn;    // f32  [H][Kp]      = |c - bf16(c)|
+  size_t total;
+};
+inline CacheLayout cache_layout(int64_t H, int K, int d) {
+  CacheLayout L;
+  L.Kp = k_pad(K);
+  L.dp = d_pad(d);
+  size_t o = 0;
+  L.off_cb = o;   o += align_up((size_t)H * L.Kp * L.dp * 2);
+  L.off_cn2h = o; o += align_up((size_t)H * L.Kp * 4);
+  L.off_cn = o;   o += align_up((size_t)H * L.Kp * 4);
+  L.off_dcn = o;  o += align_up((size_t)H * L.Kp * 4);
+  L.total = o;
+  return L;
+}
+
+// Search workspace layout (one caller-owned buffer).
+struct SearchLayout {
+  int dp;
+  size_t off_scal;    // u32[64]: [0]=max|x_b| bits, [1]=max|x-x_b| bits, [2]=#rescanned, [3]=#reranked, [4]=tc used, [5]=smem misalign flag
+  size_t off_cnt;     // u32[H]: flagged rows per codebook (directly after scal: zeroed together)
+  size_t off_xb;      // bf16 [H][N][dp]
+  size_t off_cand;    // {f32 key, i32 code} [H][N][kNumCand]
+  size_t off_flag;    // i32 [H*N] flagged row list
+  size_t off_bias;    // f32 [H][Kp]  lower-bound bias  |c|^2/2 - E_k  (needs the row stats, so per search)
+  size_t off_err;     // f32 [H][Kp]  E_k: bound on |exact score - bf16 tensor-core score| for code k
+  size_t total;
+};
+inline SearchLayout search_layout(int64_t H, int64_t N, int K, int d) {
+  SearchLayout L;
+  L.dp = d_pad(d);
+  size_t o = 0;
+  L.off_scal = o; o += 256;
+  L.off_cnt = o;  o += align_up((size_t)H * 4);
+  L.off_xb = o;   o += align_up((size_t)H * N * L.dp * 2);
+  L.off_cand = o; o += align_up((size_t)H * N * kNumCand * 8);
+  L.off_flag = o; o += align_up((size_t)H * N * 4);
+  L.off_bias = o; o += align_up((size_t)H * k_pad(K) * 4);
+  L.off_err = o;  o += align_up((size_t)H * k_pad(K) * 4);
+  L.total = o;
+  return L;
+}
+
+// ---- device helpers -----------------------------------------------------------------------
+template <typename T> __device__ __forceinline__ float to_f32(T v);
+template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <> __device__ __forceinline__ float to_f32<__half>(__half v) { return __half2float(v); }
+
+// load 4 consecutive elements (16B-aligned for f32, 8B for 16-bit types) as float4
+template <typename T> __device__ __forceinline__ float4 load4(const T* p);
+template <> __device__ __forceinline__ float4 load4<float>(const float* p) {
+  return __ldg(reinterpret_cast<const float4*>(p));
+}
+template <> __device__ __forceinline__ float4 load4<__nv_bfloat16>(const __nv_bfloat16* p) {
+  uint2 r = __ldg(reinterpret_cast<const uint2*>(p));
+  float4 o;
+  o.x = __uint_as_float(r.x << 16);
+  o.y = __uint_as_float(r.x & 0xffff0000u);
+  o.z = __uint_as_float(r.y << 16);
+  o.w = __uint_as_float(r.y & 0xffff0000u);
+  return o;
+}
+template <> __device__ __forceinline__ float4 load4<__half>(const __half* p) {
+  uint2 r = __ldg(reinterpret_cast<const uint2*>(p));
+  __half2 a = *reinterpret_cast<__half2*>(&r.x), b = *reinterpret_cast<__half2*>(&r.y);
+  float2 fa = __half22float2(a), fb = __half22float2(b);
+  return make_float4(fa.x, fa.y, fb.x, fb.y);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// dispatch a generic lambda on the latent dtype
+#define VQB_DISPATCH_DTYPE(dtype, T, ...)                                                    \
+  switch (dtype) {                                                                           \
+    case VQB_F32:  { using T = float;          __VA_ARGS__; break; }                          \
+    case VQB_BF16: { using T = __nv_bfloat16;  __VA_ARGS__; break; }                          \
+    case VQB_F16:  { using T = __half;         __VA_ARGS__; break; }                          \
+    default: vqb::set_error("unknown latent dtype %d", (int)(dtype)); return VQB_ERR_INVALID; \
+  }
+
+inline int dtype_size(int dt) { return dt == VQB_F32 ? 4 : 2; }
+
+// ---- internal launchers (defined across the .cu files) --------------------------------------
+int launch_prepare_latents(const void* x, int x_dtype, int64_t rows, int d, int dp,
+                           __nv_bfloat16* xb, uint32_t* scal, cudaStream_t st);
+int launch_make_bias(const void* cache, const CacheLayout& CL, int64_t H, int K, int metric,
+                     const uint32_t* scal, float* bias, float* err, cudaStream_t st);
+int launch_search_tc(const __nv_bfloat16* xb, const __nv_bfloat16* cb, const float* bias,
+                     int64_t H, int64_t N, int K, int dp, void* cand, uint32_t* scal, cudaStream_t st);
+
+}  // namespace vqb

@@ -1,0 +1,487 @@
+// ema.cu -- EMA codebook statistics and refresh.
+//
+// Replaces (reference file:line under vector_quantization/):
+//   codebooks.py:405-408  masked one-hot column sums        -> per-code counts (exact integers)
+//   codebooks.py:413      einsum("h n d, h n c -> h c d")   -> per-code sums of assigned rows (a third 2NKd SGEMM)
+//   codebooks.py:411,417  ema_inplace (lerp_)               \
+//   codebooks.py:419-425  laplace smoothing, divide, l2norm  > vqb_ema_apply
+//   codebooks.py:241-243  dead-code replacement scatter      -> vqb_expire_scatter
+//
+// Reduction = sort-and-segment: a counting sort of row ids by code (histogram, scan, placement), then
+// warps walk fixed 64-row chunks of the sorted order, gather each row once (coalesced 4d-byte reads)
+// and accumulate per lane in registers, flushing at every code boundary.
+// Determinism: the per-row contributions are converted to 64-bit fixed point (scale 2^s chosen from a
+// bound on max|x| so that nothing can overflow) and added as INTEGERS -- integer addition is associative,
+// so the result is bitwise independent of placement order, chunking and atomics, and its error
+// (<= count * 2^-(s+1) absolute, s ~ 39 for unit-scale data) is far below one fp32 ulp of the sum.
+// HBM traffic: x once (4d or 2d bytes/row) + 2 x idx + row-id permutation + K(d+1) accumulators.
+#include "common.cuh"
+
+namespace vqb {
+
+constexpr int kChunkRows = 64;
+
+struct EmaLayout {
+  size_t off_counts;   // u32 [H][K]
+  size_t off_cursor;   // u32 [H][K]
+  size_t off_start;    // u32 [H][K+1]
+  size_t off_scale;    // i32 [4]   s, and fp bound
+  size_t off_acc;      // i64 [H][K][d]
+  size_t zero_bytes;   // counts + cursor + start + scale + acc are zeroed together
+  size_t off_sorted;   // i32 [H][N]
+  size_t off_total;    // f32 [H]   (ema_apply scratch)
+  size_t total;
+};
+inline EmaLayout ema_layout(int64_t H, int64_t N, int K, int d) {
+  EmaLayout L;
+  size_t o = 0;
+  L.off_counts = o; o += align_up((size_t)H * K * 4);
+  L.off_cursor = o; o += align_up((size_t)H * K * 4);
+  L.off_start = o;  o += align_up((size_t)H * (K + 1) * 4);
+  L.off_scale = o;  o += 256;
+  L.off_acc = o;    o += align_up((size_t)H * K * d * 8);
+  L.zero_bytes = o;
+  L.off_sorted = o; o += align_up((size_t)(H * N > 0 ? H * N : 1) * 4);
+  L.off_total = o;  o += align_up((size_t)H * 4);
+  L.total = o;
+  return L;
+}
+
+// --- bound on max|x_j| when the caller has none: one extra read of x ---------------------------------
+template <typename T>
+__global__ void absmax_kernel(const T* __restrict__ x, int64_t n, uint32_t* __restrict__ out) {
+  float m = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    m = fmaxf(m, fabsf(to_f32<T>(x[i])));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(out, __float_as_uint(m));
+}
+
+// s = 61 - ceil(log2(bound * rows)), clamped; scale[0] = s
+__global__ void ema_scale_kernel(const float* __restrict__ bound2, const uint32_t* __restrict__ own_bound,
+                                 int64_t rows, int* __restrict__ scale) {
+  float b = bound2 ? (bound2[0] + bound2[1]) : __uint_as_float(own_bound[0]);
+  if (!(b > 0.f) || !isfinite(b)) b = 1.f;
+  int e;
+  frexpf(b, &e);                              // b < 2^e
+  int lr = 0;
+  while (((int64_t)1 << lr) < rows + 1) ++lr; // rows < 2^lr
+  int s = 61 - (e + lr);
+  if (s > 100) s = 100;
+  if (s < -60) s = -60;
+  scale[0] = s;
+}
+
+__global__ void ema_hist_kernel(const int64_t* __restrict__ idx, const uint8_t* __restrict__ mask, int64_t N, int K,
+                                uint32_t* __restrict__ counts) {
+  const int h = blockIdx.y;
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  if (mask && !mask[n]) return;
+  const int64_t k = idx[(int64_t)h * N + n];
+  if (k >= 0 && k < K) atomicAdd(counts + (int64_t)h * K + k, 1u);
+}
+
+// exclusive scan of counts -> start (one block per codebook; K <= 2^24)
+__global__ void ema_scan_kernel(const uint32_t* __restrict__ counts, int K, uint32_t* __restrict__ start) {
+  const int h = blockIdx.x;
+  const uint32_t* c = counts + (int64_t)h * K;
+  uint32_t* s = start + (int64_t)h * (K + 1);
+  __shared__ uint32_t wsum[32];
+  __shared__ uint32_t carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int base = 0; base < K; base += 1024) {
+    const int k = base + threadIdx.x;
+    const uint32_t v = k < K ? c[k] : 0u;
+    uint32_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    if (lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+      uint32_t w = wsum[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, w, o);
+        if (lane >= o) w += t;
+      }
+      wsum[lane] = w;   // inclusive over warps
+    }
+    __syncthreads();
+    const uint32_t before = carry + (warp ? wsum[warp - 1] : 0u) + inc - v;
+    if (k < K) s[k] = before;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry = before + v;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) s[K] = carry;
+}
+
+__global__ void ema_place_kernel(const int64_t* __restrict__ idx, const uint8_t* __restrict__ mask, int64_t N, int K,
+                                 const uint32_t* __restrict__ start, uint32_t* __restrict__ cursor,
+                                 int* __restrict__ sorted) {
+  const int h = blockIdx.y;
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  if (mask && !mask[n]) return;
+  const int64_t k = idx[(int64_t)h * N + n];
+  if (k < 0 || k >= K) return;
+  const uint32_t pos = start[(int64_t)h * (K + 1) + k] + atomicAdd(cursor + (int64_t)h * K + k, 1u);
+  sorted[(int64_t)h * N + pos] = (int)n;
+}
+
+// one warp per 64 consecutive positions of the sorted order; lanes own columns {cb*128 + lane*4 .. +3}
+template <typename T>
+__global__ void __launch_bounds__(256)
+ema_segsum_kernel(const T* __restrict__ x, const int64_t* __restrict__ idx, const int* __restrict__ sorted,
+                  const uint32_t* __restrict__ start, int64_t N, int K, int d, const int* __restrict__ scale_p,
+                  unsigned long long* __restrict__ acc) {
+  const int h = blockIdx.y;
+  const int lane = threadIdx.x & 31;
+  const int64_t chunk = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t total = start[(int64_t)h * (K + 1) + K];     // rows that take part (mask applied)
+  const int64_t p0 = chunk * kChunkRows;
+  if (p0 >= total) return;
+  const int64_t p1 = p0 + kChunkRows < total ? p0 + kChunkRows : total;
+  const float scale = ldexpf(1.f, scale_p[0]);
+  const T* xh = x + (int64_t)h * N * d;
+  const int64_t* idxh = idx + (int64_t)h * N;
+  const int* srt = sorted + (int64_t)h * N;
+  unsigned long long* acch = acc + (int64_t)h * K * d;
+  const bool vec = (d & 3) == 0;
+
+  // row ids and codes of the chunk live in registers (2 per lane) and are broadcast with shuffles,
+  // so the only dependent memory access in the row loop is the row itself
+  const int n = (int)(p1 - p0);
+  const int r_lo = lane < n ? srt[p0 + lane] : 0;
+  const int r_hi = lane + 32 < n ? srt[p0 + 32 + lane] : 0;
+  const int k_lo = lane < n ? (int)idxh[r_lo] : -1;
+  const int k_hi = lane + 32 < n ? (int)idxh[r_hi] : -1;
+
+  for (int c0 = 0; c0 < d; c0 += 128) {        // column block of 128 (4 per lane)
+    const int j = c0 + lane * 4;
+    const bool on = j < d;
+    long long a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+    int cur = -1;
+    for (int i0 = 0; i0 < n; i0 += 4) {
+      float4 v[4];
+      int kk[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {            // 4 independent row loads in flight
+        const int i = i0 + u;
+        const int r = __shfl_sync(0xffffffffu, i < 32 ? r_lo : r_hi, i & 31);
+        kk[u] = __shfl_sync(0xffffffffu, i < 32 ? k_lo : k_hi, i & 31);
+        v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < n && on) {
+          const T* xr = xh + (int64_t)r * d + j;
+          if (vec) v[u] = load4<T>(xr);
+          else {
+            v[u].x = to_f32<T>(xr[0]);
+            v[u].y = j + 1 < d ? to_f32<T>(xr[1]) : 0.f;
+            v[u].z = j + 2 < d ? to_f32<T>(xr[2]) : 0.f;
+            v[u].w = j + 3 < d ? to_f32<T>(xr[3]) : 0.f;
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (i0 + u < n) {
+          if (kk[u] != cur) {                   // warp-uniform: code boundary -> flush
+            if (cur >= 0 && on) {
+              unsigned long long* o = acch + (int64_t)cur * d + j;
+              if (a0) atomicAdd(o + 0, (unsigned long long)a0);
+              if (j + 1 < d && a1) atomicAdd(o + 1, (unsigned long long)a1);
+              if (j + 2 < d && a2) atomicAdd(o + 2, (unsigned long long)a2);
+              if (j + 3 < d && a3) atomicAdd(o + 3, (unsigned long long)a3);
+            }
+            a0 = a1 = a2 = a3 = 0;
+            cur = kk[u];
+          }
+          a0 += __float2ll_rn(v[u].x * scale);
+          a1 += __float2ll_rn(v[u].y * scale);
+          a2 += __float2ll_rn(v[u].z * scale);
+          a3 += __float2ll_rn(v[u].w * scale);
+        }
+      }
+    }
+    if (cur >= 0 && on) {
+      unsigned long long* o = acch + (int64_t)cur * d + j;
+      if (a0) atomicAdd(o + 0, (unsigned long long)a0);
+      if (j + 1 < d && a1) atomicAdd(o + 1, (unsigned long long)a1);
+      if (j + 2 < d && a2) atomicAdd(o + 2, (unsigned long long)a2);
+      if (j + 3 < d && a3) atomicAdd(o + 3, (unsigned long long)a3);
+    }
+  }
+}
+
+// stats[h][k][:d] = fixed -> float, stats[h][k][d] = count
+__global__ void ema_finalize_kernel(const long long* __restrict__ acc, const uint32_t* __restrict__ counts,
+                                    const int* __restrict__ scale_p, int64_t HK, int d, float* __restrict__ stats) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t n = HK * (d + 1);
+  if (i >= n) return;
+  const int64_t k = i / (d + 1);
+  const int j = (int)(i - k * (d + 1));
+  if (j == d) stats[i] = (float)counts[k];
+  else stats[i] = (float)ldexp((double)acc[k * d + j], -scale_p[0]);
+}
+
+// --- apply ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float torch_lerp(float a, float b, float w) {
+  // ATen lerp: |w| < 0.5 ? a + w*(b-a) : b - (b-a)*(1-w), evaluated with one fma (both the CPU vector
+  // kernel and nvcc's contraction do that)
+  const float diff = b - a;
+  return fabsf(w) < 0.5f ? fmaf(w, diff, a) : fmaf(w - 1.f, diff, b);
+}
+
+// one block per codebook: cluster_size <- lerp(cluster_size, counts, w); total[h] = sum(cluster_size)
+__global__ void ema_apply_counts_kernel(const float* __restrict__ stats, float* __restrict__ cluster_size, float w,
+                                        int K, int d, float* __restrict__ total) {
+  const int h = blockIdx.x;
+  __shared__ double s[1024];
+  double t = 0.0;
+  for (int k = threadIdx.x; k < K; k += 1024) {
+    const int64_t i = (int64_t)h * K + k;
+    const float v = torch_lerp(cluster_size[i], stats[i * (d + 1) + d], w);
+    cluster_size[i] = v;
+    t += (double)v;
+  }
+  s[threadIdx.x] = t;
+  __syncthreads();
+  for (int o = 512; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) s[threadIdx.x] += s[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) total[h] = (float)s[0];
+}
+
+// one warp per code: embed_avg <- lerp; embeddings <- reg(embed_avg / smoothed)
+__global__ void __launch_bounds__(256)
+ema_apply_rows_kernel(const float* __restrict__ stats, const float* __restrict__ cluster_size,
+                      float* __restrict__ embed_avg, float* __restrict__ embeddings, float w, float eps, float keps,
+                      int l2, int64_t H, int K, int d, const float* __restrict__ total) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= H * K) return;
+  const int64_t h = row / K;
+  const float tot = total[h];
+  // laplace_smoothing(cs, K, eps) * cs.sum()   (utils/general.py:154-156, codebooks.py:419-421)
+  const float smoothed = __fmul_rn(__fdiv_rn(__fadd_rn(cluster_size[row], eps), __fadd_rn(tot, keps)), tot);
+  const float* st = stats + row * (int64_t)(d + 1);
+  float* ea = embed_avg + row * (int64_t)d;
+  float* em = embeddings + row * (int64_t)d;
+  float n2 = 0.f;
+  for (int j = lane; j < d; j += 32) {
+    const float a = torch_lerp(ea[j], st[j], w);
+    ea[j] = a;
+    const float e = __fdiv_rn(a, smoothed);
+    if (l2) n2 = fmaf(e, e, n2);
+    else em[j] = e;
+  }
+  if (l2) {
+    n2 = warp_sum(n2);
+    const float nrm = fmaxf(sqrtf(n2), 1e-12f);
+    for (int j = lane; j < d; j += 32) em[j] = __fdiv_rn(__fdiv_rn(ea[j], smoothed), nrm);
+  }
+}
+
+// --- expiry: the j-th dead code (ascending) takes sample row j -------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(1024)
+expire_scatter_kernel(const T* __restrict__ x, const int64_t* __restrict__ rows, int64_t m, float thr, float reset,
+                      int l2, float* __restrict__ cluster_size, float* __restrict__ embed_avg,
+                      float* __restrict__ embeddings, int64_t N, int K, int d) {
+  __shared__ int dead_k[1024];
+  __shared__ uint32_t wsum[32];
+  __shared__ uint32_t carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int base = 0; base < K; base += 1024) {
+    const int k = base + threadIdx.x;
+    const uint32_t dead = (k < K && cluster_size[k] < thr) ? 1u : 0u;
+    uint32_t inc = dead;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    if (lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+      uint32_t v = wsum[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += t;
+      }
+      wsum[lane] = v;
+    }
+    __syncthreads();
+    const uint32_t local = (warp ? wsum[warp - 1] : 0u) + inc - dead;   // dead codes before k in this chunk
+    const uint32_t ndead = wsum[31];
+    const uint32_t c0 = carry;
+    if (dead) dead_k[local] = k;
+    __syncthreads();
+    // warps copy the chunk's dead codes, one code per warp at a time
+    for (uint32_t i = warp; i < ndead; i += 32) {
+      const int kk = dead_k[i];
+      const int64_t j = (int64_t)c0 + i;
+      if (j < m) {
+        int64_t r = rows[j];
+        if (r < 0) r = 0;
+        if (r >= N) r = N - 1;
+        const T* xr = x + r * (int64_t)d;
+        float nrm = 1.f;
+        if (l2) {
+          float n2 = 0.f;
+          for (int c = lane; c < d; c += 32) { const float v = to_f32<T>(xr[c]); n2 = fmaf(v, v, n2); }
+          n2 = warp_sum(n2);
+          nrm = fmaxf(sqrtf(n2), 1e-12f);
+        }
+        for (int c = lane; c < d; c += 32) {
+          float v = to_f32<T>(xr[c]);
+          if (l2) v = __fdiv_rn(v, nrm);
+          embeddings[(int64_t)kk * d + c] = v;
+          embed_avg[(int64_t)kk * d + c] = __fmul_rn(v, reset);
+        }
+        if (lane == 0) cluster_size[kk] = reset;
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) carry = c0 + ndead;
+    __syncthreads();
+  }
+}
+
+// --- sharded-codebook keys --------------------------------------------------------------------------
+__global__ void minkey_pack_kernel(const float* __restrict__ score, const int64_t* __restrict__ idx, int64_t n,
+                                   long long* __restrict__ keys) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t u = __float_as_uint(score[i]);
+  u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);       // monotone: float order -> unsigned order
+  u ^= 0x80000000u;                                     // unsigned order -> signed int64 order of the packed key
+  keys[i] = (long long)(((unsigned long long)u << 32) | (unsigned long long)(uint32_t)idx[i]);
+}
+__global__ void minkey_unpack_kernel(const long long* __restrict__ keys, int64_t n, int64_t* __restrict__ idx,
+                                     float* __restrict__ score) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const unsigned long long kq = (unsigned long long)keys[i];
+  idx[i] = (int64_t)(uint32_t)(kq & 0xffffffffull);
+  if (score) {
+    uint32_t u = (uint32_t)(kq >> 32) ^ 0x80000000u;
+    u = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+    score[i] = __uint_as_float(u);
+  }
+}
+
+}  // namespace vqb
+
+using namespace vqb;
+
+extern "C" size_t vqb_ema_workspace_bytes(int64_t H, int64_t N, int K, int d) {
+  if (H <= 0 || N < 0 || K <= 0 || d <= 0) return 0;
+  return ema_layout(H, N, K, d).total;
+}
+
+extern "C" int vqb_ema_reduce(const void* x, int x_dtype, const int64_t* idx, const uint8_t* mask,
+                              const float* absmax_bound2, int64_t H, int64_t N, int K, int d, float* stats,
+                              void* ws, size_t ws_bytes, void* stream) {
+  VQB_REQUIRE(x && idx && stats && ws, VQB_ERR_INVALID, "vqb_ema_reduce: null pointer");
+  VQB_REQUIRE(H > 0 && N >= 0 && K > 0 && d > 0 && H < 65536, VQB_ERR_INVALID, "vqb_ema_reduce: bad shape");
+  VQB_REQUIRE(N < (1ll << 31), VQB_ERR_UNSUPPORTED, "N must be < 2^31");
+  EmaLayout L = ema_layout(H, N, K, d);
+  VQB_REQUIRE(ws_bytes >= L.total, VQB_ERR_WORKSPACE, "ema workspace too small: %zu < %zu", ws_bytes, L.total);
+  cudaStream_t st = (cudaStream_t)stream;
+  char* w = (char*)ws;
+  uint32_t* counts = (uint32_t*)(w + L.off_counts);
+  uint32_t* cursor = (uint32_t*)(w + L.off_cursor);
+  uint32_t* start = (uint32_t*)(w + L.off_start);
+  int* scale = (int*)(w + L.off_scale);
+  long long* acc = (long long*)(w + L.off_acc);
+  int* sorted = (int*)(w + L.off_sorted);
+  VQB_CUDA_TRY(cudaMemsetAsync(w, 0, L.zero_bytes, st));
+  if (N > 0) {
+    if (!absmax_bound2) {
+      VQB_DISPATCH_DTYPE(x_dtype, T,
+        absmax_kernel<T><<<1184, 256, 0, st>>>((const T*)x, H * N * (int64_t)d, (uint32_t*)(scale + 1)));
+      VQB_LAUNCH_CHECK();
+    }
+    ema_scale_kernel<<<1, 1, 0, st>>>(absmax_bound2, (const uint32_t*)(scale + 1), N, scale);
+    VQB_LAUNCH_CHECK();
+    dim3 g1((unsigned)((N + 255) / 256), (unsigned)H);
+    ema_hist_kernel<<<g1, 256, 0, st>>>(idx, mask, N, K, counts);
+    VQB_LAUNCH_CHECK();
+    ema_scan_kernel<<<(unsigned)H, 1024, 0, st>>>(counts, K, start);
+    VQB_LAUNCH_CHECK();
+    ema_place_kernel<<<g1, 256, 0, st>>>(idx, mask, N, K, start, cursor, sorted);
+    VQB_LAUNCH_CHECK();
+    const int64_t chunks = (N + kChunkRows - 1) / kChunkRows;
+    dim3 g2((unsigned)((chunks + 7) / 8), (unsigned)H);
+    VQB_DISPATCH_DTYPE(x_dtype, T,
+      ema_segsum_kernel<T><<<g2, 256, 0, st>>>((const T*)x, idx, sorted, start, N, K, d, scale,
+                                               (unsigned long long*)acc));
+    VQB_LAUNCH_CHECK();
+  }
+  const int64_t n = H * (int64_t)K * (d + 1);
+  ema_finalize_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(acc, counts, scale, H * (int64_t)K, d, stats);
+  VQB_LAUNCH_CHECK();
+  return VQB_OK;
+}
+
+extern "C" int vqb_ema_apply(const float* stats, float* cluster_size, float* embed_avg, float* embeddings,
+                             float weight, double eps, int l2norm, int64_t H, int K, int d, void* ws,
+                             size_t ws_bytes, void* stream) {
+  VQB_REQUIRE(stats && cluster_size && embed_avg && embeddings && ws, VQB_ERR_INVALID, "vqb_ema_apply: null pointer");
+  VQB_REQUIRE(H > 0 && K > 0 && d > 0, VQB_ERR_INVALID, "vqb_ema_apply: bad shape");
+  VQB_REQUIRE(ws_bytes >= (size_t)H * 4, VQB_ERR_WORKSPACE, "ema_apply workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  // the scratch for the totals is the tail of an EMA workspace if the caller passed one, else the head of ws
+  float* total = (float*)ws;
+  ema_apply_counts_kernel<<<(unsigned)H, 1024, 0, st>>>(stats, cluster_size, weight, K, d, total);
+  VQB_LAUNCH_CHECK();
+  const int64_t rows = H * (int64_t)K;
+  ema_apply_rows_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(
+      stats, cluster_size, embed_avg, embeddings, weight, (float)eps, (float)((double)K * eps), l2norm, H, K, d, total);
+  VQB_LAUNCH_CHECK();
+  return VQB_OK;
+}
+
+extern "C" int vqb_expire_scatter(const void* x, int x_dtype, const int64_t* sample_rows, int64_t m, float threshold,
+                                  float reset, int l2norm, float* cluster_size, float* embed_avg, float* embeddings,
+                                  int64_t N, int K, int d, void* stream) {
+  VQB_REQUIRE(x && cluster_size && embed_avg && embeddings, VQB_ERR_INVALID, "vqb_expire_scatter: null pointer");
+  VQB_REQUIRE(m >= 0 && N > 0 && K > 0 && d > 0, VQB_ERR_INVALID, "vqb_expire_scatter: bad shape");
+  if (m == 0) return VQB_OK;
+  VQB_REQUIRE(sample_rows != nullptr, VQB_ERR_INVALID, "vqb_expire_scatter: sample_rows is null");
+  VQB_DISPATCH_DTYPE(x_dtype, T,
+    expire_scatter_kernel<T><<<1, 1024, 0, (cudaStream_t)stream>>>((const T*)x, sample_rows, m, threshold, reset,
+                                                                  l2norm, cluster_size, embed_avg, embeddings, N, K, d));
+  VQB_LAUNCH_CHECK();
+  return VQB_OK;
+}
+
+extern "C" int vqb_minkey_pack(const float* score, const int64_t* idx, int64_t n, int64_t* keys, void* stream) {
+  VQB_REQUIRE(score && idx && keys && n >= 0, VQB_ERR_INVALID, "vqb_minkey_pack: bad argument");
+  if (n == 0) return VQB_OK;
+  minkey_pack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(score, idx, n, (long long*)keys);
+  VQB_LAUNCH_CHECK();
+  return VQB_OK;
+}
+
+extern "C" int vqb_minkey_unpack(const int64_t* keys, int64_t n, int64_t* idx, float* score, void* stream) {
+  VQB_REQUIRE(keys && idx && n >= 0, VQB_ERR_INVALID, "vqb_minkey_unpack: bad argument");
+  if (n == 0) return VQB_OK;
+  minkey_unpack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const long long*)keys, n, idx,
+                                                                                       score);
+  VQB_LAUNCH_CHECK();
+  return VQB_OK;
+}

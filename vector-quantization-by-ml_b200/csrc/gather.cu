@@ -1,0 +1,307 @@
+// gather.cu -- code gather + straight-through output + commitment loss in one pass over the latents,
+// its backward, and the fused ResidualVQ level step.
+//
+// Replaces (reference file:line under vector_quantization/):
+//   codebooks.py:393-397            one-hot einsum (2NKd flops) / batched_embedding gather
+//   vector_quantize_pytorch.py:273  quantize = x + (quantize - x).detach()
+//   vector_quantize_pytorch.py:347-364  F.mse_loss(commit_quantize, x) (masked variant included)
+//   residual_vq.py:232-233          residual -= quantized ; quantized_out += quantized
+// HBM-bound: per row read x (4d or 2d B) + idx (8 B), write q (4d B); codebook rows come from L2.
+// One warp per row, float4 lanes, rows strided over a persistent grid; loss partials are reduced
+// in a fixed order (warp shuffle -> per-block double -> single-block tree) so the loss is bitwise
+// reproducible run to run.
+#include "common.cuh"
+
+namespace vqb {
+
+constexpr int kGatherThreads = 256;
+
+struct GatherLayout {
+  size_t off_part;   // double[grid] partial sums of squared error
+  size_t off_cnt;    // int64[grid]  rows used
+  size_t total;
+};
+static int gather_grid(int64_t rows) {
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  int64_t need = (rows + (kGatherThreads / 32) - 1) / (kGatherThreads / 32);
+  int64_t cap = (int64_t)sms * 8;
+  return (int)(need < cap ? (need > 0 ? need : 1) : cap);
+}
+static GatherLayout gather_layout() {
+  GatherLayout L;
+  const size_t maxgrid = 148 * 8 * 4;   // generous upper bound on gather_grid()
+  L.off_part = 0;
+  L.off_cnt = align_up(maxgrid * 8);
+  L.total = L.off_cnt + align_up(maxgrid * 8);
+  return L;
+}
+
+// q = training ? fl(x + fl(c - x)) : c ; optional squared-error partials
+template <typename T, bool kLoss>
+__global__ void __launch_bounds__(kGatherThreads)
+gather_st_loss_kernel(const T* __restrict__ x, const float* __restrict__ cb, const int64_t* __restrict__ idx,
+                      const uint8_t* __restrict__ mask, int training, float* __restrict__ q, int64_t H, int64_t N,
+                      int K, int d, double* __restrict__ part, long long* __restrict__ cntp) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int wpb = kGatherThreads / 32;
+  const int64_t rows = H * N;
+  float sq = 0.f;        // per-lane partial; one row contributes d/32 terms per lane
+  double sqd = 0.0;      // folded into fp64 after every row
+  long long used = 0;
+  for (int64_t row = (int64_t)blockIdx.x * wpb + warp; row < rows; row += (int64_t)gridDim.x * wpb) {
+    const int64_t h = row / N;
+    const int64_t n = row - h * N;
+    const int64_t code = idx[row];
+    const bool in_loss = mask == nullptr || mask[n] != 0;
+    const T* xr = x + row * (int64_t)d;
+    const float* cr = cb + (h * K + code) * (int64_t)d;
+    float* qr = q + row * (int64_t)d;
+    sq = 0.f;
+    if ((d & 3) == 0) {
+      for (int j = lane * 4; j < d; j += 128) {
+        const float4 xv = load4<T>(xr + j);
+        const float4 cv = __ldg(reinterpret_cast<const float4*>(cr + j));
+        const float4 df = make_float4(__fsub_rn(cv.x, xv.x), __fsub_rn(cv.y, xv.y), __fsub_rn(cv.z, xv.z),
+                                      __fsub_rn(cv.w, xv.w));
+        float4 o;
+        if (training) o = make_float4(__fadd_rn(xv.x, df.x), __fadd_rn(xv.y, df.y), __fadd_rn(xv.z, df.z),
+                                      __fadd_rn(xv.w, df.w));
+        else o = cv;
+        __stcs(reinterpret_cast<float4*>(qr + j), o);
+        if (kLoss) { sq = fmaf(df.x, df.x, sq); sq = fmaf(df.y, df.y, sq); sq = fmaf(df.z, df.z, sq); sq = fmaf(df.w, df.w, sq); }
+      }
+    } else {
+      for (int j = lane; j < d; j += 32) {
+        const float xv = to_f32<T>(xr[j]);
+        const float cv = cr[j];
+        const float df = __fsub_rn(cv, xv);
+        qr[j] = training ? __fadd_rn(xv, df) : cv;
+        if (kLoss) sq = fmaf(df, df, sq);
+      }
+    }
+    if (kLoss && in_loss) { sqd += (double)sq; if (lane == 0) ++used; }
+  }
+  if (kLoss) {
+    sqd = warp_sum(sqd);
+    __shared__ double s_sq[kGatherThreads / 32];
+    __shared__ long long s_n[kGatherThreads / 32];
+    if (lane == 0) { s_sq[warp] = sqd; s_n[warp] = used; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = 0.0;
+      long long c = 0;
+      for (int i = 0; i < wpb; ++i) { t += s_sq[i]; c += s_n[i]; }
+      part[blockIdx.x] = t;
+      cntp[blockIdx.x] = c;
+    }
+  }
+}
+
+// fixed-order reduction of the per-block partials: loss_out[0] = sum / (rows_used * d), loss_out[1] = rows_used
+__global__ void loss_finalize_kernel(const double* __restrict__ part, const long long* __restrict__ cntp, int nblocks,
+                                     int d, float* __restrict__ loss_out) {
+  __shared__ double s[256];
+  __shared__ long long c[256];
+  double t = 0.0;
+  long long n = 0;
+  for (int i = threadIdx.x; i < nblocks; i += 256) { t += part[i]; n += cntp[i]; }
+  s[threadIdx.x] = t;
+  c[threadIdx.x] = n;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) { s[threadIdx.x] += s[threadIdx.x + o]; c[threadIdx.x] += c[threadIdx.x + o]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const double denom = (double)c[0] * (double)d;
+    loss_out[0] = denom > 0.0 ? (float)(s[0] / denom) : __int_as_float(0x7fc00000);   // torch: mean of empty = nan
+    loss_out[1] = (float)c[0];
+  }
+}
+
+// grad_x = grad_q + coef * grad_loss[0] * (x - c)   (rows with mask==0: grad_q only)
+template <typename T>
+__global__ void __launch_bounds__(kGatherThreads)
+st_commit_backward_kernel(const float* __restrict__ gq, const float* __restrict__ gl, const T* __restrict__ x,
+                          const float* __restrict__ cb, const int64_t* __restrict__ idx,
+                          const uint8_t* __restrict__ mask, float coef, float* __restrict__ gx, int64_t H, int64_t N,
+                          int K, int d) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int wpb = kGatherThreads / 32;
+  const int64_t rows = H * N;
+  const float s = coef * gl[0];
+  for (int64_t row = (int64_t)blockIdx.x * wpb + warp; row < rows; row += (int64_t)gridDim.x * wpb) {
+    const int64_t h = row / N, n = row - h * N;
+    const bool in_loss = mask == nullptr || mask[n] != 0;
+    const float sc = in_loss ? s : 0.f;
+    const T* xr = x + row * (int64_t)d;
+    const float* cr = cb + (h * K + idx[row]) * (int64_t)d;
+    const float* gr = gq + row * (int64_t)d;
+    float* o = gx + row * (int64_t)d;
+    for (int j = lane; j < d; j += 32) o[j] = fmaf(sc, to_f32<T>(xr[j]) - cr[j], gr[j]);
+  }
+}
+
+// One ResidualVQ level: gather + ST + loss + residual/out update + next level's bf16 operand & row stats.
+__global__ void __launch_bounds__(kGatherThreads)
+rvq_level_kernel(const float* res_in, float* res_out, const float* __restrict__ cb, const int64_t* __restrict__ idx,
+                 const uint8_t* __restrict__ mask, int training, int first, float* __restrict__ out,
+                 float* __restrict__ qout, int64_t N, int K, int d, int dp, double* __restrict__ part,
+                 long long* __restrict__ cntp, __nv_bfloat16* __restrict__ next_xb, uint32_t* __restrict__ next_scal) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int wpb = kGatherThreads / 32;
+  double sqd = 0.0;
+  long long used = 0;
+  float max_n2 = 0.f, max_r2 = 0.f;
+  for (int64_t row = (int64_t)blockIdx.x * wpb + warp; row < N; row += (int64_t)gridDim.x * wpb) {
+    const bool live = mask == nullptr || mask[row] != 0;
+    const float* rr = res_in + row * (int64_t)d;
+    float* ro = res_out + row * (int64_t)d;
+    const float* cr = cb + idx[row] * (int64_t)d;
+    float* orow = out + row * (int64_t)d;
+    float sq = 0.f, n2 = 0.f, r2 = 0.f;
+    for (int j = lane; j < dp; j += 32) {
+      float rnew = 0.f;
+      if (j < d) {
+        const float r = rr[j], c = cr[j];
+        const float df = __fsub_rn(c, r);
+        // masked-out positions return the layer input itself (vector_quantize_pytorch.py:415-418)
+        const float qv = live ? (training ? __fadd_rn(r, df) : c) : r;
+        orow[j] = first ? __fadd_rn(0.0f, qv) : __fadd_rn(orow[j], qv);
+        rnew = __fsub_rn(r, qv);
+        ro[j] = rnew;
+        if (qout) qout[row * (int64_t)d + j] = qv;
+        sq = fmaf(df, df, sq);
+      }
+      if (next_xb) {
+        const __nv_bfloat16 b = __float2bfloat16(rnew);
+        const float back = __bfloat162float(b);
+        next_xb[row * (int64_t)dp + j] = b;
+        n2 = fmaf(back, back, n2);
+        r2 = fmaf(rnew - back, rnew - back, r2);
+      }
+    }
+    sq = warp_sum(sq);
+    if (live) { sqd += (double)sq; ++used; }
+    if (next_xb) {
+      n2 = warp_sum(n2);
+      r2 = warp_sum(r2);
+      max_n2 = fmaxf(max_n2, n2);
+      max_r2 = fmaxf(max_r2, r2);
+    }
+  }
+  __shared__ double s_sq[kGatherThreads / 32];
+  __shared__ long long s_n[kGatherThreads / 32];
+  __shared__ float s_a[kGatherThreads / 32], s_b[kGatherThreads / 32];
+  if (lane == 0) { s_sq[warp] = sqd; s_n[warp] = used; s_a[warp] = max_n2; s_b[warp] = max_r2; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    long long c = 0;
+    float a = 0.f, b = 0.f;
+    for (int i = 0; i < wpb; ++i) { t += s_sq[i]; c += s_n[i]; a = fmaxf(a, s_a[i]); b = fmaxf(b, s_b[i]); }
+    part[blockIdx.x] = t;
+    cntp[blockIdx.x] = c;
+    if (next_scal) {
+      const float infl = 1.f + (float)dp * 2.4e-7f;
+      atomicMax(next_scal + 0, __float_as_uint(sqrtf(a * infl) * 1.00001f));
+      atomicMax(next_scal + 1, __float_as_uint(sqrtf(b * infl) * 1.00001f));
+    }
+  }
+}
+
+}  // namespace vqb
+
+using namespace vqb;
+
+extern "C" size_t vqb_gather_workspace_bytes(int64_t H, int64_t N, int d) {
+  (void)H; (void)N; (void)d;
+  return gather_layout().total;
+}
+
+extern "C" int vqb_gather_st_loss(const void* x, int x_dtype, const float* codebook, const int64_t* idx,
+                                  const uint8_t* mask, int training, int want_loss, float* q_out, float* loss_out,
+                                  int64_t H, int64_t N, int K, int d, void* ws, size_t ws_bytes, void* stream) {
+  VQB_REQUIRE(x && codebook && idx && q_out, VQB_ERR_INVALID, "vqb_gather_st_loss: null pointer");
+  VQB_REQUIRE(H > 0 && N >= 0 && K > 0 && d > 0, VQB_ERR_INVALID, "vqb_gather_st_loss: bad shape");
+  GatherLayout L = gather_layout();
+  if (want_loss) {
+    VQB_REQUIRE(loss_out && ws && ws_bytes >= L.total, VQB_ERR_WORKSPACE, "gather workspace too small: %zu < %zu",
+                ws_bytes, L.total);
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = gather_grid(H * N);
+  double* part = want_loss ? (double*)((char*)ws + L.off_part) : nullptr;
+  long long* cntp = want_loss ? (long long*)((char*)ws + L.off_cnt) : nullptr;
+  if (H * N > 0) {
+    if (want_loss) {
+      VQB_DISPATCH_DTYPE(x_dtype, T,
+        gather_st_loss_kernel<T, true><<<grid, kGatherThreads, 0, st>>>((const T*)x, codebook, idx, mask, training,
+                                                                        q_out, H, N, K, d, part, cntp));
+    } else {
+      VQB_DISPATCH_DTYPE(x_dtype, T,
+        gather_st_loss_kernel<T, false><<<grid, kGatherThreads, 0, st>>>((const T*)x, codebook, idx, mask, training,
+                                                                         q_out, H, N, K, d, part, cntp));
+    }
+    VQB_LAUNCH_CHECK();
+  }
+  if (want_loss) {
+    loss_finalize_kernel<<<1, 256, 0, st>>>(part, cntp, H * N > 0 ? grid : 0, d, loss_out);
+    VQB_LAUNCH_CHECK();
+  }
+  return VQB_OK;
+}
+
+extern "C" int vqb_st_commit_backward(const float* grad_q, const float* grad_loss, const void* x, int x_dtype,
+                                      const float* codebook, const int64_t* idx, const uint8_t* mask, float coef,
+                                      float* grad_x, int64_t H, int64_t N, int K, int d, void* stream) {
+  VQB_REQUIRE(grad_q && grad_loss && x && codebook && idx && grad_x, VQB_ERR_INVALID,
+              "vqb_st_commit_backward: null pointer");
+  if (H * N == 0) return VQB_OK;
+  const int grid = gather_grid(H * N);
+  VQB_DISPATCH_DTYPE(x_dtype, T,
+    st_commit_backward_kernel<T><<<grid, kGatherThreads, 0, (cudaStream_t)stream>>>(
+        grad_q, grad_loss, (const T*)x, codebook, idx, mask, coef, grad_x, H, N, K, d));
+  VQB_LAUNCH_CHECK();
+  return VQB_OK;
+}
+
+extern "C" int vqb_rvq_level(const float* residual_in, float* residual_out, const float* codebook,
+                             const int64_t* idx, const uint8_t* mask, int training, int first_level,
+                             float* quantized_out, float* q_out, float* loss_out, int64_t N, int K, int d,
+                             void* gather_ws, size_t gather_ws_bytes, void* next_ws, size_t next_ws_bytes,
+                             void* stream) {
+  VQB_REQUIRE(residual_in && residual_out && codebook && idx && quantized_out && loss_out && gather_ws,
+              VQB_ERR_INVALID, "vqb_rvq_level: null pointer");
+  GatherLayout L = gather_layout();
+  VQB_REQUIRE(gather_ws_bytes >= L.total, VQB_ERR_WORKSPACE, "gather workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  __nv_bfloat16* nxb = nullptr;
+  uint32_t* nscal = nullptr;
+  const int dp = d_pad(d);
+  if (next_ws) {
+    SearchLayout SL = search_layout(1, N, K, d);
+    VQB_REQUIRE(next_ws_bytes >= SL.total, VQB_ERR_WORKSPACE, "next-level search workspace too small");
+    nxb = (__nv_bfloat16*)((char*)next_ws + SL.off_xb);
+    nscal = (uint32_t*)((char*)next_ws + SL.off_scal);
+    VQB_CUDA_TRY(cudaMemsetAsync(nscal, 0, 8, st));
+  }
+  const int grid = gather_grid(N);
+  double* part = (double*)((char*)gather_ws + L.off_part);
+  long long* cntp = (long long*)((char*)gather_ws + L.off_cnt);
+  if (N > 0) {
+    rvq_level_kernel<<<grid, kGatherThreads, 0, st>>>(residual_in, residual_out, codebook, idx, mask, training, first_level,
+                                                      quantized_out, q_out, N, K, d, next_ws ? dp : d, part, cntp,
+                                                      nxb, nscal);
+    VQB_LAUNCH_CHECK();
+  }
+  loss_finalize_kernel<<<1, 256, 0, st>>>(part, cntp, N > 0 ? grid : 0, d, loss_out);
+  VQB_LAUNCH_CHECK();
+  return VQB_OK;
+}

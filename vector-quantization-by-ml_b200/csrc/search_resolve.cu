@@ -1,0 +1,339 @@
+// search_resolve.cu -- turns tensor-core candidates into the reference's fp32 argmin, exactly.
+//
+// Why the candidate set is complete (per row x, metric score e_k = |c_k|^2/2 - x.c_k, or -x.c_k):
+//   the tensor-core pass computes a_k = bias_k - x_b.c_bk with bf16 roundings x_b, c_bk, and
+//   |e_k - (a_k + E_k)| <= E_k  where  E_k >= |x_b|.|c_k - c_bk| + |x - x_b|.|c_k| + fp32 accumulation slack
+//   (Cauchy-Schwarz; |x_b|, |x - x_b| replaced by their maxima over the batch, prepare.cu).
+//   The kernel stores L_k = a_k (already lowered by E_k): L_k <= e_k <= L_k + 2 E_k.
+//   With j = argmin_k L_k the true argmin k* satisfies L_k* <= e_k* <= e_j <= L_j + 2 E_j, so
+//   every possible winner has L <= thr := L_j + 2 E_j (+ slack for the 5 id bits packed into L).
+//   The epilogue keeps, per 32-column group of every N tile, the two smallest L, and per class
+//   (8 per row) the three smallest of those.  Therefore a possible winner is missing only if
+//     (i)  the third entry of some class is <= thr (a fourth could exist)  -> full exact rescan, or
+//     (ii) two entries <= thr come from the same 32-column group (a third could hide there)
+//                                                                          -> rescan those 32 columns.
+//   Both are detected here; neither is assumed away.
+//
+// "Exact" score = the reference's recipe evaluated with fp64 accumulation:
+//   euclid: sqrtf(max(float(|x|^2 + |c|^2 - 2 x.c), 0))   dot: float(-x.c); lowest index wins ties.
+#include "common.cuh"
+
+namespace vqb {
+
+template <typename T>
+__device__ __forceinline__ double row_norm2(const T* __restrict__ xr, int d) {
+  double s = 0.0;
+  if ((d & 3) == 0) {
+    for (int j = 0; j < d; j += 4) {
+      float4 v = load4<T>(xr + j);
+      s = fma((double)v.x, (double)v.x, s); s = fma((double)v.y, (double)v.y, s);
+      s = fma((double)v.z, (double)v.z, s); s = fma((double)v.w, (double)v.w, s);
+    }
+  } else {
+    for (int j = 0; j < d; ++j) { double v = (double)to_f32<T>(xr[j]); s = fma(v, v, s); }
+  }
+  return s;
+}
+
+// exact score of (row, code); xn2 = |x|^2 in fp64 (ignored for the dot metric)
+template <typename T>
+__device__ __forceinline__ float exact_score(const T* __restrict__ xr, const float* __restrict__ cr, int d, int metric,
+                                             double xn2) {
+  double dot = 0.0, cn2 = 0.0;
+  if ((d & 3) == 0) {
+    for (int j = 0; j < d; j += 4) {
+      float4 a = load4<T>(xr + j);
+      float4 c = __ldg(reinterpret_cast<const float4*>(cr + j));
+      dot = fma((double)a.x, (double)c.x, dot); dot = fma((double)a.y, (double)c.y, dot);
+      dot = fma((double)a.z, (double)c.z, dot); dot = fma((double)a.w, (double)c.w, dot);
+      cn2 = fma((double)c.x, (double)c.x, cn2); cn2 = fma((double)c.y, (double)c.y, cn2);
+      cn2 = fma((double)c.z, (double)c.z, cn2); cn2 = fma((double)c.w, (double)c.w, cn2);
+    }
+  } else {
+    for (int j = 0; j < d; ++j) {
+      double a = (double)to_f32<T>(xr[j]), c = (double)cr[j];
+      dot = fma(a, c, dot);
+      cn2 = fma(c, c, cn2);
+    }
+  }
+  if (metric == VQB_DOT) return (float)(-dot);
+  float d2 = (float)(xn2 + cn2 - 2.0 * dot);
+  return sqrtf(fmaxf(d2, 0.f));
+}
+
+// one thread per row
+template <typename T>
+__global__ void __launch_bounds__(256)
+resolve_kernel(const T* __restrict__ x, const float* __restrict__ cb, const uint2* __restrict__ cand,
+               const float* __restrict__ err, int64_t H, int64_t N, int K, int Kp, int d, int metric,
+               int64_t idx_offset, int64_t* __restrict__ idx_out, float* __restrict__ score_out,
+               int* __restrict__ flag_list, uint32_t* __restrict__ flag_cnt, uint32_t* __restrict__ scal) {
+  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  bool reranked = false;
+  if (gid < H * N) {
+    const int64_t h = gid / N;
+    const int64_t row = gid - h * N;
+    float key[kNumCand];
+    int code[kNumCand];
+    const uint4* c4 = reinterpret_cast<const uint4*>(cand + gid * kNumCand);
+#pragma unroll
+    for (int i = 0; i < kNumCand / 2; ++i) {
+      uint4 v = __ldg(c4 + i);
+      key[2 * i] = __uint_as_float(v.x); code[2 * i] = (int)v.y;
+      key[2 * i + 1] = __uint_as_float(v.z); code[2 * i + 1] = (int)v.w;
+    }
+    float m1 = __int_as_float(0x7f800000);
+    int c1 = -1;
+#pragma unroll
+    for (int i = 0; i < kNumCand; ++i) {
+      const bool valid = code[i] >= 0 && code[i] < K;
+      if (!valid) key[i] = __int_as_float(0x7f800000);
+      if (valid && key[i] < m1) { m1 = key[i]; c1 = code[i]; }
+    }
+    const float E1 = c1 >= 0 ? err[h * Kp + c1] : 0.f;
+    // 2 E_j, plus the 5 packed id bits (<= 2^-18 relative per key) and the bias add rounding
+    const float thr = m1 + 2.f * E1 + (fabsf(m1) + E1) * 3.1e-5f;
+
+    int ncand = 0;
+    bool full_rescan = c1 < 0;
+    // rescan requests: (group, n-tile) pairs whose 32 columns must be evaluated exactly
+    int rs_g[8], rs_t[8], nrs = 0;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      const float k0 = key[3 * g], k1 = key[3 * g + 1], k2 = key[3 * g + 2];
+      if (k0 <= thr) ++ncand;
+      if (k1 <= thr) ++ncand;
+      if (k2 <= thr) { ++ncand; full_rescan = true; }           // (i)
+      if (k1 <= thr) {                                           // (ii)
+        const int t0 = code[3 * g] >> 8, t1 = code[3 * g + 1] >> 8;
+        if (t0 == t1) { rs_g[nrs] = g; rs_t[nrs] = t0; ++nrs; }
+      }
+    }
+    if (full_rescan) {
+      const uint32_t pos = atomicAdd(flag_cnt + h, 1u);
+      flag_list[h * N + pos] = (int)row;
+    } else if (ncand == 1 && score_out == nullptr) {
+      idx_out[gid] = (int64_t)c1 + idx_offset;
+    } else {
+      reranked = ncand > 1;
+      const T* xr = x + gid * (int64_t)d;
+      const float* cbh = cb + h * (int64_t)K * d;
+      const double xn2 = metric == VQB_EUCLID ? row_norm2<T>(xr, d) : 0.0;
+      float best = __int_as_float(0x7f800000);
+      int bi = 0x7fffffff;
+#pragma unroll 1
+      for (int i = 0; i < kNumCand; ++i) {
+        if (key[i] <= thr) {
+          const float s = exact_score<T>(xr, cbh + (int64_t)code[i] * d, d, metric, xn2);
+          if (s < best || (s == best && code[i] < bi) || bi == 0x7fffffff) { best = s; bi = code[i]; }
+        }
+      }
+#pragma unroll 1
+      for (int r = 0; r < nrs; ++r) {
+        const int half = rs_g[r] >> 2, cls = rs_g[r] & 3;
+        const int colb = rs_t[r] * kBlockN + half * 128 + cls;
+#pragma unroll 1
+        for (int i = 0; i < 32; ++i) {
+          const int k = colb + 4 * i;
+          if (k < K) {
+            const float s = exact_score<T>(xr, cbh + (int64_t)k * d, d, metric, xn2);
+            if (s < best || (s == best && k < bi)) { best = s; bi = k; }
+          }
+        }
+      }
+      idx_out[gid] = (int64_t)bi + idx_offset;
+      if (score_out) score_out[gid] = best;
+    }
+  }
+  const int nre = __syncthreads_count(reranked ? 1 : 0);
+  if (threadIdx.x == 0 && nre) atomicAdd(scal + 3, (uint32_t)nre);
+}
+
+// ------------------------------------------------------------------------------------------
+// exact scan of every code for a list of rows (flagged rows, or all rows with FORCE_EXACT / d_pad > 512).
+// Tile: 32 rows x 64 codes per 256-thread block, fp64 accumulators, same fma order as exact_score.
+// ------------------------------------------------------------------------------------------
+constexpr int kER = 32, kEC = 64, kEK = 32;
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+exact_scan_kernel(const T* __restrict__ x, const float* __restrict__ cb, const int* __restrict__ flag_list,
+                  const uint32_t* __restrict__ flag_cnt, int64_t N, int K, int d, int metric, int64_t idx_offset,
+                  int64_t* __restrict__ idx_out, float* __restrict__ score_out, uint32_t* __restrict__ scal) {
+  __shared__ float xs[kER][kEK + 1];
+  __shared__ float cs[kEC][kEK + 1];
+  __shared__ int rows_s[kER];
+  const int h = blockIdx.y;
+  const int64_t count = flag_list ? (int64_t)flag_cnt[h] : N;
+  const int* list = flag_list ? flag_list + (int64_t)h * N : nullptr;
+  const T* xh = x + (int64_t)h * N * d;
+  const float* cbh = cb + (int64_t)h * K * d;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;   // codes tx+16j (j<4), rows ty+16i (i<2)
+  if (flag_list && blockIdx.x == 0 && threadIdx.x == 0 && count) atomicAdd(scal + 2, (uint32_t)count);
+
+  for (int64_t t0 = (int64_t)blockIdx.x * kER; t0 < count; t0 += (int64_t)gridDim.x * kER) {
+    __syncthreads();
+    if (threadIdx.x < kER) {
+      const int64_t r = t0 + threadIdx.x;
+      rows_s[threadIdx.x] = r < count ? (list ? list[r] : (int)r) : -1;
+    }
+    __syncthreads();
+    float best[2] = {__int_as_float(0x7f800000), __int_as_float(0x7f800000)};
+    int bidx[2] = {0x7fffffff, 0x7fffffff};
+    // |x|^2 of this thread's two rows, fp64, same order as row_norm2 (recomputed per code tile: cheap)
+    for (int k0 = 0; k0 < K; k0 += kEC) {
+      double acc[2][4], xn[2] = {0.0, 0.0}, cn[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+      for (int d0 = 0; d0 < d; d0 += kEK) {
+        __syncthreads();
+        for (int e = threadIdx.x; e < kER * kEK; e += 256) {
+          const int r = e / kEK, c = e % kEK;
+          const int rr = rows_s[r];
+          xs[r][c] = (rr >= 0 && d0 + c < d) ? to_f32<T>(xh[(int64_t)rr * d + d0 + c]) : 0.f;
+        }
+        for (int e = threadIdx.x; e < kEC * kEK; e += 256) {
+          const int r = e / kEK, c = e % kEK;
+          cs[r][c] = (k0 + r < K && d0 + c < d) ? cbh[(int64_t)(k0 + r) * d + d0 + c] : 0.f;
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (int c = 0; c < kEK; ++c) {
+          double xv[2], cv[4];
+#pragma unroll
+          for (int i = 0; i < 2; ++i) { xv[i] = (double)xs[ty + 16 * i][c]; xn[i] = fma(xv[i], xv[i], xn[i]); }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) { cv[j] = (double)cs[tx + 16 * j][c]; cn[j] = fma(cv[j], cv[j], cn[j]); }
+#pragma unroll
+          for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] = fma(xv[i], cv[j], acc[i][j]);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int k = k0 + tx + 16 * j;
+          if (k < K) {
+            float s;
+            if (metric == VQB_DOT) s = (float)(-acc[i][j]);
+            else s = sqrtf(fmaxf((float)(xn[i] + cn[j] - 2.0 * acc[i][j]), 0.f));
+            if (s < best[i] || (s == best[i] && k < bidx[i])) { best[i] = s; bidx[i] = k; }
+          }
+        }
+    }
+    // reduce over the 16 threads (tx) that share a row: lanes of one half-warp
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, best[i], o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bidx[i], o);
+        if (ob < best[i] || (ob == best[i] && oi < bidx[i])) { best[i] = ob; bidx[i] = oi; }
+      }
+      const int rr = rows_s[ty + 16 * i];
+      if (tx == 0 && rr >= 0) {
+        idx_out[(int64_t)h * N + rr] = (int64_t)bidx[i] + idx_offset;
+        if (score_out) score_out[(int64_t)h * N + rr] = best[i];
+      }
+    }
+  }
+}
+
+static int g_num_sms = 0;
+static int num_sms() {
+  if (!g_num_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+
+}  // namespace vqb
+
+using namespace vqb;
+
+extern "C" size_t vqb_search_workspace_bytes(int64_t H, int64_t N, int K, int d) {
+  if (H <= 0 || N < 0 || K <= 0 || d <= 0) return 0;
+  return search_layout(H, N, K, d).total;
+}
+
+extern "C" int vqb_search(const void* x, int x_dtype, const float* codebook, const void* cache, int metric,
+                          int64_t H, int64_t N, int K, int d, int64_t idx_offset, int64_t* idx_out,
+                          float* score_out, int flags, void* ws, size_t ws_bytes, void* stream) {
+  VQB_REQUIRE(x && codebook && idx_out && ws, VQB_ERR_INVALID, "vqb_search: null pointer");
+  VQB_REQUIRE(H > 0 && N >= 0 && K > 0 && d > 0, VQB_ERR_INVALID, "vqb_search: bad shape H=%lld N=%lld K=%d d=%d",
+              (long long)H, (long long)N, K, d);
+  VQB_REQUIRE(metric == VQB_EUCLID || metric == VQB_DOT, VQB_ERR_INVALID, "unknown metric %d", metric);
+  VQB_REQUIRE(H * N < (1ll << 31), VQB_ERR_UNSUPPORTED, "H*N must be < 2^31");
+  VQB_REQUIRE(H < 65536, VQB_ERR_UNSUPPORTED, "too many codebooks");
+  SearchLayout SL = search_layout(H, N, K, d);
+  VQB_REQUIRE(ws_bytes >= SL.total, VQB_ERR_WORKSPACE, "search workspace too small: %zu < %zu", ws_bytes, SL.total);
+  if (N == 0) return VQB_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  char* w = (char*)ws;
+  uint32_t* scal = (uint32_t*)(w + SL.off_scal);
+  uint32_t* cnt = (uint32_t*)(w + SL.off_cnt);
+  int* flag_list = (int*)(w + SL.off_flag);
+  const bool prepared = (flags & VQB_SEARCH_LATENTS_PREPARED) != 0;
+  const bool tc = !(flags & VQB_SEARCH_FORCE_EXACT) && SL.dp <= 512 && cache != nullptr;
+  // scal[0..1] hold the row statistics: keep them when the caller prepared the latents
+  const size_t zoff = prepared ? 8 : 0;
+  VQB_CUDA_TRY(cudaMemsetAsync((char*)scal + zoff, 0, (SL.off_cnt - SL.off_scal) + (size_t)H * 4 - zoff, st));
+
+  const int grid_scan = (int)((N + kER - 1) / kER < 4 * (int64_t)num_sms() ? (N + kER - 1) / kER : 4 * num_sms());
+  if (!tc) {
+    VQB_DISPATCH_DTYPE(x_dtype, T,
+      exact_scan_kernel<T><<<dim3((unsigned)grid_scan, (unsigned)H), 256, 0, st>>>(
+          (const T*)x, codebook, nullptr, nullptr, N, K, d, metric, idx_offset, idx_out, score_out, scal));
+    VQB_LAUNCH_CHECK();
+    return VQB_OK;
+  }
+
+  CacheLayout CL = cache_layout(H, K, d);
+  const char* cbase = (const char*)cache;
+  __nv_bfloat16* xb = (__nv_bfloat16*)(w + SL.off_xb);
+  float* bias = (float*)(w + SL.off_bias);
+  float* err = (float*)(w + SL.off_err);
+  int rc;
+  if (!prepared) {
+    rc = launch_prepare_latents(x, x_dtype, H * N, d, SL.dp, xb, scal, st);
+    if (rc) return rc;
+  }
+  rc = launch_make_bias(cache, CL, H, K, metric, scal, bias, err, st);
+  if (rc) return rc;
+  rc = launch_search_tc(xb, (const __nv_bfloat16*)(cbase + CL.off_cb), bias, H, N, K, SL.dp, w + SL.off_cand, scal, st);
+  if (rc) return rc;
+  const int64_t total = H * N;
+  VQB_DISPATCH_DTYPE(x_dtype, T,
+    resolve_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
+        (const T*)x, codebook, (const uint2*)(w + SL.off_cand), err, H, N, K, CL.Kp, d, metric, idx_offset,
+        idx_out, score_out, flag_list, cnt, scal));
+  VQB_LAUNCH_CHECK();
+  // flagged rows (count is device-side): fixed small grid, blocks exit at once when there is nothing to do
+  const int grid_flag = grid_scan < 2 * num_sms() ? grid_scan : 2 * num_sms();
+  VQB_DISPATCH_DTYPE(x_dtype, T,
+    exact_scan_kernel<T><<<dim3((unsigned)grid_flag, (unsigned)H), 256, 0, st>>>(
+        (const T*)x, codebook, flag_list, cnt, N, K, d, metric, idx_offset, idx_out, score_out, scal));
+  VQB_LAUNCH_CHECK();
+  uint32_t one = 1;
+  (void)one;
+  return VQB_OK;
+}
+
+extern "C" int vqb_search_stats(const void* ws, int64_t* host_out3, void* stream) {
+  VQB_REQUIRE(ws && host_out3, VQB_ERR_INVALID, "vqb_search_stats: null pointer");
+  uint32_t hbuf[8];
+  VQB_CUDA_TRY(cudaMemcpyAsync(hbuf, ws, sizeof(hbuf), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  VQB_CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+  host_out3[0] = hbuf[3];
+  host_out3[1] = hbuf[2];
+  host_out3[2] = hbuf[4];
+  if (hbuf[5]) { set_error("search_tc: dynamic shared memory base was not 1024B aligned"); return VQB_ERR_CUDA; }
+  return VQB_OK;
+}

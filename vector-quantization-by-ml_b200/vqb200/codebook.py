@@ -1,0 +1,265 @@
+"""``Codebook``: drop-in for reference vector_quantization/codebooks.py:81-435 on the EMA path.
+
+Same constructor, same persistent buffers (``embeddings`` (H,K,d), ``embed_avg`` (H,K,d),
+``cluster_size`` (H,K), fp32) and the same ``forward(x, mask, freeze_codebook)`` contract;
+the numeric work (search, gather, EMA statistics, refresh, expiry scatter) runs in
+libvqb200.so.  Options that are off the named hot path (learnable codebook, affine
+re-parametrisation, stochastic gumbel sampling) raise NotImplementedError -- there is
+no silent fallback.
+"""
+from __future__ import annotations
+
+from dataclasses import asdict, is_dataclass
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+from torch import nn
+
+from . import ops
+from .params import GumbelParams, KmeansParameters
+
+
+def _uniform_init(*shape):
+    # reference utils/general.py:101-104
+    t = torch.empty(shape)
+    nn.init.kaiming_uniform_(t)
+    return t
+
+
+def _l2norm_cpu_or_cuda(t: torch.Tensor) -> torch.Tensor:
+    # construction-time only (tiny, may be on CPU); the forward path uses the CUDA kernel
+    return torch.nn.functional.normalize(t, p=2, dim=-1)
+
+
+class Codebook(nn.Module):
+    def __init__(self, dim, codebook_size, num_codebooks=1, initialization_by_kmeans: bool = False,
+                 kmeans_params: KmeansParameters = None, decay: float = 0.8, eps_for_smoothing: float = 1e-5,
+                 threshold_ema_dead_code: int = 2, reset_cluster_size: int = None, use_ddp: bool = False,
+                 distributed_replace_codes: bool = True, learnable_codebook: bool = False,
+                 gumbel_params: GumbelParams = GumbelParams(), ema_update: bool = True, use_affine: bool = False,
+                 affine_params=None, transform_input: str = "identity", use_cosine_sim: bool = False,
+                 weights_regularization: str = "identity"):
+        super().__init__()
+        for name, val in (("transform_input", transform_input), ("weights_regularization", weights_regularization)):
+            if val not in ("identity", "l2norm"):
+                # the reference does `raise f"..."` here (a TypeError); keep the intent, not the bug
+                raise ValueError(f"The option {val} for {name} is not implemented")
+        if learnable_codebook:
+            raise NotImplementedError("vqb200: learnable_codebook is outside the accelerated EMA path")
+        if use_affine:
+            raise NotImplementedError("vqb200: use_affine is outside the accelerated EMA path")
+        gp = asdict(gumbel_params) if is_dataclass(gumbel_params) else dict(gumbel_params)
+        if gp.get("stochastic") or gp.get("straight_through") or gp.get("reinmax"):
+            raise NotImplementedError("vqb200: stochastic / straight-through gumbel sampling is outside the "
+                                      "accelerated path (deterministic argmax only)")
+
+        self.input_l2norm = transform_input == "l2norm"
+        self.weights_l2norm = weights_regularization == "l2norm"
+        self.use_cosine_sim = use_cosine_sim
+        self.decay = decay
+        self.ema_update = ema_update
+        self.codebook_size = codebook_size
+        self.num_codebooks = num_codebooks
+        self.dim = dim
+        self.kmeans_params = asdict(kmeans_params) if is_dataclass(kmeans_params) else kmeans_params
+        self.eps_for_smoothing = eps_for_smoothing
+        self.threshold_ema_dead_code = threshold_ema_dead_code
+        self.reset_cluster_size = reset_cluster_size if reset_cluster_size is not None else threshold_ema_dead_code
+        assert not (use_ddp and num_codebooks > 1 and initialization_by_kmeans), \
+            "kmeans init is not compatible with multiple codebooks in distributed environment for now"
+        self.use_ddp = use_ddp
+        # the reference indexes kmeans_params["sync"] unconditionally and crashes when it is None
+        # (codebooks.py:164-166); treat a missing KmeansParameters as its defaults instead
+        self._kmeans_sync = bool((self.kmeans_params or {"sync": True})["sync"])
+        self.distributed_replace_codes = distributed_replace_codes
+        self.learnable_codebook = False
+        self.use_affine = False
+
+        init = torch.zeros(num_codebooks, codebook_size, dim) if initialization_by_kmeans else \
+            _uniform_init(num_codebooks, codebook_size, dim)
+        if self.weights_l2norm:
+            init = _l2norm_cpu_or_cuda(init)
+        self.is_initialized = not initialization_by_kmeans
+        self.register_buffer("cluster_size", torch.zeros(num_codebooks, codebook_size))
+        self.register_buffer("embed_avg", init.clone())
+        self.register_buffer("embeddings", init)
+
+        # derived, non-persistent: bf16 copy + norms for the tensor-core search
+        self._cache: Optional[torch.Tensor] = None
+        self._cache_key = None
+        self._dirty = True
+        self.last_search_ws: Optional[torch.Tensor] = None
+
+    # ------------------------------------------------------------------ transforms
+    def transform_input(self, x: torch.Tensor) -> torch.Tensor:
+        """reference: identity | l2norm (utils/losses.py:19), applied by VectorQuantize before the codebook."""
+        if not self.input_l2norm:
+            return x
+        return ops.l2norm_rows(x.contiguous())
+
+    # ------------------------------------------------------------------ cache
+    def _codebook_cache(self) -> torch.Tensor:
+        e = self.embeddings
+        key = (e.data_ptr(), e._version, tuple(e.shape), self.use_cosine_sim)
+        if self._dirty or self._cache is None or key != self._cache_key:
+            self._cache = ops.prepare_codebook(e, self.use_cosine_sim, self._cache)
+            self._cache_key = key
+            self._dirty = False
+        return self._cache
+
+    def invalidate_cache(self) -> None:
+        self._dirty = True
+
+    # ------------------------------------------------------------------ helpers
+    def _all_reduce(self, t: torch.Tensor) -> None:
+        if self.use_ddp and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            dist.all_reduce(t)
+
+    @staticmethod
+    def _draw_rows(num_rows: int, m: int, device) -> torch.Tensor:
+        # reference utils/general.py:62-66 -- same calls on the same (global) generator
+        if num_rows >= m:
+            return torch.randperm(num_rows, device=device)[:m]
+        return torch.randint(0, num_rows, (m,), device=device)
+
+    def _flatten(self, x: torch.Tensor):
+        """(H, ..., d) -> contiguous (H, N, d) in a kernel dtype; also returns the leading shape."""
+        if x.dtype not in (torch.float32, torch.bfloat16, torch.float16):
+            x = x.float()
+        H, d = x.shape[0], x.shape[-1]
+        lead = tuple(x.shape[1:-1])
+        return x.reshape(H, -1, d).contiguous(), lead
+
+    def _expand_mask(self, mask: Optional[torch.Tensor], n_rows: int) -> Optional[torch.Tensor]:
+        # reference codebooks.py:361-367: repeat(mask, "b n -> c (b h n)")
+        if mask is None:
+            return None
+        b, n = mask.shape
+        rep = n_rows // (b * n)
+        m = mask[:, None, :].expand(b, rep, n).reshape(-1)
+        return m.to(torch.uint8).contiguous()
+
+    # ------------------------------------------------------------------ kmeans init (reference utils/kmeans.py)
+    @torch.no_grad()
+    def _kmeans_init(self, flat: torch.Tensor, mask_u8: Optional[torch.Tensor]) -> None:
+        H, N, d = flat.shape
+        K = self.codebook_size
+        data = flat.float()
+        if mask_u8 is not None:
+            keep = mask_u8.bool()
+            data = data[:, keep].contiguous()
+            N = data.shape[1]
+        iters = int((self.kmeans_params or {"iter": 10})["iter"])
+        sync = self.use_ddp and self._kmeans_sync
+        cents = torch.stack([data[h][self._draw_rows(N, K, data.device)] for h in range(H)], 0).contiguous()
+        counts = torch.zeros(H, K, device=data.device)
+        for _ in range(iters):
+            cache = ops.prepare_codebook(cents, self.use_cosine_sim)
+            idx, _, ws = ops.search(data, cents, cache, self.use_cosine_sim)
+            stats = ops.ema_reduce(data, idx, None, K, bound_ws=ws)
+            counts = stats[..., d].clone()
+            if sync:
+                self._all_reduce(counts)
+            empty = counts == 0
+            means = stats[..., :d] / counts.masked_fill(empty, 1.0)[..., None]
+            if sync:
+                means = means.contiguous()
+                self._all_reduce(means)
+            if self.use_cosine_sim:
+                means = ops.l2norm_rows(means.contiguous())
+            cents = torch.where(empty[..., None], cents, means).contiguous()
+        self.embeddings.data.copy_(cents)
+        self.embed_avg.data.copy_(cents * counts[..., None])
+        self.cluster_size.data.copy_(counts)
+        self._dirty = True
+
+    # ------------------------------------------------------------------ expiry (reference codebooks.py:230-255)
+    @torch.no_grad()
+    def expire_codes_(self, flat: torch.Tensor) -> None:
+        if self.threshold_ema_dead_code == 0:
+            return
+        dead = self.cluster_size < self.threshold_ema_dead_code
+        if not torch.any(dead):                       # host sync, as in the reference (:251)
+            return
+        H, N, d = flat.shape
+        counts = dead.sum(dim=-1).tolist()            # the reference syncs per codebook (:234)
+        for h in range(H):
+            m = int(counts[h])
+            rows = self._draw_rows(N, m, flat.device)
+            ops.expire_scatter(flat[h], rows, float(self.threshold_ema_dead_code), float(self.reset_cluster_size),
+                               self.weights_l2norm, self.cluster_size.data[h], self.embed_avg.data[h],
+                               self.embeddings.data[h])
+        self._dirty = True
+
+    # ------------------------------------------------------------------ core
+    def _run(self, x: torch.Tensor, mask: Optional[torch.Tensor], freeze_codebook: bool, fuse_st: bool,
+             want_commit: bool):
+        """Shared by forward() and VectorQuantize.  x: (H, ..., d).  Returns (quantize (H,...,d), idx (H,...),
+        commit scalar | None)."""
+        if not x.is_cuda:
+            raise RuntimeError(f"vqb200.Codebook: input must be on a CUDA device (got {x.device}); "
+                               "there is no CPU implementation")
+        flat, lead = self._flatten(x)
+        H, N, d = flat.shape
+        if H != self.num_codebooks or d != self.embeddings.shape[-1]:
+            raise ValueError(f"vqb200.Codebook: input {tuple(x.shape)} does not match codebook "
+                             f"{tuple(self.embeddings.shape)}")
+        mask_u8 = self._expand_mask(mask, N)
+
+        if not self.is_initialized:
+            self._kmeans_init(flat, mask_u8)
+            self.is_initialized = True
+
+        emb = self.embeddings.detach()
+        idx, _, ws = ops.search(flat, emb, self._codebook_cache(), self.use_cosine_sim)
+        self.last_search_ws = ws
+
+        training = self.training
+        commit = None
+        if fuse_st and training:
+            quant, commit = ops.quantize_training(flat, emb, idx, mask_u8, want_commit)
+        else:
+            with torch.no_grad():
+                quant, _ = ops.gather_st_loss(flat, emb, idx, None, False, False)
+
+        if training and self.ema_update and not freeze_codebook:
+            with torch.no_grad():
+                stats = ops.ema_reduce(flat, idx, mask_u8, self.codebook_size, bound_ws=ws)
+                self._all_reduce(stats)                       # one packed (H,K,d+1) allreduce (reference: two)
+                ops.ema_apply(stats, self.cluster_size.data, self.embed_avg.data, self.embeddings.data,
+                              1 - self.decay, self.eps_for_smoothing, self.weights_l2norm)
+                self._dirty = True
+                self.expire_codes_(flat)
+
+        return quant.reshape(H, *lead, d), idx.reshape(H, *lead), commit
+
+    @torch.amp.autocast(device_type="cuda", enabled=False)
+    def forward(self, x, mask=None, freeze_codebook=False):
+        """reference codebooks.py:350-435.  Returns (quantize, embed_ind, similarities) with
+        similarities=None: the N x K matrix is never materialised on this path."""
+        needs_codebook_dim = x.ndim < 4
+        if needs_codebook_dim:
+            x = x[None]
+        quant, ind, _ = self._run(x, mask, freeze_codebook, fuse_st=False, want_commit=False)
+        if needs_codebook_dim:
+            quant, ind = quant[0], ind[0]
+        return quant, ind, None
+
+
+class EuclideanCodebook(Codebook):
+    """Upstream name for ``Codebook(use_cosine_sim=False)`` (reference Changelog.md:11-12)."""
+
+    def __init__(self, dim, codebook_size, **kw):
+        kw.setdefault("use_cosine_sim", False)
+        super().__init__(dim, codebook_size, **kw)
+
+
+class CosineSimCodebook(Codebook):
+    """Upstream name for the cosine codebook: dot similarity on l2-normalised inputs and codes."""
+
+    def __init__(self, dim, codebook_size, **kw):
+        kw.setdefault("use_cosine_sim", True)
+        kw.setdefault("transform_input", "l2norm")
+        kw.setdefault("weights_regularization", "l2norm")
+        super().__init__(dim, codebook_size, **kw)

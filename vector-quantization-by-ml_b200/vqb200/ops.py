@@ -1,0 +1,244 @@
+"""Tensor-level wrappers over the C ABI (include/vqb.h).  PyTorch is plumbing here: it owns
+device memory and the stream; every numeric step of the hot path runs in libvqb200.so.
+
+Shapes: latents (H,N,d) contiguous, codebook (H,K,d) fp32 contiguous, indices (H,N) int64.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from . import _lib as L
+
+# ---------------------------------------------------------------------------------------------
+# workspaces: caller-owned scratch, one growing buffer per (kind, device, stream)
+# ---------------------------------------------------------------------------------------------
+_WS: Dict[Tuple[str, int, int], torch.Tensor] = {}
+
+
+def workspace(kind: str, nbytes: int, device: torch.device) -> torch.Tensor:
+    key = (kind, device.index if device.index is not None else torch.cuda.current_device(),
+           L.stream_ptr(device))
+    buf = _WS.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+        _WS[key] = buf
+    return buf
+
+
+def release_workspaces() -> None:
+    _WS.clear()
+
+
+def _metric(use_cosine_sim: bool) -> int:
+    return L.VQB_DOT if use_cosine_sim else L.VQB_EUCLID
+
+
+def _mask_u8(mask: Optional[torch.Tensor], n: int) -> Optional[torch.Tensor]:
+    if mask is None:
+        return None
+    m = mask.reshape(-1).to(torch.uint8).contiguous()
+    if m.numel() != n:
+        raise ValueError(f"vqb200: mask has {m.numel()} rows, expected {n}")
+    return m
+
+
+# ---------------------------------------------------------------------------------------------
+# codebook cache + search
+# ---------------------------------------------------------------------------------------------
+def prepare_codebook(embeddings: torch.Tensor, use_cosine_sim: bool,
+                     out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """bf16 copy + norms + rounding bounds of `embeddings` for the tensor-core search."""
+    L.require_cuda(embeddings, "embeddings")
+    assert embeddings.dtype == torch.float32 and embeddings.ndim == 3
+    H, K, d = embeddings.shape
+    nbytes = L.lib().vqb_codebook_cache_bytes(H, K, d)
+    if out is None or out.numel() < nbytes or out.device != embeddings.device:
+        out = torch.empty(nbytes, dtype=torch.uint8, device=embeddings.device)
+    L.check(L.lib().vqb_prepare_codebook(L.ptr(embeddings), H, K, d, _metric(use_cosine_sim), L.ptr(out),
+                                         out.numel(), L.stream_ptr(embeddings.device)), "vqb_prepare_codebook")
+    return out
+
+
+def search(x: torch.Tensor, embeddings: torch.Tensor, cache: Optional[torch.Tensor], use_cosine_sim: bool, *,
+           idx_offset: int = 0, want_score: bool = False, latents_prepared: bool = False,
+           force_exact: bool = False) -> Tuple[torch.Tensor, Optional[torch.Tensor], torch.Tensor]:
+    """Nearest code of every row.  Returns (idx (H,N) int64, score (H,N) fp32 | None, search workspace)."""
+    L.require_cuda(x, "x")
+    L.require_cuda(embeddings, "embeddings")
+    H, N, d = x.shape
+    Hc, K, dc = embeddings.shape
+    if (Hc, dc) != (H, d):
+        raise ValueError(f"vqb200: latents {tuple(x.shape)} do not match codebook {tuple(embeddings.shape)}")
+    dev = x.device
+    idx = torch.empty((H, N), dtype=torch.int64, device=dev)
+    score = torch.empty((H, N), dtype=torch.float32, device=dev) if want_score else None
+    ws = workspace("search", L.lib().vqb_search_workspace_bytes(H, N, K, d), dev)
+    flags = (L.SEARCH_LATENTS_PREPARED if latents_prepared else 0) | (L.SEARCH_FORCE_EXACT if force_exact else 0)
+    L.check(L.lib().vqb_search(L.ptr(x), L.dtype_code(x), L.ptr(embeddings), L.ptr(cache), _metric(use_cosine_sim),
+                               H, N, K, d, int(idx_offset), L.ptr(idx), L.ptr(score), flags, L.ptr(ws), ws.numel(),
+                               L.stream_ptr(dev)), "vqb_search")
+    return idx, score, ws
+
+
+def search_stats(ws: torch.Tensor) -> Dict[str, int]:
+    import ctypes as C
+    out = (C.c_int64 * 3)()
+    L.check(L.lib().vqb_search_stats(L.ptr(ws), C.cast(out, C.c_void_p), L.stream_ptr(ws.device)), "vqb_search_stats")
+    return {"reranked_rows": int(out[0]), "rescanned_rows": int(out[1]), "tensor_core_pass": int(out[2])}
+
+
+def l2norm_rows(x: torch.Tensor) -> torch.Tensor:
+    L.require_cuda(x, "x")
+    d = x.shape[-1]
+    out = torch.empty(x.shape, dtype=torch.float32, device=x.device)
+    rows = x.numel() // d if d else 0
+    L.check(L.lib().vqb_l2norm_rows(L.ptr(x), L.dtype_code(x), L.ptr(out), rows, d, L.stream_ptr(x.device)),
+            "vqb_l2norm_rows")
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# gather + straight-through + commitment loss (autograd-aware)
+# ---------------------------------------------------------------------------------------------
+def gather_st_loss(x: torch.Tensor, embeddings: torch.Tensor, idx: torch.Tensor, mask_u8: Optional[torch.Tensor],
+                   training: bool, want_loss: bool) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    """q (H,N,d) fp32 and loss_buf = [mean((c-x)^2), rows_used] (device) or None."""
+    L.require_cuda(x, "x")
+    H, N, d = x.shape
+    K = embeddings.shape[1]
+    dev = x.device
+    q = torch.empty((H, N, d), dtype=torch.float32, device=dev)
+    loss = torch.empty(2, dtype=torch.float32, device=dev) if want_loss else None
+    ws = workspace("gather", L.lib().vqb_gather_workspace_bytes(H, N, d), dev)
+    L.check(L.lib().vqb_gather_st_loss(L.ptr(x), L.dtype_code(x), L.ptr(embeddings), L.ptr(idx), L.ptr(mask_u8),
+                                       int(training), int(want_loss), L.ptr(q), L.ptr(loss), H, N, K, d,
+                                       L.ptr(ws), ws.numel(), L.stream_ptr(dev)), "vqb_gather_st_loss")
+    return q, loss
+
+
+class _QuantizeST(torch.autograd.Function):
+    """Training-mode quantize: returns (x + (c - x).detach(), mse(c.detach(), x)).
+
+    Backward (reference autograd through vector_quantize_pytorch.py:273,362):
+      grad_x = grad_q + grad_commit * 2 (x - c) / (rows_used * d);  the codebook gets no gradient.
+    """
+
+    @staticmethod
+    def forward(ctx, x, embeddings, idx, mask_u8, want_loss):
+        q, loss = gather_st_loss(x, embeddings, idx, mask_u8, True, want_loss)
+        ctx.save_for_backward(x, embeddings, idx, mask_u8 if mask_u8 is not None else torch.empty(0), loss
+                              if loss is not None else torch.empty(0))
+        ctx.has_mask = mask_u8 is not None
+        ctx.want_loss = want_loss
+        commit = loss[0] if want_loss else torch.zeros((), device=x.device)
+        return q, commit
+
+    @staticmethod
+    def backward(ctx, grad_q, grad_commit):
+        x, embeddings, idx, mask_u8, loss = ctx.saved_tensors
+        H, N, d = x.shape
+        K = embeddings.shape[1]
+        if grad_q is None:
+            grad_q = torch.zeros((H, N, d), dtype=torch.float32, device=x.device)
+        grad_q = grad_q.contiguous().float()
+        if not ctx.want_loss or grad_commit is None:
+            return grad_q.to(x.dtype), None, None, None, None
+        # device scalar: grad_commit * 2 / (rows_used * d)   (no host sync)
+        g = (grad_commit.float() * (2.0 / d) / loss[1]).reshape(1).contiguous()
+        gx = torch.empty((H, N, d), dtype=torch.float32, device=x.device)
+        L.check(L.lib().vqb_st_commit_backward(L.ptr(grad_q), L.ptr(g), L.ptr(x), L.dtype_code(x), L.ptr(embeddings),
+                                               L.ptr(idx), L.ptr(mask_u8) if ctx.has_mask else 0, 1.0, L.ptr(gx),
+                                               H, N, K, d, L.stream_ptr(x.device)), "vqb_st_commit_backward")
+        return gx.to(x.dtype), None, None, None, None
+
+
+def quantize_training(x, embeddings, idx, mask_u8, want_loss):
+    return _QuantizeST.apply(x, embeddings, idx, mask_u8, want_loss)
+
+
+# ---------------------------------------------------------------------------------------------
+# EMA statistics / refresh / expiry
+# ---------------------------------------------------------------------------------------------
+def ema_reduce(x: torch.Tensor, idx: torch.Tensor, mask_u8: Optional[torch.Tensor], K: int,
+               bound_ws: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """stats (H,K,d+1): per-code sums of assigned rows and counts.  Bitwise reproducible."""
+    L.require_cuda(x, "x")
+    H, N, d = x.shape
+    dev = x.device
+    stats = torch.empty((H, K, d + 1), dtype=torch.float32, device=dev)
+    ws = workspace("ema", L.lib().vqb_ema_workspace_bytes(H, N, K, d), dev)
+    L.check(L.lib().vqb_ema_reduce(L.ptr(x), L.dtype_code(x), L.ptr(idx), L.ptr(mask_u8), L.ptr(bound_ws), H, N, K, d,
+                                   L.ptr(stats), L.ptr(ws), ws.numel(), L.stream_ptr(dev)), "vqb_ema_reduce")
+    return stats
+
+
+def ema_apply(stats: torch.Tensor, cluster_size: torch.Tensor, embed_avg: torch.Tensor, embeddings: torch.Tensor,
+              weight: float, eps: float, weights_l2norm: bool) -> None:
+    H, K, d1 = stats.shape
+    d = d1 - 1
+    for t, n in ((stats, "stats"), (cluster_size, "cluster_size"), (embed_avg, "embed_avg"), (embeddings, "embeddings")):
+        L.require_cuda(t, n)
+    dev = stats.device
+    ws = workspace("ema", max(256, 4 * H), dev)
+    L.check(L.lib().vqb_ema_apply(L.ptr(stats), L.ptr(cluster_size), L.ptr(embed_avg), L.ptr(embeddings),
+                                  float(weight), float(eps), int(weights_l2norm), H, K, d, L.ptr(ws), ws.numel(),
+                                  L.stream_ptr(dev)), "vqb_ema_apply")
+
+
+def expire_scatter(x_rows: torch.Tensor, sample_rows: torch.Tensor, threshold: float, reset: float,
+                   weights_l2norm: bool, cluster_size: torch.Tensor, embed_avg: torch.Tensor,
+                   embeddings: torch.Tensor) -> None:
+    """One codebook: x_rows (N,d); cluster_size (K,), embed_avg/embeddings (K,d) views of codebook h."""
+    L.require_cuda(x_rows, "x")
+    N, d = x_rows.shape
+    K = cluster_size.shape[0]
+    for t, n in ((cluster_size, "cluster_size"), (embed_avg, "embed_avg"), (embeddings, "embeddings")):
+        L.require_cuda(t, n)
+    sample_rows = sample_rows.to(device=x_rows.device, dtype=torch.int64).contiguous()
+    L.check(L.lib().vqb_expire_scatter(L.ptr(x_rows), L.dtype_code(x_rows), L.ptr(sample_rows), sample_rows.numel(),
+                                       float(threshold), float(reset), int(weights_l2norm), L.ptr(cluster_size),
+                                       L.ptr(embed_avg), L.ptr(embeddings), N, K, d, L.stream_ptr(x_rows.device)),
+            "vqb_expire_scatter")
+
+
+# ---------------------------------------------------------------------------------------------
+# ResidualVQ level step and sharded-codebook keys
+# ---------------------------------------------------------------------------------------------
+def rvq_level(residual: torch.Tensor, residual_next: torch.Tensor, embeddings: torch.Tensor, idx: torch.Tensor,
+              mask_u8: Optional[torch.Tensor], training: bool, first_level: bool, quantized_out: torch.Tensor,
+              prepare_next: bool, q_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Reads `residual` (N,d fp32), writes `residual_next` and updates `quantized_out` in place;
+    returns loss_buf [mean sq err, rows used]."""
+    L.require_cuda(residual, "residual")
+    L.require_cuda(residual_next, "residual_next")
+    assert residual.dtype == torch.float32 and residual.ndim == 2 and residual_next.shape == residual.shape
+    N, d = residual.shape
+    K = embeddings.shape[-2]
+    dev = residual.device
+    loss = torch.empty(2, dtype=torch.float32, device=dev)
+    gws = workspace("gather", L.lib().vqb_gather_workspace_bytes(1, N, d), dev)
+    nws = workspace("search", L.lib().vqb_search_workspace_bytes(1, N, K, d), dev) if prepare_next else None
+    L.check(L.lib().vqb_rvq_level(L.ptr(residual), L.ptr(residual_next), L.ptr(embeddings), L.ptr(idx), L.ptr(mask_u8), int(training),
+                                  int(first_level), L.ptr(quantized_out), L.ptr(q_out), L.ptr(loss), N, K, d,
+                                  L.ptr(gws), gws.numel(), L.ptr(nws), nws.numel() if nws is not None else 0,
+                                  L.stream_ptr(dev)), "vqb_rvq_level")
+    return loss
+
+
+def minkey_pack(score: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+    L.require_cuda(score, "score")
+    keys = torch.empty(score.numel(), dtype=torch.int64, device=score.device)
+    L.check(L.lib().vqb_minkey_pack(L.ptr(score), L.ptr(idx), score.numel(), L.ptr(keys), L.stream_ptr(score.device)),
+            "vqb_minkey_pack")
+    return keys
+
+
+def minkey_unpack(keys: torch.Tensor, want_score: bool = False):
+    L.require_cuda(keys, "keys")
+    idx = torch.empty(keys.numel(), dtype=torch.int64, device=keys.device)
+    score = torch.empty(keys.numel(), dtype=torch.float32, device=keys.device) if want_score else None
+    L.check(L.lib().vqb_minkey_unpack(L.ptr(keys), keys.numel(), L.ptr(idx), L.ptr(score), L.stream_ptr(keys.device)),
+            "vqb_minkey_unpack")
+    return idx, score

@@ -1,0 +1,211 @@
+"""``ResidualVQ`` / ``GroupedResidualVQ``: drop-ins for reference vector_quantization/residual_vq.py.
+
+The per-level loop (reference :212-243) has two implementations with identical results:
+  * generic: each level is a ``VectorQuantize`` call and the residual arithmetic is autograd-visible;
+  * fused (no autograd needed): one kernel per level does gather + straight-through + commitment loss
+    + ``residual -= q`` + ``quantized_out += q`` and emits the next level's bf16 search operand, so the
+    residual is read once per level (``vqb_rvq_level``).
+"""
+from __future__ import annotations
+
+import random
+from functools import partial
+from math import ceil
+
+import torch
+import torch.distributed as dist
+import torch.nn.functional as F
+from torch import nn
+
+from . import ops
+from .vq import VectorQuantize
+
+
+def _round_up_multiple(num, mult):
+    return ceil(num / mult) * mult
+
+
+class ResidualVQ(nn.Module):
+    def __init__(self, *, dim, num_quantizers, codebook_dim=None, shared_codebook=False, heads=1,
+                 quantize_dropout=False, quantize_dropout_cutoff_index=0, quantize_dropout_multiple_of=1, **kwargs):
+        super().__init__()
+        assert heads == 1, "residual vq is not compatible with multi-headed codes"
+        codebook_dim = codebook_dim if codebook_dim is not None else dim
+        requires_projection = codebook_dim * heads != dim
+        self.project_in = nn.Linear(dim, codebook_dim) if requires_projection else nn.Identity()
+        self.project_out = nn.Linear(codebook_dim, dim) if requires_projection else nn.Identity()
+        self.has_projections = requires_projection
+        self.num_quantizers = num_quantizers
+        self.layers = nn.ModuleList([VectorQuantize(dim=codebook_dim, codebook_dim=codebook_dim, **kwargs)
+                                     for _ in range(num_quantizers)])
+        assert all(not vq.has_projections for vq in self.layers)
+        self.quantize_dropout = quantize_dropout and num_quantizers > 1
+        assert quantize_dropout_cutoff_index >= 0
+        self.quantize_dropout_cutoff_index = quantize_dropout_cutoff_index
+        self.quantize_dropout_multiple_of = quantize_dropout_multiple_of
+        self.use_fused_levels = True
+        if shared_codebook:
+            first = self.layers[0]._codebook
+            for vq in self.layers[1:]:
+                vq._codebook = first
+
+    @property
+    def codebooks(self):
+        return torch.stack([layer._codebook.embeddings[0] for layer in self.layers], dim=0)
+
+    def get_codes_from_indices(self, indices):
+        q_dim = indices.shape[-1]
+        lead = tuple(indices.shape[:-1])
+        flat = indices.reshape(indices.shape[0], -1, q_dim)
+        if q_dim < self.num_quantizers:
+            assert self.quantize_dropout > 0.0, "quantize dropout must be greater than 0 if you wish to " \
+                                                "reconstruct from a signal with less fine quantizations"
+            flat = F.pad(flat, (0, self.num_quantizers - q_dim), value=-1)
+        dropped = flat == -1
+        flat = flat.masked_fill(dropped, 0)
+        books = self.codebooks
+        codes = torch.stack([books[i][flat[..., i]] for i in range(self.num_quantizers)], dim=0)   # q b n d
+        codes = codes.masked_fill(dropped.permute(2, 0, 1)[..., None], 0.0)
+        return codes.reshape(self.num_quantizers, *lead, codes.shape[-1])
+
+    def get_output_from_indices(self, indices):
+        return self.project_out(self.get_codes_from_indices(indices).sum(dim=0))
+
+    # ------------------------------------------------------------------ fused level loop
+    def _can_fuse(self, x, dropout_active) -> bool:
+        if not self.use_fused_levels or dropout_active or not x.is_cuda or x.ndim != 3:
+            return False
+        if torch.is_grad_enabled() and x.requires_grad:
+            return False
+        l0 = self.layers[0]
+        return l0.channel_last and not l0._codebook.input_l2norm and l0.heads == 1
+
+    @torch.no_grad()
+    def _forward_fused(self, x, mask, freeze_codebook):
+        B, n, d = x.shape
+        N = B * n
+        dev = x.device
+        res = [x.reshape(N, d).float().contiguous().clone(), torch.empty((N, d), dtype=torch.float32, device=dev)]
+        out = torch.empty((N, d), dtype=torch.float32, device=dev)
+        all_idx, all_loss = [], []
+        Q = len(self.layers)
+        prepared = False
+        for li, layer in enumerate(self.layers):
+            cb = layer._codebook
+            cur, nxt = res[li & 1], res[(li + 1) & 1]
+            flat = cur[None]
+            mask_u8 = cb._expand_mask(mask, N)
+            if not cb.is_initialized:
+                cb._kmeans_init(flat, mask_u8)
+                cb.is_initialized = True
+                prepared = False
+            emb = cb.embeddings.detach()
+            idx, _, ws = ops.search(flat, emb, cb._codebook_cache(), cb.use_cosine_sim, latents_prepared=prepared)
+            training = self.training and layer.training
+            do_ema = training and cb.ema_update and not freeze_codebook
+            stats = ops.ema_reduce(flat, idx, mask_u8, cb.codebook_size, bound_ws=ws) if do_ema else None
+            loss_buf = ops.rvq_level(cur, nxt, emb[0], idx[0], mask_u8, training, li == 0, out,
+                                     prepare_next=li + 1 < Q)
+            prepared = li + 1 < Q
+            if do_ema:
+                cb._all_reduce(stats)
+                ops.ema_apply(stats, cb.cluster_size.data, cb.embed_avg.data, cb.embeddings.data, 1 - cb.decay,
+                              cb.eps_for_smoothing, cb.weights_l2norm)
+                cb._dirty = True
+                cb.expire_codes_(flat)
+            loss = torch.zeros(1, device=dev)
+            if training and layer.has_commitment_loss:
+                loss = loss + loss_buf[0] * layer.commitment_weight
+            all_idx.append(idx.reshape(B, n))
+            all_loss.append(loss)
+        return out.reshape(B, n, d), all_idx, all_loss
+
+    # ------------------------------------------------------------------ forward (reference :134-269)
+    def forward(self, x, mask=None, indices=None, return_all_codes=False, freeze_codebook=False,
+                rand_quantize_dropout_fixed_seed=None):
+        assert indices is None, "the indices / cross-entropy path is disabled in the reference as well (:152)"
+        num_quant, mult = self.num_quantizers, self.quantize_dropout_multiple_of
+        device = x.device
+        x = self.project_in(x)
+
+        should_dropout = self.training and self.quantize_dropout
+        if should_dropout:
+            if rand_quantize_dropout_fixed_seed is not None:
+                rand = random.Random(rand_quantize_dropout_fixed_seed)
+            elif dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+                # the reference's seed sync is broken (residual_vq.py:183-185); broadcast rank 0's seed instead
+                t = torch.tensor([random.randrange(10_000)], device=device)
+                dist.broadcast(t, src=0)
+                rand = random.Random(int(t.item()))
+            else:
+                rand = random
+            dropout_index = rand.randrange(self.quantize_dropout_cutoff_index, num_quant)
+            if mult != 1:
+                dropout_index = _round_up_multiple(dropout_index + 1, mult) - 1
+            null_shape = (x.shape[0], *x.shape[-2:]) if x.ndim >= 4 else tuple(x.shape[:2])
+            null_indices = torch.full(null_shape, -1, device=device, dtype=torch.long)
+            null_loss = torch.full((1,), 0.0, device=device, dtype=x.dtype)
+
+        if self._can_fuse(x, should_dropout):
+            quantized_out, all_indices, all_losses = self._forward_fused(x, mask, freeze_codebook)
+        else:
+            quantized_out = 0.0
+            residual = x
+            all_losses, all_indices = [], []
+            for qi, layer in enumerate(self.layers):
+                if should_dropout and qi > dropout_index:
+                    all_indices.append(null_indices)
+                    all_losses.append(null_loss)
+                    continue
+                quantized, idx, loss = layer(residual, mask=mask, freeze_codebook=freeze_codebook)
+                residual = residual - quantized.detach()
+                quantized_out = quantized_out + quantized
+                all_indices.append(idx)
+                all_losses.append(loss)
+
+        quantized_out = self.project_out(quantized_out)
+        all_losses, all_indices = map(partial(torch.stack, dim=-1), (all_losses, all_indices))
+        ret = (quantized_out, all_indices, all_losses)
+        if return_all_codes:
+            ret = (*ret, self.get_codes_from_indices(all_indices))
+        return ret
+
+
+class GroupedResidualVQ(nn.Module):
+    """reference residual_vq.py:275-357: split the feature dim into groups, one ResidualVQ each."""
+
+    def __init__(self, *, dim, groups=1, channel_last=True, **kwargs):
+        super().__init__()
+        self.dim = dim
+        self.groups = groups
+        assert dim % groups == 0
+        self.channel_last = channel_last
+        self.rvqs = nn.ModuleList([ResidualVQ(dim=dim // groups, **kwargs) for _ in range(groups)])
+
+    @property
+    def split_dim(self):
+        return -1 if self.channel_last else 1
+
+    @property
+    def codebooks(self):
+        return torch.stack(tuple(rvq.codebooks for rvq in self.rvqs))
+
+    def get_codes_from_indices(self, indices):
+        return torch.stack(tuple(rvq.get_codes_from_indices(i) for rvq, i in zip(self.rvqs, indices)))
+
+    def get_output_from_indices(self, indices):
+        outs = tuple(rvq.get_output_from_indices(i) for rvq, i in zip(self.rvqs, indices))
+        return torch.cat(outs, dim=self.split_dim)
+
+    def forward(self, x, indices=None, return_all_codes=False, freeze_codebook=False, mask=None):
+        assert indices is None or len(indices) == 0, "the indices / cross-entropy path is not supported"
+        assert x.shape[self.split_dim] == self.dim
+        chunks = x.chunk(self.groups, dim=self.split_dim)
+        seed = random.randint(0, int(1e7))
+        out = tuple(rvq(c.contiguous(), return_all_codes=return_all_codes, mask=mask, freeze_codebook=freeze_codebook,
+                        rand_quantize_dropout_fixed_seed=seed) for rvq, c in zip(self.rvqs, chunks))
+        quantized, all_indices, commit_losses, *maybe_codes = tuple(zip(*out))
+        ret = (torch.cat(quantized, dim=self.split_dim), torch.stack(all_indices), torch.stack(commit_losses))
+        if maybe_codes:
+            ret = (*ret, torch.stack(maybe_codes[0]))
+        return ret

@@ -1,0 +1,183 @@
+"""``VectorQuantize``: drop-in for reference vector_quantization/vector_quantize_pytorch.py:38-430.
+
+Same constructor arguments and ``forward`` returns.  The layout glue (channel-first, images/video,
+multi-head, projections, masks) is host code; search, gather + straight-through + commitment loss
+and the EMA update are CUDA kernels behind ``Codebook``.  Options that need the dense N x K
+similarity matrix (cross-entropy to given indices, CE commitment, diversity loss) or a learnable
+codebook (orthogonal regularisation, in-place optimizer, sync_update_v) raise NotImplementedError.
+"""
+from __future__ import annotations
+
+from collections import namedtuple
+from dataclasses import asdict, replace
+
+import torch
+import torch.distributed as dist
+from torch import nn
+
+from .codebook import Codebook
+from .params import CodebookParams
+
+LossBreakdown = namedtuple("LossBreakdown", ["commitment", "codebook_diversity", "orthogonal_reg", "inplace_optimize"])
+
+
+def _is_distributed() -> bool:
+    return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+
+
+class VectorQuantize(nn.Module):
+    def __init__(self, dim, codebook_params: CodebookParams, codebook_dim=None, heads=1,
+                 separate_codebook_per_head=False, layernorm_after_project_in=False, channel_last=True,
+                 commitment_weight=1.0, commitment_use_cross_entropy_loss=False, orthogonal_reg_weight=0.0,
+                 orthogonal_reg_active_codes_only=False, orthogonal_reg_max_codes=None,
+                 codebook_diversity_loss_weight=0.0, codebook_diversity_temperature=100.0, sync_codebook=None,
+                 in_place_codebook_optimizer=None, sync_update_v=0.0):
+        super().__init__()
+        self.dim = dim
+        self.heads = heads
+        self.separate_codebook_per_head = separate_codebook_per_head
+        codebook_dim = codebook_dim if codebook_dim is not None else dim
+        codebook_input_dim = codebook_dim * heads
+        requires_projection = codebook_input_dim != dim
+
+        if requires_projection and layernorm_after_project_in:
+            self.project_in = nn.Sequential(nn.Linear(dim, codebook_input_dim), nn.LayerNorm(codebook_input_dim))
+        elif requires_projection:
+            self.project_in = nn.Linear(dim, codebook_input_dim)
+        else:
+            self.project_in = nn.Identity()
+        self.project_out = nn.Linear(codebook_input_dim, dim) if requires_projection else nn.Identity()
+        self.has_projections = requires_projection
+
+        self.has_commitment_loss = commitment_weight > 0.0
+        self.commitment_weight = commitment_weight
+
+        unsupported = []
+        if commitment_use_cross_entropy_loss:
+            unsupported.append("commitment_use_cross_entropy_loss (needs the dense N x K similarities)")
+        if orthogonal_reg_weight > 0.0:
+            unsupported.append("orthogonal_reg_weight (needs a learnable codebook)")
+        if codebook_diversity_loss_weight > 0.0:
+            unsupported.append("codebook_diversity_loss_weight (needs the dense N x K similarities)")
+        if in_place_codebook_optimizer is not None:
+            unsupported.append("in_place_codebook_optimizer (needs a learnable codebook)")
+        if sync_update_v > 0.0:
+            unsupported.append("sync_update_v (needs a learnable codebook)")
+        if unsupported:
+            raise NotImplementedError("vqb200.VectorQuantize: outside the accelerated EMA path: " + "; ".join(unsupported))
+
+        if sync_codebook is None:
+            sync_codebook = _is_distributed()
+
+        self.codebook_params = replace(codebook_params, dim=codebook_dim,
+                                       num_codebooks=heads if separate_codebook_per_head else 1,
+                                       learnable_codebook=codebook_params.learnable_codebook,
+                                       use_ddp=sync_codebook)
+        self.learnable_codebook = codebook_params.learnable_codebook
+        assert not (codebook_params.ema_update and codebook_params.learnable_codebook), \
+            "learnable codebook not compatible with EMA update"
+        kw = asdict(self.codebook_params)
+        self._codebook = Codebook(**kw)
+        self.channel_last = channel_last
+        self.register_buffer("zero", torch.tensor(0.0), persistent=False)
+
+    # reference :140-176 reads `_codebook.embed`, which does not exist there; implemented on `embeddings`
+    @property
+    def codebook(self):
+        cb = self._codebook.embeddings
+        return cb if self.separate_codebook_per_head else cb[0]
+
+    @codebook.setter
+    def codebook(self, codes):
+        if not self.separate_codebook_per_head:
+            codes = codes[None]
+        self._codebook.embeddings.copy_(codes)
+        self._codebook.invalidate_cache()
+
+    def get_codes_from_indices(self, indices):
+        cb = self.codebook
+        if cb.ndim == 2:
+            codes = cb[indices]
+        else:
+            b = indices.shape[0]
+            h = indices.shape[-1]
+            flat = indices.reshape(b, -1, h)                                   # b n h
+            gathered = torch.stack([cb[i][flat[..., i]] for i in range(h)], dim=2)   # b n h d
+            codes = gathered.reshape(b, flat.shape[1], -1).reshape(*indices.shape[:-1], -1)
+        if not self.channel_last:
+            codes = codes.movedim(-1, 1)
+        return codes
+
+    def get_output_from_indices(self, indices):
+        return self.project_out(self.get_codes_from_indices(indices))
+
+    def forward(self, x, indices=None, mask=None, freeze_codebook=False, return_loss_breakdown=False):
+        if indices is not None:
+            raise NotImplementedError("vqb200.VectorQuantize: cross-entropy to given indices needs the dense "
+                                      "N x K similarities, which this path never materialises")
+        orig_input = x
+        only_one = x.ndim == 2
+        if only_one:
+            assert mask is None
+            x = x[:, None, :]
+        heads, multi = self.heads, self.heads > 1
+        B = x.shape[0]
+        device = x.device
+
+        if not self.channel_last:
+            x = x.movedim(1, -1)
+        spatial = None
+        if x.ndim >= 4:
+            spatial = tuple(x.shape[1:-1])
+            x = x.reshape(B, -1, x.shape[-1])
+        x = self.project_in(x)
+        if multi:
+            n, dh = x.shape[1], x.shape[-1] // heads
+            xh = x.reshape(B, n, heads, dh)
+            x = xh.permute(2, 0, 1, 3) if self.separate_codebook_per_head else \
+                xh.permute(0, 2, 1, 3).reshape(1, B * heads, n, dh)
+        x = self._codebook.transform_input(x)
+
+        cb_in = x if x.ndim == 4 else x[None]
+        training = self.training
+        want_commit = training and self.has_commitment_loss
+        quantize, embed_ind, commit = self._codebook._run(cb_in, mask, freeze_codebook, fuse_st=True,
+                                                          want_commit=want_commit)
+        if x.ndim < 4:
+            quantize, embed_ind = quantize[0], embed_ind[0]
+
+        commit_loss = self.zero
+        if multi:
+            if self.separate_codebook_per_head:
+                embed_ind = embed_ind.permute(1, 2, 0)
+            else:
+                embed_ind = embed_ind.reshape(B, heads, -1).permute(0, 2, 1)
+        if spatial is not None:
+            embed_ind = embed_ind.reshape(B, *spatial, *embed_ind.shape[2:])
+        if only_one:
+            embed_ind = embed_ind[:, 0]
+
+        loss = torch.tensor([0.0], device=device, requires_grad=training)
+        if want_commit:
+            commit_loss = commit
+            loss = loss + commit_loss * self.commitment_weight
+
+        if multi:
+            if self.separate_codebook_per_head:
+                quantize = quantize.permute(1, 2, 0, 3).reshape(B, quantize.shape[2], -1)
+            else:
+                n = quantize.shape[2]
+                quantize = quantize.reshape(B, heads, n, -1).permute(0, 2, 1, 3).reshape(B, n, -1)
+        quantize = self.project_out(quantize)
+        if spatial is not None:
+            quantize = quantize.reshape(B, *spatial, quantize.shape[-1])
+        if not self.channel_last:
+            quantize = quantize.movedim(-1, 1)
+        if only_one:
+            quantize = quantize[:, 0]
+        if mask is not None:
+            quantize = torch.where(mask[..., None], quantize, orig_input)
+
+        if not return_loss_breakdown:
+            return quantize, embed_ind, loss
+        return quantize, embed_ind, loss, LossBreakdown(commit_loss, self.zero, self.zero, self.zero)
