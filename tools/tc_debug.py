@@ -21,11 +21,15 @@ shapes = [  # H, N, K, d, cosine, cb_scale
     (1, 1024, 512, 256, False, None),   # default-init scale codebook (near ties)
     (1, 40000, 8192, 256, False, 0.5),
 ]
+BF16 = False
 if len(sys.argv) > 1 and sys.argv[1] == "big":
     shapes = [(1, 1 << 20, 8192, 256, False, 0.5)]
+    BF16 = True
 for (H, N, K, d, cos, scale) in shapes:
     g = torch.Generator().manual_seed(N + K)
     x = torch.randn(H, N, d, generator=g)
+    if BF16:
+        x = x.bfloat16()
     if scale is None:
         c = (torch.rand(H, K, d, generator=g) * 2 - 1) * (6.0 / (K * d)) ** 0.5
     else:
@@ -44,7 +48,7 @@ for (H, N, K, d, cos, scale) in shapes:
     neq = int((idx_tc != idx_ex).sum())
     msg = f"H={H} N={N} K={K} d={d} cos={cos} scale={scale}: tc_vs_exact mismatches={neq} stats={st} t_tc={t1-t0:.4f}s t_exact={t2-t1:.3f}s"
     if N * K <= 1 << 24:
-        sim = (torch.einsum('hnd,hkd->hnk', x, c) if cos else -torch.cdist(x, c))
+        sim = (torch.einsum('hnd,hkd->hnk', x.float(), c) if cos else -torch.cdist(x.float(), c))
         ref = sim.argmax(-1)
         top2 = sim.topk(2, -1).values
         gap = (top2[..., 0] - top2[..., 1]).abs() / top2[..., 0].abs().clamp_min(1e-30)
@@ -55,6 +59,13 @@ for (H, N, K, d, cos, scale) in shapes:
         rows = (idx_tc != idx_ex).nonzero()[:5]
         for h, r in rows.tolist():
             print("   row", h, r, "tc", int(idx_tc[h, r]), "exact", int(idx_ex[h, r]), "score", float(sc_ex[h, r]), flush=True)
+# per-kernel breakdown for the last shape
+from torch.profiler import ProfilerActivity, profile
+with profile(activities=[ProfilerActivity.CUDA]) as prof:
+    for _ in range(3):
+        ops.search(xd, cd, cache, cos)
+    torch.cuda.synchronize()
+print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=12, max_name_column_width=70), flush=True)
 # timing loop for the last shape
 torch.cuda.synchronize()
 for it in range(3):

@@ -49,10 +49,11 @@ inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 // Derived codebook cache layout (one caller-owned buffer).
 struct CacheLayout {
   int Kp, dp;
-  size_t off_cb;     // bf16 [H][Kp][dp]  = bf16(-c), zero padded
+  size_t off_hdr;    // f32  [H][4]       = {s_c (power of two), 1/s_c, max|c|, -}
+  size_t off_cb;     // fp16 [H][Kp][dp]  = fp16(c * s_c), zero padded
   size_t off_cn2h;   // f32  [H][Kp]      = |c|^2 / 2   (0 for the dot metric)
   size_t off_cn;     // f32  [H][Kp]      = |c|
-  size_t off_dcn;    // f32  [H][Kp]      = |c - bf16(c)|
+  size_t off_dcn;    // f32  [H][Kp]      = |c - fp16(c*s_c)/s_c|
   size_t total;
 };
 inline CacheLayout cache_layout(int64_t H, int K, int d) {
@@ -60,6 +61,7 @@ inline CacheLayout cache_layout(int64_t H, int K, int d) {
   L.Kp = k_pad(K);
   L.dp = d_pad(d);
   size_t o = 0;
+  L.off_hdr = o;  o += align_up((size_t)H * 16);
   L.off_cb = o;   o += align_up((size_t)H * L.Kp * L.dp * 2);
   L.off_cn2h = o; o += align_up((size_t)H * L.Kp * 4);
   L.off_cn = o;   o += align_up((size_t)H * L.Kp * 4);
@@ -73,7 +75,9 @@ struct SearchLayout {
   int dp;
   size_t off_scal;    // u32[64]: [0]=max|x_b| bits, [1]=max|x-x_b| bits, [2]=#rescanned, [3]=#reranked, [4]=tc used, [5]=smem misalign flag
   size_t off_cnt;     // u32[H]: flagged rows per codebook (directly after scal: zeroed together)
-  size_t off_xb;      // bf16 [H][N][dp]
+  size_t off_xb;      // fp16 [H][N][dp]  = fp16(x * s_row), zero padded
+  size_t off_xinv;    // f32  [H][N]      = 1 / s_row (exact power of two)
+  size_t off_keys;    // u64  [H][N]      packed (score, index) min-keys of rows being rescanned
   size_t off_cand;    // {f32 key, i32 code} [H][N][kNumCand]
   size_t off_flag;    // i32 [H*N] flagged row list
   size_t off_bias;    // f32 [H][Kp]  lower-bound bias  |c|^2/2 - E_k  (needs the row stats, so per search)
@@ -87,6 +91,8 @@ inline SearchLayout search_layout(int64_t H, int64_t N, int K, int d) {
   L.off_scal = o; o += 256;
   L.off_cnt = o;  o += align_up((size_t)H * 4);
   L.off_xb = o;   o += align_up((size_t)H * N * L.dp * 2);
+  L.off_xinv = o; o += align_up((size_t)H * N * 4);
+  L.off_keys = o; o += align_up((size_t)H * N * 8);
   L.off_cand = o; o += align_up((size_t)H * N * kNumCand * 8);
   L.off_flag = o; o += align_up((size_t)H * N * 4);
   L.off_bias = o; o += align_up((size_t)H * k_pad(K) * 4);
@@ -146,10 +152,20 @@ inline int dtype_size(int dt) { return dt == VQB_F32 ? 4 : 2; }
 
 // ---- internal launchers (defined across the .cu files) --------------------------------------
 int launch_prepare_latents(const void* x, int x_dtype, int64_t rows, int d, int dp,
-                           __nv_bfloat16* xb, uint32_t* scal, cudaStream_t st);
+                           __half* xb, float* xinv, uint32_t* scal, cudaStream_t st);
 int launch_make_bias(const void* cache, const CacheLayout& CL, int64_t H, int K, int metric,
                      const uint32_t* scal, float* bias, float* err, cudaStream_t st);
-int launch_search_tc(const __nv_bfloat16* xb, const __nv_bfloat16* cb, const float* bias,
+int launch_search_tc(const __half* xb, const float* xinv, const __half* cb, const float* chdr, const float* bias,
                      int64_t H, int64_t N, int K, int dp, void* cand, uint32_t* scal, cudaStream_t st);
+
+// power-of-two scale that brings a magnitude bound m below 2^14 (fp16 max is 65504)
+__host__ __device__ inline float pow2_scale(float m) {
+  if (!(m > 0.f) || !isfinite(m)) return 1.f;
+  int e = ilogbf(m) + 1;                 // m < 2^e
+  int sh = 14 - e;
+  if (sh > 100) sh = 100;
+  if (sh < -100) sh = -100;
+  return ldexpf(1.f, sh);
+}
 
 }  // namespace vqb

@@ -148,48 +148,109 @@ st_commit_backward_kernel(const float* __restrict__ gq, const float* __restrict_
   }
 }
 
-// One ResidualVQ level: gather + ST + loss + residual/out update + next level's bf16 operand & row stats.
+// One ResidualVQ level: gather + ST + loss + residual/out update + next level's fp16 operand & row stats.
+// Lanes own float4 column groups {lane*4 + 128*t}; the new residual row stays in registers between the
+// update pass and the scaled-fp16 conversion pass (d_pad <= 512 when the next operand is requested).
 __global__ void __launch_bounds__(kGatherThreads)
 rvq_level_kernel(const float* res_in, float* res_out, const float* __restrict__ cb, const int64_t* __restrict__ idx,
                  const uint8_t* __restrict__ mask, int training, int first, float* __restrict__ out,
                  float* __restrict__ qout, int64_t N, int K, int d, int dp, double* __restrict__ part,
-                 long long* __restrict__ cntp, __nv_bfloat16* __restrict__ next_xb, uint32_t* __restrict__ next_scal) {
+                 long long* __restrict__ cntp, __half* __restrict__ next_xb, float* __restrict__ next_xinv,
+                 uint32_t* __restrict__ next_scal) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int wpb = kGatherThreads / 32;
   double sqd = 0.0;
   long long used = 0;
   float max_n2 = 0.f, max_r2 = 0.f;
+  const bool vec = (d & 3) == 0;
   for (int64_t row = (int64_t)blockIdx.x * wpb + warp; row < N; row += (int64_t)gridDim.x * wpb) {
     const bool live = mask == nullptr || mask[row] != 0;
     const float* rr = res_in + row * (int64_t)d;
     float* ro = res_out + row * (int64_t)d;
     const float* cr = cb + idx[row] * (int64_t)d;
     float* orow = out + row * (int64_t)d;
-    float sq = 0.f, n2 = 0.f, r2 = 0.f;
-    for (int j = lane; j < dp; j += 32) {
-      float rnew = 0.f;
-      if (j < d) {
+    float sq = 0.f, m = 0.f;
+    float4 keep[4];                      // new residual, columns lane*4 + 128*t (t < 4 covers d_pad <= 512)
+#pragma unroll
+    for (int t = 0; t < 4; ++t) keep[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (vec) {
+#pragma unroll
+      for (int t = 0; t < 16; ++t) {
+        const int j = lane * 4 + 128 * t;
+        if (j >= d) break;
+        const float4 r = *reinterpret_cast<const float4*>(rr + j);
+        const float4 c = __ldg(reinterpret_cast<const float4*>(cr + j));
+        const float4 df = make_float4(__fsub_rn(c.x, r.x), __fsub_rn(c.y, r.y), __fsub_rn(c.z, r.z), __fsub_rn(c.w, r.w));
+        float4 qv;
+        // masked-out positions return the layer input itself (vector_quantize_pytorch.py:415-418)
+        if (!live) qv = r;
+        else if (training) qv = make_float4(__fadd_rn(r.x, df.x), __fadd_rn(r.y, df.y), __fadd_rn(r.z, df.z), __fadd_rn(r.w, df.w));
+        else qv = c;
+        float4 o;
+        if (first) o = make_float4(__fadd_rn(0.f, qv.x), __fadd_rn(0.f, qv.y), __fadd_rn(0.f, qv.z), __fadd_rn(0.f, qv.w));
+        else {
+          const float4 p = *reinterpret_cast<const float4*>(orow + j);
+          o = make_float4(__fadd_rn(p.x, qv.x), __fadd_rn(p.y, qv.y), __fadd_rn(p.z, qv.z), __fadd_rn(p.w, qv.w));
+        }
+        *reinterpret_cast<float4*>(orow + j) = o;
+        const float4 rn = make_float4(__fsub_rn(r.x, qv.x), __fsub_rn(r.y, qv.y), __fsub_rn(r.z, qv.z), __fsub_rn(r.w, qv.w));
+        *reinterpret_cast<float4*>(ro + j) = rn;
+        if (qout) *reinterpret_cast<float4*>(qout + row * (int64_t)d + j) = qv;
+        sq = fmaf(df.x, df.x, sq); sq = fmaf(df.y, df.y, sq); sq = fmaf(df.z, df.z, sq); sq = fmaf(df.w, df.w, sq);
+        if (t < 4) keep[t] = rn;
+        m = fmaxf(fmaxf(fmaxf(m, fabsf(rn.x)), fmaxf(fabsf(rn.y), fabsf(rn.z))), fabsf(rn.w));
+      }
+    } else {
+      for (int j = lane; j < d; j += 32) {
         const float r = rr[j], c = cr[j];
         const float df = __fsub_rn(c, r);
-        // masked-out positions return the layer input itself (vector_quantize_pytorch.py:415-418)
         const float qv = live ? (training ? __fadd_rn(r, df) : c) : r;
         orow[j] = first ? __fadd_rn(0.0f, qv) : __fadd_rn(orow[j], qv);
-        rnew = __fsub_rn(r, qv);
-        ro[j] = rnew;
+        const float rn = __fsub_rn(r, qv);
+        ro[j] = rn;
         if (qout) qout[row * (int64_t)d + j] = qv;
         sq = fmaf(df, df, sq);
-      }
-      if (next_xb) {
-        const __nv_bfloat16 b = __float2bfloat16(rnew);
-        const float back = __bfloat162float(b);
-        next_xb[row * (int64_t)dp + j] = b;
-        n2 = fmaf(back, back, n2);
-        r2 = fmaf(rnew - back, rnew - back, r2);
+        m = fmaxf(m, fabsf(rn));
       }
     }
     sq = warp_sum(sq);
     if (live) { sqd += (double)sq; ++used; }
     if (next_xb) {
+#pragma unroll
+      for (int o2 = 16; o2 > 0; o2 >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o2));
+      const float s = pow2_scale(m), is = 1.f / s;
+      if (lane == 0) next_xinv[row] = is;
+      __half* xo = next_xb + row * (int64_t)dp;
+      float n2 = 0.f, r2 = 0.f;
+      if (vec) {
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const int j = lane * 4 + 128 * t;
+          if (j < dp) {
+            const float4 v = keep[t];     // zero beyond d
+            const __half2 h0 = __floats2half2_rn(v.x * s, v.y * s), h1 = __floats2half2_rn(v.z * s, v.w * s);
+            const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+            uint2 pk;
+            pk.x = *reinterpret_cast<const uint32_t*>(&h0);
+            pk.y = *reinterpret_cast<const uint32_t*>(&h1);
+            *reinterpret_cast<uint2*>(xo + j) = pk;
+            const float b0 = f0.x * is, b1 = f0.y * is, b2 = f1.x * is, b3 = f1.y * is;
+            n2 += b0 * b0 + b1 * b1 + b2 * b2 + b3 * b3;
+            const float e0 = v.x - b0, e1 = v.y - b1, e2 = v.z - b2, e3 = v.w - b3;
+            r2 += e0 * e0 + e1 * e1 + e2 * e2 + e3 * e3;
+          }
+        }
+      } else {
+        __syncwarp();                     // res_out row was just written by this warp: re-read it
+        for (int j = lane; j < dp; j += 32) {
+          const float v = j < d ? ro[j] : 0.f;
+          const __half hv = __float2half_rn(v * s);
+          const float back = __half2float(hv) * is;
+          xo[j] = hv;
+          n2 += back * back;
+          r2 += (v - back) * (v - back);
+        }
+      }
       n2 = warp_sum(n2);
       r2 = warp_sum(r2);
       max_n2 = fmaxf(max_n2, n2);
@@ -282,13 +343,16 @@ extern "C" int vqb_rvq_level(const float* residual_in, float* residual_out, cons
   GatherLayout L = gather_layout();
   VQB_REQUIRE(gather_ws_bytes >= L.total, VQB_ERR_WORKSPACE, "gather workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
-  __nv_bfloat16* nxb = nullptr;
+  __half* nxb = nullptr;
+  float* nxinv = nullptr;
   uint32_t* nscal = nullptr;
   const int dp = d_pad(d);
+  if (next_ws && dp > 512) next_ws = nullptr;   // no tensor-core pass for this width: nothing to prepare
   if (next_ws) {
     SearchLayout SL = search_layout(1, N, K, d);
     VQB_REQUIRE(next_ws_bytes >= SL.total, VQB_ERR_WORKSPACE, "next-level search workspace too small");
-    nxb = (__nv_bfloat16*)((char*)next_ws + SL.off_xb);
+    nxb = (__half*)((char*)next_ws + SL.off_xb);
+    nxinv = (float*)((char*)next_ws + SL.off_xinv);
     nscal = (uint32_t*)((char*)next_ws + SL.off_scal);
     VQB_CUDA_TRY(cudaMemsetAsync(nscal, 0, 8, st));
   }
@@ -297,8 +361,8 @@ extern "C" int vqb_rvq_level(const float* residual_in, float* residual_out, cons
   long long* cntp = (long long*)((char*)gather_ws + L.off_cnt);
   if (N > 0) {
     rvq_level_kernel<<<grid, kGatherThreads, 0, st>>>(residual_in, residual_out, codebook, idx, mask, training, first_level,
-                                                      quantized_out, q_out, N, K, d, next_ws ? dp : d, part, cntp,
-                                                      nxb, nscal);
+                                                      quantized_out, q_out, N, K, d, dp, part, cntp,
+                                                      nxb, nxinv, nscal);
     VQB_LAUNCH_CHECK();
   }
   loss_finalize_kernel<<<1, 256, 0, st>>>(part, cntp, N > 0 ? grid : 0, d, loss_out);

@@ -1,36 +1,55 @@
 // prepare.cu -- operand preparation for the tensor-core search:
-//   * codebook cache: bf16(-c) padded copy + per-code norms / rounding residual norms
-//   * latents: bf16 padded copy + global max row norm / max rounding residual norm
+//   * codebook cache: fp16(c * s_c) padded copy (s_c = power of two per codebook) + per-code norms /
+//     rounding residual norms
+//   * latents: fp16(x * s_row) padded copy (s_row = power of two per row) + global max row norm /
+//     max rounding residual norm.  fp16 carries 3 more mantissa bits than bf16 at the same tensor-core
+//     rate, which makes the rigorous rounding bound E_k (and so the re-rank rate) 8x smaller; the
+//     power-of-two scales remove fp16's range problem and are undone exactly in the epilogue.
 //   * per-search lower-bound bias  L_k = |c_k|^2/2 - E_k  (see search_resolve.cu for the proof sketch)
 //   * l2norm of rows (reference utils/losses.py:19)
 #include "common.cuh"
 
 namespace vqb {
 
-// one warp per code row (incl. padded rows k in [K, Kp))
+// max |c| per codebook -> hdr[h][2] (bits of a non-negative float order like unsigned ints)
+__global__ void codebook_absmax_kernel(const float* __restrict__ cb, int64_t per_head, float* __restrict__ hdr) {
+  const int h = blockIdx.y;
+  const float* c = cb + (int64_t)h * per_head;
+  float m = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < per_head; i += (int64_t)gridDim.x * blockDim.x)
+    m = fmaxf(m, fabsf(c[i]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<uint32_t*>(hdr + h * 4 + 2), __float_as_uint(m));
+}
+
+// one warp per code row (incl. padded rows k in [K, Kp)): fp16(c * s_c) + norms of c and of the rounding residual
 __global__ void prepare_codebook_kernel(const float* __restrict__ cb, int64_t H, int K, int Kp, int d, int dp,
-                                        int metric, __nv_bfloat16* __restrict__ out, float* __restrict__ cn2h,
-                                        float* __restrict__ cn, float* __restrict__ dcn) {
+                                        int metric, float* __restrict__ hdr, __half* __restrict__ out,
+                                        float* __restrict__ cn2h, float* __restrict__ cn, float* __restrict__ dcn) {
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= H * (int64_t)Kp) return;
   const int64_t h = row / Kp;
   const int k = (int)(row - h * Kp);
-  __nv_bfloat16* o = out + row * dp;
+  const float sc = pow2_scale(hdr[h * 4 + 2]);
+  const float isc = 1.f / sc;
+  if (k == 0 && lane == 0) { hdr[h * 4 + 0] = sc; hdr[h * 4 + 1] = isc; }
+  __half* o = out + row * dp;
   if (k >= K) {
-    for (int j = lane; j < dp; j += 32) o[j] = __float2bfloat16(0.f);
+    for (int j = lane; j < dp; j += 32) o[j] = __float2half(0.f);
     if (lane == 0) { cn2h[row] = kPadBias; cn[row] = 0.f; dcn[row] = 0.f; }
     return;
   }
   const float* c = cb + (h * K + k) * (int64_t)d;
   double n2 = 0.0, r2 = 0.0;
   for (int j = lane; j < dp; j += 32) {
-    float v = j < d ? c[j] : 0.f;
-    __nv_bfloat16 b = __float2bfloat16(v);
-    float back = __bfloat162float(b);
-    o[j] = __float2bfloat16(-back);                  // exact negation: the MMA then yields -x.c
+    const float v = j < d ? c[j] : 0.f;
+    const __half hv = __float2half_rn(v * sc);           // power-of-two scaling is exact
+    const float back = __half2float(hv) * isc;
+    o[j] = hv;
     n2 = fma((double)v, (double)v, n2);
-    double r = (double)v - (double)back;
+    const double r = (double)v - (double)back;
     r2 = fma(r, r, r2);
   }
   n2 = warp_sum(n2);
@@ -42,35 +61,53 @@ __global__ void prepare_codebook_kernel(const float* __restrict__ cb, int64_t H,
   }
 }
 
-// one warp per latent row: bf16 copy (zero padded to dp) + atomicMax of |x_b| and |x - x_b|
+// one warp per latent row: per-row power-of-two scale, fp16 copy (zero padded to dp),
+// atomicMax of |x~| and |x - x~| where x~ = fp16(x s)/s is what the tensor core really sees
 template <typename T>
 __global__ void prepare_latents_kernel(const T* __restrict__ x, int64_t rows, int d, int dp,
-                                       __nv_bfloat16* __restrict__ xb, uint32_t* __restrict__ scal) {
+                                       __half* __restrict__ xb, float* __restrict__ xinv,
+                                       uint32_t* __restrict__ scal) {
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   float n2 = 0.f, r2 = 0.f;
   if (row < rows) {
     const T* xr = x + row * (int64_t)d;
-    __nv_bfloat16* o = xb + row * (int64_t)dp;
-    if ((d & 3) == 0) {
+    __half* o = xb + row * (int64_t)dp;
+    const bool vec = (d & 3) == 0;
+    // pass 1: row max (the second pass re-reads the row from L1/L2)
+    float m = 0.f;
+    if (vec) {
+      for (int j = lane * 4; j < d; j += 128) {
+        const float4 v = load4<T>(xr + j);
+        m = fmaxf(fmaxf(fmaxf(m, fabsf(v.x)), fmaxf(fabsf(v.y), fabsf(v.z))), fabsf(v.w));
+      }
+    } else {
+      for (int j = lane; j < d; j += 32) m = fmaxf(m, fabsf(to_f32<T>(xr[j])));
+    }
+#pragma unroll
+    for (int o2 = 16; o2 > 0; o2 >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o2));
+    const float s = pow2_scale(m), is = 1.f / s;
+    if (lane == 0) xinv[row] = is;
+    if (vec) {
       for (int j = lane * 4; j < dp; j += 128) {
-        float4 v = j < d ? load4<T>(xr + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-        __nv_bfloat162 b0 = __floats2bfloat162_rn(v.x, v.y), b1 = __floats2bfloat162_rn(v.z, v.w);
-        float2 f0 = __bfloat1622float2(b0), f1 = __bfloat1622float2(b1);
+        const float4 v = j < d ? load4<T>(xr + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const __half2 h0 = __floats2half2_rn(v.x * s, v.y * s), h1 = __floats2half2_rn(v.z * s, v.w * s);
+        const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
         uint2 pk;
-        pk.x = *reinterpret_cast<uint32_t*>(&b0);
-        pk.y = *reinterpret_cast<uint32_t*>(&b1);
+        pk.x = *reinterpret_cast<const uint32_t*>(&h0);
+        pk.y = *reinterpret_cast<const uint32_t*>(&h1);
         *reinterpret_cast<uint2*>(o + j) = pk;
-        n2 += f0.x * f0.x + f0.y * f0.y + f1.x * f1.x + f1.y * f1.y;
-        float e0 = v.x - f0.x, e1 = v.y - f0.y, e2 = v.z - f1.x, e3 = v.w - f1.y;
+        const float b0 = f0.x * is, b1 = f0.y * is, b2 = f1.x * is, b3 = f1.y * is;
+        n2 += b0 * b0 + b1 * b1 + b2 * b2 + b3 * b3;
+        const float e0 = v.x - b0, e1 = v.y - b1, e2 = v.z - b2, e3 = v.w - b3;
         r2 += e0 * e0 + e1 * e1 + e2 * e2 + e3 * e3;
       }
     } else {
       for (int j = lane; j < dp; j += 32) {
-        float v = j < d ? to_f32<T>(xr[j]) : 0.f;
-        __nv_bfloat16 b = __float2bfloat16(v);
-        float back = __bfloat162float(b);
-        o[j] = b;
+        const float v = j < d ? to_f32<T>(xr[j]) : 0.f;
+        const __half hv = __float2half_rn(v * s);
+        const float back = __half2float(hv) * is;
+        o[j] = hv;
         n2 += back * back;
         r2 += (v - back) * (v - back);
       }
@@ -95,17 +132,17 @@ __global__ void prepare_latents_kernel(const T* __restrict__ x, int64_t rows, in
 }
 
 int launch_prepare_latents(const void* x, int x_dtype, int64_t rows, int d, int dp,
-                           __nv_bfloat16* xb, uint32_t* scal, cudaStream_t st) {
+                           __half* xb, float* xinv, uint32_t* scal, cudaStream_t st) {
   const int warps = 8;
   const int64_t blocks = (rows + warps - 1) / warps;
   VQB_REQUIRE(blocks < (1ll << 31), VQB_ERR_UNSUPPORTED, "too many latent rows: %lld", (long long)rows);
   VQB_DISPATCH_DTYPE(x_dtype, T,
-    prepare_latents_kernel<T><<<(unsigned)blocks, warps * 32, 0, st>>>((const T*)x, rows, d, dp, xb, scal));
+    prepare_latents_kernel<T><<<(unsigned)blocks, warps * 32, 0, st>>>((const T*)x, rows, d, dp, xb, xinv, scal));
   VQB_LAUNCH_CHECK();
   return VQB_OK;
 }
 
-// E_k = Xmax*|c_k - bf16(c_k)| + DXmax*|c_k| + accumulation slack;  bias_k = |c_k|^2/2 - E_k
+// E_k = Xmax*|c_k - c~_k| + DXmax*|c_k| + accumulation slack;  bias_k = |c_k|^2/2 - E_k
 __global__ void make_bias_kernel(const float* __restrict__ cn2h, const float* __restrict__ cn,
                                  const float* __restrict__ dcn, int64_t total, int Kp, int K,
                                  const uint32_t* __restrict__ scal, float* __restrict__ bias,
@@ -116,7 +153,7 @@ __global__ void make_bias_kernel(const float* __restrict__ cn2h, const float* __
   if (k >= K) { bias[i] = kPadBias; err[i] = 0.f; return; }
   float xmax = __uint_as_float(scal[0]), dxmax = __uint_as_float(scal[1]);
   float c = cn[i], h = cn2h[i];
-  // rounding of products is exact in the tensor core (bf16 x bf16 fits fp32); accumulation is fp32-ish:
+  // products are exact in the tensor core (fp16 x fp16 = 22 bits, fits fp32); accumulation is fp32-ish:
   // allow 2^-16 of the largest possible |sum| plus the fp32 rounding of |c|^2/2.
   float e = xmax * dcn[i] + dxmax * c + 1.6e-5f * (xmax * c) + 2.4e-7f * h;
   e = e * 1.001f + 1e-30f;
@@ -182,10 +219,18 @@ extern "C" int vqb_prepare_codebook(const float* codebook, int64_t H, int K, int
   CacheLayout CL = cache_layout(H, K, d);
   VQB_REQUIRE(cache_bytes >= CL.total, VQB_ERR_WORKSPACE, "codebook cache too small: %zu < %zu", cache_bytes, CL.total);
   char* base = (char*)cache;
+  cudaStream_t st = (cudaStream_t)stream;
+  float* hdr = (float*)(base + CL.off_hdr);
+  VQB_CUDA_TRY(cudaMemsetAsync(hdr, 0, (size_t)H * 16, st));
+  const int64_t per_head = (int64_t)K * d;
+  int gx = (int)((per_head + 256 * 8 - 1) / (256 * 8));
+  if (gx > 1024) gx = 1024;
+  codebook_absmax_kernel<<<dim3((unsigned)gx, (unsigned)H), 256, 0, st>>>(codebook, per_head, hdr);
+  VQB_LAUNCH_CHECK();
   const int warps = 8;
   int64_t rows = H * (int64_t)CL.Kp;
-  prepare_codebook_kernel<<<(unsigned)((rows + warps - 1) / warps), warps * 32, 0, (cudaStream_t)stream>>>(
-      codebook, H, K, CL.Kp, d, CL.dp, metric, (__nv_bfloat16*)(base + CL.off_cb), (float*)(base + CL.off_cn2h),
+  prepare_codebook_kernel<<<(unsigned)((rows + warps - 1) / warps), warps * 32, 0, st>>>(
+      codebook, H, K, CL.Kp, d, CL.dp, metric, hdr, (__half*)(base + CL.off_cb), (float*)(base + CL.off_cn2h),
       (float*)(base + CL.off_cn), (float*)(base + CL.off_dcn));
   VQB_LAUNCH_CHECK();
   return VQB_OK;

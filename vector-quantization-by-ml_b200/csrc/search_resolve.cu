@@ -67,7 +67,8 @@ __global__ void __launch_bounds__(256)
 resolve_kernel(const T* __restrict__ x, const float* __restrict__ cb, const uint2* __restrict__ cand,
                const float* __restrict__ err, int64_t H, int64_t N, int K, int Kp, int d, int metric,
                int64_t idx_offset, int64_t* __restrict__ idx_out, float* __restrict__ score_out,
-               int* __restrict__ flag_list, uint32_t* __restrict__ flag_cnt, uint32_t* __restrict__ scal) {
+               int* __restrict__ flag_list, uint32_t* __restrict__ flag_cnt,
+               unsigned long long* __restrict__ keys, uint32_t* __restrict__ scal) {
   const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   bool reranked = false;
   if (gid < H * N) {
@@ -112,6 +113,7 @@ resolve_kernel(const T* __restrict__ x, const float* __restrict__ cb, const uint
     if (full_rescan) {
       const uint32_t pos = atomicAdd(flag_cnt + h, 1u);
       flag_list[h * N + pos] = (int)row;
+      keys[gid] = ~0ull;                      // min-key accumulator of the K-split rescan
     } else if (ncand == 1 && score_out == nullptr) {
       idx_out[gid] = (int64_t)c1 + idx_offset;
     } else {
@@ -155,11 +157,25 @@ resolve_kernel(const T* __restrict__ x, const float* __restrict__ cb, const uint
 // ------------------------------------------------------------------------------------------
 constexpr int kER = 32, kEC = 64, kEK = 32;
 
-template <typename T>
+__device__ __forceinline__ unsigned long long pack_key(float score, int idx) {
+  uint32_t u = __float_as_uint(score);
+  u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);      // float order -> unsigned order
+  return ((unsigned long long)u << 32) | (unsigned long long)(uint32_t)idx;
+}
+__device__ __forceinline__ float unpack_score(unsigned long long key) {
+  uint32_t u = (uint32_t)(key >> 32);
+  u = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+  return __uint_as_float(u);
+}
+
+// kSplit: blockIdx.z owns the code range [z*ksplit_codes, (z+1)*ksplit_codes) and the per-row result is merged
+// with a 64-bit atomicMin on (orderable score, index) keys -- the lowest index wins ties, like torch.argmax.
+template <typename T, bool kSplit>
 __global__ void __launch_bounds__(256)
 exact_scan_kernel(const T* __restrict__ x, const float* __restrict__ cb, const int* __restrict__ flag_list,
                   const uint32_t* __restrict__ flag_cnt, int64_t N, int K, int d, int metric, int64_t idx_offset,
-                  int64_t* __restrict__ idx_out, float* __restrict__ score_out, uint32_t* __restrict__ scal) {
+                  int64_t* __restrict__ idx_out, float* __restrict__ score_out, uint32_t* __restrict__ scal,
+                  int ksplit_codes, unsigned long long* __restrict__ keys) {
   __shared__ float xs[kER][kEK + 1];
   __shared__ float cs[kEC][kEK + 1];
   __shared__ int rows_s[kER];
@@ -169,7 +185,10 @@ exact_scan_kernel(const T* __restrict__ x, const float* __restrict__ cb, const i
   const T* xh = x + (int64_t)h * N * d;
   const float* cbh = cb + (int64_t)h * K * d;
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;   // codes tx+16j (j<4), rows ty+16i (i<2)
-  if (flag_list && blockIdx.x == 0 && threadIdx.x == 0 && count) atomicAdd(scal + 2, (uint32_t)count);
+  if (flag_list && blockIdx.x == 0 && blockIdx.z == 0 && threadIdx.x == 0 && count) atomicAdd(scal + 2, (uint32_t)count);
+  const int kbeg = kSplit ? (int)blockIdx.z * ksplit_codes : 0;
+  const int kend = kSplit ? (kbeg + ksplit_codes < K ? kbeg + ksplit_codes : K) : K;
+  if (kbeg >= kend) return;
 
   for (int64_t t0 = (int64_t)blockIdx.x * kER; t0 < count; t0 += (int64_t)gridDim.x * kER) {
     __syncthreads();
@@ -181,7 +200,7 @@ exact_scan_kernel(const T* __restrict__ x, const float* __restrict__ cb, const i
     float best[2] = {__int_as_float(0x7f800000), __int_as_float(0x7f800000)};
     int bidx[2] = {0x7fffffff, 0x7fffffff};
     // |x|^2 of this thread's two rows, fp64, same order as row_norm2 (recomputed per code tile: cheap)
-    for (int k0 = 0; k0 < K; k0 += kEC) {
+    for (int k0 = kbeg; k0 < kend; k0 += kEC) {
       double acc[2][4], xn[2] = {0.0, 0.0}, cn[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
       for (int i = 0; i < 2; ++i)
@@ -196,7 +215,7 @@ exact_scan_kernel(const T* __restrict__ x, const float* __restrict__ cb, const i
         }
         for (int e = threadIdx.x; e < kEC * kEK; e += 256) {
           const int r = e / kEK, c = e % kEK;
-          cs[r][c] = (k0 + r < K && d0 + c < d) ? cbh[(int64_t)(k0 + r) * d + d0 + c] : 0.f;
+          cs[r][c] = (k0 + r < kend && d0 + c < d) ? cbh[(int64_t)(k0 + r) * d + d0 + c] : 0.f;
         }
         __syncthreads();
 #pragma unroll 4
@@ -217,7 +236,7 @@ exact_scan_kernel(const T* __restrict__ x, const float* __restrict__ cb, const i
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int k = k0 + tx + 16 * j;
-          if (k < K) {
+          if (k < kend) {
             float s;
             if (metric == VQB_DOT) s = (float)(-acc[i][j]);
             else s = sqrtf(fmaxf((float)(xn[i] + cn[j] - 2.0 * acc[i][j]), 0.f));
@@ -236,10 +255,28 @@ exact_scan_kernel(const T* __restrict__ x, const float* __restrict__ cb, const i
       }
       const int rr = rows_s[ty + 16 * i];
       if (tx == 0 && rr >= 0) {
-        idx_out[(int64_t)h * N + rr] = (int64_t)bidx[i] + idx_offset;
-        if (score_out) score_out[(int64_t)h * N + rr] = best[i];
+        if (kSplit) {
+          atomicMin(keys + (int64_t)h * N + rr, pack_key(best[i], bidx[i]));
+        } else {
+          idx_out[(int64_t)h * N + rr] = (int64_t)bidx[i] + idx_offset;
+          if (score_out) score_out[(int64_t)h * N + rr] = best[i];
+        }
       }
     }
+  }
+}
+
+// unpack the merged keys of the rescanned rows
+__global__ void rescan_finalize_kernel(const int* __restrict__ flag_list, const uint32_t* __restrict__ flag_cnt,
+                                       const unsigned long long* __restrict__ keys, int64_t N, int64_t idx_offset,
+                                       int64_t* __restrict__ idx_out, float* __restrict__ score_out) {
+  const int h = blockIdx.y;
+  const int64_t count = flag_cnt[h];
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < count; p += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t g = (int64_t)h * N + flag_list[(int64_t)h * N + p];
+    const unsigned long long key = keys[g];
+    idx_out[g] = (int64_t)(uint32_t)(key & 0xffffffffull) + idx_offset;
+    if (score_out) score_out[g] = unpack_score(key);
   }
 }
 
@@ -289,40 +326,50 @@ extern "C" int vqb_search(const void* x, int x_dtype, const float* codebook, con
   const int grid_scan = (int)((N + kER - 1) / kER < 4 * (int64_t)num_sms() ? (N + kER - 1) / kER : 4 * num_sms());
   if (!tc) {
     VQB_DISPATCH_DTYPE(x_dtype, T,
-      exact_scan_kernel<T><<<dim3((unsigned)grid_scan, (unsigned)H), 256, 0, st>>>(
-          (const T*)x, codebook, nullptr, nullptr, N, K, d, metric, idx_offset, idx_out, score_out, scal));
+      exact_scan_kernel<T, false><<<dim3((unsigned)grid_scan, (unsigned)H), 256, 0, st>>>(
+          (const T*)x, codebook, nullptr, nullptr, N, K, d, metric, idx_offset, idx_out, score_out, scal, 0, nullptr));
     VQB_LAUNCH_CHECK();
     return VQB_OK;
   }
 
   CacheLayout CL = cache_layout(H, K, d);
   const char* cbase = (const char*)cache;
-  __nv_bfloat16* xb = (__nv_bfloat16*)(w + SL.off_xb);
+  __half* xb = (__half*)(w + SL.off_xb);
+  float* xinv = (float*)(w + SL.off_xinv);
+  unsigned long long* keys = (unsigned long long*)(w + SL.off_keys);
   float* bias = (float*)(w + SL.off_bias);
   float* err = (float*)(w + SL.off_err);
   int rc;
   if (!prepared) {
-    rc = launch_prepare_latents(x, x_dtype, H * N, d, SL.dp, xb, scal, st);
+    rc = launch_prepare_latents(x, x_dtype, H * N, d, SL.dp, xb, xinv, scal, st);
     if (rc) return rc;
   }
   rc = launch_make_bias(cache, CL, H, K, metric, scal, bias, err, st);
   if (rc) return rc;
-  rc = launch_search_tc(xb, (const __nv_bfloat16*)(cbase + CL.off_cb), bias, H, N, K, SL.dp, w + SL.off_cand, scal, st);
+  rc = launch_search_tc(xb, xinv, (const __half*)(cbase + CL.off_cb), (const float*)(cbase + CL.off_hdr), bias, H, N, K,
+                        SL.dp, w + SL.off_cand, scal, st);
   if (rc) return rc;
   const int64_t total = H * N;
   VQB_DISPATCH_DTYPE(x_dtype, T,
     resolve_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
         (const T*)x, codebook, (const uint2*)(w + SL.off_cand), err, H, N, K, CL.Kp, d, metric, idx_offset,
-        idx_out, score_out, flag_list, cnt, scal));
+        idx_out, score_out, flag_list, cnt, keys, scal));
   VQB_LAUNCH_CHECK();
-  // flagged rows (count is device-side): fixed small grid, blocks exit at once when there is nothing to do
-  const int grid_flag = grid_scan < 2 * num_sms() ? grid_scan : 2 * num_sms();
+  // flagged rows (count is device-side): fixed grid, code range split over blockIdx.z so that even a handful of
+  // rows spreads over the whole chip; blocks exit at once when there is nothing to do
+  const int ksplit_codes = 512;
+  const int nsplit = (K + ksplit_codes - 1) / ksplit_codes;
+  int grid_rows = (2 * num_sms() + nsplit - 1) / nsplit;
+  if (grid_rows > grid_scan) grid_rows = grid_scan;
+  if (grid_rows < 1) grid_rows = 1;
+  VQB_REQUIRE(nsplit <= 65535, VQB_ERR_UNSUPPORTED, "codebook too large for the rescan grid");
   VQB_DISPATCH_DTYPE(x_dtype, T,
-    exact_scan_kernel<T><<<dim3((unsigned)grid_flag, (unsigned)H), 256, 0, st>>>(
-        (const T*)x, codebook, flag_list, cnt, N, K, d, metric, idx_offset, idx_out, score_out, scal));
+    exact_scan_kernel<T, true><<<dim3((unsigned)grid_rows, (unsigned)H, (unsigned)nsplit), 256, 0, st>>>(
+        (const T*)x, codebook, flag_list, cnt, N, K, d, metric, idx_offset, idx_out, score_out, scal, ksplit_codes,
+        keys));
   VQB_LAUNCH_CHECK();
-  uint32_t one = 1;
-  (void)one;
+  rescan_finalize_kernel<<<dim3(8, (unsigned)H), 256, 0, st>>>(flag_list, cnt, keys, N, idx_offset, idx_out, score_out);
+  VQB_LAUNCH_CHECK();
   return VQB_OK;
 }
 

@@ -4,7 +4,7 @@
 // utils/general.py:128-129 (argmax + one_hot) with ONE persistent kernel:
 //
 //   TMA (cp.async.bulk.tensor, 128B swizzle)  ->  smem ring      (warp 0, one lane)
-//   tcgen05.mma kind::f16, bf16 x bf16 -> fp32 in TMEM            (warp 1, one lane)
+//   tcgen05.mma kind::f16, fp16 x fp16 -> fp32 in TMEM            (warp 1, one lane)
 //   tcgen05.ld + bias + packed running top-2 per row              (warps 4..11)
 //
 // Per CTA: a 128-row tile of latents stays resident in smem (A operand, d/64 slabs of 16 KB);
@@ -14,7 +14,9 @@
 // With CLUSTER=2 the two CTAs of a cluster work on neighbouring row tiles and share every B
 // stage: each loads half of it and multicasts to both (halves L2->SM traffic).
 //
-// The scores are lower bounds  L_k = |c_k|^2/2 - E_k - x_b.c_b  (bias precomputed per search,
+// Operands are fp16 with exact power-of-two scales (per latent row, per codebook) that the epilogue
+// undoes with the same FFMA that adds the bias.
+// The scores are lower bounds  L_k = |c_k|^2/2 - E_k - x~.c~_k  (bias precomputed per search,
 // prepare.cu); each row keeps, for 8 disjoint column groups, the three smallest L (low 5 mantissa
 // bits carry the column id inside the group).  search_resolve.cu turns these 16 candidates into
 // the exact fp32 argmin or proves that it cannot and flags the row for an exact rescan.
@@ -87,8 +89,8 @@ __device__ __forceinline__ void tma_load_3d_mc(uint32_t dst, const CUtensorMap* 
       ::"r"(dst), "l"(map), "r"(bar), "h"(mask), "r"(c0), "r"(c1), "r"(c2), "l"(hint) : "memory");
 }
 
-// D[tmem] (+)= A[smem] . B[smem]^T, bf16 inputs, fp32 accumulate; issued by ONE thread.
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+// D[tmem] (+)= A[smem] . B[smem]^T, fp16 inputs, fp32 accumulate; issued by ONE thread.
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                           uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
@@ -111,10 +113,9 @@ __device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
 __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr) {
   return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
-// cute::UMMA::InstrDescriptor: c=f32 [4,6)=1, a=bf16 [7,10)=1, b=bf16 [10,13)=1, K-major both,
+// cute::UMMA::InstrDescriptor: c=f32 [4,6)=1, a=f16 [7,10)=0, b=f16 [10,13)=0, K-major both,
 // N>>3 at [17,23), M>>4 at [24,29)
-constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kBlockN >> 3) << 17) |
-                            ((uint32_t)(kBlockM >> 4) << 24);
+constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(kBlockN >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
 
 #define TMEM_LD32(taddr, r)                                                                                      \
   asm volatile(                                                                                                  \
@@ -159,14 +160,16 @@ __device__ __forceinline__ void top3_insert(float& M1, float& M2, float& M3, int
 constexpr int kThreads = 384;          // 12 warps: 0 TMA, 1 MMA, 2 TMEM alloc, 3 spare, 4..11 epilogue
 constexpr int kEpiWarp0 = 4;
 constexpr int kNumEpiWarps = 8;
-constexpr int kSlabBytes = kBlockM * kBlockK * 2;     // 16 KB: 128 rows x 64 bf16
-constexpr int kStageBytes = kBlockN * kBlockK * 2;    // 32 KB: 256 codes x 64 bf16
+constexpr int kSlabBytes = kBlockM * kBlockK * 2;     // 16 KB: 128 rows x 64 fp16
+constexpr int kStageBytes = kBlockN * kBlockK * 2;    // 32 KB: 256 codes x 64 fp16
 constexpr int kMaxKB = 8;                              // d_pad <= 512
 constexpr int kMaxStages = 6;
 constexpr int kTmemCols = 512;
 
 struct SearchParams {
   const float* bias;   // [H][Kp]
+  const float* xinv;   // [H][N]   1 / s_row
+  const float* chdr;   // [H][4]   {s_c, 1/s_c, ..}
   void* cand;          // [H][N][24] {f32 key, i32 code}
   uint32_t* scal;
   int64_t N;           // rows per codebook
@@ -290,7 +293,7 @@ search_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
 #pragma unroll
             for (int kk = 0; kk < kBlockK / 16; ++kk) {
               // +32 B per 16-element k step inside the 128B swizzle atom = +2 in the (addr>>4) field
-              umma_bf16(d_tmem, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), kIdesc,
+              umma_f16(d_tmem, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), kIdesc,
                         (kb | kk) != 0 ? 1u : 0u);
             }
             if (CLUSTER > 1) umma_commit_mc(smem_u32(&bars->empty[stage]), (uint16_t)((1u << CLUSTER) - 1u));
@@ -319,6 +322,8 @@ search_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
 #pragma unroll
       for (int c = 0; c < 4; ++c) { M1[c] = INF; M2[c] = INF; M3[c] = INF; C1[c] = -1; C2[c] = -1; C3[c] = -1; }
       const float* bias_h = P.bias + (size_t)h * P.Kp + half * 128;
+      // acc = (x s_row).(c s_c)  ->  score = bias - acc / (s_row s_c): one FFMA per element
+      const float ninv = row < P.N ? -(P.xinv[(size_t)h * P.N + row] * P.chdr[h * 4 + 1]) : 0.f;
 
       for (int nt = 0; nt < P.NT; ++nt) {
         float a1[4], a2[4];
@@ -341,10 +346,10 @@ search_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
           for (int i = 0; i < 8; ++i) {
             // column j = 4*i + c  ->  class c, id-in-class (ch*8 + i) in the low 5 mantissa bits
             const uint32_t id = (uint32_t)(ch * 8 + i);
-            key[4 * i + 0] = __uint_as_float((__float_as_uint(__uint_as_float(r[4 * i + 0]) + b[i].x) & 0xFFFFFFE0u) | id);
-            key[4 * i + 1] = __uint_as_float((__float_as_uint(__uint_as_float(r[4 * i + 1]) + b[i].y) & 0xFFFFFFE0u) | id);
-            key[4 * i + 2] = __uint_as_float((__float_as_uint(__uint_as_float(r[4 * i + 2]) + b[i].z) & 0xFFFFFFE0u) | id);
-            key[4 * i + 3] = __uint_as_float((__float_as_uint(__uint_as_float(r[4 * i + 3]) + b[i].w) & 0xFFFFFFE0u) | id);
+            key[4 * i + 0] = __uint_as_float((__float_as_uint(fmaf(__uint_as_float(r[4 * i + 0]), ninv, b[i].x)) & 0xFFFFFFE0u) | id);
+            key[4 * i + 1] = __uint_as_float((__float_as_uint(fmaf(__uint_as_float(r[4 * i + 1]), ninv, b[i].y)) & 0xFFFFFFE0u) | id);
+            key[4 * i + 2] = __uint_as_float((__float_as_uint(fmaf(__uint_as_float(r[4 * i + 2]), ninv, b[i].z)) & 0xFFFFFFE0u) | id);
+            key[4 * i + 3] = __uint_as_float((__float_as_uint(fmaf(__uint_as_float(r[4 * i + 3]), ninv, b[i].w)) & 0xFFFFFFE0u) | id);
           }
 #pragma unroll
           for (int i = 0; i < 8; i += 2) {
@@ -413,7 +418,7 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// 3-D bf16 tensor (inner, rows, heads), box (64, box_rows, 1), 128B swizzle, OOB rows read as zero
+// 3-D fp16 tensor (inner, rows, heads), box (64, box_rows, 1), 128B swizzle, OOB rows read as zero
 static int make_map(CUtensorMap* m, const void* base, int inner, int64_t rows, int64_t heads, int box_rows) {
   EncodeTiledFn enc = get_encode_fn();
   VQB_REQUIRE(enc != nullptr, VQB_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
@@ -421,7 +426,7 @@ static int make_map(CUtensorMap* m, const void* base, int inner, int64_t rows, i
   cuuint64_t strides[2] = {(cuuint64_t)inner * 2, (cuuint64_t)inner * 2 * (cuuint64_t)rows};
   cuuint32_t box[3] = {(cuuint32_t)kBlockK, (cuuint32_t)box_rows, 1};
   cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   VQB_REQUIRE(r == CUDA_SUCCESS, VQB_ERR_CUDA, "cuTensorMapEncodeTiled failed: %d (inner=%d rows=%lld heads=%lld)",
@@ -456,8 +461,8 @@ static int launch_impl(const CUtensorMap& mx, const CUtensorMap& mc, const Searc
   return VQB_OK;
 }
 
-int launch_search_tc(const __nv_bfloat16* xb, const __nv_bfloat16* cb, const float* bias, int64_t H, int64_t N,
-                     int K, int dp, void* cand, uint32_t* scal, cudaStream_t st) {
+int launch_search_tc(const __half* xb, const float* xinv, const __half* cb, const float* chdr, const float* bias,
+                     int64_t H, int64_t N, int K, int dp, void* cand, uint32_t* scal, cudaStream_t st) {
   const int Kp = k_pad(K);
   VQB_REQUIRE(dp % kBlockK == 0 && dp / kBlockK <= kMaxKB, VQB_ERR_UNSUPPORTED, "d_pad %d unsupported by the TC path", dp);
   VQB_REQUIRE(N < (1ll << 31) - kBlockM, VQB_ERR_UNSUPPORTED, "N too large for TMA coordinates");
@@ -475,7 +480,7 @@ int launch_search_tc(const __nv_bfloat16* xb, const __nv_bfloat16* cb, const flo
   int cluster = (g_cluster_override == 1 || g_cluster_override == 2) ? g_cluster_override : (MT >= 2 * num_sms ? 2 : 1);
 
   SearchParams P;
-  P.bias = bias; P.cand = cand; P.scal = scal; P.N = N; P.Kp = Kp; P.H = (int)H;
+  P.bias = bias; P.xinv = xinv; P.chdr = chdr; P.cand = cand; P.scal = scal; P.N = N; P.Kp = Kp; P.H = (int)H;
   P.KB = dp / kBlockK;
   P.NT = Kp / kBlockN;
   const size_t fixed = (size_t)P.KB * kSlabBytes + sizeof(Barriers);
