@@ -51,9 +51,12 @@ extern "C" {
 /* vqb_search flags */
 #define VQB_SEARCH_LATENTS_PREPARED 1  /* ws already holds bf16 latents + row stats (written by vqb_rvq_level) */
 #define VQB_SEARCH_FORCE_EXACT      2  /* skip the tensor-core pass: fp32/fp64 CUDA-core scan of every code */
+#define VQB_SEARCH_TIMING           4  /* bracket the tensor-core kernel with CUDA events (see vqb_search_timing) */
 
 int         vqb_version(void);
 const char* vqb_last_error(void);
+/* number of kernels this library has launched in this process (measurement aid for bench.py) */
+int64_t     vqb_launch_count(void);
 
 /* ---- derived codebook cache ---------------------------------------------------------
  * bf16 (negated, padded) copy of the codebook for the tensor-core pass + per-code norms and
@@ -81,6 +84,12 @@ int    vqb_search(const void* x, int x_dtype, const float* codebook, const void*
 /* debug/statistics of the last vqb_search on this ws: host_out[0]=rows re-ranked,
  * [1]=rows rescanned exactly, [2]=tensor-core pass used (0/1).  Synchronises `stream`. */
 int    vqb_search_stats(const void* ws, int64_t* host_out3, void* stream);
+
+/* Durations of the tensor-core kernel for searches made with VQB_SEARCH_TIMING: the events are recorded on
+ * the search's own stream around that one launch.  Returns how many timed searches have been recorded since
+ * the last call and writes up to `cap` of their durations (ms, oldest first) to host_ms; synchronises on the
+ * recorded events and resets the ring (64 slots). */
+int    vqb_search_timing(float* host_ms, int cap);
 
 /* ---- l2 normalisation of rows (transform_input="l2norm") ------------------------------
  * Replaces vector_quantize_pytorch.py:221 -> utils/losses.py:19 (F.normalize, eps 1e-12). */

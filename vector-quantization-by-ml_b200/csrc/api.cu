@@ -4,6 +4,7 @@
 #include "common.cuh"
 
 namespace vqb {
+int64_t g_launch_count = 0;
 static thread_local char g_err[1024] = "";
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -15,3 +16,4 @@ void set_error(const char* fmt, ...) {
 
 extern "C" int vqb_version(void) { return VQB_VERSION; }
 extern "C" const char* vqb_last_error(void) { return vqb::g_err; }
+extern "C" int64_t vqb_launch_count(void) { return vqb::g_launch_count; }

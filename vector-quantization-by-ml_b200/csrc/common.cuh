@@ -31,7 +31,12 @@ void set_error(const char* fmt, ...);
     }                                                                                   \
   } while (0)
 
-#define VQB_LAUNCH_CHECK() VQB_CUDA_TRY(cudaGetLastError())
+extern int64_t g_launch_count;   // every kernel launch is followed by VQB_LAUNCH_CHECK()
+#define VQB_LAUNCH_CHECK()                 \
+  do {                                     \
+    ++vqb::g_launch_count;                 \
+    VQB_CUDA_TRY(cudaGetLastError());      \
+  } while (0)
 
 // ---- geometry shared by prepare / search / resolve ----------------------------------------
 constexpr int kBlockM = 128;   // latent rows per CTA tile (TMEM lanes)
@@ -156,7 +161,7 @@ int launch_prepare_latents(const void* x, int x_dtype, int64_t rows, int d, int 
 int launch_make_bias(const void* cache, const CacheLayout& CL, int64_t H, int K, int metric,
                      const uint32_t* scal, float* bias, float* err, cudaStream_t st);
 int launch_search_tc(const __half* xb, const float* xinv, const __half* cb, const float* chdr, const float* bias,
-                     int64_t H, int64_t N, int K, int dp, void* cand, uint32_t* scal, cudaStream_t st);
+                     int64_t H, int64_t N, int K, int dp, void* cand, uint32_t* scal, bool timing, cudaStream_t st);
 
 // power-of-two scale that brings a magnitude bound m below 2^14 (fp16 max is 65504)
 __host__ __device__ inline float pow2_scale(float m) {

@@ -347,7 +347,7 @@ extern "C" int vqb_search(const void* x, int x_dtype, const float* codebook, con
   rc = launch_make_bias(cache, CL, H, K, metric, scal, bias, err, st);
   if (rc) return rc;
   rc = launch_search_tc(xb, xinv, (const __half*)(cbase + CL.off_cb), (const float*)(cbase + CL.off_hdr), bias, H, N, K,
-                        SL.dp, w + SL.off_cand, scal, st);
+                        SL.dp, w + SL.off_cand, scal, (flags & VQB_SEARCH_TIMING) != 0, st);
   if (rc) return rc;
   const int64_t total = H * N;
   VQB_DISPATCH_DTYPE(x_dtype, T,

@@ -436,9 +436,15 @@ static int make_map(CUtensorMap* m, const void* base, int inner, int64_t rows, i
 
 static int g_cluster_override = -1;   // test hook (env VQB_CLUSTER): 1 or 2
 
+// timing ring for VQB_SEARCH_TIMING: event pairs recorded on the search stream around the kernel launch
+constexpr int kTimingSlots = 64;
+static cudaEvent_t g_ev0[kTimingSlots], g_ev1[kTimingSlots];
+static bool g_ev_made = false;
+static int g_ev_count = 0;
+
 template <int CLUSTER>
 static int launch_impl(const CUtensorMap& mx, const CUtensorMap& mc, const SearchParams& P, size_t smem_bytes,
-                       int grid, cudaStream_t st) {
+                       int grid, bool timing, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
     VQB_CUDA_TRY(cudaFuncSetAttribute(search_tc_kernel<CLUSTER>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -457,12 +463,26 @@ static int launch_impl(const CUtensorMap& mx, const CUtensorMap& mc, const Searc
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  int slot = -1;
+  if (timing) {
+    if (!g_ev_made) {
+      for (int i = 0; i < kTimingSlots; ++i) {
+        VQB_CUDA_TRY(cudaEventCreate(&g_ev0[i]));
+        VQB_CUDA_TRY(cudaEventCreate(&g_ev1[i]));
+      }
+      g_ev_made = true;
+    }
+    if (g_ev_count < kTimingSlots) slot = g_ev_count++;
+  }
+  if (slot >= 0) VQB_CUDA_TRY(cudaEventRecord(g_ev0[slot], st));
   VQB_CUDA_TRY(cudaLaunchKernelEx(&cfg, search_tc_kernel<CLUSTER>, mx, mc, P));
+  ++g_launch_count;
+  if (slot >= 0) VQB_CUDA_TRY(cudaEventRecord(g_ev1[slot], st));
   return VQB_OK;
 }
 
 int launch_search_tc(const __half* xb, const float* xinv, const __half* cb, const float* chdr, const float* bias,
-                     int64_t H, int64_t N, int K, int dp, void* cand, uint32_t* scal, cudaStream_t st) {
+                     int64_t H, int64_t N, int K, int dp, void* cand, uint32_t* scal, bool timing, cudaStream_t st) {
   const int Kp = k_pad(K);
   VQB_REQUIRE(dp % kBlockK == 0 && dp / kBlockK <= kMaxKB, VQB_ERR_UNSUPPORTED, "d_pad %d unsupported by the TC path", dp);
   VQB_REQUIRE(N < (1ll << 31) - kBlockM, VQB_ERR_UNSUPPORTED, "N too large for TMA coordinates");
@@ -500,8 +520,22 @@ int launch_search_tc(const __half* xb, const float* xinv, const __half* cb, cons
   if (rc) return rc;
   rc = make_map(&mc, cb, dp, Kp, H, kBlockN / cluster);
   if (rc) return rc;
-  if (cluster == 2) return launch_impl<2>(mx, mc, P, smem_bytes, grid, st);
-  return launch_impl<1>(mx, mc, P, smem_bytes, grid, st);
+  if (cluster == 2) return launch_impl<2>(mx, mc, P, smem_bytes, grid, timing, st);
+  return launch_impl<1>(mx, mc, P, smem_bytes, grid, timing, st);
+}
+
+int search_timing(float* host_ms, int cap) {
+  const int n = g_ev_count;
+  for (int i = 0; i < n; ++i) {
+    VQB_CUDA_TRY(cudaEventSynchronize(g_ev1[i]));
+    float ms = 0.f;
+    VQB_CUDA_TRY(cudaEventElapsedTime(&ms, g_ev0[i], g_ev1[i]));
+    if (i < cap && host_ms) host_ms[i] = ms;
+  }
+  g_ev_count = 0;
+  return n;
 }
 
 }  // namespace vqb
+
+extern "C" int vqb_search_timing(float* host_ms, int cap) { return vqb::search_timing(host_ms, cap); }

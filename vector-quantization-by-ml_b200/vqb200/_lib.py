@@ -17,6 +17,7 @@ VQB_F32, VQB_BF16, VQB_F16 = 0, 1, 2
 VQB_EUCLID, VQB_DOT = 0, 1
 SEARCH_LATENTS_PREPARED = 1
 SEARCH_FORCE_EXACT = 2
+SEARCH_TIMING = 4
 
 _DTYPES = {torch.float32: VQB_F32, torch.bfloat16: VQB_BF16, torch.float16: VQB_F16}
 
@@ -26,6 +27,8 @@ _p, _i64, _i32, _sz, _f32, _f64 = C.c_void_p, C.c_int64, C.c_int, C.c_size_t, C.
 SIGNATURES = {
     "vqb_version": (_i32, []),
     "vqb_last_error": (C.c_char_p, []),
+    "vqb_launch_count": (_i64, []),
+    "vqb_search_timing": (_i32, [_p, _i32]),
     "vqb_codebook_cache_bytes": (_sz, [_i64, _i32, _i32]),
     "vqb_prepare_codebook": (_i32, [_p, _i64, _i32, _i32, _i32, _p, _sz, _p]),
     "vqb_search_workspace_bytes": (_sz, [_i64, _i64, _i32, _i32]),

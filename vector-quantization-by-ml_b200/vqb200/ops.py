@@ -27,6 +27,23 @@ def workspace(kind: str, nbytes: int, device: torch.device) -> torch.Tensor:
     return buf
 
 
+TIME_SEARCH_KERNEL = False   # bench.py: bracket the tensor-core kernel with CUDA events on its stream
+
+
+def search_kernel_times_ms():
+    """Durations (ms) of the tensor-core kernel of the searches made since the last call (needs TIME_SEARCH_KERNEL)."""
+    import ctypes as C
+    buf = (C.c_float * 64)()
+    n = L.lib().vqb_search_timing(C.cast(buf, C.c_void_p), 64)
+    if n < 0:
+        L.check(n, "vqb_search_timing")
+    return [float(buf[i]) for i in range(min(n, 64))]
+
+
+def launch_count() -> int:
+    return int(L.lib().vqb_launch_count())
+
+
 def release_workspaces() -> None:
     _WS.clear()
 
@@ -75,7 +92,8 @@ def search(x: torch.Tensor, embeddings: torch.Tensor, cache: Optional[torch.Tens
     idx = torch.empty((H, N), dtype=torch.int64, device=dev)
     score = torch.empty((H, N), dtype=torch.float32, device=dev) if want_score else None
     ws = workspace("search", L.lib().vqb_search_workspace_bytes(H, N, K, d), dev)
-    flags = (L.SEARCH_LATENTS_PREPARED if latents_prepared else 0) | (L.SEARCH_FORCE_EXACT if force_exact else 0)
+    flags = (L.SEARCH_LATENTS_PREPARED if latents_prepared else 0) | (L.SEARCH_FORCE_EXACT if force_exact else 0) \
+        | (L.SEARCH_TIMING if TIME_SEARCH_KERNEL else 0)
     L.check(L.lib().vqb_search(L.ptr(x), L.dtype_code(x), L.ptr(embeddings), L.ptr(cache), _metric(use_cosine_sim),
                                H, N, K, d, int(idx_offset), L.ptr(idx), L.ptr(score), flags, L.ptr(ws), ws.numel(),
                                L.stream_ptr(dev)), "vqb_search")
