@@ -1,0 +1,60 @@
+"""Per-kernel breakdown of one full training step (VectorQuantize.forward) at a named config.
+usage: python tools/profile_step.py [c2|c3|c4|c1]"""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "vector-quantization-by-ml_b200"))
+import torch
+from torch.profiler import ProfilerActivity, profile
+
+from vqb200 import CodebookParams, KmeansParameters, ResidualVQ, VectorQuantize, ops
+
+cfg = sys.argv[1] if len(sys.argv) > 1 else "c2"
+dev = torch.device("cuda:0")
+torch.manual_seed(0)
+g = torch.Generator(device=dev).manual_seed(1)
+
+
+def seed_codebook(cb, scale=0.5, l2=False):
+    c = torch.randn(cb.embeddings.shape, generator=g, device=dev) * scale
+    if l2:
+        c = torch.nn.functional.normalize(c, dim=-1)
+    cb.embeddings.copy_(c); cb.embed_avg.copy_(c); cb.cluster_size.fill_(1.0); cb.invalidate_cache()
+
+
+if cfg == "c2":
+    mod = VectorQuantize(dim=256, codebook_params=CodebookParams(dim=256, codebook_size=8192)).to(dev)
+    seed_codebook(mod._codebook)
+    x = torch.randn(1024, 1024, 256, generator=g, device=dev).bfloat16()
+elif cfg == "c3":
+    mod = VectorQuantize(dim=512, codebook_params=CodebookParams(dim=512, codebook_size=16384, use_cosine_sim=True,
+                         transform_input="l2norm", weights_regularization="l2norm")).to(dev)
+    seed_codebook(mod._codebook, l2=True)
+    x = torch.randn(512, 1024, 512, generator=g, device=dev)
+elif cfg == "c4":
+    mod = ResidualVQ(dim=512, num_quantizers=8, codebook_params=CodebookParams(dim=512, codebook_size=1024)).to(dev)
+    for i, l in enumerate(mod.layers):
+        seed_codebook(l._codebook, scale=0.5 / (1.5 ** i))
+    x = torch.randn(64, 4096, 512, generator=g, device=dev)
+else:
+    mod = VectorQuantize(dim=256, codebook_params=CodebookParams(dim=256, codebook_size=512, threshold_ema_dead_code=0)).to(dev)
+    x = torch.randn(1, 1024, 256, generator=g, device=dev)
+mod.train()
+with torch.no_grad():
+    for _ in range(3):
+        mod(x)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        mod(x)
+    e1.record()
+    torch.cuda.synchronize()
+    print(f"{cfg}: {e0.elapsed_time(e1) / 5:.3f} ms per step", flush=True)
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        for _ in range(3):
+            mod(x)
+        torch.cuda.synchronize()
+print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=25, max_name_column_width=64), flush=True)

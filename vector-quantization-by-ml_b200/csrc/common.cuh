@@ -85,6 +85,7 @@ struct SearchLayout {
   size_t off_keys;    // u64  [H][N]      packed (score, index) min-keys of rows being rescanned
   size_t off_cand;    // {f32 key, i32 code} [H][N][kNumCand]
   size_t off_flag;    // i32 [H*N] flagged row list
+  size_t off_rr;      // i32 [H*N] rows queued for the warp-per-row re-rank (length in scal[3])
   size_t off_bias;    // f32 [H][Kp]  lower-bound bias  |c|^2/2 - E_k  (needs the row stats, so per search)
   size_t off_err;     // f32 [H][Kp]  E_k: bound on |exact score - bf16 tensor-core score| for code k
   size_t total;
@@ -100,6 +101,7 @@ inline SearchLayout search_layout(int64_t H, int64_t N, int K, int d) {
   L.off_keys = o; o += align_up((size_t)H * N * 8);
   L.off_cand = o; o += align_up((size_t)H * N * kNumCand * 8);
   L.off_flag = o; o += align_up((size_t)H * N * 4);
+  L.off_rr = o;   o += align_up((size_t)H * N * 4);
   L.off_bias = o; o += align_up((size_t)H * k_pad(K) * 4);
   L.off_err = o;  o += align_up((size_t)H * k_pad(K) * 4);
   L.total = o;
@@ -131,6 +133,35 @@ template <> __device__ __forceinline__ float4 load4<__half>(const __half* p) {
   __half2 a = *reinterpret_cast<__half2*>(&r.x), b = *reinterpret_cast<__half2*>(&r.y);
   float2 fa = __half22float2(a), fb = __half22float2(b);
   return make_float4(fa.x, fa.y, fb.x, fb.y);
+}
+
+// load 8 consecutive elements (32B-aligned for f32, 16B for 16-bit types)
+struct F8 { float v[8]; };
+template <typename T> __device__ __forceinline__ F8 load8(const T* p);
+template <> __device__ __forceinline__ F8 load8<float>(const float* p) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  F8 o; o.v[0] = a.x; o.v[1] = a.y; o.v[2] = a.z; o.v[3] = a.w; o.v[4] = b.x; o.v[5] = b.y; o.v[6] = b.z; o.v[7] = b.w;
+  return o;
+}
+template <> __device__ __forceinline__ F8 load8<__nv_bfloat16>(const __nv_bfloat16* p) {
+  const uint4 r = __ldg(reinterpret_cast<const uint4*>(p));
+  F8 o;
+  o.v[0] = __uint_as_float(r.x << 16); o.v[1] = __uint_as_float(r.x & 0xffff0000u);
+  o.v[2] = __uint_as_float(r.y << 16); o.v[3] = __uint_as_float(r.y & 0xffff0000u);
+  o.v[4] = __uint_as_float(r.z << 16); o.v[5] = __uint_as_float(r.z & 0xffff0000u);
+  o.v[6] = __uint_as_float(r.w << 16); o.v[7] = __uint_as_float(r.w & 0xffff0000u);
+  return o;
+}
+template <> __device__ __forceinline__ F8 load8<__half>(const __half* p) {
+  const uint4 r = __ldg(reinterpret_cast<const uint4*>(p));
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+  F8 o;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+    o.v[2 * i] = f.x; o.v[2 * i + 1] = f.y;
+  }
+  return o;
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

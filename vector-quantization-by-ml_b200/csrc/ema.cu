@@ -164,6 +164,56 @@ ema_segsum_kernel(const T* __restrict__ x, const int64_t* __restrict__ idx, cons
   const int k_lo = lane < n ? (int)idxh[r_lo] : -1;
   const int k_hi = lane + 32 < n ? (int)idxh[r_hi] : -1;
 
+  if ((d & 7) == 0) {
+    // column blocks of 256 (8 per lane: one 16-byte load per row for 16-bit latents)
+    for (int c0 = 0; c0 < d; c0 += 256) {
+      const int j = c0 + lane * 8;
+      const bool on = j < d;
+      long long a[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) a[e] = 0;
+      int cur = -1;
+      for (int i0 = 0; i0 < n; i0 += 4) {
+        F8 v[4];
+        int kk[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {            // 4 independent row loads in flight
+          const int i = i0 + u;
+          const int r = __shfl_sync(0xffffffffu, i < 32 ? r_lo : r_hi, i & 31);
+          kk[u] = __shfl_sync(0xffffffffu, i < 32 ? k_lo : k_hi, i & 31);
+          if (i < n && on) v[u] = load8<T>(xh + (int64_t)r * d + j);
+          else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[u].v[e] = 0.f;
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (i0 + u < n) {
+            if (kk[u] != cur) {                   // warp-uniform: code boundary -> flush
+              if (cur >= 0 && on) {
+                unsigned long long* o = acch + (int64_t)cur * d + j;
+#pragma unroll
+                for (int e = 0; e < 8; ++e) if (a[e]) atomicAdd(o + e, (unsigned long long)a[e]);
+              }
+#pragma unroll
+              for (int e = 0; e < 8; ++e) a[e] = 0;
+              cur = kk[u];
+            }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) a[e] += __float2ll_rn(v[u].v[e] * scale);
+          }
+        }
+      }
+      if (cur >= 0 && on) {
+        unsigned long long* o = acch + (int64_t)cur * d + j;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) if (a[e]) atomicAdd(o + e, (unsigned long long)a[e]);
+      }
+    }
+    return;
+  }
+
   for (int c0 = 0; c0 < d; c0 += 128) {        // column block of 128 (4 per lane)
     const int j = c0 + lane * 4;
     const bool on = j < d;

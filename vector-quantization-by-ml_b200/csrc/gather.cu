@@ -63,7 +63,22 @@ gather_st_loss_kernel(const T* __restrict__ x, const float* __restrict__ cb, con
     const float* cr = cb + (h * K + code) * (int64_t)d;
     float* qr = q + row * (int64_t)d;
     sq = 0.f;
-    if ((d & 3) == 0) {
+    if ((d & 7) == 0) {
+      for (int j = lane * 8; j < d; j += 256) {
+        const F8 xv = load8<T>(xr + j);
+        const float4 c0 = __ldg(reinterpret_cast<const float4*>(cr + j)), c1 = __ldg(reinterpret_cast<const float4*>(cr + j) + 1);
+        const float cv[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+        float o[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float df = __fsub_rn(cv[e], xv.v[e]);
+          o[e] = training ? __fadd_rn(xv.v[e], df) : cv[e];
+          if (kLoss) sq = fmaf(df, df, sq);
+        }
+        __stcs(reinterpret_cast<float4*>(qr + j), make_float4(o[0], o[1], o[2], o[3]));
+        __stcs(reinterpret_cast<float4*>(qr + j) + 1, make_float4(o[4], o[5], o[6], o[7]));
+      }
+    } else if ((d & 3) == 0) {
       for (int j = lane * 4; j < d; j += 128) {
         const float4 xv = load4<T>(xr + j);
         const float4 cv = __ldg(reinterpret_cast<const float4*>(cr + j));

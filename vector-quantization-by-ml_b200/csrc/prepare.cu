@@ -73,13 +73,21 @@ __global__ void prepare_latents_kernel(const T* __restrict__ x, int64_t rows, in
   if (row < rows) {
     const T* xr = x + row * (int64_t)d;
     __half* o = xb + row * (int64_t)dp;
-    const bool vec = (d & 3) == 0;
-    // pass 1: row max (the second pass re-reads the row from L1/L2)
+    const bool vec = (d & 7) == 0;
+    // the row stays in registers between the max pass and the conversion pass (d_pad <= 512: 2 x 8 per lane)
+    F8 keep[2];
     float m = 0.f;
     if (vec) {
-      for (int j = lane * 4; j < d; j += 128) {
-        const float4 v = load4<T>(xr + j);
-        m = fmaxf(fmaxf(fmaxf(m, fabsf(v.x)), fmaxf(fabsf(v.y), fabsf(v.z))), fabsf(v.w));
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        const int j = lane * 8 + 256 * t;
+        if (j < d) keep[t] = load8<T>(xr + j);
+        else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) keep[t].v[e] = 0.f;
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) m = fmaxf(m, fabsf(keep[t].v[e]));
       }
     } else {
       for (int j = lane; j < d; j += 32) m = fmaxf(m, fabsf(to_f32<T>(xr[j])));
@@ -89,18 +97,23 @@ __global__ void prepare_latents_kernel(const T* __restrict__ x, int64_t rows, in
     const float s = pow2_scale(m), is = 1.f / s;
     if (lane == 0) xinv[row] = is;
     if (vec) {
-      for (int j = lane * 4; j < dp; j += 128) {
-        const float4 v = j < d ? load4<T>(xr + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-        const __half2 h0 = __floats2half2_rn(v.x * s, v.y * s), h1 = __floats2half2_rn(v.z * s, v.w * s);
-        const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
-        uint2 pk;
-        pk.x = *reinterpret_cast<const uint32_t*>(&h0);
-        pk.y = *reinterpret_cast<const uint32_t*>(&h1);
-        *reinterpret_cast<uint2*>(o + j) = pk;
-        const float b0 = f0.x * is, b1 = f0.y * is, b2 = f1.x * is, b3 = f1.y * is;
-        n2 += b0 * b0 + b1 * b1 + b2 * b2 + b3 * b3;
-        const float e0 = v.x - b0, e1 = v.y - b1, e2 = v.z - b2, e3 = v.w - b3;
-        r2 += e0 * e0 + e1 * e1 + e2 * e2 + e3 * e3;
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        const int j = lane * 8 + 256 * t;
+        if (j >= dp) break;
+        uint32_t pk[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float v0 = keep[t].v[2 * e], v1 = keep[t].v[2 * e + 1];
+          const __half2 h = __floats2half2_rn(v0 * s, v1 * s);
+          const float2 f = __half22float2(h);
+          pk[e] = *reinterpret_cast<const uint32_t*>(&h);
+          const float b0 = f.x * is, b1 = f.y * is;
+          n2 += b0 * b0 + b1 * b1;
+          const float e0 = v0 - b0, e1 = v1 - b1;
+          r2 += e0 * e0 + e1 * e1;
+        }
+        *reinterpret_cast<uint4*>(o + j) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
       }
     } else {
       for (int j = lane; j < dp; j += 32) {
@@ -133,6 +146,7 @@ __global__ void prepare_latents_kernel(const T* __restrict__ x, int64_t rows, in
 
 int launch_prepare_latents(const void* x, int x_dtype, int64_t rows, int d, int dp,
                            __half* xb, float* xinv, uint32_t* scal, cudaStream_t st) {
+  VQB_REQUIRE(dp <= 512, VQB_ERR_UNSUPPORTED, "prepare_latents: d_pad %d > 512", dp);
   const int warps = 8;
   const int64_t blocks = (rows + warps - 1) / warps;
   VQB_REQUIRE(blocks < (1ll << 31), VQB_ERR_UNSUPPORTED, "too many latent rows: %lld", (long long)rows);

@@ -7,12 +7,16 @@
 //   The kernel stores L_k = a_k (already lowered by E_k): L_k <= e_k <= L_k + 2 E_k.
 //   With j = argmin_k L_k the true argmin k* satisfies L_k* <= e_k* <= e_j <= L_j + 2 E_j, so
 //   every possible winner has L <= thr := L_j + 2 E_j (+ slack for the 5 id bits packed into L).
-//   The epilogue keeps, per 32-column group of every N tile, the two smallest L, and per class
-//   (8 per row) the three smallest of those.  Therefore a possible winner is missing only if
+//   The epilogue keeps, per 64-column group (one class of one column half of a pair of N tiles), the two
+//   smallest L, and per class (8 per row) the three smallest of those.  Therefore a possible winner is missing only if
 //     (i)  the third entry of some class is <= thr (a fourth could exist)  -> full exact rescan, or
-//     (ii) two entries <= thr come from the same 32-column group (a third could hide there)
-//                                                                          -> rescan those 32 columns.
+//     (ii) two entries <= thr come from the same 64-column group (a third could hide there)
+//                                                                          -> rescan those 64 columns.
 //   Both are detected here; neither is assumed away.
+//   (x_b, c_bk above stand for the scaled-fp16 values x~ = fp16(x s_row)/s_row, c~ = fp16(c s_c)/s_c.)
+//
+// Two phases: a streaming one-thread-per-row classification (accept / queue / flag), then one warp per queued
+// row where lane i evaluates candidate i exactly.
 //
 // "Exact" score = the reference's recipe evaluated with fp64 accumulation:
 //   euclid: sqrtf(max(float(|x|^2 + |c|^2 - 2 x.c), 0))   dot: float(-x.c); lowest index wins ties.
@@ -61,94 +65,162 @@ __device__ __forceinline__ float exact_score(const T* __restrict__ xr, const flo
   return sqrtf(fmaxf(d2, 0.f));
 }
 
-// one thread per row
-template <typename T>
+constexpr float kPackSlack = 6.2e-5f;   // 2 keys x 2^-17 (6 id bits) + fma rounding, with margin
+
+// candidate bookkeeping shared by both resolve phases ------------------------------------------------
+struct RowCands {
+  float key[kNumCand];
+  int code[kNumCand];
+  float thr;
+  int c1;
+  int ncand;
+  bool full_rescan;   // hazard (i)
+  bool local_rescan;  // hazard (ii) somewhere
+};
+
+__device__ __forceinline__ void load_cands(const uint2* __restrict__ cand, int64_t gid, int K, int Kp, int64_t h,
+                                           const float* __restrict__ err, RowCands& R) {
+  const uint4* c4 = reinterpret_cast<const uint4*>(cand + gid * kNumCand);
+#pragma unroll
+  for (int i = 0; i < kNumCand / 2; ++i) {
+    const uint4 v = __ldg(c4 + i);
+    R.key[2 * i] = __uint_as_float(v.x); R.code[2 * i] = (int)v.y;
+    R.key[2 * i + 1] = __uint_as_float(v.z); R.code[2 * i + 1] = (int)v.w;
+  }
+  float m1 = __int_as_float(0x7f800000);
+  int c1 = -1;
+#pragma unroll
+  for (int i = 0; i < kNumCand; ++i) {
+    const bool valid = R.code[i] >= 0 && R.code[i] < K;
+    if (!valid) R.key[i] = __int_as_float(0x7f800000);
+    if (valid && R.key[i] < m1) { m1 = R.key[i]; c1 = R.code[i]; }
+  }
+  const float E1 = c1 >= 0 ? err[h * Kp + c1] : 0.f;
+  // 2 E_j, plus the 6 packed id bits (<= 2^-17 relative per key) and the bias fma rounding
+  R.thr = m1 + 2.f * E1 + (fabsf(m1) + E1) * kPackSlack;
+  R.c1 = c1;
+  R.ncand = 0;
+  R.full_rescan = c1 < 0;
+  R.local_rescan = false;
+#pragma unroll
+  for (int g = 0; g < 8; ++g) {
+    const float k0 = R.key[3 * g], k1 = R.key[3 * g + 1], k2 = R.key[3 * g + 2];
+    if (k0 <= R.thr) ++R.ncand;
+    if (k1 <= R.thr) {
+      ++R.ncand;
+      if ((R.code[3 * g] >> 9) == (R.code[3 * g + 1] >> 9)) R.local_rescan = true;   // (ii)
+    }
+    if (k2 <= R.thr) { ++R.ncand; R.full_rescan = true; }                            // (i)
+  }
+}
+
+// phase 1, one thread per row, pure streaming: accept the unique candidate, or queue the row for the
+// warp-per-row re-rank (phase 2), or flag it for the exact rescan
 __global__ void __launch_bounds__(256)
-resolve_kernel(const T* __restrict__ x, const float* __restrict__ cb, const uint2* __restrict__ cand,
-               const float* __restrict__ err, int64_t H, int64_t N, int K, int Kp, int d, int metric,
-               int64_t idx_offset, int64_t* __restrict__ idx_out, float* __restrict__ score_out,
-               int* __restrict__ flag_list, uint32_t* __restrict__ flag_cnt,
-               unsigned long long* __restrict__ keys, uint32_t* __restrict__ scal) {
+resolve_classify_kernel(const uint2* __restrict__ cand, const float* __restrict__ err, int64_t H, int64_t N, int K,
+                        int Kp, int64_t idx_offset, int want_score, int64_t* __restrict__ idx_out,
+                        int* __restrict__ rr_list, int* __restrict__ flag_list, uint32_t* __restrict__ flag_cnt,
+                        unsigned long long* __restrict__ keys, uint32_t* __restrict__ scal) {
   const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  bool reranked = false;
+  bool queue = false;
   if (gid < H * N) {
     const int64_t h = gid / N;
-    const int64_t row = gid - h * N;
-    float key[kNumCand];
-    int code[kNumCand];
-    const uint4* c4 = reinterpret_cast<const uint4*>(cand + gid * kNumCand);
-#pragma unroll
-    for (int i = 0; i < kNumCand / 2; ++i) {
-      uint4 v = __ldg(c4 + i);
-      key[2 * i] = __uint_as_float(v.x); code[2 * i] = (int)v.y;
-      key[2 * i + 1] = __uint_as_float(v.z); code[2 * i + 1] = (int)v.w;
+    RowCands R;
+    load_cands(cand, gid, K, Kp, h, err, R);
+    if (R.full_rescan) {
+      const uint32_t pos = atomicAdd(flag_cnt + h, 1u);
+      flag_list[h * N + pos] = (int)(gid - h * N);
+      keys[gid] = ~0ull;                      // min-key accumulator of the K-split rescan
+    } else if (R.ncand == 1 && !R.local_rescan && !want_score) {
+      idx_out[gid] = (int64_t)R.c1 + idx_offset;
+    } else {
+      queue = true;
     }
-    float m1 = __int_as_float(0x7f800000);
-    int c1 = -1;
+  }
+  // warp-aggregated append to the re-rank list (scal[3] is its length)
+  const uint32_t m = __ballot_sync(0xffffffffu, queue);
+  if (m) {
+    const int lane = threadIdx.x & 31;
+    uint32_t base = 0;
+    if (lane == __ffs(m) - 1) base = atomicAdd(scal + 3, (uint32_t)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+    if (queue) rr_list[base + __popc(m & ((1u << lane) - 1u))] = (int)gid;
+  }
+}
+
+// phase 2, one warp per queued row: lane i evaluates candidate i exactly (and, for hazard (ii), column i of
+// the 32-column group), then a lexicographic (score, index) warp-min picks the winner
+template <typename T>
+__global__ void __launch_bounds__(256)
+resolve_rerank_kernel(const T* __restrict__ x, const float* __restrict__ cb, const uint2* __restrict__ cand,
+                      const float* __restrict__ err, int64_t N, int K, int Kp, int d, int metric,
+                      int64_t idx_offset, int64_t* __restrict__ idx_out, float* __restrict__ score_out,
+                      const int* __restrict__ rr_list, const uint32_t* __restrict__ scal) {
+  const int lane = threadIdx.x & 31;
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const int64_t count = scal[3];
+  for (int64_t it = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); it < count; it += nwarps) {
+    const int64_t gid = rr_list[it];
+    const int64_t h = gid / N;
+    // lane i < 24 owns candidate i
+    float key = __int_as_float(0x7f800000);
+    int code = -1;
+    if (lane < kNumCand) {
+      const uint2 v = __ldg(cand + gid * kNumCand + lane);
+      code = (int)v.y;
+      if (code >= 0 && code < K) key = __uint_as_float(v.x); else code = -1;
+    }
+    float m1 = key;
+    int c1 = code;
 #pragma unroll
-    for (int i = 0; i < kNumCand; ++i) {
-      const bool valid = code[i] >= 0 && code[i] < K;
-      if (!valid) key[i] = __int_as_float(0x7f800000);
-      if (valid && key[i] < m1) { m1 = key[i]; c1 = code[i]; }
+    for (int o = 16; o > 0; o >>= 1) {
+      const float om = __shfl_xor_sync(0xffffffffu, m1, o);
+      const int oc = __shfl_xor_sync(0xffffffffu, c1, o);
+      if (om < m1 || (om == m1 && oc > c1)) { m1 = om; c1 = oc; }   // any consistent tie rule: only E(c1) is used
     }
     const float E1 = c1 >= 0 ? err[h * Kp + c1] : 0.f;
-    // 2 E_j, plus the 5 packed id bits (<= 2^-18 relative per key) and the bias add rounding
-    const float thr = m1 + 2.f * E1 + (fabsf(m1) + E1) * 3.1e-5f;
+    const float thr = m1 + 2.f * E1 + (fabsf(m1) + E1) * kPackSlack;
 
-    int ncand = 0;
-    bool full_rescan = c1 < 0;
-    // rescan requests: (group, n-tile) pairs whose 32 columns must be evaluated exactly
-    int rs_g[8], rs_t[8], nrs = 0;
-#pragma unroll
-    for (int g = 0; g < 8; ++g) {
-      const float k0 = key[3 * g], k1 = key[3 * g + 1], k2 = key[3 * g + 2];
-      if (k0 <= thr) ++ncand;
-      if (k1 <= thr) ++ncand;
-      if (k2 <= thr) { ++ncand; full_rescan = true; }           // (i)
-      if (k1 <= thr) {                                           // (ii)
-        const int t0 = code[3 * g] >> 8, t1 = code[3 * g + 1] >> 8;
-        if (t0 == t1) { rs_g[nrs] = g; rs_t[nrs] = t0; ++nrs; }
+    const T* xr = x + gid * (int64_t)d;
+    const float* cbh = cb + h * (int64_t)K * d;
+    const double xn2 = metric == VQB_EUCLID ? row_norm2<T>(xr, d) : 0.0;
+    float best = __int_as_float(0x7f800000);
+    int bi = 0x7fffffff;
+    if (code >= 0 && key <= thr) {
+      best = exact_score<T>(xr, cbh + (int64_t)code * d, d, metric, xn2);
+      bi = code;
+    }
+    // hazard (ii): entries 3g and 3g+1 both within thr and from the same N tile -> rescan that 32-column group
+    const float key_next = __shfl_down_sync(0xffffffffu, key, 1);
+    const int code_next = __shfl_down_sync(0xffffffffu, code, 1);
+    const bool req = lane < kNumCand && (lane % 3) == 0 && key <= thr && key_next <= thr && code >= 0 &&
+                     code_next >= 0 && (code >> 9) == (code_next >> 9);
+    uint32_t reqs = __ballot_sync(0xffffffffu, req);
+    while (reqs) {
+      const int src = __ffs(reqs) - 1;
+      reqs &= reqs - 1;
+      const int c0 = __shfl_sync(0xffffffffu, code, src);
+      const int g = src / 3;                                     // group = half*4 + class
+#pragma unroll 1
+      for (int t = 0; t < 2; ++t) {                              // the group spans a pair of N tiles: 64 columns
+        const int k = ((c0 >> 9) * 2 + t) * kBlockN + (g >> 2) * 128 + (g & 3) + 4 * lane;
+        if (k < K) {
+          const float s = exact_score<T>(xr, cbh + (int64_t)k * d, d, metric, xn2);
+          if (s < best || (s == best && k < bi)) { best = s; bi = k; }
+        }
       }
     }
-    if (full_rescan) {
-      const uint32_t pos = atomicAdd(flag_cnt + h, 1u);
-      flag_list[h * N + pos] = (int)row;
-      keys[gid] = ~0ull;                      // min-key accumulator of the K-split rescan
-    } else if (ncand == 1 && score_out == nullptr) {
-      idx_out[gid] = (int64_t)c1 + idx_offset;
-    } else {
-      reranked = ncand > 1;
-      const T* xr = x + gid * (int64_t)d;
-      const float* cbh = cb + h * (int64_t)K * d;
-      const double xn2 = metric == VQB_EUCLID ? row_norm2<T>(xr, d) : 0.0;
-      float best = __int_as_float(0x7f800000);
-      int bi = 0x7fffffff;
-#pragma unroll 1
-      for (int i = 0; i < kNumCand; ++i) {
-        if (key[i] <= thr) {
-          const float s = exact_score<T>(xr, cbh + (int64_t)code[i] * d, d, metric, xn2);
-          if (s < best || (s == best && code[i] < bi) || bi == 0x7fffffff) { best = s; bi = code[i]; }
-        }
-      }
-#pragma unroll 1
-      for (int r = 0; r < nrs; ++r) {
-        const int half = rs_g[r] >> 2, cls = rs_g[r] & 3;
-        const int colb = rs_t[r] * kBlockN + half * 128 + cls;
-#pragma unroll 1
-        for (int i = 0; i < 32; ++i) {
-          const int k = colb + 4 * i;
-          if (k < K) {
-            const float s = exact_score<T>(xr, cbh + (int64_t)k * d, d, metric, xn2);
-            if (s < best || (s == best && k < bi)) { best = s; bi = k; }
-          }
-        }
-      }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ob < best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+    }
+    if (lane == 0) {
       idx_out[gid] = (int64_t)bi + idx_offset;
       if (score_out) score_out[gid] = best;
     }
   }
-  const int nre = __syncthreads_count(reranked ? 1 : 0);
-  if (threadIdx.x == 0 && nre) atomicAdd(scal + 3, (uint32_t)nre);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -350,14 +422,24 @@ extern "C" int vqb_search(const void* x, int x_dtype, const float* codebook, con
                         SL.dp, w + SL.off_cand, scal, (flags & VQB_SEARCH_TIMING) != 0, st);
   if (rc) return rc;
   const int64_t total = H * N;
-  VQB_DISPATCH_DTYPE(x_dtype, T,
-    resolve_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
-        (const T*)x, codebook, (const uint2*)(w + SL.off_cand), err, H, N, K, CL.Kp, d, metric, idx_offset,
-        idx_out, score_out, flag_list, cnt, keys, scal));
+  int* rr_list = (int*)(w + SL.off_rr);
+  resolve_classify_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
+      (const uint2*)(w + SL.off_cand), err, H, N, K, CL.Kp, idx_offset, score_out != nullptr, idx_out, rr_list,
+      flag_list, cnt, keys, scal);
   VQB_LAUNCH_CHECK();
+  {
+    int64_t want = score_out ? (total + 7) / 8 : (total / 16 + 7) / 8 + 1;   // blocks of 8 warps
+    const int64_t cap = (int64_t)num_sms() * 8;
+    const int grid_rr = (int)(want < cap ? want : cap);
+    VQB_DISPATCH_DTYPE(x_dtype, T,
+      resolve_rerank_kernel<T><<<grid_rr, 256, 0, st>>>(
+          (const T*)x, codebook, (const uint2*)(w + SL.off_cand), err, N, K, CL.Kp, d, metric, idx_offset, idx_out,
+          score_out, rr_list, scal));
+    VQB_LAUNCH_CHECK();
+  }
   // flagged rows (count is device-side): fixed grid, code range split over blockIdx.z so that even a handful of
   // rows spreads over the whole chip; blocks exit at once when there is nothing to do
-  const int ksplit_codes = 512;
+  const int ksplit_codes = K <= 16384 ? 64 : (K <= 65536 ? 128 : 64 * ((K + 64 * 4096 - 1) / (64 * 4096)));
   const int nsplit = (K + ksplit_codes - 1) / ksplit_codes;
   int grid_rows = (2 * num_sms() + nsplit - 1) / nsplit;
   if (grid_rows > grid_scan) grid_rows = grid_scan;

@@ -17,8 +17,8 @@
 // Operands are fp16 with exact power-of-two scales (per latent row, per codebook) that the epilogue
 // undoes with the same FFMA that adds the bias.
 // The scores are lower bounds  L_k = |c_k|^2/2 - E_k - x~.c~_k  (bias precomputed per search,
-// prepare.cu); each row keeps, for 8 disjoint column groups, the three smallest L (low 5 mantissa
-// bits carry the column id inside the group).  search_resolve.cu turns these 16 candidates into
+// prepare.cu); each row keeps, for 8 disjoint column groups, the three smallest L (low 6 mantissa
+// bits carry the column id inside a 64-column group = one class of one column half of a PAIR of N tiles).  search_resolve.cu turns these 16 candidates into
 // the exact fp32 argmin or proves that it cannot and flags the row for an exact rescan.
 // (tile-local top-2 per 32-column group feeds a running top-3 per class: see search_resolve.cu)
 #include <cuda.h>
@@ -55,6 +55,15 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   printf("vqb search_tc: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", (int)blockIdx.x,
          (int)threadIdx.x, bar, parity);
   __trap();
+}
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
 }
 __device__ __forceinline__ void fence_barrier_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -140,6 +149,54 @@ __device__ __forceinline__ void top2_pair(float& m1, float& m2, float a, float b
   float t = fmaxf(m1, lo);
   m2 = min3f(m2, hi, t);
   m1 = fminf(m1, lo);
+}
+
+// key = (bits & mask) | id in ONE LOP3 (mask lives in a register, id is an immediate); lut 0xEA = (a & b) | c
+template <uint32_t ID>
+__device__ __forceinline__ float pack_id(float v, uint32_t mask) {
+  uint32_t r;
+  asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(r) : "r"(__float_as_uint(v)), "r"(mask), "n"(ID));
+  return __uint_as_float(r);
+}
+
+template <uint32_t IDBASE, int I>
+__device__ __forceinline__ void pack4(float (&key)[32], uint32_t mask) {
+  key[4 * I + 0] = pack_id<IDBASE + I>(key[4 * I + 0], mask);
+  key[4 * I + 1] = pack_id<IDBASE + I>(key[4 * I + 1], mask);
+  key[4 * I + 2] = pack_id<IDBASE + I>(key[4 * I + 2], mask);
+  key[4 * I + 3] = pack_id<IDBASE + I>(key[4 * I + 3], mask);
+}
+
+// The epilogue is a software pipeline over 32-column chunks: the tcgen05.ld of chunk n+1 is in flight while
+// the ALU work (id packing + running top-2) of chunk n executes.
+//   scores(): wait for the chunk's accumulators, score = acc*ninv + bias (FFMA) -> key[]; r[] is dead afterwards
+//   rank<PARITY,CH>(): 6-bit id PARITY*32 + CH*8 + i into the low mantissa bits (column j = 4*i + c is class c),
+//                      running top-2 per class
+__device__ __forceinline__ void chunk_scores(const uint32_t (&r)[32], const float4* __restrict__ bias4, float ninv,
+                                             float (&key)[32]) {
+  float4 b[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) b[i] = __ldg(bias4 + i);
+  tmem_ld_wait();
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    key[4 * i + 0] = fmaf(__uint_as_float(r[4 * i + 0]), ninv, b[i].x);
+    key[4 * i + 1] = fmaf(__uint_as_float(r[4 * i + 1]), ninv, b[i].y);
+    key[4 * i + 2] = fmaf(__uint_as_float(r[4 * i + 2]), ninv, b[i].z);
+    key[4 * i + 3] = fmaf(__uint_as_float(r[4 * i + 3]), ninv, b[i].w);
+  }
+}
+
+template <int PARITY, int CH>
+__device__ __forceinline__ void chunk_rank(float (&key)[32], uint32_t idmask, float (&a1)[4], float (&a2)[4]) {
+  constexpr uint32_t kBase = (uint32_t)(PARITY * 32 + CH * 8);
+  pack4<kBase, 0>(key, idmask); pack4<kBase, 1>(key, idmask); pack4<kBase, 2>(key, idmask); pack4<kBase, 3>(key, idmask);
+  pack4<kBase, 4>(key, idmask); pack4<kBase, 5>(key, idmask); pack4<kBase, 6>(key, idmask); pack4<kBase, 7>(key, idmask);
+#pragma unroll
+  for (int i = 0; i < 8; i += 2) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) top2_pair(a1[c], a2[c], key[4 * i + c], key[4 * i + 4 + c]);
+  }
 }
 
 // insert (v, c) into the ascending triple (M1,M2,M3) with payloads (C1,C2,C3)
@@ -313,6 +370,13 @@ search_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     const int half = (warp - kEpiWarp0) >> 2;     // which 128 of the tile's 256 columns
     uint32_t acc = 0, acc_ph = 0;
     const float INF = __int_as_float(0x7f800000);
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + half * 128;
+    uint32_t r[32];
+    if (cid < G) {   // pipeline prologue: first chunk of the very first tile (later ones are prefetched in the loop)
+      mbar_wait(smem_u32(&bars->tmem_full[0]), 0);
+      tc_fence_after();
+      TMEM_LD32(lane_addr, r);
+    }
     for (int g = cid; g < G; g += num_clusters) {
       const int h = g / P.GPH;
       const int mt = (g - h * P.GPH) * CLUSTER + (int)rank;
@@ -325,52 +389,62 @@ search_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
       // acc = (x s_row).(c s_c)  ->  score = bias - acc / (s_row s_c): one FFMA per element
       const float ninv = row < P.N ? -(P.xinv[(size_t)h * P.N + row] * P.chdr[h * 4 + 1]) : 0.f;
 
-      for (int nt = 0; nt < P.NT; ++nt) {
+      // the id mask lives in a register so that "(bits & mask) | id" is a single LOP3 (opaque to constant folding)
+      uint32_t idmask;
+      asm volatile("mov.u32 %0, 0xFFFFFFC0;" : "=r"(idmask));
+      for (int nt = 0; nt < P.NT; nt += 2) {       // N tiles in pairs: one top-3 merge per 512 codes
         float a1[4], a2[4];
 #pragma unroll
         for (int c = 0; c < 4; ++c) { a1[c] = INF; a2[c] = INF; }
-        mbar_wait(smem_u32(&bars->tmem_full[acc]), acc_ph);
-        tc_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * (uint32_t)kBlockN + half * 128;
-        const float4* bias4 = reinterpret_cast<const float4*>(bias_h + nt * kBlockN);
 #pragma unroll
-        for (int ch = 0; ch < 4; ++ch) {
-          uint32_t r[32];
-          TMEM_LD32(taddr + ch * 32, r);
-          float4 b[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) b[i] = __ldg(bias4 + ch * 8 + i);
-          tmem_ld_wait();
-          float key[32];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            // column j = 4*i + c  ->  class c, id-in-class (ch*8 + i) in the low 5 mantissa bits
-            const uint32_t id = (uint32_t)(ch * 8 + i);
-            key[4 * i + 0] = __uint_as_float((__float_as_uint(fmaf(__uint_as_float(r[4 * i + 0]), ninv, b[i].x)) & 0xFFFFFFE0u) | id);
-            key[4 * i + 1] = __uint_as_float((__float_as_uint(fmaf(__uint_as_float(r[4 * i + 1]), ninv, b[i].y)) & 0xFFFFFFE0u) | id);
-            key[4 * i + 2] = __uint_as_float((__float_as_uint(fmaf(__uint_as_float(r[4 * i + 2]), ninv, b[i].z)) & 0xFFFFFFE0u) | id);
-            key[4 * i + 3] = __uint_as_float((__float_as_uint(fmaf(__uint_as_float(r[4 * i + 3]), ninv, b[i].w)) & 0xFFFFFFE0u) | id);
-          }
-#pragma unroll
-          for (int i = 0; i < 8; i += 2) {
-#pragma unroll
-            for (int c = 0; c < 4; ++c) top2_pair(a1[c], a2[c], key[4 * i + c], key[4 * i + 4 + c]);
+        for (int par = 0; par < 2; ++par) {
+          if (nt + par < P.NT) {
+            const uint32_t taddr = lane_addr + acc * (uint32_t)kBlockN;
+            const float4* bias4 = reinterpret_cast<const float4*>(bias_h + (nt + par) * kBlockN);
+            float key[32];
+#define VQB_CHUNK(CH)                                                        \
+            chunk_scores(r, bias4 + (CH) * 8, ninv, key);                   \
+            if ((CH) < 3) TMEM_LD32(taddr + ((CH) + 1) * 32, r);            \
+            if (par == 0) chunk_rank<0, (CH)>(key, idmask, a1, a2);         \
+            else chunk_rank<1, (CH)>(key, idmask, a1, a2);
+            VQB_CHUNK(0)
+            VQB_CHUNK(1)
+            VQB_CHUNK(2)
+            // last chunk: scores first (all TMEM reads of this tile are then complete), hand the buffer back to
+            // the MMA warp, and start loading the next tile's first chunk before this chunk's ALU work if its
+            // accumulator is already complete
+            chunk_scores(r, bias4 + 24, ninv, key);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&bars->tmem_empty[acc]));
+            if (++acc == 2) { acc = 0; acc_ph ^= 1u; }
+            const bool more = (nt + par + 1 < P.NT) || (g + num_clusters < G);
+            bool issued = false;
+            if (more && mbar_try(smem_u32(&bars->tmem_full[acc]), acc_ph)) {
+              tc_fence_after();
+              TMEM_LD32(lane_addr + acc * (uint32_t)kBlockN, r);
+              issued = true;
+            }
+            if (par == 0) chunk_rank<0, 3>(key, idmask, a1, a2);
+            else chunk_rank<1, 3>(key, idmask, a1, a2);
+            if (more && !issued) {
+              mbar_wait(smem_u32(&bars->tmem_full[acc]), acc_ph);
+              tc_fence_after();
+              TMEM_LD32(lane_addr + acc * (uint32_t)kBlockN, r);
+            }
+#undef VQB_CHUNK
           }
         }
-        // accumulator fully read: hand the TMEM buffer back to the MMA warp
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&bars->tmem_empty[acc]));
-        if (++acc == 2) { acc = 0; acc_ph ^= 1u; }
-
-        // merge this tile's top-2 into the running top-3 of the class (with global code ids)
+        // merge this tile pair's top-2 into the running top-3 of the class (with global code ids):
+        // id bit 5 = which tile of the pair, bits 0..4 = position inside the class
         const int col0 = nt * kBlockN + half * 128;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
+          const uint32_t i1 = __float_as_uint(a1[c]) & 63u, i2 = __float_as_uint(a2[c]) & 63u;
           top3_insert(M1[c], M2[c], M3[c], C1[c], C2[c], C3[c], a1[c],
-                      col0 + (int)((__float_as_uint(a1[c]) & 31u) << 2) + c);
+                      col0 + (int)(i1 >> 5) * kBlockN + (int)((i1 & 31u) << 2) + c);
           top3_insert(M1[c], M2[c], M3[c], C1[c], C2[c], C3[c], a2[c],
-                      col0 + (int)((__float_as_uint(a2[c]) & 31u) << 2) + c);
+                      col0 + (int)(i2 >> 5) * kBlockN + (int)((i2 & 31u) << 2) + c);
         }
       }
       if (row < P.N) {

@@ -90,6 +90,15 @@ def require_cuda(t: torch.Tensor, name: str) -> None:
         raise RuntimeError(f"vqb200: `{name}` must be contiguous")
 
 
+def aligned(t: torch.Tensor) -> torch.Tensor:
+    """Contiguous and 16-byte aligned (the kernels use 128-bit loads); copies only when needed."""
+    if not t.is_contiguous() or t.data_ptr() % 16:
+        t = t.contiguous()
+        if t.data_ptr() % 16:
+            t = t.clone(memory_format=torch.contiguous_format)
+    return t
+
+
 def ptr(t) -> int:
     return 0 if t is None else t.data_ptr()
 

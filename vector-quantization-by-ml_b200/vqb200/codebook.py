@@ -16,7 +16,7 @@ import torch
 import torch.distributed as dist
 from torch import nn
 
-from . import ops
+from . import _lib, ops
 from .params import GumbelParams, KmeansParameters
 
 
@@ -129,7 +129,7 @@ class Codebook(nn.Module):
             x = x.float()
         H, d = x.shape[0], x.shape[-1]
         lead = tuple(x.shape[1:-1])
-        return x.reshape(H, -1, d).contiguous(), lead
+        return _lib.aligned(x.reshape(H, -1, d)), lead
 
     def _expand_mask(self, mask: Optional[torch.Tensor], n_rows: int) -> Optional[torch.Tensor]:
         # reference codebooks.py:361-367: repeat(mask, "b n -> c (b h n)")
