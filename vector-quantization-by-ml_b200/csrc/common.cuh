@@ -78,7 +78,7 @@ inline CacheLayout cache_layout(int64_t H, int K, int d) {
 // Search workspace layout (one caller-owned buffer).
 struct SearchLayout {
   int dp;
-  size_t off_scal;    // u32[64]: [0]=max|x_b| bits, [1]=max|x-x_b| bits, [2]=#rescanned, [3]=#reranked, [4]=tc used, [5]=smem misalign flag
+  size_t off_scal;    // u32[64]: [0]=max|x_b| bits, [1]=max|x-x_b| bits, [2]=#rescanned, [3]=#reranked, [4]=tc used, [5]=smem misalign flag, [6]=max E_k bits
   size_t off_cnt;     // u32[H]: flagged rows per codebook (directly after scal: zeroed together)
   size_t off_xb;      // fp16 [H][N][dp]  = fp16(x * s_row), zero padded
   size_t off_xinv;    // f32  [H][N]      = 1 / s_row (exact power of two)
@@ -190,7 +190,7 @@ inline int dtype_size(int dt) { return dt == VQB_F32 ? 4 : 2; }
 int launch_prepare_latents(const void* x, int x_dtype, int64_t rows, int d, int dp,
                            __half* xb, float* xinv, uint32_t* scal, cudaStream_t st);
 int launch_make_bias(const void* cache, const CacheLayout& CL, int64_t H, int K, int metric,
-                     const uint32_t* scal, float* bias, float* err, cudaStream_t st);
+                     uint32_t* scal, float* bias, float* err, cudaStream_t st);
 int launch_search_tc(const __half* xb, const float* xinv, const __half* cb, const float* chdr, const float* bias,
                      int64_t H, int64_t N, int K, int dp, void* cand, uint32_t* scal, bool timing, cudaStream_t st);
 

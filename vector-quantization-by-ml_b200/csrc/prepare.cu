@@ -159,24 +159,33 @@ int launch_prepare_latents(const void* x, int x_dtype, int64_t rows, int d, int 
 // E_k = Xmax*|c_k - c~_k| + DXmax*|c_k| + accumulation slack;  bias_k = |c_k|^2/2 - E_k
 __global__ void make_bias_kernel(const float* __restrict__ cn2h, const float* __restrict__ cn,
                                  const float* __restrict__ dcn, int64_t total, int Kp, int K,
-                                 const uint32_t* __restrict__ scal, float* __restrict__ bias,
-                                 float* __restrict__ err) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  int k = (int)(i % Kp);
-  if (k >= K) { bias[i] = kPadBias; err[i] = 0.f; return; }
-  float xmax = __uint_as_float(scal[0]), dxmax = __uint_as_float(scal[1]);
-  float c = cn[i], h = cn2h[i];
-  // products are exact in the tensor core (fp16 x fp16 = 22 bits, fits fp32); accumulation is fp32-ish:
-  // allow 2^-16 of the largest possible |sum| plus the fp32 rounding of |c|^2/2.
-  float e = xmax * dcn[i] + dxmax * c + 1.6e-5f * (xmax * c) + 2.4e-7f * h;
-  e = e * 1.001f + 1e-30f;
-  err[i] = e;
-  bias[i] = h - e;
+                                 uint32_t* __restrict__ scal, float* __restrict__ bias, float* __restrict__ err) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  float e = 0.f;
+  if (i < total) {
+    const int k = (int)(i % Kp);
+    if (k >= K) {
+      bias[i] = kPadBias;
+      err[i] = 0.f;
+    } else {
+      const float xmax = __uint_as_float(scal[0]), dxmax = __uint_as_float(scal[1]);
+      const float c = cn[i], h = cn2h[i];
+      // products are exact in the tensor core (fp16 x fp16 = 22 bits, fits fp32); accumulation is fp32-ish:
+      // allow 2^-16 of the largest possible |sum| plus the fp32 rounding of |c|^2/2.
+      e = xmax * dcn[i] + dxmax * c + 1.6e-5f * (xmax * c) + 2.4e-7f * h;
+      e = e * 1.001f + 1e-30f;
+      err[i] = e;
+      bias[i] = h - e;
+    }
+  }
+  // scal[6] = max_k E_k: the search epilogue's skip test needs a bound that holds for whichever code wins
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) e = fmaxf(e, __shfl_xor_sync(0xffffffffu, e, o));
+  if ((threadIdx.x & 31) == 0 && e > 0.f) atomicMax(scal + 6, __float_as_uint(e));
 }
 
 int launch_make_bias(const void* cache, const CacheLayout& CL, int64_t H, int K, int metric,
-                     const uint32_t* scal, float* bias, float* err, cudaStream_t st) {
+                     uint32_t* scal, float* bias, float* err, cudaStream_t st) {
   (void)metric;
   const char* base = (const char*)cache;
   int64_t total = H * (int64_t)CL.Kp;

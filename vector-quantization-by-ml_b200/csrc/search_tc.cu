@@ -65,6 +65,13 @@ __device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
       : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
   return ok != 0;
 }
+// mbar_wait that adds the cycles spent to `acc` when profiling is on (bring-up only)
+__device__ __forceinline__ void mbar_wait_t(uint32_t bar, uint32_t parity, bool prof, unsigned long long& acc) {
+  if (!prof) { mbar_wait(bar, parity); return; }
+  const long long t0 = clock64();
+  mbar_wait(bar, parity);
+  acc += (unsigned long long)(clock64() - t0);
+}
 __device__ __forceinline__ void fence_barrier_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
@@ -136,6 +143,13 @@ constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(kBlockN >> 3) << 17) | ((uin
         "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),  \
         "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])   \
       : "r"(taddr))
+#define TMEM_LD16(taddr, r)                                                                                      \
+  asm volatile(                                                                                                  \
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "                                                                  \
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"                           \
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),          \
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])     \
+      : "r"(taddr))
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 __device__ __forceinline__ float min3f(float a, float b, float c) {
@@ -151,6 +165,10 @@ __device__ __forceinline__ void top2_pair(float& m1, float& m2, float a, float b
   m1 = fminf(m1, lo);
 }
 
+__device__ unsigned long long g_dbg_cycles[16];    // bring-up only (VQB_TC_DEBUG & 32): where each role waits
+__device__ unsigned long long g_dbg_counters[2];   // bring-up only (VQB_TC_DEBUG & 16): ranked / skipped chunks
+constexpr float kPackSlackTC = 6.2e-5f;   // must equal kPackSlack in search_resolve.cu
+
 // key = (bits & mask) | id in ONE LOP3 (mask lives in a register, id is an immediate); lut 0xEA = (a & b) | c
 template <uint32_t ID>
 __device__ __forceinline__ float pack_id(float v, uint32_t mask) {
@@ -159,43 +177,68 @@ __device__ __forceinline__ float pack_id(float v, uint32_t mask) {
   return __uint_as_float(r);
 }
 
-template <uint32_t IDBASE, int I>
-__device__ __forceinline__ void pack4(float (&key)[32], uint32_t mask) {
-  key[4 * I + 0] = pack_id<IDBASE + I>(key[4 * I + 0], mask);
-  key[4 * I + 1] = pack_id<IDBASE + I>(key[4 * I + 1], mask);
-  key[4 * I + 2] = pack_id<IDBASE + I>(key[4 * I + 2], mask);
-  key[4 * I + 3] = pack_id<IDBASE + I>(key[4 * I + 3], mask);
-}
-
-// The epilogue is a software pipeline over 32-column chunks: the tcgen05.ld of chunk n+1 is in flight while
-// the ALU work (id packing + running top-2) of chunk n executes.
-//   scores(): wait for the chunk's accumulators, score = acc*ninv + bias (FFMA) -> key[]; r[] is dead afterwards
-//   rank<PARITY,CH>(): 6-bit id PARITY*32 + CH*8 + i into the low mantissa bits (column j = 4*i + c is class c),
-//                      running top-2 per class
-__device__ __forceinline__ void chunk_scores(const uint32_t (&r)[32], const float4* __restrict__ bias4, float ninv,
-                                             float (&key)[32]) {
-  float4 b[8];
+// The epilogue is a software pipeline over 16-column chunks of one thread's row (8 chunks per N tile):
+//   scores : wait for the chunk's accumulators (tcgen05.wait::ld), score = acc*ninv + bias (FFMA, undoes the operand
+//            scales and adds |c|^2/2 - E_k), chunk minimum with an FMNMX3 tree.  The accumulator registers are dead
+//            afterwards, so the NEXT chunk's tcgen05.ld is issued right here and is in flight during
+//   rank   : FAST PATH -- a score can be a candidate of the final answer only if it is <= thr_final = m + |m| slack
+//            + 2E (m = final row minimum); thr is monotone in m and the running minimum only decreases, so if every
+//            score of the chunk exceeds t_run = thr(running minimum, Emax) for every row of the warp, the chunk holds
+//            no candidate and nothing else is done.  SLOW PATH -- 6-bit id PARITY*32 + CH*4 + i packed into the low
+//            mantissa bits (column j = 4*i + c is class c), running top-2 per class, exactly as if no chunk had been
+//            skipped.
+__device__ __forceinline__ float chunk_scores(const uint32_t (&r)[16], const float4* bias4, float ninv,
+                                              float (&key)[16]) {
+  float4 b[4];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) b[i] = __ldg(bias4 + i);
+  for (int i = 0; i < 4; ++i) b[i] = bias4[i];          // shared memory, same address in every lane: broadcast
   tmem_ld_wait();
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
+  for (int i = 0; i < 4; ++i) {
     key[4 * i + 0] = fmaf(__uint_as_float(r[4 * i + 0]), ninv, b[i].x);
     key[4 * i + 1] = fmaf(__uint_as_float(r[4 * i + 1]), ninv, b[i].y);
     key[4 * i + 2] = fmaf(__uint_as_float(r[4 * i + 2]), ninv, b[i].z);
     key[4 * i + 3] = fmaf(__uint_as_float(r[4 * i + 3]), ninv, b[i].w);
   }
+  float cm[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) cm[c] = fminf(min3f(key[c], key[4 + c], key[8 + c]), key[12 + c]);
+  return fminf(min3f(cm[0], cm[1], cm[2]), cm[3]);
+}
+
+template <uint32_t ID>
+__device__ __forceinline__ void pack_row4(float (&key)[16], int i, uint32_t mask) {
+  key[4 * i + 0] = pack_id<ID>(key[4 * i + 0], mask);
+  key[4 * i + 1] = pack_id<ID>(key[4 * i + 1], mask);
+  key[4 * i + 2] = pack_id<ID>(key[4 * i + 2], mask);
+  key[4 * i + 3] = pack_id<ID>(key[4 * i + 3], mask);
 }
 
 template <int PARITY, int CH>
-__device__ __forceinline__ void chunk_rank(float (&key)[32], uint32_t idmask, float (&a1)[4], float (&a2)[4]) {
-  constexpr uint32_t kBase = (uint32_t)(PARITY * 32 + CH * 8);
-  pack4<kBase, 0>(key, idmask); pack4<kBase, 1>(key, idmask); pack4<kBase, 2>(key, idmask); pack4<kBase, 3>(key, idmask);
-  pack4<kBase, 4>(key, idmask); pack4<kBase, 5>(key, idmask); pack4<kBase, 6>(key, idmask); pack4<kBase, 7>(key, idmask);
+__device__ __forceinline__ void chunk_rank(float (&key)[16], float cmin, uint32_t idmask, float tconst, float& m_run,
+                                           float& t_run, float (&a1)[4], float (&a2)[4], bool& any_slow, int dbg) {
+  bool trig = __any_sync(0xffffffffu, cmin <= t_run);
+  if (dbg) {   // bring-up knobs: 4 = never rank, 8 = always rank, 16 = count ranked / skipped chunks
+    if (dbg & 4) trig = false;
+    if (dbg & 8) trig = true;
+    if ((dbg & 16) && (threadIdx.x & 31) == 0) atomicAdd(g_dbg_counters + (trig ? 0 : 1), 1ull);
+  }
+  if (trig) {
+    any_slow = true;
+    constexpr uint32_t kBase = (uint32_t)(PARITY * 32 + CH * 4);
+    pack_row4<kBase + 0>(key, 0, idmask);
+    pack_row4<kBase + 1>(key, 1, idmask);
+    pack_row4<kBase + 2>(key, 2, idmask);
+    pack_row4<kBase + 3>(key, 3, idmask);
 #pragma unroll
-  for (int i = 0; i < 8; i += 2) {
-#pragma unroll
-    for (int c = 0; c < 4; ++c) top2_pair(a1[c], a2[c], key[4 * i + c], key[4 * i + 4 + c]);
+    for (int c = 0; c < 4; ++c) {
+      top2_pair(a1[c], a2[c], key[c], key[4 + c]);
+      top2_pair(a1[c], a2[c], key[8 + c], key[12 + c]);
+    }
+    if (cmin < m_run) {
+      m_run = cmin;
+      t_run = fmaf(fabsf(cmin), kPackSlackTC, cmin) + tconst;
+    }
   }
 }
 
@@ -236,6 +279,7 @@ struct SearchParams {
   int NT;              // N tiles = Kp / 256
   int S;               // B stages
   int GPH;             // row-tile groups per head = ceil(ceil(N/128) / CLUSTER)
+  int dbg;             // bring-up knobs (env VQB_TC_DEBUG): 4 = never rank, 8 = always rank, 16 = count ranked chunks
 };
 
 struct Barriers {
@@ -245,8 +289,10 @@ struct Barriers {
   uint64_t a_empty[kMaxKB];
   uint64_t tmem_full[2];
   uint64_t tmem_empty[2];
+  uint64_t bias_full[2];
   uint32_t tmem_base;
   uint32_t pad;
+  alignas(16) float bias[2][kBlockN];   // per-accumulator-buffer copy of the N tile's biases (staged by warp 3)
 };
 
 template <int CLUSTER>
@@ -286,6 +332,7 @@ search_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     for (int i = 0; i < 2; ++i) {
       mbar_init(smem_u32(&bars->tmem_full[i]), 1);
       mbar_init(smem_u32(&bars->tmem_empty[i]), kNumEpiWarps);
+      mbar_init(smem_u32(&bars->bias_full[i]), 1);
     }
     fence_barrier_init();
   }
@@ -303,6 +350,9 @@ search_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     // =============================== TMA producer ===============================
     if (lane == 0) {
       uint32_t stage = 0, ph = 0, a_ph = 0;
+      const bool prof = (P.dbg & 32) != 0;
+      unsigned long long w_a = 0, w_e = 0;
+      const long long t_begin = clock64();
       for (int g = cid; g < G; g += num_clusters) {
         const int h = g / P.GPH;
         const int mt = (g - h * P.GPH) * CLUSTER + (int)rank;
@@ -310,12 +360,12 @@ search_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
         for (int nt = 0; nt < P.NT; ++nt) {
           for (int kb = 0; kb < P.KB; ++kb) {
             if (nt == 0) {   // (re)load slab kb of this row tile as soon as the previous tile's MMAs released it
-              mbar_wait(smem_u32(&bars->a_empty[kb]), a_ph ^ 1u);
+              mbar_wait_t(smem_u32(&bars->a_empty[kb]), a_ph ^ 1u, prof, w_a);
               mbar_expect_tx(smem_u32(&bars->a_full[kb]), kSlabBytes);
               tma_load_3d(a_base + kb * kSlabBytes, &map_x, smem_u32(&bars->a_full[kb]), kb * kBlockK, row0, h,
                           kEvictFirst);
             }
-            mbar_wait(smem_u32(&bars->empty[stage]), ph ^ 1u);
+            mbar_wait_t(smem_u32(&bars->empty[stage]), ph ^ 1u, prof, w_e);
             mbar_expect_tx(smem_u32(&bars->full[stage]), kStageBytes);
             if (CLUSTER > 1) {
               constexpr int rows = kBlockN / CLUSTER;
@@ -331,19 +381,27 @@ search_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
         }
         a_ph ^= 1u;
       }
+      if (prof) {
+        atomicAdd(g_dbg_cycles + 0, (unsigned long long)(clock64() - t_begin));
+        atomicAdd(g_dbg_cycles + 1, w_a);
+        atomicAdd(g_dbg_cycles + 2, w_e);
+      }
     }
   } else if (warp == 1) {
     // =============================== MMA issuer ===============================
     if (lane == 0) {
       uint32_t stage = 0, ph = 0, a_ph = 0, acc = 0, acc_ph = 0;
+      const bool prof = (P.dbg & 32) != 0;
+      unsigned long long w_te = 0, w_a = 0, w_f = 0;
+      const long long t_begin = clock64();
       for (int g = cid; g < G; g += num_clusters) {
         for (int nt = 0; nt < P.NT; ++nt) {
-          mbar_wait(smem_u32(&bars->tmem_empty[acc]), acc_ph ^ 1u);   // epilogue drained this accumulator
+          mbar_wait_t(smem_u32(&bars->tmem_empty[acc]), acc_ph ^ 1u, prof, w_te);   // epilogue drained this accumulator
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + acc * (uint32_t)kBlockN;
           for (int kb = 0; kb < P.KB; ++kb) {
-            if (nt == 0) mbar_wait(smem_u32(&bars->a_full[kb]), a_ph);
-            mbar_wait(smem_u32(&bars->full[stage]), ph);
+            if (nt == 0) mbar_wait_t(smem_u32(&bars->a_full[kb]), a_ph, prof, w_a);
+            mbar_wait_t(smem_u32(&bars->full[stage]), ph, prof, w_f);
             tc_fence_after();
             const uint64_t adesc = make_sw128_desc(a_base + kb * kSlabBytes);
             const uint64_t bdesc = make_sw128_desc(b_base + stage * kStageBytes);
@@ -363,6 +421,33 @@ search_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
         }
         a_ph ^= 1u;
       }
+      if (prof) {
+        atomicAdd(g_dbg_cycles + 3, (unsigned long long)(clock64() - t_begin));
+        atomicAdd(g_dbg_cycles + 4, w_te);
+        atomicAdd(g_dbg_cycles + 5, w_a);
+        atomicAdd(g_dbg_cycles + 6, w_f);
+      }
+    }
+  } else if (warp == 3) {
+    // =============================== bias stager ===============================
+    // Only ~34 KB of L1 is left next to 193 KB of dynamic smem, and the bias vector (4 B per code) is re-read for
+    // every row tile, so global loads in the epilogue would miss L1 and sit in its dependency chain.  This warp
+    // copies each N tile's 256 biases into smem, one slot per accumulator buffer, as soon as the epilogue has
+    // released that buffer (same cadence as the MMA warp).
+    uint32_t acc = 0, acc_ph = 0;
+    for (int g = cid; g < G; g += num_clusters) {
+      const int h = g / P.GPH;
+      const float* bias_h = P.bias + (size_t)h * P.Kp;
+      for (int nt = 0; nt < P.NT; ++nt) {
+        const float4 v0 = __ldg(reinterpret_cast<const float4*>(bias_h + nt * kBlockN) + lane);
+        const float4 v1 = __ldg(reinterpret_cast<const float4*>(bias_h + nt * kBlockN) + 32 + lane);
+        mbar_wait(smem_u32(&bars->tmem_empty[acc]), acc_ph ^ 1u);
+        reinterpret_cast<float4*>(bars->bias[acc])[lane] = v0;
+        reinterpret_cast<float4*>(bars->bias[acc])[32 + lane] = v1;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&bars->bias_full[acc]));   // release semantics order the stores
+        if (++acc == 2) { acc = 0; acc_ph ^= 1u; }
+      }
     }
   } else if (warp >= kEpiWarp0) {
     // =============================== epilogue: bias + packed running top-2 ===============================
@@ -371,11 +456,16 @@ search_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     uint32_t acc = 0, acc_ph = 0;
     const float INF = __int_as_float(0x7f800000);
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + half * 128;
-    uint32_t r[32];
+    // Emax * (2 + slack): the part of the candidate threshold that does not depend on the row minimum
+    const float tconst = __uint_as_float(P.scal[6]) * (2.f + kPackSlackTC);
+    const bool prof = (P.dbg & 32) != 0 && warp == kEpiWarp0;
+    unsigned long long w_tf = 0, w_bias = 0;
+    const long long t_begin = clock64();
+    uint32_t r[16];
     if (cid < G) {   // pipeline prologue: first chunk of the very first tile (later ones are prefetched in the loop)
       mbar_wait(smem_u32(&bars->tmem_full[0]), 0);
       tc_fence_after();
-      TMEM_LD32(lane_addr, r);
+      TMEM_LD16(lane_addr, r);
     }
     for (int g = cid; g < G; g += num_clusters) {
       const int h = g / P.GPH;
@@ -385,35 +475,38 @@ search_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
       int C1[4], C2[4], C3[4];
 #pragma unroll
       for (int c = 0; c < 4; ++c) { M1[c] = INF; M2[c] = INF; M3[c] = INF; C1[c] = -1; C2[c] = -1; C3[c] = -1; }
-      const float* bias_h = P.bias + (size_t)h * P.Kp + half * 128;
       // acc = (x s_row).(c s_c)  ->  score = bias - acc / (s_row s_c): one FFMA per element
       const float ninv = row < P.N ? -(P.xinv[(size_t)h * P.N + row] * P.chdr[h * 4 + 1]) : 0.f;
 
       // the id mask lives in a register so that "(bits & mask) | id" is a single LOP3 (opaque to constant folding)
       uint32_t idmask;
       asm volatile("mov.u32 %0, 0xFFFFFFC0;" : "=r"(idmask));
+      float m_run = INF, t_run = INF;              // running row minimum (this thread's columns) and its threshold
       for (int nt = 0; nt < P.NT; nt += 2) {       // N tiles in pairs: one top-3 merge per 512 codes
         float a1[4], a2[4];
 #pragma unroll
         for (int c = 0; c < 4; ++c) { a1[c] = INF; a2[c] = INF; }
+        bool any_slow = false;
 #pragma unroll
         for (int par = 0; par < 2; ++par) {
           if (nt + par < P.NT) {
+            // r[] already holds (or is receiving) chunk 0 of this tile
             const uint32_t taddr = lane_addr + acc * (uint32_t)kBlockN;
-            const float4* bias4 = reinterpret_cast<const float4*>(bias_h + (nt + par) * kBlockN);
-            float key[32];
-#define VQB_CHUNK(CH)                                                        \
-            chunk_scores(r, bias4 + (CH) * 8, ninv, key);                   \
-            if ((CH) < 3) TMEM_LD32(taddr + ((CH) + 1) * 32, r);            \
-            if (par == 0) chunk_rank<0, (CH)>(key, idmask, a1, a2);         \
-            else chunk_rank<1, (CH)>(key, idmask, a1, a2);
-            VQB_CHUNK(0)
-            VQB_CHUNK(1)
-            VQB_CHUNK(2)
-            // last chunk: scores first (all TMEM reads of this tile are then complete), hand the buffer back to
-            // the MMA warp, and start loading the next tile's first chunk before this chunk's ALU work if its
-            // accumulator is already complete
-            chunk_scores(r, bias4 + 24, ninv, key);
+            mbar_wait_t(smem_u32(&bars->bias_full[acc]), acc_ph, prof, w_bias);
+            const float4* bias4 = reinterpret_cast<const float4*>(bars->bias[acc] + half * 128);
+            float key[16];
+            float cmin;
+#define VQB_CHUNK(CH)                                                                                      \
+            cmin = chunk_scores(r, bias4 + (CH) * 4, ninv, key);                                           \
+            TMEM_LD16(taddr + ((CH) + 1) * 16, r);                                                         \
+            if (par == 0) chunk_rank<0, (CH)>(key, cmin, idmask, tconst, m_run, t_run, a1, a2, any_slow, P.dbg); \
+            else chunk_rank<1, (CH)>(key, cmin, idmask, tconst, m_run, t_run, a1, a2, any_slow, P.dbg);
+            VQB_CHUNK(0) VQB_CHUNK(1) VQB_CHUNK(2) VQB_CHUNK(3) VQB_CHUNK(4) VQB_CHUNK(5) VQB_CHUNK(6)
+#undef VQB_CHUNK
+            // last chunk: once its scores are formed every TMEM read of this tile is complete -> hand the buffer
+            // back to the MMA warp, then start loading the next tile's first chunk (before this chunk's ranking
+            // work if that accumulator is already complete)
+            cmin = chunk_scores(r, bias4 + 28, ninv, key);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&bars->tmem_empty[acc]));
@@ -422,19 +515,19 @@ search_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
             bool issued = false;
             if (more && mbar_try(smem_u32(&bars->tmem_full[acc]), acc_ph)) {
               tc_fence_after();
-              TMEM_LD32(lane_addr + acc * (uint32_t)kBlockN, r);
+              TMEM_LD16(lane_addr + acc * (uint32_t)kBlockN, r);
               issued = true;
             }
-            if (par == 0) chunk_rank<0, 3>(key, idmask, a1, a2);
-            else chunk_rank<1, 3>(key, idmask, a1, a2);
+            if (par == 0) chunk_rank<0, 7>(key, cmin, idmask, tconst, m_run, t_run, a1, a2, any_slow, P.dbg);
+            else chunk_rank<1, 7>(key, cmin, idmask, tconst, m_run, t_run, a1, a2, any_slow, P.dbg);
             if (more && !issued) {
-              mbar_wait(smem_u32(&bars->tmem_full[acc]), acc_ph);
+              mbar_wait_t(smem_u32(&bars->tmem_full[acc]), acc_ph, prof, w_tf);
               tc_fence_after();
-              TMEM_LD32(lane_addr + acc * (uint32_t)kBlockN, r);
+              TMEM_LD16(lane_addr + acc * (uint32_t)kBlockN, r);
             }
-#undef VQB_CHUNK
           }
         }
+        if (!any_slow) continue;                   // warp-uniform: nothing was ranked in this tile pair
         // merge this tile pair's top-2 into the running top-3 of the class (with global code ids):
         // id bit 5 = which tile of the pair, bits 0..4 = position inside the class
         const int col0 = nt * kBlockN + half * 128;
@@ -462,6 +555,11 @@ search_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
 #pragma unroll
         for (int i = 0; i < 6; ++i) out4[i] = make_uint4(e[4 * i], e[4 * i + 1], e[4 * i + 2], e[4 * i + 3]);
       }
+    }
+    if (prof && lane == 0) {
+      atomicAdd(g_dbg_cycles + 7, (unsigned long long)(clock64() - t_begin));
+      atomicAdd(g_dbg_cycles + 8, w_tf);
+      atomicAdd(g_dbg_cycles + 9, w_bias);
     }
   }
 
@@ -571,10 +669,17 @@ int launch_search_tc(const __half* xb, const float* xinv, const __half* cb, cons
     g_cluster_override = e ? atoi(e) : 0;
   }
   const int MT = (int)((N + kBlockM - 1) / kBlockM);
-  int cluster = (g_cluster_override == 1 || g_cluster_override == 2) ? g_cluster_override : (MT >= 2 * num_sms ? 2 : 1);
+  // measured on B200 (C2 shape): L2 serves the un-shared B stream fine (1 CTA: 3.99 ms, 2-CTA multicast: 4.15 ms),
+  // so multicast clusters are opt-in (VQB_CLUSTER=2)
+  int cluster = (g_cluster_override == 2 && MT >= 2) ? 2 : 1;
 
   SearchParams P;
   P.bias = bias; P.xinv = xinv; P.chdr = chdr; P.cand = cand; P.scal = scal; P.N = N; P.Kp = Kp; P.H = (int)H;
+  {
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = getenv("VQB_TC_DEBUG"); dbg = e ? atoi(e) : 0; }
+    P.dbg = dbg;
+  }
   P.KB = dp / kBlockK;
   P.NT = Kp / kBlockN;
   const size_t fixed = (size_t)P.KB * kSlabBytes + sizeof(Barriers);
@@ -598,6 +703,15 @@ int launch_search_tc(const __half* xb, const float* xinv, const __half* cb, cons
   return launch_impl<1>(mx, mc, P, smem_bytes, grid, timing, st);
 }
 
+int debug_counters(unsigned long long* out18) {   // [0..1] ranked/skipped chunks, [2..17] cycle counters
+  VQB_CUDA_TRY(cudaMemcpyFromSymbol(out18, g_dbg_counters, 16));
+  VQB_CUDA_TRY(cudaMemcpyFromSymbol(out18 + 2, g_dbg_cycles, 128));
+  unsigned long long z[16] = {0};
+  VQB_CUDA_TRY(cudaMemcpyToSymbol(g_dbg_counters, z, 16));
+  VQB_CUDA_TRY(cudaMemcpyToSymbol(g_dbg_cycles, z, 128));
+  return VQB_OK;
+}
+
 int search_timing(float* host_ms, int cap) {
   const int n = g_ev_count;
   for (int i = 0; i < n; ++i) {
@@ -613,3 +727,5 @@ int search_timing(float* host_ms, int cap) {
 }  // namespace vqb
 
 extern "C" int vqb_search_timing(float* host_ms, int cap) { return vqb::search_timing(host_ms, cap); }
+// bring-up aid, not part of include/vqb.h
+extern "C" int vqb_debug_counters(unsigned long long* out2) { return vqb::debug_counters(out2); }
