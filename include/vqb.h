@@ -133,6 +133,15 @@ int    vqb_ema_apply(const float* stats, float* cluster_size, float* embed_avg, 
                      float weight, double eps, int l2norm, int64_t H, int K, int d,
                      void* ws, size_t ws_bytes, void* stream);
 
+/* The two phases of vqb_ema_apply, for a codebook whose rows are sharded across GPUs: the Laplace term needs
+ * sum(cluster_size) over ALL shards, so the caller all-reduces `totals` (H floats) between the calls and passes
+ * the global code count k_total (the K*eps term of utils/general.py:154-156). */
+int    vqb_ema_apply_counts(const float* stats, float* cluster_size, float weight, int64_t H, int K, int d,
+                            float* totals_out, void* stream);
+int    vqb_ema_apply_rows(const float* stats, const float* cluster_size, float* embed_avg, float* embeddings,
+                          float weight, double eps, int64_t k_total, int l2norm, int64_t H, int K, int d,
+                          const float* totals, void* stream);
+
 /* ---- dead-code expiry scatter ---------------------------------------------------------
  * Replaces codebooks.py:241-243 for one codebook h: the j-th dead code (ascending index,
  * dead = cluster_size < threshold) takes row sample_rows[j] of x (l2-normalised first when

@@ -1,0 +1,85 @@
+"""world_size-2 Gloo tests (CPU) of the multi-GPU host logic: replica-consistent replacement sampling, the packed
+statistics all_reduce used by data parallel, and the min-key merge used by the sharded codebook."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _pack(score: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+    """Pure-torch mirror of vqb_minkey_pack (csrc/ema.cu), test-side only."""
+    u = score.view(torch.int32).to(torch.int64) & 0xFFFFFFFF
+    neg = (u >> 31) == 1
+    u = torch.where(neg, (~u) & 0xFFFFFFFF, u | 0x80000000)
+    u = u ^ 0x80000000
+    key = (u << 32) | (idx & 0xFFFFFFFF)
+    return torch.where(key >= (1 << 63), key - (1 << 64), key) if False else (key - ((key >> 63) << 64))
+
+
+def _worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "vector-quantization-by-ml_b200"))
+    from vqb200 import distributed as D
+    from vqb200.codebook import Codebook
+    res = {}
+    # 1. replica-consistent sampling: same vectors on both ranks, every vector is a row of some rank's data
+    torch.manual_seed(100 + rank)
+    local = torch.randn(50 + 10 * rank, 8) + 100 * rank
+    torch.manual_seed(7)          # rank 0's multinomial + both ranks' local draws
+    s = D.sample_vectors_distributed(local, 23, Codebook._draw_rows)
+    gathered = [torch.empty_like(s) for _ in range(world)]
+    dist.all_gather(gathered, s)
+    res["same"] = all(torch.equal(gathered[0], g) for g in gathered)
+    res["shape"] = tuple(s.shape)
+    alls = [torch.empty(50 + 10 * r, 8) for r in range(world)]
+    for r in range(world):
+        buf = local if r == rank else alls[r]
+        dist.broadcast(buf, src=r)
+        alls[r] = buf
+    union = torch.cat(alls)
+    res["member"] = bool(((s[:, None, :] == union[None]).all(-1).any(-1)).all())
+    # 2. data parallel: ONE packed all_reduce of (H,K,d+1) statistics == statistics of the concatenated batch
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(2, 64, 4, generator=g)                      # (rank, rows, d)
+    idx = torch.randint(0, 6, (2, 64), generator=g)
+    def stats_of(xr, ir):
+        oh = torch.nn.functional.one_hot(ir, 6).float()
+        return torch.cat([torch.einsum("nd,nc->cd", xr, oh), oh.sum(0)[:, None]], -1)[None]
+    st = stats_of(x[rank], idx[rank])
+    D.all_reduce_sum(st)
+    ref = stats_of(x.reshape(-1, 4), idx.reshape(-1))
+    res["stats"] = bool(torch.allclose(st, ref, rtol=1e-6, atol=1e-6)) and torch.equal(st[..., -1], ref[..., -1])
+    # 3. sharded codebook merge: min over ranks of (score, global index) keys, lowest index on ties
+    score = torch.tensor([[1.5, -2.0, 0.0, 3.0, -0.0, 7.0], [1.5, -2.5, 0.0, 2.0, 0.0, 7.0]])[rank]
+    gidx = torch.tensor([[3, 9, 4, 1, 2, 5], [11, 8, 12, 10, 15, 13]])[rank]
+    keys = _pack(score, gidx)
+    D.merge_min_keys(keys)
+    res["win_idx"] = (keys & 0xFFFFFFFF).tolist()
+    if rank == 0:
+        torch.save(res, out)
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_host_logic(tmp_path):
+    out = str(tmp_path / "res.pt")
+    mp.spawn(_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    res = torch.load(out)
+    assert res["same"] and res["shape"] == (23, 8) and res["member"]
+    assert res["stats"]
+    # scores: equal 1.5 -> lower index 3; -2.5 < -2.0 -> 8; 0.0 tie -> 4; 2.0 < 3.0 -> 10; -0.0 vs 0.0: -0.0 sorts first -> 2; 7 tie -> 5
+    assert res["win_idx"] == [3, 8, 4, 10, 2, 5]

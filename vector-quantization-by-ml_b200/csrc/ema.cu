@@ -487,22 +487,37 @@ extern "C" int vqb_ema_reduce(const void* x, int x_dtype, const int64_t* idx, co
   return VQB_OK;
 }
 
+extern "C" int vqb_ema_apply_counts(const float* stats, float* cluster_size, float weight, int64_t H, int K, int d,
+                                    float* totals_out, void* stream) {
+  VQB_REQUIRE(stats && cluster_size && totals_out, VQB_ERR_INVALID, "vqb_ema_apply_counts: null pointer");
+  VQB_REQUIRE(H > 0 && K > 0 && d > 0, VQB_ERR_INVALID, "vqb_ema_apply_counts: bad shape");
+  ema_apply_counts_kernel<<<(unsigned)H, 1024, 0, (cudaStream_t)stream>>>(stats, cluster_size, weight, K, d, totals_out);
+  VQB_LAUNCH_CHECK();
+  return VQB_OK;
+}
+
+extern "C" int vqb_ema_apply_rows(const float* stats, const float* cluster_size, float* embed_avg, float* embeddings,
+                                  float weight, double eps, int64_t k_total, int l2norm, int64_t H, int K, int d,
+                                  const float* totals, void* stream) {
+  VQB_REQUIRE(stats && cluster_size && embed_avg && embeddings && totals, VQB_ERR_INVALID,
+              "vqb_ema_apply_rows: null pointer");
+  VQB_REQUIRE(H > 0 && K > 0 && d > 0 && k_total >= K, VQB_ERR_INVALID, "vqb_ema_apply_rows: bad shape");
+  const int64_t rows = H * (int64_t)K;
+  ema_apply_rows_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(
+      stats, cluster_size, embed_avg, embeddings, weight, (float)eps, (float)((double)k_total * eps), l2norm, H, K, d,
+      totals);
+  VQB_LAUNCH_CHECK();
+  return VQB_OK;
+}
+
 extern "C" int vqb_ema_apply(const float* stats, float* cluster_size, float* embed_avg, float* embeddings,
                              float weight, double eps, int l2norm, int64_t H, int K, int d, void* ws,
                              size_t ws_bytes, void* stream) {
-  VQB_REQUIRE(stats && cluster_size && embed_avg && embeddings && ws, VQB_ERR_INVALID, "vqb_ema_apply: null pointer");
-  VQB_REQUIRE(H > 0 && K > 0 && d > 0, VQB_ERR_INVALID, "vqb_ema_apply: bad shape");
-  VQB_REQUIRE(ws_bytes >= (size_t)H * 4, VQB_ERR_WORKSPACE, "ema_apply workspace too small");
-  cudaStream_t st = (cudaStream_t)stream;
-  // the scratch for the totals is the tail of an EMA workspace if the caller passed one, else the head of ws
-  float* total = (float*)ws;
-  ema_apply_counts_kernel<<<(unsigned)H, 1024, 0, st>>>(stats, cluster_size, weight, K, d, total);
-  VQB_LAUNCH_CHECK();
-  const int64_t rows = H * (int64_t)K;
-  ema_apply_rows_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(
-      stats, cluster_size, embed_avg, embeddings, weight, (float)eps, (float)((double)K * eps), l2norm, H, K, d, total);
-  VQB_LAUNCH_CHECK();
-  return VQB_OK;
+  VQB_REQUIRE(ws != nullptr && ws_bytes >= (size_t)H * 4, VQB_ERR_WORKSPACE, "ema_apply workspace too small");
+  int rc = vqb_ema_apply_counts(stats, cluster_size, weight, H, K, d, (float*)ws, stream);
+  if (rc) return rc;
+  return vqb_ema_apply_rows(stats, cluster_size, embed_avg, embeddings, weight, eps, K, l2norm, H, K, d,
+                            (const float*)ws, stream);
 }
 
 extern "C" int vqb_expire_scatter(const void* x, int x_dtype, const int64_t* sample_rows, int64_t m, float threshold,

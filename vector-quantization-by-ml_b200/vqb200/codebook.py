@@ -184,10 +184,17 @@ class Codebook(nn.Module):
             return
         H, N, d = flat.shape
         counts = dead.sum(dim=-1).tolist()            # the reference syncs per codebook (:234)
+        from . import distributed as D
+        synced = self.use_ddp and self._kmeans_sync and self.distributed_replace_codes and D.is_distributed()
         for h in range(H):
             m = int(counts[h])
-            rows = self._draw_rows(N, m, flat.device)
-            ops.expire_scatter(flat[h], rows, float(self.threshold_ema_dead_code), float(self.reset_cluster_size),
+            if synced:
+                # reference codebooks.py:171-175: sample_vectors_distributed -> identical replacements on every rank
+                src = D.sample_vectors_distributed(flat[h], m, self._draw_rows)
+                rows = torch.arange(m, device=flat.device)
+            else:
+                src, rows = flat[h], self._draw_rows(N, m, flat.device)
+            ops.expire_scatter(src, rows, float(self.threshold_ema_dead_code), float(self.reset_cluster_size),
                                self.weights_l2norm, self.cluster_size.data[h], self.embed_avg.data[h],
                                self.embeddings.data[h])
         self._dirty = True

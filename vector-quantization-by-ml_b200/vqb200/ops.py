@@ -205,6 +205,23 @@ def ema_apply(stats: torch.Tensor, cluster_size: torch.Tensor, embed_avg: torch.
                                   L.stream_ptr(dev)), "vqb_ema_apply")
 
 
+def ema_apply_sharded(stats: torch.Tensor, cluster_size: torch.Tensor, embed_avg: torch.Tensor,
+                      embeddings: torch.Tensor, weight: float, eps: float, weights_l2norm: bool, k_total: int,
+                      all_reduce) -> None:
+    """vqb_ema_apply for a row-sharded codebook: `all_reduce(totals)` sums sum(cluster_size) over the shards."""
+    H, K, d1 = stats.shape
+    d = d1 - 1
+    dev = stats.device
+    totals = torch.empty(H, dtype=torch.float32, device=dev)
+    st = L.stream_ptr(dev)
+    L.check(L.lib().vqb_ema_apply_counts(L.ptr(stats), L.ptr(cluster_size), float(weight), H, K, d, L.ptr(totals), st),
+            "vqb_ema_apply_counts")
+    all_reduce(totals)
+    L.check(L.lib().vqb_ema_apply_rows(L.ptr(stats), L.ptr(cluster_size), L.ptr(embed_avg), L.ptr(embeddings),
+                                       float(weight), float(eps), int(k_total), int(weights_l2norm), H, K, d,
+                                       L.ptr(totals), st), "vqb_ema_apply_rows")
+
+
 def expire_scatter(x_rows: torch.Tensor, sample_rows: torch.Tensor, threshold: float, reset: float,
                    weights_l2norm: bool, cluster_size: torch.Tensor, embed_avg: torch.Tensor,
                    embeddings: torch.Tensor) -> None:
