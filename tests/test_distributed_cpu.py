@@ -53,6 +53,9 @@ def _worker(rank, world, port, out):
         alls[r] = buf
     union = torch.cat(alls)
     res["member"] = bool(((s[:, None, :] == union[None]).all(-1).any(-1)).all())
+    # ... and they are exactly the rows one process would draw from the concatenated batch with the same generator
+    torch.manual_seed(7)
+    res["as_single"] = torch.equal(s, union[Codebook._draw_rows(union.shape[0], 23, union.device)])
     # 2. data parallel: ONE packed all_reduce of (H,K,d+1) statistics == statistics of the concatenated batch
     g = torch.Generator().manual_seed(5)
     x = torch.randn(2, 64, 4, generator=g)                      # (rank, rows, d)
@@ -79,7 +82,7 @@ def test_two_rank_gloo_host_logic(tmp_path):
     out = str(tmp_path / "res.pt")
     mp.spawn(_worker, args=(2, _free_port(), out), nprocs=2, join=True)
     res = torch.load(out)
-    assert res["same"] and res["shape"] == (23, 8) and res["member"]
+    assert res["same"] and res["shape"] == (23, 8) and res["member"] and res["as_single"]
     assert res["stats"]
     # scores: equal 1.5 -> lower index 3; -2.5 < -2.0 -> 8; 0.0 tie -> 4; 2.0 < 3.0 -> 10; -0.0 vs 0.0: -0.0 sorts first -> 2; 7 tie -> 5
     assert res["win_idx"] == [3, 8, 4, 10, 2, 5]

@@ -152,7 +152,11 @@ class Codebook(nn.Module):
             N = data.shape[1]
         iters = int((self.kmeans_params or {"iter": 10})["iter"])
         sync = self.use_ddp and self._kmeans_sync
-        cents = torch.stack([data[h][self._draw_rows(N, K, data.device)] for h in range(H)], 0).contiguous()
+        from . import distributed as D
+        if sync and D.is_distributed():      # reference codebooks.py:164-168: identical centroids on every rank
+            cents = torch.stack([D.sample_vectors_distributed(data[h], K, self._draw_rows) for h in range(H)], 0)
+        else:
+            cents = torch.stack([data[h][self._draw_rows(N, K, data.device)] for h in range(H)], 0).contiguous()
         counts = torch.zeros(H, K, device=data.device)
         for _ in range(iters):
             cache = ops.prepare_codebook(cents, self.use_cosine_sim)

@@ -33,43 +33,35 @@ def merge_min_keys(keys: torch.Tensor, group=None) -> torch.Tensor:
     return keys
 
 
-# ---- replica-consistent sampling (reference utils/distributed.py:12-75) ---------------------------------------
-def _multinomial_counts(total: int, probs: torch.Tensor) -> torch.Tensor:
-    """utils/distributed.py:36-52: sequential binomials on the CPU generator of rank 0."""
-    probs = probs.cpu()
-    remaining = probs.new_full((), total)
-    rest = probs.new_ones(())
-    out = torch.empty_like(probs, dtype=torch.long)
-    for i, p in enumerate(probs):
-        s = torch.binomial(remaining, (p / rest).clamp(0, 1))
-        out[i] = s
-        remaining -= s
-        rest -= p
-    return out
-
-
+# ---- replica-consistent sampling ----------------------------------------------------------------------------------
 def sample_vectors_distributed(local: torch.Tensor, num: int, draw_rows: Callable, group=None) -> torch.Tensor:
-    """`num` vectors drawn from the union of all ranks' `local` (N_r, d) rows; identical result on every rank."""
+    """`num` vectors drawn from the union of all ranks' `local` (N_r, d) rows; identical result on every rank.
+
+    Same purpose as reference utils/distributed.py:55-75 (all_gather sizes -> rank-0 multinomial on the CPU ->
+    broadcast -> per-rank sampling -> W variable-size broadcasts), with three collectives and no host round trip
+    except rank 0's row count: rank 0 draws GLOBAL row ids with the very calls a single process would make on the
+    rank-concatenated batch (utils/general.py:62-66), broadcasts them, and one all_reduce(SUM) assembles the rows
+    (every rank contributes the rows it owns, zeros elsewhere).  So W ranks replace dead codes exactly like one
+    process on the concatenated batch with the same generator state.
+    """
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     dev = local.device
-    size = torch.tensor([local.shape[0]], dtype=torch.long, device=dev)
-    sizes = [torch.empty_like(size) for _ in range(world)]
-    dist.all_gather(sizes, size, group=group)
+    n_local = local.shape[0]
+    sizes = [torch.empty(1, dtype=torch.long, device=dev) for _ in range(world)]
+    dist.all_gather(sizes, torch.tensor([n_local], dtype=torch.long, device=dev), group=group)
     sizes = torch.cat(sizes)
+    ends = torch.cumsum(sizes, 0)
+    start = ends[rank] - sizes[rank]                       # device scalar: no host sync on ranks != 0
     if rank == 0:
-        per_rank = _multinomial_counts(num, sizes.float() / sizes.sum()).to(dev)
+        rows = draw_rows(int(ends[-1].item()), num, dev).to(torch.long)
     else:
-        per_rank = torch.empty(world, dtype=torch.long, device=dev)
-    dist.broadcast(per_rank, src=0, group=group)
-    counts = per_rank.tolist()
-    mine = local[draw_rows(local.shape[0], counts[rank], dev)].float().contiguous()
-    parts = []
-    for r, c in enumerate(counts):
-        buf = mine if r == rank else torch.empty((c, local.shape[1]), dtype=torch.float32, device=dev)
-        if c:
-            dist.broadcast(buf, src=r, group=group)
-        parts.append(buf)
-    return torch.cat(parts, 0)
+        rows = torch.empty(num, dtype=torch.long, device=dev)
+    dist.broadcast(rows, src=0, group=group)
+    mine = (rows >= start) & (rows < start + n_local)
+    picked = local[(rows - start).clamp_(0, max(n_local - 1, 0))].float()
+    out = torch.where(mine[:, None], picked, torch.zeros((), dtype=torch.float32, device=dev))
+    dist.all_reduce(out, op=dist.ReduceOp.SUM, group=group)
+    return out
 
 
 # ---- sharded codebook -----------------------------------------------------------------------------------------
