@@ -34,6 +34,22 @@ CPU_SAMPLE_ROWS = 16384                 # bounded sample for the CPU legs (N x K
 WORKLOAD = "C2: EuclideanCodebook search+EMA, N=1048576 latents x d=256, K=8192, bf16 latents"
 
 
+def ncu_traffic_bytes():
+    """dram__bytes_read.sum + dram__bytes_write.sum of one search-kernel launch, from the committed ncu --set full
+    capture of this same command (profiles/rNN_ncu_summary.json); None if there is no capture."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_summary.json")))
+    if not files:
+        return None
+    try:
+        for k in json.load(open(files[-1]))["ncu_full"]:
+            if "search_tc_kernel" in k["kernel"]:
+                return (k["dram_rd_MB"] + k["dram_wr_MB"]) * 1e6
+    except Exception:
+        return None
+    return None
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -280,7 +296,8 @@ def main():
                     "peak_source": pk["source"] + " bf16 burst (cuBLAS 8192^3); sustained %.1f" % pk["tflops_sustained"],
                     "frac_of_sustained": achieved / pk["tflops_sustained"],
                     "kernel_ms": tc_avg, "kernel_share_of_step": tc_avg / (ms / args.steps),
-                    "algorithmic_flops_per_launch": flops, "traffic": None}
+                    "algorithmic_flops_per_launch": flops, "traffic": ncu_traffic_bytes(),
+                    "traffic_unit": "bytes of DRAM read+write per launch (ncu --set full, profiles/)"}
         threads = os.cpu_count() or 1
         cpu_val, cpu_n = time_cpu_port(args.cpu_seconds, threads)
         sample = (f"{CPU_SAMPLE_ROWS} of {N_ROWS} latents per step x {cpu_n} steps (the reference materialises N x K: "

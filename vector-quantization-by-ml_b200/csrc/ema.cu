@@ -138,7 +138,7 @@ __global__ void ema_place_kernel(const int64_t* __restrict__ idx, const uint8_t*
 
 // one warp per 64 consecutive positions of the sorted order; lanes own columns {cb*128 + lane*4 .. +3}
 template <typename T>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 ema_segsum_kernel(const T* __restrict__ x, const int64_t* __restrict__ idx, const int* __restrict__ sorted,
                   const uint32_t* __restrict__ start, int64_t N, int K, int d, const int* __restrict__ scale_p,
                   unsigned long long* __restrict__ acc) {

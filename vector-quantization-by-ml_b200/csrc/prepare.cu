@@ -68,9 +68,10 @@ __global__ void prepare_latents_kernel(const T* __restrict__ x, int64_t rows, in
                                        __half* __restrict__ xb, float* __restrict__ xinv,
                                        uint32_t* __restrict__ scal) {
   const int lane = threadIdx.x & 31;
-  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  float n2 = 0.f, r2 = 0.f;
-  if (row < rows) {
+  const int wpb = blockDim.x >> 5;
+  float max_n2 = 0.f, max_r2 = 0.f;          // running maxima of this warp's rows (one atomic pair per BLOCK at the end)
+  for (int64_t row = (int64_t)blockIdx.x * wpb + (threadIdx.x >> 5); row < rows; row += (int64_t)gridDim.x * wpb) {
+    float n2 = 0.f, r2 = 0.f;
     const T* xr = x + row * (int64_t)d;
     __half* o = xb + row * (int64_t)dp;
     const bool vec = (d & 7) == 0;
@@ -125,17 +126,19 @@ __global__ void prepare_latents_kernel(const T* __restrict__ x, int64_t rows, in
         r2 += (v - back) * (v - back);
       }
     }
+    n2 = warp_sum(n2);
+    r2 = warp_sum(r2);
+    max_n2 = fmaxf(max_n2, n2);
+    max_r2 = fmaxf(max_r2, r2);
   }
-  n2 = warp_sum(n2);
-  r2 = warp_sum(r2);
-  // block-level max first, then one atomic per block
+  // block-level max, then one atomic pair per block
   __shared__ float s_n[32], s_r[32];
   const int w = threadIdx.x >> 5;
-  if (lane == 0) { s_n[w] = n2; s_r[w] = r2; }
+  if (lane == 0) { s_n[w] = max_n2; s_r[w] = max_r2; }
   __syncthreads();
   if (threadIdx.x == 0) {
     float mn = 0.f, mr = 0.f;
-    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { mn = fmaxf(mn, s_n[i]); mr = fmaxf(mr, s_r[i]); }
+    for (int i = 0; i < wpb; ++i) { mn = fmaxf(mn, s_n[i]); mr = fmaxf(mr, s_r[i]); }
     // fp32 accumulation of a sum of squares: inflate by (1 + dp * 2^-23) before the square root
     float infl = 1.f + (float)dp * 2.4e-7f;
     float a = sqrtf(mn * infl) * 1.00001f, b = sqrtf(mr * infl) * 1.00001f;
@@ -148,8 +151,16 @@ int launch_prepare_latents(const void* x, int x_dtype, int64_t rows, int d, int 
                            __half* xb, float* xinv, uint32_t* scal, cudaStream_t st) {
   VQB_REQUIRE(dp <= 512, VQB_ERR_UNSUPPORTED, "prepare_latents: d_pad %d > 512", dp);
   const int warps = 8;
-  const int64_t blocks = (rows + warps - 1) / warps;
-  VQB_REQUIRE(blocks < (1ll << 31), VQB_ERR_UNSUPPORTED, "too many latent rows: %lld", (long long)rows);
+  int64_t blocks = (rows + warps - 1) / warps;
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  if (blocks > (int64_t)sms * 8) blocks = (int64_t)sms * 8;     // persistent: rows strided over the grid
+  if (blocks < 1) blocks = 1;
   VQB_DISPATCH_DTYPE(x_dtype, T,
     prepare_latents_kernel<T><<<(unsigned)blocks, warps * 32, 0, st>>>((const T*)x, rows, d, dp, xb, xinv, scal));
   VQB_LAUNCH_CHECK();

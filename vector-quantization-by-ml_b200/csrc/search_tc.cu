@@ -177,37 +177,42 @@ __device__ __forceinline__ float pack_id(float v, uint32_t mask) {
   return __uint_as_float(r);
 }
 
-// The epilogue is a software pipeline over 16-column chunks of one thread's row (8 chunks per N tile):
+// The epilogue is a software pipeline over 32-column chunks of one thread's row (4 chunks per N tile).  Measured
+// with the cycle counters below: a tcgen05.ld -> wait round trip costs ~400 cycles while the tensor pipe is
+// accumulating into TMEM, so the per-tile epilogue time is (#round trips) x (latency + exposed work).
 //   scores : wait for the chunk's accumulators (tcgen05.wait::ld), score = acc*ninv + bias (FFMA, undoes the operand
 //            scales and adds |c|^2/2 - E_k), chunk minimum with an FMNMX3 tree.  The accumulator registers are dead
 //            afterwards, so the NEXT chunk's tcgen05.ld is issued right here and is in flight during
 //   rank   : FAST PATH -- a score can be a candidate of the final answer only if it is <= thr_final = m + |m| slack
 //            + 2E (m = final row minimum); thr is monotone in m and the running minimum only decreases, so if every
 //            score of the chunk exceeds t_run = thr(running minimum, Emax) for every row of the warp, the chunk holds
-//            no candidate and nothing else is done.  SLOW PATH -- 6-bit id PARITY*32 + CH*4 + i packed into the low
+//            no candidate and nothing else is done.  SLOW PATH -- 6-bit id PARITY*32 + CH*8 + i packed into the low
 //            mantissa bits (column j = 4*i + c is class c), running top-2 per class, exactly as if no chunk had been
 //            skipped.
-__device__ __forceinline__ float chunk_scores(const uint32_t (&r)[16], const float4* bias4, float ninv,
-                                              float (&key)[16]) {
-  float4 b[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) b[i] = bias4[i];          // shared memory, same address in every lane: broadcast
+__device__ __forceinline__ float chunk_scores(const uint32_t (&r)[32], const float4* bias4, float ninv,
+                                              float (&key)[32]) {
   tmem_ld_wait();
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    key[4 * i + 0] = fmaf(__uint_as_float(r[4 * i + 0]), ninv, b[i].x);
-    key[4 * i + 1] = fmaf(__uint_as_float(r[4 * i + 1]), ninv, b[i].y);
-    key[4 * i + 2] = fmaf(__uint_as_float(r[4 * i + 2]), ninv, b[i].z);
-    key[4 * i + 3] = fmaf(__uint_as_float(r[4 * i + 3]), ninv, b[i].w);
+  for (int i = 0; i < 8; ++i) {
+    const float4 b = bias4[i];          // shared memory, same address in every lane: broadcast
+    key[4 * i + 0] = fmaf(__uint_as_float(r[4 * i + 0]), ninv, b.x);
+    key[4 * i + 1] = fmaf(__uint_as_float(r[4 * i + 1]), ninv, b.y);
+    key[4 * i + 2] = fmaf(__uint_as_float(r[4 * i + 2]), ninv, b.z);
+    key[4 * i + 3] = fmaf(__uint_as_float(r[4 * i + 3]), ninv, b.w);
   }
   float cm[4];
 #pragma unroll
-  for (int c = 0; c < 4; ++c) cm[c] = fminf(min3f(key[c], key[4 + c], key[8 + c]), key[12 + c]);
+  for (int c = 0; c < 4; ++c) {
+    cm[c] = min3f(key[c], key[4 + c], key[8 + c]);
+    cm[c] = min3f(cm[c], key[12 + c], key[16 + c]);
+    cm[c] = min3f(cm[c], key[20 + c], key[24 + c]);
+    cm[c] = fminf(cm[c], key[28 + c]);
+  }
   return fminf(min3f(cm[0], cm[1], cm[2]), cm[3]);
 }
 
 template <uint32_t ID>
-__device__ __forceinline__ void pack_row4(float (&key)[16], int i, uint32_t mask) {
+__device__ __forceinline__ void pack_row4(float (&key)[32], int i, uint32_t mask) {
   key[4 * i + 0] = pack_id<ID>(key[4 * i + 0], mask);
   key[4 * i + 1] = pack_id<ID>(key[4 * i + 1], mask);
   key[4 * i + 2] = pack_id<ID>(key[4 * i + 2], mask);
@@ -215,7 +220,7 @@ __device__ __forceinline__ void pack_row4(float (&key)[16], int i, uint32_t mask
 }
 
 template <int PARITY, int CH>
-__device__ __forceinline__ void chunk_rank(float (&key)[16], float cmin, uint32_t idmask, float tconst, float& m_run,
+__device__ __forceinline__ void chunk_rank(float (&key)[32], float cmin, uint32_t idmask, float tconst, float& m_run,
                                            float& t_run, float (&a1)[4], float (&a2)[4], bool& any_slow, int dbg) {
   bool trig = __any_sync(0xffffffffu, cmin <= t_run);
   if (dbg) {   // bring-up knobs: 4 = never rank, 8 = always rank, 16 = count ranked / skipped chunks
@@ -225,15 +230,15 @@ __device__ __forceinline__ void chunk_rank(float (&key)[16], float cmin, uint32_
   }
   if (trig) {
     any_slow = true;
-    constexpr uint32_t kBase = (uint32_t)(PARITY * 32 + CH * 4);
-    pack_row4<kBase + 0>(key, 0, idmask);
-    pack_row4<kBase + 1>(key, 1, idmask);
-    pack_row4<kBase + 2>(key, 2, idmask);
-    pack_row4<kBase + 3>(key, 3, idmask);
+    constexpr uint32_t kBase = (uint32_t)(PARITY * 32 + CH * 8);
+    pack_row4<kBase + 0>(key, 0, idmask); pack_row4<kBase + 1>(key, 1, idmask);
+    pack_row4<kBase + 2>(key, 2, idmask); pack_row4<kBase + 3>(key, 3, idmask);
+    pack_row4<kBase + 4>(key, 4, idmask); pack_row4<kBase + 5>(key, 5, idmask);
+    pack_row4<kBase + 6>(key, 6, idmask); pack_row4<kBase + 7>(key, 7, idmask);
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      top2_pair(a1[c], a2[c], key[c], key[4 + c]);
-      top2_pair(a1[c], a2[c], key[8 + c], key[12 + c]);
+    for (int i = 0; i < 8; i += 2) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) top2_pair(a1[c], a2[c], key[4 * i + c], key[4 * i + 4 + c]);
     }
     if (cmin < m_run) {
       m_run = cmin;
@@ -257,9 +262,13 @@ __device__ __forceinline__ void top3_insert(float& M1, float& M2, float& M3, int
 // ------------------------------------------------------------------------------------------
 // kernel
 // ------------------------------------------------------------------------------------------
-constexpr int kThreads = 384;          // 12 warps: 0 TMA, 1 MMA, 2 TMEM alloc, 3 spare, 4..11 epilogue
-constexpr int kEpiWarp0 = 4;
+// 12 warps.  The warp arbiter of an SM sub-partition prefers the highest warp id, and the TMA producer and the MMA
+// issuer are single threads that must never wait for an issue slot behind the instruction-heavy epilogue warps
+// sharing their sub-partition -- so they get the HIGHEST ids: 0..7 epilogue, 8 bias stager, 9 TMEM allocator,
+// 10 TMA producer, 11 MMA issuer.
+constexpr int kThreads = 384;
 constexpr int kNumEpiWarps = 8;
+constexpr int kWarpStager = 8, kWarpAlloc = 9, kWarpTma = 10, kWarpMma = 11;
 constexpr int kSlabBytes = kBlockM * kBlockK * 2;     // 16 KB: 128 rows x 64 fp16
 constexpr int kStageBytes = kBlockN * kBlockK * 2;    // 32 KB: 256 codes x 64 fp16
 constexpr int kMaxKB = 8;                              // d_pad <= 512
@@ -316,11 +325,11 @@ search_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     atomicExch(P.scal + 5, 1u);
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) P.scal[4] = 1u;   // "tensor-core pass ran" marker for vqb_search_stats
-  if (warp == 0 && lane == 0) {
+  if (warp == kWarpTma && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_c) : "memory");
   }
-  if (warp == 1 && lane == 0) {
+  if (warp == kWarpMma && lane == 0) {
     for (int i = 0; i < P.S; ++i) {
       mbar_init(smem_u32(&bars->full[i]), 1);
       mbar_init(smem_u32(&bars->empty[i]), CLUSTER);
@@ -336,7 +345,7 @@ search_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     }
     fence_barrier_init();
   }
-  if (warp == 2) {
+  if (warp == kWarpAlloc) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)),
                  "n"(kTmemCols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -346,7 +355,7 @@ search_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
 
-  if (warp == 0) {
+  if (warp == kWarpTma) {
     // =============================== TMA producer ===============================
     if (lane == 0) {
       uint32_t stage = 0, ph = 0, a_ph = 0;
@@ -387,7 +396,7 @@ search_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
         atomicAdd(g_dbg_cycles + 2, w_e);
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == kWarpMma) {
     // =============================== MMA issuer ===============================
     if (lane == 0) {
       uint32_t stage = 0, ph = 0, a_ph = 0, acc = 0, acc_ph = 0;
@@ -428,7 +437,7 @@ search_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
         atomicAdd(g_dbg_cycles + 6, w_f);
       }
     }
-  } else if (warp == 3) {
+  } else if (warp == kWarpStager) {
     // =============================== bias stager ===============================
     // Only ~34 KB of L1 is left next to 193 KB of dynamic smem, and the bias vector (4 B per code) is re-read for
     // every row tile, so global loads in the epilogue would miss L1 and sit in its dependency chain.  This warp
@@ -449,23 +458,23 @@ search_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
         if (++acc == 2) { acc = 0; acc_ph ^= 1u; }
       }
     }
-  } else if (warp >= kEpiWarp0) {
+  } else if (warp < kNumEpiWarps) {
     // =============================== epilogue: bias + packed running top-2 ===============================
     const int q = warp & 3;                       // TMEM lane quadrant this warp may touch
-    const int half = (warp - kEpiWarp0) >> 2;     // which 128 of the tile's 256 columns
+    const int half = warp >> 2;                   // which 128 of the tile's 256 columns
     uint32_t acc = 0, acc_ph = 0;
     const float INF = __int_as_float(0x7f800000);
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + half * 128;
     // Emax * (2 + slack): the part of the candidate threshold that does not depend on the row minimum
     const float tconst = __uint_as_float(P.scal[6]) * (2.f + kPackSlackTC);
-    const bool prof = (P.dbg & 32) != 0 && warp == kEpiWarp0;
+    const bool prof = (P.dbg & 32) != 0 && warp == 0;
     unsigned long long w_tf = 0, w_bias = 0;
     const long long t_begin = clock64();
-    uint32_t r[16];
+    uint32_t r[32];
     if (cid < G) {   // pipeline prologue: first chunk of the very first tile (later ones are prefetched in the loop)
       mbar_wait(smem_u32(&bars->tmem_full[0]), 0);
       tc_fence_after();
-      TMEM_LD16(lane_addr, r);
+      TMEM_LD32(lane_addr, r);
     }
     for (int g = cid; g < G; g += num_clusters) {
       const int h = g / P.GPH;
@@ -494,19 +503,19 @@ search_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
             const uint32_t taddr = lane_addr + acc * (uint32_t)kBlockN;
             mbar_wait_t(smem_u32(&bars->bias_full[acc]), acc_ph, prof, w_bias);
             const float4* bias4 = reinterpret_cast<const float4*>(bars->bias[acc] + half * 128);
-            float key[16];
+            float key[32];
             float cmin;
 #define VQB_CHUNK(CH)                                                                                      \
-            cmin = chunk_scores(r, bias4 + (CH) * 4, ninv, key);                                           \
-            TMEM_LD16(taddr + ((CH) + 1) * 16, r);                                                         \
+            cmin = chunk_scores(r, bias4 + (CH) * 8, ninv, key);                                           \
+            TMEM_LD32(taddr + ((CH) + 1) * 32, r);                                                         \
             if (par == 0) chunk_rank<0, (CH)>(key, cmin, idmask, tconst, m_run, t_run, a1, a2, any_slow, P.dbg); \
             else chunk_rank<1, (CH)>(key, cmin, idmask, tconst, m_run, t_run, a1, a2, any_slow, P.dbg);
-            VQB_CHUNK(0) VQB_CHUNK(1) VQB_CHUNK(2) VQB_CHUNK(3) VQB_CHUNK(4) VQB_CHUNK(5) VQB_CHUNK(6)
+            VQB_CHUNK(0) VQB_CHUNK(1) VQB_CHUNK(2)
 #undef VQB_CHUNK
             // last chunk: once its scores are formed every TMEM read of this tile is complete -> hand the buffer
             // back to the MMA warp, then start loading the next tile's first chunk (before this chunk's ranking
             // work if that accumulator is already complete)
-            cmin = chunk_scores(r, bias4 + 28, ninv, key);
+            cmin = chunk_scores(r, bias4 + 24, ninv, key);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&bars->tmem_empty[acc]));
@@ -515,15 +524,15 @@ search_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
             bool issued = false;
             if (more && mbar_try(smem_u32(&bars->tmem_full[acc]), acc_ph)) {
               tc_fence_after();
-              TMEM_LD16(lane_addr + acc * (uint32_t)kBlockN, r);
+              TMEM_LD32(lane_addr + acc * (uint32_t)kBlockN, r);
               issued = true;
             }
-            if (par == 0) chunk_rank<0, 7>(key, cmin, idmask, tconst, m_run, t_run, a1, a2, any_slow, P.dbg);
-            else chunk_rank<1, 7>(key, cmin, idmask, tconst, m_run, t_run, a1, a2, any_slow, P.dbg);
+            if (par == 0) chunk_rank<0, 3>(key, cmin, idmask, tconst, m_run, t_run, a1, a2, any_slow, P.dbg);
+            else chunk_rank<1, 3>(key, cmin, idmask, tconst, m_run, t_run, a1, a2, any_slow, P.dbg);
             if (more && !issued) {
               mbar_wait_t(smem_u32(&bars->tmem_full[acc]), acc_ph, prof, w_tf);
               tc_fence_after();
-              TMEM_LD16(lane_addr + acc * (uint32_t)kBlockN, r);
+              TMEM_LD32(lane_addr + acc * (uint32_t)kBlockN, r);
             }
           }
         }
@@ -566,7 +575,7 @@ search_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
   // teardown: everything issued has been consumed (epilogue waited on the last tmem_full)
   tc_fence_before();
   if (CLUSTER > 1) cluster_sync_all(); else __syncthreads();
-  if (warp == 2) {
+  if (warp == kWarpAlloc) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
   }
 }
