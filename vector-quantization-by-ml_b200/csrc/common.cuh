@@ -42,7 +42,7 @@ extern int64_t g_launch_count;   // every kernel launch is followed by VQB_LAUNC
 constexpr int kBlockM = 128;   // latent rows per CTA tile (TMEM lanes)
 constexpr int kBlockN = 256;   // codes per N tile (UMMA N)
 constexpr int kBlockK = 64;    // bf16 elements per k-block = one 128B swizzle atom
-constexpr int kNumCand = 24;   // candidates kept per row: 2 column-halves x 4 classes x top-3
+constexpr int kNumCand = 24;   // candidates kept per row: 4 column quarters x 2 classes x top-3
 constexpr float kPadBias = 3.0e38f;
 
 __host__ __device__ inline int round_up(int a, int b) { return (a + b - 1) / b * b; }

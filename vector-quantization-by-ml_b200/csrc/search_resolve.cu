@@ -7,8 +7,8 @@
 //   The kernel stores L_k = a_k (already lowered by E_k): L_k <= e_k <= L_k + 2 E_k.
 //   With j = argmin_k L_k the true argmin k* satisfies L_k* <= e_k* <= e_j <= L_j + 2 E_j, so
 //   every possible winner has L <= thr := L_j + 2 E_j (+ slack for the 5 id bits packed into L).
-//   The epilogue keeps, per 64-column group (one class of one column half of a pair of N tiles), the two
-//   smallest L, and per class (8 per row) the three smallest of those.  Therefore a possible winner is missing only if
+//   The epilogue keeps, per 64-column group (one class of one column quarter of a pair of N tiles), the two
+//   smallest L, and per class (8 per row: 4 quarters x 2 classes) the three smallest of those.  Therefore a possible winner is missing only if
 //     (i)  the third entry of some class is <= thr (a fourth could exist)  -> full exact rescan, or
 //     (ii) two entries <= thr come from the same 64-column group (a third could hide there)
 //                                                                          -> rescan those 64 columns.
@@ -28,6 +28,7 @@ template <typename T>
 __device__ __forceinline__ double row_norm2(const T* __restrict__ xr, int d) {
   double s = 0.0;
   if ((d & 3) == 0) {
+#pragma unroll 8
     for (int j = 0; j < d; j += 4) {
       float4 v = load4<T>(xr + j);
       s = fma((double)v.x, (double)v.x, s); s = fma((double)v.y, (double)v.y, s);
@@ -45,6 +46,7 @@ __device__ __forceinline__ float exact_score(const T* __restrict__ xr, const flo
                                              double xn2) {
   double dot = 0.0, cn2 = 0.0;
   if ((d & 3) == 0) {
+#pragma unroll 8          // 16 independent loads in flight; the fma chains keep their order (same result)
     for (int j = 0; j < d; j += 4) {
       float4 a = load4<T>(xr + j);
       float4 c = __ldg(reinterpret_cast<const float4*>(cr + j));
@@ -200,10 +202,10 @@ resolve_rerank_kernel(const T* __restrict__ x, const float* __restrict__ cb, con
       const int src = __ffs(reqs) - 1;
       reqs &= reqs - 1;
       const int c0 = __shfl_sync(0xffffffffu, code, src);
-      const int g = src / 3;                                     // group = half*4 + class
+      const int g = src / 3;                                     // group = quarter*2 + class
 #pragma unroll 1
       for (int t = 0; t < 2; ++t) {                              // the group spans a pair of N tiles: 64 columns
-        const int k = ((c0 >> 9) * 2 + t) * kBlockN + (g >> 2) * 128 + (g & 3) + 4 * lane;
+        const int k = ((c0 >> 9) * 2 + t) * kBlockN + (g >> 1) * 64 + (g & 1) + 2 * lane;
         if (k < K) {
           const float s = exact_score<T>(xr, cbh + (int64_t)k * d, d, metric, xn2);
           if (s < best || (s == best && k < bi)) { best = s; bi = k; }

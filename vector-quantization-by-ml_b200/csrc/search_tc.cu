@@ -3,9 +3,9 @@
 // Replaces reference codebooks.py:386 (-cdist / einsum: an N x K fp32 matrix in HBM) and
 // utils/general.py:128-129 (argmax + one_hot) with ONE persistent kernel:
 //
-//   TMA (cp.async.bulk.tensor, 128B swizzle)  ->  smem ring      (warp 0, one lane)
-//   tcgen05.mma kind::f16, fp16 x fp16 -> fp32 in TMEM            (warp 1, one lane)
-//   tcgen05.ld + bias + packed running top-2 per row              (warps 4..11)
+//   TMA (cp.async.bulk.tensor, 128B swizzle)  ->  smem ring      (one lane of the TMA warp)
+//   tcgen05.mma kind::f16, fp16 x fp16 -> fp32 in TMEM            (one lane of the MMA warp)
+//   tcgen05.ld + bias + packed running top-2 per row              (16 epilogue warps)
 //
 // Per CTA: a 128-row tile of latents stays resident in smem (A operand, d/64 slabs of 16 KB);
 // the whole codebook streams through a ring of 32 KB stages (B operand, 256 codes x 64 dims).
@@ -17,8 +17,8 @@
 // Operands are fp16 with exact power-of-two scales (per latent row, per codebook) that the epilogue
 // undoes with the same FFMA that adds the bias.
 // The scores are lower bounds  L_k = |c_k|^2/2 - E_k - x~.c~_k  (bias precomputed per search,
-// prepare.cu); each row keeps, for 8 disjoint column groups, the three smallest L (low 6 mantissa
-// bits carry the column id inside a 64-column group = one class of one column half of a PAIR of N tiles).  search_resolve.cu turns these 16 candidates into
+// prepare.cu); each row keeps, for 8 disjoint column groups (4 column quarters x 2 classes), the three smallest L
+// (low 6 mantissa bits carry the column id inside a 64-column group = one class of one quarter of a PAIR of N tiles).  search_resolve.cu turns these 16 candidates into
 // the exact fp32 argmin or proves that it cannot and flags the row for an exact rescan.
 // (tile-local top-2 per 32-column group feeds a running top-3 per class: see search_resolve.cu)
 #include <cuda.h>
@@ -177,9 +177,10 @@ __device__ __forceinline__ float pack_id(float v, uint32_t mask) {
   return __uint_as_float(r);
 }
 
-// The epilogue is a software pipeline over 32-column chunks of one thread's row (4 chunks per N tile).  Measured
-// with the cycle counters below: a tcgen05.ld -> wait round trip costs ~400 cycles while the tensor pipe is
-// accumulating into TMEM, so the per-tile epilogue time is (#round trips) x (latency + exposed work).
+// The epilogue is a software pipeline over 16-column chunks of one thread's row: a thread owns one row (TMEM lane)
+// and a 64-column quarter of the tile = 4 chunks.  Measured with the cycle counters below: a tcgen05.ld -> wait round
+// trip costs ~400 cycles of latency plus ~8 cycles per column of transfer while the tensor pipe is accumulating into
+// TMEM; with four epilogue warps per sub-partition those waits overlap.
 //   scores : wait for the chunk's accumulators (tcgen05.wait::ld), score = acc*ninv + bias (FFMA, undoes the operand
 //            scales and adds |c|^2/2 - E_k), chunk minimum with an FMNMX3 tree.  The accumulator registers are dead
 //            afterwards, so the NEXT chunk's tcgen05.ld is issued right here and is in flight during
@@ -187,13 +188,13 @@ __device__ __forceinline__ float pack_id(float v, uint32_t mask) {
 //            + 2E (m = final row minimum); thr is monotone in m and the running minimum only decreases, so if every
 //            score of the chunk exceeds t_run = thr(running minimum, Emax) for every row of the warp, the chunk holds
 //            no candidate and nothing else is done.  SLOW PATH -- 6-bit id PARITY*32 + CH*8 + i packed into the low
-//            mantissa bits (column j = 4*i + c is class c), running top-2 per class, exactly as if no chunk had been
+//            mantissa bits (column j = 2*i + c is class c), running top-2 per class, exactly as if no chunk had been
 //            skipped.
-__device__ __forceinline__ float chunk_scores(const uint32_t (&r)[32], const float4* bias4, float ninv,
-                                              float (&key)[32]) {
+__device__ __forceinline__ float chunk_scores(const uint32_t (&r)[16], const float4* bias4, float ninv,
+                                              float (&key)[16]) {
   tmem_ld_wait();
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
+  for (int i = 0; i < 4; ++i) {
     const float4 b = bias4[i];          // shared memory, same address in every lane: broadcast
     key[4 * i + 0] = fmaf(__uint_as_float(r[4 * i + 0]), ninv, b.x);
     key[4 * i + 1] = fmaf(__uint_as_float(r[4 * i + 1]), ninv, b.y);
@@ -202,26 +203,19 @@ __device__ __forceinline__ float chunk_scores(const uint32_t (&r)[32], const flo
   }
   float cm[4];
 #pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    cm[c] = min3f(key[c], key[4 + c], key[8 + c]);
-    cm[c] = min3f(cm[c], key[12 + c], key[16 + c]);
-    cm[c] = min3f(cm[c], key[20 + c], key[24 + c]);
-    cm[c] = fminf(cm[c], key[28 + c]);
-  }
+  for (int c = 0; c < 4; ++c) cm[c] = fminf(min3f(key[c], key[4 + c], key[8 + c]), key[12 + c]);
   return fminf(min3f(cm[0], cm[1], cm[2]), cm[3]);
 }
 
 template <uint32_t ID>
-__device__ __forceinline__ void pack_row4(float (&key)[32], int i, uint32_t mask) {
-  key[4 * i + 0] = pack_id<ID>(key[4 * i + 0], mask);
-  key[4 * i + 1] = pack_id<ID>(key[4 * i + 1], mask);
-  key[4 * i + 2] = pack_id<ID>(key[4 * i + 2], mask);
-  key[4 * i + 3] = pack_id<ID>(key[4 * i + 3], mask);
+__device__ __forceinline__ void pack_pair(float (&key)[16], int i, uint32_t mask) {
+  key[2 * i + 0] = pack_id<ID>(key[2 * i + 0], mask);
+  key[2 * i + 1] = pack_id<ID>(key[2 * i + 1], mask);
 }
 
 template <int PARITY, int CH>
-__device__ __forceinline__ void chunk_rank(float (&key)[32], float cmin, uint32_t idmask, float tconst, float& m_run,
-                                           float& t_run, float (&a1)[4], float (&a2)[4], bool& any_slow, int dbg) {
+__device__ __forceinline__ void chunk_rank(float (&key)[16], float cmin, uint32_t idmask, float tconst, float& m_run,
+                                           float& t_run, float (&a1)[2], float (&a2)[2], bool& any_slow, int dbg) {
   bool trig = __any_sync(0xffffffffu, cmin <= t_run);
   if (dbg) {   // bring-up knobs: 4 = never rank, 8 = always rank, 16 = count ranked / skipped chunks
     if (dbg & 4) trig = false;
@@ -231,14 +225,14 @@ __device__ __forceinline__ void chunk_rank(float (&key)[32], float cmin, uint32_
   if (trig) {
     any_slow = true;
     constexpr uint32_t kBase = (uint32_t)(PARITY * 32 + CH * 8);
-    pack_row4<kBase + 0>(key, 0, idmask); pack_row4<kBase + 1>(key, 1, idmask);
-    pack_row4<kBase + 2>(key, 2, idmask); pack_row4<kBase + 3>(key, 3, idmask);
-    pack_row4<kBase + 4>(key, 4, idmask); pack_row4<kBase + 5>(key, 5, idmask);
-    pack_row4<kBase + 6>(key, 6, idmask); pack_row4<kBase + 7>(key, 7, idmask);
+    pack_pair<kBase + 0>(key, 0, idmask); pack_pair<kBase + 1>(key, 1, idmask);
+    pack_pair<kBase + 2>(key, 2, idmask); pack_pair<kBase + 3>(key, 3, idmask);
+    pack_pair<kBase + 4>(key, 4, idmask); pack_pair<kBase + 5>(key, 5, idmask);
+    pack_pair<kBase + 6>(key, 6, idmask); pack_pair<kBase + 7>(key, 7, idmask);
 #pragma unroll
     for (int i = 0; i < 8; i += 2) {
-#pragma unroll
-      for (int c = 0; c < 4; ++c) top2_pair(a1[c], a2[c], key[4 * i + c], key[4 * i + 4 + c]);
+      top2_pair(a1[0], a2[0], key[2 * i + 0], key[2 * i + 2]);
+      top2_pair(a1[1], a2[1], key[2 * i + 1], key[2 * i + 3]);
     }
     if (cmin < m_run) {
       m_run = cmin;
@@ -262,13 +256,12 @@ __device__ __forceinline__ void top3_insert(float& M1, float& M2, float& M3, int
 // ------------------------------------------------------------------------------------------
 // kernel
 // ------------------------------------------------------------------------------------------
-// 12 warps.  The warp arbiter of an SM sub-partition prefers the highest warp id, and the TMA producer and the MMA
-// issuer are single threads that must never wait for an issue slot behind the instruction-heavy epilogue warps
-// sharing their sub-partition -- so they get the HIGHEST ids: 0..7 epilogue, 8 bias stager, 9 TMEM allocator,
-// 10 TMA producer, 11 MMA issuer.
-constexpr int kThreads = 384;
-constexpr int kNumEpiWarps = 8;
-constexpr int kWarpStager = 8, kWarpAlloc = 9, kWarpTma = 10, kWarpMma = 11;
+// 20 warps: 0..15 epilogue (4 per SM sub-partition: TMEM-load latencies of one warp hide behind the other three),
+// 16 bias stager, 17 TMEM allocator, 18 TMA producer, 19 MMA issuer.  Epilogue warp w reads TMEM lane quadrant
+// w & 3 (hardware rule: a warp may only touch lanes 32*(warp%4)..+31) and the 64-column quarter w >> 2 of a tile.
+constexpr int kThreads = 640;
+constexpr int kNumEpiWarps = 16;
+constexpr int kWarpStager = 16, kWarpAlloc = 17, kWarpTma = 18, kWarpMma = 19;
 constexpr int kSlabBytes = kBlockM * kBlockK * 2;     // 16 KB: 128 rows x 64 fp16
 constexpr int kStageBytes = kBlockN * kBlockK * 2;    // 32 KB: 256 codes x 64 fp16
 constexpr int kMaxKB = 8;                              // d_pad <= 512
@@ -461,40 +454,39 @@ search_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
   } else if (warp < kNumEpiWarps) {
     // =============================== epilogue: bias + packed running top-2 ===============================
     const int q = warp & 3;                       // TMEM lane quadrant this warp may touch
-    const int half = warp >> 2;                   // which 128 of the tile's 256 columns
+    const int quarter = warp >> 2;                // which 64 of the tile's 256 columns
     uint32_t acc = 0, acc_ph = 0;
     const float INF = __int_as_float(0x7f800000);
-    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + half * 128;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + quarter * 64;
     // Emax * (2 + slack): the part of the candidate threshold that does not depend on the row minimum
     const float tconst = __uint_as_float(P.scal[6]) * (2.f + kPackSlackTC);
     const bool prof = (P.dbg & 32) != 0 && warp == 0;
     unsigned long long w_tf = 0, w_bias = 0;
     const long long t_begin = clock64();
-    uint32_t r[32];
+    uint32_t r[16];
     if (cid < G) {   // pipeline prologue: first chunk of the very first tile (later ones are prefetched in the loop)
       mbar_wait(smem_u32(&bars->tmem_full[0]), 0);
       tc_fence_after();
-      TMEM_LD32(lane_addr, r);
+      TMEM_LD16(lane_addr, r);
     }
     for (int g = cid; g < G; g += num_clusters) {
       const int h = g / P.GPH;
       const int mt = (g - h * P.GPH) * CLUSTER + (int)rank;
       const int64_t row = (int64_t)mt * kBlockM + q * 32 + lane;
-      float M1[4], M2[4], M3[4];
-      int C1[4], C2[4], C3[4];
+      float M1[2], M2[2], M3[2];
+      int C1[2], C2[2], C3[2];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) { M1[c] = INF; M2[c] = INF; M3[c] = INF; C1[c] = -1; C2[c] = -1; C3[c] = -1; }
+      for (int c = 0; c < 2; ++c) { M1[c] = INF; M2[c] = INF; M3[c] = INF; C1[c] = -1; C2[c] = -1; C3[c] = -1; }
       // acc = (x s_row).(c s_c)  ->  score = bias - acc / (s_row s_c): one FFMA per element
       const float ninv = row < P.N ? -(P.xinv[(size_t)h * P.N + row] * P.chdr[h * 4 + 1]) : 0.f;
-
       // the id mask lives in a register so that "(bits & mask) | id" is a single LOP3 (opaque to constant folding)
       uint32_t idmask;
       asm volatile("mov.u32 %0, 0xFFFFFFC0;" : "=r"(idmask));
       float m_run = INF, t_run = INF;              // running row minimum (this thread's columns) and its threshold
       for (int nt = 0; nt < P.NT; nt += 2) {       // N tiles in pairs: one top-3 merge per 512 codes
-        float a1[4], a2[4];
+        float a1[2], a2[2];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) { a1[c] = INF; a2[c] = INF; }
+        for (int c = 0; c < 2; ++c) { a1[c] = INF; a2[c] = INF; }
         bool any_slow = false;
 #pragma unroll
         for (int par = 0; par < 2; ++par) {
@@ -502,12 +494,12 @@ search_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
             // r[] already holds (or is receiving) chunk 0 of this tile
             const uint32_t taddr = lane_addr + acc * (uint32_t)kBlockN;
             mbar_wait_t(smem_u32(&bars->bias_full[acc]), acc_ph, prof, w_bias);
-            const float4* bias4 = reinterpret_cast<const float4*>(bars->bias[acc] + half * 128);
-            float key[32];
+            const float4* bias4 = reinterpret_cast<const float4*>(bars->bias[acc] + quarter * 64);
+            float key[16];
             float cmin;
 #define VQB_CHUNK(CH)                                                                                      \
-            cmin = chunk_scores(r, bias4 + (CH) * 8, ninv, key);                                           \
-            TMEM_LD32(taddr + ((CH) + 1) * 32, r);                                                         \
+            cmin = chunk_scores(r, bias4 + (CH) * 4, ninv, key);                                           \
+            TMEM_LD16(taddr + ((CH) + 1) * 16, r);                                                         \
             if (par == 0) chunk_rank<0, (CH)>(key, cmin, idmask, tconst, m_run, t_run, a1, a2, any_slow, P.dbg); \
             else chunk_rank<1, (CH)>(key, cmin, idmask, tconst, m_run, t_run, a1, a2, any_slow, P.dbg);
             VQB_CHUNK(0) VQB_CHUNK(1) VQB_CHUNK(2)
@@ -515,7 +507,7 @@ search_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
             // last chunk: once its scores are formed every TMEM read of this tile is complete -> hand the buffer
             // back to the MMA warp, then start loading the next tile's first chunk (before this chunk's ranking
             // work if that accumulator is already complete)
-            cmin = chunk_scores(r, bias4 + 24, ninv, key);
+            cmin = chunk_scores(r, bias4 + 12, ninv, key);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&bars->tmem_empty[acc]));
@@ -524,7 +516,7 @@ search_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
             bool issued = false;
             if (more && mbar_try(smem_u32(&bars->tmem_full[acc]), acc_ph)) {
               tc_fence_after();
-              TMEM_LD32(lane_addr + acc * (uint32_t)kBlockN, r);
+              TMEM_LD16(lane_addr + acc * (uint32_t)kBlockN, r);
               issued = true;
             }
             if (par == 0) chunk_rank<0, 3>(key, cmin, idmask, tconst, m_run, t_run, a1, a2, any_slow, P.dbg);
@@ -532,37 +524,30 @@ search_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
             if (more && !issued) {
               mbar_wait_t(smem_u32(&bars->tmem_full[acc]), acc_ph, prof, w_tf);
               tc_fence_after();
-              TMEM_LD32(lane_addr + acc * (uint32_t)kBlockN, r);
+              TMEM_LD16(lane_addr + acc * (uint32_t)kBlockN, r);
             }
           }
         }
         if (!any_slow) continue;                   // warp-uniform: nothing was ranked in this tile pair
         // merge this tile pair's top-2 into the running top-3 of the class (with global code ids):
-        // id bit 5 = which tile of the pair, bits 0..4 = position inside the class
-        const int col0 = nt * kBlockN + half * 128;
+        // id bit 5 = which tile of the pair, bits 0..4 = position inside the class (column = 2*pos + class)
+        const int col0 = nt * kBlockN + quarter * 64;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < 2; ++c) {
           const uint32_t i1 = __float_as_uint(a1[c]) & 63u, i2 = __float_as_uint(a2[c]) & 63u;
           top3_insert(M1[c], M2[c], M3[c], C1[c], C2[c], C3[c], a1[c],
-                      col0 + (int)(i1 >> 5) * kBlockN + (int)((i1 & 31u) << 2) + c);
+                      col0 + (int)(i1 >> 5) * kBlockN + (int)((i1 & 31u) << 1) + c);
           top3_insert(M1[c], M2[c], M3[c], C1[c], C2[c], C3[c], a2[c],
-                      col0 + (int)(i2 >> 5) * kBlockN + (int)((i2 & 31u) << 2) + c);
+                      col0 + (int)(i2 >> 5) * kBlockN + (int)((i2 & 31u) << 1) + c);
         }
       }
       if (row < P.N) {
-        // 12 entries {key, code} = 96 B per (row, half): class-major, ascending inside a class
-        uint2* out = reinterpret_cast<uint2*>(reinterpret_cast<uint8_t*>(P.cand) +
-                                              (((size_t)h * P.N + row) * kNumCand + half * (kNumCand / 2)) * 8);
-        uint32_t e[24];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          e[6 * c + 0] = __float_as_uint(M1[c]); e[6 * c + 1] = (uint32_t)C1[c];
-          e[6 * c + 2] = __float_as_uint(M2[c]); e[6 * c + 3] = (uint32_t)C2[c];
-          e[6 * c + 4] = __float_as_uint(M3[c]); e[6 * c + 5] = (uint32_t)C3[c];
-        }
-        uint4* out4 = reinterpret_cast<uint4*>(out);
-#pragma unroll
-        for (int i = 0; i < 6; ++i) out4[i] = make_uint4(e[4 * i], e[4 * i + 1], e[4 * i + 2], e[4 * i + 3]);
+        // 6 entries {key, code} = 48 B per (row, quarter): class-major, ascending inside a class
+        uint4* out4 = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(P.cand) +
+                                               (((size_t)h * P.N + row) * kNumCand + quarter * (kNumCand / 4)) * 8);
+        out4[0] = make_uint4(__float_as_uint(M1[0]), (uint32_t)C1[0], __float_as_uint(M2[0]), (uint32_t)C2[0]);
+        out4[1] = make_uint4(__float_as_uint(M3[0]), (uint32_t)C3[0], __float_as_uint(M1[1]), (uint32_t)C1[1]);
+        out4[2] = make_uint4(__float_as_uint(M2[1]), (uint32_t)C2[1], __float_as_uint(M3[1]), (uint32_t)C3[1]);
       }
     }
     if (prof && lane == 0) {
