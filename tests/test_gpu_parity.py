@@ -270,3 +270,33 @@ def test_state_dict_roundtrip_and_cache_invalidation():
     _, i1, _ = vq(x)
     ref = (-torch.cdist(x.reshape(1, -1, 32).cpu(), new.cpu())).argmax(-1).reshape(2, 50)
     assert torch.equal(i1.cpu(), ref), "search must see embeddings written through load_state_dict"
+
+
+@pytest.mark.parametrize("mode", ["2", "3"])
+def test_alternate_search_kernel_modes_match_exact_scan(mode):
+    """VQB_CLUSTER=2 (2-CTA TMA multicast of the codebook stream) and =3 (cta_group::2 pair MMA) are opt-in variants of
+    the search kernel; they must give the same indices as the exact scan (env is read once per process -> subprocess)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = r'''
+import sys, torch
+sys.path.insert(0, r"%s")
+from vqb200 import ops
+dev = torch.device("cuda:0")
+for (H, N, K, d, cos) in [(1, 700, 300, 72, False), (2, 1500, 520, 256, True), (1, 40000, 2048, 128, False), (1, 257, 4096, 512, False)]:
+    g = torch.Generator().manual_seed(N)
+    x = torch.randn(H, N, d, generator=g).to(dev)
+    c = (torch.randn(H, K, d, generator=g) * 0.5).to(dev)
+    cache = ops.prepare_codebook(c, cos)
+    a, _, ws = ops.search(x, c, cache, cos)
+    st = ops.search_stats(ws)
+    b, _, _ = ops.search(x, c, cache, cos, force_exact=True)
+    assert st["tensor_core_pass"] == 1
+    assert torch.equal(a, b), (H, N, K, d, int((a != b).sum()))
+print("MODE OK")
+''' % os.path.join(root, "vector-quantization-by-ml_b200")
+    env = dict(os.environ, VQB_CLUSTER=mode)
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, env=env)
+    assert out.returncode == 0 and "MODE OK" in out.stdout, out.stdout[-1500:] + out.stderr[-3000:]

@@ -105,6 +105,33 @@ __device__ __forceinline__ void tma_load_3d_mc(uint32_t dst, const CUtensorMap* 
       ::"r"(dst), "l"(map), "r"(bar), "h"(mask), "r"(c0), "r"(c1), "r"(c2), "l"(hint) : "memory");
 }
 
+// ---- 2-CTA ("pair") forms: one tcgen05.mma.cta_group::2 covers 256 rows (128 per CTA) x 256 codes (each CTA holds
+// 128 of them in ITS shared memory), issued by the leader CTA only.  Shared-window addresses of the odd CTA carry
+// bit 24; clearing it addresses the same offset in the even (leader) CTA.
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;
+__device__ __forceinline__ void tma_load_3d_pair(uint32_t dst, const CUtensorMap* map, uint32_t leader_bar, int c0,
+                                                 int c1, int c2, uint64_t hint) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4, %5}], [%2], %6;"
+      ::"r"(dst), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2), "l"(hint) : "memory");
+}
+__device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {   // arrives on `bar` in BOTH CTAs of the pair
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {  // arrive on the leader CTA's copy of `bar`
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar & kPeerBitMask) : "memory");
+}
+
 // D[tmem] (+)= A[smem] . B[smem]^T, fp16 inputs, fp32 accumulate; issued by ONE thread.
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                           uint32_t accumulate) {
@@ -132,6 +159,7 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr) {
 // cute::UMMA::InstrDescriptor: c=f32 [4,6)=1, a=f16 [7,10)=0, b=f16 [10,13)=0, K-major both,
 // N>>3 at [17,23), M>>4 at [24,29)
 constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(kBlockN >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
+constexpr uint32_t kIdescPair = (1u << 4) | ((uint32_t)(kBlockN >> 3) << 17) | ((uint32_t)((2 * kBlockM) >> 4) << 24);
 
 #define TMEM_LD32(taddr, r)                                                                                      \
   asm volatile(                                                                                                  \
@@ -265,7 +293,7 @@ constexpr int kWarpStager = 16, kWarpAlloc = 17, kWarpTma = 18, kWarpMma = 19;
 constexpr int kSlabBytes = kBlockM * kBlockK * 2;     // 16 KB: 128 rows x 64 fp16
 constexpr int kStageBytes = kBlockN * kBlockK * 2;    // 32 KB: 256 codes x 64 fp16
 constexpr int kMaxKB = 8;                              // d_pad <= 512
-constexpr int kMaxStages = 6;
+constexpr int kMaxStages = 12;
 constexpr int kTmemCols = 512;
 
 struct SearchParams {
@@ -292,12 +320,16 @@ struct Barriers {
   uint64_t tmem_full[2];
   uint64_t tmem_empty[2];
   uint64_t bias_full[2];
+  uint64_t bias_empty[2];   // pair mode only: the local epilogue released the bias slot
   uint32_t tmem_base;
   uint32_t pad;
   alignas(16) float bias[2][kBlockN];   // per-accumulator-buffer copy of the N tile's biases (staged by warp 3)
 };
 
-template <int CLUSTER>
+// CLUSTER = 1: independent CTAs.  CLUSTER = 2, !PAIR: two CTAs share every B stage by TMA multicast (each runs its own
+// 128-row MMAs).  CLUSTER = 2, PAIR: cta_group::2 -- one 256-row MMA per pair, each CTA stores only half of B (half the
+// shared-memory operand traffic per SM, twice the stages in flight).
+template <int CLUSTER, bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1)
 search_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_c,
                  const SearchParams P) {
@@ -307,7 +339,8 @@ search_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t a_base = smem_base;
   const uint32_t b_base = smem_base + (uint32_t)P.KB * kSlabBytes;
-  Barriers* bars = reinterpret_cast<Barriers*>(smem + (size_t)P.KB * kSlabBytes + (size_t)P.S * kStageBytes);
+  constexpr uint32_t kStageStride = PAIR ? kStageBytes / 2 : kStageBytes;   // bytes of one B stage in THIS CTA
+  Barriers* bars = reinterpret_cast<Barriers*>(smem + (size_t)P.KB * kSlabBytes + (size_t)P.S * kStageStride);
 
   const uint32_t rank = CLUSTER > 1 ? cluster_ctarank() : 0u;
   const int cid = blockIdx.x / CLUSTER;
@@ -325,7 +358,7 @@ search_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
   if (warp == kWarpMma && lane == 0) {
     for (int i = 0; i < P.S; ++i) {
       mbar_init(smem_u32(&bars->full[i]), 1);
-      mbar_init(smem_u32(&bars->empty[i]), CLUSTER);
+      mbar_init(smem_u32(&bars->empty[i]), PAIR ? 1 : CLUSTER);
     }
     for (int i = 0; i < P.KB; ++i) {
       mbar_init(smem_u32(&bars->a_full[i]), 1);
@@ -333,15 +366,22 @@ search_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(smem_u32(&bars->tmem_full[i]), 1);
-      mbar_init(smem_u32(&bars->tmem_empty[i]), kNumEpiWarps);
+      mbar_init(smem_u32(&bars->tmem_empty[i]), PAIR ? 2 * kNumEpiWarps : kNumEpiWarps);
       mbar_init(smem_u32(&bars->bias_full[i]), 1);
+      mbar_init(smem_u32(&bars->bias_empty[i]), kNumEpiWarps);
     }
     fence_barrier_init();
   }
   if (warp == kWarpAlloc) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)),
-                 "n"(kTmemCols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (PAIR) {   // both CTAs of the pair issue it, same warp id, same destination offset
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;"
+                   ::"r"(smem_u32(&bars->tmem_base)), "n"(kTmemCols) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                   ::"r"(smem_u32(&bars->tmem_base)), "n"(kTmemCols) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
   if (CLUSTER > 1) cluster_sync_all(); else __syncthreads();
@@ -363,11 +403,24 @@ search_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
           for (int kb = 0; kb < P.KB; ++kb) {
             if (nt == 0) {   // (re)load slab kb of this row tile as soon as the previous tile's MMAs released it
               mbar_wait_t(smem_u32(&bars->a_empty[kb]), a_ph ^ 1u, prof, w_a);
-              mbar_expect_tx(smem_u32(&bars->a_full[kb]), kSlabBytes);
-              tma_load_3d(a_base + kb * kSlabBytes, &map_x, smem_u32(&bars->a_full[kb]), kb * kBlockK, row0, h,
-                          kEvictFirst);
+              if (PAIR) {   // both CTAs' slabs complete on the LEADER's barrier
+                if (rank == 0) mbar_expect_tx(smem_u32(&bars->a_full[kb]), 2 * kSlabBytes);
+                tma_load_3d_pair(a_base + kb * kSlabBytes, &map_x, smem_u32(&bars->a_full[kb]) & kPeerBitMask,
+                                 kb * kBlockK, row0, h, kEvictFirst);
+              } else {
+                mbar_expect_tx(smem_u32(&bars->a_full[kb]), kSlabBytes);
+                tma_load_3d(a_base + kb * kSlabBytes, &map_x, smem_u32(&bars->a_full[kb]), kb * kBlockK, row0, h,
+                            kEvictFirst);
+              }
             }
             mbar_wait_t(smem_u32(&bars->empty[stage]), ph ^ 1u, prof, w_e);
+            if (PAIR) {     // this CTA's 128 codes of the N tile into ITS stage; bytes counted on the leader's barrier
+              if (rank == 0) mbar_expect_tx(smem_u32(&bars->full[stage]), kStageBytes);
+              tma_load_3d_pair(b_base + stage * kStageStride, &map_c, smem_u32(&bars->full[stage]) & kPeerBitMask,
+                               kb * kBlockK, nt * kBlockN + (int)rank * (kBlockN / 2), h, kEvictLast);
+              if (++stage == (uint32_t)P.S) { stage = 0; ph ^= 1u; }
+              continue;
+            }
             mbar_expect_tx(smem_u32(&bars->full[stage]), kStageBytes);
             if (CLUSTER > 1) {
               constexpr int rows = kBlockN / CLUSTER;
@@ -390,8 +443,8 @@ search_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
       }
     }
   } else if (warp == kWarpMma) {
-    // =============================== MMA issuer ===============================
-    if (lane == 0) {
+    // =============================== MMA issuer (pair mode: leader CTA only) ===============================
+    if (lane == 0 && (!PAIR || rank == 0)) {
       uint32_t stage = 0, ph = 0, a_ph = 0, acc = 0, acc_ph = 0;
       const bool prof = (P.dbg & 32) != 0;
       unsigned long long w_te = 0, w_a = 0, w_f = 0;
@@ -406,19 +459,26 @@ search_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
             mbar_wait_t(smem_u32(&bars->full[stage]), ph, prof, w_f);
             tc_fence_after();
             const uint64_t adesc = make_sw128_desc(a_base + kb * kSlabBytes);
-            const uint64_t bdesc = make_sw128_desc(b_base + stage * kStageBytes);
+            const uint64_t bdesc = make_sw128_desc(b_base + stage * kStageStride);
 #pragma unroll
             for (int kk = 0; kk < kBlockK / 16; ++kk) {
               // +32 B per 16-element k step inside the 128B swizzle atom = +2 in the (addr>>4) field
-              umma_f16(d_tmem, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), kIdesc,
-                        (kb | kk) != 0 ? 1u : 0u);
+              if (PAIR) umma_f16_pair(d_tmem, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), kIdescPair,
+                                      (kb | kk) != 0 ? 1u : 0u);
+              else umma_f16(d_tmem, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), kIdesc,
+                            (kb | kk) != 0 ? 1u : 0u);
             }
-            if (CLUSTER > 1) umma_commit_mc(smem_u32(&bars->empty[stage]), (uint16_t)((1u << CLUSTER) - 1u));
+            if (PAIR) umma_commit_pair(smem_u32(&bars->empty[stage]));
+            else if (CLUSTER > 1) umma_commit_mc(smem_u32(&bars->empty[stage]), (uint16_t)((1u << CLUSTER) - 1u));
             else umma_commit(smem_u32(&bars->empty[stage]));
-            if (nt == P.NT - 1) umma_commit(smem_u32(&bars->a_empty[kb]));   // slab kb may be overwritten
+            if (nt == P.NT - 1) {                                            // slab kb may be overwritten
+              if (PAIR) umma_commit_pair(smem_u32(&bars->a_empty[kb]));
+              else umma_commit(smem_u32(&bars->a_empty[kb]));
+            }
             if (++stage == (uint32_t)P.S) { stage = 0; ph ^= 1u; }
           }
-          umma_commit(smem_u32(&bars->tmem_full[acc]));
+          if (PAIR) umma_commit_pair(smem_u32(&bars->tmem_full[acc]));
+          else umma_commit(smem_u32(&bars->tmem_full[acc]));
           if (++acc == 2) { acc = 0; acc_ph ^= 1u; }
         }
         a_ph ^= 1u;
@@ -443,7 +503,8 @@ search_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
       for (int nt = 0; nt < P.NT; ++nt) {
         const float4 v0 = __ldg(reinterpret_cast<const float4*>(bias_h + nt * kBlockN) + lane);
         const float4 v1 = __ldg(reinterpret_cast<const float4*>(bias_h + nt * kBlockN) + 32 + lane);
-        mbar_wait(smem_u32(&bars->tmem_empty[acc]), acc_ph ^ 1u);
+        if (PAIR) mbar_wait(smem_u32(&bars->bias_empty[acc]), acc_ph ^ 1u);   // local epilogue released the slot
+        else mbar_wait(smem_u32(&bars->tmem_empty[acc]), acc_ph ^ 1u);
         reinterpret_cast<float4*>(bars->bias[acc])[lane] = v0;
         reinterpret_cast<float4*>(bars->bias[acc])[32 + lane] = v1;
         __syncwarp();
@@ -510,7 +571,14 @@ search_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
             cmin = chunk_scores(r, bias4 + 12, ninv, key);
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(&bars->tmem_empty[acc]));
+            if (lane == 0) {
+              if (PAIR) {   // the leader's MMA thread waits for BOTH CTAs' epilogues; the bias slot is local
+                mbar_arrive_leader(smem_u32(&bars->tmem_empty[acc]));
+                mbar_arrive(smem_u32(&bars->bias_empty[acc]));
+              } else {
+                mbar_arrive(smem_u32(&bars->tmem_empty[acc]));
+              }
+            }
             if (++acc == 2) { acc = 0; acc_ph ^= 1u; }
             const bool more = (nt + par + 1 < P.NT) || (g + num_clusters < G);
             bool issued = false;
@@ -561,7 +629,8 @@ search_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
   tc_fence_before();
   if (CLUSTER > 1) cluster_sync_all(); else __syncthreads();
   if (warp == kWarpAlloc) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
+    if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
   }
 }
 
@@ -600,7 +669,8 @@ static int make_map(CUtensorMap* m, const void* base, int inner, int64_t rows, i
   return VQB_OK;
 }
 
-static int g_cluster_override = -1;   // test hook (env VQB_CLUSTER): 1 or 2
+static int g_cluster_override = -1;   // env VQB_CLUSTER: 1, 2 (multicast) or 3 (pair MMA)
+constexpr int kDefaultMode = 1;
 
 // timing ring for VQB_SEARCH_TIMING: event pairs recorded on the search stream around the kernel launch
 constexpr int kTimingSlots = 64;
@@ -608,12 +678,12 @@ static cudaEvent_t g_ev0[kTimingSlots], g_ev1[kTimingSlots];
 static bool g_ev_made = false;
 static int g_ev_count = 0;
 
-template <int CLUSTER>
+template <int CLUSTER, bool PAIR>
 static int launch_impl(const CUtensorMap& mx, const CUtensorMap& mc, const SearchParams& P, size_t smem_bytes,
                        int grid, bool timing, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
-    VQB_CUDA_TRY(cudaFuncSetAttribute(search_tc_kernel<CLUSTER>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    VQB_CUDA_TRY(cudaFuncSetAttribute(search_tc_kernel<CLUSTER, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       227 * 1024));
     configured = true;
   }
@@ -641,7 +711,7 @@ static int launch_impl(const CUtensorMap& mx, const CUtensorMap& mc, const Searc
     if (g_ev_count < kTimingSlots) slot = g_ev_count++;
   }
   if (slot >= 0) VQB_CUDA_TRY(cudaEventRecord(g_ev0[slot], st));
-  VQB_CUDA_TRY(cudaLaunchKernelEx(&cfg, search_tc_kernel<CLUSTER>, mx, mc, P));
+  VQB_CUDA_TRY(cudaLaunchKernelEx(&cfg, search_tc_kernel<CLUSTER, PAIR>, mx, mc, P));
   ++g_launch_count;
   if (slot >= 0) VQB_CUDA_TRY(cudaEventRecord(g_ev1[slot], st));
   return VQB_OK;
@@ -663,9 +733,12 @@ int launch_search_tc(const __half* xb, const float* xinv, const __half* cb, cons
     g_cluster_override = e ? atoi(e) : 0;
   }
   const int MT = (int)((N + kBlockM - 1) / kBlockM);
-  // measured on B200 (C2 shape): L2 serves the un-shared B stream fine (1 CTA: 3.99 ms, 2-CTA multicast: 4.15 ms),
-  // so multicast clusters are opt-in (VQB_CLUSTER=2)
-  int cluster = (g_cluster_override == 2 && MT >= 2) ? 2 : 1;
+  // VQB_CLUSTER: 1 = independent CTAs, 2 = 2-CTA TMA multicast of B (measured: not faster, L2 is not the limiter),
+  // 3 = cta_group::2 pair MMA (each CTA holds half of B).  Default: see below.
+  int mode = g_cluster_override >= 1 && g_cluster_override <= 3 ? g_cluster_override : kDefaultMode;
+  if (MT < 2) mode = 1;
+  const bool pair = mode == 3;
+  const int cluster = mode == 1 ? 1 : 2;
 
   SearchParams P;
   P.bias = bias; P.xinv = xinv; P.chdr = chdr; P.cand = cand; P.scal = scal; P.N = N; P.Kp = Kp; P.H = (int)H;
@@ -676,13 +749,14 @@ int launch_search_tc(const __half* xb, const float* xinv, const __half* cb, cons
   }
   P.KB = dp / kBlockK;
   P.NT = Kp / kBlockN;
+  const size_t stage_bytes = pair ? kStageBytes / 2 : kStageBytes;     // per CTA
   const size_t fixed = (size_t)P.KB * kSlabBytes + sizeof(Barriers);
-  int S = (int)((227 * 1024 - fixed) / kStageBytes);
+  int S = (int)((227 * 1024 - fixed) / stage_bytes);
   if (S > kMaxStages) S = kMaxStages;
   VQB_REQUIRE(S >= 2, VQB_ERR_UNSUPPORTED, "not enough shared memory for d_pad=%d", dp);
   P.S = S;
   P.GPH = (MT + cluster - 1) / cluster;
-  const size_t smem_bytes = fixed + (size_t)S * kStageBytes;
+  const size_t smem_bytes = fixed + (size_t)S * stage_bytes;
   const int G = (int)H * P.GPH;
   int nclusters = num_sms / cluster;
   if (nclusters > G) nclusters = G;
@@ -693,8 +767,9 @@ int launch_search_tc(const __half* xb, const float* xinv, const __half* cb, cons
   if (rc) return rc;
   rc = make_map(&mc, cb, dp, Kp, H, kBlockN / cluster);
   if (rc) return rc;
-  if (cluster == 2) return launch_impl<2>(mx, mc, P, smem_bytes, grid, timing, st);
-  return launch_impl<1>(mx, mc, P, smem_bytes, grid, timing, st);
+  if (pair) return launch_impl<2, true>(mx, mc, P, smem_bytes, grid, timing, st);
+  if (cluster == 2) return launch_impl<2, false>(mx, mc, P, smem_bytes, grid, timing, st);
+  return launch_impl<1, false>(mx, mc, P, smem_bytes, grid, timing, st);
 }
 
 int debug_counters(unsigned long long* out18) {   // [0..1] ranked/skipped chunks, [2..17] cycle counters
