@@ -272,10 +272,10 @@ def test_state_dict_roundtrip_and_cache_invalidation():
     assert torch.equal(i1.cpu(), ref), "search must see embeddings written through load_state_dict"
 
 
-@pytest.mark.parametrize("mode", ["2", "3"])
+@pytest.mark.parametrize("mode", ["1", "2"])
 def test_alternate_search_kernel_modes_match_exact_scan(mode):
-    """VQB_CLUSTER=2 (2-CTA TMA multicast of the codebook stream) and =3 (cta_group::2 pair MMA) are opt-in variants of
-    the search kernel; they must give the same indices as the exact scan (env is read once per process -> subprocess)."""
+    """VQB_CLUSTER=1 (independent CTAs) and =2 (2-CTA TMA multicast of the codebook stream) are opt-in variants of
+    the search kernel (default: 3 = cta_group::2 pair MMA); they must give the same indices as the exact scan (env is read once per process -> subprocess)."""
     import os
     import subprocess
     import sys

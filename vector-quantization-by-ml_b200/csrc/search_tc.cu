@@ -78,6 +78,17 @@ __device__ __forceinline__ void fence_barrier_init() {
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// true in exactly one lane of a fully active warp; unlike `lane == 0` the compiler knows the enclosing code stays
+// warp-uniform, so the tensor-core / TMA issue instructions (uniform datapath) are not wrapped in election loops
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+      "elect.sync rx|px, %1;\n\t"
+      "@px mov.s32 %0, 1;\n\t}"
+      : "+r"(pred) : "r"(0xFFFFFFFFu));
+  return pred != 0;
+}
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -390,7 +401,8 @@ search_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
 
   if (warp == kWarpTma) {
     // =============================== TMA producer ===============================
-    if (lane == 0) {
+    // The whole warp runs the loop (barrier waits are warp-uniform); one elected lane issues expect_tx + TMA.
+    {
       uint32_t stage = 0, ph = 0, a_ph = 0;
       const bool prof = (P.dbg & 32) != 0;
       unsigned long long w_a = 0, w_e = 0;
@@ -403,40 +415,45 @@ search_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
           for (int kb = 0; kb < P.KB; ++kb) {
             if (nt == 0) {   // (re)load slab kb of this row tile as soon as the previous tile's MMAs released it
               mbar_wait_t(smem_u32(&bars->a_empty[kb]), a_ph ^ 1u, prof, w_a);
-              if (PAIR) {   // both CTAs' slabs complete on the LEADER's barrier
-                if (rank == 0) mbar_expect_tx(smem_u32(&bars->a_full[kb]), 2 * kSlabBytes);
-                tma_load_3d_pair(a_base + kb * kSlabBytes, &map_x, smem_u32(&bars->a_full[kb]) & kPeerBitMask,
-                                 kb * kBlockK, row0, h, kEvictFirst);
-              } else {
-                mbar_expect_tx(smem_u32(&bars->a_full[kb]), kSlabBytes);
-                tma_load_3d(a_base + kb * kSlabBytes, &map_x, smem_u32(&bars->a_full[kb]), kb * kBlockK, row0, h,
-                            kEvictFirst);
+              if (elect_one()) {
+                if (PAIR) {   // both CTAs' slabs complete on the LEADER's barrier
+                  if (rank == 0) mbar_expect_tx(smem_u32(&bars->a_full[kb]), 2 * kSlabBytes);
+                  tma_load_3d_pair(a_base + kb * kSlabBytes, &map_x, smem_u32(&bars->a_full[kb]) & kPeerBitMask,
+                                   kb * kBlockK, row0, h, kEvictFirst);
+                } else {
+                  mbar_expect_tx(smem_u32(&bars->a_full[kb]), kSlabBytes);
+                  tma_load_3d(a_base + kb * kSlabBytes, &map_x, smem_u32(&bars->a_full[kb]), kb * kBlockK, row0, h,
+                              kEvictFirst);
+                }
               }
+              __syncwarp();
             }
             mbar_wait_t(smem_u32(&bars->empty[stage]), ph ^ 1u, prof, w_e);
-            if (PAIR) {     // this CTA's 128 codes of the N tile into ITS stage; bytes counted on the leader's barrier
-              if (rank == 0) mbar_expect_tx(smem_u32(&bars->full[stage]), kStageBytes);
-              tma_load_3d_pair(b_base + stage * kStageStride, &map_c, smem_u32(&bars->full[stage]) & kPeerBitMask,
-                               kb * kBlockK, nt * kBlockN + (int)rank * (kBlockN / 2), h, kEvictLast);
-              if (++stage == (uint32_t)P.S) { stage = 0; ph ^= 1u; }
-              continue;
+            if (elect_one()) {
+              if (PAIR) {   // this CTA's 128 codes of the N tile into ITS stage; bytes counted on the leader's barrier
+                if (rank == 0) mbar_expect_tx(smem_u32(&bars->full[stage]), kStageBytes);
+                tma_load_3d_pair(b_base + stage * kStageStride, &map_c, smem_u32(&bars->full[stage]) & kPeerBitMask,
+                                 kb * kBlockK, nt * kBlockN + (int)rank * (kBlockN / 2), h, kEvictLast);
+              } else {
+                mbar_expect_tx(smem_u32(&bars->full[stage]), kStageBytes);
+                if (CLUSTER > 1) {
+                  constexpr int rows = kBlockN / CLUSTER;
+                  tma_load_3d_mc(b_base + stage * kStageBytes + rank * (rows * kBlockK * 2), &map_c,
+                                 smem_u32(&bars->full[stage]), kb * kBlockK, nt * kBlockN + (int)rank * rows, h,
+                                 (uint16_t)((1u << CLUSTER) - 1u), kEvictLast);
+                } else {
+                  tma_load_3d(b_base + stage * kStageBytes, &map_c, smem_u32(&bars->full[stage]), kb * kBlockK,
+                              nt * kBlockN, h, kEvictLast);
+                }
+              }
             }
-            mbar_expect_tx(smem_u32(&bars->full[stage]), kStageBytes);
-            if (CLUSTER > 1) {
-              constexpr int rows = kBlockN / CLUSTER;
-              tma_load_3d_mc(b_base + stage * kStageBytes + rank * (rows * kBlockK * 2), &map_c,
-                             smem_u32(&bars->full[stage]), kb * kBlockK, nt * kBlockN + (int)rank * rows, h,
-                             (uint16_t)((1u << CLUSTER) - 1u), kEvictLast);
-            } else {
-              tma_load_3d(b_base + stage * kStageBytes, &map_c, smem_u32(&bars->full[stage]), kb * kBlockK,
-                          nt * kBlockN, h, kEvictLast);
-            }
+            __syncwarp();
             if (++stage == (uint32_t)P.S) { stage = 0; ph ^= 1u; }
           }
         }
         a_ph ^= 1u;
       }
-      if (prof) {
+      if (prof && lane == 0) {
         atomicAdd(g_dbg_cycles + 0, (unsigned long long)(clock64() - t_begin));
         atomicAdd(g_dbg_cycles + 1, w_a);
         atomicAdd(g_dbg_cycles + 2, w_e);
@@ -444,7 +461,8 @@ search_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     }
   } else if (warp == kWarpMma) {
     // =============================== MMA issuer (pair mode: leader CTA only) ===============================
-    if (lane == 0 && (!PAIR || rank == 0)) {
+    // The whole warp runs the loop; one elected lane issues the tcgen05.mma / tcgen05.commit instructions.
+    if (!PAIR || rank == 0) {
       uint32_t stage = 0, ph = 0, a_ph = 0, acc = 0, acc_ph = 0;
       const bool prof = (P.dbg & 32) != 0;
       unsigned long long w_te = 0, w_a = 0, w_f = 0;
@@ -458,32 +476,37 @@ search_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
             if (nt == 0) mbar_wait_t(smem_u32(&bars->a_full[kb]), a_ph, prof, w_a);
             mbar_wait_t(smem_u32(&bars->full[stage]), ph, prof, w_f);
             tc_fence_after();
-            const uint64_t adesc = make_sw128_desc(a_base + kb * kSlabBytes);
-            const uint64_t bdesc = make_sw128_desc(b_base + stage * kStageStride);
+            if (elect_one()) {
+              const uint64_t adesc = make_sw128_desc(a_base + kb * kSlabBytes);
+              const uint64_t bdesc = make_sw128_desc(b_base + stage * kStageStride);
 #pragma unroll
-            for (int kk = 0; kk < kBlockK / 16; ++kk) {
-              // +32 B per 16-element k step inside the 128B swizzle atom = +2 in the (addr>>4) field
-              if (PAIR) umma_f16_pair(d_tmem, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), kIdescPair,
-                                      (kb | kk) != 0 ? 1u : 0u);
-              else umma_f16(d_tmem, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), kIdesc,
-                            (kb | kk) != 0 ? 1u : 0u);
+              for (int kk = 0; kk < kBlockK / 16; ++kk) {
+                // +32 B per 16-element k step inside the 128B swizzle atom = +2 in the (addr>>4) field
+                if (PAIR) umma_f16_pair(d_tmem, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), kIdescPair,
+                                        (kb | kk) != 0 ? 1u : 0u);
+                else umma_f16(d_tmem, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), kIdesc,
+                              (kb | kk) != 0 ? 1u : 0u);
+              }
+              if (PAIR) umma_commit_pair(smem_u32(&bars->empty[stage]));
+              else if (CLUSTER > 1) umma_commit_mc(smem_u32(&bars->empty[stage]), (uint16_t)((1u << CLUSTER) - 1u));
+              else umma_commit(smem_u32(&bars->empty[stage]));
+              if (nt == P.NT - 1) {                                            // slab kb may be overwritten
+                if (PAIR) umma_commit_pair(smem_u32(&bars->a_empty[kb]));
+                else umma_commit(smem_u32(&bars->a_empty[kb]));
+              }
+              if (kb == P.KB - 1) {                                            // accumulator complete
+                if (PAIR) umma_commit_pair(smem_u32(&bars->tmem_full[acc]));
+                else umma_commit(smem_u32(&bars->tmem_full[acc]));
+              }
             }
-            if (PAIR) umma_commit_pair(smem_u32(&bars->empty[stage]));
-            else if (CLUSTER > 1) umma_commit_mc(smem_u32(&bars->empty[stage]), (uint16_t)((1u << CLUSTER) - 1u));
-            else umma_commit(smem_u32(&bars->empty[stage]));
-            if (nt == P.NT - 1) {                                            // slab kb may be overwritten
-              if (PAIR) umma_commit_pair(smem_u32(&bars->a_empty[kb]));
-              else umma_commit(smem_u32(&bars->a_empty[kb]));
-            }
+            __syncwarp();
             if (++stage == (uint32_t)P.S) { stage = 0; ph ^= 1u; }
           }
-          if (PAIR) umma_commit_pair(smem_u32(&bars->tmem_full[acc]));
-          else umma_commit(smem_u32(&bars->tmem_full[acc]));
           if (++acc == 2) { acc = 0; acc_ph ^= 1u; }
         }
         a_ph ^= 1u;
       }
-      if (prof) {
+      if (prof && lane == 0) {
         atomicAdd(g_dbg_cycles + 3, (unsigned long long)(clock64() - t_begin));
         atomicAdd(g_dbg_cycles + 4, w_te);
         atomicAdd(g_dbg_cycles + 5, w_a);
@@ -670,7 +693,7 @@ static int make_map(CUtensorMap* m, const void* base, int inner, int64_t rows, i
 }
 
 static int g_cluster_override = -1;   // env VQB_CLUSTER: 1, 2 (multicast) or 3 (pair MMA)
-constexpr int kDefaultMode = 1;
+constexpr int kDefaultMode = 3;   // cta_group::2 pair MMA: measured fastest on B200 for d >= 256, equal at d = 64
 
 // timing ring for VQB_SEARCH_TIMING: event pairs recorded on the search stream around the kernel launch
 constexpr int kTimingSlots = 64;
