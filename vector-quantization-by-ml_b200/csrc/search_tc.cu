@@ -208,6 +208,10 @@ __device__ unsigned long long g_dbg_cycles[16];    // bring-up only (VQB_TC_DEBU
 __device__ unsigned long long g_dbg_counters[2];   // bring-up only (VQB_TC_DEBUG & 16): ranked / skipped chunks
 constexpr float kPackSlackTC = 6.2e-5f;   // must equal kPackSlack in search_resolve.cu
 
+// order-preserving float <-> int (involution): lets shared-memory atomicMin work on scores of either sign
+__device__ __forceinline__ int f2ord(float f) { const int i = __float_as_int(f); return i ^ ((i >> 31) & 0x7fffffff); }
+__device__ __forceinline__ float ord2f(int i) { return __int_as_float(i ^ ((i >> 31) & 0x7fffffff)); }
+
 // key = (bits & mask) | id in ONE LOP3 (mask lives in a register, id is an immediate); lut 0xEA = (a & b) | c
 template <uint32_t ID>
 __device__ __forceinline__ float pack_id(float v, uint32_t mask) {
@@ -254,7 +258,8 @@ __device__ __forceinline__ void pack_pair(float (&key)[16], int i, uint32_t mask
 
 template <int PARITY, int CH>
 __device__ __forceinline__ void chunk_rank(float (&key)[16], float cmin, uint32_t idmask, float tconst, float& m_run,
-                                           float& t_run, float (&a1)[2], float (&a2)[2], bool& any_slow, int dbg) {
+                                           float& t_run, int* row_slot, float (&a1)[2], float (&a2)[2],
+                                           bool& any_slow, int dbg) {
   bool trig = __any_sync(0xffffffffu, cmin <= t_run);
   if (dbg) {   // bring-up knobs: 4 = never rank, 8 = always rank, 16 = count ranked / skipped chunks
     if (dbg & 4) trig = false;
@@ -275,7 +280,8 @@ __device__ __forceinline__ void chunk_rank(float (&key)[16], float cmin, uint32_
     }
     if (cmin < m_run) {
       m_run = cmin;
-      t_run = fmaf(fabsf(cmin), kPackSlackTC, cmin) + tconst;
+      t_run = fminf(t_run, fmaf(fabsf(cmin), kPackSlackTC, cmin) + tconst);
+      if (row_slot) atomicMin(row_slot, f2ord(cmin));     // publish to the other quarter-warps of this row
     }
   }
 }
@@ -335,6 +341,12 @@ struct Barriers {
   uint32_t tmem_base;
   uint32_t pad;
   alignas(16) float bias[2][kBlockN];   // per-accumulator-buffer copy of the N tile's biases (staged by warp 3)
+  // Running row minima shared by the four quarter-warps of a row (order-preserving int encoding of the float), three
+  // slots rotating with the row tile: slot (i+1)%3 is reset when a warp starts its i-th row tile.  Epilogue warps are
+  // never more than ~2 N tiles apart (tmem_empty needs all of them), so with NT >= 4 no value of an older row tile
+  // can land in a slot after its last reset.  Any value in the slot is a score of the CURRENT row, hence an upper
+  // bound of its final minimum -- all the skip test needs.
+  int rowmin[3][kBlockM];
 };
 
 // CLUSTER = 1: independent CTAs.  CLUSTER = 2, !PAIR: two CTAs share every B stage by TMA multicast (each runs its own
@@ -383,6 +395,7 @@ search_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     }
     fence_barrier_init();
   }
+  if (threadIdx.x < 3 * kBlockM) (&bars->rowmin[0][0])[threadIdx.x] = 0x7fffffff;
   if (warp == kWarpAlloc) {
     if (PAIR) {   // both CTAs of the pair issue it, same warp id, same destination offset
       asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;"
@@ -548,6 +561,7 @@ search_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     unsigned long long w_tf = 0, w_bias = 0;
     const long long t_begin = clock64();
     uint32_t r[16];
+    uint32_t tile_it = 0;                           // row tiles processed by this CTA so far
     if (cid < G) {   // pipeline prologue: first chunk of the very first tile (later ones are prefetched in the loop)
       mbar_wait(smem_u32(&bars->tmem_full[0]), 0);
       tc_fence_after();
@@ -567,7 +581,18 @@ search_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
       uint32_t idmask;
       asm volatile("mov.u32 %0, 0xFFFFFFC0;" : "=r"(idmask));
       float m_run = INF, t_run = INF;              // running row minimum (this thread's columns) and its threshold
+      // shared running minimum of the row (all four quarters); disabled for tiny codebooks (see Barriers::rowmin)
+      int* row_slot = nullptr;
+      if (P.NT >= 4 && !(P.dbg & 64)) {
+        bars->rowmin[(tile_it + 1) % 3][q * 32 + lane] = 0x7fffffff;        // reset the NEXT row tile's slot
+        row_slot = &bars->rowmin[tile_it % 3][q * 32 + lane];
+      }
+      ++tile_it;
       for (int nt = 0; nt < P.NT; nt += 2) {       // N tiles in pairs: one top-3 merge per 512 codes
+        if (row_slot) {                            // tighten the threshold with what the other quarters have seen
+          const float gmin = ord2f(*reinterpret_cast<volatile int*>(row_slot));
+          t_run = fminf(t_run, fmaf(fabsf(gmin), kPackSlackTC, gmin) + tconst);
+        }
         float a1[2], a2[2];
 #pragma unroll
         for (int c = 0; c < 2; ++c) { a1[c] = INF; a2[c] = INF; }
@@ -584,8 +609,8 @@ search_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
 #define VQB_CHUNK(CH)                                                                                      \
             cmin = chunk_scores(r, bias4 + (CH) * 4, ninv, key);                                           \
             TMEM_LD16(taddr + ((CH) + 1) * 16, r);                                                         \
-            if (par == 0) chunk_rank<0, (CH)>(key, cmin, idmask, tconst, m_run, t_run, a1, a2, any_slow, P.dbg); \
-            else chunk_rank<1, (CH)>(key, cmin, idmask, tconst, m_run, t_run, a1, a2, any_slow, P.dbg);
+            if (par == 0) chunk_rank<0, (CH)>(key, cmin, idmask, tconst, m_run, t_run, row_slot, a1, a2, any_slow, P.dbg); \
+            else chunk_rank<1, (CH)>(key, cmin, idmask, tconst, m_run, t_run, row_slot, a1, a2, any_slow, P.dbg);
             VQB_CHUNK(0) VQB_CHUNK(1) VQB_CHUNK(2)
 #undef VQB_CHUNK
             // last chunk: once its scores are formed every TMEM read of this tile is complete -> hand the buffer
@@ -610,8 +635,8 @@ search_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
               TMEM_LD16(lane_addr + acc * (uint32_t)kBlockN, r);
               issued = true;
             }
-            if (par == 0) chunk_rank<0, 3>(key, cmin, idmask, tconst, m_run, t_run, a1, a2, any_slow, P.dbg);
-            else chunk_rank<1, 3>(key, cmin, idmask, tconst, m_run, t_run, a1, a2, any_slow, P.dbg);
+            if (par == 0) chunk_rank<0, 3>(key, cmin, idmask, tconst, m_run, t_run, row_slot, a1, a2, any_slow, P.dbg);
+            else chunk_rank<1, 3>(key, cmin, idmask, tconst, m_run, t_run, row_slot, a1, a2, any_slow, P.dbg);
             if (more && !issued) {
               mbar_wait_t(smem_u32(&bars->tmem_full[acc]), acc_ph, prof, w_tf);
               tc_fence_after();

@@ -184,10 +184,11 @@ class Codebook(nn.Module):
         if self.threshold_ema_dead_code == 0:
             return
         dead = self.cluster_size < self.threshold_ema_dead_code
-        if not torch.any(dead):                       # host sync, as in the reference (:251)
+        # ONE host sync: the per-codebook counts (the reference syncs twice: torch.any at :251, .item() at :234)
+        counts = dead.sum(dim=-1).tolist()
+        if not any(counts):
             return
         H, N, d = flat.shape
-        counts = dead.sum(dim=-1).tolist()            # the reference syncs per codebook (:234)
         from . import distributed as D
         synced = self.use_ddp and self._kmeans_sync and self.distributed_replace_codes and D.is_distributed()
         for h in range(H):
