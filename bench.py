@@ -4,7 +4,8 @@
 A "step" is one pass of the codebook hot path over one batch of synthetic latents: the training-mode
 `VectorQuantize.forward` = nearest-code search + gather/straight-through/commitment loss + EMA statistics,
 codebook refresh and dead-code check.  Workload (configs[1] of BASELINE.json): 1,048,576 latents x d=256,
-codebook K=8192, bf16 latents, Euclidean, default thresholds.
+codebook K=8192, bf16 latents, Euclidean, EMA decay 0.8; config 2 is "search+EMA" (dead-code expiry belongs to
+config 3), so threshold_ema_dead_code=0 here -- stated in the JSON line -- in both arms.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
@@ -114,7 +115,7 @@ def cpu_port_step(rows, threads):
     c = torch.randn(1, K_CODES, DIM, generator=g) * 0.5
     st = O.CodebookState(c.clone(), c.clone(), torch.ones(1, K_CODES))
     x = torch.randn(1, rows, DIM, generator=g).bfloat16()
-    opts = O.VQOpts(codebook=O.CodebookOpts())
+    opts = O.VQOpts(codebook=O.CodebookOpts(threshold_ema_dead_code=0))
 
     def step():
         O.vq_forward(st, x, opts, training=True)
@@ -188,7 +189,8 @@ def main():
 
     # ---- module + synthetic data (seeds: module 0 on every rank, latents 1234 + rank) ----
     torch.manual_seed(0)
-    vq = VectorQuantize(dim=DIM, codebook_params=CodebookParams(dim=DIM, codebook_size=K_CODES),
+    vq = VectorQuantize(dim=DIM, codebook_params=CodebookParams(dim=DIM, codebook_size=K_CODES,
+                                                                threshold_ema_dead_code=0),
                         sync_codebook=world > 1).to(dev)
     g = torch.Generator().manual_seed(0)
     c = (torch.randn(1, K_CODES, DIM, generator=g) * 0.5).to(dev)      # trained-like codebook
@@ -307,7 +309,8 @@ def main():
                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16",
                "data": "synthetic",
                "config": {"workload": WORKLOAD, "step": "VectorQuantize training forward: search + gather/ST/commit loss "
-                          "+ EMA reduce/refresh + dead-code check", "rows_per_gpu": N_ROWS, "codebook_size": K_CODES,
+                          "+ EMA reduce/refresh (config 2 = search+EMA: threshold_ema_dead_code=0; expiry is measured "
+                          "with config 3 in tools/bench_configs.py)", "rows_per_gpu": N_ROWS, "codebook_size": K_CODES,
                           "dim": DIM, "latent_dtype": "bf16", "parallelism": f"dp{world}",
                           "l2": "inputs (512 MiB per batch, 2 rotating buffers) exceed the 126 MB L2; no flush",
                           "search": stats},
