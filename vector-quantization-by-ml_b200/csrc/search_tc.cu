@@ -724,16 +724,19 @@ constexpr int kDefaultMode = 3;   // cta_group::2 pair MMA: measured fastest on 
 constexpr int kTimingSlots = 64;
 static cudaEvent_t g_ev0[kTimingSlots], g_ev1[kTimingSlots];
 static bool g_ev_made = false;
+static int g_ev_dev = -1;              // the events belong to the device of the first timed search
 static int g_ev_count = 0;
 
 template <int CLUSTER, bool PAIR>
 static int launch_impl(const CUtensorMap& mx, const CUtensorMap& mc, const SearchParams& P, size_t smem_bytes,
                        int grid, bool timing, cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[64] = {};      // function attributes are per device
+  int dev = 0;
+  VQB_CUDA_TRY(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || !configured[dev]) {
     VQB_CUDA_TRY(cudaFuncSetAttribute(search_tc_kernel<CLUSTER, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       227 * 1024));
-    configured = true;
+    if (dev >= 0 && dev < 64) configured[dev] = true;
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid);
@@ -748,8 +751,9 @@ static int launch_impl(const CUtensorMap& mx, const CUtensorMap& mc, const Searc
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   int slot = -1;
-  if (timing) {
+  if (timing && (g_ev_dev < 0 || g_ev_dev == dev)) {
     if (!g_ev_made) {
+      g_ev_dev = dev;
       for (int i = 0; i < kTimingSlots; ++i) {
         VQB_CUDA_TRY(cudaEventCreate(&g_ev0[i]));
         VQB_CUDA_TRY(cudaEventCreate(&g_ev1[i]));
