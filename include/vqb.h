@@ -142,6 +142,24 @@ int    vqb_ema_apply_rows(const float* stats, const float* cluster_size, float* 
                           float weight, double eps, int64_t k_total, int l2norm, int64_t H, int K, int d,
                           const float* totals, void* stream);
 
+/* ---- fused tail of the training step: gather + straight-through + loss + EMA sums ------
+ * One pass over the latents in code-sorted order instead of vqb_gather_st_loss followed by
+ * vqb_ema_reduce: x is read once, the code row stays in registers for the run of rows assigned
+ * to it.  Same results: q_out / loss_out as vqb_gather_st_loss with mask = NULL (bit-exact given
+ * idx), stats as vqb_ema_reduce (integer-exact counts; sums accumulated in fixed point, bitwise
+ * reproducible).  Replaces codebooks.py:393-397 + vector_quantize_pytorch.py:273,362 +
+ * codebooks.py:405-408,413 for the un-masked training forward.
+ *   training = 0 writes q = c (Codebook.forward on its own); want_loss = 0 skips loss_out.
+ *   Supported widths: d a power of two <= 256, or d = 512 (vqb_quantize_ema_supported); callers
+ *   use the two separate entry points otherwise, and whenever a mask is present. */
+int    vqb_quantize_ema_supported(int d);
+size_t vqb_quantize_ema_workspace_bytes(int64_t H, int64_t N, int K, int d);
+int    vqb_quantize_ema(const void* x, int x_dtype, const float* codebook, const int64_t* idx,
+                        const float* absmax_bound2, int training, int want_loss,
+                        float* q_out, float* loss_out, float* stats,
+                        int64_t H, int64_t N, int K, int d,
+                        void* ws, size_t ws_bytes, void* stream);
+
 /* ---- dead-code expiry scatter ---------------------------------------------------------
  * Replaces codebooks.py:241-243 for one codebook h: the j-th dead code (ascending index,
  * dead = cluster_size < threshold) takes row sample_rows[j] of x (l2-normalised first when

@@ -206,7 +206,7 @@ def test_gather_st_loss_and_backward_match_torch():
     idx = torch.randint(0, K, (H, N), generator=g)
     mask = torch.rand(N, generator=g) > 0.3
     xd = x.to(_dev()).requires_grad_(True)
-    q, commit = ops.quantize_training(xd, c.to(_dev()), idx.to(_dev()), mask.to(torch.uint8).to(_dev()), True)
+    q, commit, _ = ops.quantize_training(xd, c.to(_dev()), idx.to(_dev()), mask.to(torch.uint8).to(_dev()), True)
     gq = torch.randn(H, N, d, generator=g)
     (q * gq.to(_dev())).sum().add(commit * 0.7).backward()
     xr = x.clone().requires_grad_(True)
@@ -237,6 +237,70 @@ def test_ema_reduce_is_deterministic_and_exact():
     ref_sum = torch.einsum("hnd,hnc->hcd", x.double(), onehot)
     assert torch.equal(a[..., d].double(), ref_cnt)
     assert float((a[..., :d].double() - ref_sum).abs().max()) <= 1e-6 * float(ref_sum.abs().max())
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("H,N,K,d", [(1, 5000, 97, 64), (2, 3000, 50, 256), (1, 2500, 31, 512), (3, 700, 9, 8),
+                                      (1, 4097, 300, 128), (1, 1, 4, 32)])
+def test_fused_quantize_ema_matches_separate_passes(H, N, K, d, dtype):
+    """vqb_quantize_ema == vqb_gather_st_loss + vqb_ema_reduce (q bit-exact, counts exact, sums vs fp64), and is
+    bitwise reproducible although its row placement uses atomics."""
+    from vqb200 import ops
+    assert ops.quantize_ema_supported(d)
+    g = torch.Generator().manual_seed(5 + d)
+    x = (torch.randn(H, N, d, generator=g) * 3).to(dtype)
+    c = torch.randn(H, K, d, generator=g)
+    idx = torch.randint(0, K, (H, N), generator=g)
+    idx[:, : N // 3] = K - 1                # one long segment, spanning several 64-row chunks
+    xd, cd, idd = x.to(_dev()), c.to(_dev()), idx.to(_dev())
+    for training in (True, False):
+        q, loss, stats = ops.quantize_ema(xd, cd, idd, training, True)
+        q2, loss2, stats2 = ops.quantize_ema(xd, cd, idd, training, True)
+        assert torch.equal(q, q2) and torch.equal(loss, loss2) and torch.equal(stats, stats2)
+        qs, ls = ops.gather_st_loss(xd, cd, idd, None, training, True)
+        assert torch.equal(q, qs), "fused q must be bit-identical to the gather kernel"
+        assert torch.allclose(loss.cpu(), ls.cpu(), rtol=1e-6)
+        xf = x.double()
+        onehot = torch.nn.functional.one_hot(idx, K).double()
+        ref_sum = torch.einsum("hnd,hnc->hcd", xf, onehot)
+        st = stats.cpu()
+        assert torch.equal(st[..., d].double(), onehot.sum(1))
+        assert float((st[..., :d].double() - ref_sum).abs().max()) <= 1e-6 * max(float(ref_sum.abs().max()), 1e-30)
+        sep = ops.ema_reduce(xd, idd, None, K).cpu()
+        assert float((st - sep).abs().max()) <= 2e-6 * max(float(sep.abs().max()), 1e-30)
+        cq = torch.stack([c[h][idx[h]] for h in range(H)])
+        ref_loss = ((cq.double() - xf) ** 2).mean()
+        assert abs(float(loss[0]) - float(ref_loss)) <= 1e-6 * float(ref_loss)
+        assert float(loss[1]) == H * N
+
+
+def test_fused_quantize_ema_extreme_scales_and_module_switch():
+    """Tiny / huge magnitudes go through the fixed-point scale; the module gives the same buffers with the fused pass
+    on and off."""
+    from vqb200 import CodebookParams, VectorQuantize, ops
+    g = torch.Generator().manual_seed(9)
+    for scale in (1e-20, 1e15):
+        x = torch.randn(1, 1000, 64, generator=g) * scale
+        c = torch.randn(1, 16, 64, generator=g) * scale
+        idx = torch.randint(0, 16, (1, 1000), generator=g)
+        _, _, st = ops.quantize_ema(x.to(_dev()), c.to(_dev()), idx.to(_dev()), True, False)
+        ref = torch.einsum("hnd,hnc->hcd", x.double(), torch.nn.functional.one_hot(idx, 16).double())
+        assert float((st[..., :64].cpu().double() - ref).abs().max()) <= 1e-6 * float(ref.abs().max())
+    outs = []
+    for fused in (True, False):
+        torch.manual_seed(0)
+        vq = VectorQuantize(dim=64, codebook_params=CodebookParams(dim=64, codebook_size=128,
+                                                                  threshold_ema_dead_code=0)).to(_dev()).train()
+        vq._codebook.fused_quantize_ema = fused
+        xx = torch.randn(4, 500, 64, generator=torch.Generator().manual_seed(1)).to(_dev()).requires_grad_(True)
+        q, ind, loss = vq(xx)
+        (q.sum() + loss.sum()).backward()
+        outs.append((q.detach(), ind, loss.detach(), xx.grad, vq._codebook.embeddings.clone(),
+                     vq._codebook.cluster_size.clone()))
+    a, b = outs
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(a[5], b[5])
+    assert torch.allclose(a[2], b[2], rtol=1e-6) and torch.allclose(a[3], b[3], rtol=1e-5, atol=1e-8)
+    assert torch.allclose(a[4], b[4], rtol=1e-5, atol=1e-7)
 
 
 def test_minkey_roundtrip_and_order():

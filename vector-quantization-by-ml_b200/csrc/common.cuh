@@ -194,6 +194,9 @@ int launch_make_bias(const void* cache, const CacheLayout& CL, int64_t H, int K,
 int launch_search_tc(const __half* xb, const float* xinv, const __half* cb, const float* chdr, const float* bias,
                      int64_t H, int64_t N, int K, int dp, void* cand, uint32_t* scal, bool timing, cudaStream_t st);
 
+int launch_loss_finalize(const double* part, const long long* cntp, int nblocks, int d, float* loss_out,
+                         cudaStream_t st);
+
 // power-of-two scale that brings a magnitude bound m below 2^14 (fp16 max is 65504)
 __host__ __device__ inline float pow2_scale(float m) {
   if (!(m > 0.f) || !isfinite(m)) return 1.f;

@@ -282,6 +282,203 @@ __global__ void ema_finalize_kernel(const long long* __restrict__ acc, const uin
   else stats[i] = (float)ldexp((double)acc[k * d + j], -scale_p[0]);
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// Fused tail of the training step: gather + straight-through + commitment loss + EMA sums in ONE pass
+// over the latents, walking them in code-sorted order (vqb_quantize_ema).  A row is read once; the code
+// row stays in registers for the whole run of rows assigned to it.
+//   lanes: LPR = d/8 lanes (d <= 256) or 32 lanes x NB column blocks (d = 512) own 8 columns each of a row;
+//          a warp therefore works on RPI = 32/LPR rows at a time, each lane group with its own running segment.
+//   sums : fixed point by the "magic constant" trick -- t = v + M1 rounds v to a multiple of q1 = ulp(M1) and the
+//          integer v/q1 is bits(t) - bits(M1): one FADD + one IADD per element instead of a 64-bit F2I (16/clk/SM).
+//          fp32 latents add a second term for the rounding error v - (t - M1) (exact, Fast2Sum) with quantum
+//          q2 = 2^-(P-22) q1, so the result carries P <= 44 bits below the bound; 16-bit latents (8 / 11 significant
+//          bits) are already exact down to 2^-14 / 2^-11 of the bound with one term.  Integer sums are associative:
+//          the result does not depend on the (atomic) placement order -- bitwise reproducible.
+//   loss : (c - x)^2 summed per row in a fixed lane order, one float per row, reduced afterwards in a fixed tree.
+struct FusedScale { int s; int pad; int e; int P; };   // ws scale block: quantum 2^-s, |v| < 2^e, P total bits
+
+__global__ void fused_scale_kernel(const float* __restrict__ bound2, const uint32_t* __restrict__ own_bound,
+                                   int64_t rows, int two_terms, int* __restrict__ scale) {
+  float b = bound2 ? (bound2[0] + bound2[1]) : __uint_as_float(own_bound[0]);
+  if (!(b > 0.f) || !isfinite(b)) b = 1.f;
+  int e;
+  frexpf(b, &e);                  // b < 2^e
+  e += 1;                         // one binade of head room: t = v + M1 never reaches the next binade
+  if (e > 100) e = 100;
+  if (e < -100) e = -100;
+  int lr = 0;
+  while (((int64_t)1 << lr) < rows + 1) ++lr;
+  int P = 22;
+  if (two_terms) { P = 62 - lr; if (P > 44) P = 44; }
+  scale[0] = P - e;               // value = integer * 2^(e-P)
+  scale[2] = e;
+  scale[3] = P;
+}
+
+template <typename T, int NB, int TERMS>
+__global__ void __launch_bounds__(256, 2)
+quantize_ema_kernel(const T* __restrict__ x, const float* __restrict__ cb, const int64_t* __restrict__ idx,
+                    const int* __restrict__ sorted, const uint32_t* __restrict__ start, int64_t N, int K, int d,
+                    int training, const int* __restrict__ scale_p, float* __restrict__ q,
+                    float* __restrict__ loss_rows, unsigned long long* __restrict__ acc) {
+  constexpr int U = NB == 1 ? 4 : 2;            // rows in flight per lane group
+  const int h = blockIdx.y;
+  const int lane = threadIdx.x & 31;
+  const int64_t chunk = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t total = start[(int64_t)h * (K + 1) + K];
+  const int64_t p0 = chunk * kChunkRows;
+  if (p0 >= total) return;
+  const int n = (int)((p0 + kChunkRows < total ? p0 + kChunkRows : total) - p0);
+  const int lpr = NB == 1 ? d >> 3 : 32;        // lanes per row
+  const int rpi = 32 / lpr;                     // rows per warp iteration
+  const int grp = lane / lpr, gl = lane - grp * lpr;
+  const int j = gl * 8;                         // first owned column (of column block 0)
+  const int e = scale_p[2], P = scale_p[3];
+  const float M1 = ldexpf(1.5f, e + 1);         // ulp(M1) = 2^(e-22)
+  const float M2 = ldexpf(1.5f, e + 23 - P);    // ulp(M2) = 2^(e-P)
+  const uint32_t M1b = __float_as_uint(M1), M2b = __float_as_uint(M2);
+  const int shift = P - 22;
+  const T* xh = x + (int64_t)h * N * d;
+  const float* cbh = cb + (int64_t)h * K * d;
+  const int64_t* idxh = idx + (int64_t)h * N;
+  const int* srt = sorted + (int64_t)h * N;
+  float* qh = q + (int64_t)h * N * d;
+  unsigned long long* acch = acc + (int64_t)h * K * d;
+
+  const int r_lo = lane < n ? srt[p0 + lane] : 0;
+  const int r_hi = lane + 32 < n ? srt[p0 + 32 + lane] : 0;
+  const int k_lo = lane < n ? (int)idxh[r_lo] : -1;
+  const int k_hi = lane + 32 < n ? (int)idxh[r_hi] : -1;
+
+  uint32_t sh[NB][8], sl[NB][8];                // wrapped sums of bits(t) (and bits(t2))
+  float c[NB][8];
+#pragma unroll
+  for (int b = 0; b < NB; ++b)
+#pragma unroll
+    for (int t = 0; t < 8; ++t) { sh[b][t] = 0u; sl[b][t] = 0u; c[b][t] = 0.f; }
+  int cur = -1;
+  uint32_t cnt = 0;                             // rows in the open segment of this lane group
+
+  auto flush = [&]() {
+    if (cur >= 0) {
+#pragma unroll
+      for (int b = 0; b < NB; ++b) {
+        unsigned long long* o = acch + (int64_t)cur * d + b * 256 + j;
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+          long long v = (long long)(int)(sh[b][t] - cnt * M1b);
+          if (TERMS == 2) v = (v << shift) + (long long)(int)(sl[b][t] - cnt * M2b);
+          if (v) atomicAdd(o + t, (unsigned long long)v);
+          sh[b][t] = 0u; sl[b][t] = 0u;
+        }
+      }
+    }
+    cnt = 0;
+  };
+
+  for (int i0 = 0; i0 < n; i0 += U * rpi) {
+    F8 v[U][NB];
+    int kk[U], rr[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {               // U independent row loads in flight per group
+      const int i = i0 + u * rpi + grp;
+      rr[u] = __shfl_sync(0xffffffffu, i < 32 ? r_lo : r_hi, i & 31);
+      kk[u] = __shfl_sync(0xffffffffu, i < 32 ? k_lo : k_hi, i & 31);
+      if (i >= n) kk[u] = -1;
+#pragma unroll
+      for (int b = 0; b < NB; ++b) {
+        if (kk[u] >= 0) v[u][b] = load8<T>(xh + (int64_t)rr[u] * d + b * 256 + j);
+        else {
+#pragma unroll
+          for (int t = 0; t < 8; ++t) v[u][b].v[t] = 0.f;
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      float sq = 0.f;
+      if (kk[u] >= 0) {
+        if (kk[u] != cur) {                     // group-uniform: segment boundary
+          flush();
+          cur = kk[u];
+#pragma unroll
+          for (int b = 0; b < NB; ++b) {
+            const float4 a0 = __ldg(reinterpret_cast<const float4*>(cbh + (int64_t)cur * d + b * 256 + j));
+            const float4 a1 = __ldg(reinterpret_cast<const float4*>(cbh + (int64_t)cur * d + b * 256 + j) + 1);
+            c[b][0] = a0.x; c[b][1] = a0.y; c[b][2] = a0.z; c[b][3] = a0.w;
+            c[b][4] = a1.x; c[b][5] = a1.y; c[b][6] = a1.z; c[b][7] = a1.w;
+          }
+        }
+        ++cnt;
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+          float o[8];
+#pragma unroll
+          for (int t = 0; t < 8; ++t) {
+            const float xv = v[u][b].v[t];
+            const float df = __fsub_rn(c[b][t], xv);
+            o[t] = training ? __fadd_rn(xv, df) : c[b][t];
+            sq = fmaf(df, df, sq);
+            const float t1 = __fadd_rn(xv, M1);
+            sh[b][t] += __float_as_uint(t1);
+            if (TERMS == 2) {
+              const float lo = __fsub_rn(xv, __fsub_rn(t1, M1));
+              sl[b][t] += __float_as_uint(__fadd_rn(lo, M2));
+            }
+          }
+          float* qr = qh + (int64_t)rr[u] * d + b * 256 + j;
+          __stcs(reinterpret_cast<float4*>(qr), make_float4(o[0], o[1], o[2], o[3]));
+          __stcs(reinterpret_cast<float4*>(qr) + 1, make_float4(o[4], o[5], o[6], o[7]));
+        }
+      }
+      if (loss_rows) {                          // fixed-order sum over the lanes of the row
+        for (int o2 = lpr >> 1; o2 > 0; o2 >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o2);
+        if (kk[u] >= 0 && gl == 0) loss_rows[(int64_t)h * N + rr[u]] = sq;
+      }
+    }
+  }
+  flush();
+}
+
+// fixed-order partial sums of the per-row squared errors: block b owns rows [b*span, (b+1)*span)
+__global__ void __launch_bounds__(256)
+loss_rows_partial_kernel(const float* __restrict__ loss_rows, int64_t rows, int64_t span, double* __restrict__ part,
+                         long long* __restrict__ cntp) {
+  const int64_t r0 = (int64_t)blockIdx.x * span;
+  const int64_t r1 = r0 + span < rows ? r0 + span : rows;
+  double t = 0.0;
+  for (int64_t r = r0 + threadIdx.x; r < r1; r += 256) t += (double)loss_rows[r];
+  __shared__ double s[256];
+  s[threadIdx.x] = t;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) s[threadIdx.x] += s[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { part[blockIdx.x] = s[0]; cntp[blockIdx.x] = r1 > r0 ? r1 - r0 : 0; }
+}
+
+constexpr int kLossBlocks = 1024;
+struct FusedLayout {
+  EmaLayout E;
+  size_t off_loss_rows;   // f32 [H*N]
+  size_t off_part;        // f64 [kLossBlocks]
+  size_t off_cnt;         // i64 [kLossBlocks]
+  size_t total;
+};
+inline FusedLayout fused_layout(int64_t H, int64_t N, int K, int d) {
+  FusedLayout L;
+  L.E = ema_layout(H, N, K, d);
+  size_t o = L.E.total;
+  L.off_loss_rows = o; o += align_up((size_t)(H * N > 0 ? H * N : 1) * 4);
+  L.off_part = o;      o += align_up((size_t)kLossBlocks * 8);
+  L.off_cnt = o;       o += align_up((size_t)kLossBlocks * 8);
+  L.total = o;
+  return L;
+}
+inline bool fused_width_ok(int d) { return d == 512 || (d >= 8 && d <= 256 && (d & (d - 1)) == 0); }
+
 // --- apply ------------------------------------------------------------------------------------------
 __device__ __forceinline__ float torch_lerp(float a, float b, float w) {
   // ATen lerp: |w| < 0.5 ? a + w*(b-a) : b - (b-a)*(1-w), evaluated with one fma (both the CPU vector
@@ -484,6 +681,90 @@ extern "C" int vqb_ema_reduce(const void* x, int x_dtype, const int64_t* idx, co
   const int64_t n = H * (int64_t)K * (d + 1);
   ema_finalize_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(acc, counts, scale, H * (int64_t)K, d, stats);
   VQB_LAUNCH_CHECK();
+  return VQB_OK;
+}
+
+extern "C" int vqb_quantize_ema_supported(int d) { return fused_width_ok(d) ? 1 : 0; }
+
+extern "C" size_t vqb_quantize_ema_workspace_bytes(int64_t H, int64_t N, int K, int d) {
+  if (H <= 0 || N < 0 || K <= 0 || d <= 0) return 0;
+  return fused_layout(H, N, K, d).total;
+}
+
+extern "C" int vqb_quantize_ema(const void* x, int x_dtype, const float* codebook, const int64_t* idx,
+                                const float* absmax_bound2, int training, int want_loss, float* q_out,
+                                float* loss_out, float* stats, int64_t H, int64_t N, int K, int d, void* ws,
+                                size_t ws_bytes, void* stream) {
+  VQB_REQUIRE(x && codebook && idx && q_out && stats && ws, VQB_ERR_INVALID, "vqb_quantize_ema: null pointer");
+  VQB_REQUIRE(H > 0 && N >= 0 && K > 0 && d > 0 && H < 65536, VQB_ERR_INVALID, "vqb_quantize_ema: bad shape");
+  VQB_REQUIRE(N < (1ll << 31), VQB_ERR_UNSUPPORTED, "N must be < 2^31");
+  VQB_REQUIRE(fused_width_ok(d), VQB_ERR_UNSUPPORTED, "vqb_quantize_ema: d=%d (need a power of two <= 256, or 512)", d);
+  VQB_REQUIRE(!want_loss || loss_out, VQB_ERR_INVALID, "vqb_quantize_ema: loss_out is null");
+  FusedLayout L = fused_layout(H, N, K, d);
+  VQB_REQUIRE(ws_bytes >= L.total, VQB_ERR_WORKSPACE, "quantize_ema workspace too small: %zu < %zu", ws_bytes, L.total);
+  cudaStream_t st = (cudaStream_t)stream;
+  char* w = (char*)ws;
+  uint32_t* counts = (uint32_t*)(w + L.E.off_counts);
+  uint32_t* cursor = (uint32_t*)(w + L.E.off_cursor);
+  uint32_t* start = (uint32_t*)(w + L.E.off_start);
+  int* scale = (int*)(w + L.E.off_scale);
+  long long* acc = (long long*)(w + L.E.off_acc);
+  int* sorted = (int*)(w + L.E.off_sorted);
+  float* loss_rows = want_loss ? (float*)(w + L.off_loss_rows) : nullptr;
+  double* part = (double*)(w + L.off_part);
+  long long* cntp = (long long*)(w + L.off_cnt);
+  const int two_terms = x_dtype == VQB_F32 ? 1 : 0;
+  VQB_CUDA_TRY(cudaMemsetAsync(w, 0, L.E.zero_bytes, st));
+  if (N > 0) {
+    if (!absmax_bound2) {
+      VQB_DISPATCH_DTYPE(x_dtype, T,
+        absmax_kernel<T><<<1184, 256, 0, st>>>((const T*)x, H * N * (int64_t)d, (uint32_t*)(scale + 1)));
+      VQB_LAUNCH_CHECK();
+    }
+    fused_scale_kernel<<<1, 1, 0, st>>>(absmax_bound2, (const uint32_t*)(scale + 1), N, two_terms, scale);
+    VQB_LAUNCH_CHECK();
+    dim3 g1((unsigned)((N + 255) / 256), (unsigned)H);
+    ema_hist_kernel<<<g1, 256, 0, st>>>(idx, nullptr, N, K, counts);
+    VQB_LAUNCH_CHECK();
+    ema_scan_kernel<<<(unsigned)H, 1024, 0, st>>>(counts, K, start);
+    VQB_LAUNCH_CHECK();
+    ema_place_kernel<<<g1, 256, 0, st>>>(idx, nullptr, N, K, start, cursor, sorted);
+    VQB_LAUNCH_CHECK();
+    const int64_t chunks = (N + kChunkRows - 1) / kChunkRows;
+    dim3 g2((unsigned)((chunks + 7) / 8), (unsigned)H);
+#define VQB_QE_LAUNCH(T, NB, TERMS)                                                                          \
+    quantize_ema_kernel<T, NB, TERMS><<<g2, 256, 0, st>>>((const T*)x, codebook, idx, sorted, start, N, K, d, \
+                                                          training, scale, q_out, loss_rows,                 \
+                                                          (unsigned long long*)acc)
+    if (d == 512) {
+      if (x_dtype == VQB_F32) VQB_QE_LAUNCH(float, 2, 2);
+      else if (x_dtype == VQB_BF16) VQB_QE_LAUNCH(__nv_bfloat16, 2, 1);
+      else if (x_dtype == VQB_F16) VQB_QE_LAUNCH(__half, 2, 1);
+      else { set_error("unknown latent dtype %d", x_dtype); return VQB_ERR_INVALID; }
+    } else {
+      if (x_dtype == VQB_F32) VQB_QE_LAUNCH(float, 1, 2);
+      else if (x_dtype == VQB_BF16) VQB_QE_LAUNCH(__nv_bfloat16, 1, 1);
+      else if (x_dtype == VQB_F16) VQB_QE_LAUNCH(__half, 1, 1);
+      else { set_error("unknown latent dtype %d", x_dtype); return VQB_ERR_INVALID; }
+    }
+#undef VQB_QE_LAUNCH
+    VQB_LAUNCH_CHECK();
+  }
+  const int64_t n = H * (int64_t)K * (d + 1);
+  ema_finalize_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(acc, counts, scale, H * (int64_t)K, d, stats);
+  VQB_LAUNCH_CHECK();
+  if (want_loss) {
+    const int64_t rows = H * N;
+    int nblocks = 0;
+    if (rows > 0) {
+      const int64_t span = (rows + kLossBlocks - 1) / kLossBlocks;
+      nblocks = (int)((rows + span - 1) / span);
+      loss_rows_partial_kernel<<<nblocks, 256, 0, st>>>(loss_rows, rows, span, part, cntp);
+      VQB_LAUNCH_CHECK();
+    }
+    int rc = launch_loss_finalize(part, cntp, nblocks, d, loss_out, st);
+    if (rc) return rc;
+  }
   return VQB_OK;
 }
 

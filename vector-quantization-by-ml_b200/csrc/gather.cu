@@ -292,6 +292,13 @@ rvq_level_kernel(const float* res_in, float* res_out, const float* __restrict__ 
   }
 }
 
+int launch_loss_finalize(const double* part, const long long* cntp, int nblocks, int d, float* loss_out,
+                         cudaStream_t st) {
+  loss_finalize_kernel<<<1, 256, 0, st>>>(part, cntp, nblocks, d, loss_out);
+  VQB_LAUNCH_CHECK();
+  return VQB_OK;
+}
+
 }  // namespace vqb
 
 using namespace vqb;

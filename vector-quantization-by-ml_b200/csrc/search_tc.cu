@@ -233,9 +233,14 @@ __device__ __forceinline__ float pack_id(float v, uint32_t mask) {
 //            no candidate and nothing else is done.  SLOW PATH -- 6-bit id PARITY*32 + CH*8 + i packed into the low
 //            mantissa bits (column j = 2*i + c is class c), running top-2 per class, exactly as if no chunk had been
 //            skipped.
+template <int MODE>
 __device__ __forceinline__ float chunk_scores(const uint32_t (&r)[16], const float4* bias4, float ninv,
                                               float (&key)[16]) {
   tmem_ld_wait();
+  if (MODE == 2) {   // timing experiment: what the epilogue costs when the accumulator already IS the key
+#pragma unroll
+    for (int i = 0; i < 16; ++i) key[i] = __uint_as_float(r[i]);
+  } else
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const float4 b = bias4[i];          // shared memory, same address in every lane: broadcast
@@ -256,12 +261,13 @@ __device__ __forceinline__ void pack_pair(float (&key)[16], int i, uint32_t mask
   key[2 * i + 1] = pack_id<ID>(key[2 * i + 1], mask);
 }
 
-template <int PARITY, int CH>
+template <int PARITY, int CH, int MODE>
 __device__ __forceinline__ void chunk_rank(float (&key)[16], float cmin, uint32_t idmask, float tconst, float& m_run,
                                            float& t_run, int* row_slot, float (&a1)[2], float (&a2)[2],
                                            bool& any_slow, int dbg) {
+  if (MODE == 2) return;
   bool trig = __any_sync(0xffffffffu, cmin <= t_run);
-  if (dbg) {   // bring-up knobs: 4 = never rank, 8 = always rank, 16 = count ranked / skipped chunks
+  if (MODE == 1 && dbg) {   // bring-up knobs: 4 = never rank, 8 = always rank, 16 = count ranked / skipped chunks
     if (dbg & 4) trig = false;
     if (dbg & 8) trig = true;
     if ((dbg & 16) && (threadIdx.x & 31) == 0) atomicAdd(g_dbg_counters + (trig ? 0 : 1), 1ull);
@@ -352,7 +358,8 @@ struct Barriers {
 // CLUSTER = 1: independent CTAs.  CLUSTER = 2, !PAIR: two CTAs share every B stage by TMA multicast (each runs its own
 // 128-row MMAs).  CLUSTER = 2, PAIR: cta_group::2 -- one 256-row MMA per pair, each CTA stores only half of B (half the
 // shared-memory operand traffic per SM, twice the stages in flight).
-template <int CLUSTER, bool PAIR>
+// MODE 0 = production (no knobs compiled in), 1 = bring-up knobs (VQB_TC_DEBUG), 2 = timing experiment (raw keys)
+template <int CLUSTER, bool PAIR, int MODE>
 __global__ void __launch_bounds__(kThreads, 1)
 search_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_c,
                  const SearchParams P) {
@@ -417,7 +424,7 @@ search_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     // The whole warp runs the loop (barrier waits are warp-uniform); one elected lane issues expect_tx + TMA.
     {
       uint32_t stage = 0, ph = 0, a_ph = 0;
-      const bool prof = (P.dbg & 32) != 0;
+      const bool prof = MODE == 1 && (P.dbg & 32) != 0;
       unsigned long long w_a = 0, w_e = 0;
       const long long t_begin = clock64();
       for (int g = cid; g < G; g += num_clusters) {
@@ -477,7 +484,7 @@ search_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     // The whole warp runs the loop; one elected lane issues the tcgen05.mma / tcgen05.commit instructions.
     if (!PAIR || rank == 0) {
       uint32_t stage = 0, ph = 0, a_ph = 0, acc = 0, acc_ph = 0;
-      const bool prof = (P.dbg & 32) != 0;
+      const bool prof = MODE == 1 && (P.dbg & 32) != 0;
       unsigned long long w_te = 0, w_a = 0, w_f = 0;
       const long long t_begin = clock64();
       for (int g = cid; g < G; g += num_clusters) {
@@ -499,6 +506,10 @@ search_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
                                         (kb | kk) != 0 ? 1u : 0u);
                 else umma_f16(d_tmem, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), kIdesc,
                               (kb | kk) != 0 ? 1u : 0u);
+              }
+              if (MODE == 2 && kb == P.KB - 1) {   // stands in for the bias-augmentation k-step
+                if (PAIR) umma_f16_pair(d_tmem, adesc, bdesc, kIdescPair, 1u);
+                else umma_f16(d_tmem, adesc, bdesc, kIdesc, 1u);
               }
               if (PAIR) umma_commit_pair(smem_u32(&bars->empty[stage]));
               else if (CLUSTER > 1) umma_commit_mc(smem_u32(&bars->empty[stage]), (uint16_t)((1u << CLUSTER) - 1u));
@@ -532,21 +543,32 @@ search_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     // every row tile, so global loads in the epilogue would miss L1 and sit in its dependency chain.  This warp
     // copies each N tile's 256 biases into smem, one slot per accumulator buffer, as soon as the epilogue has
     // released that buffer (same cadence as the MMA warp).
+    // The loads of tile i+1 are issued before the wait for tile i's slot, so their L2 latency is off the critical path.
     uint32_t acc = 0, acc_ph = 0;
-    for (int g = cid; g < G; g += num_clusters) {
-      const int h = g / P.GPH;
-      const float* bias_h = P.bias + (size_t)h * P.Kp;
-      for (int nt = 0; nt < P.NT; ++nt) {
-        const float4 v0 = __ldg(reinterpret_cast<const float4*>(bias_h + nt * kBlockN) + lane);
-        const float4 v1 = __ldg(reinterpret_cast<const float4*>(bias_h + nt * kBlockN) + 32 + lane);
-        if (PAIR) mbar_wait(smem_u32(&bars->bias_empty[acc]), acc_ph ^ 1u);   // local epilogue released the slot
-        else mbar_wait(smem_u32(&bars->tmem_empty[acc]), acc_ph ^ 1u);
-        reinterpret_cast<float4*>(bars->bias[acc])[lane] = v0;
-        reinterpret_cast<float4*>(bars->bias[acc])[32 + lane] = v1;
-        __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&bars->bias_full[acc]));   // release semantics order the stores
-        if (++acc == 2) { acc = 0; acc_ph ^= 1u; }
+    int g = cid, nt = 0;
+    float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+    if (g < G) {
+      const float* b = P.bias + (size_t)(g / P.GPH) * P.Kp;
+      v0 = __ldg(reinterpret_cast<const float4*>(b) + lane);
+      v1 = __ldg(reinterpret_cast<const float4*>(b) + 32 + lane);
+    }
+    while (g < G) {
+      int g2 = g, nt2 = nt + 1;
+      if (nt2 == P.NT) { nt2 = 0; g2 += num_clusters; }
+      float4 n0 = v0, n1 = v1;
+      if (g2 < G) {
+        const float* b = P.bias + (size_t)(g2 / P.GPH) * P.Kp + nt2 * kBlockN;
+        n0 = __ldg(reinterpret_cast<const float4*>(b) + lane);
+        n1 = __ldg(reinterpret_cast<const float4*>(b) + 32 + lane);
       }
+      if (PAIR) mbar_wait(smem_u32(&bars->bias_empty[acc]), acc_ph ^ 1u);   // local epilogue released the slot
+      else mbar_wait(smem_u32(&bars->tmem_empty[acc]), acc_ph ^ 1u);
+      reinterpret_cast<float4*>(bars->bias[acc])[lane] = v0;
+      reinterpret_cast<float4*>(bars->bias[acc])[32 + lane] = v1;
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&bars->bias_full[acc]));   // release semantics order the stores
+      if (++acc == 2) { acc = 0; acc_ph ^= 1u; }
+      v0 = n0; v1 = n1; g = g2; nt = nt2;
     }
   } else if (warp < kNumEpiWarps) {
     // =============================== epilogue: bias + packed running top-2 ===============================
@@ -557,7 +579,7 @@ search_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + quarter * 64;
     // Emax * (2 + slack): the part of the candidate threshold that does not depend on the row minimum
     const float tconst = __uint_as_float(P.scal[6]) * (2.f + kPackSlackTC);
-    const bool prof = (P.dbg & 32) != 0 && warp == 0;
+    const bool prof = MODE == 1 && (P.dbg & 32) != 0 && warp == 0;
     unsigned long long w_tf = 0, w_bias = 0;
     const long long t_begin = clock64();
     uint32_t r[16];
@@ -583,7 +605,7 @@ search_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
       float m_run = INF, t_run = INF;              // running row minimum (this thread's columns) and its threshold
       // shared running minimum of the row (all four quarters); disabled for tiny codebooks (see Barriers::rowmin)
       int* row_slot = nullptr;
-      if (P.NT >= 4 && !(P.dbg & 64)) {
+      if (P.NT >= 4 && !(MODE == 1 && (P.dbg & 64))) {
         bars->rowmin[(tile_it + 1) % 3][q * 32 + lane] = 0x7fffffff;        // reset the NEXT row tile's slot
         row_slot = &bars->rowmin[tile_it % 3][q * 32 + lane];
       }
@@ -602,21 +624,21 @@ search_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
           if (nt + par < P.NT) {
             // r[] already holds (or is receiving) chunk 0 of this tile
             const uint32_t taddr = lane_addr + acc * (uint32_t)kBlockN;
-            mbar_wait_t(smem_u32(&bars->bias_full[acc]), acc_ph, prof, w_bias);
+            if (MODE != 2) mbar_wait_t(smem_u32(&bars->bias_full[acc]), acc_ph, prof, w_bias);
             const float4* bias4 = reinterpret_cast<const float4*>(bars->bias[acc] + quarter * 64);
             float key[16];
             float cmin;
 #define VQB_CHUNK(CH)                                                                                      \
-            cmin = chunk_scores(r, bias4 + (CH) * 4, ninv, key);                                           \
+            cmin = chunk_scores<MODE>(r, bias4 + (CH) * 4, ninv, key);                                     \
             TMEM_LD16(taddr + ((CH) + 1) * 16, r);                                                         \
-            if (par == 0) chunk_rank<0, (CH)>(key, cmin, idmask, tconst, m_run, t_run, row_slot, a1, a2, any_slow, P.dbg); \
-            else chunk_rank<1, (CH)>(key, cmin, idmask, tconst, m_run, t_run, row_slot, a1, a2, any_slow, P.dbg);
+            if (par == 0) chunk_rank<0, (CH), MODE>(key, cmin, idmask, tconst, m_run, t_run, row_slot, a1, a2, any_slow, P.dbg); \
+            else chunk_rank<1, (CH), MODE>(key, cmin, idmask, tconst, m_run, t_run, row_slot, a1, a2, any_slow, P.dbg);
             VQB_CHUNK(0) VQB_CHUNK(1) VQB_CHUNK(2)
 #undef VQB_CHUNK
             // last chunk: once its scores are formed every TMEM read of this tile is complete -> hand the buffer
             // back to the MMA warp, then start loading the next tile's first chunk (before this chunk's ranking
             // work if that accumulator is already complete)
-            cmin = chunk_scores(r, bias4 + 12, ninv, key);
+            cmin = chunk_scores<MODE>(r, bias4 + 12, ninv, key);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
@@ -635,8 +657,8 @@ search_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
               TMEM_LD16(lane_addr + acc * (uint32_t)kBlockN, r);
               issued = true;
             }
-            if (par == 0) chunk_rank<0, 3>(key, cmin, idmask, tconst, m_run, t_run, row_slot, a1, a2, any_slow, P.dbg);
-            else chunk_rank<1, 3>(key, cmin, idmask, tconst, m_run, t_run, row_slot, a1, a2, any_slow, P.dbg);
+            if (par == 0) chunk_rank<0, 3, MODE>(key, cmin, idmask, tconst, m_run, t_run, row_slot, a1, a2, any_slow, P.dbg);
+            else chunk_rank<1, 3, MODE>(key, cmin, idmask, tconst, m_run, t_run, row_slot, a1, a2, any_slow, P.dbg);
             if (more && !issued) {
               mbar_wait_t(smem_u32(&bars->tmem_full[acc]), acc_ph, prof, w_tf);
               tc_fence_after();
@@ -727,14 +749,14 @@ static bool g_ev_made = false;
 static int g_ev_dev = -1;              // the events belong to the device of the first timed search
 static int g_ev_count = 0;
 
-template <int CLUSTER, bool PAIR>
+template <int CLUSTER, bool PAIR, int MODE>
 static int launch_impl(const CUtensorMap& mx, const CUtensorMap& mc, const SearchParams& P, size_t smem_bytes,
                        int grid, bool timing, cudaStream_t st) {
   static bool configured[64] = {};      // function attributes are per device
   int dev = 0;
   VQB_CUDA_TRY(cudaGetDevice(&dev));
   if (dev < 0 || dev >= 64 || !configured[dev]) {
-    VQB_CUDA_TRY(cudaFuncSetAttribute(search_tc_kernel<CLUSTER, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    VQB_CUDA_TRY(cudaFuncSetAttribute(search_tc_kernel<CLUSTER, PAIR, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       227 * 1024));
     if (dev >= 0 && dev < 64) configured[dev] = true;
   }
@@ -763,7 +785,7 @@ static int launch_impl(const CUtensorMap& mx, const CUtensorMap& mc, const Searc
     if (g_ev_count < kTimingSlots) slot = g_ev_count++;
   }
   if (slot >= 0) VQB_CUDA_TRY(cudaEventRecord(g_ev0[slot], st));
-  VQB_CUDA_TRY(cudaLaunchKernelEx(&cfg, search_tc_kernel<CLUSTER, PAIR>, mx, mc, P));
+  VQB_CUDA_TRY(cudaLaunchKernelEx(&cfg, search_tc_kernel<CLUSTER, PAIR, MODE>, mx, mc, P));
   ++g_launch_count;
   if (slot >= 0) VQB_CUDA_TRY(cudaEventRecord(g_ev1[slot], st));
   return VQB_OK;
@@ -819,9 +841,15 @@ int launch_search_tc(const __half* xb, const float* xinv, const __half* cb, cons
   if (rc) return rc;
   rc = make_map(&mc, cb, dp, Kp, H, kBlockN / cluster);
   if (rc) return rc;
-  if (pair) return launch_impl<2, true>(mx, mc, P, smem_bytes, grid, timing, st);
-  if (cluster == 2) return launch_impl<2, false>(mx, mc, P, smem_bytes, grid, timing, st);
-  return launch_impl<1, false>(mx, mc, P, smem_bytes, grid, timing, st);
+  const int kmode = P.dbg == 0 ? 0 : ((P.dbg & 128) ? 2 : 1);
+#define VQB_LAUNCH_MODE(C, PR)                                                                         \
+  (kmode == 0 ? launch_impl<C, PR, 0>(mx, mc, P, smem_bytes, grid, timing, st)                         \
+   : kmode == 1 ? launch_impl<C, PR, 1>(mx, mc, P, smem_bytes, grid, timing, st)                       \
+                : launch_impl<C, PR, 2>(mx, mc, P, smem_bytes, grid, timing, st))
+  if (pair) return VQB_LAUNCH_MODE(2, true);
+  if (cluster == 2) return VQB_LAUNCH_MODE(2, false);
+  return VQB_LAUNCH_MODE(1, false);
+#undef VQB_LAUNCH_MODE
 }
 
 int debug_counters(unsigned long long* out18) {   // [0..1] ranked/skipped chunks, [2..17] cycle counters

@@ -90,6 +90,7 @@ class Codebook(nn.Module):
         self._cache_key = None
         self._dirty = True
         self.last_search_ws: Optional[torch.Tensor] = None
+        self.fused_quantize_ema = True     # False: separate gather and EMA-reduce passes (same results)
 
     # ------------------------------------------------------------------ transforms
     def transform_input(self, x: torch.Tensor) -> torch.Tensor:
@@ -229,15 +230,25 @@ class Codebook(nn.Module):
 
         training = self.training
         commit = None
-        if fuse_st and training:
-            quant, commit = ops.quantize_training(flat, emb, idx, mask_u8, want_commit)
+        update = training and self.ema_update and not freeze_codebook
+        # un-masked training step: gather/ST/loss and the EMA sums share ONE pass over the latents
+        fused = update and mask_u8 is None and self.fused_quantize_ema and ops.quantize_ema_supported(d)
+        stats = None
+        if fused and fuse_st:
+            quant, commit, stats = ops.quantize_training(flat, emb, idx, None, want_commit, ema=True, bound_ws=ws)
+        elif fused:
+            with torch.no_grad():
+                quant, _, stats = ops.quantize_ema(flat, emb, idx, False, False, bound_ws=ws)
+        elif fuse_st and training:
+            quant, commit, _ = ops.quantize_training(flat, emb, idx, mask_u8, want_commit)
         else:
             with torch.no_grad():
                 quant, _ = ops.gather_st_loss(flat, emb, idx, None, False, False)
 
-        if training and self.ema_update and not freeze_codebook:
+        if update:
             with torch.no_grad():
-                stats = ops.ema_reduce(flat, idx, mask_u8, self.codebook_size, bound_ws=ws)
+                if stats is None:
+                    stats = ops.ema_reduce(flat, idx, mask_u8, self.codebook_size, bound_ws=ws)
                 self._all_reduce(stats)                       # one packed (H,K,d+1) allreduce (reference: two)
                 ops.ema_apply(stats, self.cluster_size.data, self.embed_avg.data, self.embeddings.data,
                               1 - self.decay, self.eps_for_smoothing, self.weights_l2norm)

@@ -136,44 +136,77 @@ def gather_st_loss(x: torch.Tensor, embeddings: torch.Tensor, idx: torch.Tensor,
     return q, loss
 
 
-class _QuantizeST(torch.autograd.Function):
-    """Training-mode quantize: returns (x + (c - x).detach(), mse(c.detach(), x)).
+def quantize_ema_supported(d: int) -> bool:
+    return bool(L.lib().vqb_quantize_ema_supported(int(d)))
 
+
+def quantize_ema(x: torch.Tensor, embeddings: torch.Tensor, idx: torch.Tensor, training: bool, want_loss: bool,
+                 bound_ws: Optional[torch.Tensor] = None):
+    """Fused gather/ST/loss + EMA sums (no mask): returns (q (H,N,d) fp32, loss_buf | None, stats (H,K,d+1))."""
+    L.require_cuda(x, "x")
+    H, N, d = x.shape
+    K = embeddings.shape[1]
+    dev = x.device
+    q = torch.empty((H, N, d), dtype=torch.float32, device=dev)
+    loss = torch.empty(2, dtype=torch.float32, device=dev) if want_loss else None
+    stats = torch.empty((H, K, d + 1), dtype=torch.float32, device=dev)
+    ws = workspace("ema", L.lib().vqb_quantize_ema_workspace_bytes(H, N, K, d), dev)
+    L.check(L.lib().vqb_quantize_ema(L.ptr(x), L.dtype_code(x), L.ptr(embeddings), L.ptr(idx), L.ptr(bound_ws),
+                                     int(training), int(want_loss), L.ptr(q), L.ptr(loss), L.ptr(stats), H, N, K, d,
+                                     L.ptr(ws), ws.numel(), L.stream_ptr(dev)), "vqb_quantize_ema")
+    return q, loss, stats
+
+
+class _QuantizeST(torch.autograd.Function):
+    """Training-mode quantize: returns (x + (c - x).detach(), mse(c.detach(), x), stats | None).
+
+    With `ema` set (no mask) the forward is the fused pass that also produces the EMA statistics.
     Backward (reference autograd through vector_quantize_pytorch.py:273,362):
       grad_x = grad_q + grad_commit * 2 (x - c) / (rows_used * d);  the codebook gets no gradient.
     """
 
     @staticmethod
-    def forward(ctx, x, embeddings, idx, mask_u8, want_loss):
-        q, loss = gather_st_loss(x, embeddings, idx, mask_u8, True, want_loss)
+    def forward(ctx, x, embeddings, idx, mask_u8, want_loss, ema, bound_ws):
+        stats = None
+        if ema:
+            q, loss, stats = quantize_ema(x, embeddings, idx, True, want_loss, bound_ws)
+        else:
+            q, loss = gather_st_loss(x, embeddings, idx, mask_u8, True, want_loss)
         ctx.save_for_backward(x, embeddings, idx, mask_u8 if mask_u8 is not None else torch.empty(0), loss
                               if loss is not None else torch.empty(0))
         ctx.has_mask = mask_u8 is not None
         ctx.want_loss = want_loss
         commit = loss[0] if want_loss else torch.zeros((), device=x.device)
-        return q, commit
+        if stats is None:
+            stats = torch.empty(0, device=x.device)
+        ctx.mark_non_differentiable(stats)
+        return q, commit, stats
 
     @staticmethod
-    def backward(ctx, grad_q, grad_commit):
+    def backward(ctx, grad_q, grad_commit, _grad_stats):
         x, embeddings, idx, mask_u8, loss = ctx.saved_tensors
         H, N, d = x.shape
         K = embeddings.shape[1]
         if grad_q is None:
             grad_q = torch.zeros((H, N, d), dtype=torch.float32, device=x.device)
         grad_q = grad_q.contiguous().float()
+        none = (None,) * 6
         if not ctx.want_loss or grad_commit is None:
-            return grad_q.to(x.dtype), None, None, None, None
+            return (grad_q.to(x.dtype),) + none
         # device scalar: grad_commit * 2 / (rows_used * d)   (no host sync)
         g = (grad_commit.float() * (2.0 / d) / loss[1]).reshape(1).contiguous()
         gx = torch.empty((H, N, d), dtype=torch.float32, device=x.device)
         L.check(L.lib().vqb_st_commit_backward(L.ptr(grad_q), L.ptr(g), L.ptr(x), L.dtype_code(x), L.ptr(embeddings),
                                                L.ptr(idx), L.ptr(mask_u8) if ctx.has_mask else 0, 1.0, L.ptr(gx),
                                                H, N, K, d, L.stream_ptr(x.device)), "vqb_st_commit_backward")
-        return gx.to(x.dtype), None, None, None, None
+        return (gx.to(x.dtype),) + none
 
 
-def quantize_training(x, embeddings, idx, mask_u8, want_loss):
-    return _QuantizeST.apply(x, embeddings, idx, mask_u8, want_loss)
+def quantize_training(x, embeddings, idx, mask_u8, want_loss, ema: bool = False, bound_ws=None):
+    """(q, commit, stats | None); `ema=True` (mask must be None) uses the fused gather+EMA pass."""
+    assert not (ema and mask_u8 is not None)
+    q, commit, stats = _QuantizeST.apply(x, embeddings, idx, mask_u8, want_loss, ema, bound_ws)
+    return q, commit, (stats if ema else None)
 
 
 # ---------------------------------------------------------------------------------------------
