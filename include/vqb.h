@@ -180,14 +180,17 @@ int    vqb_expire_scatter(const void* x, int x_dtype, const int64_t* sample_rows
  *   r_next   = fl(r - q)                  (residual_out; may alias residual_in, but the caller normally
  *                                          ping-pongs two buffers so the level input survives for expiry sampling)
  *   loss_out = [mean((c - r)^2) over rows with mask!=0, rows used]   (as vqb_gather_st_loss)
- *   next_ws  : bf16 copy + row stats of r_next, laid out exactly as vqb_search expects with
- *              VQB_SEARCH_LATENTS_PREPARED (NULL on the last level).
+ *   next_ws  : scaled fp16 copy + row stats + bias operand of r_next, laid out exactly as vqb_search expects
+ *              with VQB_SEARCH_LATENTS_PREPARED (NULL on the last level).
+ *   next_cache: codebook cache (vqb_prepare_codebook) of the level that will search next_ws -- the bias
+ *              operand depends on its scale; required when next_ws is given.  If that cache is rebuilt with
+ *              a different scale before the search, the search notices and rescans exactly.
  *   q_out    : nullable, per-level quantized output (needed only for return_all_codes). */
 int    vqb_rvq_level(const float* residual_in, float* residual_out, const float* codebook, const int64_t* idx,
                      const uint8_t* mask, int training, int first_level, float* quantized_out, float* q_out,
                      float* loss_out, int64_t N, int K, int d,
                      void* gather_ws, size_t gather_ws_bytes,
-                     void* next_ws, size_t next_ws_bytes, void* stream);
+                     void* next_ws, size_t next_ws_bytes, const void* next_cache, void* stream);
 
 /* ---- sharded-codebook merge (K >= 64K split across GPUs) ------------------------------
  * No reference counterpart.  key = (orderable(score) << 32) | index, so an

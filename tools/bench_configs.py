@@ -53,6 +53,9 @@ def op_level(x, c, cos, K):
     st = ops.search_stats(ws)
     t_gather = timed(lambda: ops.gather_st_loss(x, c, idx, None, True, True), iters=5, warm=2)
     t_ema = timed(lambda: ops.ema_reduce(x, idx, None, K, bound_ws=ws), iters=5, warm=2)
+    t_fused = None
+    if ops.quantize_ema_supported(d):
+        t_fused = timed(lambda: ops.quantize_ema(x, c, idx, True, True, bound_ws=ws), iters=5, warm=2)
     gather_bytes = N * (esz * d + 4 * d + 8)
     ema_bytes = N * (esz * d + 8) + K * (d + 1) * 4
     flops = 2.0 * N * K * d
@@ -62,6 +65,10 @@ def op_level(x, c, cos, K):
             "rescanned_rows": st["rescanned_rows"],
             "gather_ms": t_gather, "gather_GBs": gather_bytes / t_gather / 1e6,
             "gather_frac_hbm": gather_bytes / t_gather / 1e6 / PEAK["hbm_gbs"],
+            "fused_gather_ema_ms": t_fused,
+            "fused_GBs": None if t_fused is None else (N * (esz * d + 4 * d + 8) + K * (d + 1) * 4) / t_fused / 1e6,
+            "fused_frac_hbm": None if t_fused is None else (N * (esz * d + 4 * d + 8) + K * (d + 1) * 4) / t_fused / 1e6 / PEAK["hbm_gbs"],
+            "fused_vs_separate_ops_frac_hbm": None if t_fused is None else (gather_bytes + ema_bytes) / t_fused / 1e6 / PEAK["hbm_gbs"],
             "ema_reduce_ms": t_ema, "ema_GBs": ema_bytes / t_ema / 1e6, "ema_frac_hbm": ema_bytes / t_ema / 1e6 / PEAK["hbm_gbs"]}
 
 

@@ -29,7 +29,7 @@ if cy[3]:
     f = lambda v: f"{v / nb / 1e3:9.1f}k"
     print(f"   per CTA-launch cycles: producer total {f(cy[0])} wait a_empty {f(cy[1])} wait stage-empty {f(cy[2])}")
     print(f"                          mma      total {f(cy[3])} wait tmem_empty {f(cy[4])} wait a_full {f(cy[5])} wait stage-full {f(cy[6])}")
-    print(f"                          epi warp total {f(cy[7])} wait tmem_full {f(cy[8])} wait bias {f(cy[9])}")
+    print(f"                          epi warp total {f(cy[7])} wait tmem_full {f(cy[8])} wait bias {f(cy[9])} tmem ld wait {f(cy[10])} try tmem_full {f(cy[11])}")
 if buf[0] + buf[1]:
     print(f"   ranked chunks {buf[0]}  skipped {buf[1]}  -> ranked fraction {buf[0] / (buf[0] + buf[1]):.3f}")
 print(f"VQB_CLUSTER={os.environ.get('VQB_CLUSTER','-')} VQB_TC_DEBUG={os.environ.get('VQB_TC_DEBUG','0')} N={N} K={K} d={d}: "

@@ -44,6 +44,7 @@ constexpr int kBlockN = 256;   // codes per N tile (UMMA N)
 constexpr int kBlockK = 64;    // bf16 elements per k-block = one 128B swizzle atom
 constexpr int kNumCand = 24;   // candidates kept per row: 4 column quarters x 2 classes x top-3
 constexpr float kPadBias = 3.0e38f;
+constexpr int kHdrFloats = 8;  // per-codebook header of the cache (see CacheLayout)
 
 __host__ __device__ inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
 __host__ __device__ inline int64_t round_up64(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
@@ -54,8 +55,8 @@ inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 // Derived codebook cache layout (one caller-owned buffer).
 struct CacheLayout {
   int Kp, dp;
-  size_t off_hdr;    // f32  [H][4]       = {s_c (power of two), 1/s_c, max|c|, -}
-  size_t off_cb;     // fp16 [H][Kp][dp]  = fp16(c * s_c), zero padded
+  size_t off_hdr;    // f32  [H][8]       = {s_c (power of two), 1/s_c, max|c|, max|c|^2/2, 2^q, 2^-q, -, -}  (2^q: scale of the bias operand)
+  size_t off_cb;     // fp16 [H][Kp][dp]  = -fp16(c * s_c), zero padded (negated: the accumulator is then a score)
   size_t off_cn2h;   // f32  [H][Kp]      = |c|^2 / 2   (0 for the dot metric)
   size_t off_cn;     // f32  [H][Kp]      = |c|
   size_t off_dcn;    // f32  [H][Kp]      = |c - fp16(c*s_c)/s_c|
@@ -66,7 +67,7 @@ inline CacheLayout cache_layout(int64_t H, int K, int d) {
   L.Kp = k_pad(K);
   L.dp = d_pad(d);
   size_t o = 0;
-  L.off_hdr = o;  o += align_up((size_t)H * 16);
+  L.off_hdr = o;  o += align_up((size_t)H * kHdrFloats * 4);
   L.off_cb = o;   o += align_up((size_t)H * L.Kp * L.dp * 2);
   L.off_cn2h = o; o += align_up((size_t)H * L.Kp * 4);
   L.off_cn = o;   o += align_up((size_t)H * L.Kp * 4);
@@ -78,16 +79,20 @@ inline CacheLayout cache_layout(int64_t H, int K, int d) {
 // Search workspace layout (one caller-owned buffer).
 struct SearchLayout {
   int dp;
-  size_t off_scal;    // u32[64]: [0]=max|x_b| bits, [1]=max|x-x_b| bits, [2]=#rescanned, [3]=#reranked, [4]=tc used, [5]=smem misalign flag, [6]=max E_k bits
+  size_t off_scal;    // u32[64]: [0]=max|x_b| bits, [1]=max|x-x_b| bits, [2]=#rescanned, [3]=#reranked, [4]=tc used, [5]=smem misalign flag, [6]=max E_k bits, [7]=2^q bits of operands prepared by vqb_rvq_level (0: prepared by this search), [8]=1: keys not pre-lowered by E_k (window 2 Emax)
   size_t off_cnt;     // u32[H]: flagged rows per codebook (directly after scal: zeroed together)
   size_t off_xb;      // fp16 [H][N][dp]  = fp16(x * s_row), zero padded
-  size_t off_xinv;    // f32  [H][N]      = 1 / s_row (exact power of two)
+  size_t off_xinv;    // f32  [H][N]      = 1 / s_row (exact power of two); NEGATIVE marks a row whose bias operand
+                      //                    s_row 2^-q is not an fp16 number: such rows are rescanned exactly
+  size_t off_xaug;    // fp16 [H][N][8]   = {a, a, a, 0, ...}, a = s_row 2^-q: the latent side of the bias k-step
   size_t off_keys;    // u64  [H][N]      packed (score, index) min-keys of rows being rescanned
   size_t off_cand;    // {f32 key, i32 code} [H][N][kNumCand]
   size_t off_flag;    // i32 [H*N] flagged row list
   size_t off_rr;      // i32 [H*N] rows queued for the warp-per-row re-rank (length in scal[3])
   size_t off_bias;    // f32 [H][Kp]  lower-bound bias  |c|^2/2 - E_k  (needs the row stats, so per search)
   size_t off_err;     // f32 [H][Kp]  E_k: bound on |exact score - bf16 tensor-core score| for code k
+  size_t off_caug;    // fp16 [H][Kp][8]  three fp16 pieces of s_c 2^q bias_k (+inf for padded codes), then zeros:
+                      //                  the bias term of the score as one extra MMA k-step (search_tc.cu)
   size_t total;
 };
 inline SearchLayout search_layout(int64_t H, int64_t N, int K, int d) {
@@ -98,12 +103,14 @@ inline SearchLayout search_layout(int64_t H, int64_t N, int K, int d) {
   L.off_cnt = o;  o += align_up((size_t)H * 4);
   L.off_xb = o;   o += align_up((size_t)H * N * L.dp * 2);
   L.off_xinv = o; o += align_up((size_t)H * N * 4);
+  L.off_xaug = o; o += align_up((size_t)H * N * 16);
   L.off_keys = o; o += align_up((size_t)H * N * 8);
   L.off_cand = o; o += align_up((size_t)H * N * kNumCand * 8);
   L.off_flag = o; o += align_up((size_t)H * N * 4);
   L.off_rr = o;   o += align_up((size_t)H * N * 4);
   L.off_bias = o; o += align_up((size_t)H * k_pad(K) * 4);
   L.off_err = o;  o += align_up((size_t)H * k_pad(K) * 4);
+  L.off_caug = o; o += align_up((size_t)H * k_pad(K) * 16);
   L.total = o;
   return L;
 }
@@ -187,15 +194,32 @@ __device__ __forceinline__ double warp_sum(double v) {
 inline int dtype_size(int dt) { return dt == VQB_F32 ? 4 : 2; }
 
 // ---- internal launchers (defined across the .cu files) --------------------------------------
-int launch_prepare_latents(const void* x, int x_dtype, int64_t rows, int d, int dp,
-                           __half* xb, float* xinv, uint32_t* scal, cudaStream_t st);
+// chdr: per-codebook cache header (nullable: no bias operand is written then); rows_per_head maps a row to its header
+int launch_prepare_latents(const void* x, int x_dtype, int64_t rows, int64_t rows_per_head, int d, int dp,
+                           const float* chdr, __half* xb, float* xinv, __half* xaug, uint32_t* scal, cudaStream_t st);
 int launch_make_bias(const void* cache, const CacheLayout& CL, int64_t H, int K, int metric,
-                     uint32_t* scal, float* bias, float* err, cudaStream_t st);
-int launch_search_tc(const __half* xb, const float* xinv, const __half* cb, const float* chdr, const float* bias,
-                     int64_t H, int64_t N, int K, int dp, void* cand, uint32_t* scal, bool timing, cudaStream_t st);
+                     uint32_t* scal, float* bias, float* err, __half* caug, cudaStream_t st);
+// xaug / caug: the bias k-step operands (both NULL: bias added in the epilogue from `bias`)
+// aug_mode (search_tc_aug_mode): 0 = bias added in the epilogue from `bias`; 1 = bias as an extra MMA k-step;
+// 2 = same kernel without the k-step (dot metric, no padded codes)
+int launch_search_tc(const __half* xb, const float* xinv, const __half* xaug, const __half* cb, const __half* caug,
+                     const float* chdr, const float* bias, int aug_mode, int64_t H, int64_t N, int K, int dp,
+                     void* cand, uint32_t* scal, bool timing, cudaStream_t st);
+int search_tc_aug_mode(int64_t N, int K, int metric);
 
 int launch_loss_finalize(const double* part, const long long* cntp, int nblocks, int d, float* loss_out,
                          cudaStream_t st);
+
+// Row scale for the tensor-core operand and the bias operand a = s 2^-q that goes with it: s is the natural
+// power-of-two scale (max|x~| in [2^13, 2^14)), lowered if needed so that a <= 2^15 stays an fp16 number
+// (a smaller s only moves x~ down inside fp16's 40 binades; the rounding residual is MEASURED, not assumed).
+// Returns a, or 0 when a would fall below fp16's smallest subnormal (such rows are rescanned exactly).
+__device__ __forceinline__ float clamp_row_scale(float& s, float two_q, float two_mq) {
+  const float cap = 32768.f * two_q;           // a = s 2^-q <= 2^15
+  if (s > cap) s = cap;
+  const float a = s * two_mq;
+  return a >= 5.9604645e-8f ? a : 0.f;          // 2^-24
+}
 
 // power-of-two scale that brings a magnitude bound m below 2^14 (fp16 max is 65504)
 __host__ __device__ inline float pow2_scale(float m) {

@@ -171,7 +171,8 @@ rvq_level_kernel(const float* res_in, float* res_out, const float* __restrict__ 
                  const uint8_t* __restrict__ mask, int training, int first, float* __restrict__ out,
                  float* __restrict__ qout, int64_t N, int K, int d, int dp, double* __restrict__ part,
                  long long* __restrict__ cntp, __half* __restrict__ next_xb, float* __restrict__ next_xinv,
-                 uint32_t* __restrict__ next_scal) {
+                 uint32_t* __restrict__ next_scal, __half* __restrict__ next_xaug,
+                 const float* __restrict__ next_chdr) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int wpb = kGatherThreads / 32;
   double sqd = 0.0;
@@ -233,8 +234,14 @@ rvq_level_kernel(const float* res_in, float* res_out, const float* __restrict__ 
     if (next_xb) {
 #pragma unroll
       for (int o2 = 16; o2 > 0; o2 >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o2));
-      const float s = pow2_scale(m), is = 1.f / s;
-      if (lane == 0) next_xinv[row] = is;
+      float s = pow2_scale(m);
+      const float a = clamp_row_scale(s, next_chdr[4], next_chdr[5]);    // bias operand of the next level's search
+      const float is = 1.f / s;
+      if (lane == 0) {
+        next_xinv[row] = a > 0.f ? is : -is;
+        const uint32_t aa = (uint32_t)__half_as_ushort(__float2half_rn(a));
+        *reinterpret_cast<uint4*>(next_xaug + row * 8) = make_uint4(aa | (aa << 16), aa, 0u, 0u);
+      }
       __half* xo = next_xb + row * (int64_t)dp;
       float n2 = 0.f, r2 = 0.f;
       if (vec) {
@@ -288,6 +295,7 @@ rvq_level_kernel(const float* res_in, float* res_out, const float* __restrict__ 
       const float infl = 1.f + (float)dp * 2.4e-7f;
       atomicMax(next_scal + 0, __float_as_uint(sqrtf(a * infl) * 1.00001f));
       atomicMax(next_scal + 1, __float_as_uint(sqrtf(b * infl) * 1.00001f));
+      if (blockIdx.x == 0) next_scal[7] = __float_as_uint(next_chdr[4]);   // the 2^q these operands were built with
     }
   }
 }
@@ -360,23 +368,29 @@ extern "C" int vqb_rvq_level(const float* residual_in, float* residual_out, cons
                              const int64_t* idx, const uint8_t* mask, int training, int first_level,
                              float* quantized_out, float* q_out, float* loss_out, int64_t N, int K, int d,
                              void* gather_ws, size_t gather_ws_bytes, void* next_ws, size_t next_ws_bytes,
-                             void* stream) {
+                             const void* next_cache, void* stream) {
   VQB_REQUIRE(residual_in && residual_out && codebook && idx && quantized_out && loss_out && gather_ws,
               VQB_ERR_INVALID, "vqb_rvq_level: null pointer");
   GatherLayout L = gather_layout();
   VQB_REQUIRE(gather_ws_bytes >= L.total, VQB_ERR_WORKSPACE, "gather workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
   __half* nxb = nullptr;
+  __half* nxaug = nullptr;
   float* nxinv = nullptr;
   uint32_t* nscal = nullptr;
+  const float* nchdr = nullptr;
   const int dp = d_pad(d);
   if (next_ws && dp > 512) next_ws = nullptr;   // no tensor-core pass for this width: nothing to prepare
   if (next_ws) {
+    VQB_REQUIRE(next_cache != nullptr, VQB_ERR_INVALID,
+                "vqb_rvq_level: next_ws needs next_cache (the codebook cache of the level that will search it)");
     SearchLayout SL = search_layout(1, N, K, d);
     VQB_REQUIRE(next_ws_bytes >= SL.total, VQB_ERR_WORKSPACE, "next-level search workspace too small");
     nxb = (__half*)((char*)next_ws + SL.off_xb);
+    nxaug = (__half*)((char*)next_ws + SL.off_xaug);
     nxinv = (float*)((char*)next_ws + SL.off_xinv);
     nscal = (uint32_t*)((char*)next_ws + SL.off_scal);
+    nchdr = (const float*)((const char*)next_cache + cache_layout(1, K, d).off_hdr);
     VQB_CUDA_TRY(cudaMemsetAsync(nscal, 0, 8, st));
   }
   const int grid = gather_grid(N);
@@ -385,7 +399,7 @@ extern "C" int vqb_rvq_level(const float* residual_in, float* residual_out, cons
   if (N > 0) {
     rvq_level_kernel<<<grid, kGatherThreads, 0, st>>>(residual_in, residual_out, codebook, idx, mask, training, first_level,
                                                       quantized_out, q_out, N, K, d, dp, part, cntp,
-                                                      nxb, nxinv, nscal);
+                                                      nxb, nxinv, nscal, nxaug, nchdr);
     VQB_LAUNCH_CHECK();
   }
   loss_finalize_kernel<<<1, 256, 0, st>>>(part, cntp, N > 0 ? grid : 0, d, loss_out);

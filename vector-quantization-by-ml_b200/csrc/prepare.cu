@@ -20,7 +20,7 @@ __global__ void codebook_absmax_kernel(const float* __restrict__ cb, int64_t per
     m = fmaxf(m, fabsf(c[i]));
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-  if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<uint32_t*>(hdr + h * 4 + 2), __float_as_uint(m));
+  if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<uint32_t*>(hdr + h * kHdrFloats + 2), __float_as_uint(m));
 }
 
 // one warp per code row (incl. padded rows k in [K, Kp)): fp16(c * s_c) + norms of c and of the rounding residual
@@ -32,9 +32,9 @@ __global__ void prepare_codebook_kernel(const float* __restrict__ cb, int64_t H,
   if (row >= H * (int64_t)Kp) return;
   const int64_t h = row / Kp;
   const int k = (int)(row - h * Kp);
-  const float sc = pow2_scale(hdr[h * 4 + 2]);
+  const float sc = pow2_scale(hdr[h * kHdrFloats + 2]);
   const float isc = 1.f / sc;
-  if (k == 0 && lane == 0) { hdr[h * 4 + 0] = sc; hdr[h * 4 + 1] = isc; }
+  if (k == 0 && lane == 0) { hdr[h * kHdrFloats + 0] = sc; hdr[h * kHdrFloats + 1] = isc; }
   __half* o = out + row * dp;
   if (k >= K) {
     for (int j = lane; j < dp; j += 32) o[j] = __float2half(0.f);
@@ -47,7 +47,7 @@ __global__ void prepare_codebook_kernel(const float* __restrict__ cb, int64_t H,
     const float v = j < d ? c[j] : 0.f;
     const __half hv = __float2half_rn(v * sc);           // power-of-two scaling is exact
     const float back = __half2float(hv) * isc;
-    o[j] = hv;
+    o[j] = __hneg(hv);                                   // stored negated: accumulator = s_row s_c (|c|^2/2 - x.c)
     n2 = fma((double)v, (double)v, n2);
     const double r = (double)v - (double)back;
     r2 = fma(r, r, r2);
@@ -55,10 +55,31 @@ __global__ void prepare_codebook_kernel(const float* __restrict__ cb, int64_t H,
   n2 = warp_sum(n2);
   r2 = warp_sum(r2);
   if (lane == 0) {
-    cn2h[row] = metric == VQB_EUCLID ? (float)(0.5 * n2) : 0.f;
+    const float hh = metric == VQB_EUCLID ? (float)(0.5 * n2) : 0.f;
+    cn2h[row] = hh;
+    if (hh > 0.f) atomicMax(reinterpret_cast<uint32_t*>(hdr + h * kHdrFloats + 3), __float_as_uint(hh));
     cn[row] = __double2float_ru(sqrt(n2)) * 1.000001f;
     dcn[row] = __double2float_ru(sqrt(r2)) * 1.000001f;
   }
+}
+
+// Scale of the bias operand: b_k = s_c 2^q (|c_k|^2/2 - E_k) must be an fp16 number; q is chosen per codebook so that
+// s_c 2^q max_k |c_k|^2/2 lies in [2^12, 2^13) -- three binades of head room for E_k (make_bias_kernel checks it).
+__global__ void codebook_aug_scale_kernel(int64_t H, float* __restrict__ hdr) {
+  const int64_t h = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (h >= H) return;
+  const float sc = hdr[h * kHdrFloats + 0], hmax = hdr[h * kHdrFloats + 3];
+  int qe = 0;
+  const float t = sc * hmax;
+  if (t > 0.f && isfinite(t)) {
+    int e;
+    frexpf(t, &e);                 // t = m 2^e, m in [0.5, 1)
+    qe = 13 - e;
+    if (qe > 100) qe = 100;
+    if (qe < -100) qe = -100;
+  }
+  hdr[h * kHdrFloats + 4] = ldexpf(1.f, qe);
+  hdr[h * kHdrFloats + 5] = ldexpf(1.f, -qe);
 }
 
 // Fast variant for d % 8 == 0, d <= 256 (one 8-element group per lane): a warp converts FOUR rows per iteration with
@@ -66,8 +87,9 @@ __global__ void prepare_codebook_kernel(const float* __restrict__ cb, int64_t H,
 // ~19 KB per SM in flight ~ 3.5 TB/s).
 template <typename T>
 __global__ void __launch_bounds__(256)
-prepare_latents4_kernel(const T* __restrict__ x, int64_t rows, int d, int dp, __half* __restrict__ xb,
-                        float* __restrict__ xinv, uint32_t* __restrict__ scal) {
+prepare_latents4_kernel(const T* __restrict__ x, int64_t rows, int64_t rows_per_head, bool single_head, int d, int dp,
+                        const float* __restrict__ chdr, __half* __restrict__ xb, float* __restrict__ xinv,
+                        __half* __restrict__ xaug, uint32_t* __restrict__ scal) {
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
   const int j = lane * 8;
@@ -76,6 +98,12 @@ prepare_latents4_kernel(const T* __restrict__ x, int64_t rows, int d, int dp, __
   for (int64_t row0 = ((int64_t)blockIdx.x * wpb + (threadIdx.x >> 5)) * 4; row0 < rows;
        row0 += (int64_t)gridDim.x * wpb * 4) {
     F8 v[4];
+    float my_is = 0.f, my_a = 0.f;
+    float two_q = 1.f, two_mq = 1.f;
+    if (chdr) {   // the four rows of an iteration share a codebook (rows_per_head % 4 == 0 is checked by the launcher)
+      const float* hd = chdr + (single_head ? 0 : (uint32_t)row0 / (uint32_t)rows_per_head) * kHdrFloats;
+      two_q = hd[4]; two_mq = hd[5];
+    }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       if (on && row0 + u < rows) v[u] = load8<T>(x + (row0 + u) * (int64_t)d + j);
@@ -92,8 +120,11 @@ prepare_latents4_kernel(const T* __restrict__ x, int64_t rows, int d, int dp, __
       for (int e = 0; e < 8; ++e) m = fmaxf(m, fabsf(v[u].v[e]));
 #pragma unroll
       for (int o2 = 16; o2 > 0; o2 >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o2));
-      const float s = pow2_scale(m), is = 1.f / s;
-      if (lane == 0) xinv[row0 + u] = is;
+      float s = pow2_scale(m);
+      float a = 1.f;
+      if (chdr) a = clamp_row_scale(s, two_q, two_mq);
+      const float is = 1.f / s;
+      if (lane == u) { my_is = a > 0.f ? is : -is; my_a = a; }     // lane u keeps row u's scalars for one 4-row store
       float n2 = 0.f, r2 = 0.f;
       if (j < dp) {
         uint32_t pk[4];
@@ -115,6 +146,13 @@ prepare_latents4_kernel(const T* __restrict__ x, int64_t rows, int d, int dp, __
       max_n2 = fmaxf(max_n2, n2);
       max_r2 = fmaxf(max_r2, r2);
     }
+    if (lane < 4 && row0 + lane < rows) {          // 16 B of scales + 64 B of bias operands per iteration, coalesced
+      xinv[row0 + lane] = my_is;
+      if (xaug) {
+        const uint32_t aa = (uint32_t)__half_as_ushort(__float2half_rn(my_a));
+        *reinterpret_cast<uint4*>(xaug + (row0 + lane) * 8) = make_uint4(aa | (aa << 16), aa, 0u, 0u);
+      }
+    }
   }
   __shared__ float s_n[32], s_r[32];
   const int w = threadIdx.x >> 5;
@@ -132,8 +170,9 @@ prepare_latents4_kernel(const T* __restrict__ x, int64_t rows, int d, int dp, __
 // one warp per latent row: per-row power-of-two scale, fp16 copy (zero padded to dp),
 // atomicMax of |x~| and |x - x~| where x~ = fp16(x s)/s is what the tensor core really sees
 template <typename T>
-__global__ void prepare_latents_kernel(const T* __restrict__ x, int64_t rows, int d, int dp,
-                                       __half* __restrict__ xb, float* __restrict__ xinv,
+__global__ void prepare_latents_kernel(const T* __restrict__ x, int64_t rows, int64_t rows_per_head, int d, int dp,
+                                       const float* __restrict__ chdr, __half* __restrict__ xb,
+                                       float* __restrict__ xinv, __half* __restrict__ xaug,
                                        uint32_t* __restrict__ scal) {
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
@@ -163,8 +202,20 @@ __global__ void prepare_latents_kernel(const T* __restrict__ x, int64_t rows, in
     }
 #pragma unroll
     for (int o2 = 16; o2 > 0; o2 >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o2));
-    const float s = pow2_scale(m), is = 1.f / s;
-    if (lane == 0) xinv[row] = is;
+    float s = pow2_scale(m);
+    float a = 1.f;
+    if (chdr) {
+      const float* hd = chdr + (rows_per_head >= rows ? 0 : row / rows_per_head) * kHdrFloats;
+      a = clamp_row_scale(s, hd[4], hd[5]);
+    }
+    const float is = 1.f / s;
+    if (lane == 0) {
+      xinv[row] = a > 0.f ? is : -is;
+      if (xaug) {
+        const uint32_t aa = (uint32_t)__half_as_ushort(__float2half_rn(a));
+        *reinterpret_cast<uint4*>(xaug + row * 8) = make_uint4(aa | (aa << 16), aa, 0u, 0u);
+      }
+    }
     if (vec) {
 #pragma unroll
       for (int t = 0; t < 2; ++t) {
@@ -215,8 +266,10 @@ __global__ void prepare_latents_kernel(const T* __restrict__ x, int64_t rows, in
   }
 }
 
-int launch_prepare_latents(const void* x, int x_dtype, int64_t rows, int d, int dp,
-                           __half* xb, float* xinv, uint32_t* scal, cudaStream_t st) {
+int launch_prepare_latents(const void* x, int x_dtype, int64_t rows, int64_t rows_per_head, int d, int dp,
+                           const float* chdr, __half* xb, float* xinv, __half* xaug, uint32_t* scal,
+                           cudaStream_t st) {
+  if (rows_per_head < 1) rows_per_head = 1;
   VQB_REQUIRE(dp <= 512, VQB_ERR_UNSUPPORTED, "prepare_latents: d_pad %d > 512", dp);
   const int warps = 8;
   int64_t blocks = (rows + warps - 1) / warps;
@@ -229,12 +282,15 @@ int launch_prepare_latents(const void* x, int x_dtype, int64_t rows, int d, int 
   }
   if (blocks > (int64_t)sms * 8) blocks = (int64_t)sms * 8;     // persistent: rows strided over the grid
   if (blocks < 1) blocks = 1;
-  if ((d & 7) == 0 && d <= 256) {
+  if ((d & 7) == 0 && d <= 256 && (rows_per_head >= rows || (rows_per_head % 4 == 0 && rows < (1ll << 32)))) {
     VQB_DISPATCH_DTYPE(x_dtype, T,
-      prepare_latents4_kernel<T><<<(unsigned)blocks, warps * 32, 0, st>>>((const T*)x, rows, d, dp, xb, xinv, scal));
+      prepare_latents4_kernel<T><<<(unsigned)blocks, warps * 32, 0, st>>>((const T*)x, rows, rows_per_head,
+                                                                          rows_per_head >= rows, d, dp, chdr,
+                                                                          xb, xinv, xaug, scal));
   } else {
     VQB_DISPATCH_DTYPE(x_dtype, T,
-      prepare_latents_kernel<T><<<(unsigned)blocks, warps * 32, 0, st>>>((const T*)x, rows, d, dp, xb, xinv, scal));
+      prepare_latents_kernel<T><<<(unsigned)blocks, warps * 32, 0, st>>>((const T*)x, rows, rows_per_head, d, dp, chdr,
+                                                                         xb, xinv, xaug, scal));
   }
   VQB_LAUNCH_CHECK();
   return VQB_OK;
@@ -243,11 +299,13 @@ int launch_prepare_latents(const void* x, int x_dtype, int64_t rows, int d, int 
 // E_k = Xmax*|c_k - c~_k| + DXmax*|c_k| + accumulation slack;  bias_k = |c_k|^2/2 - E_k
 __global__ void make_bias_kernel(const float* __restrict__ cn2h, const float* __restrict__ cn,
                                  const float* __restrict__ dcn, int64_t total, int Kp, int K,
-                                 uint32_t* __restrict__ scal, float* __restrict__ bias, float* __restrict__ err) {
+                                 const float* __restrict__ hdr, uint32_t* __restrict__ scal,
+                                 float* __restrict__ bias, float* __restrict__ err) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   float e = 0.f;
   if (i < total) {
     const int k = (int)(i % Kp);
+    const float hmax = hdr[(i / Kp) * kHdrFloats + 3];
     if (k >= K) {
       bias[i] = kPadBias;
       err[i] = 0.f;
@@ -256,7 +314,9 @@ __global__ void make_bias_kernel(const float* __restrict__ cn2h, const float* __
       const float c = cn[i], h = cn2h[i];
       // products are exact in the tensor core (fp16 x fp16 = 22 bits, fits fp32); accumulation is fp32-ish:
       // allow 2^-16 of the largest possible |sum| plus the fp32 rounding of |c|^2/2.
-      e = xmax * dcn[i] + dxmax * c + 1.6e-5f * (xmax * c) + 2.4e-7f * h;
+      // (with the bias k-step |c|^2/2 goes through the same accumulator: same 2^-16 allowance, plus the
+      // representation error of its three fp16 pieces, < 2^-33 relative / 2^-37 of the largest bias)
+      e = xmax * dcn[i] + dxmax * c + 1.6e-5f * (xmax * c + h) + 1e-9f * hmax;
       e = e * 1.001f + 1e-30f;
       err[i] = e;
       bias[i] = h - e;
@@ -268,15 +328,53 @@ __global__ void make_bias_kernel(const float* __restrict__ cn2h, const float* __
   if ((threadIdx.x & 31) == 0 && e > 0.f) atomicMax(scal + 6, __float_as_uint(e));
 }
 
+// Bias operand of the codebook for this search: three fp16 pieces (33 bits) of b_k = s_c 2^q bias_k, +inf for padded
+// codes (they can never become candidates).  bias_k = |c_k|^2/2 - E_k (keys pre-lowered, window L_min + 2 E_j) whenever
+// every b_k is an fp16 number; otherwise (E_k far above max |c|^2/2) bias_k = |c_k|^2/2 and scal[8] = 1 tells resolve
+// to use the symmetric window min + 2 Emax.
+__global__ void make_bias_operand_kernel(const float* __restrict__ cn2h, const float* __restrict__ err,
+                                         const float* __restrict__ hdr, int64_t total, int Kp, int K,
+                                         uint32_t* __restrict__ scal, __half* __restrict__ caug) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int64_t h = i / Kp;
+  const int k = (int)(i - h * Kp);
+  const float* hd = hdr + h * kHdrFloats;
+  const float emax = __uint_as_float(scal[6]);
+  const float scq = hd[0] * hd[4];                       // s_c 2^q (power of two)
+  // per codebook; one head falling back switches resolve to the (always valid, wider) 2 Emax window for all heads
+  const bool lowered = (hd[3] + emax) * scq < 60000.f;
+  if (k == 0 && !lowered) scal[8] = 1u;
+  __half p[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) p[j] = __float2half(0.f);
+  if (k >= K) {
+    p[0] = __ushort_as_half((unsigned short)0x7C00);     // +inf
+  } else {
+    const float b = (lowered ? cn2h[i] - err[i] : cn2h[i]) * scq;
+    const __half b1 = __float2half_rn(b);
+    const float r1 = b - __half2float(b1);               // exact (Sterbenz)
+    const __half b2 = __float2half_rn(r1);
+    const __half b3 = __float2half_rn(r1 - __half2float(b2));
+    p[0] = b1; p[1] = b2; p[2] = b3;
+  }
+  *reinterpret_cast<uint4*>(caug + i * 8) = *reinterpret_cast<const uint4*>(p);
+}
+
 int launch_make_bias(const void* cache, const CacheLayout& CL, int64_t H, int K, int metric,
-                     uint32_t* scal, float* bias, float* err, cudaStream_t st) {
+                     uint32_t* scal, float* bias, float* err, __half* caug, cudaStream_t st) {
   (void)metric;
   const char* base = (const char*)cache;
   int64_t total = H * (int64_t)CL.Kp;
   make_bias_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
       (const float*)(base + CL.off_cn2h), (const float*)(base + CL.off_cn), (const float*)(base + CL.off_dcn),
-      total, CL.Kp, K, scal, bias, err);
+      total, CL.Kp, K, (const float*)(base + CL.off_hdr), scal, bias, err);
   VQB_LAUNCH_CHECK();
+  if (caug) {
+    make_bias_operand_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
+        (const float*)(base + CL.off_cn2h), err, (const float*)(base + CL.off_hdr), total, CL.Kp, K, scal, caug);
+    VQB_LAUNCH_CHECK();
+  }
   return VQB_OK;
 }
 
@@ -328,7 +426,7 @@ extern "C" int vqb_prepare_codebook(const float* codebook, int64_t H, int K, int
   char* base = (char*)cache;
   cudaStream_t st = (cudaStream_t)stream;
   float* hdr = (float*)(base + CL.off_hdr);
-  VQB_CUDA_TRY(cudaMemsetAsync(hdr, 0, (size_t)H * 16, st));
+  VQB_CUDA_TRY(cudaMemsetAsync(hdr, 0, (size_t)H * kHdrFloats * 4, st));
   const int64_t per_head = (int64_t)K * d;
   int gx = (int)((per_head + 256 * 8 - 1) / (256 * 8));
   if (gx > 1024) gx = 1024;
@@ -339,6 +437,8 @@ extern "C" int vqb_prepare_codebook(const float* codebook, int64_t H, int K, int
   prepare_codebook_kernel<<<(unsigned)((rows + warps - 1) / warps), warps * 32, 0, st>>>(
       codebook, H, K, CL.Kp, d, CL.dp, metric, hdr, (__half*)(base + CL.off_cb), (float*)(base + CL.off_cn2h),
       (float*)(base + CL.off_cn), (float*)(base + CL.off_dcn));
+  VQB_LAUNCH_CHECK();
+  codebook_aug_scale_kernel<<<(unsigned)((H + 63) / 64), 64, 0, st>>>(H, hdr);
   VQB_LAUNCH_CHECK();
   return VQB_OK;
 }

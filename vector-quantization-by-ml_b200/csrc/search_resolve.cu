@@ -80,8 +80,10 @@ struct RowCands {
   bool local_rescan;  // hazard (ii) somewhere
 };
 
+// emax > 0: the keys are NOT pre-lowered by E_k (no bias k-step, or E_k too large for the fp16 bias operand) and the
+// window is the symmetric min + 2 Emax for every code
 __device__ __forceinline__ void load_cands(const uint2* __restrict__ cand, int64_t gid, int K, int Kp, int64_t h,
-                                           const float* __restrict__ err, RowCands& R) {
+                                           const float* __restrict__ err, float emax, RowCands& R) {
   const uint4* c4 = reinterpret_cast<const uint4*>(cand + gid * kNumCand);
 #pragma unroll
   for (int i = 0; i < kNumCand / 2; ++i) {
@@ -97,7 +99,7 @@ __device__ __forceinline__ void load_cands(const uint2* __restrict__ cand, int64
     if (!valid) R.key[i] = __int_as_float(0x7f800000);
     if (valid && R.key[i] < m1) { m1 = R.key[i]; c1 = R.code[i]; }
   }
-  const float E1 = c1 >= 0 ? err[h * Kp + c1] : 0.f;
+  const float E1 = emax > 0.f ? emax : (c1 >= 0 ? err[h * Kp + c1] : 0.f);
   // 2 E_j, plus the 6 packed id bits (<= 2^-17 relative per key) and the bias fma rounding
   R.thr = m1 + 2.f * E1 + (fabsf(m1) + E1) * kPackSlack;
   R.c1 = c1;
@@ -122,13 +124,18 @@ __global__ void __launch_bounds__(256)
 resolve_classify_kernel(const uint2* __restrict__ cand, const float* __restrict__ err, int64_t H, int64_t N, int K,
                         int Kp, int64_t idx_offset, int want_score, int64_t* __restrict__ idx_out,
                         int* __restrict__ rr_list, int* __restrict__ flag_list, uint32_t* __restrict__ flag_cnt,
-                        unsigned long long* __restrict__ keys, uint32_t* __restrict__ scal) {
+                        unsigned long long* __restrict__ keys, uint32_t* __restrict__ scal,
+                        const float* __restrict__ xinv, const float* __restrict__ chdr, int aug) {
   const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   bool queue = false;
   if (gid < H * N) {
     const int64_t h = gid / N;
     RowCands R;
-    load_cands(cand, gid, K, Kp, h, err, R);
+    load_cands(cand, gid, K, Kp, h, err, (aug == 2 || scal[8]) ? __uint_as_float(scal[6]) : 0.f, R);
+    // no fp16 bias operand for this row (prepare.cu), or operands prepared by vqb_rvq_level against a cache that
+    // has been rebuilt with another 2^q since (scal[7] records the one used): rescan exactly
+    if (aug && (xinv[gid] < 0.f || (scal[7] != 0u && scal[7] != __float_as_uint(chdr[h * kHdrFloats + 4]))))
+      R.full_rescan = true;
     if (R.full_rescan) {
       const uint32_t pos = atomicAdd(flag_cnt + h, 1u);
       flag_list[h * N + pos] = (int)(gid - h * N);
@@ -157,7 +164,7 @@ __global__ void __launch_bounds__(256)
 resolve_rerank_kernel(const T* __restrict__ x, const float* __restrict__ cb, const uint2* __restrict__ cand,
                       const float* __restrict__ err, int64_t N, int K, int Kp, int d, int metric,
                       int64_t idx_offset, int64_t* __restrict__ idx_out, float* __restrict__ score_out,
-                      const int* __restrict__ rr_list, const uint32_t* __restrict__ scal) {
+                      const int* __restrict__ rr_list, const uint32_t* __restrict__ scal, int aug) {
   const int lane = threadIdx.x & 31;
   const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
   const int64_t count = scal[3];
@@ -180,7 +187,7 @@ resolve_rerank_kernel(const T* __restrict__ x, const float* __restrict__ cb, con
       const int oc = __shfl_xor_sync(0xffffffffu, c1, o);
       if (om < m1 || (om == m1 && oc > c1)) { m1 = om; c1 = oc; }   // any consistent tie rule: only E(c1) is used
     }
-    const float E1 = c1 >= 0 ? err[h * Kp + c1] : 0.f;
+    const float E1 = (aug == 2 || scal[8]) ? __uint_as_float(scal[6]) : (c1 >= 0 ? err[h * Kp + c1] : 0.f);
     const float thr = m1 + 2.f * E1 + (fabsf(m1) + E1) * kPackSlack;
 
     const T* xr = x + gid * (int64_t)d;
@@ -394,8 +401,12 @@ extern "C" int vqb_search(const void* x, int x_dtype, const float* codebook, con
   const bool prepared = (flags & VQB_SEARCH_LATENTS_PREPARED) != 0;
   const bool tc = !(flags & VQB_SEARCH_FORCE_EXACT) && SL.dp <= 512 && cache != nullptr;
   // scal[0..1] hold the row statistics: keep them when the caller prepared the latents
-  const size_t zoff = prepared ? 8 : 0;
-  VQB_CUDA_TRY(cudaMemsetAsync((char*)scal + zoff, 0, (SL.off_cnt - SL.off_scal) + (size_t)H * 4 - zoff, st));
+  if (prepared) {   // keep [0..1] (row statistics) and [7] (2^q of the prepared bias operands)
+    VQB_CUDA_TRY(cudaMemsetAsync((char*)scal + 8, 0, 20, st));
+    VQB_CUDA_TRY(cudaMemsetAsync((char*)scal + 32, 0, (SL.off_cnt - SL.off_scal) + (size_t)H * 4 - 32, st));
+  } else {
+    VQB_CUDA_TRY(cudaMemsetAsync((char*)scal, 0, (SL.off_cnt - SL.off_scal) + (size_t)H * 4, st));
+  }
 
   const int grid_scan = (int)((N + kER - 1) / kER < 4 * (int64_t)num_sms() ? (N + kER - 1) / kER : 4 * num_sms());
   if (!tc) {
@@ -414,20 +425,24 @@ extern "C" int vqb_search(const void* x, int x_dtype, const float* codebook, con
   float* bias = (float*)(w + SL.off_bias);
   float* err = (float*)(w + SL.off_err);
   int rc;
+  __half* xaug = (__half*)(w + SL.off_xaug);
+  const float* chdr = (const float*)(cbase + CL.off_hdr);
   if (!prepared) {
-    rc = launch_prepare_latents(x, x_dtype, H * N, d, SL.dp, xb, xinv, scal, st);
+    rc = launch_prepare_latents(x, x_dtype, H * N, N, d, SL.dp, chdr, xb, xinv, xaug, scal, st);
     if (rc) return rc;
   }
-  rc = launch_make_bias(cache, CL, H, K, metric, scal, bias, err, st);
+  const int aug = search_tc_aug_mode(N, K, metric);
+  __half* caug = (__half*)(w + SL.off_caug);
+  rc = launch_make_bias(cache, CL, H, K, metric, scal, bias, err, aug == 1 ? caug : nullptr, st);
   if (rc) return rc;
-  rc = launch_search_tc(xb, xinv, (const __half*)(cbase + CL.off_cb), (const float*)(cbase + CL.off_hdr), bias, H, N, K,
-                        SL.dp, w + SL.off_cand, scal, (flags & VQB_SEARCH_TIMING) != 0, st);
+  rc = launch_search_tc(xb, xinv, xaug, (const __half*)(cbase + CL.off_cb), caug, chdr,
+                        bias, aug, H, N, K, SL.dp, w + SL.off_cand, scal, (flags & VQB_SEARCH_TIMING) != 0, st);
   if (rc) return rc;
   const int64_t total = H * N;
   int* rr_list = (int*)(w + SL.off_rr);
   resolve_classify_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
       (const uint2*)(w + SL.off_cand), err, H, N, K, CL.Kp, idx_offset, score_out != nullptr, idx_out, rr_list,
-      flag_list, cnt, keys, scal);
+      flag_list, cnt, keys, scal, xinv, chdr, aug);
   VQB_LAUNCH_CHECK();
   {
     int64_t want = score_out ? (total + 7) / 8 : (total / 16 + 7) / 8 + 1;   // blocks of 8 warps
@@ -436,7 +451,7 @@ extern "C" int vqb_search(const void* x, int x_dtype, const float* codebook, con
     VQB_DISPATCH_DTYPE(x_dtype, T,
       resolve_rerank_kernel<T><<<grid_rr, 256, 0, st>>>(
           (const T*)x, codebook, (const uint2*)(w + SL.off_cand), err, N, K, CL.Kp, d, metric, idx_offset, idx_out,
-          score_out, rr_list, scal));
+          score_out, rr_list, scal, aug));
     VQB_LAUNCH_CHECK();
   }
   // flagged rows (count is device-side): fixed grid, code range split over blockIdx.z so that even a handful of

@@ -235,8 +235,14 @@ __device__ __forceinline__ float pack_id(float v, uint32_t mask) {
 //            skipped.
 template <int MODE>
 __device__ __forceinline__ float chunk_scores(const uint32_t (&r)[16], const float4* bias4, float ninv,
-                                              float (&key)[16]) {
-  tmem_ld_wait();
+                                              float (&key)[16], bool prof, unsigned long long& w_ld) {
+  if (MODE == 1 && prof) {
+    const long long t0 = clock64();
+    tmem_ld_wait();
+    w_ld += (unsigned long long)(clock64() - t0);
+  } else {
+    tmem_ld_wait();
+  }
   if (MODE == 2) {   // timing experiment: what the epilogue costs when the accumulator already IS the key
 #pragma unroll
     for (int i = 0; i < 16; ++i) key[i] = __uint_as_float(r[i]);
@@ -580,7 +586,7 @@ search_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     // Emax * (2 + slack): the part of the candidate threshold that does not depend on the row minimum
     const float tconst = __uint_as_float(P.scal[6]) * (2.f + kPackSlackTC);
     const bool prof = MODE == 1 && (P.dbg & 32) != 0 && warp == 0;
-    unsigned long long w_tf = 0, w_bias = 0;
+    unsigned long long w_tf = 0, w_bias = 0, w_ld = 0, w_try = 0;
     const long long t_begin = clock64();
     uint32_t r[16];
     uint32_t tile_it = 0;                           // row tiles processed by this CTA so far
@@ -597,8 +603,8 @@ search_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
       int C1[2], C2[2], C3[2];
 #pragma unroll
       for (int c = 0; c < 2; ++c) { M1[c] = INF; M2[c] = INF; M3[c] = INF; C1[c] = -1; C2[c] = -1; C3[c] = -1; }
-      // acc = (x s_row).(c s_c)  ->  score = bias - acc / (s_row s_c): one FFMA per element
-      const float ninv = row < P.N ? -(P.xinv[(size_t)h * P.N + row] * P.chdr[h * 4 + 1]) : 0.f;
+      // acc = (x s_row).(-c s_c)  ->  score = bias + acc / (s_row s_c): one FFMA per element
+      const float ninv = row < P.N ? fabsf(P.xinv[(size_t)h * P.N + row]) * P.chdr[h * kHdrFloats + 1] : 0.f;
       // the id mask lives in a register so that "(bits & mask) | id" is a single LOP3 (opaque to constant folding)
       uint32_t idmask;
       asm volatile("mov.u32 %0, 0xFFFFFFC0;" : "=r"(idmask));
@@ -629,7 +635,7 @@ search_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
             float key[16];
             float cmin;
 #define VQB_CHUNK(CH)                                                                                      \
-            cmin = chunk_scores<MODE>(r, bias4 + (CH) * 4, ninv, key);                                     \
+            cmin = chunk_scores<MODE>(r, bias4 + (CH) * 4, ninv, key, prof, w_ld);                                   \
             TMEM_LD16(taddr + ((CH) + 1) * 16, r);                                                         \
             if (par == 0) chunk_rank<0, (CH), MODE>(key, cmin, idmask, tconst, m_run, t_run, row_slot, a1, a2, any_slow, P.dbg); \
             else chunk_rank<1, (CH), MODE>(key, cmin, idmask, tconst, m_run, t_run, row_slot, a1, a2, any_slow, P.dbg);
@@ -638,7 +644,7 @@ search_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
             // last chunk: once its scores are formed every TMEM read of this tile is complete -> hand the buffer
             // back to the MMA warp, then start loading the next tile's first chunk (before this chunk's ranking
             // work if that accumulator is already complete)
-            cmin = chunk_scores<MODE>(r, bias4 + 12, ninv, key);
+            cmin = chunk_scores<MODE>(r, bias4 + 12, ninv, key, prof, w_ld);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
@@ -652,11 +658,13 @@ search_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
             if (++acc == 2) { acc = 0; acc_ph ^= 1u; }
             const bool more = (nt + par + 1 < P.NT) || (g + num_clusters < G);
             bool issued = false;
+            const long long t_try = (MODE == 1 && prof) ? clock64() : 0;
             if (more && mbar_try(smem_u32(&bars->tmem_full[acc]), acc_ph)) {
               tc_fence_after();
               TMEM_LD16(lane_addr + acc * (uint32_t)kBlockN, r);
               issued = true;
             }
+            if (MODE == 1 && prof) w_try += (unsigned long long)(clock64() - t_try);
             if (par == 0) chunk_rank<0, 3, MODE>(key, cmin, idmask, tconst, m_run, t_run, row_slot, a1, a2, any_slow, P.dbg);
             else chunk_rank<1, 3, MODE>(key, cmin, idmask, tconst, m_run, t_run, row_slot, a1, a2, any_slow, P.dbg);
             if (more && !issued) {
@@ -692,6 +700,8 @@ search_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
       atomicAdd(g_dbg_cycles + 7, (unsigned long long)(clock64() - t_begin));
       atomicAdd(g_dbg_cycles + 8, w_tf);
       atomicAdd(g_dbg_cycles + 9, w_bias);
+      atomicAdd(g_dbg_cycles + 10, w_ld);
+      atomicAdd(g_dbg_cycles + 11, w_try);
     }
   }
 
@@ -702,6 +712,306 @@ search_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
     else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
   }
+}
+
+// ------------------------------------------------------------------------------------------
+// Bias in the MMA ("aug") variant, cta_group::2 only.
+// The codebook operand is stored negated and every N tile gets ONE extra k-step whose operands are
+//   A: {a, a, a, 0...} per row, a = s_row 2^-q          (fp16, written by prepare_latents)
+//   B: {b1, b2, b3, 0...} per code, b1+b2+b3 = s_c 2^q |c_k|^2/2 to 33 bits (codebook cache; +inf for padded codes)
+// so the fp32 accumulator IS the score times the positive row constant s_row s_c:
+//   acc = s_row s_c (|c_k|^2/2 - x~.c~_k).
+// The epilogue is then a pure packed min over raw accumulators: no FFMA, no bias in shared memory, no stager warp.
+// Thresholds are applied in the row's scaled units; keys are unscaled once, when the 24 candidates are written.
+// The bound |exact - key| <= E_k is symmetric here (the key is not pre-lowered by E_k), so the candidate window
+// is min + 2 Emax: resolve uses Emax for every code (search_resolve.cu).
+// Operand plumbing: the two 16-byte-per-row aug chunks use the no-swizzle K-major canonical layout (8-row core
+// matrices of 128 B, SBO = 128 B); the second k-chunk (k = 8..15) of both operands is one shared block of zeros
+// addressed through LBO.  The aug chunk of B rides in a 2 KB tail of every B stage and completes on the stage's
+// barrier with the last k-block; the aug chunk of A completes on the last slab's barrier: no extra barriers.
+// ------------------------------------------------------------------------------------------
+constexpr int kAugChunkBytes = kBlockM * 16;                 // 128 rows x 8 fp16
+constexpr int kStageStrideAug = kStageBytes / 2 + kAugChunkBytes;
+
+__device__ __forceinline__ uint64_t make_nosw_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46);
+}
+
+struct AugParams {
+  const float* xinv;   // [H][N]   +-1 / s_row
+  const float* chdr;   // [H][kHdrFloats]
+  void* cand;
+  uint32_t* scal;
+  int64_t N;
+  int Kp, H, KB, NT, S, GPH;
+  int aug;             // 0: dot metric with K % 256 == 0 -- no bias k-step at all
+};
+
+struct AugBarriers {
+  uint64_t full[kMaxStages];
+  uint64_t empty[kMaxStages];
+  uint64_t a_full[kMaxKB];
+  uint64_t a_empty[kMaxKB];
+  uint64_t tmem_full[2];
+  uint64_t tmem_empty[2];
+  uint32_t tmem_base;
+  uint32_t pad;
+  int rowmin[3][kBlockM];     // see Barriers::rowmin
+};
+
+__device__ __forceinline__ float chunk_min16(const uint32_t (&r)[16]) {
+  tmem_ld_wait();
+  float cm[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+    cm[c] = fminf(min3f(__uint_as_float(r[c]), __uint_as_float(r[4 + c]), __uint_as_float(r[8 + c])),
+                  __uint_as_float(r[12 + c]));
+  return fminf(min3f(cm[0], cm[1], cm[2]), cm[3]);
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+search_aug_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_c,
+                  const __grid_constant__ CUtensorMap map_xa, const __grid_constant__ CUtensorMap map_ca,
+                  const AugParams P) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t a_base = smem_base;
+  const uint32_t b_base = smem_base + (uint32_t)P.KB * kSlabBytes;
+  const uint32_t xa_base = b_base + (uint32_t)P.S * kStageStrideAug;       // A aug chunk (2 KB)
+  const uint32_t zero_base = xa_base + kAugChunkBytes;                     // shared zero k-chunk (2 KB)
+  AugBarriers* bars = reinterpret_cast<AugBarriers*>(smem + (size_t)P.KB * kSlabBytes + (size_t)P.S * kStageStrideAug +
+                                                     2 * kAugChunkBytes);
+  const uint32_t rank = cluster_ctarank();
+  const int cid = blockIdx.x / 2;
+  const int num_clusters = gridDim.x / 2;
+  const int G = P.H * P.GPH;
+  const bool aug = P.aug != 0;
+
+  if (threadIdx.x == 0 && (smem_base & 1023u)) atomicExch(P.scal + 5, 1u);
+  if (blockIdx.x == 0 && threadIdx.x == 0) P.scal[4] = 1u;
+  if (warp == kWarpTma && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_c) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_xa) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_ca) : "memory");
+  }
+  if (warp == kWarpMma && lane == 0) {
+    for (int i = 0; i < P.S; ++i) {
+      mbar_init(smem_u32(&bars->full[i]), 1);
+      mbar_init(smem_u32(&bars->empty[i]), 1);
+    }
+    for (int i = 0; i < P.KB; ++i) {
+      mbar_init(smem_u32(&bars->a_full[i]), 1);
+      mbar_init(smem_u32(&bars->a_empty[i]), 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&bars->tmem_full[i]), 1);
+      mbar_init(smem_u32(&bars->tmem_empty[i]), 2 * kNumEpiWarps);
+    }
+    fence_barrier_init();
+  }
+  if (threadIdx.x < 3 * kBlockM) (&bars->rowmin[0][0])[threadIdx.x] = 0x7fffffff;
+  if (warp == kWarpStager) {   // the zero k-chunk, read by the tensor core (async proxy)
+    for (int i = lane; i < kAugChunkBytes / 16; i += 32)
+      reinterpret_cast<uint4*>(smem + (zero_base - smem_base))[i] = make_uint4(0u, 0u, 0u, 0u);
+    fence_proxy_async();
+  }
+  if (warp == kWarpAlloc) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;"
+                 ::"r"(smem_u32(&bars->tmem_base)), "n"(kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  if (warp == kWarpTma) {
+    // =============================== TMA producer ===============================
+    uint32_t stage = 0, ph = 0, a_ph = 0;
+    for (int g = cid; g < G; g += num_clusters) {
+      const int h = g / P.GPH;
+      const int mt = (g - h * P.GPH) * 2 + (int)rank;
+      const int row0 = mt * kBlockM;
+      for (int nt = 0; nt < P.NT; ++nt) {
+        for (int kb = 0; kb < P.KB; ++kb) {
+          const bool last = kb == P.KB - 1;
+          if (nt == 0) {
+            mbar_wait(smem_u32(&bars->a_empty[kb]), a_ph ^ 1u);
+            if (elect_one()) {
+              const uint32_t bar = smem_u32(&bars->a_full[kb]);
+              if (rank == 0) mbar_expect_tx(bar, 2 * kSlabBytes + (last && aug ? 2 * kAugChunkBytes : 0));
+              tma_load_3d_pair(a_base + kb * kSlabBytes, &map_x, bar & kPeerBitMask, kb * kBlockK, row0, h, kEvictFirst);
+              if (last && aug) tma_load_3d_pair(xa_base, &map_xa, bar & kPeerBitMask, 0, row0, h, kEvictFirst);
+            }
+            __syncwarp();
+          }
+          mbar_wait(smem_u32(&bars->empty[stage]), ph ^ 1u);
+          if (elect_one()) {
+            const uint32_t bar = smem_u32(&bars->full[stage]);
+            if (rank == 0) mbar_expect_tx(bar, kStageBytes + (last && aug ? 2 * kAugChunkBytes : 0));
+            const uint32_t dst = b_base + stage * kStageStrideAug;
+            const int code0 = nt * kBlockN + (int)rank * (kBlockN / 2);
+            tma_load_3d_pair(dst, &map_c, bar & kPeerBitMask, kb * kBlockK, code0, h, kEvictLast);
+            if (last && aug) tma_load_3d_pair(dst + kStageBytes / 2, &map_ca, bar & kPeerBitMask, 0, code0, h, kEvictLast);
+          }
+          __syncwarp();
+          if (++stage == (uint32_t)P.S) { stage = 0; ph ^= 1u; }
+        }
+      }
+      a_ph ^= 1u;
+    }
+  } else if (warp == kWarpMma) {
+    // =============================== MMA issuer (leader CTA) ===============================
+    if (rank == 0) {
+      uint32_t stage = 0, ph = 0, a_ph = 0, acc = 0, acc_ph = 0;
+      for (int g = cid; g < G; g += num_clusters) {
+        for (int nt = 0; nt < P.NT; ++nt) {
+          mbar_wait(smem_u32(&bars->tmem_empty[acc]), acc_ph ^ 1u);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + acc * (uint32_t)kBlockN;
+          for (int kb = 0; kb < P.KB; ++kb) {
+            if (nt == 0) mbar_wait(smem_u32(&bars->a_full[kb]), a_ph);
+            mbar_wait(smem_u32(&bars->full[stage]), ph);
+            tc_fence_after();
+            if (elect_one()) {
+              const uint32_t b_addr = b_base + stage * kStageStrideAug;
+              const uint64_t adesc = make_sw128_desc(a_base + kb * kSlabBytes);
+              const uint64_t bdesc = make_sw128_desc(b_addr);
+#pragma unroll
+              for (int kk = 0; kk < kBlockK / 16; ++kk)
+                umma_f16_pair(d_tmem, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), kIdescPair,
+                              (kb | kk) != 0 ? 1u : 0u);
+              if (kb == P.KB - 1 && aug) {        // + a (b1 + b2 + b3) = s_row s_c |c|^2/2
+                const uint32_t ca = b_addr + kStageBytes / 2;
+                umma_f16_pair(d_tmem, make_nosw_desc(xa_base, zero_base - xa_base, 128),
+                              make_nosw_desc(ca, zero_base - ca, 128), kIdescPair, 1u);
+              }
+              umma_commit_pair(smem_u32(&bars->empty[stage]));
+              if (nt == P.NT - 1) umma_commit_pair(smem_u32(&bars->a_empty[kb]));
+              if (kb == P.KB - 1) umma_commit_pair(smem_u32(&bars->tmem_full[acc]));
+            }
+            __syncwarp();
+            if (++stage == (uint32_t)P.S) { stage = 0; ph ^= 1u; }
+          }
+          if (++acc == 2) { acc = 0; acc_ph ^= 1u; }
+        }
+        a_ph ^= 1u;
+      }
+    }
+  } else if (warp < kNumEpiWarps) {
+    // =============================== epilogue: packed running top-2 on raw accumulators ===============================
+    const int q = warp & 3;
+    const int quarter = warp >> 2;
+    uint32_t acc = 0, acc_ph = 0;
+    const float INF = __int_as_float(0x7f800000);
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + quarter * 64;
+    const float tconst = __uint_as_float(P.scal[6]) * (2.f + kPackSlackTC);
+    uint32_t rA[16], rB[16];
+    uint32_t tile_it = 0;
+    if (cid < G) {
+      mbar_wait(smem_u32(&bars->tmem_full[0]), 0);
+      tc_fence_after();
+      TMEM_LD16(lane_addr, rA);
+    }
+    for (int g = cid; g < G; g += num_clusters) {
+      const int h = g / P.GPH;
+      const int mt = (g - h * P.GPH) * 2 + (int)rank;
+      const int64_t row = (int64_t)mt * kBlockM + q * 32 + lane;
+      float M1[2], M2[2], M3[2];
+      int C1[2], C2[2], C3[2];
+#pragma unroll
+      for (int c = 0; c < 2; ++c) { M1[c] = INF; M2[c] = INF; M3[c] = INF; C1[c] = -1; C2[c] = -1; C3[c] = -1; }
+      // key = s_row s_c score: inv undoes it (exact, powers of two); thresholds live in the scaled units
+      const float inv = row < P.N ? fabsf(P.xinv[(size_t)h * P.N + row]) * P.chdr[h * kHdrFloats + 1] : 0.f;
+      const float trow = inv > 0.f ? tconst / inv : 0.f;
+      uint32_t idmask;
+      asm volatile("mov.u32 %0, 0xFFFFFFC0;" : "=r"(idmask));
+      float m_run = INF, t_run = INF;
+      int* row_slot = nullptr;
+      if (P.NT >= 4) {
+        bars->rowmin[(tile_it + 1) % 3][q * 32 + lane] = 0x7fffffff;
+        row_slot = &bars->rowmin[tile_it % 3][q * 32 + lane];
+      }
+      ++tile_it;
+      for (int nt = 0; nt < P.NT; nt += 2) {
+        if (row_slot) {
+          const float gmin = ord2f(*reinterpret_cast<volatile int*>(row_slot));
+          t_run = fminf(t_run, fmaf(fabsf(gmin), kPackSlackTC, gmin) + trow);
+        }
+        float a1[2], a2[2];
+#pragma unroll
+        for (int c = 0; c < 2; ++c) { a1[c] = INF; a2[c] = INF; }
+        bool any_slow = false;
+#pragma unroll
+        for (int par = 0; par < 2; ++par) {
+          if (nt + par < P.NT) {
+            const uint32_t taddr = lane_addr + acc * (uint32_t)kBlockN;
+            float cmin;
+            // the accumulator registers ARE the keys: two register sets alternate so that the next chunk's
+            // tcgen05.ld is in flight while this chunk is ranked
+#define VQB_AUG_CHUNK(CH, RCUR, RNEXT)                                                                      \
+            cmin = chunk_min16(RCUR);                                                                       \
+            TMEM_LD16(taddr + ((CH) + 1) * 16, RNEXT);                                                      \
+            if (par == 0) chunk_rank<0, (CH), 0>(reinterpret_cast<float(&)[16]>(RCUR), cmin, idmask, trow, m_run, \
+                                                 t_run, row_slot, a1, a2, any_slow, 0);                     \
+            else chunk_rank<1, (CH), 0>(reinterpret_cast<float(&)[16]>(RCUR), cmin, idmask, trow, m_run, t_run,  \
+                                        row_slot, a1, a2, any_slow, 0);
+            VQB_AUG_CHUNK(0, rA, rB) VQB_AUG_CHUNK(1, rB, rA) VQB_AUG_CHUNK(2, rA, rB)
+#undef VQB_AUG_CHUNK
+            cmin = chunk_min16(rB);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_leader(smem_u32(&bars->tmem_empty[acc]));
+            if (++acc == 2) { acc = 0; acc_ph ^= 1u; }
+            const bool more = (nt + par + 1 < P.NT) || (g + num_clusters < G);
+            bool issued = false;
+            if (more && mbar_try(smem_u32(&bars->tmem_full[acc]), acc_ph)) {
+              tc_fence_after();
+              TMEM_LD16(lane_addr + acc * (uint32_t)kBlockN, rA);
+              issued = true;
+            }
+            if (par == 0) chunk_rank<0, 3, 0>(reinterpret_cast<float(&)[16]>(rB), cmin, idmask, trow, m_run, t_run,
+                                              row_slot, a1, a2, any_slow, 0);
+            else chunk_rank<1, 3, 0>(reinterpret_cast<float(&)[16]>(rB), cmin, idmask, trow, m_run, t_run, row_slot,
+                                     a1, a2, any_slow, 0);
+            if (more && !issued) {
+              mbar_wait(smem_u32(&bars->tmem_full[acc]), acc_ph);
+              tc_fence_after();
+              TMEM_LD16(lane_addr + acc * (uint32_t)kBlockN, rA);
+            }
+          }
+        }
+        if (!any_slow) continue;
+        const int col0 = nt * kBlockN + quarter * 64;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const uint32_t i1 = __float_as_uint(a1[c]) & 63u, i2 = __float_as_uint(a2[c]) & 63u;
+          top3_insert(M1[c], M2[c], M3[c], C1[c], C2[c], C3[c], a1[c],
+                      col0 + (int)(i1 >> 5) * kBlockN + (int)((i1 & 31u) << 1) + c);
+          top3_insert(M1[c], M2[c], M3[c], C1[c], C2[c], C3[c], a2[c],
+                      col0 + (int)(i2 >> 5) * kBlockN + (int)((i2 & 31u) << 1) + c);
+        }
+      }
+      if (row < P.N) {
+        uint4* out4 = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(P.cand) +
+                                               (((size_t)h * P.N + row) * kNumCand + quarter * (kNumCand / 4)) * 8);
+#pragma unroll
+        for (int c = 0; c < 2; ++c) { M1[c] *= inv; M2[c] *= inv; M3[c] *= inv; }   // inf stays inf
+        out4[0] = make_uint4(__float_as_uint(M1[0]), (uint32_t)C1[0], __float_as_uint(M2[0]), (uint32_t)C2[0]);
+        out4[1] = make_uint4(__float_as_uint(M3[0]), (uint32_t)C3[0], __float_as_uint(M1[1]), (uint32_t)C1[1]);
+        out4[2] = make_uint4(__float_as_uint(M2[1]), (uint32_t)C2[1], __float_as_uint(M3[1]), (uint32_t)C3[1]);
+      }
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == kWarpAlloc)
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
 }
 
 // ------------------------------------------------------------------------------------------
@@ -723,16 +1033,20 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// 3-D fp16 tensor (inner, rows, heads), box (64, box_rows, 1), 128B swizzle, OOB rows read as zero
-static int make_map(CUtensorMap* m, const void* base, int inner, int64_t rows, int64_t heads, int box_rows) {
+// 3-D fp16 tensor (inner, rows, heads), box (box_inner, box_rows, 1), OOB rows read as zero;
+// 128B swizzle for the 64-wide operand tiles, none for the 8-wide bias chunks
+static int make_map(CUtensorMap* m, const void* base, int inner, int64_t rows, int64_t heads, int box_rows,
+                    int box_inner = kBlockK) {
   EncodeTiledFn enc = get_encode_fn();
   VQB_REQUIRE(enc != nullptr, VQB_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
   cuuint64_t dims[3] = {(cuuint64_t)inner, (cuuint64_t)rows, (cuuint64_t)heads};
   cuuint64_t strides[2] = {(cuuint64_t)inner * 2, (cuuint64_t)inner * 2 * (cuuint64_t)rows};
-  cuuint32_t box[3] = {(cuuint32_t)kBlockK, (cuuint32_t)box_rows, 1};
+  cuuint32_t box[3] = {(cuuint32_t)box_inner, (cuuint32_t)box_rows, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   box_inner == kBlockK ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   VQB_REQUIRE(r == CUDA_SUCCESS, VQB_ERR_CUDA, "cuTensorMapEncodeTiled failed: %d (inner=%d rows=%lld heads=%lld)",
               (int)r, inner, (long long)rows, (long long)heads);
@@ -791,9 +1105,111 @@ static int launch_impl(const CUtensorMap& mx, const CUtensorMap& mc, const Searc
   return VQB_OK;
 }
 
-int launch_search_tc(const __half* xb, const float* xinv, const __half* cb, const float* chdr, const float* bias,
-                     int64_t H, int64_t N, int K, int dp, void* cand, uint32_t* scal, bool timing, cudaStream_t st) {
+static int aug_env() {   // env VQB_AUG=0: bias added in the epilogue (the first version of the kernel), for A/B runs
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("VQB_AUG"); v = e ? atoi(e) : 1; }
+  return v;
+}
+static int mode_env() {
+  if (g_cluster_override < 0) {
+    const char* e = getenv("VQB_CLUSTER");
+    g_cluster_override = e ? atoi(e) : 0;
+  }
+  return g_cluster_override;
+}
+static int dbg_env() {
+  static int dbg = -1;
+  if (dbg < 0) { const char* e = getenv("VQB_TC_DEBUG"); dbg = e ? atoi(e) : 0; }
+  return dbg;
+}
+
+// the bias k-step needs the pair kernel (>= 2 row tiles) and no bring-up knob / alternate mode requested
+// returns 0: bias in the epilogue (first kernel); 1: bias k-step; 2: no bias at all (dot metric, no padded codes)
+int search_tc_aug_mode(int64_t N, int K, int metric) {
+  const int mode = mode_env();
+  if (aug_env() == 0 || dbg_env() != 0 || (mode >= 1 && mode <= 2) || (N + kBlockM - 1) / kBlockM < 2) return 0;
+  return (metric == VQB_DOT && K % kBlockN == 0) ? 2 : 1;
+}
+
+static int launch_aug(const __half* xb, const float* xinv, const __half* xaug, const __half* cb, const __half* caug,
+                      const float* chdr, int64_t H, int64_t N, int K, int dp, int aug_on, void* cand, uint32_t* scal,
+                      bool timing, cudaStream_t st) {
   const int Kp = k_pad(K);
+  static int num_sms = 0;
+  int dev = 0;
+  VQB_CUDA_TRY(cudaGetDevice(&dev));
+  if (!num_sms) VQB_CUDA_TRY(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  static bool configured[64] = {};
+  if (dev < 0 || dev >= 64 || !configured[dev]) {
+    VQB_CUDA_TRY(cudaFuncSetAttribute(search_aug_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    if (dev >= 0 && dev < 64) configured[dev] = true;
+  }
+  AugParams P;
+  P.xinv = xinv; P.chdr = chdr; P.cand = cand; P.scal = scal; P.N = N; P.Kp = Kp; P.H = (int)H;
+  P.KB = dp / kBlockK;
+  P.NT = Kp / kBlockN;
+  P.aug = aug_on;
+  const size_t fixed = (size_t)P.KB * kSlabBytes + 2 * kAugChunkBytes + sizeof(AugBarriers);
+  int S = (int)((227 * 1024 - fixed) / kStageStrideAug);
+  if (S > kMaxStages) S = kMaxStages;
+  VQB_REQUIRE(S >= 2, VQB_ERR_UNSUPPORTED, "not enough shared memory for d_pad=%d", dp);
+  P.S = S;
+  const int MT = (int)((N + kBlockM - 1) / kBlockM);
+  P.GPH = (MT + 1) / 2;
+  const size_t smem_bytes = fixed + (size_t)S * kStageStrideAug;
+  const int G = (int)H * P.GPH;
+  int nclusters = num_sms / 2;
+  if (nclusters > G) nclusters = G;
+  CUtensorMap mx, mc, mxa, mca;
+  int rc = make_map(&mx, xb, dp, N, H, kBlockM);
+  if (rc) return rc;
+  rc = make_map(&mc, cb, dp, Kp, H, kBlockN / 2);
+  if (rc) return rc;
+  rc = make_map(&mxa, xaug, 8, N, H, kBlockM, 8);
+  if (rc) return rc;
+  rc = make_map(&mca, caug, 8, Kp, H, kBlockN / 2, 8);
+  if (rc) return rc;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(nclusters * 2));
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem_bytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int slot = -1;
+  if (timing && (g_ev_dev < 0 || g_ev_dev == dev)) {
+    if (!g_ev_made) {
+      g_ev_dev = dev;
+      for (int i = 0; i < kTimingSlots; ++i) {
+        VQB_CUDA_TRY(cudaEventCreate(&g_ev0[i]));
+        VQB_CUDA_TRY(cudaEventCreate(&g_ev1[i]));
+      }
+      g_ev_made = true;
+    }
+    if (g_ev_count < kTimingSlots) slot = g_ev_count++;
+  }
+  if (slot >= 0) VQB_CUDA_TRY(cudaEventRecord(g_ev0[slot], st));
+  VQB_CUDA_TRY(cudaLaunchKernelEx(&cfg, search_aug_kernel, mx, mc, mxa, mca, P));
+  ++g_launch_count;
+  if (slot >= 0) VQB_CUDA_TRY(cudaEventRecord(g_ev1[slot], st));
+  return VQB_OK;
+}
+
+int launch_search_tc(const __half* xb, const float* xinv, const __half* xaug, const __half* cb, const __half* caug,
+                     const float* chdr, const float* bias, int aug_mode, int64_t H, int64_t N, int K, int dp,
+                     void* cand, uint32_t* scal, bool timing, cudaStream_t st) {
+  const int Kp = k_pad(K);
+  if (aug_mode) {
+    VQB_REQUIRE(xaug && caug, VQB_ERR_INVALID, "search: bias operands missing");
+    VQB_REQUIRE(dp % kBlockK == 0 && dp / kBlockK <= kMaxKB, VQB_ERR_UNSUPPORTED, "d_pad %d unsupported by the TC path", dp);
+    VQB_REQUIRE(N < (1ll << 31) - kBlockM, VQB_ERR_UNSUPPORTED, "N too large for TMA coordinates");
+    return launch_aug(xb, xinv, xaug, cb, caug, chdr, H, N, K, dp, aug_mode == 1 ? 1 : 0, cand, scal, timing, st);
+  }
   VQB_REQUIRE(dp % kBlockK == 0 && dp / kBlockK <= kMaxKB, VQB_ERR_UNSUPPORTED, "d_pad %d unsupported by the TC path", dp);
   VQB_REQUIRE(N < (1ll << 31) - kBlockM, VQB_ERR_UNSUPPORTED, "N too large for TMA coordinates");
   static int num_sms = 0;
@@ -802,10 +1218,7 @@ int launch_search_tc(const __half* xb, const float* xinv, const __half* cb, cons
     VQB_CUDA_TRY(cudaGetDevice(&dev));
     VQB_CUDA_TRY(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
-  if (g_cluster_override < 0) {
-    const char* e = getenv("VQB_CLUSTER");
-    g_cluster_override = e ? atoi(e) : 0;
-  }
+  mode_env();
   const int MT = (int)((N + kBlockM - 1) / kBlockM);
   // VQB_CLUSTER: 1 = independent CTAs, 2 = 2-CTA TMA multicast of B (measured: not faster, L2 is not the limiter),
   // 3 = cta_group::2 pair MMA (each CTA holds half of B).  Default: see below.
@@ -816,11 +1229,7 @@ int launch_search_tc(const __half* xb, const float* xinv, const __half* cb, cons
 
   SearchParams P;
   P.bias = bias; P.xinv = xinv; P.chdr = chdr; P.cand = cand; P.scal = scal; P.N = N; P.Kp = Kp; P.H = (int)H;
-  {
-    static int dbg = -1;
-    if (dbg < 0) { const char* e = getenv("VQB_TC_DEBUG"); dbg = e ? atoi(e) : 0; }
-    P.dbg = dbg;
-  }
+  P.dbg = dbg_env();
   P.KB = dp / kBlockK;
   P.NT = Kp / kBlockN;
   const size_t stage_bytes = pair ? kStageBytes / 2 : kStageBytes;     // per CTA

@@ -276,9 +276,11 @@ def expire_scatter(x_rows: torch.Tensor, sample_rows: torch.Tensor, threshold: f
 # ---------------------------------------------------------------------------------------------
 def rvq_level(residual: torch.Tensor, residual_next: torch.Tensor, embeddings: torch.Tensor, idx: torch.Tensor,
               mask_u8: Optional[torch.Tensor], training: bool, first_level: bool, quantized_out: torch.Tensor,
-              prepare_next: bool, q_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+              next_cache: Optional[torch.Tensor], q_out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Reads `residual` (N,d fp32), writes `residual_next` and updates `quantized_out` in place;
-    returns loss_buf [mean sq err, rows used]."""
+    returns loss_buf [mean sq err, rows used].  `next_cache`: codebook cache of the level that searches
+    `residual_next` next (its operands are prepared in the same pass), or None."""
+    prepare_next = next_cache is not None
     L.require_cuda(residual, "residual")
     L.require_cuda(residual_next, "residual_next")
     assert residual.dtype == torch.float32 and residual.ndim == 2 and residual_next.shape == residual.shape
@@ -291,7 +293,7 @@ def rvq_level(residual: torch.Tensor, residual_next: torch.Tensor, embeddings: t
     L.check(L.lib().vqb_rvq_level(L.ptr(residual), L.ptr(residual_next), L.ptr(embeddings), L.ptr(idx), L.ptr(mask_u8), int(training),
                                   int(first_level), L.ptr(quantized_out), L.ptr(q_out), L.ptr(loss), N, K, d,
                                   L.ptr(gws), gws.numel(), L.ptr(nws), nws.numel() if nws is not None else 0,
-                                  L.stream_ptr(dev)), "vqb_rvq_level")
+                                  L.ptr(next_cache), L.stream_ptr(dev)), "vqb_rvq_level")
     return loss
 
 

@@ -104,9 +104,15 @@ class ResidualVQ(nn.Module):
             training = self.training and layer.training
             do_ema = training and cb.ema_update and not freeze_codebook
             stats = ops.ema_reduce(flat, idx, mask_u8, cb.codebook_size, bound_ws=ws) if do_ema else None
-            loss_buf = ops.rvq_level(cur, nxt, emb[0], idx[0], mask_u8, training, li == 0, out,
-                                     prepare_next=li + 1 < Q)
-            prepared = li + 1 < Q
+            # the next level's operands are prepared in the same pass when its codebook cache is already final:
+            # a different codebook object (not shared) that is initialised and of the same metric
+            next_cache = None
+            if li + 1 < Q:
+                ncb = self.layers[li + 1]._codebook
+                if ncb is not cb and ncb.is_initialized:
+                    next_cache = ncb._codebook_cache()
+            loss_buf = ops.rvq_level(cur, nxt, emb[0], idx[0], mask_u8, training, li == 0, out, next_cache)
+            prepared = next_cache is not None
             if do_ema:
                 cb._all_reduce(stats)
                 ops.ema_apply(stats, cb.cluster_size.data, cb.embed_avg.data, cb.embeddings.data, 1 - cb.decay,
