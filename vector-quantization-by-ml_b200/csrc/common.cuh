@@ -171,6 +171,42 @@ template <> __device__ __forceinline__ F8 load8<__half>(const __half* p) {
   return o;
 }
 
+// 8 consecutive latent elements kept in their storage type while the load is in flight (half the registers of the
+// fp32 form for 16-bit latents, so twice as many rows can be outstanding per thread)
+template <typename T> struct Raw8 { uint4 r; };
+template <> struct Raw8<float> { float4 a, b; };
+template <typename T> __device__ __forceinline__ Raw8<T> load_raw8(const T* p) {
+  Raw8<T> o; o.r = __ldg(reinterpret_cast<const uint4*>(p)); return o;
+}
+template <> __device__ __forceinline__ Raw8<float> load_raw8<float>(const float* p) {
+  Raw8<float> o;
+  o.a = __ldg(reinterpret_cast<const float4*>(p));
+  o.b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  return o;
+}
+__device__ __forceinline__ F8 raw_to_f8(const Raw8<float>& w) {
+  F8 o; o.v[0] = w.a.x; o.v[1] = w.a.y; o.v[2] = w.a.z; o.v[3] = w.a.w; o.v[4] = w.b.x; o.v[5] = w.b.y; o.v[6] = w.b.z; o.v[7] = w.b.w;
+  return o;
+}
+__device__ __forceinline__ F8 raw_to_f8(const Raw8<__nv_bfloat16>& w) {
+  F8 o;
+  o.v[0] = __uint_as_float(w.r.x << 16); o.v[1] = __uint_as_float(w.r.x & 0xffff0000u);
+  o.v[2] = __uint_as_float(w.r.y << 16); o.v[3] = __uint_as_float(w.r.y & 0xffff0000u);
+  o.v[4] = __uint_as_float(w.r.z << 16); o.v[5] = __uint_as_float(w.r.z & 0xffff0000u);
+  o.v[6] = __uint_as_float(w.r.w << 16); o.v[7] = __uint_as_float(w.r.w & 0xffff0000u);
+  return o;
+}
+__device__ __forceinline__ F8 raw_to_f8(const Raw8<__half>& w) {
+  const uint32_t u[4] = {w.r.x, w.r.y, w.r.z, w.r.w};
+  F8 o;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&u[i]));
+    o.v[2 * i] = f.x; o.v[2 * i + 1] = f.y;
+  }
+  return o;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -220,6 +256,18 @@ __device__ __forceinline__ float clamp_row_scale(float& s, float two_q, float tw
   const float a = s * two_mq;
   return a >= 5.9604645e-8f ? a : 0.f;          // 2^-24
 }
+
+// pow2_scale(m) from the exponent field (same value for every input, a handful of integer instructions)
+__device__ __forceinline__ float pow2_scale_bits(float m) {
+  const uint32_t ef = (__float_as_uint(m) >> 23) & 0xffu;
+  if (!(m > 0.f) || ef == 0xffu) return 1.f;
+  int sh = 14 - ((int)ef - 126);            // m < 2^(ef-126); denormals: ef = 0 -> clamped below
+  if (sh > 100) sh = 100;
+  if (sh < -100) sh = -100;
+  return __uint_as_float((uint32_t)(127 + sh) << 23);
+}
+// 1 / s for a normal power of two s
+__device__ __forceinline__ float pow2_recip(float s) { return __uint_as_float(0x7F000000u - __float_as_uint(s)); }
 
 // power-of-two scale that brings a magnitude bound m below 2^14 (fp16 max is 65504)
 __host__ __device__ inline float pow2_scale(float m) {

@@ -316,20 +316,23 @@ __global__ void fused_scale_kernel(const float* __restrict__ bound2, const uint3
   scale[3] = P;
 }
 
+
+constexpr int kFusedChunkRows = 128;   // sorted positions per warp in the fused pass
+
 template <typename T, int NB, int TERMS>
 __global__ void __launch_bounds__(256, 2)
 quantize_ema_kernel(const T* __restrict__ x, const float* __restrict__ cb, const int64_t* __restrict__ idx,
                     const int* __restrict__ sorted, const uint32_t* __restrict__ start, int64_t N, int K, int d,
                     int training, const int* __restrict__ scale_p, float* __restrict__ q,
                     float* __restrict__ loss_rows, unsigned long long* __restrict__ acc) {
-  constexpr int U = NB == 1 ? 4 : 2;            // rows in flight per lane group
+  constexpr int U = (sizeof(T) == 2 ? 8 : 4) / NB;   // rows in flight per lane group (32 registers of raw data)
   const int h = blockIdx.y;
   const int lane = threadIdx.x & 31;
   const int64_t chunk = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int64_t total = start[(int64_t)h * (K + 1) + K];
-  const int64_t p0 = chunk * kChunkRows;
+  const int64_t p0 = chunk * kFusedChunkRows;
   if (p0 >= total) return;
-  const int n = (int)((p0 + kChunkRows < total ? p0 + kChunkRows : total) - p0);
+  const int n = (int)((p0 + kFusedChunkRows < total ? p0 + kFusedChunkRows : total) - p0);
   const int lpr = NB == 1 ? d >> 3 : 32;        // lanes per row
   const int rpi = 32 / lpr;                     // rows per warp iteration
   const int grp = lane / lpr, gl = lane - grp * lpr;
@@ -346,10 +349,13 @@ quantize_ema_kernel(const T* __restrict__ x, const float* __restrict__ cb, const
   float* qh = q + (int64_t)h * N * d;
   unsigned long long* acch = acc + (int64_t)h * K * d;
 
-  const int r_lo = lane < n ? srt[p0 + lane] : 0;
-  const int r_hi = lane + 32 < n ? srt[p0 + 32 + lane] : 0;
-  const int k_lo = lane < n ? (int)idxh[r_lo] : -1;
-  const int k_hi = lane + 32 < n ? (int)idxh[r_hi] : -1;
+  // row ids and codes of the chunk: 4 registers each per lane, broadcast with shuffles in the row loop
+  int rid[4], kid[4];
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    rid[t] = lane + 32 * t < n ? srt[p0 + 32 * t + lane] : 0;
+    kid[t] = lane + 32 * t < n ? (int)idxh[rid[t]] : -1;
+  }
 
   uint32_t sh[NB][8], sl[NB][8];                // wrapped sums of bits(t) (and bits(t2))
   float c[NB][8];
@@ -378,22 +384,20 @@ quantize_ema_kernel(const T* __restrict__ x, const float* __restrict__ cb, const
   };
 
   for (int i0 = 0; i0 < n; i0 += U * rpi) {
-    F8 v[U][NB];
+    Raw8<T> raw[U][NB];
     int kk[U], rr[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {               // U independent row loads in flight per group
       const int i = i0 + u * rpi + grp;
-      rr[u] = __shfl_sync(0xffffffffu, i < 32 ? r_lo : r_hi, i & 31);
-      kk[u] = __shfl_sync(0xffffffffu, i < 32 ? k_lo : k_hi, i & 31);
+      const int w = (i >> 5) & 3;
+      const int rsel = w == 0 ? rid[0] : (w == 1 ? rid[1] : (w == 2 ? rid[2] : rid[3]));
+      const int ksel = w == 0 ? kid[0] : (w == 1 ? kid[1] : (w == 2 ? kid[2] : kid[3]));
+      rr[u] = __shfl_sync(0xffffffffu, rsel, i & 31);
+      kk[u] = __shfl_sync(0xffffffffu, ksel, i & 31);
       if (i >= n) kk[u] = -1;
 #pragma unroll
-      for (int b = 0; b < NB; ++b) {
-        if (kk[u] >= 0) v[u][b] = load8<T>(xh + (int64_t)rr[u] * d + b * 256 + j);
-        else {
-#pragma unroll
-          for (int t = 0; t < 8; ++t) v[u][b].v[t] = 0.f;
-        }
-      }
+      for (int b = 0; b < NB; ++b)
+        raw[u][b] = load_raw8<T>(xh + (int64_t)(kk[u] >= 0 ? rr[u] : 0) * d + b * 256 + j);
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
@@ -414,9 +418,10 @@ quantize_ema_kernel(const T* __restrict__ x, const float* __restrict__ cb, const
 #pragma unroll
         for (int b = 0; b < NB; ++b) {
           float o[8];
+          const F8 v = raw_to_f8(raw[u][b]);
 #pragma unroll
           for (int t = 0; t < 8; ++t) {
-            const float xv = v[u][b].v[t];
+            const float xv = v.v[t];
             const float df = __fsub_rn(c[b][t], xv);
             o[t] = training ? __fadd_rn(xv, df) : c[b][t];
             sq = fmaf(df, df, sq);
@@ -730,7 +735,7 @@ extern "C" int vqb_quantize_ema(const void* x, int x_dtype, const float* codeboo
     VQB_LAUNCH_CHECK();
     ema_place_kernel<<<g1, 256, 0, st>>>(idx, nullptr, N, K, start, cursor, sorted);
     VQB_LAUNCH_CHECK();
-    const int64_t chunks = (N + kChunkRows - 1) / kChunkRows;
+    const int64_t chunks = (N + kFusedChunkRows - 1) / kFusedChunkRows;
     dim3 g2((unsigned)((chunks + 7) / 8), (unsigned)H);
 #define VQB_QE_LAUNCH(T, NB, TERMS)                                                                          \
     quantize_ema_kernel<T, NB, TERMS><<<g2, 256, 0, st>>>((const T*)x, codebook, idx, sorted, start, N, K, d, \

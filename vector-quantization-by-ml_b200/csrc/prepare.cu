@@ -82,71 +82,94 @@ __global__ void codebook_aug_scale_kernel(int64_t H, float* __restrict__ hdr) {
   hdr[h * kHdrFloats + 5] = ldexpf(1.f, -qe);
 }
 
-// Fast variant for d % 8 == 0, d <= 256 (one 8-element group per lane): a warp converts FOUR rows per iteration with
-// all four loads issued up front -- with one 512 B row per warp in flight the kernel is latency bound (Little's law:
+// Fast variant for d % 8 == 0, d <= 256 (one 8-element group per lane): a warp converts 4 (fp32) or 8 (16-bit) rows per
+// iteration with all loads issued up front -- with one 512 B row per warp in flight the kernel is latency bound (Little's law:
 // ~19 KB per SM in flight ~ 3.5 TB/s).
 template <typename T>
 __global__ void __launch_bounds__(256)
 prepare_latents4_kernel(const T* __restrict__ x, int64_t rows, int64_t rows_per_head, bool single_head, int d, int dp,
                         const float* __restrict__ chdr, __half* __restrict__ xb, float* __restrict__ xinv,
                         __half* __restrict__ xaug, uint32_t* __restrict__ scal) {
+  constexpr int U = sizeof(T) == 2 ? 8 : 4;       // rows in flight per warp (32 registers of raw data)
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
   const int j = lane * 8;
   const bool on = j < d;
   float max_n2 = 0.f, max_r2 = 0.f;
-  for (int64_t row0 = ((int64_t)blockIdx.x * wpb + (threadIdx.x >> 5)) * 4; row0 < rows;
-       row0 += (int64_t)gridDim.x * wpb * 4) {
-    F8 v[4];
+  for (int64_t row0 = ((int64_t)blockIdx.x * wpb + (threadIdx.x >> 5)) * U; row0 < rows;
+       row0 += (int64_t)gridDim.x * wpb * U) {
+    Raw8<T> raw[U];
     float my_is = 0.f, my_a = 0.f;
     float two_q = 1.f, two_mq = 1.f;
-    if (chdr) {   // the four rows of an iteration share a codebook (rows_per_head % 4 == 0 is checked by the launcher)
+    if (chdr) {   // the rows of an iteration share a codebook (rows_per_head % 8 == 0 is checked by the launcher)
       const float* hd = chdr + (single_head ? 0 : (uint32_t)row0 / (uint32_t)rows_per_head) * kHdrFloats;
       two_q = hd[4]; two_mq = hd[5];
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      if (on && row0 + u < rows) v[u] = load8<T>(x + (row0 + u) * (int64_t)d + j);
-      else {
+    for (int u = 0; u < U; ++u)                    // all U row loads are issued before the first use
+      raw[u] = load_raw8<T>(x + (on && row0 + u < rows ? (row0 + u) * (int64_t)d + j : 0));
 #pragma unroll
-        for (int e = 0; e < 8; ++e) v[u].v[e] = 0.f;
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < U; ++u) {
       if (row0 + u >= rows) break;                 // warp-uniform
+      F8 vv = raw_to_f8(raw[u]);
+      if (!on) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) vv.v[e] = 0.f;
+      }
       float m = 0.f;
 #pragma unroll
-      for (int e = 0; e < 8; ++e) m = fmaxf(m, fabsf(v[u].v[e]));
+      for (int e = 0; e < 8; ++e) m = fmaxf(m, fabsf(vv.v[e]));
 #pragma unroll
       for (int o2 = 16; o2 > 0; o2 >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o2));
-      float s = pow2_scale(m);
+      float s = pow2_scale_bits(m);
       float a = 1.f;
       if (chdr) a = clamp_row_scale(s, two_q, two_mq);
-      const float is = 1.f / s;
+      const float is = pow2_recip(s);
       if (lane == u) { my_is = a > 0.f ? is : -is; my_a = a; }     // lane u keeps row u's scalars for one 4-row store
       float n2 = 0.f, r2 = 0.f;
-      if (j < dp) {
-        uint32_t pk[4];
+      if (sizeof(T) == 2) {
+        // 16-bit latents (8 or 11 significant bits) times a power of two are fp16 numbers unless they land in
+        // fp16's subnormal range, where the rounding error is at most 2^-25: |x - x~|_j <= 2^-25 / s for every j.
+        // The residual norm is therefore BOUNDED analytically instead of measured, and |x~| <= |x| + |x - x~|.
+        if (j < dp) {
+          uint32_t pk[4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float v0 = v[u].v[2 * e], v1 = v[u].v[2 * e + 1];
-          const __half2 h = __floats2half2_rn(v0 * s, v1 * s);
-          const float2 f = __half22float2(h);
-          pk[e] = *reinterpret_cast<const uint32_t*>(&h);
-          const float b0 = f.x * is, b1 = f.y * is;
-          n2 += b0 * b0 + b1 * b1;
-          const float e0 = v0 - b0, e1 = v1 - b1;
-          r2 += e0 * e0 + e1 * e1;
+          for (int e = 0; e < 4; ++e) {
+            const float v0 = vv.v[2 * e], v1 = vv.v[2 * e + 1];
+            const __half2 h = __floats2half2_rn(v0 * s, v1 * s);
+            pk[e] = *reinterpret_cast<const uint32_t*>(&h);
+            n2 = fmaf(v0, v0, n2);
+            n2 = fmaf(v1, v1, n2);
+          }
+          *reinterpret_cast<uint4*>(xb + (row0 + u) * (int64_t)dp + j) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
         }
-        *reinterpret_cast<uint4*>(xb + (row0 + u) * (int64_t)dp + j) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        n2 = warp_sum(n2);
+        const float rb = 2.9802322e-8f * is;                       // 2^-25 / s
+        r2 = (float)dp * rb * rb * 1.0001f;
+        n2 = n2 * 1.000001f + r2 * 1.0001e6f;                      // (a + b)^2 <= a^2 (1 + e) + b^2 (1 + 1/e), e = 1e-6
+      } else {
+        if (j < dp) {
+          uint32_t pk[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float v0 = vv.v[2 * e], v1 = vv.v[2 * e + 1];
+            const __half2 h = __floats2half2_rn(v0 * s, v1 * s);
+            const float2 f = __half22float2(h);
+            pk[e] = *reinterpret_cast<const uint32_t*>(&h);
+            const float b0 = f.x * is, b1 = f.y * is;
+            n2 += b0 * b0 + b1 * b1;
+            const float e0 = v0 - b0, e1 = v1 - b1;
+            r2 += e0 * e0 + e1 * e1;
+          }
+          *reinterpret_cast<uint4*>(xb + (row0 + u) * (int64_t)dp + j) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
+        n2 = warp_sum(n2);
+        r2 = warp_sum(r2);
       }
-      n2 = warp_sum(n2);
-      r2 = warp_sum(r2);
       max_n2 = fmaxf(max_n2, n2);
       max_r2 = fmaxf(max_r2, r2);
     }
-    if (lane < 4 && row0 + lane < rows) {          // 16 B of scales + 64 B of bias operands per iteration, coalesced
+    if (lane < U && row0 + lane < rows) {          // scales + bias operands of the U rows in one coalesced store each
       xinv[row0 + lane] = my_is;
       if (xaug) {
         const uint32_t aa = (uint32_t)__half_as_ushort(__float2half_rn(my_a));
@@ -282,7 +305,7 @@ int launch_prepare_latents(const void* x, int x_dtype, int64_t rows, int64_t row
   }
   if (blocks > (int64_t)sms * 8) blocks = (int64_t)sms * 8;     // persistent: rows strided over the grid
   if (blocks < 1) blocks = 1;
-  if ((d & 7) == 0 && d <= 256 && (rows_per_head >= rows || (rows_per_head % 4 == 0 && rows < (1ll << 32)))) {
+  if ((d & 7) == 0 && d <= 256 && (rows_per_head >= rows || (rows_per_head % 8 == 0 && rows < (1ll << 32)))) {
     VQB_DISPATCH_DTYPE(x_dtype, T,
       prepare_latents4_kernel<T><<<(unsigned)blocks, warps * 32, 0, st>>>((const T*)x, rows, rows_per_head,
                                                                           rows_per_head >= rows, d, dp, chdr,
