@@ -118,6 +118,60 @@ gather_st_loss_kernel(const T* __restrict__ x, const float* __restrict__ cb, con
   }
 }
 
+// Narrow rows (d = 8..128, a power of two): d/8 lanes per row, so a warp works on 32/(d/8) rows at a time instead of
+// leaving most lanes idle (d = 64 with one row per warp moves 256 B per warp-level load and reached 28 % of HBM).
+template <typename T, bool kLoss>
+__global__ void __launch_bounds__(kGatherThreads)
+gather_st_loss_narrow_kernel(const T* __restrict__ x, const float* __restrict__ cb, const int64_t* __restrict__ idx,
+                             const uint8_t* __restrict__ mask, int training, float* __restrict__ q, int64_t H,
+                             int64_t N, int K, int d, double* __restrict__ part, long long* __restrict__ cntp) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int wpb = kGatherThreads / 32;
+  const int lpr = d >> 3, rpi = 32 / lpr;
+  const int grp = lane / lpr, j = (lane - grp * lpr) * 8;
+  const int64_t rows = H * N;
+  double sqd = 0.0;
+  long long used = 0;
+  for (int64_t row0 = ((int64_t)blockIdx.x * wpb + warp) * rpi; row0 < rows; row0 += (int64_t)gridDim.x * wpb * rpi) {
+    const int64_t row = row0 + grp;
+    if (row >= rows) continue;
+    const int64_t h = row / N, n = row - h * N;
+    const int64_t code = idx[row];
+    const bool in_loss = mask == nullptr || mask[n] != 0;
+    const F8 xv = load8<T>(x + row * (int64_t)d + j);
+    const float* cr = cb + (h * K + code) * (int64_t)d + j;
+    const float4 c0 = __ldg(reinterpret_cast<const float4*>(cr)), c1 = __ldg(reinterpret_cast<const float4*>(cr) + 1);
+    const float cv[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+    float o[8], sq = 0.f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float df = __fsub_rn(cv[e], xv.v[e]);
+      o[e] = training ? __fadd_rn(xv.v[e], df) : cv[e];
+      if (kLoss) sq = fmaf(df, df, sq);
+    }
+    float* qr = q + row * (int64_t)d + j;
+    __stcs(reinterpret_cast<float4*>(qr), make_float4(o[0], o[1], o[2], o[3]));
+    __stcs(reinterpret_cast<float4*>(qr) + 1, make_float4(o[4], o[5], o[6], o[7]));
+    if (kLoss && in_loss) { sqd += (double)sq; if (j == 0) ++used; }
+  }
+  if (kLoss) {
+    sqd = warp_sum(sqd);
+#pragma unroll
+    for (int o2 = 16; o2 > 0; o2 >>= 1) used += __shfl_xor_sync(0xffffffffu, used, o2);
+    __shared__ double s_sq[kGatherThreads / 32];
+    __shared__ long long s_n[kGatherThreads / 32];
+    if (lane == 0) { s_sq[warp] = sqd; s_n[warp] = used; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = 0.0;
+      long long c = 0;
+      for (int i = 0; i < wpb; ++i) { t += s_sq[i]; c += s_n[i]; }
+      part[blockIdx.x] = t;
+      cntp[blockIdx.x] = c;
+    }
+  }
+}
+
 // fixed-order reduction of the per-block partials: loss_out[0] = sum / (rows_used * d), loss_out[1] = rows_used
 __global__ void loss_finalize_kernel(const double* __restrict__ part, const long long* __restrict__ cntp, int nblocks,
                                      int d, float* __restrict__ loss_out) {
@@ -330,7 +384,19 @@ extern "C" int vqb_gather_st_loss(const void* x, int x_dtype, const float* codeb
   const int grid = gather_grid(H * N);
   double* part = want_loss ? (double*)((char*)ws + L.off_part) : nullptr;
   long long* cntp = want_loss ? (long long*)((char*)ws + L.off_cnt) : nullptr;
-  if (H * N > 0) {
+  const bool narrow = d >= 8 && d <= 128 && (d & (d - 1)) == 0;
+  if (H * N > 0 && narrow) {
+    if (want_loss) {
+      VQB_DISPATCH_DTYPE(x_dtype, T,
+        gather_st_loss_narrow_kernel<T, true><<<grid, kGatherThreads, 0, st>>>((const T*)x, codebook, idx, mask, training,
+                                                                               q_out, H, N, K, d, part, cntp));
+    } else {
+      VQB_DISPATCH_DTYPE(x_dtype, T,
+        gather_st_loss_narrow_kernel<T, false><<<grid, kGatherThreads, 0, st>>>((const T*)x, codebook, idx, mask, training,
+                                                                                q_out, H, N, K, d, part, cntp));
+    }
+    VQB_LAUNCH_CHECK();
+  } else if (H * N > 0) {
     // (a 4-rows-per-warp variant was measured SLOWER here: 462 vs 351 us at C2 -- the code-row gather wants occupancy)
     if (want_loss) {
       VQB_DISPATCH_DTYPE(x_dtype, T,

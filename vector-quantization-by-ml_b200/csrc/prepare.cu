@@ -190,6 +190,98 @@ prepare_latents4_kernel(const T* __restrict__ x, int64_t rows, int64_t rows_per_
   }
 }
 
+// Narrow rows (d_pad = 64 or 128): d_pad/8 lanes per row, so a warp converts 4 or 2 rows at a time (x U in flight)
+// instead of leaving most of its lanes idle.  Same arithmetic as prepare_latents4_kernel.
+template <typename T>
+__global__ void __launch_bounds__(256, 3)
+prepare_latents_narrow_kernel(const T* __restrict__ x, int64_t rows, int64_t rows_per_head, bool single_head, int d,
+                              int dp, const float* __restrict__ chdr, __half* __restrict__ xb,
+                              float* __restrict__ xinv, __half* __restrict__ xaug, uint32_t* __restrict__ scal) {
+  constexpr int U = sizeof(T) == 2 ? 8 : 4;
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  const int lpr = dp >> 3, rpi = 32 / lpr;
+  const int grp = lane / lpr, gl = lane - grp * lpr;
+  const int j = gl * 8;
+  const bool on = j < d;
+  float max_n2 = 0.f, max_r2 = 0.f;
+  for (int64_t row0 = ((int64_t)blockIdx.x * wpb + (threadIdx.x >> 5)) * (U * rpi); row0 < rows;
+       row0 += (int64_t)gridDim.x * wpb * (U * rpi)) {
+    Raw8<T> raw[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t row = row0 + u * rpi + grp;
+      raw[u] = load_raw8<T>(x + (on && row < rows ? row * (int64_t)d + j : 0));
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t row = row0 + u * rpi + grp;
+      const bool live = row < rows;
+      F8 vv = raw_to_f8(raw[u]);
+      if (!on || !live) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) vv.v[e] = 0.f;
+      }
+      float m = 0.f;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) m = fmaxf(m, fabsf(vv.v[e]));
+      for (int o2 = lpr >> 1; o2 > 0; o2 >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o2));
+      float s = pow2_scale_bits(m);
+      float a = 1.f;
+      if (chdr && live) {
+        const float* hd = chdr + (single_head ? 0 : (uint32_t)row / (uint32_t)rows_per_head) * kHdrFloats;
+        a = clamp_row_scale(s, hd[4], hd[5]);
+      }
+      const float is = pow2_recip(s);
+      float n2 = 0.f, r2 = 0.f;
+      uint32_t pk[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float v0 = vv.v[2 * e], v1 = vv.v[2 * e + 1];
+        const __half2 h = __floats2half2_rn(v0 * s, v1 * s);
+        const float2 f = __half22float2(h);
+        pk[e] = *reinterpret_cast<const uint32_t*>(&h);
+        const float b0 = f.x * is, b1 = f.y * is;
+        n2 += b0 * b0 + b1 * b1;
+        const float e0 = v0 - b0, e1 = v1 - b1;
+        r2 += e0 * e0 + e1 * e1;
+      }
+      if (live) {
+        *reinterpret_cast<uint4*>(xb + row * (int64_t)dp + j) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        if (gl == 0) {
+          xinv[row] = a > 0.f ? is : -is;
+          if (xaug) {
+            const uint32_t aa = (uint32_t)__half_as_ushort(__float2half_rn(a));
+            *reinterpret_cast<uint4*>(xaug + row * 8) = make_uint4(aa | (aa << 16), aa, 0u, 0u);
+          }
+        }
+      }
+      for (int o2 = lpr >> 1; o2 > 0; o2 >>= 1) {
+        n2 += __shfl_xor_sync(0xffffffffu, n2, o2);
+        r2 += __shfl_xor_sync(0xffffffffu, r2, o2);
+      }
+      max_n2 = fmaxf(max_n2, n2);
+      max_r2 = fmaxf(max_r2, r2);
+    }
+  }
+#pragma unroll
+  for (int o2 = 16; o2 > 0; o2 >>= 1) {
+    max_n2 = fmaxf(max_n2, __shfl_xor_sync(0xffffffffu, max_n2, o2));
+    max_r2 = fmaxf(max_r2, __shfl_xor_sync(0xffffffffu, max_r2, o2));
+  }
+  __shared__ float s_n[32], s_r[32];
+  const int w = threadIdx.x >> 5;
+  if (lane == 0) { s_n[w] = max_n2; s_r[w] = max_r2; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float mn = 0.f, mr = 0.f;
+    for (int i = 0; i < wpb; ++i) { mn = fmaxf(mn, s_n[i]); mr = fmaxf(mr, s_r[i]); }
+    const float infl = 1.f + (float)dp * 2.4e-7f;
+    atomicMax(scal + 0, __float_as_uint(sqrtf(mn * infl) * 1.00001f));
+    atomicMax(scal + 1, __float_as_uint(sqrtf(mr * infl) * 1.00001f));
+  }
+}
+
 // one warp per latent row: per-row power-of-two scale, fp16 copy (zero padded to dp),
 // atomicMax of |x~| and |x - x~| where x~ = fp16(x s)/s is what the tensor core really sees
 template <typename T>
@@ -305,7 +397,12 @@ int launch_prepare_latents(const void* x, int x_dtype, int64_t rows, int64_t row
   }
   if (blocks > (int64_t)sms * 8) blocks = (int64_t)sms * 8;     // persistent: rows strided over the grid
   if (blocks < 1) blocks = 1;
-  if ((d & 7) == 0 && d <= 256 && (rows_per_head >= rows || (rows_per_head % 8 == 0 && rows < (1ll << 32)))) {
+  if ((d & 7) == 0 && dp <= 128 && rows < (1ll << 32)) {
+    VQB_DISPATCH_DTYPE(x_dtype, T,
+      prepare_latents_narrow_kernel<T><<<(unsigned)blocks, warps * 32, 0, st>>>((const T*)x, rows, rows_per_head,
+                                                                                rows_per_head >= rows, d, dp, chdr,
+                                                                                xb, xinv, xaug, scal));
+  } else if ((d & 7) == 0 && d <= 256 && (rows_per_head >= rows || (rows_per_head % 8 == 0 && rows < (1ll << 32)))) {
     VQB_DISPATCH_DTYPE(x_dtype, T,
       prepare_latents4_kernel<T><<<(unsigned)blocks, warps * 32, 0, st>>>((const T*)x, rows, rows_per_head,
                                                                           rows_per_head >= rows, d, dp, chdr,
