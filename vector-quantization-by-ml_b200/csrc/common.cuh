@@ -79,8 +79,8 @@ inline CacheLayout cache_layout(int64_t H, int K, int d) {
 // Search workspace layout (one caller-owned buffer).
 struct SearchLayout {
   int dp;
-  size_t off_scal;    // u32[64]: [0]=max|x_b| bits, [1]=max|x-x_b| bits, [2]=#rescanned, [3]=#reranked, [4]=tc used, [5]=smem misalign flag, [6]=max E_k bits, [7]=2^q bits of operands prepared by vqb_rvq_level (0: prepared by this search), [8]=1: keys not pre-lowered by E_k (window 2 Emax)
-  size_t off_cnt;     // u32[H]: flagged rows per codebook (directly after scal: zeroed together)
+  size_t off_scal;    // u32[64]: [0]=max|x_b| bits, [1]=max|x-x_b| bits, [2]=#rescanned, [3]=#reranked, [4]=tc used, [5]=smem misalign flag, [6]=max E_k bits, [7]=2^q bits of operands prepared by vqb_rvq_level (0: prepared by this search), [8]=1: keys not pre-lowered by E_k (window 2 Emax), [9]=#pairs
+  size_t off_cnt;     // u32[3][H]: flagged rows per codebook | left to the tiled rescan | pair plan (after scal: zeroed together)
   size_t off_xb;      // fp16 [H][N][dp]  = fp16(x * s_row), zero padded
   size_t off_xinv;    // f32  [H][N]      = 1 / s_row (exact power of two); NEGATIVE marks a row whose bias operand
                       //                    s_row 2^-q is not an fp16 number: such rows are rescanned exactly
@@ -91,6 +91,8 @@ struct SearchLayout {
   size_t off_rr;      // i32 [H*N] rows queued for the warp-per-row re-rank (length in scal[3])
   size_t off_bias;    // f32 [H][Kp]  lower-bound bias  |c|^2/2 - E_k  (needs the row stats, so per search)
   size_t off_err;     // f32 [H][Kp]  E_k: bound on |exact score - bf16 tensor-core score| for code k
+  size_t off_pairs;   // {u32 row, u32 code} [pair_cap]  (row, code) pairs scored exactly in resolve phase 2 (count in scal[9])
+  size_t pair_cap;
   size_t off_caug;    // fp16 [H][Kp][8]  three fp16 pieces of s_c 2^q bias_k (+inf for padded codes), then zeros:
                       //                  the bias term of the score as one extra MMA k-step (search_tc.cu)
   size_t total;
@@ -100,7 +102,7 @@ inline SearchLayout search_layout(int64_t H, int64_t N, int K, int d) {
   L.dp = d_pad(d);
   size_t o = 0;
   L.off_scal = o; o += 256;
-  L.off_cnt = o;  o += align_up((size_t)H * 4);
+  L.off_cnt = o;  o += align_up((size_t)H * 12);
   L.off_xb = o;   o += align_up((size_t)H * N * L.dp * 2);
   L.off_xinv = o; o += align_up((size_t)H * N * 4);
   L.off_xaug = o; o += align_up((size_t)H * N * 16);
@@ -111,6 +113,8 @@ inline SearchLayout search_layout(int64_t H, int64_t N, int K, int d) {
   L.off_bias = o; o += align_up((size_t)H * k_pad(K) * 4);
   L.off_err = o;  o += align_up((size_t)H * k_pad(K) * 4);
   L.off_caug = o; o += align_up((size_t)H * k_pad(K) * 16);
+  L.pair_cap = (size_t)H * N * 4 + 4096;
+  L.off_pairs = o; o += align_up(L.pair_cap * 8);
   L.total = o;
   return L;
 }

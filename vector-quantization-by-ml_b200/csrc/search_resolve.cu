@@ -144,6 +144,7 @@ resolve_classify_kernel(const uint2* __restrict__ cand, const float* __restrict_
       idx_out[gid] = (int64_t)R.c1 + idx_offset;
     } else {
       queue = true;
+      keys[gid] = ~0ull;                      // min-key accumulator of the pair scoring
     }
   }
   // warp-aggregated append to the re-rank list (scal[3] is its length)
@@ -157,21 +158,27 @@ resolve_classify_kernel(const uint2* __restrict__ cand, const float* __restrict_
   }
 }
 
-// phase 2, one warp per queued row: lane i evaluates candidate i exactly (and, for hazard (ii), column i of
-// the 32-column group), then a lexicographic (score, index) warp-min picks the winner
-template <typename T>
+// phase 2 works on (row, code) PAIRS so that every lane of the scoring kernel is busy: a queued row has 24 candidate
+// slots but typically only 2-3 of them inside the window, and a warp-per-row kernel spends its issue slots (the
+// fp32 -> fp64 conversions run at 16 lanes/clk/SM) on 2-3 active lanes.
+//   2a  one warp per queued row: window from the 24 candidates, emit one pair per candidate inside it and, for
+//       hazard (ii), the 64 columns of the group; a row that does not fit the pair list goes to the exact rescan
+//   2b  one THREAD per pair: exact score (same fma order as everywhere else), 64-bit atomicMin of (orderable score,
+//       index) into the row's key -- the lowest index wins ties, like torch.argmax
+//   2c  one thread per queued row: unpack the key
+__device__ __forceinline__ unsigned long long pack_key(float score, int idx);
+__device__ __forceinline__ float unpack_score(unsigned long long key);
+
 __global__ void __launch_bounds__(256)
-resolve_rerank_kernel(const T* __restrict__ x, const float* __restrict__ cb, const uint2* __restrict__ cand,
-                      const float* __restrict__ err, int64_t N, int K, int Kp, int d, int metric,
-                      int64_t idx_offset, int64_t* __restrict__ idx_out, float* __restrict__ score_out,
-                      const int* __restrict__ rr_list, const uint32_t* __restrict__ scal, int aug) {
+rerank_emit_kernel(const uint2* __restrict__ cand, const float* __restrict__ err, int64_t N, int K, int Kp,
+                   const int* __restrict__ rr_list, uint32_t* __restrict__ scal, int aug, uint2* __restrict__ pairs,
+                   uint32_t pair_cap, int* __restrict__ flag_list, uint32_t* __restrict__ flag_cnt) {
   const int lane = threadIdx.x & 31;
   const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
   const int64_t count = scal[3];
   for (int64_t it = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); it < count; it += nwarps) {
     const int64_t gid = rr_list[it];
     const int64_t h = gid / N;
-    // lane i < 24 owns candidate i
     float key = __int_as_float(0x7f800000);
     int code = -1;
     if (lane < kNumCand) {
@@ -189,46 +196,106 @@ resolve_rerank_kernel(const T* __restrict__ x, const float* __restrict__ cb, con
     }
     const float E1 = (aug == 2 || scal[8]) ? __uint_as_float(scal[6]) : (c1 >= 0 ? err[h * Kp + c1] : 0.f);
     const float thr = m1 + 2.f * E1 + (fabsf(m1) + E1) * kPackSlack;
-
-    const T* xr = x + gid * (int64_t)d;
-    const float* cbh = cb + h * (int64_t)K * d;
-    const double xn2 = metric == VQB_EUCLID ? row_norm2<T>(xr, d) : 0.0;
-    float best = __int_as_float(0x7f800000);
-    int bi = 0x7fffffff;
-    if (code >= 0 && key <= thr) {
-      best = exact_score<T>(xr, cbh + (int64_t)code * d, d, metric, xn2);
-      bi = code;
-    }
-    // hazard (ii): entries 3g and 3g+1 both within thr and from the same N tile -> rescan that 32-column group
+    const bool act = code >= 0 && key <= thr;
+    // hazard (ii): entries 3g and 3g+1 both within thr and from the same pair of N tiles -> that 64-column group
     const float key_next = __shfl_down_sync(0xffffffffu, key, 1);
     const int code_next = __shfl_down_sync(0xffffffffu, code, 1);
     const bool req = lane < kNumCand && (lane % 3) == 0 && key <= thr && key_next <= thr && code >= 0 &&
                      code_next >= 0 && (code >> 9) == (code_next >> 9);
+    const uint32_t acts = __ballot_sync(0xffffffffu, act);
     uint32_t reqs = __ballot_sync(0xffffffffu, req);
+    const uint32_t n = (uint32_t)__popc(acts) + 64u * (uint32_t)__popc(reqs);
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(scal + 9, n);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (base + n > pair_cap) {          // no room: the exact rescan takes the row (its key is already ~0)
+      if (lane == 0) flag_list[h * N + atomicAdd(flag_cnt + h, 1u)] = (int)(gid - h * N);
+      for (uint32_t i = base + lane; i < base + n && i < pair_cap; i += 32)   // void the reserved slots
+        pairs[i] = make_uint2((uint32_t)gid, 0xffffffffu);
+      continue;
+    }
+    if (act) pairs[base + __popc(acts & ((1u << lane) - 1u))] = make_uint2((uint32_t)gid, (uint32_t)code);
+    uint32_t off = base + (uint32_t)__popc(acts);
     while (reqs) {
       const int src = __ffs(reqs) - 1;
       reqs &= reqs - 1;
       const int c0 = __shfl_sync(0xffffffffu, code, src);
       const int g = src / 3;                                     // group = quarter*2 + class
-#pragma unroll 1
+#pragma unroll
       for (int t = 0; t < 2; ++t) {                              // the group spans a pair of N tiles: 64 columns
         const int k = ((c0 >> 9) * 2 + t) * kBlockN + (g >> 1) * 64 + (g & 1) + 2 * lane;
-        if (k < K) {
-          const float s = exact_score<T>(xr, cbh + (int64_t)k * d, d, metric, xn2);
-          if (s < best || (s == best && k < bi)) { best = s; bi = k; }
-        }
+        // columns beyond K cannot win: repeat the requesting candidate instead (harmless duplicate)
+        pairs[off + t * 32 + lane] = make_uint2((uint32_t)gid, (uint32_t)(k < K ? k : c0));
       }
+      off += 64;
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-      if (ob < best || (ob == best && oi < bi)) { best = ob; bi = oi; }
-    }
-    if (lane == 0) {
-      idx_out[gid] = (int64_t)bi + idx_offset;
-      if (score_out) score_out[gid] = best;
-    }
+  }
+}
+
+// A handful of flagged rows are cheaper as (row, code) pairs over ALL codes than as a tiled rescan (whose latency
+// is ~60 us however few rows there are).  Per codebook: if its flagged rows x K fit the budget and the pair list,
+// reserve the pairs (plan[h] = first slot) and leave nothing for the tiled rescan (scan_cnt[h] = 0).
+constexpr uint32_t kFlagPairBudget = 1u << 17;
+__global__ void flag_plan_kernel(const uint32_t* __restrict__ flag_cnt, int H, int K, uint32_t pair_cap,
+                                 uint32_t* __restrict__ scal, uint32_t* __restrict__ scan_cnt,
+                                 uint32_t* __restrict__ plan) {
+  const int h = blockIdx.x * blockDim.x + threadIdx.x;
+  if (h >= H) return;
+  const uint32_t n = flag_cnt[h];
+  scan_cnt[h] = n;
+  plan[h] = 0xffffffffu;
+  if (n == 0 || (uint64_t)n * (uint64_t)K > kFlagPairBudget) return;
+  const uint32_t need = n * (uint32_t)K;
+  const uint32_t base = atomicAdd(scal + 9, need);
+  if ((uint64_t)base + need > pair_cap) return;     // (the over-reservation is clamped away by pair_score_kernel)
+  plan[h] = base;
+  scan_cnt[h] = 0;
+  atomicAdd(scal + 2, n);                           // statistics: rows resolved by a scan of every code
+}
+__global__ void __launch_bounds__(256)
+flag_emit_kernel(const int* __restrict__ flag_list, const uint32_t* __restrict__ flag_cnt,
+                 const uint32_t* __restrict__ plan, int64_t N, int K, uint2* __restrict__ pairs) {
+  const int h = blockIdx.y;
+  const uint32_t base = plan[h];
+  if (base == 0xffffffffu) return;
+  const uint64_t total = (uint64_t)flag_cnt[h] * (uint64_t)K;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t p = (uint32_t)(i / (uint32_t)K), k = (uint32_t)(i - (uint64_t)p * (uint32_t)K);
+    pairs[base + i] = make_uint2((uint32_t)((int64_t)h * N + flag_list[(int64_t)h * N + p]), k);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+pair_score_kernel(const T* __restrict__ x, const float* __restrict__ cb, const uint2* __restrict__ pairs,
+                  const uint32_t* __restrict__ scal, uint32_t pair_cap, int64_t total_rows, int64_t N, int K, int d,
+                  int metric, unsigned long long* __restrict__ keys) {
+  uint32_t count = scal[9];
+  if (count > pair_cap) count = pair_cap;      // over-reserved by rows that were diverted to the rescan
+  for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < count; p += gridDim.x * blockDim.x) {
+    const uint2 pr = pairs[p];
+    const int64_t gid = pr.x;
+    // voided slot (row diverted to the rescan), or a slot of a reservation that did not fit and was never written:
+    // whatever in-range (row, code) such a slot holds is a true score of a real code -- harmless for the minimum
+    if (pr.y >= (uint32_t)K || gid >= total_rows) continue;
+    const int64_t h = gid / N;
+    const T* xr = x + gid * (int64_t)d;
+    const double xn2 = metric == VQB_EUCLID ? row_norm2<T>(xr, d) : 0.0;
+    const float s = exact_score<T>(xr, cb + (h * K + (int64_t)pr.y) * d, d, metric, xn2);
+    atomicMin(keys + gid, pack_key(s, (int)pr.y));
+  }
+}
+
+__global__ void rerank_finalize_kernel(const int* __restrict__ rr_list, const uint32_t* __restrict__ scal,
+                                       const unsigned long long* __restrict__ keys, int64_t idx_offset,
+                                       int64_t* __restrict__ idx_out, float* __restrict__ score_out) {
+  const int64_t count = scal[3];
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < count; p += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t gid = rr_list[p];
+    const unsigned long long key = keys[gid];
+    if (key == ~0ull) continue;                // diverted to the rescan: rescan_finalize writes it
+    idx_out[gid] = (int64_t)(uint32_t)(key & 0xffffffffull) + idx_offset;
+    if (score_out) score_out[gid] = unpack_score(key);
   }
 }
 
@@ -396,16 +463,18 @@ extern "C" int vqb_search(const void* x, int x_dtype, const float* codebook, con
   cudaStream_t st = (cudaStream_t)stream;
   char* w = (char*)ws;
   uint32_t* scal = (uint32_t*)(w + SL.off_scal);
-  uint32_t* cnt = (uint32_t*)(w + SL.off_cnt);
+  uint32_t* cnt = (uint32_t*)(w + SL.off_cnt);          // [H] flagged rows | [H] of them left to the tiled rescan | [H] plan
+  uint32_t* scan_cnt = cnt + H;
+  uint32_t* plan = cnt + 2 * H;
   int* flag_list = (int*)(w + SL.off_flag);
   const bool prepared = (flags & VQB_SEARCH_LATENTS_PREPARED) != 0;
   const bool tc = !(flags & VQB_SEARCH_FORCE_EXACT) && SL.dp <= 512 && cache != nullptr;
   // scal[0..1] hold the row statistics: keep them when the caller prepared the latents
   if (prepared) {   // keep [0..1] (row statistics) and [7] (2^q of the prepared bias operands)
     VQB_CUDA_TRY(cudaMemsetAsync((char*)scal + 8, 0, 20, st));
-    VQB_CUDA_TRY(cudaMemsetAsync((char*)scal + 32, 0, (SL.off_cnt - SL.off_scal) + (size_t)H * 4 - 32, st));
+    VQB_CUDA_TRY(cudaMemsetAsync((char*)scal + 32, 0, (SL.off_cnt - SL.off_scal) + (size_t)H * 12 - 32, st));
   } else {
-    VQB_CUDA_TRY(cudaMemsetAsync((char*)scal, 0, (SL.off_cnt - SL.off_scal) + (size_t)H * 4, st));
+    VQB_CUDA_TRY(cudaMemsetAsync((char*)scal, 0, (SL.off_cnt - SL.off_scal) + (size_t)H * 12, st));
   }
 
   const int grid_scan = (int)((N + kER - 1) / kER < 4 * (int64_t)num_sms() ? (N + kER - 1) / kER : 4 * num_sms());
@@ -445,13 +514,25 @@ extern "C" int vqb_search(const void* x, int x_dtype, const float* codebook, con
       flag_list, cnt, keys, scal, xinv, chdr, aug);
   VQB_LAUNCH_CHECK();
   {
+    uint2* pairs = (uint2*)(w + SL.off_pairs);
+    const uint32_t pair_cap = (uint32_t)(SL.pair_cap < 0xffffff00ull ? SL.pair_cap : 0xffffff00ull);
     int64_t want = score_out ? (total + 7) / 8 : (total / 16 + 7) / 8 + 1;   // blocks of 8 warps
     const int64_t cap = (int64_t)num_sms() * 8;
     const int grid_rr = (int)(want < cap ? want : cap);
+    rerank_emit_kernel<<<grid_rr, 256, 0, st>>>((const uint2*)(w + SL.off_cand), err, N, K, CL.Kp, rr_list, scal, aug,
+                                                pairs, pair_cap, flag_list, cnt);
+    VQB_LAUNCH_CHECK();
+    flag_plan_kernel<<<(unsigned)((H + 63) / 64), 64, 0, st>>>(cnt, (int)H, K, pair_cap, scal, scan_cnt, plan);
+    VQB_LAUNCH_CHECK();
+    flag_emit_kernel<<<dim3(64, (unsigned)H), 256, 0, st>>>(flag_list, cnt, plan, N, K, pairs);
+    VQB_LAUNCH_CHECK();
+    int64_t wantp = score_out ? (total + 255) / 256 : (total / 8 + 255) / 256 + 1;
+    const int grid_ps = (int)(wantp < cap ? wantp : cap);
     VQB_DISPATCH_DTYPE(x_dtype, T,
-      resolve_rerank_kernel<T><<<grid_rr, 256, 0, st>>>(
-          (const T*)x, codebook, (const uint2*)(w + SL.off_cand), err, N, K, CL.Kp, d, metric, idx_offset, idx_out,
-          score_out, rr_list, scal, aug));
+      pair_score_kernel<T><<<grid_ps, 256, 0, st>>>((const T*)x, codebook, pairs, scal, pair_cap, total, N, K, d, metric,
+                                                    keys));
+    VQB_LAUNCH_CHECK();
+    rerank_finalize_kernel<<<grid_rr, 256, 0, st>>>(rr_list, scal, keys, idx_offset, idx_out, score_out);
     VQB_LAUNCH_CHECK();
   }
   // flagged rows (count is device-side): fixed grid, code range split over blockIdx.z so that even a handful of
@@ -464,7 +545,7 @@ extern "C" int vqb_search(const void* x, int x_dtype, const float* codebook, con
   VQB_REQUIRE(nsplit <= 65535, VQB_ERR_UNSUPPORTED, "codebook too large for the rescan grid");
   VQB_DISPATCH_DTYPE(x_dtype, T,
     exact_scan_kernel<T, true><<<dim3((unsigned)grid_rows, (unsigned)H, (unsigned)nsplit), 256, 0, st>>>(
-        (const T*)x, codebook, flag_list, cnt, N, K, d, metric, idx_offset, idx_out, score_out, scal, ksplit_codes,
+        (const T*)x, codebook, flag_list, scan_cnt, N, K, d, metric, idx_offset, idx_out, score_out, scal, ksplit_codes,
         keys));
   VQB_LAUNCH_CHECK();
   rescan_finalize_kernel<<<dim3(8, (unsigned)H), 256, 0, st>>>(flag_list, cnt, keys, N, idx_offset, idx_out, score_out);
