@@ -192,6 +192,17 @@ int    vqb_rvq_level(const float* residual_in, float* residual_out, const float*
                      void* gather_ws, size_t gather_ws_bytes,
                      void* next_ws, size_t next_ws_bytes, const void* next_cache, void* stream);
 
+/* vqb_rvq_level and vqb_ema_reduce of one level in ONE pass over the residual, in code-sorted order (the same kernel
+ * as vqb_quantize_ema): un-masked training levels only, d = 64, 128, 256 or 512 (vqb_rvq_level_ema_supported), fp32
+ * residual, residual_out != residual_in.  Outputs as vqb_rvq_level (loss_out, quantized_out, residual_out, q_out,
+ * next_ws) plus stats (K,d+1) as vqb_ema_reduce; ws: vqb_quantize_ema_workspace_bytes(1, N, K, d). */
+int    vqb_rvq_level_ema_supported(int d);
+int    vqb_rvq_level_ema(const float* residual_in, float* residual_out, const float* codebook, const int64_t* idx,
+                         const float* absmax_bound2, int training, int first_level, float* quantized_out,
+                         float* q_out, float* loss_out, float* stats, int64_t N, int K, int d,
+                         void* ws, size_t ws_bytes, void* next_ws, size_t next_ws_bytes, const void* next_cache,
+                         void* stream);
+
 /* ---- sharded-codebook merge (K >= 64K split across GPUs) ------------------------------
  * No reference counterpart.  key = (orderable(score) << 32) | index, so an
  * all_reduce(MIN) over uint64 (as int64 with the sign bit clear) picks the smallest score and,

@@ -303,6 +303,40 @@ def test_fused_quantize_ema_extreme_scales_and_module_switch():
     assert torch.allclose(a[4], b[4], rtol=1e-5, atol=1e-7)
 
 
+@pytest.mark.parametrize("d,K", [(512, 64), (256, 37), (64, 100), (128, 8)])
+def test_rvq_level_ema_matches_separate_kernels(d, K):
+    """vqb_rvq_level_ema == vqb_rvq_level + vqb_ema_reduce on every output, including the next level's operands
+    (checked through the search they feed)."""
+    from vqb200 import ops
+    g = torch.Generator().manual_seed(d + K)
+    N = 3000
+    res = (torch.randn(N, d, generator=g) * 2).to(_dev())
+    c = torch.randn(1, K, d, generator=g).to(_dev())
+    c2 = (torch.randn(1, K, d, generator=g) * 0.5).to(_dev())
+    idx = torch.randint(0, K, (1, N), generator=g).to(_dev())
+    idx[:, :700] = K - 1
+    cache2 = ops.prepare_codebook(c2, False)
+    for first in (True, False):
+        outs = []
+        for fused in (True, False):
+            out = torch.full((N, d), 0.25, device=_dev())
+            nxt = torch.empty_like(res)
+            if fused:
+                loss, stats = ops.rvq_level_ema(res, nxt, c[0], idx[0], True, first, out, cache2)
+            else:
+                stats = ops.ema_reduce(res[None], idx, None, K)
+                loss = ops.rvq_level(res, nxt, c[0], idx[0], None, True, first, out, cache2)
+            nidx, _, _ = ops.search(nxt[None], c2, cache2, False, latents_prepared=True)
+            outs.append((out.clone(), nxt.clone(), loss.clone(), stats.clone(), nidx.clone()))
+        a, b = outs
+        assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(a[4], b[4])
+        assert torch.allclose(a[2], b[2], rtol=1e-6)
+        assert torch.equal(a[3][..., d], b[3][..., d])
+        assert float((a[3] - b[3]).abs().max()) <= 2e-6 * float(b[3].abs().max())
+        ref_idx, _, _ = ops.search(a[1][None], c2, cache2, False)
+        assert torch.equal(a[4], ref_idx)
+
+
 def test_minkey_roundtrip_and_order():
     from vqb200 import ops
     g = torch.Generator().manual_seed(2)

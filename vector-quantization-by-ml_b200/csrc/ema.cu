@@ -319,13 +319,31 @@ __global__ void fused_scale_kernel(const float* __restrict__ bound2, const uint3
 
 constexpr int kFusedChunkRows = 128;   // sorted positions per warp in the fused pass
 
-template <typename T, int NB, int TERMS>
+// ResidualVQ level extras (RVQ = true, H = 1, fp32 residual): the same pass also does residual_vq.py:232-233 and prepares
+// the next level's search operand (what vqb_rvq_level does in row order):
+//   out = first ? 0 + q : out + q ;  r_next = r - q ;  next operand = scaled fp16 of r_next + row scale + bias operand
+struct RvqExtra {
+  float* out;             // (N,d) running sum of the levels' outputs, updated in place
+  float* res_out;         // (N,d) next residual
+  float* q_level;         // (N,d) this level's output, nullable
+  __half* next_xb;        // nullable: no next level
+  float* next_xinv;
+  __half* next_xaug;
+  uint32_t* next_scal;
+  const float* next_chdr;
+  int first;
+  int dp;
+};
+
+template <typename T, int NB, int TERMS, bool RVQ>
 __global__ void __launch_bounds__(256, 2)
 quantize_ema_kernel(const T* __restrict__ x, const float* __restrict__ cb, const int64_t* __restrict__ idx,
                     const int* __restrict__ sorted, const uint32_t* __restrict__ start, int64_t N, int K, int d,
                     int training, const int* __restrict__ scale_p, float* __restrict__ q,
-                    float* __restrict__ loss_rows, unsigned long long* __restrict__ acc) {
-  constexpr int U = (sizeof(T) == 2 ? 8 : 4) / NB;   // rows in flight per lane group (32 registers of raw data)
+                    float* __restrict__ loss_rows, unsigned long long* __restrict__ acc, const RvqExtra R) {
+  // rows in flight per lane group: 32 registers of raw data (half of that in the register-hungry RVQ form)
+  constexpr int U0 = (sizeof(T) == 2 ? 8 : 4) / NB;
+  constexpr int U = RVQ ? (U0 > 1 ? U0 / 2 : 1) : U0;
   const int h = blockIdx.y;
   const int lane = threadIdx.x & 31;
   const int64_t chunk = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -365,6 +383,7 @@ quantize_ema_kernel(const T* __restrict__ x, const float* __restrict__ cb, const
     for (int t = 0; t < 8; ++t) { sh[b][t] = 0u; sl[b][t] = 0u; c[b][t] = 0.f; }
   int cur = -1;
   uint32_t cnt = 0;                             // rows in the open segment of this lane group
+  float max_n2 = 0.f, max_r2 = 0.f;             // RVQ: statistics of the next level's operand
 
   auto flush = [&]() {
     if (cur >= 0) {
@@ -402,6 +421,14 @@ quantize_ema_kernel(const T* __restrict__ x, const float* __restrict__ cb, const
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       float sq = 0.f;
+      F8 rn[NB];                                // RVQ: the new residual stays in registers for the fp16 conversion
+      float mabs = 0.f;
+      if (RVQ) {
+#pragma unroll
+        for (int b = 0; b < NB; ++b)
+#pragma unroll
+          for (int t = 0; t < 8; ++t) rn[b].v[t] = 0.f;
+      }
       if (kk[u] >= 0) {
         if (kk[u] != cur) {                     // group-uniform: segment boundary
           flush();
@@ -432,10 +459,72 @@ quantize_ema_kernel(const T* __restrict__ x, const float* __restrict__ cb, const
               sl[b][t] += __float_as_uint(__fadd_rn(lo, M2));
             }
           }
-          float* qr = qh + (int64_t)rr[u] * d + b * 256 + j;
-          __stcs(reinterpret_cast<float4*>(qr), make_float4(o[0], o[1], o[2], o[3]));
-          __stcs(reinterpret_cast<float4*>(qr) + 1, make_float4(o[4], o[5], o[6], o[7]));
+          const int64_t off = (int64_t)rr[u] * d + b * 256 + j;
+          if (!RVQ) {
+            __stcs(reinterpret_cast<float4*>(qh + off), make_float4(o[0], o[1], o[2], o[3]));
+            __stcs(reinterpret_cast<float4*>(qh + off) + 1, make_float4(o[4], o[5], o[6], o[7]));
+          } else {
+            float acc8[8];
+            if (R.first) {
+#pragma unroll
+              for (int t = 0; t < 8; ++t) acc8[t] = __fadd_rn(0.f, o[t]);
+            } else {
+              const float4 p0 = *reinterpret_cast<const float4*>(R.out + off), p1 = *(reinterpret_cast<const float4*>(R.out + off) + 1);
+              const float pv[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+#pragma unroll
+              for (int t = 0; t < 8; ++t) acc8[t] = __fadd_rn(pv[t], o[t]);
+            }
+            *reinterpret_cast<float4*>(R.out + off) = make_float4(acc8[0], acc8[1], acc8[2], acc8[3]);
+            *(reinterpret_cast<float4*>(R.out + off) + 1) = make_float4(acc8[4], acc8[5], acc8[6], acc8[7]);
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+              rn[b].v[t] = __fsub_rn(v.v[t], o[t]);
+              mabs = fmaxf(mabs, fabsf(rn[b].v[t]));
+            }
+            *reinterpret_cast<float4*>(R.res_out + off) = make_float4(rn[b].v[0], rn[b].v[1], rn[b].v[2], rn[b].v[3]);
+            *(reinterpret_cast<float4*>(R.res_out + off) + 1) = make_float4(rn[b].v[4], rn[b].v[5], rn[b].v[6], rn[b].v[7]);
+            if (R.q_level) {
+              *reinterpret_cast<float4*>(R.q_level + off) = make_float4(o[0], o[1], o[2], o[3]);
+              *(reinterpret_cast<float4*>(R.q_level + off) + 1) = make_float4(o[4], o[5], o[6], o[7]);
+            }
+          }
         }
+      }
+      if (RVQ && R.next_xb) {                   // next level's operand (shuffles: every lane takes part)
+        const bool live = kk[u] >= 0;
+        for (int o2 = lpr >> 1; o2 > 0; o2 >>= 1) mabs = fmaxf(mabs, __shfl_xor_sync(0xffffffffu, mabs, o2));
+        float s = pow2_scale_bits(mabs);
+        const float a = clamp_row_scale(s, R.next_chdr[4], R.next_chdr[5]);
+        const float is = pow2_recip(s);
+        if (gl == 0 && live) {
+          R.next_xinv[rr[u]] = a > 0.f ? is : -is;
+          const uint32_t aa = (uint32_t)__half_as_ushort(__float2half_rn(a));
+          *reinterpret_cast<uint4*>(R.next_xaug + (int64_t)rr[u] * 8) = make_uint4(aa | (aa << 16), aa, 0u, 0u);
+        }
+        float n2 = 0.f, r2 = 0.f;
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+          uint32_t pk[4];
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const float v0 = rn[b].v[2 * t], v1 = rn[b].v[2 * t + 1];
+            const __half2 hh = __floats2half2_rn(v0 * s, v1 * s);
+            const float2 f = __half22float2(hh);
+            pk[t] = *reinterpret_cast<const uint32_t*>(&hh);
+            const float b0 = f.x * is, b1 = f.y * is;
+            n2 += b0 * b0 + b1 * b1;
+            const float e0 = v0 - b0, e1 = v1 - b1;
+            r2 += e0 * e0 + e1 * e1;
+          }
+          if (live)
+            *reinterpret_cast<uint4*>(R.next_xb + (int64_t)rr[u] * R.dp + b * 256 + j) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
+        for (int o2 = lpr >> 1; o2 > 0; o2 >>= 1) {
+          n2 += __shfl_xor_sync(0xffffffffu, n2, o2);
+          r2 += __shfl_xor_sync(0xffffffffu, r2, o2);
+        }
+        max_n2 = fmaxf(max_n2, n2);
+        max_r2 = fmaxf(max_r2, r2);
       }
       if (loss_rows) {                          // fixed-order sum over the lanes of the row
         for (int o2 = lpr >> 1; o2 > 0; o2 >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o2);
@@ -444,6 +533,19 @@ quantize_ema_kernel(const T* __restrict__ x, const float* __restrict__ cb, const
     }
   }
   flush();
+  if (RVQ && R.next_xb) {
+#pragma unroll
+    for (int o2 = 16; o2 > 0; o2 >>= 1) {
+      max_n2 = fmaxf(max_n2, __shfl_xor_sync(0xffffffffu, max_n2, o2));
+      max_r2 = fmaxf(max_r2, __shfl_xor_sync(0xffffffffu, max_r2, o2));
+    }
+    if (lane == 0) {
+      const float infl = 1.f + (float)R.dp * 2.4e-7f;
+      atomicMax(R.next_scal + 0, __float_as_uint(sqrtf(max_n2 * infl) * 1.00001f));
+      atomicMax(R.next_scal + 1, __float_as_uint(sqrtf(max_r2 * infl) * 1.00001f));
+      if (blockIdx.x == 0 && threadIdx.x == 0) R.next_scal[7] = __float_as_uint(R.next_chdr[4]);
+    }
+  }
 }
 
 // fixed-order partial sums of the per-row squared errors: block b owns rows [b*span, (b+1)*span)
@@ -696,11 +798,12 @@ extern "C" size_t vqb_quantize_ema_workspace_bytes(int64_t H, int64_t N, int K, 
   return fused_layout(H, N, K, d).total;
 }
 
-extern "C" int vqb_quantize_ema(const void* x, int x_dtype, const float* codebook, const int64_t* idx,
-                                const float* absmax_bound2, int training, int want_loss, float* q_out,
-                                float* loss_out, float* stats, int64_t H, int64_t N, int K, int d, void* ws,
-                                size_t ws_bytes, void* stream) {
-  VQB_REQUIRE(x && codebook && idx && q_out && stats && ws, VQB_ERR_INVALID, "vqb_quantize_ema: null pointer");
+// shared by vqb_quantize_ema (rvq == nullptr) and vqb_rvq_level_ema
+static int quantize_ema_impl(const void* x, int x_dtype, const float* codebook, const int64_t* idx,
+                             const float* absmax_bound2, int training, int want_loss, float* q_out,
+                             float* loss_out, float* stats, int64_t H, int64_t N, int K, int d, void* ws,
+                             size_t ws_bytes, const RvqExtra* rvq, void* stream) {
+  VQB_REQUIRE(x && codebook && idx && (q_out || rvq) && stats && ws, VQB_ERR_INVALID, "vqb_quantize_ema: null pointer");
   VQB_REQUIRE(H > 0 && N >= 0 && K > 0 && d > 0 && H < 65536, VQB_ERR_INVALID, "vqb_quantize_ema: bad shape");
   VQB_REQUIRE(N < (1ll << 31), VQB_ERR_UNSUPPORTED, "N must be < 2^31");
   VQB_REQUIRE(fused_width_ok(d), VQB_ERR_UNSUPPORTED, "vqb_quantize_ema: d=%d (need a power of two <= 256, or 512)", d);
@@ -728,6 +831,8 @@ extern "C" int vqb_quantize_ema(const void* x, int x_dtype, const float* codeboo
     }
     fused_scale_kernel<<<1, 1, 0, st>>>(absmax_bound2, (const uint32_t*)(scale + 1), N, two_terms, scale);
     VQB_LAUNCH_CHECK();
+    // the next level's statistics usually live in the workspace absmax_bound2 points into: zero them only now
+    if (rvq && rvq->next_scal) VQB_CUDA_TRY(cudaMemsetAsync(rvq->next_scal, 0, 8, st));
     dim3 g1((unsigned)((N + 255) / 256), (unsigned)H);
     ema_hist_kernel<<<g1, 256, 0, st>>>(idx, nullptr, N, K, counts);
     VQB_LAUNCH_CHECK();
@@ -738,10 +843,19 @@ extern "C" int vqb_quantize_ema(const void* x, int x_dtype, const float* codeboo
     const int64_t chunks = (N + kFusedChunkRows - 1) / kFusedChunkRows;
     dim3 g2((unsigned)((chunks + 7) / 8), (unsigned)H);
 #define VQB_QE_LAUNCH(T, NB, TERMS)                                                                          \
-    quantize_ema_kernel<T, NB, TERMS><<<g2, 256, 0, st>>>((const T*)x, codebook, idx, sorted, start, N, K, d, \
-                                                          training, scale, q_out, loss_rows,                 \
-                                                          (unsigned long long*)acc)
-    if (d == 512) {
+    quantize_ema_kernel<T, NB, TERMS, false><<<g2, 256, 0, st>>>((const T*)x, codebook, idx, sorted, start, N, K, d, \
+                                                                 training, scale, q_out, loss_rows,              \
+                                                                 (unsigned long long*)acc, RvqExtra{})
+    if (rvq) {
+      if (d == 512)
+        quantize_ema_kernel<float, 2, 2, true><<<g2, 256, 0, st>>>((const float*)x, codebook, idx, sorted, start, N, K, d,
+                                                                   training, scale, nullptr, loss_rows,
+                                                                   (unsigned long long*)acc, *rvq);
+      else
+        quantize_ema_kernel<float, 1, 2, true><<<g2, 256, 0, st>>>((const float*)x, codebook, idx, sorted, start, N, K, d,
+                                                                   training, scale, nullptr, loss_rows,
+                                                                   (unsigned long long*)acc, *rvq);
+    } else if (d == 512) {
       if (x_dtype == VQB_F32) VQB_QE_LAUNCH(float, 2, 2);
       else if (x_dtype == VQB_BF16) VQB_QE_LAUNCH(__nv_bfloat16, 2, 1);
       else if (x_dtype == VQB_F16) VQB_QE_LAUNCH(__half, 2, 1);
@@ -771,6 +885,41 @@ extern "C" int vqb_quantize_ema(const void* x, int x_dtype, const float* codeboo
     if (rc) return rc;
   }
   return VQB_OK;
+}
+
+extern "C" int vqb_quantize_ema(const void* x, int x_dtype, const float* codebook, const int64_t* idx,
+                                const float* absmax_bound2, int training, int want_loss, float* q_out,
+                                float* loss_out, float* stats, int64_t H, int64_t N, int K, int d, void* ws,
+                                size_t ws_bytes, void* stream) {
+  return quantize_ema_impl(x, x_dtype, codebook, idx, absmax_bound2, training, want_loss, q_out, loss_out, stats, H, N,
+                           K, d, ws, ws_bytes, nullptr, stream);
+}
+
+extern "C" int vqb_rvq_level_ema_supported(int d) { return (d == 64 || d == 128 || d == 256 || d == 512) ? 1 : 0; }
+
+extern "C" int vqb_rvq_level_ema(const float* residual_in, float* residual_out, const float* codebook,
+                                 const int64_t* idx, const float* absmax_bound2, int training, int first_level,
+                                 float* quantized_out, float* q_out, float* loss_out, float* stats, int64_t N, int K,
+                                 int d, void* ws, size_t ws_bytes, void* next_ws, size_t next_ws_bytes,
+                                 const void* next_cache, void* stream) {
+  VQB_REQUIRE(residual_in && residual_out && quantized_out && loss_out, VQB_ERR_INVALID, "vqb_rvq_level_ema: null pointer");
+  VQB_REQUIRE(vqb_rvq_level_ema_supported(d), VQB_ERR_UNSUPPORTED, "vqb_rvq_level_ema: d=%d (64, 128, 256 or 512)", d);
+  VQB_REQUIRE(residual_in != residual_out, VQB_ERR_INVALID, "vqb_rvq_level_ema: rows are visited in code order, the "
+              "residual cannot be updated in place");
+  RvqExtra R = {};
+  R.out = quantized_out; R.res_out = residual_out; R.q_level = q_out; R.first = first_level; R.dp = d_pad(d);
+  if (next_ws) {
+    VQB_REQUIRE(next_cache != nullptr, VQB_ERR_INVALID, "vqb_rvq_level_ema: next_ws needs next_cache");
+    SearchLayout SL = search_layout(1, N, K, d);
+    VQB_REQUIRE(next_ws_bytes >= SL.total, VQB_ERR_WORKSPACE, "next-level search workspace too small");
+    R.next_xb = (__half*)((char*)next_ws + SL.off_xb);
+    R.next_xaug = (__half*)((char*)next_ws + SL.off_xaug);
+    R.next_xinv = (float*)((char*)next_ws + SL.off_xinv);
+    R.next_scal = (uint32_t*)((char*)next_ws + SL.off_scal);
+    R.next_chdr = (const float*)((const char*)next_cache + cache_layout(1, K, d).off_hdr);
+  }
+  return quantize_ema_impl(residual_in, VQB_F32, codebook, idx, absmax_bound2, training, 1, nullptr, loss_out, stats, 1,
+                           N, K, d, ws, ws_bytes, &R, stream);
 }
 
 extern "C" int vqb_ema_apply_counts(const float* stats, float* cluster_size, float weight, int64_t H, int K, int d,

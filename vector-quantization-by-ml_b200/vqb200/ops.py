@@ -297,6 +297,32 @@ def rvq_level(residual: torch.Tensor, residual_next: torch.Tensor, embeddings: t
     return loss
 
 
+def rvq_level_ema_supported(d: int) -> bool:
+    return bool(L.lib().vqb_rvq_level_ema_supported(int(d)))
+
+
+def rvq_level_ema(residual: torch.Tensor, residual_next: torch.Tensor, embeddings: torch.Tensor, idx: torch.Tensor,
+                  training: bool, first_level: bool, quantized_out: torch.Tensor, next_cache: Optional[torch.Tensor],
+                  bound_ws: Optional[torch.Tensor] = None, q_out: Optional[torch.Tensor] = None):
+    """rvq_level + ema_reduce of an un-masked level in one pass: returns (loss_buf, stats (1,K,d+1))."""
+    L.require_cuda(residual, "residual")
+    L.require_cuda(residual_next, "residual_next")
+    assert residual.dtype == torch.float32 and residual.ndim == 2 and residual_next.shape == residual.shape
+    N, d = residual.shape
+    K = embeddings.shape[-2]
+    dev = residual.device
+    loss = torch.empty(2, dtype=torch.float32, device=dev)
+    stats = torch.empty((1, K, d + 1), dtype=torch.float32, device=dev)
+    ws = workspace("ema", L.lib().vqb_quantize_ema_workspace_bytes(1, N, K, d), dev)
+    nws = workspace("search", L.lib().vqb_search_workspace_bytes(1, N, K, d), dev) if next_cache is not None else None
+    L.check(L.lib().vqb_rvq_level_ema(L.ptr(residual), L.ptr(residual_next), L.ptr(embeddings), L.ptr(idx),
+                                      L.ptr(bound_ws), int(training), int(first_level), L.ptr(quantized_out),
+                                      L.ptr(q_out), L.ptr(loss), L.ptr(stats), N, K, d, L.ptr(ws), ws.numel(),
+                                      L.ptr(nws), nws.numel() if nws is not None else 0, L.ptr(next_cache),
+                                      L.stream_ptr(dev)), "vqb_rvq_level_ema")
+    return loss, stats
+
+
 def minkey_pack(score: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
     L.require_cuda(score, "score")
     keys = torch.empty(score.numel(), dtype=torch.int64, device=score.device)

@@ -103,15 +103,20 @@ class ResidualVQ(nn.Module):
             idx, _, ws = ops.search(flat, emb, cb._codebook_cache(), cb.use_cosine_sim, latents_prepared=prepared)
             training = self.training and layer.training
             do_ema = training and cb.ema_update and not freeze_codebook
-            stats = ops.ema_reduce(flat, idx, mask_u8, cb.codebook_size, bound_ws=ws) if do_ema else None
             # the next level's operands are prepared in the same pass when its codebook cache is already final:
-            # a different codebook object (not shared) that is initialised and of the same metric
+            # a different codebook object (not shared) that is initialised
             next_cache = None
             if li + 1 < Q:
                 ncb = self.layers[li + 1]._codebook
                 if ncb is not cb and ncb.is_initialized:
                     next_cache = ncb._codebook_cache()
-            loss_buf = ops.rvq_level(cur, nxt, emb[0], idx[0], mask_u8, training, li == 0, out, next_cache)
+            if do_ema and mask_u8 is None and cb.fused_quantize_ema and ops.rvq_level_ema_supported(d):
+                # un-masked training level: level step and EMA sums share one pass over the residual
+                loss_buf, stats = ops.rvq_level_ema(cur, nxt, emb[0], idx[0], training, li == 0, out, next_cache,
+                                                    bound_ws=ws)
+            else:
+                stats = ops.ema_reduce(flat, idx, mask_u8, cb.codebook_size, bound_ws=ws) if do_ema else None
+                loss_buf = ops.rvq_level(cur, nxt, emb[0], idx[0], mask_u8, training, li == 0, out, next_cache)
             prepared = next_cache is not None
             if do_ema:
                 cb._all_reduce(stats)
