@@ -44,7 +44,7 @@ def ncu_traffic_bytes():
         return None
     try:
         for k in json.load(open(files[-1]))["ncu_full"]:
-            if "search_tc_kernel" in k["kernel"]:
+            if "search_aug_kernel" in k["kernel"] or "search_tc_kernel" in k["kernel"]:
                 return (k["dram_rd_MB"] + k["dram_wr_MB"]) * 1e6
     except Exception:
         return None
@@ -293,7 +293,7 @@ def main():
         flops = 2.0 * N_ROWS * K_CODES * DIM                     # algorithmic flops per launch of the search kernel
         tc_avg = sum(tc_ms) / len(tc_ms) if tc_ms else float("nan")
         achieved = flops / (tc_avg / 1e3) / 1e12
-        roofline = {"kernel": "search_tc_kernel (tcgen05 GEMM + fused top-k epilogue)", "bound": "tensor",
+        roofline = {"kernel": "search_aug_kernel (tcgen05 GEMM, bias as an extra MMA k-step, fused packed top-k epilogue)", "bound": "tensor",
                     "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"],
                     "peak_source": pk["source"] + " bf16 burst (cuBLAS 8192^3); sustained %.1f" % pk["tflops_sustained"],
                     "frac_of_sustained": achieved / pk["tflops_sustained"],

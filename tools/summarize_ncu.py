@@ -19,9 +19,11 @@ for r in rows[hi + 1:]:
     v = float(r[idx["Metric Value"]].replace(",", ""))
     ns = v * {"ns": 1, "us": 1e3, "ms": 1e6, "s": 1e9}.get(r[idx["Metric Unit"]], 1)
     L.append((r[idx["Kernel Name"]], ns))
-tc = [i for i, (n, _) in enumerate(L) if "search_tc_kernel" in n]
-a, b = tc[4], tc[5]                      # one timed step: from the prepare kernels before one search to the next
-step = L[a - 2:b - 2]
+tc = [i for i, (n, _) in enumerate(L) if "search_aug_kernel" in n or "search_tc_kernel" in n]
+a, b = tc[4], tc[5]                      # one timed step: from the codebook refresh before one search to the next
+first = [i for i, (n, _) in enumerate(L) if "codebook_absmax_kernel" in n]
+sa, sb = max(i for i in first if i < a), max(i for i in first if i < b)
+step = L[sa:sb]
 tot = sum(x[1] for x in step)
 agg = collections.OrderedDict()
 for n, ns in step:
