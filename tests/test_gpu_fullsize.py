@@ -23,7 +23,17 @@ def _sample_check(x, c, idx, cos, n_sample=2048, seed=0):
     gap = (top2[:, 0] - top2[:, 1]).abs() / top2[:, 0].abs().clamp_min(1e-30)
     got = idx[0, rows.to(idx.device)].cpu()
     bad = (got != ref) & (gap >= 1e-6)
-    assert not bool(bad.any()), f"{int(bad.sum())} sampled rows differ from the oracle outside the tie exemption"
+    if bool(bad.any()):          # say what the exact CUDA scan and a second search make of the offending rows
+        from vqb200 import ops
+        br = rows[bad][:8]
+        ex, _, _ = ops.search(x[:, br.to(x.device)].contiguous(), c, None, cos, force_exact=True)
+        again, _, ws = ops.search(x, c, ops.prepare_codebook(c, cos), cos)
+        detail = [(int(r), int(got[bad][i]), int(ref[bad][i]), int(ex[0, i]), int(again[0, int(r)]), float(gap[bad][i]))
+                  for i, r in enumerate(br)]
+        raise AssertionError(f"{int(bad.sum())} sampled rows differ from the oracle outside the tie exemption; "
+                             f"(row, got, oracle, exact scan, second search, gap): {detail}; "
+                             f"whole batch vs second search: {int((again != idx).sum())} rows differ; "
+                             f"stats {ops.search_stats(ws)}")
     return int((got != ref).sum())
 
 

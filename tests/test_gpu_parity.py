@@ -337,6 +337,29 @@ def test_rvq_level_ema_matches_separate_kernels(d, K):
         assert torch.equal(a[4], ref_idx)
 
 
+def test_search_is_repeatable_through_a_shared_workspace():
+    """Searches of different shapes alternate through one workspace; every repetition must reproduce the first result
+    of its shape bit for bit (indices and scores): nothing may depend on timing (shared running minima, atomic
+    pair-list order) or on what the previous search left behind."""
+    from vqb200 import ops
+    g = torch.Generator(device=_dev()).manual_seed(3)
+    cases = []
+    for (N, K, d, dt) in [(40000, 1000, 72, torch.float32), (150000, 2048, 256, torch.bfloat16),
+                          (9000, 512, 64, torch.float32), (70000, 700, 512, torch.float32)]:
+        x = torch.randn(1, N, d, generator=g, device=_dev()).to(dt).contiguous()
+        c = torch.randn(1, K, d, generator=g, device=_dev()) * 0.5
+        cache = ops.prepare_codebook(c, False)
+        ref, rs, _ = ops.search(x, c, cache, False, want_score=True)
+        cases.append((x, c, cache, ref.clone(), rs.clone()))
+    for r in range(6):
+        for ci, (x, c, cache, ref, rs) in enumerate(cases):
+            want = (r + ci) % 2 == 0
+            idx, sc, _ = ops.search(x, c, cache, False, want_score=want)
+            assert torch.equal(idx, ref), f"repetition {r} of case {ci}: {int((idx != ref).sum())} indices changed"
+            if want:
+                assert torch.equal(sc, rs)
+
+
 def test_minkey_roundtrip_and_order():
     from vqb200 import ops
     g = torch.Generator().manual_seed(2)

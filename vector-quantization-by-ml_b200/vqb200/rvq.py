@@ -17,7 +17,7 @@ import torch.distributed as dist
 import torch.nn.functional as F
 from torch import nn
 
-from . import ops
+from . import _lib, ops
 from .vq import VectorQuantize
 
 
@@ -85,14 +85,26 @@ class ResidualVQ(nn.Module):
         B, n, d = x.shape
         N = B * n
         dev = x.device
-        res = [x.reshape(N, d).float().contiguous().clone(), torch.empty((N, d), dtype=torch.float32, device=dev)]
+        # level 0 reads the input itself (never written: every level writes its residual to another buffer)
+        x0 = _lib.aligned(x.reshape(N, d).float())
+        bufs = [torch.empty((N, d), dtype=torch.float32, device=dev) for _ in range(min(2, len(self.layers)))]
         out = torch.empty((N, d), dtype=torch.float32, device=dev)
         all_idx, all_loss = [], []
         Q = len(self.layers)
         prepared = False
+        # Dead-code check (reference codebooks.py:245-252) costs one host sync per level (0.75 ms of an 8.8 ms C4 step).
+        # A level's codebook is not read again in this forward unless it is shared, so the checks of all levels are
+        # answered by ONE sync after the loop; in the rare case that a code did die, that level's input is
+        # reconstructed bit-exactly from the indices (same IEEE operations as the level kernel) and the draws happen
+        # in level order, i.e. in the reference's RNG order.  Not possible while a later level still has to run its
+        # kmeans init (that draws too) or when the codebook is shared.
+        books = [l._codebook for l in self.layers]
+        defer = len({id(b) for b in books}) == Q and all(b.is_initialized for b in books)
+        pending, pre_emb = [], []
         for li, layer in enumerate(self.layers):
             cb = layer._codebook
-            cur, nxt = res[li & 1], res[(li + 1) & 1]
+            cur = x0 if li == 0 else bufs[(li - 1) % len(bufs)]
+            nxt = bufs[li % len(bufs)]
             flat = cur[None]
             mask_u8 = cb._expand_mask(mask, N)
             if not cb.is_initialized:
@@ -103,6 +115,8 @@ class ResidualVQ(nn.Module):
             idx, _, ws = ops.search(flat, emb, cb._codebook_cache(), cb.use_cosine_sim, latents_prepared=prepared)
             training = self.training and layer.training
             do_ema = training and cb.ema_update and not freeze_codebook
+            if defer:       # the codebook the gather uses (the EMA refresh below overwrites it in place)
+                pre_emb.append((emb.clone() if do_ema else emb, training))
             # the next level's operands are prepared in the same pass when its codebook cache is already final:
             # a different codebook object (not shared) that is initialised
             next_cache = None
@@ -123,12 +137,32 @@ class ResidualVQ(nn.Module):
                 ops.ema_apply(stats, cb.cluster_size.data, cb.embed_avg.data, cb.embeddings.data, 1 - cb.decay,
                               cb.eps_for_smoothing, cb.weights_l2norm)
                 cb._dirty = True
-                cb.expire_codes_(flat)
+                if not defer:
+                    cb.expire_codes_(flat)
+                elif cb.threshold_ema_dead_code != 0:
+                    pending.append((li, cb, (cb.cluster_size < cb.threshold_ema_dead_code).sum()))
             loss = torch.zeros(1, device=dev)
             if training and layer.has_commitment_loss:
                 loss = loss + loss_buf[0] * layer.commitment_weight
             all_idx.append(idx.reshape(B, n))
             all_loss.append(loss)
+        if pending:
+            dead = torch.stack([p[2] for p in pending]).tolist()        # the one host sync
+            if any(dead):
+                live = None if mask is None else books[0]._expand_mask(mask, N).bool()[:, None]
+                r, at = x0, 0
+                for (li, cb, _), m in zip(pending, dead):
+                    if not m:
+                        continue
+                    while at < li:                                       # replay levels at .. li-1 on the residual
+                        e, tr = pre_emb[at]
+                        cq = e[0][all_idx[at].reshape(-1)]
+                        q = r + (cq - r) if tr else cq
+                        if live is not None:
+                            q = torch.where(live, q, r)
+                        r = r - q
+                        at += 1
+                    cb.expire_codes_(r[None])
         return out.reshape(B, n, d), all_idx, all_loss
 
     # ------------------------------------------------------------------ forward (reference :134-269)
