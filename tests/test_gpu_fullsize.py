@@ -23,17 +23,31 @@ def _sample_check(x, c, idx, cos, n_sample=2048, seed=0):
     gap = (top2[:, 0] - top2[:, 1]).abs() / top2[:, 0].abs().clamp_min(1e-30)
     got = idx[0, rows.to(idx.device)].cpu()
     bad = (got != ref) & (gap >= 1e-6)
-    if bool(bad.any()):          # say what the exact CUDA scan and a second search make of the offending rows
-        from vqb200 import ops
-        br = rows[bad][:8]
-        ex, _, _ = ops.search(x[:, br.to(x.device)].contiguous(), c, None, cos, force_exact=True)
-        again, _, ws = ops.search(x, c, ops.prepare_codebook(c, cos), cos)
-        detail = [(int(r), int(got[bad][i]), int(ref[bad][i]), int(ex[0, i]), int(again[0, int(r)]), float(gap[bad][i]))
-                  for i, r in enumerate(br)]
-        raise AssertionError(f"{int(bad.sum())} sampled rows differ from the oracle outside the tie exemption; "
-                             f"(row, got, oracle, exact scan, second search, gap): {detail}; "
-                             f"whole batch vs second search: {int((again != idx).sum())} rows differ; "
-                             f"stats {ops.search_stats(ws)}")
+    if bool(bad.any()):
+        # The oracle is the reference's fp32 recipe: its own rounding noise on |x|^2 + |c|^2 - 2 x.c (d + 2 fp32
+        # additions at magnitude ~|x|^2) reaches ~1e-6 relative on the distance in the tail and depends on the host
+        # BLAS blocking (CPU model, thread count).  A row just outside the 1e-6 window may therefore be mis-ordered
+        # by the ORACLE.  Arbitrate with fp64 ground truth: a differing row is accepted only if the CUDA index is the
+        # fp64 argmin and the fp64 gap is still a near-tie (< 1e-5 relative); anything else fails with details.
+        br = rows[bad]
+        xs64, c64 = x[0, br.to(x.device)].double().cpu(), c[0].double().cpu()
+        s64 = xs64 @ c64.T if cos else -torch.cdist(xs64, c64)
+        arg64 = s64.argmax(-1)
+        t2 = s64.topk(2, -1).values
+        gap64 = (t2[:, 0] - t2[:, 1]).abs() / t2[:, 0].abs().clamp_min(1e-30)
+        wrong = (got[bad] != arg64) | (gap64 >= 1e-5)
+        if bool(wrong.any()):
+            from vqb200 import ops
+            ex, _, _ = ops.search(x[:, br.to(x.device)].contiguous(), c, None, cos, force_exact=True)
+            again, _, ws = ops.search(x, c, ops.prepare_codebook(c, cos), cos)
+            detail = [(int(r), int(got[bad][i]), int(ref[bad][i]), int(arg64[i]), int(ex[0, i]), int(again[0, int(r)]),
+                       float(gap[bad][i]), float(gap64[i])) for i, r in enumerate(br[:8])]
+            raise AssertionError(f"{int(wrong.sum())} sampled rows differ from the oracle AND from fp64 ground truth; "
+                                 f"(row, got, oracle, fp64 argmin, exact scan, second search, oracle gap, fp64 gap): "
+                                 f"{detail}; whole batch vs second search: {int((again != idx).sum())} rows differ; "
+                                 f"stats {ops.search_stats(ws)}")
+        print(f"note: {int(bad.sum())} sampled rows where the fp32 oracle mis-orders a near-tie just outside the "
+              f"1e-6 window (CUDA index == fp64 argmin, fp64 gaps {[float(v) for v in gap64]})")
     return int((got != ref).sum())
 
 
