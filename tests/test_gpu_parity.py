@@ -173,7 +173,17 @@ def test_search_matches_oracle(H, N, K, d, cos, scale, dtype):
     else:
         gap = torch.full(ref.shape, float("inf"))
     bad = (idx.cpu() != ref) & (gap >= 1e-6)
-    assert not bool(bad.any()), f"{int(bad.sum())} mismatches outside the tie exemption"
+    if bool(bad.any()):
+        # the fp32 oracle's own rounding can mis-order a near-tie just outside the window (host-BLAS dependent):
+        # accept such a row only if the CUDA index is the fp64 argmin and the fp64 gap is still a near-tie
+        hh, nn = bad.nonzero(as_tuple=True)
+        for h_, n_ in zip(hh.tolist(), nn.tolist()):
+            x64, c64 = x[h_, n_].double(), c[h_].double()
+            s64 = c64 @ x64 if cos else -(c64 - x64).pow(2).sum(-1).sqrt()
+            t2 = s64.topk(2).values
+            g64 = float((t2[0] - t2[1]).abs() / t2[0].abs().clamp_min(1e-30))
+            assert int(idx[h_, n_]) == int(s64.argmax()) and g64 < 1e-5, \
+                f"row ({h_},{n_}): got {int(idx[h_, n_])}, oracle {int(ref[h_, n_])}, fp64 argmin {int(s64.argmax())}, fp64 gap {g64}"
     # score: distance (euclid) or -similarity (dot) of the winner
     ref_score = -sim.gather(-1, idx.cpu()[..., None])[..., 0]
     assert torch.allclose(score.cpu(), ref_score, rtol=2e-5, atol=2e-5 * float(ref_score.abs().max()) + 1e-7)
