@@ -243,10 +243,6 @@ __device__ __forceinline__ float chunk_scores(const uint32_t (&r)[16], const flo
   } else {
     tmem_ld_wait();
   }
-  if (MODE == 2) {   // timing experiment: what the epilogue costs when the accumulator already IS the key
-#pragma unroll
-    for (int i = 0; i < 16; ++i) key[i] = __uint_as_float(r[i]);
-  } else
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const float4 b = bias4[i];          // shared memory, same address in every lane: broadcast
@@ -271,7 +267,6 @@ template <int PARITY, int CH, int MODE>
 __device__ __forceinline__ void chunk_rank(float (&key)[16], float cmin, uint32_t idmask, float tconst, float& m_run,
                                            float& t_run, int* row_slot, float (&a1)[2], float (&a2)[2],
                                            bool& any_slow, int dbg) {
-  if (MODE == 2) return;
   bool trig = __any_sync(0xffffffffu, cmin <= t_run);
   if (MODE == 1 && dbg) {   // bring-up knobs: 4 = never rank, 8 = always rank, 16 = count ranked / skipped chunks
     if (dbg & 4) trig = false;
@@ -364,7 +359,7 @@ struct Barriers {
 // CLUSTER = 1: independent CTAs.  CLUSTER = 2, !PAIR: two CTAs share every B stage by TMA multicast (each runs its own
 // 128-row MMAs).  CLUSTER = 2, PAIR: cta_group::2 -- one 256-row MMA per pair, each CTA stores only half of B (half the
 // shared-memory operand traffic per SM, twice the stages in flight).
-// MODE 0 = production (no knobs compiled in), 1 = bring-up knobs (VQB_TC_DEBUG), 2 = timing experiment (raw keys)
+// MODE 0 = production (no knobs compiled in), 1 = bring-up knobs (VQB_TC_DEBUG)
 template <int CLUSTER, bool PAIR, int MODE>
 __global__ void __launch_bounds__(kThreads, 1)
 search_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_c,
@@ -513,10 +508,6 @@ search_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
                 else umma_f16(d_tmem, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), kIdesc,
                               (kb | kk) != 0 ? 1u : 0u);
               }
-              if (MODE == 2 && kb == P.KB - 1) {   // stands in for the bias-augmentation k-step
-                if (PAIR) umma_f16_pair(d_tmem, adesc, bdesc, kIdescPair, 1u);
-                else umma_f16(d_tmem, adesc, bdesc, kIdesc, 1u);
-              }
               if (PAIR) umma_commit_pair(smem_u32(&bars->empty[stage]));
               else if (CLUSTER > 1) umma_commit_mc(smem_u32(&bars->empty[stage]), (uint16_t)((1u << CLUSTER) - 1u));
               else umma_commit(smem_u32(&bars->empty[stage]));
@@ -630,7 +621,7 @@ search_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
           if (nt + par < P.NT) {
             // r[] already holds (or is receiving) chunk 0 of this tile
             const uint32_t taddr = lane_addr + acc * (uint32_t)kBlockN;
-            if (MODE != 2) mbar_wait_t(smem_u32(&bars->bias_full[acc]), acc_ph, prof, w_bias);
+            mbar_wait_t(smem_u32(&bars->bias_full[acc]), acc_ph, prof, w_bias);
             const float4* bias4 = reinterpret_cast<const float4*>(bars->bias[acc] + quarter * 64);
             float key[16];
             float cmin;
@@ -1250,11 +1241,9 @@ int launch_search_tc(const __half* xb, const float* xinv, const __half* xaug, co
   if (rc) return rc;
   rc = make_map(&mc, cb, dp, Kp, H, kBlockN / cluster);
   if (rc) return rc;
-  const int kmode = P.dbg == 0 ? 0 : ((P.dbg & 128) ? 2 : 1);
 #define VQB_LAUNCH_MODE(C, PR)                                                                         \
-  (kmode == 0 ? launch_impl<C, PR, 0>(mx, mc, P, smem_bytes, grid, timing, st)                         \
-   : kmode == 1 ? launch_impl<C, PR, 1>(mx, mc, P, smem_bytes, grid, timing, st)                       \
-                : launch_impl<C, PR, 2>(mx, mc, P, smem_bytes, grid, timing, st))
+  (P.dbg == 0 ? launch_impl<C, PR, 0>(mx, mc, P, smem_bytes, grid, timing, st)                         \
+              : launch_impl<C, PR, 1>(mx, mc, P, smem_bytes, grid, timing, st))
   if (pair) return VQB_LAUNCH_MODE(2, true);
   if (cluster == 2) return VQB_LAUNCH_MODE(2, false);
   return VQB_LAUNCH_MODE(1, false);
