@@ -1,0 +1,50 @@
+"""Golden fixtures for the learnable-codebook path (reference vector_quantize_pytorch.py:261-273,362 with
+learnable_codebook=True, ema_update=False; optionally sync_update_v > 0): forward outputs and the gradients of a fixed
+scalar with respect to the input and the codebook, recorded from the UNMODIFIED reference.
+
+    python tests/golden/make_golden_learnable.py       # writes tests/golden/learnable/*.pt
+"""
+import os
+import sys
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import make_golden as MG  # noqa: E402  (einx stand-in + reference import)
+
+CASES = {
+    "learnable_plain": {"dim": 32, "K": 48, "shape": (3, 70, 32), "mask": False, "v": 0.0, "cw": 1.0},
+    "learnable_masked_v": {"dim": 16, "K": 20, "shape": (2, 33, 16), "mask": True, "v": 0.3, "cw": 0.25},
+}
+
+
+def main():
+    VectorQuantize, _, CodebookParams, _ = MG._import_reference()
+    for name, cfg in CASES.items():
+        torch.manual_seed(0)
+        cp = CodebookParams(dim=cfg["dim"], codebook_size=cfg["K"], learnable_codebook=True, ema_update=False,
+                            threshold_ema_dead_code=0)
+        vq = VectorQuantize(dim=cfg["dim"], codebook_params=cp, commitment_weight=cfg["cw"], sync_update_v=cfg["v"],
+                            sync_codebook=False).train()
+        g = torch.Generator().manual_seed(7)
+        with torch.no_grad():
+            vq._codebook.embeddings.copy_(torch.randn(vq._codebook.embeddings.shape, generator=g) * 0.7)
+        x = torch.randn(*cfg["shape"], generator=g).requires_grad_(True)
+        mask = None
+        if cfg["mask"]:
+            b, n = cfg["shape"][:2]
+            mask = torch.rand(b, n, generator=g) > 0.3
+        w = torch.randn(*cfg["shape"], generator=g)
+        init = vq._codebook.embeddings.detach().clone()
+        q, ind, loss = vq(x, mask=mask)
+        (q * w).sum().add(loss.sum() * 1.7).backward()
+        fx = {"cfg": cfg, "x": x.detach().clone(), "mask": mask, "w": w, "init_embeddings": init,
+              "quantize": q.detach().clone(), "indices": ind.clone(), "loss": loss.detach().clone(),
+              "grad_x": x.grad.clone(), "grad_embeddings": vq._codebook.embeddings.grad.clone()}
+        torch.save(fx, os.path.join(HERE, "learnable", name + ".pt"))
+        print(name, "loss", float(loss), "|grad_emb|", float(fx["grad_embeddings"].abs().max()))
+
+
+if __name__ == "__main__":
+    main()

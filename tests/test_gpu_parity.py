@@ -370,6 +370,42 @@ def test_search_is_repeatable_through_a_shared_workspace():
                 assert torch.equal(sc, rs)
 
 
+@pytest.mark.parametrize("name", ["learnable_plain", "learnable_masked_v"])
+def test_learnable_codebook_matches_reference_fixture(name):
+    """learnable_codebook=True, ema_update=False (+ sync_update_v): outputs and the gradients with respect to the input
+    and the codebook against the live reference (tests/golden/make_golden_learnable.py)."""
+    import os
+    from vqb200 import CodebookParams, VectorQuantize
+    fx = torch.load(os.path.join(gu.GOLDEN_DIR, "learnable", name + ".pt"), weights_only=False)
+    cfg = fx["cfg"]
+    cp = CodebookParams(dim=cfg["dim"], codebook_size=cfg["K"], learnable_codebook=True, ema_update=False,
+                        threshold_ema_dead_code=0)
+    vq = VectorQuantize(dim=cfg["dim"], codebook_params=cp, commitment_weight=cfg["cw"], sync_update_v=cfg["v"],
+                        sync_codebook=False).to(_dev()).train()
+    assert isinstance(vq._codebook.embeddings, torch.nn.Parameter)
+    with torch.no_grad():
+        vq._codebook.embeddings.copy_(fx["init_embeddings"])
+    vq._codebook.invalidate_cache()
+    x = fx["x"].to(_dev()).requires_grad_(True)
+    mask = fx["mask"].to(_dev()) if fx["mask"] is not None else None
+    q, ind, loss = vq(x, mask=mask)
+    (q * fx["w"].to(_dev())).sum().add(loss.sum() * 1.7).backward()
+    assert torch.equal(ind.cpu(), fx["indices"])
+    assert torch.equal(q.detach().cpu(), fx["quantize"])
+    assert torch.allclose(loss.detach().cpu(), fx["loss"], rtol=1e-6)
+    assert torch.allclose(x.grad.cpu(), fx["grad_x"], rtol=1e-5, atol=1e-7)
+    ge = vq._codebook.embeddings.grad.cpu()
+    assert gu.rel_err(ge, fx["grad_embeddings"]) <= 1e-5
+    # the codebook did not move (no EMA) and an optimizer step invalidates the search cache through the version counter
+    assert torch.equal(vq._codebook.embeddings.detach().cpu(), fx["init_embeddings"])
+    torch.optim.SGD(vq.parameters(), lr=0.5).step()
+    q2, ind2, _ = vq(fx["x"].to(_dev()), mask=mask)
+    from vqb200 import ops
+    ex, _, _ = ops.search(fx["x"].to(_dev()).reshape(1, -1, cfg["dim"]).contiguous(), vq._codebook.embeddings.detach(),
+                          None, False, force_exact=True)
+    assert torch.equal(ind2.reshape(-1), ex.reshape(-1))
+
+
 def test_minkey_roundtrip_and_order():
     from vqb200 import ops
     g = torch.Generator().manual_seed(2)

@@ -92,8 +92,8 @@ def test_no_cpu_fallback_and_unsupported_options_fail_loudly():
     vq = VectorQuantize(dim=8, codebook_params=CodebookParams(dim=8, codebook_size=4))
     with pytest.raises(RuntimeError, match="CUDA"):
         vq(torch.randn(1, 3, 8))
-    with pytest.raises(NotImplementedError):
-        Codebook(8, 4, learnable_codebook=True)
+    cb = Codebook(8, 4, learnable_codebook=True, ema_update=False)       # supported: embeddings is a Parameter
+    assert isinstance(cb.embeddings, torch.nn.Parameter) and "embeddings" in cb.state_dict()
     with pytest.raises(NotImplementedError):
         Codebook(8, 4, use_affine=True)
     with pytest.raises(NotImplementedError):
@@ -101,9 +101,13 @@ def test_no_cpu_fallback_and_unsupported_options_fail_loudly():
     with pytest.raises(ValueError):
         Codebook(8, 4, transform_input="tanh")
     for kw in (dict(codebook_diversity_loss_weight=0.1), dict(orthogonal_reg_weight=1.0),
-               dict(commitment_use_cross_entropy_loss=True), dict(sync_update_v=0.5)):
+               dict(commitment_use_cross_entropy_loss=True), dict(in_place_codebook_optimizer=torch.optim.SGD)):
         with pytest.raises(NotImplementedError):
             VectorQuantize(dim=8, codebook_params=CodebookParams(dim=8, codebook_size=4), **kw)
+    with pytest.raises(AssertionError):          # reference: sync_update_v needs a learnable codebook
+        VectorQuantize(dim=8, codebook_params=CodebookParams(dim=8, codebook_size=4), sync_update_v=0.5)
+    with pytest.raises(AssertionError):          # reference: learnable codebook is not compatible with the EMA update
+        VectorQuantize(dim=8, codebook_params=CodebookParams(dim=8, codebook_size=4, learnable_codebook=True))
 
 
 def test_product_code_never_imports_the_oracle():

@@ -3,9 +3,10 @@
 Same constructor, same persistent buffers (``embeddings`` (H,K,d), ``embed_avg`` (H,K,d),
 ``cluster_size`` (H,K), fp32) and the same ``forward(x, mask, freeze_codebook)`` contract;
 the numeric work (search, gather, EMA statistics, refresh, expiry scatter) runs in
-libvqb200.so.  Options that are off the named hot path (learnable codebook, affine
-re-parametrisation, stochastic gumbel sampling) raise NotImplementedError -- there is
-no silent fallback.
+libvqb200.so.  Options that are off the named hot path (affine re-parametrisation,
+stochastic gumbel sampling) raise NotImplementedError -- there is
+no silent fallback.  ``learnable_codebook=True`` makes ``embeddings`` a Parameter that receives the gradient
+of the commitment loss / of the gathered codes (a segmented sum over the rows of each code).
 """
 from __future__ import annotations
 
@@ -45,8 +46,6 @@ class Codebook(nn.Module):
             if val not in ("identity", "l2norm"):
                 # the reference does `raise f"..."` here (a TypeError); keep the intent, not the bug
                 raise ValueError(f"The option {val} for {name} is not implemented")
-        if learnable_codebook:
-            raise NotImplementedError("vqb200: learnable_codebook is outside the accelerated EMA path")
         if use_affine:
             raise NotImplementedError("vqb200: use_affine is outside the accelerated EMA path")
         gp = asdict(gumbel_params) if is_dataclass(gumbel_params) else dict(gumbel_params)
@@ -73,7 +72,7 @@ class Codebook(nn.Module):
         # (codebooks.py:164-166); treat a missing KmeansParameters as its defaults instead
         self._kmeans_sync = bool((self.kmeans_params or {"sync": True})["sync"])
         self.distributed_replace_codes = distributed_replace_codes
-        self.learnable_codebook = False
+        self.learnable_codebook = bool(learnable_codebook)
         self.use_affine = False
 
         init = torch.zeros(num_codebooks, codebook_size, dim) if initialization_by_kmeans else \
@@ -83,7 +82,10 @@ class Codebook(nn.Module):
         self.is_initialized = not initialization_by_kmeans
         self.register_buffer("cluster_size", torch.zeros(num_codebooks, codebook_size))
         self.register_buffer("embed_avg", init.clone())
-        self.register_buffer("embeddings", init)
+        if self.learnable_codebook:          # reference codebooks.py:186-190: a Parameter, trained by the user's optimizer
+            self.embeddings = nn.Parameter(init)
+        else:
+            self.register_buffer("embeddings", init)
 
         # derived, non-persistent: bf16 copy + norms for the tensor-core search
         self._cache: Optional[torch.Tensor] = None
@@ -231,8 +233,13 @@ class Codebook(nn.Module):
         training = self.training
         commit = None
         update = training and self.ema_update and not freeze_codebook
+        # learnable codebook (reference codebooks.py:375-377, vector_quantize_pytorch.py:262-268): the commitment loss
+        # and the gathered codes are differentiable with respect to `embeddings`
+        emb_param = self.embeddings if (self.learnable_codebook and training and not freeze_codebook
+                                        and torch.is_grad_enabled() and self.embeddings.requires_grad) else None
         # un-masked training step: gather/ST/loss and the EMA sums share ONE pass over the latents
-        fused = update and mask_u8 is None and self.fused_quantize_ema and ops.quantize_ema_supported(d)
+        fused = update and mask_u8 is None and self.fused_quantize_ema and ops.quantize_ema_supported(d) \
+            and emb_param is None
         stats = None
         if fused and fuse_st:
             quant, commit, stats = ops.quantize_training(flat, emb, idx, None, want_commit, ema=True, bound_ws=ws)
@@ -240,7 +247,10 @@ class Codebook(nn.Module):
             with torch.no_grad():
                 quant, _, stats = ops.quantize_ema(flat, emb, idx, False, False, bound_ws=ws)
         elif fuse_st and training:
-            quant, commit, _ = ops.quantize_training(flat, emb, idx, mask_u8, want_commit)
+            quant, commit, _ = ops.quantize_training(flat, emb if emb_param is None else emb_param, idx, mask_u8,
+                                                     want_commit)
+        elif emb_param is not None:
+            quant = ops.gather_codes(emb_param, idx)
         else:
             with torch.no_grad():
                 quant, _ = ops.gather_st_loss(flat, emb, idx, None, False, False)

@@ -191,6 +191,13 @@ class _QuantizeST(torch.autograd.Function):
             grad_q = torch.zeros((H, N, d), dtype=torch.float32, device=x.device)
         grad_q = grad_q.contiguous().float()
         none = (None,) * 6
+        g_emb = None
+        if ctx.needs_input_grad[1] and ctx.want_loss and grad_commit is not None:
+            # learnable codebook: d mse(C[idx], x) / d C[k] = 2 (n_k C[k] - sum of the rows assigned to k) / (rows * d),
+            # from the same deterministic segmented sums as the EMA statistics
+            st = ema_reduce(x, idx, mask_u8 if ctx.has_mask else None, K)
+            g_emb = (grad_commit.float() * (2.0 / d) / loss[1]) * (st[..., d:] * embeddings.detach() - st[..., :d])
+        none = (g_emb,) + (None,) * 5
         if not ctx.want_loss or grad_commit is None:
             return (grad_q.to(x.dtype),) + none
         # device scalar: grad_commit * 2 / (rows_used * d)   (no host sync)
@@ -200,6 +207,29 @@ class _QuantizeST(torch.autograd.Function):
                                                L.ptr(idx), L.ptr(mask_u8) if ctx.has_mask else 0, 1.0, L.ptr(gx),
                                                H, N, K, d, L.stream_ptr(x.device)), "vqb_st_commit_backward")
         return (gx.to(x.dtype),) + none
+
+
+class _GatherCodes(torch.autograd.Function):
+    """Codebook.forward with a learnable codebook: quantize = C[idx], d/dC[k] = sum of the incoming rows assigned to k."""
+
+    @staticmethod
+    def forward(ctx, embeddings, idx):
+        H, K, d = embeddings.shape
+        e = embeddings.detach()
+        q = torch.stack([e[h][idx[h]] for h in range(H)], 0)      # plain gather; the backward is the kernel work
+        ctx.save_for_backward(idx)
+        ctx.K = K
+        return q
+
+    @staticmethod
+    def backward(ctx, grad_q):
+        (idx,) = ctx.saved_tensors
+        st = ema_reduce(grad_q.contiguous().float(), idx, None, ctx.K)
+        return st[..., :-1].contiguous(), None
+
+
+def gather_codes(embeddings: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+    return _GatherCodes.apply(embeddings, idx)
 
 
 def quantize_training(x, embeddings, idx, mask_u8, want_loss, ema: bool = False, bound_ws=None):

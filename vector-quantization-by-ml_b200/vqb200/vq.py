@@ -3,8 +3,9 @@
 Same constructor arguments and ``forward`` returns.  The layout glue (channel-first, images/video,
 multi-head, projections, masks) is host code; search, gather + straight-through + commitment loss
 and the EMA update are CUDA kernels behind ``Codebook``.  Options that need the dense N x K
-similarity matrix (cross-entropy to given indices, CE commitment, diversity loss) or a learnable
-codebook (orthogonal regularisation, in-place optimizer, sync_update_v) raise NotImplementedError.
+similarity matrix (cross-entropy to given indices, CE commitment, diversity loss), orthogonal regularisation
+(broken in the reference itself) and the in-place codebook optimizer raise NotImplementedError; a learnable
+codebook (`learnable_codebook=True, ema_update=False`, optionally `sync_update_v`) is supported.
 """
 from __future__ import annotations
 
@@ -56,13 +57,12 @@ class VectorQuantize(nn.Module):
         if commitment_use_cross_entropy_loss:
             unsupported.append("commitment_use_cross_entropy_loss (needs the dense N x K similarities)")
         if orthogonal_reg_weight > 0.0:
-            unsupported.append("orthogonal_reg_weight (needs a learnable codebook)")
+            unsupported.append("orthogonal_reg_weight (the reference itself raises AttributeError on this path: "
+                               "vector_quantize_pytorch.py:367 reads the non-existent `_codebook.embed`)")
         if codebook_diversity_loss_weight > 0.0:
             unsupported.append("codebook_diversity_loss_weight (needs the dense N x K similarities)")
         if in_place_codebook_optimizer is not None:
-            unsupported.append("in_place_codebook_optimizer (needs a learnable codebook)")
-        if sync_update_v > 0.0:
-            unsupported.append("sync_update_v (needs a learnable codebook)")
+            unsupported.append("in_place_codebook_optimizer (a second search inside forward; not built)")
         if unsupported:
             raise NotImplementedError("vqb200.VectorQuantize: outside the accelerated EMA path: " + "; ".join(unsupported))
 
@@ -76,6 +76,9 @@ class VectorQuantize(nn.Module):
         self.learnable_codebook = codebook_params.learnable_codebook
         assert not (codebook_params.ema_update and codebook_params.learnable_codebook), \
             "learnable codebook not compatible with EMA update"
+        assert 0 <= sync_update_v <= 1.0
+        assert not (sync_update_v > 0.0 and not codebook_params.learnable_codebook), "learnable codebook must be turned on"
+        self.sync_update_v = sync_update_v
         kw = asdict(self.codebook_params)
         self._codebook = Codebook(**kw)
         self.channel_last = channel_last
@@ -91,7 +94,8 @@ class VectorQuantize(nn.Module):
     def codebook(self, codes):
         if not self.separate_codebook_per_head:
             codes = codes[None]
-        self._codebook.embeddings.copy_(codes)
+        with torch.no_grad():
+            self._codebook.embeddings.copy_(codes)
         self._codebook.invalidate_cache()
 
     def get_codes_from_indices(self, indices):
@@ -145,6 +149,9 @@ class VectorQuantize(nn.Module):
                                                           want_commit=want_commit)
         if x.ndim < 4:
             quantize, embed_ind = quantize[0], embed_ind[0]
+        if training and self.sync_update_v > 0.0:
+            # reference :275-279: value unchanged, the gradient to the input is scaled by (1 + v)
+            quantize = quantize + self.sync_update_v * (quantize - quantize.detach())
 
         commit_loss = self.zero
         if multi:
