@@ -94,6 +94,13 @@ int    vqb_search_timing(float* host_ms, int cap);
 /* ---- l2 normalisation of rows (transform_input="l2norm") ------------------------------
  * Replaces vector_quantize_pytorch.py:221 -> utils/losses.py:19 (F.normalize, eps 1e-12). */
 int vqb_l2norm_rows(const void* x, int x_dtype, float* out, int64_t rows, int d, void* stream);
+/* The same normalisation AND the search's operand preparation in one pass over x: writes out = x / |x| (bit-identical
+ * to vqb_l2norm_rows) and, into search_ws, the scaled fp16 copy / row scales / bias operands / row statistics of
+ * `out`, so that the following vqb_search(out, ..., VQB_SEARCH_LATENTS_PREPARED, search_ws) skips its own pass.
+ * cache: the codebook cache that search will use.  d % 4 == 0 and d_pad <= 512 (vqb_l2norm_prepare_supported). */
+int vqb_l2norm_prepare_supported(int d);
+int vqb_l2norm_prepare(const void* x, int x_dtype, float* out, int64_t H, int64_t N, int K, int d,
+                       const void* cache, void* search_ws, size_t ws_bytes, void* stream);
 
 /* ---- gather + straight-through + commitment loss --------------------------------------
  * Replaces codebooks.py:393-397 (one-hot einsum / batched_embedding gather),

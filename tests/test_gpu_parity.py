@@ -406,6 +406,85 @@ def test_learnable_codebook_matches_reference_fixture(name):
     assert torch.equal(ind2.reshape(-1), ex.reshape(-1))
 
 
+@pytest.mark.parametrize("cos", [False, True])
+@pytest.mark.parametrize("case", ["mixed_row_scales", "zero_codebook", "huge_codes_tiny_rows", "huge_rows_tiny_codes",
+                                  "padded_codes", "constant_rows"])
+def test_search_scale_extremes_match_exact_scan(case, cos):
+    """The bias k-step folds s_row 2^-q and s_c 2^q |c|^2/2 into fp16 operands: rows / codebooks at the edges of those
+    ranges (zero rows, 10 orders of magnitude between rows, all-zero codebook, bias far larger or smaller than the dot
+    products, padded code columns) must still give the exact scan's answer, index and score, bit for bit."""
+    from vqb200 import ops
+    g = torch.Generator().manual_seed(sum(map(ord, case)))
+    N, K, d = 3000, 1024, 128
+    x = torch.randn(1, N, d, generator=g)
+    c = torch.randn(1, K, d, generator=g) * 0.5
+    if case == "mixed_row_scales":
+        scale = 10.0 ** torch.randint(-6, 5, (N, 1), generator=g).float()
+        x = x * scale
+        x[0, :50] = 0.0
+        x[0, 50:60] = 1e-30
+    elif case == "zero_codebook":
+        c = torch.zeros(1, K, d)
+        c[0, 5] = 1e-3
+    elif case == "huge_codes_tiny_rows":
+        c, x = c * 1e3, x * 1e-4
+    elif case == "huge_rows_tiny_codes":
+        c, x = c * 1e-3, x * 1e4
+    elif case == "padded_codes":
+        K = 1000
+        c = c[:, :K].contiguous()
+    elif case == "constant_rows":
+        x = torch.ones(1, N, d) * torch.linspace(-3, 3, N)[None, :, None]
+    if cos:
+        c = torch.nn.functional.normalize(c, dim=-1) if case != "zero_codebook" else c
+    xd, cd = x.to(_dev()).contiguous(), c.to(_dev()).contiguous()
+    cache = ops.prepare_codebook(cd, cos)
+    idx, score, ws = ops.search(xd, cd, cache, cos, want_score=True)
+    st = ops.search_stats(ws)
+    ex, es, _ = ops.search(xd, cd, None, cos, force_exact=True, want_score=True)
+    assert st["tensor_core_pass"] == 1
+    assert torch.equal(idx, ex), f"{case}: {int((idx != ex).sum())} rows differ from the exact scan; stats {st}"
+    assert torch.equal(score, es)
+
+
+def test_cosine_input_gradient_passes_through_the_normalisation():
+    """transform_input="l2norm": d loss / d x must include the Jacobian of x -> x / |x| (reference: F.normalize under
+    autograd), and the no-grad path (normalisation fused with the search's operand preparation) must give the same
+    forward results as the differentiable one."""
+    from vqb200 import CodebookParams, VectorQuantize
+    torch.manual_seed(0)
+    cp = CodebookParams(dim=64, codebook_size=96, use_cosine_sim=True, transform_input="l2norm",
+                        weights_regularization="l2norm", threshold_ema_dead_code=0)
+    vq = VectorQuantize(dim=64, codebook_params=cp, sync_codebook=False).to(_dev()).train()
+    g = torch.Generator().manual_seed(4)
+    x = (torch.randn(3, 200, 64, generator=g) * 2.5)
+    w = torch.randn(3, 200, 64, generator=g)
+    emb0 = vq._codebook.embeddings.clone()
+    xd = x.to(_dev()).requires_grad_(True)
+    q, ind, loss = vq(xd)
+    (q * w.to(_dev())).sum().add(loss.sum() * 0.9).backward()
+    # torch restatement with the indices the module chose
+    xr = x.clone().requires_grad_(True)
+    xn = torch.nn.functional.normalize(xr, p=2, dim=-1)
+    cq = emb0[0].cpu()[ind.cpu()]
+    qr = xn + (cq - xn).detach()
+    lr = torch.nn.functional.mse_loss(cq, xn)
+    (qr * w).sum().add(lr * 0.9).backward()
+    # (torch's CUDA and CPU normalisations reduce in different orders: last-bit differences in x^ are expected here)
+    assert torch.allclose(q.detach().cpu(), qr.detach(), rtol=1e-6, atol=1e-7)
+    assert torch.allclose(loss.detach().cpu(), lr.detach().reshape(1), rtol=1e-5)
+    assert torch.allclose(xd.grad.cpu(), xr.grad, rtol=1e-4, atol=1e-6)
+    # same forward through the fused no-grad path (fresh module with the same initial codebook)
+    vq2 = VectorQuantize(dim=64, codebook_params=cp, sync_codebook=False).to(_dev()).train()
+    vq2._codebook.embeddings.copy_(emb0); vq2._codebook.embed_avg.copy_(emb0); vq2._codebook.invalidate_cache()
+    with torch.no_grad():
+        q2, ind2, loss2 = vq2(x.to(_dev()))
+    assert float((ind2 == ind).float().mean()) > 0.999
+    same = (ind2 == ind)[..., None].expand_as(q2)
+    assert torch.allclose(q2[same], q.detach()[same], rtol=1e-6, atol=1e-7) and torch.allclose(loss2, loss.detach(), rtol=1e-5)
+    assert torch.allclose(vq2._codebook.embeddings, vq._codebook.embeddings, rtol=1e-4, atol=1e-6)
+
+
 def test_minkey_roundtrip_and_order():
     from vqb200 import ops
     g = torch.Generator().manual_seed(2)

@@ -84,6 +84,7 @@ struct SearchLayout {
   size_t off_xb;      // fp16 [H][N][dp]  = fp16(x * s_row), zero padded
   size_t off_xinv;    // f32  [H][N]      = 1 / s_row (exact power of two); NEGATIVE marks a row whose bias operand
                       //                    s_row 2^-q is not an fp16 number: such rows are rescanned exactly
+  size_t off_xn2;     // f32  [H][N]      upper bound of |x_row|^2: sizes the window of fp32 distance ties (resolve)
   size_t off_xaug;    // fp16 [H][N][8]   = {a, a, a, 0, ...}, a = s_row 2^-q: the latent side of the bias k-step
   size_t off_keys;    // u64  [H][N]      packed (score, index) min-keys of rows being rescanned
   size_t off_cand;    // {f32 key, i32 code} [H][N][kNumCand]
@@ -105,6 +106,7 @@ inline SearchLayout search_layout(int64_t H, int64_t N, int K, int d) {
   L.off_cnt = o;  o += align_up((size_t)H * 12);
   L.off_xb = o;   o += align_up((size_t)H * N * L.dp * 2);
   L.off_xinv = o; o += align_up((size_t)H * N * 4);
+  L.off_xn2 = o;  o += align_up((size_t)H * N * 4);
   L.off_xaug = o; o += align_up((size_t)H * N * 16);
   L.off_keys = o; o += align_up((size_t)H * N * 8);
   L.off_cand = o; o += align_up((size_t)H * N * kNumCand * 8);
@@ -236,15 +238,17 @@ inline int dtype_size(int dt) { return dt == VQB_F32 ? 4 : 2; }
 // ---- internal launchers (defined across the .cu files) --------------------------------------
 // chdr: per-codebook cache header (nullable: no bias operand is written then); rows_per_head maps a row to its header
 int launch_prepare_latents(const void* x, int x_dtype, int64_t rows, int64_t rows_per_head, int d, int dp,
-                           const float* chdr, __half* xb, float* xinv, __half* xaug, uint32_t* scal, cudaStream_t st);
+                           const float* chdr, __half* xb, float* xinv, float* xn2, __half* xaug, uint32_t* scal,
+                           cudaStream_t st);
 int launch_make_bias(const void* cache, const CacheLayout& CL, int64_t H, int K, int metric,
                      uint32_t* scal, float* bias, float* err, __half* caug, cudaStream_t st);
 // xaug / caug: the bias k-step operands (both NULL: bias added in the epilogue from `bias`)
 // aug_mode (search_tc_aug_mode): 0 = bias added in the epilogue from `bias`; 1 = bias as an extra MMA k-step;
 // 2 = same kernel without the k-step (dot metric, no padded codes)
-int launch_search_tc(const __half* xb, const float* xinv, const __half* xaug, const __half* cb, const __half* caug,
-                     const float* chdr, const float* bias, int aug_mode, int64_t H, int64_t N, int K, int dp,
-                     void* cand, uint32_t* scal, bool timing, cudaStream_t st);
+// xn2 / tie: per-row bound of |x|^2 and the tie-window coefficient (kTieSlack for the Euclidean metric, 0 for dot)
+int launch_search_tc(const __half* xb, const float* xinv, const float* xn2, float tie, const __half* xaug,
+                     const __half* cb, const __half* caug, const float* chdr, const float* bias, int aug_mode,
+                     int64_t H, int64_t N, int K, int dp, void* cand, uint32_t* scal, bool timing, cudaStream_t st);
 int search_tc_aug_mode(int64_t N, int K, int metric);
 
 int launch_loss_finalize(const double* part, const long long* cntp, int nblocks, int d, float* loss_out,
@@ -259,6 +263,16 @@ __device__ __forceinline__ float clamp_row_scale(float& s, float two_q, float tw
   if (s > cap) s = cap;
   const float a = s * two_mq;
   return a >= 5.9604645e-8f ? a : 0.f;          // 2^-24
+}
+
+// The reference's distance is sqrtf(max(float(|x|^2 + |c|^2 - 2 x.c), 0)): fp32 rounding of the squared distance and of
+// the root collapses codes whose exact scores differ by less than ~2^-21 of |x - c|^2 / 2 into EQUAL distances, and
+// torch.argmax then takes the lowest index.  Every code that can tie with the winner must therefore be a candidate:
+// the window is widened by kTieSlack * (bound of |x|^2) (+ the |score| part, covered by the packing slack).
+constexpr float kTieSlack = 5.0e-7f;
+// upper bound of |x|^2 from |x~|^2 and |x - x~|^2
+__device__ __forceinline__ float row_norm2_bound(float n2, float r2) {
+  return (n2 + 2.f * sqrtf(n2 * r2) + r2) * 1.0001f;
 }
 
 // pow2_scale(m) from the exponent field (same value for every input, a handful of integer instructions)

@@ -328,6 +328,7 @@ struct RvqExtra {
   float* q_level;         // (N,d) this level's output, nullable
   __half* next_xb;        // nullable: no next level
   float* next_xinv;
+  float* next_xn2;
   __half* next_xaug;
   uint32_t* next_scal;
   const float* next_chdr;
@@ -523,6 +524,7 @@ quantize_ema_kernel(const T* __restrict__ x, const float* __restrict__ cb, const
           n2 += __shfl_xor_sync(0xffffffffu, n2, o2);
           r2 += __shfl_xor_sync(0xffffffffu, r2, o2);
         }
+        if (gl == 0 && live) R.next_xn2[rr[u]] = row_norm2_bound(n2, r2);
         max_n2 = fmaxf(max_n2, n2);
         max_r2 = fmaxf(max_r2, r2);
       }
@@ -915,6 +917,7 @@ extern "C" int vqb_rvq_level_ema(const float* residual_in, float* residual_out, 
     R.next_xb = (__half*)((char*)next_ws + SL.off_xb);
     R.next_xaug = (__half*)((char*)next_ws + SL.off_xaug);
     R.next_xinv = (float*)((char*)next_ws + SL.off_xinv);
+    R.next_xn2 = (float*)((char*)next_ws + SL.off_xn2);
     R.next_scal = (uint32_t*)((char*)next_ws + SL.off_scal);
     R.next_chdr = (const float*)((const char*)next_cache + cache_layout(1, K, d).off_hdr);
   }

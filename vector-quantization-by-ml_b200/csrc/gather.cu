@@ -226,7 +226,7 @@ rvq_level_kernel(const float* res_in, float* res_out, const float* __restrict__ 
                  float* __restrict__ qout, int64_t N, int K, int d, int dp, double* __restrict__ part,
                  long long* __restrict__ cntp, __half* __restrict__ next_xb, float* __restrict__ next_xinv,
                  uint32_t* __restrict__ next_scal, __half* __restrict__ next_xaug,
-                 const float* __restrict__ next_chdr) {
+                 const float* __restrict__ next_chdr, float* __restrict__ next_xn2) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int wpb = kGatherThreads / 32;
   double sqd = 0.0;
@@ -329,6 +329,7 @@ rvq_level_kernel(const float* res_in, float* res_out, const float* __restrict__ 
       }
       n2 = warp_sum(n2);
       r2 = warp_sum(r2);
+      if (lane == 0) next_xn2[row] = row_norm2_bound(n2, r2);
       max_n2 = fmaxf(max_n2, n2);
       max_r2 = fmaxf(max_r2, r2);
     }
@@ -443,6 +444,7 @@ extern "C" int vqb_rvq_level(const float* residual_in, float* residual_out, cons
   __half* nxb = nullptr;
   __half* nxaug = nullptr;
   float* nxinv = nullptr;
+  float* nxn2 = nullptr;
   uint32_t* nscal = nullptr;
   const float* nchdr = nullptr;
   const int dp = d_pad(d);
@@ -455,6 +457,7 @@ extern "C" int vqb_rvq_level(const float* residual_in, float* residual_out, cons
     nxb = (__half*)((char*)next_ws + SL.off_xb);
     nxaug = (__half*)((char*)next_ws + SL.off_xaug);
     nxinv = (float*)((char*)next_ws + SL.off_xinv);
+    nxn2 = (float*)((char*)next_ws + SL.off_xn2);
     nscal = (uint32_t*)((char*)next_ws + SL.off_scal);
     nchdr = (const float*)((const char*)next_cache + cache_layout(1, K, d).off_hdr);
     VQB_CUDA_TRY(cudaMemsetAsync(nscal, 0, 8, st));
@@ -465,7 +468,7 @@ extern "C" int vqb_rvq_level(const float* residual_in, float* residual_out, cons
   if (N > 0) {
     rvq_level_kernel<<<grid, kGatherThreads, 0, st>>>(residual_in, residual_out, codebook, idx, mask, training, first_level,
                                                       quantized_out, q_out, N, K, d, dp, part, cntp,
-                                                      nxb, nxinv, nscal, nxaug, nchdr);
+                                                      nxb, nxinv, nscal, nxaug, nchdr, nxn2);
     VQB_LAUNCH_CHECK();
   }
   loss_finalize_kernel<<<1, 256, 0, st>>>(part, cntp, N > 0 ? grid : 0, d, loss_out);

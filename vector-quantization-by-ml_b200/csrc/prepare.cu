@@ -89,7 +89,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 prepare_latents4_kernel(const T* __restrict__ x, int64_t rows, int64_t rows_per_head, bool single_head, int d, int dp,
                         const float* __restrict__ chdr, __half* __restrict__ xb, float* __restrict__ xinv,
-                        __half* __restrict__ xaug, uint32_t* __restrict__ scal) {
+                        float* __restrict__ xn2, __half* __restrict__ xaug, uint32_t* __restrict__ scal) {
   constexpr int U = sizeof(T) == 2 ? 8 : 4;       // rows in flight per warp (32 registers of raw data)
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
@@ -99,7 +99,7 @@ prepare_latents4_kernel(const T* __restrict__ x, int64_t rows, int64_t rows_per_
   for (int64_t row0 = ((int64_t)blockIdx.x * wpb + (threadIdx.x >> 5)) * U; row0 < rows;
        row0 += (int64_t)gridDim.x * wpb * U) {
     Raw8<T> raw[U];
-    float my_is = 0.f, my_a = 0.f;
+    float my_is = 0.f, my_a = 0.f, my_n2b = 0.f;
     float two_q = 1.f, two_mq = 1.f;
     if (chdr) {   // the rows of an iteration share a codebook (rows_per_head % 8 == 0 is checked by the launcher)
       const float* hd = chdr + (single_head ? 0 : (uint32_t)row0 / (uint32_t)rows_per_head) * kHdrFloats;
@@ -166,11 +166,13 @@ prepare_latents4_kernel(const T* __restrict__ x, int64_t rows, int64_t rows_per_
         n2 = warp_sum(n2);
         r2 = warp_sum(r2);
       }
+      if (lane == u) my_n2b = row_norm2_bound(n2, r2);
       max_n2 = fmaxf(max_n2, n2);
       max_r2 = fmaxf(max_r2, r2);
     }
     if (lane < U && row0 + lane < rows) {          // scales + bias operands of the U rows in one coalesced store each
       xinv[row0 + lane] = my_is;
+      xn2[row0 + lane] = my_n2b;
       if (xaug) {
         const uint32_t aa = (uint32_t)__half_as_ushort(__float2half_rn(my_a));
         *reinterpret_cast<uint4*>(xaug + (row0 + lane) * 8) = make_uint4(aa | (aa << 16), aa, 0u, 0u);
@@ -196,7 +198,8 @@ template <typename T>
 __global__ void __launch_bounds__(256, 3)
 prepare_latents_narrow_kernel(const T* __restrict__ x, int64_t rows, int64_t rows_per_head, bool single_head, int d,
                               int dp, const float* __restrict__ chdr, __half* __restrict__ xb,
-                              float* __restrict__ xinv, __half* __restrict__ xaug, uint32_t* __restrict__ scal) {
+                              float* __restrict__ xinv, float* __restrict__ xn2, __half* __restrict__ xaug,
+                              uint32_t* __restrict__ scal) {
   constexpr int U = sizeof(T) == 2 ? 8 : 4;
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
@@ -260,6 +263,7 @@ prepare_latents_narrow_kernel(const T* __restrict__ x, int64_t rows, int64_t row
         n2 += __shfl_xor_sync(0xffffffffu, n2, o2);
         r2 += __shfl_xor_sync(0xffffffffu, r2, o2);
       }
+      if (live && gl == 0) xn2[row] = row_norm2_bound(n2, r2);
       max_n2 = fmaxf(max_n2, n2);
       max_r2 = fmaxf(max_r2, r2);
     }
@@ -287,7 +291,7 @@ prepare_latents_narrow_kernel(const T* __restrict__ x, int64_t rows, int64_t row
 template <typename T>
 __global__ void prepare_latents_kernel(const T* __restrict__ x, int64_t rows, int64_t rows_per_head, int d, int dp,
                                        const float* __restrict__ chdr, __half* __restrict__ xb,
-                                       float* __restrict__ xinv, __half* __restrict__ xaug,
+                                       float* __restrict__ xinv, float* __restrict__ xn2, __half* __restrict__ xaug,
                                        uint32_t* __restrict__ scal) {
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
@@ -362,6 +366,7 @@ __global__ void prepare_latents_kernel(const T* __restrict__ x, int64_t rows, in
     }
     n2 = warp_sum(n2);
     r2 = warp_sum(r2);
+    if (lane == 0) xn2[row] = row_norm2_bound(n2, r2);
     max_n2 = fmaxf(max_n2, n2);
     max_r2 = fmaxf(max_r2, r2);
   }
@@ -382,7 +387,7 @@ __global__ void prepare_latents_kernel(const T* __restrict__ x, int64_t rows, in
 }
 
 int launch_prepare_latents(const void* x, int x_dtype, int64_t rows, int64_t rows_per_head, int d, int dp,
-                           const float* chdr, __half* xb, float* xinv, __half* xaug, uint32_t* scal,
+                           const float* chdr, __half* xb, float* xinv, float* xn2, __half* xaug, uint32_t* scal,
                            cudaStream_t st) {
   if (rows_per_head < 1) rows_per_head = 1;
   VQB_REQUIRE(dp <= 512, VQB_ERR_UNSUPPORTED, "prepare_latents: d_pad %d > 512", dp);
@@ -401,16 +406,16 @@ int launch_prepare_latents(const void* x, int x_dtype, int64_t rows, int64_t row
     VQB_DISPATCH_DTYPE(x_dtype, T,
       prepare_latents_narrow_kernel<T><<<(unsigned)blocks, warps * 32, 0, st>>>((const T*)x, rows, rows_per_head,
                                                                                 rows_per_head >= rows, d, dp, chdr,
-                                                                                xb, xinv, xaug, scal));
+                                                                                xb, xinv, xn2, xaug, scal));
   } else if ((d & 7) == 0 && d <= 256 && (rows_per_head >= rows || (rows_per_head % 8 == 0 && rows < (1ll << 32)))) {
     VQB_DISPATCH_DTYPE(x_dtype, T,
       prepare_latents4_kernel<T><<<(unsigned)blocks, warps * 32, 0, st>>>((const T*)x, rows, rows_per_head,
                                                                           rows_per_head >= rows, d, dp, chdr,
-                                                                          xb, xinv, xaug, scal));
+                                                                          xb, xinv, xn2, xaug, scal));
   } else {
     VQB_DISPATCH_DTYPE(x_dtype, T,
       prepare_latents_kernel<T><<<(unsigned)blocks, warps * 32, 0, st>>>((const T*)x, rows, rows_per_head, d, dp, chdr,
-                                                                         xb, xinv, xaug, scal));
+                                                                         xb, xinv, xn2, xaug, scal));
   }
   VQB_LAUNCH_CHECK();
   return VQB_OK;
@@ -528,6 +533,99 @@ __global__ void l2norm_rows_kernel(const T* __restrict__ x, float* __restrict__ 
   }
 }
 
+
+// l2norm_rows + prepare_latents in ONE pass (cosine codebooks: VectorQuantize normalises its input and the search
+// then prepares the normalised rows -- two reads of N x d fp32 and one write become one read): writes x^ = x / |x|
+// (same operations in the same order as l2norm_rows_kernel: bit-identical) and, from the registers, the scaled fp16
+// operand, row scale, bias operand and row statistics of x^ exactly as prepare_latents_kernel does.
+// d % 4 == 0, d_pad <= 512: lanes own float4 groups {lane*4 + 128 t}.
+template <typename T>
+__global__ void __launch_bounds__(256)
+l2norm_prepare_kernel(const T* __restrict__ x, float* __restrict__ out, int64_t rows, int64_t rows_per_head,
+                      bool single_head, int d, int dp, const float* __restrict__ chdr, __half* __restrict__ xb,
+                      float* __restrict__ xinv, float* __restrict__ xn2, __half* __restrict__ xaug,
+                      uint32_t* __restrict__ scal) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  float max_n2 = 0.f, max_r2 = 0.f;
+  for (int64_t row = (int64_t)blockIdx.x * wpb + (threadIdx.x >> 5); row < rows; row += (int64_t)gridDim.x * wpb) {
+    const T* xr = x + row * (int64_t)d;
+    float4 v[4];
+    float s = 0.f;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int j = lane * 4 + 128 * t;
+      v[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (j < d) {
+        v[t] = load4<T>(xr + j);
+        s = fmaf(v[t].x, v[t].x, s); s = fmaf(v[t].y, v[t].y, s); s = fmaf(v[t].z, v[t].z, s); s = fmaf(v[t].w, v[t].w, s);
+      }
+    }
+    s = warp_sum(s);
+    const float nrm = fmaxf(sqrtf(s), 1e-12f);
+    float m = 0.f;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int j = lane * 4 + 128 * t;
+      if (j < d) {
+        v[t] = make_float4(__fdiv_rn(v[t].x, nrm), __fdiv_rn(v[t].y, nrm), __fdiv_rn(v[t].z, nrm), __fdiv_rn(v[t].w, nrm));
+        *reinterpret_cast<float4*>(out + row * (int64_t)d + j) = v[t];
+        m = fmaxf(fmaxf(fmaxf(m, fabsf(v[t].x)), fmaxf(fabsf(v[t].y), fabsf(v[t].z))), fabsf(v[t].w));
+      }
+    }
+#pragma unroll
+    for (int o2 = 16; o2 > 0; o2 >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o2));
+    float sc = pow2_scale_bits(m);
+    float a = 1.f;
+    if (chdr) {
+      const float* hd = chdr + (single_head ? 0 : row / rows_per_head) * kHdrFloats;
+      a = clamp_row_scale(sc, hd[4], hd[5]);
+    }
+    const float is = pow2_recip(sc);
+    if (lane == 0) {
+      xinv[row] = a > 0.f ? is : -is;
+      if (xaug) {
+        const uint32_t aa = (uint32_t)__half_as_ushort(__float2half_rn(a));
+        *reinterpret_cast<uint4*>(xaug + row * 8) = make_uint4(aa | (aa << 16), aa, 0u, 0u);
+      }
+    }
+    float n2 = 0.f, r2 = 0.f;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int j = lane * 4 + 128 * t;
+      if (j < dp) {
+        const __half2 h0 = __floats2half2_rn(v[t].x * sc, v[t].y * sc), h1 = __floats2half2_rn(v[t].z * sc, v[t].w * sc);
+        const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+        uint2 pk;
+        pk.x = *reinterpret_cast<const uint32_t*>(&h0);
+        pk.y = *reinterpret_cast<const uint32_t*>(&h1);
+        *reinterpret_cast<uint2*>(xb + row * (int64_t)dp + j) = pk;
+        const float b0 = f0.x * is, b1 = f0.y * is, b2 = f1.x * is, b3 = f1.y * is;
+        n2 += b0 * b0 + b1 * b1 + b2 * b2 + b3 * b3;
+        const float e0 = v[t].x - b0, e1 = v[t].y - b1, e2 = v[t].z - b2, e3 = v[t].w - b3;
+        r2 += e0 * e0 + e1 * e1 + e2 * e2 + e3 * e3;
+      }
+    }
+    n2 = warp_sum(n2);
+    r2 = warp_sum(r2);
+    if (lane == 0) xn2[row] = row_norm2_bound(n2, r2);
+    max_n2 = fmaxf(max_n2, n2);
+    max_r2 = fmaxf(max_r2, r2);
+  }
+  __shared__ float s_n[32], s_r[32];
+  const int w = threadIdx.x >> 5;
+  if (lane == 0) { s_n[w] = max_n2; s_r[w] = max_r2; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float mn = 0.f, mr = 0.f;
+    for (int i = 0; i < wpb; ++i) { mn = fmaxf(mn, s_n[i]); mr = fmaxf(mr, s_r[i]); }
+    const float infl = 1.f + (float)dp * 2.4e-7f;
+    atomicMax(scal + 0, __float_as_uint(sqrtf(mn * infl) * 1.00001f));
+    atomicMax(scal + 1, __float_as_uint(sqrtf(mr * infl) * 1.00001f));
+    if (blockIdx.x == 0 && chdr && single_head) scal[7] = __float_as_uint(chdr[4]);   // the 2^q these operands use
+  }
+}
+
 }  // namespace vqb
 
 using namespace vqb;
@@ -559,6 +657,39 @@ extern "C" int vqb_prepare_codebook(const float* codebook, int64_t H, int K, int
       (float*)(base + CL.off_cn), (float*)(base + CL.off_dcn));
   VQB_LAUNCH_CHECK();
   codebook_aug_scale_kernel<<<(unsigned)((H + 63) / 64), 64, 0, st>>>(H, hdr);
+  VQB_LAUNCH_CHECK();
+  return VQB_OK;
+}
+
+extern "C" int vqb_l2norm_prepare_supported(int d) { return (d % 4 == 0 && d_pad(d) <= 512) ? 1 : 0; }
+
+extern "C" int vqb_l2norm_prepare(const void* x, int x_dtype, float* out, int64_t H, int64_t N, int K, int d,
+                                  const void* cache, void* search_ws, size_t ws_bytes, void* stream) {
+  VQB_REQUIRE(x && out && cache && search_ws, VQB_ERR_INVALID, "vqb_l2norm_prepare: null pointer");
+  VQB_REQUIRE(H > 0 && N >= 0 && K > 0 && d > 0, VQB_ERR_INVALID, "vqb_l2norm_prepare: bad shape");
+  VQB_REQUIRE(vqb_l2norm_prepare_supported(d), VQB_ERR_UNSUPPORTED, "vqb_l2norm_prepare: d=%d (d %% 4 == 0, d_pad <= 512)", d);
+  SearchLayout SL = search_layout(H, N, K, d);
+  VQB_REQUIRE(ws_bytes >= SL.total, VQB_ERR_WORKSPACE, "search workspace too small: %zu < %zu", ws_bytes, SL.total);
+  if (N == 0) return VQB_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  char* w = (char*)search_ws;
+  uint32_t* scal = (uint32_t*)(w + SL.off_scal);
+  VQB_CUDA_TRY(cudaMemsetAsync(scal, 0, 32, st));      // [0..1] statistics, [7] is written below (H = 1) or stays 0
+  const float* chdr = (const float*)((const char*)cache + cache_layout(H, K, d).off_hdr);
+  const int64_t rows = H * N;
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  int64_t blocks = (rows + 7) / 8;
+  if (blocks > (int64_t)sms * 8) blocks = (int64_t)sms * 8;
+  VQB_DISPATCH_DTYPE(x_dtype, T,
+    l2norm_prepare_kernel<T><<<(unsigned)blocks, 256, 0, st>>>((const T*)x, out, rows, N, H == 1, d, SL.dp, chdr,
+                                                               (__half*)(w + SL.off_xb), (float*)(w + SL.off_xinv),
+                                                               (float*)(w + SL.off_xn2), (__half*)(w + SL.off_xaug), scal));
   VQB_LAUNCH_CHECK();
   return VQB_OK;
 }

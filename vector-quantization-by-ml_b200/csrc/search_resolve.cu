@@ -83,7 +83,7 @@ struct RowCands {
 // emax > 0: the keys are NOT pre-lowered by E_k (no bias k-step, or E_k too large for the fp16 bias operand) and the
 // window is the symmetric min + 2 Emax for every code
 __device__ __forceinline__ void load_cands(const uint2* __restrict__ cand, int64_t gid, int K, int Kp, int64_t h,
-                                           const float* __restrict__ err, float emax, RowCands& R) {
+                                           const float* __restrict__ err, float emax, float tie_win, RowCands& R) {
   const uint4* c4 = reinterpret_cast<const uint4*>(cand + gid * kNumCand);
 #pragma unroll
   for (int i = 0; i < kNumCand / 2; ++i) {
@@ -101,7 +101,8 @@ __device__ __forceinline__ void load_cands(const uint2* __restrict__ cand, int64
   }
   const float E1 = emax > 0.f ? emax : (c1 >= 0 ? err[h * Kp + c1] : 0.f);
   // 2 E_j, plus the 6 packed id bits (<= 2^-17 relative per key) and the bias fma rounding
-  R.thr = m1 + 2.f * E1 + (fabsf(m1) + E1) * kPackSlack;
+  // + the codes that the reference's fp32 rounding of the distance can make EQUAL to the winner (kTieSlack, common.cuh)
+  R.thr = m1 + 2.f * E1 + (fabsf(m1) + E1) * kPackSlack + tie_win;
   R.c1 = c1;
   R.ncand = 0;
   R.full_rescan = c1 < 0;
@@ -125,13 +126,14 @@ resolve_classify_kernel(const uint2* __restrict__ cand, const float* __restrict_
                         int Kp, int64_t idx_offset, int want_score, int64_t* __restrict__ idx_out,
                         int* __restrict__ rr_list, int* __restrict__ flag_list, uint32_t* __restrict__ flag_cnt,
                         unsigned long long* __restrict__ keys, uint32_t* __restrict__ scal,
-                        const float* __restrict__ xinv, const float* __restrict__ chdr, int aug) {
+                        const float* __restrict__ xinv, const float* __restrict__ chdr, int aug,
+                        const float* __restrict__ xn2, float tie) {
   const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   bool queue = false;
   if (gid < H * N) {
     const int64_t h = gid / N;
     RowCands R;
-    load_cands(cand, gid, K, Kp, h, err, (aug == 2 || scal[8]) ? __uint_as_float(scal[6]) : 0.f, R);
+    load_cands(cand, gid, K, Kp, h, err, (aug == 2 || scal[8]) ? __uint_as_float(scal[6]) : 0.f, tie * xn2[gid], R);
     // no fp16 bias operand for this row (prepare.cu), or operands prepared by vqb_rvq_level against a cache that
     // has been rebuilt with another 2^q since (scal[7] records the one used): rescan exactly
     if (aug && (xinv[gid] < 0.f || (scal[7] != 0u && scal[7] != __float_as_uint(chdr[h * kHdrFloats + 4]))))
@@ -172,7 +174,8 @@ __device__ __forceinline__ float unpack_score(unsigned long long key);
 __global__ void __launch_bounds__(256)
 rerank_emit_kernel(const uint2* __restrict__ cand, const float* __restrict__ err, int64_t N, int K, int Kp,
                    const int* __restrict__ rr_list, uint32_t* __restrict__ scal, int aug, uint2* __restrict__ pairs,
-                   uint32_t pair_cap, int* __restrict__ flag_list, uint32_t* __restrict__ flag_cnt) {
+                   uint32_t pair_cap, int* __restrict__ flag_list, uint32_t* __restrict__ flag_cnt,
+                   const float* __restrict__ xn2, float tie) {
   const int lane = threadIdx.x & 31;
   const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
   const int64_t count = scal[3];
@@ -195,7 +198,7 @@ rerank_emit_kernel(const uint2* __restrict__ cand, const float* __restrict__ err
       if (om < m1 || (om == m1 && oc > c1)) { m1 = om; c1 = oc; }   // any consistent tie rule: only E(c1) is used
     }
     const float E1 = (aug == 2 || scal[8]) ? __uint_as_float(scal[6]) : (c1 >= 0 ? err[h * Kp + c1] : 0.f);
-    const float thr = m1 + 2.f * E1 + (fabsf(m1) + E1) * kPackSlack;
+    const float thr = m1 + 2.f * E1 + (fabsf(m1) + E1) * kPackSlack + tie * xn2[gid];
     const bool act = code >= 0 && key <= thr;
     // hazard (ii): entries 3g and 3g+1 both within thr and from the same pair of N tiles -> that 64-column group
     const float key_next = __shfl_down_sync(0xffffffffu, key, 1);
@@ -490,6 +493,8 @@ extern "C" int vqb_search(const void* x, int x_dtype, const float* codebook, con
   const char* cbase = (const char*)cache;
   __half* xb = (__half*)(w + SL.off_xb);
   float* xinv = (float*)(w + SL.off_xinv);
+  float* xn2 = (float*)(w + SL.off_xn2);
+  const float tie = metric == VQB_EUCLID ? kTieSlack : 0.f;
   unsigned long long* keys = (unsigned long long*)(w + SL.off_keys);
   float* bias = (float*)(w + SL.off_bias);
   float* err = (float*)(w + SL.off_err);
@@ -497,21 +502,21 @@ extern "C" int vqb_search(const void* x, int x_dtype, const float* codebook, con
   __half* xaug = (__half*)(w + SL.off_xaug);
   const float* chdr = (const float*)(cbase + CL.off_hdr);
   if (!prepared) {
-    rc = launch_prepare_latents(x, x_dtype, H * N, N, d, SL.dp, chdr, xb, xinv, xaug, scal, st);
+    rc = launch_prepare_latents(x, x_dtype, H * N, N, d, SL.dp, chdr, xb, xinv, xn2, xaug, scal, st);
     if (rc) return rc;
   }
   const int aug = search_tc_aug_mode(N, K, metric);
   __half* caug = (__half*)(w + SL.off_caug);
   rc = launch_make_bias(cache, CL, H, K, metric, scal, bias, err, aug == 1 ? caug : nullptr, st);
   if (rc) return rc;
-  rc = launch_search_tc(xb, xinv, xaug, (const __half*)(cbase + CL.off_cb), caug, chdr,
+  rc = launch_search_tc(xb, xinv, xn2, tie, xaug, (const __half*)(cbase + CL.off_cb), caug, chdr,
                         bias, aug, H, N, K, SL.dp, w + SL.off_cand, scal, (flags & VQB_SEARCH_TIMING) != 0, st);
   if (rc) return rc;
   const int64_t total = H * N;
   int* rr_list = (int*)(w + SL.off_rr);
   resolve_classify_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
       (const uint2*)(w + SL.off_cand), err, H, N, K, CL.Kp, idx_offset, score_out != nullptr, idx_out, rr_list,
-      flag_list, cnt, keys, scal, xinv, chdr, aug);
+      flag_list, cnt, keys, scal, xinv, chdr, aug, xn2, tie);
   VQB_LAUNCH_CHECK();
   {
     uint2* pairs = (uint2*)(w + SL.off_pairs);
@@ -520,7 +525,7 @@ extern "C" int vqb_search(const void* x, int x_dtype, const float* codebook, con
     const int64_t cap = (int64_t)num_sms() * 8;
     const int grid_rr = (int)(want < cap ? want : cap);
     rerank_emit_kernel<<<grid_rr, 256, 0, st>>>((const uint2*)(w + SL.off_cand), err, N, K, CL.Kp, rr_list, scal, aug,
-                                                pairs, pair_cap, flag_list, cnt);
+                                                pairs, pair_cap, flag_list, cnt, xn2, tie);
     VQB_LAUNCH_CHECK();
     flag_plan_kernel<<<(unsigned)((H + 63) / 64), 64, 0, st>>>(cnt, (int)H, K, pair_cap, scal, scan_cnt, plan);
     VQB_LAUNCH_CHECK();

@@ -322,6 +322,8 @@ constexpr int kTmemCols = 512;
 
 struct SearchParams {
   const float* bias;   // [H][Kp]
+  const float* xn2;    // [H][N]   bound of |x_row|^2
+  float tie;           // kTieSlack (Euclidean) or 0: window of fp32 distance ties = tie * xn2 (common.cuh)
   const float* xinv;   // [H][N]   1 / s_row
   const float* chdr;   // [H][4]   {s_c, 1/s_c, ..}
   void* cand;          // [H][N][24] {f32 key, i32 code}
@@ -596,6 +598,8 @@ search_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
       for (int c = 0; c < 2; ++c) { M1[c] = INF; M2[c] = INF; M3[c] = INF; C1[c] = -1; C2[c] = -1; C3[c] = -1; }
       // acc = (x s_row).(-c s_c)  ->  score = bias + acc / (s_row s_c): one FFMA per element
       const float ninv = row < P.N ? fabsf(P.xinv[(size_t)h * P.N + row]) * P.chdr[h * kHdrFloats + 1] : 0.f;
+      // candidate window of THIS row: Emax part + the fp32 distance-tie part
+      const float trow = tconst + (row < P.N ? P.tie * P.xn2[(size_t)h * P.N + row] : 0.f);
       // the id mask lives in a register so that "(bits & mask) | id" is a single LOP3 (opaque to constant folding)
       uint32_t idmask;
       asm volatile("mov.u32 %0, 0xFFFFFFC0;" : "=r"(idmask));
@@ -610,7 +614,7 @@ search_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
       for (int nt = 0; nt < P.NT; nt += 2) {       // N tiles in pairs: one top-3 merge per 512 codes
         if (row_slot) {                            // tighten the threshold with what the other quarters have seen
           const float gmin = ord2f(*reinterpret_cast<volatile int*>(row_slot));
-          t_run = fminf(t_run, fmaf(fabsf(gmin), kPackSlackTC, gmin) + tconst);
+          t_run = fminf(t_run, fmaf(fabsf(gmin), kPackSlackTC, gmin) + trow);
         }
         float a1[2], a2[2];
 #pragma unroll
@@ -628,8 +632,8 @@ search_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
 #define VQB_CHUNK(CH)                                                                                      \
             cmin = chunk_scores<MODE>(r, bias4 + (CH) * 4, ninv, key, prof, w_ld);                                   \
             TMEM_LD16(taddr + ((CH) + 1) * 16, r);                                                         \
-            if (par == 0) chunk_rank<0, (CH), MODE>(key, cmin, idmask, tconst, m_run, t_run, row_slot, a1, a2, any_slow, P.dbg); \
-            else chunk_rank<1, (CH), MODE>(key, cmin, idmask, tconst, m_run, t_run, row_slot, a1, a2, any_slow, P.dbg);
+            if (par == 0) chunk_rank<0, (CH), MODE>(key, cmin, idmask, trow, m_run, t_run, row_slot, a1, a2, any_slow, P.dbg); \
+            else chunk_rank<1, (CH), MODE>(key, cmin, idmask, trow, m_run, t_run, row_slot, a1, a2, any_slow, P.dbg);
             VQB_CHUNK(0) VQB_CHUNK(1) VQB_CHUNK(2)
 #undef VQB_CHUNK
             // last chunk: once its scores are formed every TMEM read of this tile is complete -> hand the buffer
@@ -656,8 +660,8 @@ search_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
               issued = true;
             }
             if (MODE == 1 && prof) w_try += (unsigned long long)(clock64() - t_try);
-            if (par == 0) chunk_rank<0, 3, MODE>(key, cmin, idmask, tconst, m_run, t_run, row_slot, a1, a2, any_slow, P.dbg);
-            else chunk_rank<1, 3, MODE>(key, cmin, idmask, tconst, m_run, t_run, row_slot, a1, a2, any_slow, P.dbg);
+            if (par == 0) chunk_rank<0, 3, MODE>(key, cmin, idmask, trow, m_run, t_run, row_slot, a1, a2, any_slow, P.dbg);
+            else chunk_rank<1, 3, MODE>(key, cmin, idmask, trow, m_run, t_run, row_slot, a1, a2, any_slow, P.dbg);
             if (more && !issued) {
               mbar_wait_t(smem_u32(&bars->tmem_full[acc]), acc_ph, prof, w_tf);
               tc_fence_after();
@@ -730,6 +734,8 @@ __device__ __forceinline__ uint64_t make_nosw_desc(uint32_t saddr, uint32_t lbo_
 }
 
 struct AugParams {
+  const float* xn2;    // [H][N]   bound of |x_row|^2
+  float tie;           // see SearchParams
   const float* xinv;   // [H][N]   +-1 / s_row
   const float* chdr;   // [H][kHdrFloats]
   void* cand;
@@ -918,7 +924,8 @@ search_aug_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
       for (int c = 0; c < 2; ++c) { M1[c] = INF; M2[c] = INF; M3[c] = INF; C1[c] = -1; C2[c] = -1; C3[c] = -1; }
       // key = s_row s_c score: inv undoes it (exact, powers of two); thresholds live in the scaled units
       const float inv = row < P.N ? fabsf(P.xinv[(size_t)h * P.N + row]) * P.chdr[h * kHdrFloats + 1] : 0.f;
-      const float trow = inv > 0.f ? tconst / inv : 0.f;
+      // candidate window of this row in its scaled units: Emax part + the fp32 distance-tie part
+      const float trow = inv > 0.f ? (tconst + P.tie * P.xn2[(size_t)h * P.N + row]) / inv : 0.f;
       uint32_t idmask;
       asm volatile("mov.u32 %0, 0xFFFFFFC0;" : "=r"(idmask));
       float m_run = INF, t_run = INF;
@@ -1122,7 +1129,8 @@ int search_tc_aug_mode(int64_t N, int K, int metric) {
   return (metric == VQB_DOT && K % kBlockN == 0) ? 2 : 1;
 }
 
-static int launch_aug(const __half* xb, const float* xinv, const __half* xaug, const __half* cb, const __half* caug,
+static int launch_aug(const __half* xb, const float* xinv, const float* xn2, float tie, const __half* xaug,
+                      const __half* cb, const __half* caug,
                       const float* chdr, int64_t H, int64_t N, int K, int dp, int aug_on, void* cand, uint32_t* scal,
                       bool timing, cudaStream_t st) {
   const int Kp = k_pad(K);
@@ -1136,7 +1144,8 @@ static int launch_aug(const __half* xb, const float* xinv, const __half* xaug, c
     if (dev >= 0 && dev < 64) configured[dev] = true;
   }
   AugParams P;
-  P.xinv = xinv; P.chdr = chdr; P.cand = cand; P.scal = scal; P.N = N; P.Kp = Kp; P.H = (int)H;
+  P.xinv = xinv; P.xn2 = xn2; P.tie = tie; P.chdr = chdr; P.cand = cand; P.scal = scal; P.N = N; P.Kp = Kp;
+  P.H = (int)H;
   P.KB = dp / kBlockK;
   P.NT = Kp / kBlockN;
   P.aug = aug_on;
@@ -1191,15 +1200,16 @@ static int launch_aug(const __half* xb, const float* xinv, const __half* xaug, c
   return VQB_OK;
 }
 
-int launch_search_tc(const __half* xb, const float* xinv, const __half* xaug, const __half* cb, const __half* caug,
-                     const float* chdr, const float* bias, int aug_mode, int64_t H, int64_t N, int K, int dp,
-                     void* cand, uint32_t* scal, bool timing, cudaStream_t st) {
+int launch_search_tc(const __half* xb, const float* xinv, const float* xn2, float tie, const __half* xaug,
+                     const __half* cb, const __half* caug, const float* chdr, const float* bias, int aug_mode,
+                     int64_t H, int64_t N, int K, int dp, void* cand, uint32_t* scal, bool timing, cudaStream_t st) {
   const int Kp = k_pad(K);
   if (aug_mode) {
     VQB_REQUIRE(xaug && caug, VQB_ERR_INVALID, "search: bias operands missing");
     VQB_REQUIRE(dp % kBlockK == 0 && dp / kBlockK <= kMaxKB, VQB_ERR_UNSUPPORTED, "d_pad %d unsupported by the TC path", dp);
     VQB_REQUIRE(N < (1ll << 31) - kBlockM, VQB_ERR_UNSUPPORTED, "N too large for TMA coordinates");
-    return launch_aug(xb, xinv, xaug, cb, caug, chdr, H, N, K, dp, aug_mode == 1 ? 1 : 0, cand, scal, timing, st);
+    return launch_aug(xb, xinv, xn2, tie, xaug, cb, caug, chdr, H, N, K, dp, aug_mode == 1 ? 1 : 0, cand, scal, timing,
+                      st);
   }
   VQB_REQUIRE(dp % kBlockK == 0 && dp / kBlockK <= kMaxKB, VQB_ERR_UNSUPPORTED, "d_pad %d unsupported by the TC path", dp);
   VQB_REQUIRE(N < (1ll << 31) - kBlockM, VQB_ERR_UNSUPPORTED, "N too large for TMA coordinates");
@@ -1219,7 +1229,8 @@ int launch_search_tc(const __half* xb, const float* xinv, const __half* xaug, co
   const int cluster = mode == 1 ? 1 : 2;
 
   SearchParams P;
-  P.bias = bias; P.xinv = xinv; P.chdr = chdr; P.cand = cand; P.scal = scal; P.N = N; P.Kp = Kp; P.H = (int)H;
+  P.bias = bias; P.xinv = xinv; P.xn2 = xn2; P.tie = tie; P.chdr = chdr; P.cand = cand; P.scal = scal; P.N = N;
+  P.Kp = Kp; P.H = (int)H;
   P.dbg = dbg_env();
   P.KB = dp / kBlockK;
   P.NT = Kp / kBlockN;

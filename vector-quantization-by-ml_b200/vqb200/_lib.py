@@ -35,6 +35,8 @@ SIGNATURES = {
     "vqb_search": (_i32, [_p, _i32, _p, _p, _i32, _i64, _i64, _i32, _i32, _i64, _p, _p, _i32, _p, _sz, _p]),
     "vqb_search_stats": (_i32, [_p, _p, _p]),
     "vqb_l2norm_rows": (_i32, [_p, _i32, _p, _i64, _i32, _p]),
+    "vqb_l2norm_prepare_supported": (_i32, [_i32]),
+    "vqb_l2norm_prepare": (_i32, [_p, _i32, _p, _i64, _i64, _i32, _i32, _p, _p, _sz, _p]),
     "vqb_gather_workspace_bytes": (_sz, [_i64, _i64, _i32]),
     "vqb_gather_st_loss": (_i32, [_p, _i32, _p, _p, _p, _i32, _i32, _p, _p, _i64, _i64, _i32, _i32, _p, _sz, _p]),
     "vqb_st_commit_backward": (_i32, [_p, _p, _p, _i32, _p, _p, _p, _f32, _p, _i64, _i64, _i32, _i32, _p]),

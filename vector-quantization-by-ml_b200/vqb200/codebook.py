@@ -209,7 +209,7 @@ class Codebook(nn.Module):
 
     # ------------------------------------------------------------------ core
     def _run(self, x: torch.Tensor, mask: Optional[torch.Tensor], freeze_codebook: bool, fuse_st: bool,
-             want_commit: bool):
+             want_commit: bool, normalize_input: bool = False):
         """Shared by forward() and VectorQuantize.  x: (H, ..., d).  Returns (quantize (H,...,d), idx (H,...),
         commit scalar | None)."""
         if not x.is_cuda:
@@ -222,12 +222,25 @@ class Codebook(nn.Module):
                              f"{tuple(self.embeddings.shape)}")
         mask_u8 = self._expand_mask(mask, N)
 
+        prepared = False
+        if normalize_input:
+            # transform_input="l2norm" (reference vector_quantize_pytorch.py:221): normalisation and the search's operand
+            # preparation share one pass over x when the codebook cache is already final
+            if torch.is_grad_enabled() and flat.requires_grad:
+                # the encoder's gradient passes through the normalisation: torch's own (differentiable) op
+                flat = torch.nn.functional.normalize(flat.float(), p=2, dim=-1)
+            elif self.is_initialized and ops.l2norm_prepare_supported(d):
+                flat = ops.l2norm_prepare(flat, self.codebook_size, self._codebook_cache())
+                prepared = True
+            else:
+                flat = ops.l2norm_rows(flat)
+
         if not self.is_initialized:
             self._kmeans_init(flat, mask_u8)
             self.is_initialized = True
 
         emb = self.embeddings.detach()
-        idx, _, ws = ops.search(flat, emb, self._codebook_cache(), self.use_cosine_sim)
+        idx, _, ws = ops.search(flat, emb, self._codebook_cache(), self.use_cosine_sim, latents_prepared=prepared)
         self.last_search_ws = ws
 
         training = self.training

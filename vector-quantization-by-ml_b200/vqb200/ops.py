@@ -117,6 +117,22 @@ def l2norm_rows(x: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def l2norm_prepare_supported(d: int) -> bool:
+    return bool(L.lib().vqb_l2norm_prepare_supported(int(d)))
+
+
+def l2norm_prepare(x: torch.Tensor, K: int, cache: torch.Tensor) -> torch.Tensor:
+    """x (H,N,d) -> x / |x| (fp32) and, in the shared search workspace, everything the next
+    `search(out, ..., latents_prepared=True)` with this codebook cache needs."""
+    L.require_cuda(x, "x")
+    H, N, d = x.shape
+    out = torch.empty((H, N, d), dtype=torch.float32, device=x.device)
+    ws = workspace("search", L.lib().vqb_search_workspace_bytes(H, N, K, d), x.device)
+    L.check(L.lib().vqb_l2norm_prepare(L.ptr(x), L.dtype_code(x), L.ptr(out), H, N, int(K), d, L.ptr(cache), L.ptr(ws),
+                                       ws.numel(), L.stream_ptr(x.device)), "vqb_l2norm_prepare")
+    return out
+
+
 # ---------------------------------------------------------------------------------------------
 # gather + straight-through + commitment loss (autograd-aware)
 # ---------------------------------------------------------------------------------------------

@@ -140,13 +140,13 @@ class VectorQuantize(nn.Module):
             xh = x.reshape(B, n, heads, dh)
             x = xh.permute(2, 0, 1, 3) if self.separate_codebook_per_head else \
                 xh.permute(0, 2, 1, 3).reshape(1, B * heads, n, dh)
-        x = self._codebook.transform_input(x)
-
         cb_in = x if x.ndim == 4 else x[None]
         training = self.training
         want_commit = training and self.has_commitment_loss
+        # transform_input (reference :221) happens inside _run, fused with the search's operand preparation
         quantize, embed_ind, commit = self._codebook._run(cb_in, mask, freeze_codebook, fuse_st=True,
-                                                          want_commit=want_commit)
+                                                          want_commit=want_commit,
+                                                          normalize_input=self._codebook.input_l2norm)
         if x.ndim < 4:
             quantize, embed_ind = quantize[0], embed_ind[0]
         if training and self.sync_update_v > 0.0:
