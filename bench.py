@@ -62,7 +62,7 @@ def peaks():
 
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region (profiling recipe's clocks line)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
@@ -81,17 +81,36 @@ class ClockSampler:
             self.proc = None
 
     def _pump(self):
+        import datetime
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            line = line.strip()
+            t = time.time()
+            try:    # nvidia-smi's own timestamp (local time, ms): immune to pipe buffering
+                t = datetime.datetime.strptime(line.split(",")[0].strip(), "%Y/%m/%d %H:%M:%S.%f").timestamp()
+            except Exception:
+                pass
+            self.rows.append((t, line))
 
-    def stop(self):
+    def stop(self, t_begin=None, t_end=None):
+        """Summary of the samples taken in [t_begin, t_end] (host clock around the timed region, which ends with a
+        device sync).  nvidia-smi needs ~0.2 s to deliver its first line, so the sampler is started before the
+        warm-up; if the window is shorter than the sampling period the samples nearest to it (all under the same
+        load: the warm-up runs the same step) are used."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.proc.terminate()
+        rows = self.rows
+        if t_begin is not None:
+            inside = [r for (t, r) in rows if t_begin <= t <= t_end + 0.03]
+            if len(inside) < 3:
+                mid = 0.5 * (t_begin + t_end)
+                inside = [r for (_, r) in sorted(rows, key=lambda tr: abs(tr[0] - mid))[:5]]
+        else:
+            inside = [r for (_, r) in rows]
         sm, smax, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for r in inside:
             f = [c.strip() for c in r.split(",")]
             if len(f) < 9:
                 continue
@@ -215,6 +234,11 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)                   # nvidia-smi is streaming by the time the warm-up starts
+    t_warm = time.time()                  # the warm-up runs the same step: its samples are under the same load
     for i in range(max(args.warmup, 3)):
         step(i)
     barrier()
@@ -222,22 +246,21 @@ def main():
     # ---- timed region: device-resident inputs ----
     ops.TIME_SEARCH_KERNEL = True
     ops.search_kernel_times_ms()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     launches0 = ops.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    t_begin = time.time()
     e0.record()
     for i in range(args.steps):
         step(i)
     e1.record()
     barrier()
+    t_end = time.time()
     ms = e0.elapsed_time(e1)
     launches = ops.launch_count() - launches0
     tc_ms = ops.search_kernel_times_ms()
     ops.TIME_SEARCH_KERNEL = False
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_warm, t_end) if rank == 0 else None
     stats = ops.search_stats(cb.last_search_ws)
 
     # ---- e2e: host buffers in, indices + loss out, copies inside the timed region ----
