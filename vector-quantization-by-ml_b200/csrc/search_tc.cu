@@ -757,8 +757,9 @@ struct AugBarriers {
   int rowmin[3][kBlockM];     // see Barriers::rowmin
 };
 
+template <bool WAIT = true>
 __device__ __forceinline__ float chunk_min16(const uint32_t (&r)[16]) {
-  tmem_ld_wait();
+  if (WAIT) tmem_ld_wait();
   float cm[4];
 #pragma unroll
   for (int c = 0; c < 4; ++c)
@@ -767,13 +768,24 @@ __device__ __forceinline__ float chunk_min16(const uint32_t (&r)[16]) {
   return fminf(min3f(cm[0], cm[1], cm[2]), cm[3]);
 }
 
-__global__ void __launch_bounds__(kThreads, 1)
+// DRAIN: an epilogue warp first copies its whole 64-column quarter of the accumulator into registers and hands the
+// TMEM buffer back, THEN ranks from the registers.  The buffer is then held for ~150 cycles instead of the whole
+// epilogue of the tile, so the next-but-one tile's MMAs (and the barrier round trips around them) overlap the ranking:
+// with the chunk-by-chunk form the epilogue warps of a d = 64 search waited for `tmem_full` a third of the time and
+// the MMA warp for `tmem_empty` 63 % of it (ncu source page / cycle counters), each side waiting for the other's
+// latency.  Costs 64 live accumulator registers: 18 warps (the TMA warp also allocates TMEM and writes the zero
+// chunk) x 32 x 112 registers.
+constexpr int kThreadsDrain = 576;
+template <bool DRAIN>
+__global__ void __launch_bounds__(DRAIN ? kThreadsDrain : kThreads, 1)
 search_aug_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_c,
                   const __grid_constant__ CUtensorMap map_xa, const __grid_constant__ CUtensorMap map_ca,
                   const AugParams P) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  constexpr int kWarpTma = DRAIN ? 16 : vqb::kWarpTma, kWarpMma = DRAIN ? 17 : vqb::kWarpMma;
+  constexpr int kWarpAlloc = DRAIN ? 16 : vqb::kWarpAlloc, kWarpStager = DRAIN ? 16 : vqb::kWarpStager;
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t a_base = smem_base;
   const uint32_t b_base = smem_base + (uint32_t)P.KB * kSlabBytes;
@@ -907,9 +919,10 @@ search_aug_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     const float INF = __int_as_float(0x7f800000);
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + quarter * 64;
     const float tconst = __uint_as_float(P.scal[6]) * (2.f + kPackSlackTC);
-    uint32_t rA[16], rB[16];
+    uint32_t rA[16], rB[16];                 // chunk-by-chunk form: two alternating register sets
+    uint32_t rD[DRAIN ? 4 : 1][16];          // DRAIN form: the whole 64-column quarter
     uint32_t tile_it = 0;
-    if (cid < G) {
+    if (!DRAIN && cid < G) {
       mbar_wait(smem_u32(&bars->tmem_full[0]), 0);
       tc_fence_after();
       TMEM_LD16(lane_addr, rA);
@@ -946,13 +959,37 @@ search_aug_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
         bool any_slow = false;
 #pragma unroll
         for (int par = 0; par < 2; ++par) {
-          if (nt + par < P.NT) {
+          if (DRAIN) {
+            if (nt + par < P.NT) {
+              const uint32_t taddr = lane_addr + acc * (uint32_t)kBlockN;
+              mbar_wait(smem_u32(&bars->tmem_full[acc]), acc_ph);
+              tc_fence_after();
+              TMEM_LD16(taddr, rD[0]);
+              TMEM_LD16(taddr + 16, rD[DRAIN ? 1 : 0]);
+              TMEM_LD16(taddr + 32, rD[DRAIN ? 2 : 0]);
+              TMEM_LD16(taddr + 48, rD[DRAIN ? 3 : 0]);
+              tmem_ld_wait();
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive_leader(smem_u32(&bars->tmem_empty[acc]));   // buffer handed back: rank from registers
+              if (++acc == 2) { acc = 0; acc_ph ^= 1u; }
+              float cmin;
+#define VQB_DRAIN_CHUNK(CH)                                                                                 \
+              cmin = chunk_min16<false>(rD[DRAIN ? (CH) : 0]);                                              \
+              if (par == 0) chunk_rank<0, (CH), 0>(reinterpret_cast<float(&)[16]>(rD[DRAIN ? (CH) : 0]), cmin, idmask, \
+                                                   trow, m_run, t_run, row_slot, a1, a2, any_slow, 0);      \
+              else chunk_rank<1, (CH), 0>(reinterpret_cast<float(&)[16]>(rD[DRAIN ? (CH) : 0]), cmin, idmask, trow,   \
+                                          m_run, t_run, row_slot, a1, a2, any_slow, 0);
+              VQB_DRAIN_CHUNK(0) VQB_DRAIN_CHUNK(1) VQB_DRAIN_CHUNK(2) VQB_DRAIN_CHUNK(3)
+#undef VQB_DRAIN_CHUNK
+            }
+          } else if (nt + par < P.NT) {
             const uint32_t taddr = lane_addr + acc * (uint32_t)kBlockN;
             float cmin;
             // the accumulator registers ARE the keys: two register sets alternate so that the next chunk's
             // tcgen05.ld is in flight while this chunk is ranked
 #define VQB_AUG_CHUNK(CH, RCUR, RNEXT)                                                                      \
-            cmin = chunk_min16(RCUR);                                                                       \
+            cmin = chunk_min16<true>(RCUR);                                                                 \
             TMEM_LD16(taddr + ((CH) + 1) * 16, RNEXT);                                                      \
             if (par == 0) chunk_rank<0, (CH), 0>(reinterpret_cast<float(&)[16]>(RCUR), cmin, idmask, trow, m_run, \
                                                  t_run, row_slot, a1, a2, any_slow, 0);                     \
@@ -960,7 +997,7 @@ search_aug_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
                                         row_slot, a1, a2, any_slow, 0);
             VQB_AUG_CHUNK(0, rA, rB) VQB_AUG_CHUNK(1, rB, rA) VQB_AUG_CHUNK(2, rA, rB)
 #undef VQB_AUG_CHUNK
-            cmin = chunk_min16(rB);
+            cmin = chunk_min16<true>(rB);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_leader(smem_u32(&bars->tmem_empty[acc]));
@@ -1140,9 +1177,12 @@ static int launch_aug(const __half* xb, const float* xinv, const float* xn2, flo
   if (!num_sms) VQB_CUDA_TRY(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
   static bool configured[64] = {};
   if (dev < 0 || dev >= 64 || !configured[dev]) {
-    VQB_CUDA_TRY(cudaFuncSetAttribute(search_aug_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    VQB_CUDA_TRY(cudaFuncSetAttribute(search_aug_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    VQB_CUDA_TRY(cudaFuncSetAttribute(search_aug_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     if (dev >= 0 && dev < 64) configured[dev] = true;
   }
+  static int drain = -1;     // env VQB_DRAIN=0: chunk-by-chunk epilogue (the TMEM buffer is held while it is ranked)
+  if (drain < 0) { const char* e = getenv("VQB_DRAIN"); drain = e ? atoi(e) : 1; }
   AugParams P;
   P.xinv = xinv; P.xn2 = xn2; P.tie = tie; P.chdr = chdr; P.cand = cand; P.scal = scal; P.N = N; P.Kp = Kp;
   P.H = (int)H;
@@ -1171,7 +1211,7 @@ static int launch_aug(const __half* xb, const float* xinv, const float* xn2, flo
   if (rc) return rc;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(nclusters * 2));
-  cfg.blockDim = dim3(kThreads);
+  cfg.blockDim = dim3(drain ? kThreadsDrain : kThreads);
   cfg.dynamicSmemBytes = smem_bytes;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -1194,7 +1234,8 @@ static int launch_aug(const __half* xb, const float* xinv, const float* xn2, flo
     if (g_ev_count < kTimingSlots) slot = g_ev_count++;
   }
   if (slot >= 0) VQB_CUDA_TRY(cudaEventRecord(g_ev0[slot], st));
-  VQB_CUDA_TRY(cudaLaunchKernelEx(&cfg, search_aug_kernel, mx, mc, mxa, mca, P));
+  if (drain) VQB_CUDA_TRY(cudaLaunchKernelEx(&cfg, search_aug_kernel<true>, mx, mc, mxa, mca, P));
+  else VQB_CUDA_TRY(cudaLaunchKernelEx(&cfg, search_aug_kernel<false>, mx, mc, mxa, mca, P));
   ++g_launch_count;
   if (slot >= 0) VQB_CUDA_TRY(cudaEventRecord(g_ev1[slot], st));
   return VQB_OK;
