@@ -49,7 +49,7 @@ extern "C" {
 #define VQB_DOT    1
 
 /* vqb_search flags */
-#define VQB_SEARCH_LATENTS_PREPARED 1  /* ws already holds bf16 latents + row stats (written by vqb_rvq_level) */
+#define VQB_SEARCH_LATENTS_PREPARED 1  /* ws already holds the scaled fp16 latents, row scales, bias operands and row stats (written by vqb_rvq_level[_ema] or vqb_l2norm_prepare against the SAME codebook cache) */
 #define VQB_SEARCH_FORCE_EXACT      2  /* skip the tensor-core pass: fp32/fp64 CUDA-core scan of every code */
 #define VQB_SEARCH_TIMING           4  /* bracket the tensor-core kernel with CUDA events (see vqb_search_timing) */
 
@@ -59,7 +59,7 @@ const char* vqb_last_error(void);
 int64_t     vqb_launch_count(void);
 
 /* ---- derived codebook cache ---------------------------------------------------------
- * bf16 (negated, padded) copy of the codebook for the tensor-core pass + per-code norms and
+ * scaled fp16 (negated, padded) copy of the codebook for the tensor-core pass + per-code norms and
  * rounding-error bounds.  Derived from `embeddings`; must be rebuilt whenever embeddings
  * change (EMA refresh codebooks.py:425, expiry :241, kmeans init :226, load_state_dict). */
 size_t vqb_codebook_cache_bytes(int64_t H, int K, int d);
@@ -68,8 +68,9 @@ int    vqb_prepare_codebook(const float* codebook, int64_t H, int K, int d, int 
 
 /* ---- nearest-code search ------------------------------------------------------------
  * Replaces codebooks.py:386 (similarity_fn: -cdist / einsum, N x K fp32 materialised) +
- * utils/general.py:128-129 (argmax + one_hot).  bf16 tcgen05 GEMM with a fused per-row
- * top-2 epilogue produces candidates; candidates are re-ranked with fp64-accumulated
+ * utils/general.py:128-129 (argmax + one_hot).  fp16 tcgen05 GEMM (operands scaled by exact
+ * powers of two, the |c|^2/2 bias as one extra k-step) with a fused per-row packed top-k
+ * epilogue produces candidates; candidates are re-ranked with fp64-accumulated
  * fp32 scores (sqrt(clamp(|x|^2+|c|^2-2x.c)) resp. x.c), lowest index wins ties, like
  * torch argmax.  Rows whose candidate set cannot be proven complete are rescanned exactly.
  *   idx_out   (H,N) int64  code index + idx_offset

@@ -1,4 +1,4 @@
-"""Bring-up check for the tcgen05 search kernel: TC path vs the exact CUDA-core scan vs the CPU oracle.
+"""Bring-up check for the tcgen05 search kernel: TC path vs the exact CUDA-core scan.
 Run under `timeout`; prints one line per shape."""
 import os
 import sys

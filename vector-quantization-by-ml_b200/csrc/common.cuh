@@ -41,7 +41,7 @@ extern int64_t g_launch_count;   // every kernel launch is followed by VQB_LAUNC
 // ---- geometry shared by prepare / search / resolve ----------------------------------------
 constexpr int kBlockM = 128;   // latent rows per CTA tile (TMEM lanes)
 constexpr int kBlockN = 256;   // codes per N tile (UMMA N)
-constexpr int kBlockK = 64;    // bf16 elements per k-block = one 128B swizzle atom
+constexpr int kBlockK = 64;    // fp16 elements per k-block = one 128B swizzle atom
 constexpr int kNumCand = 24;   // candidates kept per row: 4 column quarters x 2 classes x top-3
 constexpr float kPadBias = 3.0e38f;
 constexpr int kHdrFloats = 8;  // per-codebook header of the cache (see CacheLayout)
@@ -91,7 +91,7 @@ struct SearchLayout {
   size_t off_flag;    // i32 [H*N] flagged row list
   size_t off_rr;      // i32 [H*N] rows queued for the warp-per-row re-rank (length in scal[3])
   size_t off_bias;    // f32 [H][Kp]  lower-bound bias  |c|^2/2 - E_k  (needs the row stats, so per search)
-  size_t off_err;     // f32 [H][Kp]  E_k: bound on |exact score - bf16 tensor-core score| for code k
+  size_t off_err;     // f32 [H][Kp]  E_k: bound on |exact score - fp16 tensor-core score| for code k
   size_t off_pairs;   // {u32 row, u32 code} [pair_cap]  (row, code) pairs scored exactly in resolve phase 2 (count in scal[9])
   size_t pair_cap;
   size_t off_caug;    // fp16 [H][Kp][8]  three fp16 pieces of s_c 2^q bias_k (+inf for padded codes), then zeros:

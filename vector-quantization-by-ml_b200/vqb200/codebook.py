@@ -87,7 +87,7 @@ class Codebook(nn.Module):
         else:
             self.register_buffer("embeddings", init)
 
-        # derived, non-persistent: bf16 copy + norms for the tensor-core search
+        # derived, non-persistent: scaled fp16 copy + norms for the tensor-core search
         self._cache: Optional[torch.Tensor] = None
         self._cache_key = None
         self._dirty = True

@@ -66,7 +66,7 @@ def _mask_u8(mask: Optional[torch.Tensor], n: int) -> Optional[torch.Tensor]:
 # ---------------------------------------------------------------------------------------------
 def prepare_codebook(embeddings: torch.Tensor, use_cosine_sim: bool,
                      out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """bf16 copy + norms + rounding bounds of `embeddings` for the tensor-core search."""
+    """Scaled fp16 copy + norms + rounding bounds of `embeddings` for the tensor-core search."""
     L.require_cuda(embeddings, "embeddings")
     assert embeddings.dtype == torch.float32 and embeddings.ndim == 3
     H, K, d = embeddings.shape

@@ -3,7 +3,7 @@
 The per-level loop (reference :212-243) has two implementations with identical results:
   * generic: each level is a ``VectorQuantize`` call and the residual arithmetic is autograd-visible;
   * fused (no autograd needed): one kernel per level does gather + straight-through + commitment loss
-    + ``residual -= q`` + ``quantized_out += q`` and emits the next level's bf16 search operand, so the
+    + ``residual -= q`` + ``quantized_out += q`` and emits the next level's scaled fp16 search operand, so the
     residual is read once per level (``vqb_rvq_level``).
 """
 from __future__ import annotations
