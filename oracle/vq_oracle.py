@@ -375,6 +375,36 @@ def vq_forward(state: CodebookState, x: torch.Tensor, opts: VQOpts, *, training:
 
 
 # --------------------------------------------------------------------------- #
+# Learnable codebook (codebooks.py:186-190, 375-377; vector_quantize_pytorch.py:261-279, 362): single head,
+# channel-last, no EMA.  Autograd-carrying restatement: gradients come from torch autograd over the same ops.
+# --------------------------------------------------------------------------- #
+
+def vq_forward_learnable(embeddings: torch.Tensor, x: torch.Tensor, *, commitment_weight: float = 1.0,
+                         sync_update_v: float = 0.0, mask: Optional[torch.Tensor] = None):
+    """`embeddings` (1,K,d) and `x` (B,n,d) may require grad.  Returns (quantize, indices, loss[1])."""
+    flat = x.float()[None]                                              # codebooks.py:354-357
+    B, n, d = x.shape
+    sim = similarities(flat.reshape(1, -1, d).detach(), embeddings.detach(), False)   # :386 (argmax only)
+    ind = sim.argmax(-1).reshape(1, B, n)                               # utils/general.py:128
+    onehot = F.one_hot(ind, embeddings.shape[1]).type(flat.dtype)       # :129
+    quant = torch.einsum("h b n c, h c d -> h b n d", onehot, embeddings)[0]   # codebooks.py:393-395 (differentiable)
+    commit_q = quant                                                    # vector_quantize_pytorch.py:262-268
+    out = x + (quant - x).detach()                                      # :273
+    if sync_update_v > 0.0:
+        out = out + sync_update_v * (out - out.detach())                # :275-279
+    loss = torch.tensor([0.0])
+    if commitment_weight > 0:
+        if mask is not None:
+            commit = F.mse_loss(commit_q, x, reduction="none")[mask].mean()   # :347-360
+        else:
+            commit = F.mse_loss(commit_q, x)                            # :362
+        loss = loss + commit * commitment_weight
+    if mask is not None:
+        out = torch.where(mask[..., None], out, x)                      # :415-418
+    return out, ind[0], loss
+
+
+# --------------------------------------------------------------------------- #
 # ResidualVQ.forward (residual_vq.py:134-269), no quantize-dropout
 # --------------------------------------------------------------------------- #
 

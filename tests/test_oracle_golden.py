@@ -51,3 +51,22 @@ def test_row_chunked_oracle_equals_unchunked():
     assert torch.equal(a.cluster_size, b.cluster_size)
     assert gu.rel_err(b.embed_avg, a.embed_avg) <= 1e-6
     assert gu.rel_err(b.embeddings, a.embeddings) <= 1e-6
+
+
+@pytest.mark.parametrize("name", ["learnable_plain", "learnable_masked_v"])
+def test_oracle_learnable_codebook_matches_reference_fixture(name):
+    """The learnable-codebook restatement reproduces the live reference's outputs AND its gradients with respect to
+    the input and the codebook (fixtures: tests/golden/make_golden_learnable.py)."""
+    import os
+    from oracle import vq_oracle as O
+    fx = torch.load(os.path.join(gu.GOLDEN_DIR, "learnable", name + ".pt"), weights_only=False)
+    cfg = fx["cfg"]
+    emb = fx["init_embeddings"].clone().requires_grad_(True)
+    x = fx["x"].clone().requires_grad_(True)
+    q, ind, loss = O.vq_forward_learnable(emb, x, commitment_weight=cfg["cw"], sync_update_v=cfg["v"], mask=fx["mask"])
+    (q * fx["w"]).sum().add(loss.sum() * 1.7).backward()
+    assert torch.equal(ind, fx["indices"])
+    assert torch.equal(q.detach(), fx["quantize"])
+    assert torch.equal(loss.detach(), fx["loss"])
+    assert torch.allclose(x.grad, fx["grad_x"], rtol=1e-6, atol=1e-9)
+    assert torch.allclose(emb.grad, fx["grad_embeddings"], rtol=1e-6, atol=1e-9)
