@@ -405,6 +405,121 @@ def vq_forward_learnable(embeddings: torch.Tensor, x: torch.Tensor, *, commitmen
 
 
 # --------------------------------------------------------------------------- #
+# Consumers of the dense N x K similarities (vector_quantize_pytorch.py:284-299 CE to given indices,
+# :338-346 CE commitment, :324-333 codebook diversity loss).  Autograd-carrying restatement on the same torch ops.
+# --------------------------------------------------------------------------- #
+
+def _log_eps(t: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:
+    """utils/general.py:25-26."""
+    return t.clamp(min=eps).log()
+
+
+def vq_forward_dense(state: CodebookState, x: torch.Tensor, opts: VQOpts, *, training: bool = True,
+                     mask: Optional[torch.Tensor] = None, targets: Optional[torch.Tensor] = None,
+                     ce_commit: bool = False, diversity_weight: float = 0.0, diversity_temperature: float = 100.0):
+    """``x`` may require grad.  With ``targets``: returns (quantize, ce) like the reference's ``return_loss`` branch
+    (:298-299).  Otherwise (quantize, indices, loss[1], {"commitment", "codebook_diversity"}).
+
+    The similarities are built on ``embeddings.detach()`` (codebooks.py:375-377, 386) and the EMA step then overwrites
+    the SAME storage through ``.data`` (:425), which autograd does not see: the reference's input gradient therefore
+    combines the PRE-update distances with the POST-update code vectors.  This restatement keeps that (the update
+    below goes through ``.data`` aliases of the state tensors)."""
+    orig = x
+    only_one = x.ndim == 2
+    if only_one:
+        x = x[:, None, :]
+    heads, multi = opts.heads, opts.heads > 1
+    B = x.shape[0]
+    if not opts.channel_last:
+        x = x.movedim(1, -1)
+    spatial = None
+    if x.ndim >= 4:
+        spatial = x.shape[1:-1]
+        x = x.reshape(B, -1, x.shape[-1])
+    if multi:
+        n, dh = x.shape[1], x.shape[-1] // heads
+        xh = x.reshape(B, n, heads, dh)
+        x = xh.permute(2, 0, 1, 3) if opts.separate_codebook_per_head else \
+            xh.permute(0, 2, 1, 3).reshape(1, B * heads, n, dh)
+    if opts.input_l2norm:
+        x = l2norm(x)                                                   # :221
+    x4 = (x if x.ndim == 4 else x[None]).float()                        # codebooks.py:354-357
+    H, Bp, n, d = x4.shape
+    K = state.embeddings.shape[1]
+    sim = similarities(x4.reshape(H, -1, d), state.embeddings.detach(), opts.codebook.use_cosine_sim)   # :386
+    sim = sim.reshape(H, Bp, n, K)                                      # :433
+
+    alias = CodebookState(state.embeddings.data, state.embed_avg.data, state.cluster_size.data, state.is_initialized)
+    with torch.no_grad():
+        quant, ind, _ = codebook_forward(alias, x.detach(), opts.codebook, training=training, mask=mask)
+    codes_q = quant                                                     # :262-268 (detached: no learnable codebook here)
+    if training:
+        quant = x + (quant - x).detach()                                # :273
+
+    def ce_loss(codes):                                                 # :284-296
+        if not multi:
+            logits = sim.permute(0, 1, 3, 2)[0]                         # 1 b n l -> b l n
+        elif opts.separate_codebook_per_head:
+            logits = sim.permute(1, 3, 2, 0)                            # c b n l -> b l n c
+        else:
+            logits = sim.reshape(B, heads, n, K).permute(0, 3, 2, 1)    # 1 (b h) n l -> b l n h
+        return F.cross_entropy(logits, codes, ignore_index=-1)
+
+    if targets is not None:
+        return quant, ce_loss(targets)                                  # :298-299
+
+    if multi:                                                           # :303-307
+        ind = ind.permute(1, 2, 0) if opts.separate_codebook_per_head else ind.reshape(B, heads, -1).permute(0, 2, 1)
+    if spatial is not None:
+        ind = ind.reshape(B, *spatial, *ind.shape[2:])
+    if only_one:
+        ind = ind[:, 0]
+    ind = ind.contiguous()
+
+    loss = torch.tensor([0.0])
+    parts = {"commitment": torch.tensor(0.0), "codebook_diversity": torch.tensor(0.0)}
+    if training:
+        if diversity_weight > 0:                                        # :324-333
+            prob = (-sim * diversity_temperature).softmax(dim=-1)
+            avg_prob = prob.reshape(-1, n, K).mean(0)                   # "... n l -> n l"
+            div = -((-avg_prob * _log_eps(avg_prob)).sum(dim=-1)).mean()
+            parts["codebook_diversity"] = div
+            loss = loss + div * diversity_weight
+        if opts.commitment_weight > 0:
+            if ce_commit:                                               # :338-346
+                if mask is not None:
+                    m = mask[..., None].expand(*mask.shape, heads) if multi else mask
+                    ind.masked_fill_(~m, -1)                            # in place: the RETURNED indices carry the -1
+                commit = ce_loss(ind)
+            elif mask is not None:                                      # :347-360
+                per = F.mse_loss(codes_q, x, reduction="none")
+                lm = mask
+                if multi:
+                    lm = mask[None, :, None, :].expand(per.shape[0], mask.shape[0], per.shape[1] // mask.shape[0],
+                                                       mask.shape[1]).reshape(per.shape[0], per.shape[1], mask.shape[1])
+                commit = per[lm].mean()
+            else:
+                commit = F.mse_loss(codes_q, x)                         # :362
+            parts["commitment"] = commit
+            loss = loss + commit * opts.commitment_weight
+
+    if multi:                                                           # :394-398
+        if opts.separate_codebook_per_head:
+            quant = quant.permute(1, 2, 0, 3).reshape(B, quant.shape[2], -1)
+        else:
+            quant = quant.reshape(B, heads, n, -1).permute(0, 2, 1, 3).reshape(B, n, -1)
+    if spatial is not None:
+        quant = quant.reshape(B, *spatial, quant.shape[-1])
+    if not opts.channel_last:
+        quant = quant.movedim(-1, 1)
+    if only_one:
+        quant = quant[:, 0]
+    if mask is not None:
+        quant = torch.where(mask[..., None], quant, orig)
+    return quant, ind, loss, parts
+
+
+# --------------------------------------------------------------------------- #
 # ResidualVQ.forward (residual_vq.py:134-269), no quantize-dropout
 # --------------------------------------------------------------------------- #
 

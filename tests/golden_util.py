@@ -37,3 +37,27 @@ def rel_err(a, b):
     """max |a-b| relative to max |b| (buffer-level relative error)."""
     a, b = a.double(), b.double()
     return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+def dense_fixture_names():
+    return sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "dense", "*.pt")))
+
+
+def load_dense(name):
+    return torch.load(os.path.join(GOLDEN_DIR, "dense", name + ".pt"), weights_only=False)
+
+
+def dense_oracle_opts(cfg):
+    """cfg schema of tests/golden/make_golden_dense.py -> oracle VQOpts."""
+    from oracle.vq_oracle import CodebookOpts, VQOpts
+    cb = CodebookOpts(threshold_ema_dead_code=0, use_cosine_sim=cfg.get("cosine", False),
+                      weights_l2norm=bool(cfg.get("l2w")))
+    return VQOpts(heads=cfg.get("heads", 1), separate_codebook_per_head=cfg.get("separate", False),
+                  channel_last=cfg.get("channel_last", True), commitment_weight=cfg.get("cw", 1.0),
+                  input_l2norm=bool(cfg.get("l2in")), codebook=cb)
+
+
+def dense_kwargs(cfg):
+    """the dense-consumer switches of a make_golden_dense.py case (oracle keyword names)."""
+    return dict(ce_commit=cfg["kind"] == "commit" or cfg.get("ce_commit", False),
+                diversity_weight=cfg.get("dw", 0.0), diversity_temperature=cfg.get("temp", 100.0))

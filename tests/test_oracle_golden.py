@@ -70,3 +70,32 @@ def test_oracle_learnable_codebook_matches_reference_fixture(name):
     assert torch.equal(loss.detach(), fx["loss"])
     assert torch.allclose(x.grad, fx["grad_x"], rtol=1e-6, atol=1e-9)
     assert torch.allclose(emb.grad, fx["grad_embeddings"], rtol=1e-6, atol=1e-9)
+
+
+@pytest.mark.parametrize("name", gu.dense_fixture_names())
+def test_oracle_dense_consumers_match_reference_fixture(name):
+    """Cross-entropy to given indices, CE commitment and the diversity loss (the consumers of the dense N x K
+    similarities): outputs, post-step buffers and the input gradient of the live reference, bit for bit
+    (fixtures: tests/golden/make_golden_dense.py).  The gradient check pins the reference's stale-codebook behaviour:
+    pre-update distances combined with post-update code vectors."""
+    fx = gu.load_dense(name)
+    cfg = fx["cfg"]
+    opts = gu.dense_oracle_opts(cfg)
+    st = O.CodebookState(fx["init"]["embeddings"].clone(), fx["init"]["embed_avg"].clone(),
+                         fx["init"]["cluster_size"].clone())
+    x = fx["x"].clone().requires_grad_(True)
+    if cfg["kind"] == "indices":
+        q, ce = O.vq_forward_dense(st, x, opts, training=cfg["training"], targets=fx["targets"])
+        (q.sum() * 0.01 + ce * 1.3 if cfg["training"] else ce * 1.3).backward()
+        assert torch.equal(ce.detach(), fx["ce"])
+    else:
+        q, ind, loss, parts = O.vq_forward_dense(st, x, opts, training=True, mask=fx["mask"], **gu.dense_kwargs(cfg))
+        ((q * fx["w"]).sum() + loss.sum() * 1.7).backward()
+        assert torch.equal(ind, fx["indices"])
+        assert torch.equal(loss.detach(), fx["loss"])
+        assert torch.equal(parts["commitment"].detach(), fx["commitment"])
+        assert torch.equal(parts["codebook_diversity"].detach(), fx["codebook_diversity"])
+    assert torch.equal(q.detach(), fx["quantize"])
+    assert torch.allclose(x.grad, fx["grad_x"], rtol=1e-6, atol=1e-9)
+    assert torch.equal(st.cluster_size, fx["after"]["cluster_size"])
+    assert gu.rel_err(st.embeddings, fx["after"]["embeddings"]) <= 1e-6
