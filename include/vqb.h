@@ -218,6 +218,41 @@ int    vqb_rvq_level_ema(const float* residual_in, float* residual_out, const fl
 int    vqb_minkey_pack(const float* score, const int64_t* idx, int64_t n, int64_t* keys, void* stream);
 int    vqb_minkey_unpack(const int64_t* keys, int64_t n, int64_t* idx, float* score, void* stream);
 
+/* ---- consumers of the dense N x K similarities, without materialising them ---------------
+ * Replaces vector_quantize_pytorch.py:284-296 (calculate_ce_loss: F.cross_entropy(similarities, codes,
+ * ignore_index=-1) -- cross-entropy to given indices :298-299 and the cross-entropy commitment loss :338-346),
+ * :324-333 (codebook diversity loss: softmax(-similarities * temperature) averaged over heads and batch) and
+ * torch autograd through codebooks.py:386 (-cdist -> ATen _euclidean_dist_backward; einsum -> bmm).
+ * fp32 CUDA-core tiled contractions with an online-softmax epilogue (csrc/dense.cu); scores follow the reference:
+ * euclid s = -sqrtf(max(|x|^2 + |c|^2 - 2 x.c, 0)), dot s = x.c.  xn2 (H,N) / cn2 (H,K): squared row norms from
+ * vqb_dense_row_norms (NULL for the dot metric).  z_k = alpha * s_k (alpha = 1 for cross-entropy, -temperature
+ * for the diversity loss).  A row belongs to position (row % n_pos).
+ *   vqb_dense_rowstats: lse_out (H,N) = log sum_k exp(z_k); target (H,N) int64 nullable, -1 = ignored:
+ *                       target_score_out (H,N) = s_target (left untouched for ignored rows)
+ *   vqb_dense_avgprob : avg_out (n_pos,K) = mean over the H * N/n_pos rows of a position of exp(z_k - lse)
+ *   vqb_dense_rowdot  : rdot_out (H,N) = sum_k exp(z_k - lse) * table[row % n_pos][k]
+ *   vqb_dense_backward: grad_x (H,N,d) fp32 = sum_k w_k ds_k/dx with
+ *                         w_k = coef[row] (p_k - [k == target[row]])              (target given, table NULL)
+ *                         w_k = coef[row] p_k (table[row % n_pos][k] - rdot[row])  (table given, target NULL)
+ *                       p_k and ds_k/dx's 1/D_k come from codebook_dist, the combined code rows from codebook_comb:
+ *                       the reference's saved `embeddings.detach()` aliases the buffer the EMA step overwrites
+ *                       before backward runs (codebooks.py:425), so its gradient pairs pre-update distances with
+ *                       post-update code vectors; pass the same pointer twice when the codebook did not move. */
+int vqb_dense_row_norms(const void* x, int x_dtype, int64_t rows, int d, float* out, void* stream);
+int vqb_dense_rowstats(const void* x, int x_dtype, const float* xn2, const float* codebook, const float* cn2,
+                       int metric, float alpha, const int64_t* target, float* lse_out, float* target_score_out,
+                       int64_t H, int64_t N, int K, int d, void* stream);
+int vqb_dense_rowdot(const void* x, int x_dtype, const float* xn2, const float* codebook, const float* cn2,
+                     int metric, float alpha, const float* lse, const float* table, int64_t n_pos,
+                     float* rdot_out, int64_t H, int64_t N, int K, int d, void* stream);
+int vqb_dense_avgprob(const void* x, int x_dtype, const float* xn2, const float* codebook, const float* cn2,
+                      int metric, float alpha, const float* lse, float* avg_out, int64_t n_pos,
+                      int64_t H, int64_t N, int K, int d, void* stream);
+int vqb_dense_backward(const void* x, int x_dtype, const float* xn2, const float* codebook_dist, const float* cn2,
+                       const float* codebook_comb, int metric, float alpha, const float* lse, const float* coef,
+                       const int64_t* target, const float* table, const float* rdot, int64_t n_pos, float* grad_x,
+                       int64_t H, int64_t N, int K, int d, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

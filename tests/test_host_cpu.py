@@ -100,10 +100,15 @@ def test_no_cpu_fallback_and_unsupported_options_fail_loudly():
         Codebook(8, 4, gumbel_params=GumbelParams(stochastic=True))
     with pytest.raises(ValueError):
         Codebook(8, 4, transform_input="tanh")
-    for kw in (dict(codebook_diversity_loss_weight=0.1), dict(orthogonal_reg_weight=1.0),
-               dict(commitment_use_cross_entropy_loss=True), dict(in_place_codebook_optimizer=torch.optim.SGD)):
+    for kw in (dict(orthogonal_reg_weight=1.0), dict(in_place_codebook_optimizer=torch.optim.SGD)):
         with pytest.raises(NotImplementedError):
             VectorQuantize(dim=8, codebook_params=CodebookParams(dim=8, codebook_size=4), **kw)
+    # the consumers of the dense similarities are built (csrc/dense.cu) -- except with a learnable codebook
+    for kw in (dict(codebook_diversity_loss_weight=0.1), dict(commitment_use_cross_entropy_loss=True)):
+        VectorQuantize(dim=8, codebook_params=CodebookParams(dim=8, codebook_size=4), **kw)
+        with pytest.raises(NotImplementedError):
+            VectorQuantize(dim=8, codebook_params=CodebookParams(dim=8, codebook_size=4, learnable_codebook=True,
+                                                                 ema_update=False), **kw)
     with pytest.raises(AssertionError):          # reference: sync_update_v needs a learnable codebook
         VectorQuantize(dim=8, codebook_params=CodebookParams(dim=8, codebook_size=4), sync_update_v=0.5)
     with pytest.raises(AssertionError):          # reference: learnable codebook is not compatible with the EMA update

@@ -55,6 +55,12 @@ SIGNATURES = {
                                   _p, _p]),
     "vqb_minkey_pack": (_i32, [_p, _p, _i64, _p, _p]),
     "vqb_minkey_unpack": (_i32, [_p, _i64, _p, _p, _p]),
+    "vqb_dense_row_norms": (_i32, [_p, _i32, _i64, _i32, _p, _p]),
+    "vqb_dense_rowstats": (_i32, [_p, _i32, _p, _p, _p, _i32, _f32, _p, _p, _p, _i64, _i64, _i32, _i32, _p]),
+    "vqb_dense_rowdot": (_i32, [_p, _i32, _p, _p, _p, _i32, _f32, _p, _p, _i64, _p, _i64, _i64, _i32, _i32, _p]),
+    "vqb_dense_avgprob": (_i32, [_p, _i32, _p, _p, _p, _i32, _f32, _p, _p, _i64, _i64, _i64, _i32, _i32, _p]),
+    "vqb_dense_backward": (_i32, [_p, _i32, _p, _p, _p, _p, _i32, _f32, _p, _p, _p, _p, _p, _i64, _p, _i64, _i64, _i32,
+                                  _i32, _p]),
 }
 
 _lib = None

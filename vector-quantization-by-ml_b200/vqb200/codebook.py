@@ -91,6 +91,7 @@ class Codebook(nn.Module):
         self._cache: Optional[torch.Tensor] = None
         self._cache_key = None
         self._dirty = True
+        self.dense_ctx = None
         self.last_search_ws: Optional[torch.Tensor] = None
         self.fused_quantize_ema = True     # False: separate gather and EMA-reduce passes (same results)
 
@@ -209,9 +210,11 @@ class Codebook(nn.Module):
 
     # ------------------------------------------------------------------ core
     def _run(self, x: torch.Tensor, mask: Optional[torch.Tensor], freeze_codebook: bool, fuse_st: bool,
-             want_commit: bool, normalize_input: bool = False):
+             want_commit: bool, normalize_input: bool = False, keep_dense: bool = False):
         """Shared by forward() and VectorQuantize.  x: (H, ..., d).  Returns (quantize (H,...,d), idx (H,...),
-        commit scalar | None)."""
+        commit scalar | None).  `keep_dense`: leave in `self.dense_ctx` what the consumers of the dense similarities
+        (cross-entropy to indices, CE commitment, diversity loss) need: the (H,N,d) latents the search saw and the
+        codebook as it was BEFORE this forward's EMA step (reference codebooks.py:386 runs before :425)."""
         if not x.is_cuda:
             raise RuntimeError(f"vqb200.Codebook: input must be on a CUDA device (got {x.device}); "
                                "there is no CPU implementation")
@@ -240,6 +243,9 @@ class Codebook(nn.Module):
             self.is_initialized = True
 
         emb = self.embeddings.detach()
+        update = self.training and self.ema_update and not freeze_codebook
+        if keep_dense:
+            self.dense_ctx = ops._DenseCtx(flat, emb.clone() if update else emb, self.embeddings, self.use_cosine_sim)
         idx, _, ws = ops.search(flat, emb, self._codebook_cache(), self.use_cosine_sim, latents_prepared=prepared)
         self.last_search_ws = ws
 

@@ -384,3 +384,132 @@ def minkey_unpack(keys: torch.Tensor, want_score: bool = False):
     L.check(L.lib().vqb_minkey_unpack(L.ptr(keys), keys.numel(), L.ptr(idx), L.ptr(score), L.stream_ptr(keys.device)),
             "vqb_minkey_unpack")
     return idx, score
+
+
+# ---------------------------------------------------------------------------------------------
+# consumers of the dense N x K similarities (cross-entropy to indices, CE commitment, diversity loss):
+# fp32 CUDA-core passes with an online softmax, nothing of size N x K is written (csrc/dense.cu)
+# ---------------------------------------------------------------------------------------------
+def dense_row_norms(t: torch.Tensor) -> torch.Tensor:
+    """|row|^2 of a (..., d) tensor -> (...,) fp32."""
+    L.require_cuda(t, "t")
+    d = t.shape[-1]
+    out = torch.empty(t.shape[:-1], dtype=torch.float32, device=t.device)
+    L.check(L.lib().vqb_dense_row_norms(L.ptr(t), L.dtype_code(t), t.numel() // d if d else 0, d, L.ptr(out),
+                                        L.stream_ptr(t.device)), "vqb_dense_row_norms")
+    return out
+
+
+def dense_rowstats(x, xn2, emb, cn2, use_cosine_sim: bool, alpha: float, target: Optional[torch.Tensor]):
+    """lse (H,N) = log sum_k exp(alpha s_k) and, with `target` (H,N) int64 (-1 = ignore), the score of the target."""
+    L.require_cuda(x, "x")
+    H, N, d = x.shape
+    K = emb.shape[1]
+    lse = torch.empty((H, N), dtype=torch.float32, device=x.device)
+    st = torch.zeros((H, N), dtype=torch.float32, device=x.device) if target is not None else None
+    L.check(L.lib().vqb_dense_rowstats(L.ptr(x), L.dtype_code(x), L.ptr(xn2), L.ptr(emb), L.ptr(cn2),
+                                       _metric(use_cosine_sim), float(alpha), L.ptr(target), L.ptr(lse), L.ptr(st),
+                                       H, N, K, d, L.stream_ptr(x.device)), "vqb_dense_rowstats")
+    return lse, st
+
+
+def dense_avgprob(x, xn2, emb, cn2, use_cosine_sim: bool, alpha: float, lse, n_pos: int) -> torch.Tensor:
+    """(n_pos, K): softmax(alpha s) averaged over the codebooks and the N / n_pos batch entries of each position."""
+    H, N, d = x.shape
+    K = emb.shape[1]
+    avg = torch.empty((n_pos, K), dtype=torch.float32, device=x.device)
+    L.check(L.lib().vqb_dense_avgprob(L.ptr(x), L.dtype_code(x), L.ptr(xn2), L.ptr(emb), L.ptr(cn2),
+                                      _metric(use_cosine_sim), float(alpha), L.ptr(lse), L.ptr(avg), int(n_pos),
+                                      H, N, K, d, L.stream_ptr(x.device)), "vqb_dense_avgprob")
+    return avg
+
+
+def dense_rowdot(x, xn2, emb, cn2, use_cosine_sim: bool, alpha: float, lse, table, n_pos: int) -> torch.Tensor:
+    """(H,N): sum_k softmax(alpha s)_k * table[row % n_pos, k]."""
+    H, N, d = x.shape
+    K = emb.shape[1]
+    out = torch.empty((H, N), dtype=torch.float32, device=x.device)
+    L.check(L.lib().vqb_dense_rowdot(L.ptr(x), L.dtype_code(x), L.ptr(xn2), L.ptr(emb), L.ptr(cn2),
+                                     _metric(use_cosine_sim), float(alpha), L.ptr(lse), L.ptr(table), int(n_pos),
+                                     L.ptr(out), H, N, K, d, L.stream_ptr(x.device)), "vqb_dense_rowdot")
+    return out
+
+
+def dense_backward(x, xn2, emb_dist, cn2, emb_comb, use_cosine_sim: bool, alpha: float, lse, coef, target=None,
+                   table=None, rdot=None, n_pos: int = 1) -> torch.Tensor:
+    """Input gradient (H,N,d) fp32 of a loss on the similarities (see include/vqb.h: vqb_dense_backward)."""
+    H, N, d = x.shape
+    K = emb_dist.shape[1]
+    gx = torch.empty((H, N, d), dtype=torch.float32, device=x.device)
+    L.check(L.lib().vqb_dense_backward(L.ptr(x), L.dtype_code(x), L.ptr(xn2), L.ptr(emb_dist), L.ptr(cn2),
+                                       L.ptr(emb_comb), _metric(use_cosine_sim), float(alpha), L.ptr(lse), L.ptr(coef),
+                                       L.ptr(target), L.ptr(table), L.ptr(rdot), int(n_pos), L.ptr(gx), H, N, K, d,
+                                       L.stream_ptr(x.device)), "vqb_dense_backward")
+    return gx
+
+
+class _DenseCtx:
+    """What the dense consumers of one forward share: latents (H,N,d), the codebook the similarities are defined on
+    (`emb_dist`: a private copy when the EMA step overwrites `embeddings` in this forward) and the live buffer
+    (`emb_live`) whose rows the reference's backward combines (see csrc/dense.cu header), plus the row norms."""
+
+    def __init__(self, x, emb_dist, emb_live, use_cosine_sim):
+        self.x, self.emb_dist, self.emb_live, self.cos = x, emb_dist, emb_live, bool(use_cosine_sim)
+        self.xn2 = None if self.cos else dense_row_norms(x.detach())
+        self.cn2 = None if self.cos else dense_row_norms(emb_dist)
+
+
+class _DenseCE(torch.autograd.Function):
+    """mean over rows with target >= 0 of (logsumexp_k s_k - s_target): F.cross_entropy(similarities, codes,
+    ignore_index=-1) of reference vector_quantize_pytorch.py:284-296 on the (H,N) row layout."""
+
+    @staticmethod
+    def forward(ctx, x, dc, target):
+        lse, st = dense_rowstats(x, dc.xn2, dc.emb_dist, dc.cn2, dc.cos, 1.0, target)
+        valid = target >= 0
+        n_valid = valid.sum()
+        loss = (((lse.double() - st.double()) * valid).sum() / n_valid).float()
+        ctx.dc, ctx.lse, ctx.target, ctx.valid, ctx.n_valid = dc, lse, target, valid, n_valid
+        ctx.save_for_backward(x)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        dc, (x,) = ctx.dc, ctx.saved_tensors
+        coef = (g.float() / ctx.n_valid) * ctx.valid
+        gx = dense_backward(x, dc.xn2, dc.emb_dist, dc.cn2, dc.emb_live.detach(), dc.cos, 1.0, ctx.lse,
+                            coef.contiguous(), target=ctx.target)
+        return gx.to(x.dtype), None, None
+
+
+def dense_cross_entropy(dc: "_DenseCtx", target: torch.Tensor) -> torch.Tensor:
+    """`target` (H,N) int64 in the row layout of dc.x, -1 = ignored."""
+    return _DenseCE.apply(dc.x, dc, target.contiguous())
+
+
+class _DenseAvgProb(torch.autograd.Function):
+    """avg_prob (n_pos, K) of reference vector_quantize_pytorch.py:324-328: softmax(-similarities * temperature)
+    averaged over heads and batch; the entropy on top of it is K-sized torch glue."""
+
+    @staticmethod
+    def forward(ctx, x, dc, n_pos, alpha):
+        lse, _ = dense_rowstats(x, dc.xn2, dc.emb_dist, dc.cn2, dc.cos, alpha, None)
+        avg = dense_avgprob(x, dc.xn2, dc.emb_dist, dc.cn2, dc.cos, alpha, lse, n_pos)
+        ctx.dc, ctx.lse, ctx.n_pos, ctx.alpha = dc, lse, n_pos, alpha
+        ctx.save_for_backward(x)
+        return avg
+
+    @staticmethod
+    def backward(ctx, g_avg):
+        dc, (x,), n_pos, alpha = ctx.dc, ctx.saved_tensors, ctx.n_pos, ctx.alpha
+        H, N, _ = x.shape
+        table = g_avg.contiguous().float()
+        rdot = dense_rowdot(x, dc.xn2, dc.emb_dist, dc.cn2, dc.cos, alpha, ctx.lse, table, n_pos)
+        coef = torch.full((H, N), alpha / (H * (N // n_pos)), dtype=torch.float32, device=x.device)
+        gx = dense_backward(x, dc.xn2, dc.emb_dist, dc.cn2, dc.emb_live.detach(), dc.cos, alpha, ctx.lse, coef,
+                            table=table, rdot=rdot, n_pos=n_pos)
+        return gx.to(x.dtype), None, None, None
+
+
+def dense_avg_prob(dc: "_DenseCtx", n_pos: int, temperature: float) -> torch.Tensor:
+    return _DenseAvgProb.apply(dc.x, dc, int(n_pos), -float(temperature))

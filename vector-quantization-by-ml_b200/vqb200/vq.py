@@ -2,10 +2,13 @@
 
 Same constructor arguments and ``forward`` returns.  The layout glue (channel-first, images/video,
 multi-head, projections, masks) is host code; search, gather + straight-through + commitment loss
-and the EMA update are CUDA kernels behind ``Codebook``.  Options that need the dense N x K
-similarity matrix (cross-entropy to given indices, CE commitment, diversity loss), orthogonal regularisation
-(broken in the reference itself) and the in-place codebook optimizer raise NotImplementedError; a learnable
-codebook (`learnable_codebook=True, ema_update=False`, optionally `sync_update_v`) is supported.
+and the EMA update are CUDA kernels behind ``Codebook``.  The consumers of the dense N x K similarity
+matrix -- cross-entropy to given indices (reference :284-299), the cross-entropy commitment loss (:338-346)
+and the codebook diversity loss (:324-333) -- run as fp32 online-softmax passes that never write the
+matrix (csrc/dense.cu), forward and input gradient.  Orthogonal regularisation (broken in the reference
+itself), the in-place codebook optimizer and a learnable codebook combined with the dense consumers raise
+NotImplementedError; a learnable codebook (`learnable_codebook=True, ema_update=False`, optionally
+`sync_update_v`) with the mse commitment loss is supported.
 """
 from __future__ import annotations
 
@@ -16,6 +19,7 @@ import torch
 import torch.distributed as dist
 from torch import nn
 
+from . import ops
 from .codebook import Codebook
 from .params import CodebookParams
 
@@ -53,18 +57,22 @@ class VectorQuantize(nn.Module):
         self.has_commitment_loss = commitment_weight > 0.0
         self.commitment_weight = commitment_weight
 
+        self.commitment_use_cross_entropy_loss = commitment_use_cross_entropy_loss
+        self.codebook_diversity_loss_weight = codebook_diversity_loss_weight
+        self.codebook_diversity_temperature = codebook_diversity_temperature
+        self.has_codebook_diversity_loss = codebook_diversity_loss_weight > 0.0
+
         unsupported = []
-        if commitment_use_cross_entropy_loss:
-            unsupported.append("commitment_use_cross_entropy_loss (needs the dense N x K similarities)")
         if orthogonal_reg_weight > 0.0:
             unsupported.append("orthogonal_reg_weight (the reference itself raises AttributeError on this path: "
                                "vector_quantize_pytorch.py:367 reads the non-existent `_codebook.embed`)")
-        if codebook_diversity_loss_weight > 0.0:
-            unsupported.append("codebook_diversity_loss_weight (needs the dense N x K similarities)")
         if in_place_codebook_optimizer is not None:
             unsupported.append("in_place_codebook_optimizer (a second search inside forward; not built)")
+        if codebook_params.learnable_codebook and (commitment_use_cross_entropy_loss or self.has_codebook_diversity_loss):
+            unsupported.append("learnable_codebook with the cross-entropy commitment / diversity loss (the codebook "
+                               "gradient of the dense similarities is not built)")
         if unsupported:
-            raise NotImplementedError("vqb200.VectorQuantize: outside the accelerated EMA path: " + "; ".join(unsupported))
+            raise NotImplementedError("vqb200.VectorQuantize: outside the accelerated path: " + "; ".join(unsupported))
 
         if sync_codebook is None:
             sync_codebook = _is_distributed()
@@ -115,10 +123,21 @@ class VectorQuantize(nn.Module):
     def get_output_from_indices(self, indices):
         return self.project_out(self.get_codes_from_indices(indices))
 
+    def _rows_of(self, t, B, multi):
+        """(b, n[, h]) per-position integers -> the (H, N) row layout of the codebook's latents (reference
+        vector_quantize_pytorch.py:217-219: "h b n d" / "1 (b h) n d")."""
+        if not multi:
+            return t.reshape(1, -1)
+        t = t.reshape(B, -1, self.heads)
+        if self.separate_codebook_per_head:
+            return t.permute(2, 0, 1).reshape(self.heads, -1)
+        return t.permute(0, 2, 1).reshape(1, -1)
+
     def forward(self, x, indices=None, mask=None, freeze_codebook=False, return_loss_breakdown=False):
-        if indices is not None:
-            raise NotImplementedError("vqb200.VectorQuantize: cross-entropy to given indices needs the dense "
-                                      "N x K similarities, which this path never materialises")
+        return_loss = indices is not None
+        if return_loss and self.learnable_codebook:
+            raise NotImplementedError("vqb200.VectorQuantize: cross-entropy to given indices with a learnable codebook "
+                                      "(the codebook gradient of the dense similarities is not built)")
         orig_input = x
         only_one = x.ndim == 2
         if only_one:
@@ -142,18 +161,31 @@ class VectorQuantize(nn.Module):
                 xh.permute(0, 2, 1, 3).reshape(1, B * heads, n, dh)
         cb_in = x if x.ndim == 4 else x[None]
         training = self.training
-        want_commit = training and self.has_commitment_loss
+        ce_commit = training and self.has_commitment_loss and self.commitment_use_cross_entropy_loss
+        want_commit = training and self.has_commitment_loss and not ce_commit
+        diversity = training and self.has_codebook_diversity_loss
+        keep_dense = return_loss or ce_commit or diversity
         # transform_input (reference :221) happens inside _run, fused with the search's operand preparation
         quantize, embed_ind, commit = self._codebook._run(cb_in, mask, freeze_codebook, fuse_st=True,
                                                           want_commit=want_commit,
-                                                          normalize_input=self._codebook.input_l2norm)
+                                                          normalize_input=self._codebook.input_l2norm,
+                                                          keep_dense=keep_dense)
+        dense = self._codebook.dense_ctx
+        self._codebook.dense_ctx = None
+        rows_idx = embed_ind.reshape(embed_ind.shape[0], -1)          # (H, N): the row layout of the dense passes
         if x.ndim < 4:
             quantize, embed_ind = quantize[0], embed_ind[0]
         if training and self.sync_update_v > 0.0:
             # reference :275-279: value unchanged, the gradient to the input is scaled by (1 + v)
             quantize = quantize + self.sync_update_v * (quantize - quantize.detach())
 
-        commit_loss = self.zero
+        if return_loss:
+            # reference :284-299: F.cross_entropy(similarities, indices, ignore_index=-1); returns the codebook-side
+            # quantize (before head merge / projection) and the loss only
+            target = self._rows_of(indices.to(device=device, dtype=torch.int64), B, multi)
+            return quantize, ops.dense_cross_entropy(dense, target)
+
+        commit_loss = diversity_loss = self.zero
         if multi:
             if self.separate_codebook_per_head:
                 embed_ind = embed_ind.permute(1, 2, 0)
@@ -165,7 +197,25 @@ class VectorQuantize(nn.Module):
             embed_ind = embed_ind[:, 0]
 
         loss = torch.tensor([0.0], device=device, requires_grad=training)
-        if want_commit:
+        if diversity:
+            # reference :324-333: softmax(-similarities * T) averaged over heads and batch ("... n l -> n l"),
+            # then the negative entropy per position; the (n, K) entropy is torch glue on the kernel's output
+            n_pos = cb_in.shape[-2]
+            avg_prob = ops.dense_avg_prob(dense, n_pos, self.codebook_diversity_temperature)
+            diversity_loss = -((-avg_prob * avg_prob.clamp(min=1e-5).log()).sum(dim=-1)).mean()
+            loss = loss + diversity_loss * self.codebook_diversity_loss_weight
+        if ce_commit:
+            # reference :338-346: cross-entropy of the similarities against the chosen codes; masked positions are
+            # ignored AND the returned indices carry -1 there (masked_fill_ in place at :344)
+            target = rows_idx
+            if mask is not None:
+                keep = self._codebook._expand_mask(mask, rows_idx.shape[1]).bool()
+                target = torch.where(keep[None], rows_idx, torch.full_like(rows_idx, -1))
+                m = mask.reshape(embed_ind.shape[:-1] if multi else embed_ind.shape)
+                embed_ind = embed_ind.masked_fill(~(m[..., None] if multi else m), -1)
+            commit_loss = ops.dense_cross_entropy(dense, target)
+            loss = loss + commit_loss * self.commitment_weight
+        elif want_commit:
             commit_loss = commit
             loss = loss + commit_loss * self.commitment_weight
 
@@ -187,4 +237,4 @@ class VectorQuantize(nn.Module):
 
         if not return_loss_breakdown:
             return quantize, embed_ind, loss
-        return quantize, embed_ind, loss, LossBreakdown(commit_loss, self.zero, self.zero, self.zero)
+        return quantize, embed_ind, loss, LossBreakdown(commit_loss, diversity_loss, self.zero, self.zero)
