@@ -89,11 +89,14 @@ def test_backward_through_straight_through_and_commitment():
     vq = make_vq()
     x = torch.randn(2, 50, DIM, device=DEV, requires_grad=True)
     vq.train()
+    before = vq.codebook.clone()
     q, ind, loss = vq(x)
     (q.sum() + loss.sum()).backward()
     assert x.grad is not None and x.grad.shape == x.shape and torch.isfinite(x.grad).all()
-    # d(sum q)/dx = 1 (straight-through) plus the commitment term 2 (x - c) / numel
-    c = vq.codebook[ind]
+    assert not torch.equal(vq.codebook, before)          # the EMA step moved the codebook before backward ran
+    # d(sum q)/dx = 1 (straight-through) plus the commitment term 2 (x - c) / numel with the codes the loss was
+    # computed on: the PRE-update codebook (reference: commit_quantize is materialised before the EMA step)
+    c = before[ind]
     ref = torch.ones_like(x) + 2 * (x.detach() - c) / x.numel()
     assert torch.allclose(x.grad, ref, rtol=1e-5, atol=1e-6)
 

@@ -133,7 +133,12 @@ def test_dense_consumers_match_reference_fixture(name):
         assert torch.allclose(bd.commitment.detach().cpu(), fx["commitment"], rtol=1e-5)
         assert torch.allclose(bd.codebook_diversity.detach().cpu(), fx["codebook_diversity"], rtol=1e-5)
     assert __import__("vqb200").ops.launch_count() > launches0
-    assert torch.equal(q.detach().cpu(), fx["quantize"])
+    if cfg.get("l2in"):
+        # the input normalisation on the device and torch's on the CPU may differ in the last bit (as in the cosine
+        # cases of test_gpu_parity.py); given x^ the quantized vectors are exact
+        assert _rel(q.detach().cpu(), fx["quantize"]) <= 1e-6
+    else:
+        assert torch.equal(q.detach().cpu(), fx["quantize"])
     assert _rel(x.grad.cpu(), fx["grad_x"]) <= 1e-5
     if cfg["training"]:
         assert torch.equal(vq._codebook.cluster_size.cpu(), fx["after"]["cluster_size"])

@@ -449,8 +449,8 @@ extern "C" int vqb_dense_rowstats(const void* x, int x_dtype, const float* xn2, 
                                   float* lse_out, float* target_score_out, int64_t H, int64_t N, int K, int d,
                                   void* stream) {
   if (int rc = check_common(x, codebook, H, N, K, d, metric)) return rc;
-  VQB_REQUIRE(lse_out != nullptr, VQB_ERR_INVALID, "vqb_dense_rowstats: lse_out is null");
-  VQB_REQUIRE(metric == VQB_DOT || (xn2 != nullptr && cn2 != nullptr), VQB_ERR_INVALID,
+  VQB_REQUIRE(lse_out != nullptr || N == 0, VQB_ERR_INVALID, "vqb_dense_rowstats: lse_out is null");
+  VQB_REQUIRE(metric == VQB_DOT || N == 0 || (xn2 != nullptr && cn2 != nullptr), VQB_ERR_INVALID,
               "vqb_dense_rowstats: the Euclidean metric needs the row norms of x and of the codebook");
   if (N == 0) return VQB_OK;
   cudaStream_t st = (cudaStream_t)stream;
@@ -466,10 +466,11 @@ extern "C" int vqb_dense_rowdot(const void* x, int x_dtype, const float* xn2, co
                                 int metric, float alpha, const float* lse, const float* table, int64_t n_pos,
                                 float* rdot_out, int64_t H, int64_t N, int K, int d, void* stream) {
   if (int rc = check_common(x, codebook, H, N, K, d, metric)) return rc;
-  VQB_REQUIRE(lse != nullptr && table != nullptr && rdot_out != nullptr, VQB_ERR_INVALID, "vqb_dense_rowdot: null pointer");
+  VQB_REQUIRE(N == 0 || (lse != nullptr && table != nullptr && rdot_out != nullptr), VQB_ERR_INVALID,
+              "vqb_dense_rowdot: null pointer");
   VQB_REQUIRE(n_pos >= 1 && N % n_pos == 0, VQB_ERR_INVALID, "vqb_dense_rowdot: N=%lld is not a multiple of n_pos=%lld",
               (long long)N, (long long)n_pos);
-  VQB_REQUIRE(metric == VQB_DOT || (xn2 != nullptr && cn2 != nullptr), VQB_ERR_INVALID,
+  VQB_REQUIRE(metric == VQB_DOT || N == 0 || (xn2 != nullptr && cn2 != nullptr), VQB_ERR_INVALID,
               "vqb_dense_rowdot: the Euclidean metric needs the row norms");
   if (N == 0) return VQB_OK;
   cudaStream_t st = (cudaStream_t)stream;
@@ -506,13 +507,13 @@ extern "C" int vqb_dense_backward(const void* x, int x_dtype, const float* xn2, 
                                   const float* rdot, int64_t n_pos, float* grad_x, int64_t H, int64_t N, int K, int d,
                                   void* stream) {
   if (int rc = check_common(x, codebook_dist, H, N, K, d, metric)) return rc;
-  VQB_REQUIRE(codebook_comb != nullptr && lse != nullptr && coef != nullptr && grad_x != nullptr, VQB_ERR_INVALID,
-              "vqb_dense_backward: null pointer");
+  VQB_REQUIRE(N == 0 || (codebook_comb != nullptr && lse != nullptr && coef != nullptr && grad_x != nullptr),
+              VQB_ERR_INVALID, "vqb_dense_backward: null pointer");
   VQB_REQUIRE((target != nullptr) != (table != nullptr), VQB_ERR_INVALID,
               "vqb_dense_backward: exactly one of target (cross-entropy) and table (diversity) must be given");
   VQB_REQUIRE(table == nullptr || (rdot != nullptr && n_pos >= 1 && N % n_pos == 0), VQB_ERR_INVALID,
               "vqb_dense_backward: the diversity form needs rdot and N a multiple of n_pos");
-  VQB_REQUIRE(metric == VQB_DOT || (xn2 != nullptr && cn2 != nullptr), VQB_ERR_INVALID,
+  VQB_REQUIRE(metric == VQB_DOT || N == 0 || (xn2 != nullptr && cn2 != nullptr), VQB_ERR_INVALID,
               "vqb_dense_backward: the Euclidean metric needs the row norms");
   if (N == 0) return VQB_OK;
   cudaStream_t st = (cudaStream_t)stream;

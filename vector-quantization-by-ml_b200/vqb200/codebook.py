@@ -230,8 +230,9 @@ class Codebook(nn.Module):
             # transform_input="l2norm" (reference vector_quantize_pytorch.py:221): normalisation and the search's operand
             # preparation share one pass over x when the codebook cache is already final
             if torch.is_grad_enabled() and flat.requires_grad:
-                # the encoder's gradient passes through the normalisation: torch's own (differentiable) op
-                flat = torch.nn.functional.normalize(flat.float(), p=2, dim=-1)
+                # the encoder's gradient passes through the normalisation: same kernel forward (so the values do not
+                # depend on whether a gradient is wanted), F.normalize's Jacobian on the way back
+                flat = ops.l2norm_rows_autograd(flat)
             elif self.is_initialized and ops.l2norm_prepare_supported(d):
                 flat = ops.l2norm_prepare(flat, self.codebook_size, self._codebook_cache())
                 prepared = True
@@ -244,8 +245,13 @@ class Codebook(nn.Module):
 
         emb = self.embeddings.detach()
         update = self.training and self.ema_update and not freeze_codebook
+        if update and (keep_dense or (torch.is_grad_enabled() and flat.requires_grad)):
+            # this forward's EMA step overwrites `embeddings` in place before backward runs; the reference's
+            # commitment loss holds the gathered PRE-update codes (vector_quantize_pytorch.py:262-268, a tensor
+            # materialised at codebooks.py:395 before :425), so everything saved for backward reads a snapshot
+            emb = emb.clone()
         if keep_dense:
-            self.dense_ctx = ops._DenseCtx(flat, emb.clone() if update else emb, self.embeddings, self.use_cosine_sim)
+            self.dense_ctx = ops._DenseCtx(flat, emb, self.embeddings, self.use_cosine_sim)
         idx, _, ws = ops.search(flat, emb, self._codebook_cache(), self.use_cosine_sim, latents_prepared=prepared)
         self.last_search_ws = ws
 

@@ -117,6 +117,31 @@ def l2norm_rows(x: torch.Tensor) -> torch.Tensor:
     return out
 
 
+class _L2NormRows(torch.autograd.Function):
+    """x / max(|x|, 1e-12) by the kernel (bit-identical with or without autograd), Jacobian of F.normalize on the way
+    back (reference utils/losses.py:19 under autograd)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        y = l2norm_rows(x.contiguous())
+        ctx.save_for_backward(x, y)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        x, y = ctx.saved_tensors
+        norm = x.float().norm(dim=-1, keepdim=True)
+        denom = norm.clamp_min(1e-12)
+        # y = x / denom;  d denom / dx = x / norm where norm > eps, else 0
+        proj = (g * y).sum(dim=-1, keepdim=True) * torch.where(norm > 1e-12, denom / norm.clamp_min(1e-38),
+                                                               torch.zeros_like(norm))
+        return ((g - y * proj) / denom).to(x.dtype)
+
+
+def l2norm_rows_autograd(x: torch.Tensor) -> torch.Tensor:
+    return _L2NormRows.apply(x)
+
+
 def l2norm_prepare_supported(d: int) -> bool:
     return bool(L.lib().vqb_l2norm_prepare_supported(int(d)))
 
