@@ -380,10 +380,26 @@ def vq_forward(state: CodebookState, x: torch.Tensor, opts: VQOpts, *, training:
 # --------------------------------------------------------------------------- #
 
 def vq_forward_learnable(embeddings: torch.Tensor, x: torch.Tensor, *, commitment_weight: float = 1.0,
-                         sync_update_v: float = 0.0, mask: Optional[torch.Tensor] = None):
-    """`embeddings` (1,K,d) and `x` (B,n,d) may require grad.  Returns (quantize, indices, loss[1])."""
-    flat = x.float()[None]                                              # codebooks.py:354-357
+                         sync_update_v: float = 0.0, mask: Optional[torch.Tensor] = None, inplace_optimizer=None):
+    """`embeddings` (1,K,d) and `x` (B,n,d) may require grad.  Returns (quantize, indices, loss[1]); with
+    `inplace_optimizer` (a torch optimizer over [embeddings]; vector_quantize_pytorch.py:233-256) the codebook is
+    first stepped on mse(codes, x.detach()) inside the forward, and that loss is returned as a fourth value."""
     B, n, d = x.shape
+    inplace_loss = None
+    if inplace_optimizer is not None:
+        xd = x.detach().float()
+        sim0 = similarities(xd.reshape(1, -1, d), embeddings.detach(), False)
+        oh0 = F.one_hot(sim0.argmax(-1).reshape(1, B, n), embeddings.shape[1]).type(xd.dtype)
+        q0 = torch.einsum("h b n c, h c d -> h b n d", oh0, embeddings)[0]
+        if mask is not None:
+            inplace_loss = F.mse_loss(q0, xd, reduction="none")[mask].mean()   # :234-246
+        else:
+            inplace_loss = F.mse_loss(q0, xd)                            # :249
+        inplace_loss.backward()                                         # :251-253
+        inplace_optimizer.step()
+        inplace_optimizer.zero_grad()
+        inplace_loss = inplace_loss.detach()
+    flat = x.float()[None]                                              # codebooks.py:354-357
     sim = similarities(flat.reshape(1, -1, d).detach(), embeddings.detach(), False)   # :386 (argmax only)
     ind = sim.argmax(-1).reshape(1, B, n)                               # utils/general.py:128
     onehot = F.one_hot(ind, embeddings.shape[1]).type(flat.dtype)       # :129
@@ -401,6 +417,8 @@ def vq_forward_learnable(embeddings: torch.Tensor, x: torch.Tensor, *, commitmen
         loss = loss + commit * commitment_weight
     if mask is not None:
         out = torch.where(mask[..., None], out, x)                      # :415-418
+    if inplace_optimizer is not None:
+        return out, ind[0], loss, inplace_loss
     return out, ind[0], loss
 
 

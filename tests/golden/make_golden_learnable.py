@@ -16,6 +16,10 @@ import make_golden as MG  # noqa: E402  (einx stand-in + reference import)
 CASES = {
     "learnable_plain": {"dim": 32, "K": 48, "shape": (3, 70, 32), "mask": False, "v": 0.0, "cw": 1.0},
     "learnable_masked_v": {"dim": 16, "K": 20, "shape": (2, 33, 16), "mask": True, "v": 0.3, "cw": 0.25},
+    # in_place_codebook_optimizer (reference vector_quantize_pytorch.py:233-256): an SGD step on the codebook inside
+    # forward, then a second codebook pass; "lr" = learning rate of that SGD
+    "inplace_sgd": {"dim": 24, "K": 40, "shape": (3, 50, 24), "mask": False, "v": 0.0, "cw": 1.0, "lr": 0.5},
+    "inplace_sgd_masked": {"dim": 16, "K": 24, "shape": (2, 41, 16), "mask": True, "v": 0.2, "cw": 0.5, "lr": 2.0},
 }
 
 
@@ -25,8 +29,11 @@ def main():
         torch.manual_seed(0)
         cp = CodebookParams(dim=cfg["dim"], codebook_size=cfg["K"], learnable_codebook=True, ema_update=False,
                             threshold_ema_dead_code=0)
+        extra = {}
+        if "lr" in cfg:
+            extra["in_place_codebook_optimizer"] = lambda params, lr=cfg["lr"]: torch.optim.SGD(params, lr=lr)
         vq = VectorQuantize(dim=cfg["dim"], codebook_params=cp, commitment_weight=cfg["cw"], sync_update_v=cfg["v"],
-                            sync_codebook=False).train()
+                            sync_codebook=False, **extra).train()
         g = torch.Generator().manual_seed(7)
         with torch.no_grad():
             vq._codebook.embeddings.copy_(torch.randn(vq._codebook.embeddings.shape, generator=g) * 0.7)
@@ -37,11 +44,13 @@ def main():
             mask = torch.rand(b, n, generator=g) > 0.3
         w = torch.randn(*cfg["shape"], generator=g)
         init = vq._codebook.embeddings.detach().clone()
-        q, ind, loss = vq(x, mask=mask)
+        q, ind, loss, bd = vq(x, mask=mask, return_loss_breakdown=True)
         (q * w).sum().add(loss.sum() * 1.7).backward()
         fx = {"cfg": cfg, "x": x.detach().clone(), "mask": mask, "w": w, "init_embeddings": init,
               "quantize": q.detach().clone(), "indices": ind.clone(), "loss": loss.detach().clone(),
-              "grad_x": x.grad.clone(), "grad_embeddings": vq._codebook.embeddings.grad.clone()}
+              "grad_x": x.grad.clone(), "grad_embeddings": vq._codebook.embeddings.grad.clone(),
+              "inplace_optimize": bd.inplace_optimize.detach().clone(),
+              "after_embeddings": vq._codebook.embeddings.detach().clone()}
         torch.save(fx, os.path.join(HERE, "learnable", name + ".pt"))
         print(name, "loss", float(loss), "|grad_emb|", float(fx["grad_embeddings"].abs().max()))
 

@@ -205,3 +205,39 @@ def test_dense_consumers_medium_shape_bf16_and_eval_indices():
     s2 = R.sims(x64, cb.embeddings.double(), False)
     assert torch.allclose(ce2.double(), torch.nn.functional.cross_entropy(s2[0], tgt.reshape(-1)), rtol=1e-5)
     assert torch.equal(cb.embeddings, before)
+
+
+def test_residual_vq_levels_carry_the_dense_losses():
+    """ResidualVQ(commitment_use_cross_entropy_loss=True, codebook_diversity_loss_weight>0): the fused level loop is
+    bypassed and every level's loss holds the CE commitment + diversity terms, as in the reference's loop over
+    VectorQuantize (residual_vq.py:212-243); checked level by level against the CPU restatement."""
+    from oracle import vq_oracle as O
+    from vqb200 import CodebookParams, ResidualVQ
+    dev = _dev()
+    g = torch.Generator().manual_seed(9)
+    B, n, d, K, Q = 3, 40, 32, 50, 3
+    rvq = ResidualVQ(dim=d, num_quantizers=Q, codebook_params=CodebookParams(dim=d, codebook_size=K,
+                                                                           threshold_ema_dead_code=0),
+                     commitment_use_cross_entropy_loss=True, commitment_weight=0.6, codebook_diversity_loss_weight=0.4,
+                     codebook_diversity_temperature=2.0, sync_codebook=False).to(dev).train()
+    states = []
+    for layer in rvq.layers:
+        c = torch.randn(1, K, d, generator=g) * 0.6
+        cb = layer._codebook
+        with torch.no_grad():
+            cb.embeddings.copy_(c); cb.embed_avg.copy_(c); cb.cluster_size.fill_(1.0)
+        cb.invalidate_cache()
+        states.append(O.CodebookState(c.clone(), c.clone(), torch.ones(1, K)))
+    x = torch.randn(B, n, d, generator=g)
+    out, ind, losses = rvq(x.to(dev))
+    assert out.shape == (B, n, d) and ind.shape == (B, n, Q) and losses.shape == (1, Q)
+    opts = O.VQOpts(commitment_weight=0.6, codebook=O.CodebookOpts(threshold_ema_dead_code=0))
+    residual, total = x, 0.0
+    for qi in range(Q):
+        q, i, l, _ = O.vq_forward_dense(states[qi], residual, opts, training=True, ce_commit=True,
+                                        diversity_weight=0.4, diversity_temperature=2.0)
+        assert torch.equal(ind[..., qi].cpu(), i), f"level {qi}: indices"
+        assert torch.allclose(losses[:, qi].cpu(), l, rtol=1e-5), f"level {qi}: loss {losses[:, qi]} vs {l}"
+        residual = residual - q.detach()
+        total = total + q.detach()
+    assert _rel(out.detach().cpu(), total) <= 1e-6

@@ -406,6 +406,42 @@ def test_learnable_codebook_matches_reference_fixture(name):
     assert torch.equal(ind2.reshape(-1), ex.reshape(-1))
 
 
+@pytest.mark.parametrize("name", ["inplace_sgd", "inplace_sgd_masked"])
+def test_in_place_codebook_optimizer_matches_reference_fixture(name):
+    """in_place_codebook_optimizer (reference vector_quantize_pytorch.py:233-256): an SGD step on the learnable codebook
+    inside forward (search + gather kernels, codebook gradient = segmented sum), then the pass whose results are
+    returned -- outputs, the stepped codebook and both gradients against the live reference."""
+    import os
+    from vqb200 import CodebookParams, VectorQuantize
+    fx = torch.load(os.path.join(gu.GOLDEN_DIR, "learnable", name + ".pt"), weights_only=False)
+    cfg = fx["cfg"]
+    cp = CodebookParams(dim=cfg["dim"], codebook_size=cfg["K"], learnable_codebook=True, ema_update=False,
+                        threshold_ema_dead_code=0)
+    vq = VectorQuantize(dim=cfg["dim"], codebook_params=cp, commitment_weight=cfg["cw"], sync_update_v=cfg["v"],
+                        sync_codebook=False,
+                        in_place_codebook_optimizer=lambda p: torch.optim.SGD(p, lr=cfg["lr"])).to(_dev()).train()
+    with torch.no_grad():
+        vq._codebook.embeddings.copy_(fx["init_embeddings"])
+    vq._codebook.invalidate_cache()
+    x = fx["x"].to(_dev()).requires_grad_(True)
+    mask = fx["mask"].to(_dev()) if fx["mask"] is not None else None
+    q, ind, loss, bd = vq(x, mask=mask, return_loss_breakdown=True)
+    (q * fx["w"].to(_dev())).sum().add(loss.sum() * 1.7).backward()
+    assert torch.allclose(bd.inplace_optimize.cpu(), fx["inplace_optimize"], rtol=1e-6)
+    assert gu.rel_err(vq._codebook.embeddings.detach().cpu(), fx["after_embeddings"]) <= 1e-6
+    assert torch.equal(ind.cpu(), fx["indices"])
+    assert gu.rel_err(q.detach().cpu(), fx["quantize"]) <= 1e-6      # gathered from the stepped codebook
+    assert torch.allclose(loss.detach().cpu(), fx["loss"], rtol=1e-5)
+    assert torch.allclose(x.grad.cpu(), fx["grad_x"], rtol=1e-5, atol=1e-7)
+    assert gu.rel_err(vq._codebook.embeddings.grad.cpu(), fx["grad_embeddings"]) <= 1e-5
+    # eval / freeze_codebook: no step
+    before = vq._codebook.embeddings.detach().clone()
+    vq(fx["x"].to(_dev()), mask=mask, freeze_codebook=True)
+    vq.eval()
+    vq(fx["x"].to(_dev()), mask=mask)
+    assert torch.equal(vq._codebook.embeddings.detach(), before)
+
+
 @pytest.mark.parametrize("cos", [False, True])
 @pytest.mark.parametrize("case", ["mixed_row_scales", "zero_codebook", "huge_codes_tiny_rows", "huge_rows_tiny_codes",
                                   "padded_codes", "constant_rows"])

@@ -100,9 +100,17 @@ def test_no_cpu_fallback_and_unsupported_options_fail_loudly():
         Codebook(8, 4, gumbel_params=GumbelParams(stochastic=True))
     with pytest.raises(ValueError):
         Codebook(8, 4, transform_input="tanh")
-    for kw in (dict(orthogonal_reg_weight=1.0), dict(in_place_codebook_optimizer=torch.optim.SGD)):
-        with pytest.raises(NotImplementedError):
-            VectorQuantize(dim=8, codebook_params=CodebookParams(dim=8, codebook_size=4), **kw)
+    with pytest.raises(NotImplementedError):
+        VectorQuantize(dim=8, codebook_params=CodebookParams(dim=8, codebook_size=4), orthogonal_reg_weight=1.0)
+    # in_place_codebook_optimizer: a factory over the codebook's parameters, so it needs a learnable codebook
+    # (with the default EMA codebook torch raises on the empty parameter list, as in the reference)
+    with pytest.raises(ValueError):
+        VectorQuantize(dim=8, codebook_params=CodebookParams(dim=8, codebook_size=4),
+                       in_place_codebook_optimizer=lambda p: torch.optim.SGD(p, lr=0.1))
+    vqo = VectorQuantize(dim=8, codebook_params=CodebookParams(dim=8, codebook_size=4, learnable_codebook=True,
+                                                               ema_update=False),
+                         in_place_codebook_optimizer=lambda p: torch.optim.SGD(p, lr=0.1))
+    assert isinstance(vqo.in_place_codebook_optimizer, torch.optim.SGD)
     # the consumers of the dense similarities are built (csrc/dense.cu) -- except with a learnable codebook
     for kw in (dict(codebook_diversity_loss_weight=0.1), dict(commitment_use_cross_entropy_loss=True)):
         VectorQuantize(dim=8, codebook_params=CodebookParams(dim=8, codebook_size=4), **kw)

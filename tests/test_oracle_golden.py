@@ -53,7 +53,7 @@ def test_row_chunked_oracle_equals_unchunked():
     assert gu.rel_err(b.embeddings, a.embeddings) <= 1e-6
 
 
-@pytest.mark.parametrize("name", ["learnable_plain", "learnable_masked_v"])
+@pytest.mark.parametrize("name", ["learnable_plain", "learnable_masked_v", "inplace_sgd", "inplace_sgd_masked"])
 def test_oracle_learnable_codebook_matches_reference_fixture(name):
     """The learnable-codebook restatement reproduces the live reference's outputs AND its gradients with respect to
     the input and the codebook (fixtures: tests/golden/make_golden_learnable.py)."""
@@ -63,7 +63,16 @@ def test_oracle_learnable_codebook_matches_reference_fixture(name):
     cfg = fx["cfg"]
     emb = fx["init_embeddings"].clone().requires_grad_(True)
     x = fx["x"].clone().requires_grad_(True)
-    q, ind, loss = O.vq_forward_learnable(emb, x, commitment_weight=cfg["cw"], sync_update_v=cfg["v"], mask=fx["mask"])
+    if "lr" in cfg:      # in_place_codebook_optimizer: an SGD step on the codebook inside the forward
+        q, ind, loss, inplace = O.vq_forward_learnable(emb, x, commitment_weight=cfg["cw"], sync_update_v=cfg["v"],
+                                                       mask=fx["mask"],
+                                                       inplace_optimizer=torch.optim.SGD([emb], lr=cfg["lr"]))
+        assert torch.equal(inplace, fx["inplace_optimize"])
+        assert torch.equal(emb.detach(), fx["after_embeddings"])
+        assert not torch.equal(emb.detach(), fx["init_embeddings"])
+    else:
+        q, ind, loss = O.vq_forward_learnable(emb, x, commitment_weight=cfg["cw"], sync_update_v=cfg["v"],
+                                              mask=fx["mask"])
     (q * fx["w"]).sum().add(loss.sum() * 1.7).backward()
     assert torch.equal(ind, fx["indices"])
     assert torch.equal(q.detach(), fx["quantize"])

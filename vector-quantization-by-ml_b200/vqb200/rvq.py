@@ -78,6 +78,8 @@ class ResidualVQ(nn.Module):
         if torch.is_grad_enabled() and x.requires_grad:
             return False
         l0 = self.layers[0]
+        if self.training and (l0.commitment_use_cross_entropy_loss or l0.has_codebook_diversity_loss):
+            return False        # losses on the dense similarities: the generic per-level loop computes them
         return l0.channel_last and not l0._codebook.input_l2norm and l0.heads == 1
 
     @torch.no_grad()

@@ -66,8 +66,6 @@ class VectorQuantize(nn.Module):
         if orthogonal_reg_weight > 0.0:
             unsupported.append("orthogonal_reg_weight (the reference itself raises AttributeError on this path: "
                                "vector_quantize_pytorch.py:367 reads the non-existent `_codebook.embed`)")
-        if in_place_codebook_optimizer is not None:
-            unsupported.append("in_place_codebook_optimizer (a second search inside forward; not built)")
         if codebook_params.learnable_codebook and (commitment_use_cross_entropy_loss or self.has_codebook_diversity_loss):
             unsupported.append("learnable_codebook with the cross-entropy commitment / diversity loss (the codebook "
                                "gradient of the dense similarities is not built)")
@@ -89,6 +87,9 @@ class VectorQuantize(nn.Module):
         self.sync_update_v = sync_update_v
         kw = asdict(self.codebook_params)
         self._codebook = Codebook(**kw)
+        # reference :132-136: an optimizer factory over the codebook's parameters (needs a learnable codebook)
+        self.in_place_codebook_optimizer = in_place_codebook_optimizer(self._codebook.parameters()) \
+            if in_place_codebook_optimizer is not None else None
         self.channel_last = channel_last
         self.register_buffer("zero", torch.tensor(0.0), persistent=False)
 
@@ -133,6 +134,31 @@ class VectorQuantize(nn.Module):
             return t.permute(2, 0, 1).reshape(self.heads, -1)
         return t.permute(0, 2, 1).reshape(1, -1)
 
+    def _inplace_optimize(self, cb_in, mask, multi):
+        """reference :233-256: one optimizer step on mse(codes, x.detach()) inside forward, before the pass whose
+        results are returned.  Search and gather are the usual kernels; the codebook gradient is the segmented sum
+        of `ops._GatherCodes`; the N x d mse on top is torch glue."""
+        cb = self._codebook
+        with torch.enable_grad():
+            target = cb.transform_input(cb_in.detach())
+            quant, _, _ = cb._run(target, mask, False, fuse_st=False, want_commit=False)
+            if mask is not None:
+                per = torch.nn.functional.mse_loss(quant, target.float(), reduction="none")
+                m = mask
+                if multi:      # "b n -> c (b h) n"
+                    m = mask[None, :, None, :].expand(per.shape[0], mask.shape[0], per.shape[1] // mask.shape[0],
+                                                      mask.shape[1]).reshape(per.shape[0], per.shape[1], mask.shape[1])
+                else:
+                    m = mask[None]
+                loss = per[m].mean()
+            else:
+                loss = torch.nn.functional.mse_loss(quant, target.float())
+            loss.backward()
+        self.in_place_codebook_optimizer.step()
+        self.in_place_codebook_optimizer.zero_grad()
+        cb.invalidate_cache()
+        return loss.detach()
+
     def forward(self, x, indices=None, mask=None, freeze_codebook=False, return_loss_breakdown=False):
         return_loss = indices is not None
         if return_loss and self.learnable_codebook:
@@ -165,6 +191,9 @@ class VectorQuantize(nn.Module):
         want_commit = training and self.has_commitment_loss and not ce_commit
         diversity = training and self.has_codebook_diversity_loss
         keep_dense = return_loss or ce_commit or diversity
+        inplace_loss = self.zero
+        if self.in_place_codebook_optimizer is not None and training and not freeze_codebook:
+            inplace_loss = self._inplace_optimize(cb_in, mask, multi)
         # transform_input (reference :221) happens inside _run, fused with the search's operand preparation
         quantize, embed_ind, commit = self._codebook._run(cb_in, mask, freeze_codebook, fuse_st=True,
                                                           want_commit=want_commit,
@@ -237,4 +266,4 @@ class VectorQuantize(nn.Module):
 
         if not return_loss_breakdown:
             return quantize, embed_ind, loss
-        return quantize, embed_ind, loss, LossBreakdown(commit_loss, diversity_loss, self.zero, self.zero)
+        return quantize, embed_ind, loss, LossBreakdown(commit_loss, diversity_loss, self.zero, inplace_loss)
