@@ -537,6 +537,22 @@ def vq_forward_dense(state: CodebookState, x: torch.Tensor, opts: VQOpts, *, tra
     return quant, ind, loss, parts
 
 
+def rvq_forward_autograd(states: List[CodebookState], x: torch.Tensor, opts: VQOpts, *,
+                         mask: Optional[torch.Tensor] = None, **dense_kw):
+    """ResidualVQ training forward under autograd (residual_vq.py:212-243): every level is `vq_forward_dense`
+    (plain mse commitment unless `dense_kw` says otherwise); `residual -= quantized.detach()`.
+    Returns (quantized_out, indices (...,Q), losses (1,Q))."""
+    out, residual = 0.0, x
+    inds, losses = [], []
+    for st in states:
+        q, ind, loss, _ = vq_forward_dense(st, residual, opts, training=True, mask=mask, **dense_kw)
+        residual = residual - q.detach()                    # :232
+        out = out + q                                       # :233
+        inds.append(ind)
+        losses.append(loss)
+    return out, torch.stack(inds, -1), torch.stack(losses, -1)
+
+
 # --------------------------------------------------------------------------- #
 # ResidualVQ.forward (residual_vq.py:134-269), no quantize-dropout
 # --------------------------------------------------------------------------- #

@@ -61,3 +61,26 @@ def dense_kwargs(cfg):
     """the dense-consumer switches of a make_golden_dense.py case (oracle keyword names)."""
     return dict(ce_commit=cfg["kind"] == "commit" or cfg.get("ce_commit", False),
                 diversity_weight=cfg.get("dw", 0.0), diversity_temperature=cfg.get("temp", 100.0))
+
+
+def grad_fixture_names():
+    return sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "grads", "*.pt")))
+
+
+def load_grad(name):
+    return torch.load(os.path.join(GOLDEN_DIR, "grads", name + ".pt"), weights_only=False)
+
+
+def extras_fixture_names():
+    return sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "extras", "*.pt")))
+
+
+def load_extras(name):
+    return torch.load(os.path.join(GOLDEN_DIR, "extras", name + ".pt"), weights_only=False)
+
+
+def build_from_description(cfg):
+    """vqb200 module from the constructor description stored in a tests/golden/make_golden_extras.py fixture."""
+    import vqb200
+    return getattr(vqb200, cfg["cls"])(codebook_params=vqb200.CodebookParams(**cfg["cp"]), sync_codebook=False,
+                                       **cfg["kw"])

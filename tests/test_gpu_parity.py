@@ -406,6 +406,37 @@ def test_learnable_codebook_matches_reference_fixture(name):
     assert torch.equal(ind2.reshape(-1), ex.reshape(-1))
 
 
+@pytest.mark.parametrize("name", gu.grad_fixture_names())
+def test_input_gradient_on_the_ema_path_matches_reference_fixture(name):
+    """One training forward under autograd, the EMA step moving the codebook inside it, then backward: outputs,
+    buffers and the input gradient of the live reference (tests/golden/make_golden_grads.py).  The commitment term
+    must read the PRE-update codes; one / shared / separate heads, masks, cosine, channel-first images, 2-D input,
+    ResidualVQ (generic level loop: the fused loop is forward-only)."""
+    fx = gu.load_grad(name)
+    cfg = fx["cfg"]
+    mod, books = build_module(cfg)
+    mod = mod.to(_dev()).train()
+    with torch.no_grad():
+        load_state(books, fx)
+    x = fx["x"].to(_dev()).requires_grad_(True)
+    mask = fx["mask"].to(_dev()) if fx["mask"] is not None else None
+    q, ind, loss = mod(x, mask=mask)
+    ((q * fx["w"].to(_dev())).sum() + loss.sum() * 1.7).backward()
+    assert torch.equal(ind.cpu(), fx["indices"])
+    if cfg.get("l2in") or cfg["kind"] == "rvq":
+        assert gu.rel_err(q.detach().cpu(), fx["quantize"]) <= 1e-6
+    else:
+        assert torch.equal(q.detach().cpu(), fx["quantize"])
+    assert torch.allclose(loss.detach().cpu(), fx["loss"], rtol=REL)
+    # the straight-through term alone would already give grad = w: compare what is left of it as well
+    got, ref, w = x.grad.cpu(), fx["grad_x"], fx["w"]
+    assert gu.rel_err(got, ref) <= REL
+    assert gu.rel_err(got - w, ref - w) <= 1e-3, gu.rel_err(got - w, ref - w)
+    for cb, after in zip(books, fx["after"]):
+        assert torch.equal(cb.cluster_size.cpu(), after["cluster_size"])
+        assert gu.rel_err(cb.embeddings.cpu(), after["embeddings"]) <= REL
+
+
 @pytest.mark.parametrize("name", ["inplace_sgd", "inplace_sgd_masked"])
 def test_in_place_codebook_optimizer_matches_reference_fixture(name):
     """in_place_codebook_optimizer (reference vector_quantize_pytorch.py:233-256): an SGD step on the learnable codebook

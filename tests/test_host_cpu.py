@@ -131,3 +131,18 @@ def test_product_code_never_imports_the_oracle():
                 text = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in text, \
                     f"{f} mentions the oracle; the product path must not depend on it"
+
+
+@pytest.mark.parametrize("name", __import__("golden_util").extras_fixture_names())
+def test_reference_checkpoints_load_strictly(name):
+    """state_dict keys / shapes of the reference's modules (projections, LayerNorm, per-level and per-group codebooks)
+    load into the vqb200 modules built from the same constructor arguments, strict=True, and round-trip."""
+    import golden_util as gu
+    fx = gu.load_extras(name)
+    mod = gu.build_from_description(fx["cfg"])
+    missing = mod.load_state_dict(fx["state_dict"], strict=True)
+    assert not missing.missing_keys and not missing.unexpected_keys
+    sd = mod.state_dict()
+    assert set(sd) == set(fx["state_dict"])
+    for k, v in fx["state_dict"].items():
+        assert torch.equal(sd[k], v), k

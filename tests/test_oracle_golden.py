@@ -108,3 +108,26 @@ def test_oracle_dense_consumers_match_reference_fixture(name):
     assert torch.allclose(x.grad, fx["grad_x"], rtol=1e-6, atol=1e-9)
     assert torch.equal(st.cluster_size, fx["after"]["cluster_size"])
     assert gu.rel_err(st.embeddings, fx["after"]["embeddings"]) <= 1e-6
+
+
+@pytest.mark.parametrize("name", gu.grad_fixture_names())
+def test_oracle_input_gradient_on_the_ema_path_matches_reference_fixture(name):
+    """One training forward under autograd with the EMA step moving the codebook inside it (fixtures:
+    tests/golden/make_golden_grads.py): outputs, buffers and the input gradient of the live reference."""
+    fx = gu.load_grad(name)
+    cfg = fx["cfg"]
+    opts = gu.oracle_opts(cfg)
+    states = gu.oracle_states(fx)
+    x = fx["x"].clone().requires_grad_(True)
+    if cfg["kind"] == "vq":
+        q, ind, loss, _ = O.vq_forward_dense(states[0], x, opts, training=True, mask=fx["mask"])
+    else:
+        q, ind, loss = O.rvq_forward_autograd(states, x, opts, mask=fx["mask"])
+    ((q * fx["w"]).sum() + loss.sum() * 1.7).backward()
+    assert torch.equal(ind, fx["indices"])
+    assert torch.equal(q.detach(), fx["quantize"])
+    assert torch.equal(loss.detach(), fx["loss"])
+    assert torch.allclose(x.grad, fx["grad_x"], rtol=1e-6, atol=1e-9)
+    for st, after in zip(states, fx["after"]):
+        assert torch.equal(st.cluster_size, after["cluster_size"])
+        assert gu.rel_err(st.embeddings, after["embeddings"]) <= 1e-6
