@@ -253,6 +253,16 @@ int vqb_dense_backward(const void* x, int x_dtype, const float* xn2, const float
                        const int64_t* target, const float* table, const float* rdot, int64_t n_pos, float* grad_x,
                        int64_t H, int64_t N, int K, int d, void* stream);
 
+/* codebook side of vqb_dense_backward (learnable codebook: codebooks.py:375-377 leaves `embeddings` attached to the
+ * similarities): grad_c[k] = c_k sum_n rho_nk - sum_n rho_nk x_n with the same weights.  Writes n_splits partial sums
+ * grad_c_partial (n_splits,H,K,d) over disjoint sets of latent tiles, n_splits = vqb_dense_backward_codes_splits(...);
+ * the caller adds them (fixed order, no atomics). */
+int vqb_dense_backward_codes_splits(int64_t H, int64_t N, int K, int d);
+int vqb_dense_backward_codes(const void* x, int x_dtype, const float* xn2, const float* codebook, const float* cn2,
+                             int metric, float alpha, const float* lse, const float* coef, const int64_t* target,
+                             const float* table, const float* rdot, int64_t n_pos, float* grad_c_partial,
+                             int n_splits, int64_t H, int64_t N, int K, int d, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

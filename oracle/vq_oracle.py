@@ -380,10 +380,14 @@ def vq_forward(state: CodebookState, x: torch.Tensor, opts: VQOpts, *, training:
 # --------------------------------------------------------------------------- #
 
 def vq_forward_learnable(embeddings: torch.Tensor, x: torch.Tensor, *, commitment_weight: float = 1.0,
-                         sync_update_v: float = 0.0, mask: Optional[torch.Tensor] = None, inplace_optimizer=None):
+                         sync_update_v: float = 0.0, mask: Optional[torch.Tensor] = None, inplace_optimizer=None,
+                         use_cosine_sim: bool = False, ce_commit: bool = False, diversity_weight: float = 0.0,
+                         diversity_temperature: float = 100.0, targets: Optional[torch.Tensor] = None):
     """`embeddings` (1,K,d) and `x` (B,n,d) may require grad.  Returns (quantize, indices, loss[1]); with
     `inplace_optimizer` (a torch optimizer over [embeddings]; vector_quantize_pytorch.py:233-256) the codebook is
-    first stepped on mse(codes, x.detach()) inside the forward, and that loss is returned as a fourth value."""
+    first stepped on mse(codes, x.detach()) inside the forward, and that loss is returned as a fourth value.
+    `ce_commit` / `diversity_weight` / `targets`: the losses on the dense similarities, which stay attached to
+    `embeddings` here (codebooks.py:375-377); with `targets` the return is (quantize, ce) (:298-299)."""
     B, n, d = x.shape
     inplace_loss = None
     if inplace_optimizer is not None:
@@ -400,17 +404,30 @@ def vq_forward_learnable(embeddings: torch.Tensor, x: torch.Tensor, *, commitmen
         inplace_optimizer.zero_grad()
         inplace_loss = inplace_loss.detach()
     flat = x.float()[None]                                              # codebooks.py:354-357
-    sim = similarities(flat.reshape(1, -1, d).detach(), embeddings.detach(), False)   # :386 (argmax only)
-    ind = sim.argmax(-1).reshape(1, B, n)                               # utils/general.py:128
+    sim = similarities(flat.reshape(1, -1, d), embeddings, use_cosine_sim)   # :386, attached to x and the codebook
+    ind = sim.detach().argmax(-1).reshape(1, B, n)                      # utils/general.py:128
     onehot = F.one_hot(ind, embeddings.shape[1]).type(flat.dtype)       # :129
     quant = torch.einsum("h b n c, h c d -> h b n d", onehot, embeddings)[0]   # codebooks.py:393-395 (differentiable)
     commit_q = quant                                                    # vector_quantize_pytorch.py:262-268
     out = x + (quant - x).detach()                                      # :273
     if sync_update_v > 0.0:
         out = out + sync_update_v * (out - out.detach())                # :275-279
+    logits = sim.reshape(B, n, -1).permute(0, 2, 1)                     # "1 b n l -> b l n" (:286)
+    if targets is not None:
+        return out, F.cross_entropy(logits, targets, ignore_index=-1)   # :298-299
+    ind_out = ind[0].clone()
     loss = torch.tensor([0.0])
+    if diversity_weight > 0:                                            # :324-333
+        prob = (-sim.reshape(1, B, n, -1) * diversity_temperature).softmax(dim=-1)
+        avg_prob = prob.reshape(-1, n, prob.shape[-1]).mean(0)
+        div = -((-avg_prob * _log_eps(avg_prob)).sum(dim=-1)).mean()
+        loss = loss + div * diversity_weight
     if commitment_weight > 0:
-        if mask is not None:
+        if ce_commit:                                                   # :338-346
+            if mask is not None:
+                ind_out.masked_fill_(~mask, -1)
+            commit = F.cross_entropy(logits, ind_out, ignore_index=-1)
+        elif mask is not None:
             commit = F.mse_loss(commit_q, x, reduction="none")[mask].mean()   # :347-360
         else:
             commit = F.mse_loss(commit_q, x)                            # :362
@@ -418,8 +435,8 @@ def vq_forward_learnable(embeddings: torch.Tensor, x: torch.Tensor, *, commitmen
     if mask is not None:
         out = torch.where(mask[..., None], out, x)                      # :415-418
     if inplace_optimizer is not None:
-        return out, ind[0], loss, inplace_loss
-    return out, ind[0], loss
+        return out, ind_out, loss, inplace_loss
+    return out, ind_out, loss
 
 
 # --------------------------------------------------------------------------- #

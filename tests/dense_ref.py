@@ -53,3 +53,20 @@ def backward(x, c_dist, c_comb, cosine, alpha, lse, coef, target=None, table=Non
         rho = torch.where(D > 0, -w / D, torch.zeros_like(D))
         xcoef = rho.sum(-1)
     return xcoef[..., None] * x - torch.einsum("hnk,hkd->hnd", rho, c_comb)
+
+
+def backward_codes(x, c, cosine, alpha, lse, coef, target=None, table=None, rdot=None, n_pos=1):
+    """codebook side of `backward` (ATen _euclidean_dist_backward, x2 branch / bmm): (H,K,d)."""
+    H, N, _ = x.shape
+    s = sims(x, c, cosine)
+    p = torch.exp(alpha * s - lse[..., None])
+    if table is not None:
+        w = coef[..., None] * p * (_table_rows(table, H, N, n_pos) - rdot[..., None])
+    else:
+        onehot = F.one_hot(target.clamp_min(0), s.shape[-1]).to(s.dtype) * (target >= 0)[..., None]
+        w = coef[..., None] * (p - onehot)
+    if cosine:
+        return torch.einsum("hnk,hnd->hkd", w, x)
+    D = -s
+    rho = torch.where(D > 0, -w / D, torch.zeros_like(D))
+    return c * rho.sum(1)[..., None] - torch.einsum("hnk,hnd->hkd", rho, x)

@@ -82,6 +82,15 @@ def test_dense_entry_points_match_fp64_statement(H, N, K, d, n_pos, cosine, dtyp
         assert g_ce.shape == (H, N, d) and bool(torch.isfinite(g_ce).all())
         assert _rel(g_ce, g_ce_r) <= 2e-4, _rel(g_ce, g_ce_r)
 
+        gc_ce = ops.dense_backward_codes(x, xn2, c_dist, cn2, cosine, alpha, lse, coef, target=target)
+        gc_ce_r = R.backward_codes(x64, cd64, cosine, alpha, lse_r, coef.double(), target=target)
+        assert gc_ce.shape == (H, K, d) and _rel(gc_ce, gc_ce_r) <= 2e-4, _rel(gc_ce, gc_ce_r)
+        gc_dv = ops.dense_backward_codes(x, xn2, c_dist, cn2, cosine, alpha, lse, coef, table=table, rdot=rd,
+                                         n_pos=n_pos)
+        gc_dv_r = R.backward_codes(x64, cd64, cosine, alpha, lse_r, coef.double(), table=table.double(), rdot=rd_r,
+                                   n_pos=n_pos)
+        assert _rel(gc_dv, gc_dv_r) <= 2e-4, _rel(gc_dv, gc_dv_r)
+
         g_dv = ops.dense_backward(x, xn2, c_dist, cn2, c_comb, cosine, alpha, lse, coef, table=table, rdot=rd,
                                   n_pos=n_pos)
         g_dv_r = R.backward(x64, cd64, cc64, cosine, alpha, lse_r, coef.double(), table=table.double(), rdot=rd_r,
@@ -241,3 +250,43 @@ def test_residual_vq_levels_carry_the_dense_losses():
         residual = residual - q.detach()
         total = total + q.detach()
     assert _rel(out.detach().cpu(), total) <= 1e-6
+
+
+@pytest.mark.parametrize("name", ["learnable_ce_commit", "learnable_ce_commit_dot", "learnable_diversity",
+                                  "learnable_ce_indices"])
+def test_learnable_codebook_with_dense_losses_matches_reference_fixture(name):
+    """learnable codebook + CE commitment / diversity loss / CE to indices: outputs and the gradients with respect to
+    the input AND the codebook (through the similarities) against the live reference
+    (tests/golden/make_golden_learnable.py)."""
+    import os
+    from vqb200 import CodebookParams, VectorQuantize
+    dev = _dev()
+    fx = torch.load(os.path.join(gu.GOLDEN_DIR, "learnable", name + ".pt"), weights_only=False)
+    cfg = fx["cfg"]
+    cp = CodebookParams(dim=cfg["dim"], codebook_size=cfg["K"], learnable_codebook=True, ema_update=False,
+                        threshold_ema_dead_code=0, use_cosine_sim=cfg.get("cosine", False))
+    extra = {}
+    if cfg.get("ce"):
+        extra["commitment_use_cross_entropy_loss"] = True
+    if cfg.get("dw"):
+        extra.update(codebook_diversity_loss_weight=cfg["dw"], codebook_diversity_temperature=cfg["temp"])
+    vq = VectorQuantize(dim=cfg["dim"], codebook_params=cp, commitment_weight=cfg["cw"], sync_update_v=cfg["v"],
+                        sync_codebook=False, **extra).to(dev).train()
+    with torch.no_grad():
+        vq._codebook.embeddings.copy_(fx["init_embeddings"])
+    vq._codebook.invalidate_cache()
+    x = fx["x"].to(dev).requires_grad_(True)
+    if cfg.get("indices"):
+        q, ce = vq(x, indices=fx["targets"].to(dev))
+        (q.sum() * 0.01 + ce * 1.3).backward()
+        assert torch.allclose(ce.detach().cpu(), fx["ce"], rtol=1e-5)
+    else:
+        mask = fx["mask"].to(dev) if fx["mask"] is not None else None
+        q, ind, loss = vq(x, mask=mask)
+        (q * fx["w"].to(dev)).sum().add(loss.sum() * 1.7).backward()
+        assert torch.equal(ind.cpu(), fx["indices"])
+        assert torch.allclose(loss.detach().cpu(), fx["loss"], rtol=1e-5)
+    assert torch.equal(q.detach().cpu(), fx["quantize"])
+    assert _rel(x.grad.cpu(), fx["grad_x"]) <= 1e-5
+    assert _rel(vq._codebook.embeddings.grad.cpu(), fx["grad_embeddings"]) <= 2e-5
+    assert torch.equal(vq._codebook.embeddings.detach().cpu(), fx["init_embeddings"])

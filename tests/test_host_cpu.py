@@ -111,12 +111,11 @@ def test_no_cpu_fallback_and_unsupported_options_fail_loudly():
                                                                ema_update=False),
                          in_place_codebook_optimizer=lambda p: torch.optim.SGD(p, lr=0.1))
     assert isinstance(vqo.in_place_codebook_optimizer, torch.optim.SGD)
-    # the consumers of the dense similarities are built (csrc/dense.cu) -- except with a learnable codebook
+    # the consumers of the dense similarities are built (csrc/dense.cu), with a learnable codebook too
     for kw in (dict(codebook_diversity_loss_weight=0.1), dict(commitment_use_cross_entropy_loss=True)):
         VectorQuantize(dim=8, codebook_params=CodebookParams(dim=8, codebook_size=4), **kw)
-        with pytest.raises(NotImplementedError):
-            VectorQuantize(dim=8, codebook_params=CodebookParams(dim=8, codebook_size=4, learnable_codebook=True,
-                                                                 ema_update=False), **kw)
+        VectorQuantize(dim=8, codebook_params=CodebookParams(dim=8, codebook_size=4, learnable_codebook=True,
+                                                             ema_update=False), **kw)
     with pytest.raises(AssertionError):          # reference: sync_update_v needs a learnable codebook
         VectorQuantize(dim=8, codebook_params=CodebookParams(dim=8, codebook_size=4), sync_update_v=0.5)
     with pytest.raises(AssertionError):          # reference: learnable codebook is not compatible with the EMA update

@@ -53,7 +53,11 @@ def test_row_chunked_oracle_equals_unchunked():
     assert gu.rel_err(b.embeddings, a.embeddings) <= 1e-6
 
 
-@pytest.mark.parametrize("name", ["learnable_plain", "learnable_masked_v", "inplace_sgd", "inplace_sgd_masked"])
+LEARNABLE = ["learnable_plain", "learnable_masked_v", "inplace_sgd", "inplace_sgd_masked", "learnable_ce_commit",
+             "learnable_ce_commit_dot", "learnable_diversity", "learnable_ce_indices"]
+
+
+@pytest.mark.parametrize("name", LEARNABLE)
 def test_oracle_learnable_codebook_matches_reference_fixture(name):
     """The learnable-codebook restatement reproduces the live reference's outputs AND its gradients with respect to
     the input and the codebook (fixtures: tests/golden/make_golden_learnable.py)."""
@@ -63,6 +67,15 @@ def test_oracle_learnable_codebook_matches_reference_fixture(name):
     cfg = fx["cfg"]
     emb = fx["init_embeddings"].clone().requires_grad_(True)
     x = fx["x"].clone().requires_grad_(True)
+    dense = dict(use_cosine_sim=cfg.get("cosine", False), ce_commit=bool(cfg.get("ce")),
+                 diversity_weight=cfg.get("dw", 0.0), diversity_temperature=cfg.get("temp", 100.0))
+    if cfg.get("indices"):   # forward(x, indices=...) -> (quantize, ce): gradients to the input AND the codebook
+        q, ce = O.vq_forward_learnable(emb, x, targets=fx["targets"], **dense)
+        (q.sum() * 0.01 + ce * 1.3).backward()
+        assert torch.equal(q.detach(), fx["quantize"]) and torch.equal(ce.detach(), fx["ce"])
+        assert torch.allclose(x.grad, fx["grad_x"], rtol=1e-6, atol=1e-9)
+        assert torch.allclose(emb.grad, fx["grad_embeddings"], rtol=1e-6, atol=1e-9)
+        return
     if "lr" in cfg:      # in_place_codebook_optimizer: an SGD step on the codebook inside the forward
         q, ind, loss, inplace = O.vq_forward_learnable(emb, x, commitment_weight=cfg["cw"], sync_update_v=cfg["v"],
                                                        mask=fx["mask"],
@@ -72,7 +85,7 @@ def test_oracle_learnable_codebook_matches_reference_fixture(name):
         assert not torch.equal(emb.detach(), fx["init_embeddings"])
     else:
         q, ind, loss = O.vq_forward_learnable(emb, x, commitment_weight=cfg["cw"], sync_update_v=cfg["v"],
-                                              mask=fx["mask"])
+                                              mask=fx["mask"], **dense)
     (q * fx["w"]).sum().add(loss.sum() * 1.7).backward()
     assert torch.equal(ind, fx["indices"])
     assert torch.equal(q.detach(), fx["quantize"])

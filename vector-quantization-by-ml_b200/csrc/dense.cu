@@ -57,9 +57,9 @@ __device__ __forceinline__ void stage4(float (*S)[LD], int r, int kq, const floa
 
 // acc[i][j] = sum_k A[row0 + ty*4 + i][k] * B[col0 + tx*4 + j][k]   (zero-padded outside the bounds)
 // Ends with a __syncthreads(): As / Bs may be re-used and shared scalars written before the call are visible.
-template <typename T>
+template <typename T, typename TB = float>
 __device__ __forceinline__ void score_tile(const T* __restrict__ a_base, int64_t row0, int64_t row_end,
-                                           const float* __restrict__ b_base, int64_t col0, int64_t col_end, int d,
+                                           const TB* __restrict__ b_base, int64_t col0, int64_t col_end, int d,
                                            bool vec, float (*As)[LD], float (*Bs)[LD], float acc[4][4]) {
   const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
   const int lr = tid >> 2, kq = (tid & 3) * 4;
@@ -68,14 +68,14 @@ __device__ __forceinline__ void score_tile(const T* __restrict__ a_base, int64_t
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
   float4 pa = fetch4<T>(a_base, row0 + lr, row_end, d, kq, vec);
-  float4 pb = fetch4<float>(b_base, col0 + lr, col_end, d, kq, vec);
+  float4 pb = fetch4<TB>(b_base, col0 + lr, col_end, d, kq, vec);
   for (int k0 = 0; k0 < d; k0 += BK) {
     stage4(As, lr, kq, pa);
     stage4(Bs, lr, kq, pb);
     __syncthreads();
     if (k0 + BK < d) {
       pa = fetch4<T>(a_base, row0 + lr, row_end, d, k0 + BK + kq, vec);
-      pb = fetch4<float>(b_base, col0 + lr, col_end, d, k0 + BK + kq, vec);
+      pb = fetch4<TB>(b_base, col0 + lr, col_end, d, k0 + BK + kq, vec);
     }
 #pragma unroll
     for (int kk = 0; kk < BK; ++kk) {
@@ -415,6 +415,145 @@ __global__ void __launch_bounds__(kThreads) dense_backward_kernel(
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// backward with respect to the CODEBOOK (learnable codebook): the transposed contraction of dense_backward_kernel.
+//   grad_c[k] = c_k sum_n rho_nk - sum_n rho_nk x_n        (euclid; ATen _euclidean_dist_backward, x2 side)
+//             =                  - sum_n rho_nk x_n        (dot, rho = -w)
+// Rows of the tile are CODES, columns are latents: the per-latent statistics (lse, coef, target, rdot, |x|^2) are
+// re-staged for every latent tile.  grid (ceil(K/64), H * n_splits, ceil(d / (64 NSUB))): split s of a codebook
+// walks the latent tiles s, s + n_splits, ... and writes its own partial (n_splits, H, K, d), summed by the caller
+// in a fixed order (no atomics).
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T, int NSUB>
+__global__ void __launch_bounds__(kThreads) dense_backward_codes_kernel(
+    const T* __restrict__ x, const float* __restrict__ xn2, const float* __restrict__ cb, const float* __restrict__ cn2,
+    int metric, float alpha, const float* __restrict__ lse, const float* __restrict__ coef,
+    const int64_t* __restrict__ target, const float* __restrict__ table, const float* __restrict__ rdot,
+    int64_t n_pos, float* __restrict__ grad_c, int n_splits, int64_t H, int64_t N, int K, int d, int vec) {
+  __shared__ __align__(16) float As[BK][LD];
+  __shared__ __align__(16) float Bs[BK][LD];
+  __shared__ __align__(16) float Rs[BM][LD];   // rho tile  [code][latent]
+  __shared__ __align__(16) float Xs[BN][LD];   // latent tile [latent][dim]
+  __shared__ float s_xn2[BN], s_cn2[BM], s_lse[BN], s_coef[BN], s_r[BN];
+  __shared__ long long s_t[BN], s_pos[BN];
+  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+  const int64_t h = blockIdx.y / n_splits;
+  const int split = blockIdx.y % n_splits;
+  const int64_t code0 = (int64_t)blockIdx.x * BM;
+  const int dim_base = blockIdx.z * 64 * NSUB;
+  const T* x_h = x + h * N * d;
+  const float* cb_h = cb + h * (int64_t)K * d;
+  if (tid < BM) s_cn2[tid] = (cn2 != nullptr && code0 + tid < K) ? cn2[h * K + code0 + tid] : 0.f;
+  float acc2[4][NSUB * 4];
+  float rs[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    rs[i] = 0.f;
+#pragma unroll
+    for (int j = 0; j < NSUB * 4; ++j) acc2[i][j] = 0.f;
+  }
+
+  for (int64_t n0 = (int64_t)split * BN; n0 < N; n0 += (int64_t)n_splits * BN) {
+    __syncthreads();
+    if (tid < BN) {
+      const int64_t row = n0 + tid;
+      const bool ok = row < N;
+      s_xn2[tid] = (ok && xn2 != nullptr) ? xn2[h * N + row] : 0.f;
+      s_lse[tid] = ok ? lse[h * N + row] : 0.f;
+      s_coef[tid] = ok ? coef[h * N + row] : 0.f;
+      s_r[tid] = (ok && rdot != nullptr) ? rdot[h * N + row] : 0.f;
+      s_t[tid] = (ok && target != nullptr) ? (long long)target[h * N + row] : -1ll;
+      s_pos[tid] = (ok && table != nullptr) ? (long long)(row % n_pos) : 0ll;
+    }
+    float acc[4][4];
+    score_tile<float, T>(cb_h, code0, K, x_h, n0, N, d, vec != 0, As, Bs, acc);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = ty * 4 + i;
+      const int64_t code = code0 + r;
+      float rho[4] = {0.f, 0.f, 0.f, 0.f};
+      if (code < K) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int c = tx * 4 + j;
+          if (n0 + c < N) {
+            const float sc = sim_of(acc[i][j], s_xn2[c], s_cn2[r], metric);
+            const float p = expf(alpha * sc - s_lse[c]);
+            float w;
+            if (table != nullptr) {
+              w = s_coef[c] * p * (__ldg(table + s_pos[c] * K + code) - s_r[c]);
+            } else {
+              w = s_coef[c] * p;
+              if ((long long)code == s_t[c]) w -= s_coef[c];
+            }
+            if (metric == VQB_DOT) {
+              rho[j] = -w;
+            } else {
+              const float D = -sc;
+              rho[j] = D > 0.f ? -w / D : 0.f;
+            }
+            rs[i] += rho[j];
+          }
+        }
+      }
+      *reinterpret_cast<float4*>(&Rs[r][tx * 4]) = make_float4(rho[0], rho[1], rho[2], rho[3]);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int sub = 0; sub < NSUB; ++sub) {
+      const int dim0 = dim_base + sub * 64;
+      if (dim0 < d) {     // block-uniform
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int idx = tid + kThreads * q;
+          const int lat = idx >> 4, dq = (idx & 15) * 4;
+          const float4 v = fetch4<T>(x_h, n0 + lat, N, d, dim0 + dq, vec != 0);
+          *reinterpret_cast<float4*>(&Xs[lat][dq]) = v;
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (int kk = 0; kk < BN; kk += 4) {
+          float a[4][4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float4 t = *reinterpret_cast<const float4*>(&Rs[ty * 4 + i][kk]);
+            a[i][0] = t.x; a[i][1] = t.y; a[i][2] = t.z; a[i][3] = t.w;
+          }
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float b[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) b[j] = Xs[kk + e][tx + 16 * j];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+              for (int j = 0; j < 4; ++j) acc2[i][sub * 4 + j] = fmaf(a[i][e], b[j], acc2[i][sub * 4 + j]);
+          }
+        }
+        __syncthreads();
+      }
+    }
+  }
+
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float sum = rs[i];
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const int64_t code = code0 + ty * 4 + i;
+    if (code >= K) continue;
+    const float ccoef = (metric == VQB_DOT) ? 0.f : sum;
+    float* out = grad_c + (((int64_t)split * H + h) * K + code) * (int64_t)d;
+#pragma unroll
+    for (int sub = 0; sub < NSUB; ++sub)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int dim = dim_base + sub * 64 + tx + 16 * j;
+        if (dim < d) out[dim] = fmaf(ccoef, cb_h[code * (int64_t)d + dim], -acc2[i][sub * 4 + j]);
+      }
+  }
+}
+
 int check_common(const void* x, const void* cb, int64_t H, int64_t N, int K, int d, int metric) {
   VQB_REQUIRE((x != nullptr || N == 0) && cb != nullptr, VQB_ERR_INVALID, "dense: null pointer");
   VQB_REQUIRE(H >= 1 && H <= 65535 && N >= 0 && K >= 1 && d >= 1, VQB_ERR_INVALID,
@@ -528,6 +667,54 @@ extern "C" int vqb_dense_backward(const void* x, int x_dtype, const float* xn2, 
       grad_x, N, K, d, vec))
   if (nsub == 1) { VQB_DENSE_BWD(1); } else if (nsub == 2) { VQB_DENSE_BWD(2); } else { VQB_DENSE_BWD(4); }
 #undef VQB_DENSE_BWD
+  VQB_LAUNCH_CHECK();
+  return VQB_OK;
+}
+
+// number of partial sums vqb_dense_backward_codes writes (first dimension of grad_c_partial): enough blocks to fill
+// the GPU when K is small, 1 when the code tiles alone do
+extern "C" int vqb_dense_backward_codes_splits(int64_t H, int64_t N, int K, int d) {
+  if (H < 1 || N < 1 || K < 1 || d < 1) return 1;
+  const int nsub = d <= 64 ? 1 : (d <= 128 ? 2 : 4);
+  const int64_t blocks = (int64_t)((K + BM - 1) / BM) * H * ((d + 64 * nsub - 1) / (64 * nsub));
+  int64_t s = (2 * 148 + blocks - 1) / blocks;
+  const int64_t tiles = (N + BN - 1) / BN;
+  if (s > tiles) s = tiles;
+  if (s > 32) s = 32;
+  if (s < 1) s = 1;
+  return (int)s;
+}
+
+extern "C" int vqb_dense_backward_codes(const void* x, int x_dtype, const float* xn2, const float* codebook,
+                                        const float* cn2, int metric, float alpha, const float* lse,
+                                        const float* coef, const int64_t* target, const float* table,
+                                        const float* rdot, int64_t n_pos, float* grad_c_partial, int n_splits,
+                                        int64_t H, int64_t N, int K, int d, void* stream) {
+  if (int rc = check_common(x, codebook, H, N, K, d, metric)) return rc;
+  VQB_REQUIRE(N >= 1 && lse != nullptr && coef != nullptr && grad_c_partial != nullptr, VQB_ERR_INVALID,
+              "vqb_dense_backward_codes: null pointer or empty input");
+  VQB_REQUIRE((target != nullptr) != (table != nullptr), VQB_ERR_INVALID,
+              "vqb_dense_backward_codes: exactly one of target (cross-entropy) and table (diversity) must be given");
+  VQB_REQUIRE(table == nullptr || (rdot != nullptr && n_pos >= 1 && N % n_pos == 0), VQB_ERR_INVALID,
+              "vqb_dense_backward_codes: the diversity form needs rdot and N a multiple of n_pos");
+  VQB_REQUIRE(metric == VQB_DOT || (xn2 != nullptr && cn2 != nullptr), VQB_ERR_INVALID,
+              "vqb_dense_backward_codes: the Euclidean metric needs the row norms");
+  VQB_REQUIRE(n_splits >= 1 && n_splits == vqb_dense_backward_codes_splits(H, N, K, d), VQB_ERR_INVALID,
+              "vqb_dense_backward_codes: n_splits=%d, expected vqb_dense_backward_codes_splits() = %d", n_splits,
+              vqb_dense_backward_codes_splits(H, N, K, d));
+  VQB_REQUIRE(H * n_splits <= 65535, VQB_ERR_UNSUPPORTED, "vqb_dense_backward_codes: H * n_splits too large");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int vec = vec_ok(x, codebook, codebook, d);
+  const int nsub = d <= 64 ? 1 : (d <= 128 ? 2 : 4);
+  const dim3 grid((unsigned)((K + BM - 1) / BM), (unsigned)(H * n_splits), (unsigned)((d + 64 * nsub - 1) / (64 * nsub)));
+  VQB_REQUIRE(grid.z <= 65535, VQB_ERR_UNSUPPORTED, "vqb_dense_backward_codes: d=%d too large", d);
+  if (n_pos < 1) n_pos = 1;
+#define VQB_DENSE_BWDC(NS)                                                                                          \
+  VQB_DISPATCH_DTYPE(x_dtype, T, dense_backward_codes_kernel<T, NS><<<grid, kThreads, 0, st>>>(                      \
+      (const T*)x, xn2, codebook, cn2, metric, alpha, lse, coef, target, table, rdot, n_pos, grad_c_partial,        \
+      n_splits, H, N, K, d, vec))
+  if (nsub == 1) { VQB_DENSE_BWDC(1); } else if (nsub == 2) { VQB_DENSE_BWDC(2); } else { VQB_DENSE_BWDC(4); }
+#undef VQB_DENSE_BWDC
   VQB_LAUNCH_CHECK();
   return VQB_OK;
 }

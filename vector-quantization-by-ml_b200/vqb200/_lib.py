@@ -61,6 +61,9 @@ SIGNATURES = {
     "vqb_dense_avgprob": (_i32, [_p, _i32, _p, _p, _p, _i32, _f32, _p, _p, _i64, _i64, _i64, _i32, _i32, _p]),
     "vqb_dense_backward": (_i32, [_p, _i32, _p, _p, _p, _p, _i32, _f32, _p, _p, _p, _p, _p, _i64, _p, _i64, _i64, _i32,
                                   _i32, _p]),
+    "vqb_dense_backward_codes_splits": (_i32, [_i64, _i64, _i32, _i32]),
+    "vqb_dense_backward_codes": (_i32, [_p, _i32, _p, _p, _p, _i32, _f32, _p, _p, _p, _p, _p, _i64, _p, _i32, _i64, _i64,
+                                        _i32, _i32, _p]),
 }
 
 _lib = None

@@ -473,6 +473,21 @@ def dense_backward(x, xn2, emb_dist, cn2, emb_comb, use_cosine_sim: bool, alpha:
     return gx
 
 
+def dense_backward_codes(x, xn2, emb, cn2, use_cosine_sim: bool, alpha: float, lse, coef, target=None, table=None,
+                         rdot=None, n_pos: int = 1) -> torch.Tensor:
+    """Codebook gradient (H,K,d) fp32 of a loss on the similarities (learnable codebook): the transposed contraction
+    of `dense_backward`; partial sums over latent tiles are added in a fixed order."""
+    H, N, d = x.shape
+    K = emb.shape[1]
+    splits = int(L.lib().vqb_dense_backward_codes_splits(H, N, K, d))
+    part = torch.empty((splits, H, K, d), dtype=torch.float32, device=x.device)
+    L.check(L.lib().vqb_dense_backward_codes(L.ptr(x), L.dtype_code(x), L.ptr(xn2), L.ptr(emb), L.ptr(cn2),
+                                             _metric(use_cosine_sim), float(alpha), L.ptr(lse), L.ptr(coef),
+                                             L.ptr(target), L.ptr(table), L.ptr(rdot), int(n_pos), L.ptr(part),
+                                             splits, H, N, K, d, L.stream_ptr(x.device)), "vqb_dense_backward_codes")
+    return part[0] if splits == 1 else part.sum(dim=0)
+
+
 class _DenseCtx:
     """What the dense consumers of one forward share: latents (H,N,d), the codebook the similarities are defined on
     (`emb_dist`: a private copy when the EMA step overwrites `embeddings` in this forward) and the live buffer
@@ -486,10 +501,11 @@ class _DenseCtx:
 
 class _DenseCE(torch.autograd.Function):
     """mean over rows with target >= 0 of (logsumexp_k s_k - s_target): F.cross_entropy(similarities, codes,
-    ignore_index=-1) of reference vector_quantize_pytorch.py:284-296 on the (H,N) row layout."""
+    ignore_index=-1) of reference vector_quantize_pytorch.py:284-296 on the (H,N) row layout.  `emb` is the learnable
+    codebook Parameter (it then receives the gradient through the similarities, codebooks.py:375-377) or None."""
 
     @staticmethod
-    def forward(ctx, x, dc, target):
+    def forward(ctx, x, emb, dc, target):
         lse, st = dense_rowstats(x, dc.xn2, dc.emb_dist, dc.cn2, dc.cos, 1.0, target)
         valid = target >= 0
         n_valid = valid.sum()
@@ -501,15 +517,19 @@ class _DenseCE(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         dc, (x,) = ctx.dc, ctx.saved_tensors
-        coef = (g.float() / ctx.n_valid) * ctx.valid
-        gx = dense_backward(x, dc.xn2, dc.emb_dist, dc.cn2, dc.emb_live.detach(), dc.cos, 1.0, ctx.lse,
-                            coef.contiguous(), target=ctx.target)
-        return gx.to(x.dtype), None, None
+        coef = ((g.float() / ctx.n_valid) * ctx.valid).contiguous()
+        gx = ge = None
+        if ctx.needs_input_grad[0]:
+            gx = dense_backward(x, dc.xn2, dc.emb_dist, dc.cn2, dc.emb_live.detach(), dc.cos, 1.0, ctx.lse, coef,
+                                target=ctx.target).to(x.dtype)
+        if ctx.needs_input_grad[1]:
+            ge = dense_backward_codes(x, dc.xn2, dc.emb_dist, dc.cn2, dc.cos, 1.0, ctx.lse, coef, target=ctx.target)
+        return gx, ge, None, None
 
 
-def dense_cross_entropy(dc: "_DenseCtx", target: torch.Tensor) -> torch.Tensor:
+def dense_cross_entropy(dc: "_DenseCtx", target: torch.Tensor, emb_param=None) -> torch.Tensor:
     """`target` (H,N) int64 in the row layout of dc.x, -1 = ignored."""
-    return _DenseCE.apply(dc.x, dc, target.contiguous())
+    return _DenseCE.apply(dc.x, emb_param, dc, target.contiguous())
 
 
 class _DenseAvgProb(torch.autograd.Function):
@@ -517,7 +537,7 @@ class _DenseAvgProb(torch.autograd.Function):
     averaged over heads and batch; the entropy on top of it is K-sized torch glue."""
 
     @staticmethod
-    def forward(ctx, x, dc, n_pos, alpha):
+    def forward(ctx, x, emb, dc, n_pos, alpha):
         lse, _ = dense_rowstats(x, dc.xn2, dc.emb_dist, dc.cn2, dc.cos, alpha, None)
         avg = dense_avgprob(x, dc.xn2, dc.emb_dist, dc.cn2, dc.cos, alpha, lse, n_pos)
         ctx.dc, ctx.lse, ctx.n_pos, ctx.alpha = dc, lse, n_pos, alpha
@@ -531,10 +551,15 @@ class _DenseAvgProb(torch.autograd.Function):
         table = g_avg.contiguous().float()
         rdot = dense_rowdot(x, dc.xn2, dc.emb_dist, dc.cn2, dc.cos, alpha, ctx.lse, table, n_pos)
         coef = torch.full((H, N), alpha / (H * (N // n_pos)), dtype=torch.float32, device=x.device)
-        gx = dense_backward(x, dc.xn2, dc.emb_dist, dc.cn2, dc.emb_live.detach(), dc.cos, alpha, ctx.lse, coef,
-                            table=table, rdot=rdot, n_pos=n_pos)
-        return gx.to(x.dtype), None, None, None
+        gx = ge = None
+        if ctx.needs_input_grad[0]:
+            gx = dense_backward(x, dc.xn2, dc.emb_dist, dc.cn2, dc.emb_live.detach(), dc.cos, alpha, ctx.lse, coef,
+                                table=table, rdot=rdot, n_pos=n_pos).to(x.dtype)
+        if ctx.needs_input_grad[1]:
+            ge = dense_backward_codes(x, dc.xn2, dc.emb_dist, dc.cn2, dc.cos, alpha, ctx.lse, coef, table=table,
+                                      rdot=rdot, n_pos=n_pos)
+        return gx, ge, None, None, None
 
 
-def dense_avg_prob(dc: "_DenseCtx", n_pos: int, temperature: float) -> torch.Tensor:
-    return _DenseAvgProb.apply(dc.x, dc, int(n_pos), -float(temperature))
+def dense_avg_prob(dc: "_DenseCtx", n_pos: int, temperature: float, emb_param=None) -> torch.Tensor:
+    return _DenseAvgProb.apply(dc.x, emb_param, dc, int(n_pos), -float(temperature))

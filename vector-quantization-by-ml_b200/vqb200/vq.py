@@ -5,10 +5,10 @@ multi-head, projections, masks) is host code; search, gather + straight-through 
 and the EMA update are CUDA kernels behind ``Codebook``.  The consumers of the dense N x K similarity
 matrix -- cross-entropy to given indices (reference :284-299), the cross-entropy commitment loss (:338-346)
 and the codebook diversity loss (:324-333) -- run as fp32 online-softmax passes that never write the
-matrix (csrc/dense.cu), forward and input gradient.  Orthogonal regularisation (broken in the reference
-itself), the in-place codebook optimizer and a learnable codebook combined with the dense consumers raise
-NotImplementedError; a learnable codebook (`learnable_codebook=True, ema_update=False`, optionally
-`sync_update_v`) with the mse commitment loss is supported.
+matrix (csrc/dense.cu), forward, input gradient and -- with a learnable codebook -- codebook gradient.
+Orthogonal regularisation (broken in the reference itself) raises NotImplementedError; a learnable codebook
+(`learnable_codebook=True, ema_update=False`, optionally `sync_update_v` and `in_place_codebook_optimizer`)
+is supported.
 """
 from __future__ import annotations
 
@@ -66,9 +66,6 @@ class VectorQuantize(nn.Module):
         if orthogonal_reg_weight > 0.0:
             unsupported.append("orthogonal_reg_weight (the reference itself raises AttributeError on this path: "
                                "vector_quantize_pytorch.py:367 reads the non-existent `_codebook.embed`)")
-        if codebook_params.learnable_codebook and (commitment_use_cross_entropy_loss or self.has_codebook_diversity_loss):
-            unsupported.append("learnable_codebook with the cross-entropy commitment / diversity loss (the codebook "
-                               "gradient of the dense similarities is not built)")
         if unsupported:
             raise NotImplementedError("vqb200.VectorQuantize: outside the accelerated path: " + "; ".join(unsupported))
 
@@ -161,9 +158,6 @@ class VectorQuantize(nn.Module):
 
     def forward(self, x, indices=None, mask=None, freeze_codebook=False, return_loss_breakdown=False):
         return_loss = indices is not None
-        if return_loss and self.learnable_codebook:
-            raise NotImplementedError("vqb200.VectorQuantize: cross-entropy to given indices with a learnable codebook "
-                                      "(the codebook gradient of the dense similarities is not built)")
         orig_input = x
         only_one = x.ndim == 2
         if only_one:
@@ -201,6 +195,10 @@ class VectorQuantize(nn.Module):
                                                           keep_dense=keep_dense)
         dense = self._codebook.dense_ctx
         self._codebook.dense_ctx = None
+        # learnable codebook: the similarities stay attached to `embeddings` (reference codebooks.py:375-377, whatever
+        # freeze_codebook says), so the dense losses also send a gradient to the codebook
+        emb_param = self._codebook.embeddings if (self.learnable_codebook and torch.is_grad_enabled()
+                                                  and self._codebook.embeddings.requires_grad) else None
         rows_idx = embed_ind.reshape(embed_ind.shape[0], -1)          # (H, N): the row layout of the dense passes
         if x.ndim < 4:
             quantize, embed_ind = quantize[0], embed_ind[0]
@@ -212,7 +210,7 @@ class VectorQuantize(nn.Module):
             # reference :284-299: F.cross_entropy(similarities, indices, ignore_index=-1); returns the codebook-side
             # quantize (before head merge / projection) and the loss only
             target = self._rows_of(indices.to(device=device, dtype=torch.int64), B, multi)
-            return quantize, ops.dense_cross_entropy(dense, target)
+            return quantize, ops.dense_cross_entropy(dense, target, emb_param)
 
         commit_loss = diversity_loss = self.zero
         if multi:
@@ -230,7 +228,7 @@ class VectorQuantize(nn.Module):
             # reference :324-333: softmax(-similarities * T) averaged over heads and batch ("... n l -> n l"),
             # then the negative entropy per position; the (n, K) entropy is torch glue on the kernel's output
             n_pos = cb_in.shape[-2]
-            avg_prob = ops.dense_avg_prob(dense, n_pos, self.codebook_diversity_temperature)
+            avg_prob = ops.dense_avg_prob(dense, n_pos, self.codebook_diversity_temperature, emb_param)
             diversity_loss = -((-avg_prob * avg_prob.clamp(min=1e-5).log()).sum(dim=-1)).mean()
             loss = loss + diversity_loss * self.codebook_diversity_loss_weight
         if ce_commit:
@@ -242,7 +240,7 @@ class VectorQuantize(nn.Module):
                 target = torch.where(keep[None], rows_idx, torch.full_like(rows_idx, -1))
                 m = mask.reshape(embed_ind.shape[:-1] if multi else embed_ind.shape)
                 embed_ind = embed_ind.masked_fill(~(m[..., None] if multi else m), -1)
-            commit_loss = ops.dense_cross_entropy(dense, target)
+            commit_loss = ops.dense_cross_entropy(dense, target, emb_param)
             loss = loss + commit_loss * self.commitment_weight
         elif want_commit:
             commit_loss = commit
