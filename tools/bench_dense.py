@@ -42,10 +42,12 @@ def main():
         "avgprob": (lambda: ops.dense_avgprob(x, xn2, c, cn2, False, 1.0, lse, n_pos), 1),
         "rowdot": (lambda: ops.dense_rowdot(x, xn2, c, cn2, False, 1.0, lse, table, n_pos), 1),
         "backward_ce": (lambda: ops.dense_backward(x, xn2, c, cn2, c, False, 1.0, lse, coef, target=tgt), 2),
+        "backward_codes_ce": (lambda: ops.dense_backward_codes(x, xn2, c, cn2, False, 1.0, lse, coef, target=tgt), 2),
     }
     for name, (fn, passes) in runs.items():
         ms = timed(fn)
-        print(json.dumps({"pass": name, "N": N, "K": K, "d": d, "ms": round(ms, 3),
+        print(json.dumps({"pass": name, "bk": int(os.environ.get("VQB_DENSE_BK", "0")) or "default", "N": N, "K": K, "d": d,
+                          "ms": round(ms, 3),
                           "fp32_tflops": round(passes * flops / ms / 1e9, 2)}))
 
 

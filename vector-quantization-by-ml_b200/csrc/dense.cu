@@ -20,6 +20,8 @@
 // because the reference's saved `embeddings.detach()` aliases the buffer that the EMA step overwrites before backward
 // runs (codebooks.py:425 writes through `.data`): pre-update distances, post-update code vectors.  Pinned by the
 // gradients recorded from the live reference (tests/golden/dense/).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace vqb {
@@ -27,7 +29,7 @@ namespace {
 
 constexpr int BM = 64;    // rows per tile
 constexpr int BN = 64;    // codes per tile
-constexpr int BK = 16;    // k-chunk
+// k-chunk staged per step: a template parameter (16 or 32, see dense_bk())
 constexpr int LD = 68;    // padded leading dimension of the shared tiles (16-byte aligned rows)
 constexpr int kThreads = 256;
 
@@ -57,28 +59,39 @@ __device__ __forceinline__ void stage4(float (*S)[LD], int r, int kq, const floa
 
 // acc[i][j] = sum_k A[row0 + ty*4 + i][k] * B[col0 + tx*4 + j][k]   (zero-padded outside the bounds)
 // Ends with a __syncthreads(): As / Bs may be re-used and shared scalars written before the call are visible.
-template <typename T, typename TB = float>
+template <int BKT, typename T, typename TB>
 __device__ __forceinline__ void score_tile(const T* __restrict__ a_base, int64_t row0, int64_t row_end,
                                            const TB* __restrict__ b_base, int64_t col0, int64_t col_end, int d,
                                            bool vec, float (*As)[LD], float (*Bs)[LD], float acc[4][4]) {
+  constexpr int U = BKT / 16;     // quads per thread and operand in one chunk
   const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
   const int lr = tid >> 2, kq = (tid & 3) * 4;
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  float4 pa = fetch4<T>(a_base, row0 + lr, row_end, d, kq, vec);
-  float4 pb = fetch4<TB>(b_base, col0 + lr, col_end, d, kq, vec);
-  for (int k0 = 0; k0 < d; k0 += BK) {
-    stage4(As, lr, kq, pa);
-    stage4(Bs, lr, kq, pb);
+  float4 pa[U], pb[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    pa[u] = fetch4<T>(a_base, row0 + lr, row_end, d, kq + 16 * u, vec);
+    pb[u] = fetch4<TB>(b_base, col0 + lr, col_end, d, kq + 16 * u, vec);
+  }
+  for (int k0 = 0; k0 < d; k0 += BKT) {
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      stage4(As, lr, kq + 16 * u, pa[u]);
+      stage4(Bs, lr, kq + 16 * u, pb[u]);
+    }
     __syncthreads();
-    if (k0 + BK < d) {
-      pa = fetch4<T>(a_base, row0 + lr, row_end, d, k0 + BK + kq, vec);
-      pb = fetch4<TB>(b_base, col0 + lr, col_end, d, k0 + BK + kq, vec);
+    if (k0 + BKT < d) {
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        pa[u] = fetch4<T>(a_base, row0 + lr, row_end, d, k0 + BKT + kq + 16 * u, vec);
+        pb[u] = fetch4<TB>(b_base, col0 + lr, col_end, d, k0 + BKT + kq + 16 * u, vec);
+      }
     }
 #pragma unroll
-    for (int kk = 0; kk < BK; ++kk) {
+    for (int kk = 0; kk < BKT; ++kk) {
       const float4 a = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
       const float4 b = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
       const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
@@ -120,14 +133,15 @@ __global__ void __launch_bounds__(256) row_norm2_kernel(const T* __restrict__ x,
 // rowstats (MODE 0): lse[row] = log sum_k exp(alpha s_k), st[row] = s_target        grid (ceil(N/64), H)
 // rowdot   (MODE 1): r[row]   = sum_k exp(alpha s_k - lse[row]) * table[row % n_pos][k]
 // ---------------------------------------------------------------------------------------------------------------
-template <typename T, int MODE>
+template <typename T, int MODE, int BKT>
 __global__ void __launch_bounds__(kThreads) dense_rowstats_kernel(
     const T* __restrict__ x, const float* __restrict__ xn2, const float* __restrict__ cb, const float* __restrict__ cn2,
     int metric, float alpha, const int64_t* __restrict__ target, const float* __restrict__ lse_in,
     const float* __restrict__ table, int64_t n_pos, float* __restrict__ out0, float* __restrict__ st_out,
     int64_t N, int K, int d, int vec) {
-  __shared__ __align__(16) float As[BK][LD];
-  __shared__ __align__(16) float Bs[BK][LD];
+  __shared__ __align__(16) float pool[2 * BKT * LD];
+  float (*As)[LD] = reinterpret_cast<float (*)[LD]>(pool);
+  float (*Bs)[LD] = reinterpret_cast<float (*)[LD]>(pool + BKT * LD);
   __shared__ float s_xn2[BM], s_cn2[BN], s_lse[BM];
   __shared__ long long s_t[BM];
   const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
@@ -149,7 +163,7 @@ __global__ void __launch_bounds__(kThreads) dense_rowstats_kernel(
     __syncthreads();
     if (tid < BN) s_cn2[tid] = (cn2 != nullptr && col0 + tid < K) ? cn2[h * K + col0 + tid] : 0.f;
     float acc[4][4];
-    score_tile<T>(x_h, row0, N, cb_h, col0, K, d, vec != 0, As, Bs, acc);
+    score_tile<BKT, T, float>(x_h, row0, N, cb_h, col0, K, d, vec != 0, As, Bs, acc);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int r = ty * 4 + i;
@@ -214,13 +228,14 @@ __global__ void __launch_bounds__(kThreads) dense_rowstats_kernel(
 // avgprob: avg[pos][k] = (1 / (H Bp)) sum_{h, b} exp(alpha s(h, b n_pos + pos, k) - lse)      grid (ceil(n_pos/64), ceil(K/64))
 // A block owns a (64 positions x 64 codes) tile of the output and walks over heads and batch: no atomics, fixed order.
 // ---------------------------------------------------------------------------------------------------------------
-template <typename T>
+template <typename T, int BKT>
 __global__ void __launch_bounds__(kThreads) dense_avgprob_kernel(
     const T* __restrict__ x, const float* __restrict__ xn2, const float* __restrict__ cb, const float* __restrict__ cn2,
     int metric, float alpha, const float* __restrict__ lse, float* __restrict__ avg, int64_t n_pos, int64_t H,
     int64_t N, int K, int d, int vec) {
-  __shared__ __align__(16) float As[BK][LD];
-  __shared__ __align__(16) float Bs[BK][LD];
+  __shared__ __align__(16) float pool[2 * BKT * LD];
+  float (*As)[LD] = reinterpret_cast<float (*)[LD]>(pool);
+  float (*Bs)[LD] = reinterpret_cast<float (*)[LD]>(pool + BKT * LD);
   __shared__ float s_xn2[BM], s_cn2[BN], s_lse[BM];
   const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
   const int64_t pos0 = (int64_t)blockIdx.x * BM, col0 = (int64_t)blockIdx.y * BN;
@@ -245,7 +260,7 @@ __global__ void __launch_bounds__(kThreads) dense_avgprob_kernel(
         s_cn2[tid] = (cn2 != nullptr && col0 + tid < K) ? cn2[h * K + col0 + tid] : 0.f;
       }
       float acc[4][4];
-      score_tile<T>(x_h, row0, row_end, cb_h, col0, K, d, vec != 0, As, Bs, acc);
+      score_tile<BKT, T, float>(x_h, row0, row_end, cb_h, col0, K, d, vec != 0, As, Bs, acc);
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int r = ty * 4 + i;
@@ -282,17 +297,21 @@ __global__ void __launch_bounds__(kThreads) dense_avgprob_kernel(
 //   dot   : ds/dx = c:  rho_k = -w_k,  xcoef = 0
 // The weights of a 64 x 64 tile go to shared memory and feed a second tiled contraction with the code vectors.
 // ---------------------------------------------------------------------------------------------------------------
-template <typename T, int NSUB>
+template <typename T, int NSUB, int BKT>
 __global__ void __launch_bounds__(kThreads) dense_backward_kernel(
     const T* __restrict__ x, const float* __restrict__ xn2, const float* __restrict__ cb_dist,
     const float* __restrict__ cn2, const float* __restrict__ cb_comb, int metric, float alpha,
     const float* __restrict__ lse, const float* __restrict__ coef, const int64_t* __restrict__ target,
     const float* __restrict__ table, const float* __restrict__ rdot, int64_t n_pos, float* __restrict__ grad_x,
     int64_t N, int K, int d, int vec) {
-  __shared__ __align__(16) float As[BK][LD];
-  __shared__ __align__(16) float Bs[BK][LD];
+  // the score operands (first contraction) and the code tile (second contraction) are live at different times and
+  // share one pool
+  constexpr int kPool = (2 * BKT > BN ? 2 * BKT : BN) * LD;
+  __shared__ __align__(16) float pool[kPool];
+  float (*As)[LD] = reinterpret_cast<float (*)[LD]>(pool);
+  float (*Bs)[LD] = reinterpret_cast<float (*)[LD]>(pool + BKT * LD);
+  float (*Cs)[LD] = reinterpret_cast<float (*)[LD]>(pool);   // code tile [code][dim]
   __shared__ __align__(16) float Rs[BM][LD];   // rho tile  [row][code]
-  __shared__ __align__(16) float Cs[BN][LD];   // code tile [code][dim]
   __shared__ float s_xn2[BM], s_cn2[BN], s_lse[BM], s_coef[BM], s_r[BM];
   __shared__ long long s_t[BM];
   const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
@@ -323,7 +342,7 @@ __global__ void __launch_bounds__(kThreads) dense_backward_kernel(
     __syncthreads();
     if (tid < BN) s_cn2[tid] = (cn2 != nullptr && col0 + tid < K) ? cn2[h * K + col0 + tid] : 0.f;
     float acc[4][4];
-    score_tile<T>(x_h, row0, N, cd_h, col0, K, d, vec != 0, As, Bs, acc);
+    score_tile<BKT, T, float>(x_h, row0, N, cd_h, col0, K, d, vec != 0, As, Bs, acc);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int r = ty * 4 + i;
@@ -424,16 +443,18 @@ __global__ void __launch_bounds__(kThreads) dense_backward_kernel(
 // walks the latent tiles s, s + n_splits, ... and writes its own partial (n_splits, H, K, d), summed by the caller
 // in a fixed order (no atomics).
 // ---------------------------------------------------------------------------------------------------------------
-template <typename T, int NSUB>
+template <typename T, int NSUB, int BKT>
 __global__ void __launch_bounds__(kThreads) dense_backward_codes_kernel(
     const T* __restrict__ x, const float* __restrict__ xn2, const float* __restrict__ cb, const float* __restrict__ cn2,
     int metric, float alpha, const float* __restrict__ lse, const float* __restrict__ coef,
     const int64_t* __restrict__ target, const float* __restrict__ table, const float* __restrict__ rdot,
     int64_t n_pos, float* __restrict__ grad_c, int n_splits, int64_t H, int64_t N, int K, int d, int vec) {
-  __shared__ __align__(16) float As[BK][LD];
-  __shared__ __align__(16) float Bs[BK][LD];
+  constexpr int kPool = (2 * BKT > BN ? 2 * BKT : BN) * LD;
+  __shared__ __align__(16) float pool[kPool];
+  float (*As)[LD] = reinterpret_cast<float (*)[LD]>(pool);
+  float (*Bs)[LD] = reinterpret_cast<float (*)[LD]>(pool + BKT * LD);
+  float (*Xs)[LD] = reinterpret_cast<float (*)[LD]>(pool);   // latent tile [latent][dim], after the scores are done
   __shared__ __align__(16) float Rs[BM][LD];   // rho tile  [code][latent]
-  __shared__ __align__(16) float Xs[BN][LD];   // latent tile [latent][dim]
   __shared__ float s_xn2[BN], s_cn2[BM], s_lse[BN], s_coef[BN], s_r[BN];
   __shared__ long long s_t[BN], s_pos[BN];
   const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
@@ -466,7 +487,7 @@ __global__ void __launch_bounds__(kThreads) dense_backward_codes_kernel(
       s_pos[tid] = (ok && table != nullptr) ? (long long)(row % n_pos) : 0ll;
     }
     float acc[4][4];
-    score_tile<float, T>(cb_h, code0, K, x_h, n0, N, d, vec != 0, As, Bs, acc);
+    score_tile<BKT, float, T>(cb_h, code0, K, x_h, n0, N, d, vec != 0, As, Bs, acc);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int r = ty * 4 + i;
@@ -563,6 +584,17 @@ int check_common(const void* x, const void* cb, int64_t H, int64_t N, int K, int
   return VQB_OK;
 }
 
+// k-chunk of the score contraction: 16 or 32 floats per operand row and step (VQB_DENSE_BK overrides the default).
+// With 32 a chunk is ~1100 issue cycles per block, longer than the global-load latency of the prefetched next chunk.
+inline int dense_bk() {
+  static const int bk = [] {
+    const char* e = getenv("VQB_DENSE_BK");
+    const int v = e ? atoi(e) : 16;
+    return v == 32 ? 32 : 16;
+  }();
+  return bk;
+}
+
 inline int vec_ok(const void* x, const void* a, const void* b, int d) {
   return (d % 4 == 0) && ((uintptr_t)x % 16 == 0) && ((uintptr_t)a % 16 == 0) && ((uintptr_t)b % 16 == 0);
 }
@@ -595,8 +627,12 @@ extern "C" int vqb_dense_rowstats(const void* x, int x_dtype, const float* xn2, 
   cudaStream_t st = (cudaStream_t)stream;
   const dim3 grid((unsigned)((N + BM - 1) / BM), (unsigned)H);
   const int vec = vec_ok(x, codebook, codebook, d);
-  VQB_DISPATCH_DTYPE(x_dtype, T, dense_rowstats_kernel<T, 0><<<grid, kThreads, 0, st>>>(
-      (const T*)x, xn2, codebook, cn2, metric, alpha, target, nullptr, nullptr, 1, lse_out, target_score_out, N, K, d, vec));
+#define VQB_DENSE_RS0(BKT)                                                                                  \
+  VQB_DISPATCH_DTYPE(x_dtype, T, dense_rowstats_kernel<T, 0, BKT><<<grid, kThreads, 0, st>>>(                 \
+      (const T*)x, xn2, codebook, cn2, metric, alpha, target, nullptr, nullptr, 1, lse_out, target_score_out, \
+      N, K, d, vec))
+  if (dense_bk() == 32) { VQB_DENSE_RS0(32); } else { VQB_DENSE_RS0(16); }
+#undef VQB_DENSE_RS0
   VQB_LAUNCH_CHECK();
   return VQB_OK;
 }
@@ -615,8 +651,11 @@ extern "C" int vqb_dense_rowdot(const void* x, int x_dtype, const float* xn2, co
   cudaStream_t st = (cudaStream_t)stream;
   const dim3 grid((unsigned)((N + BM - 1) / BM), (unsigned)H);
   const int vec = vec_ok(x, codebook, codebook, d);
-  VQB_DISPATCH_DTYPE(x_dtype, T, dense_rowstats_kernel<T, 1><<<grid, kThreads, 0, st>>>(
-      (const T*)x, xn2, codebook, cn2, metric, alpha, nullptr, lse, table, n_pos, rdot_out, nullptr, N, K, d, vec));
+#define VQB_DENSE_RS1(BKT)                                                                                       \
+  VQB_DISPATCH_DTYPE(x_dtype, T, dense_rowstats_kernel<T, 1, BKT><<<grid, kThreads, 0, st>>>(                      \
+      (const T*)x, xn2, codebook, cn2, metric, alpha, nullptr, lse, table, n_pos, rdot_out, nullptr, N, K, d, vec))
+  if (dense_bk() == 32) { VQB_DENSE_RS1(32); } else { VQB_DENSE_RS1(16); }
+#undef VQB_DENSE_RS1
   VQB_LAUNCH_CHECK();
   return VQB_OK;
 }
@@ -634,8 +673,11 @@ extern "C" int vqb_dense_avgprob(const void* x, int x_dtype, const float* xn2, c
   cudaStream_t st = (cudaStream_t)stream;
   const dim3 grid((unsigned)((n_pos + BM - 1) / BM), (unsigned)((K + BN - 1) / BN));
   const int vec = vec_ok(x, codebook, codebook, d);
-  VQB_DISPATCH_DTYPE(x_dtype, T, dense_avgprob_kernel<T><<<grid, kThreads, 0, st>>>(
-      (const T*)x, xn2, codebook, cn2, metric, alpha, lse, avg_out, n_pos, H, N, K, d, vec));
+#define VQB_DENSE_AP(BKT)                                                                        \
+  VQB_DISPATCH_DTYPE(x_dtype, T, dense_avgprob_kernel<T, BKT><<<grid, kThreads, 0, st>>>(         \
+      (const T*)x, xn2, codebook, cn2, metric, alpha, lse, avg_out, n_pos, H, N, K, d, vec))
+  if (dense_bk() == 32) { VQB_DENSE_AP(32); } else { VQB_DENSE_AP(16); }
+#undef VQB_DENSE_AP
   VQB_LAUNCH_CHECK();
   return VQB_OK;
 }
@@ -661,11 +703,15 @@ extern "C" int vqb_dense_backward(const void* x, int x_dtype, const float* xn2, 
   const dim3 grid((unsigned)((N + BM - 1) / BM), (unsigned)H, (unsigned)((d + 64 * nsub - 1) / (64 * nsub)));
   VQB_REQUIRE(grid.z <= 65535, VQB_ERR_UNSUPPORTED, "vqb_dense_backward: d=%d too large", d);
   if (n_pos < 1) n_pos = 1;
-#define VQB_DENSE_BWD(NS)                                                                                        \
-  VQB_DISPATCH_DTYPE(x_dtype, T, dense_backward_kernel<T, NS><<<grid, kThreads, 0, st>>>(                          \
+#define VQB_DENSE_BWD(NS, BKT)                                                                                   \
+  VQB_DISPATCH_DTYPE(x_dtype, T, dense_backward_kernel<T, NS, BKT><<<grid, kThreads, 0, st>>>(                     \
       (const T*)x, xn2, codebook_dist, cn2, codebook_comb, metric, alpha, lse, coef, target, table, rdot, n_pos, \
       grad_x, N, K, d, vec))
-  if (nsub == 1) { VQB_DENSE_BWD(1); } else if (nsub == 2) { VQB_DENSE_BWD(2); } else { VQB_DENSE_BWD(4); }
+  if (dense_bk() == 32) {
+    if (nsub == 1) { VQB_DENSE_BWD(1, 32); } else if (nsub == 2) { VQB_DENSE_BWD(2, 32); } else { VQB_DENSE_BWD(4, 32); }
+  } else {
+    if (nsub == 1) { VQB_DENSE_BWD(1, 16); } else if (nsub == 2) { VQB_DENSE_BWD(2, 16); } else { VQB_DENSE_BWD(4, 16); }
+  }
 #undef VQB_DENSE_BWD
   VQB_LAUNCH_CHECK();
   return VQB_OK;
@@ -709,11 +755,15 @@ extern "C" int vqb_dense_backward_codes(const void* x, int x_dtype, const float*
   const dim3 grid((unsigned)((K + BM - 1) / BM), (unsigned)(H * n_splits), (unsigned)((d + 64 * nsub - 1) / (64 * nsub)));
   VQB_REQUIRE(grid.z <= 65535, VQB_ERR_UNSUPPORTED, "vqb_dense_backward_codes: d=%d too large", d);
   if (n_pos < 1) n_pos = 1;
-#define VQB_DENSE_BWDC(NS)                                                                                          \
-  VQB_DISPATCH_DTYPE(x_dtype, T, dense_backward_codes_kernel<T, NS><<<grid, kThreads, 0, st>>>(                      \
+#define VQB_DENSE_BWDC(NS, BKT)                                                                                     \
+  VQB_DISPATCH_DTYPE(x_dtype, T, dense_backward_codes_kernel<T, NS, BKT><<<grid, kThreads, 0, st>>>(                 \
       (const T*)x, xn2, codebook, cn2, metric, alpha, lse, coef, target, table, rdot, n_pos, grad_c_partial,        \
       n_splits, H, N, K, d, vec))
-  if (nsub == 1) { VQB_DENSE_BWDC(1); } else if (nsub == 2) { VQB_DENSE_BWDC(2); } else { VQB_DENSE_BWDC(4); }
+  if (dense_bk() == 32) {
+    if (nsub == 1) { VQB_DENSE_BWDC(1, 32); } else if (nsub == 2) { VQB_DENSE_BWDC(2, 32); } else { VQB_DENSE_BWDC(4, 32); }
+  } else {
+    if (nsub == 1) { VQB_DENSE_BWDC(1, 16); } else if (nsub == 2) { VQB_DENSE_BWDC(2, 16); } else { VQB_DENSE_BWDC(4, 16); }
+  }
 #undef VQB_DENSE_BWDC
   VQB_LAUNCH_CHECK();
   return VQB_OK;
