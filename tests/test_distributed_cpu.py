@@ -73,6 +73,9 @@ def _worker(rank, world, port, out):
     keys = _pack(score, gidx)
     D.merge_min_keys(keys)
     res["win_idx"] = (keys & 0xFFFFFFFF).tolist()
+    # 4. distributed_replace_codes=False: locally sampled replacements averaged over the ranks
+    loc = torch.full((3, 4), float(rank + 1))
+    res["mean"] = D.maybe_distributed_mean(loc).tolist()
     if rank == 0:
         torch.save(res, out)
     dist.destroy_process_group()
@@ -86,3 +89,4 @@ def test_two_rank_gloo_host_logic(tmp_path):
     assert res["stats"]
     # scores: equal 1.5 -> lower index 3; -2.5 < -2.0 -> 8; 0.0 tie -> 4; 2.0 < 3.0 -> 10; -0.0 vs 0.0: -0.0 sorts first -> 2; 7 tie -> 5
     assert res["win_idx"] == [3, 8, 4, 10, 2, 5]
+    assert res["mean"] == [[1.5] * 4] * 3

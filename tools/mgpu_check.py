@@ -63,6 +63,25 @@ for thr in (0, 2):
         dist.broadcast(ref, src=0)
         check(torch.equal(mine, ref), f"replicas diverged: {name} (thr={thr})")
 
+# ---------------- 1b. distributed_replace_codes=False (reference codebooks.py:238-239) ----------------
+# every rank samples its own replacement rows and the replacements are their mean over the ranks: replicas must stay
+# identical, and the replaced codes must differ from any single rank's rows (they are means of W rows)
+torch.manual_seed(1 + rank)            # different local draws on every rank
+dpm = VectorQuantize(dim=d, codebook_params=CodebookParams(dim=d, codebook_size=K, threshold_ema_dead_code=2,
+                                                           kmeans_params=KmeansParameters(),
+                                                           distributed_replace_codes=False), sync_codebook=True).to(dev)
+cbm = dpm._codebook
+cbm.embeddings.copy_(c0); cbm.embed_avg.copy_(c0); cbm.cluster_size.fill_(0.5); cbm.invalidate_cache()
+dpm.train()
+with torch.no_grad():
+    dpm(x_all[rank][None].to(dev))
+for name in ("embeddings", "embed_avg", "cluster_size"):
+    mine = getattr(cbm, name).contiguous()
+    ref = mine.clone()
+    dist.broadcast(ref, src=0)
+    check(torch.equal(mine, ref), f"replicas diverged with distributed_replace_codes=False: {name}")
+check(bool((cbm.cluster_size == 2.0).any()), "no code was replaced in the distributed_replace_codes=False case")
+
 # ---------------- 2. sharded codebook ----------------
 K, d, N = 4096, 64, 20000
 g = torch.Generator().manual_seed(9)

@@ -201,6 +201,17 @@ class Codebook(nn.Module):
                 # reference codebooks.py:171-175: sample_vectors_distributed -> identical replacements on every rank
                 src = D.sample_vectors_distributed(flat[h], m, self._draw_rows)
                 rows = torch.arange(m, device=flat.device)
+            elif not self.distributed_replace_codes and D.is_distributed():
+                # reference codebooks.py:231-239: every rank samples locally (after weights_regularization) and the
+                # replacements are the mean over the ranks (not re-normalised)
+                src = flat[h][self._draw_rows(N, m, flat.device)].float().contiguous()
+                if self.weights_l2norm:
+                    src = ops.l2norm_rows(src)
+                src = D.maybe_distributed_mean(src)
+                ops.expire_scatter(src, torch.arange(m, device=flat.device), float(self.threshold_ema_dead_code),
+                                   float(self.reset_cluster_size), False, self.cluster_size.data[h],
+                                   self.embed_avg.data[h], self.embeddings.data[h])
+                continue
             else:
                 src, rows = flat[h], self._draw_rows(N, m, flat.device)
             ops.expire_scatter(src, rows, float(self.threshold_ema_dead_code), float(self.reset_cluster_size),

@@ -26,6 +26,16 @@ def all_reduce_sum(t: torch.Tensor, group=None) -> None:
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
 
 
+def maybe_distributed_mean(t: torch.Tensor, group=None) -> torch.Tensor:
+    """reference utils/distributed.py:86-92: mean over the ranks when a process group is up (used for the locally
+    sampled replacement codes when `distributed_replace_codes=False`, codebooks.py:238-239)."""
+    if not is_distributed():
+        return t
+    t = t.contiguous()
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return t / dist.get_world_size(group)
+
+
 def merge_min_keys(keys: torch.Tensor, group=None) -> torch.Tensor:
     """all_reduce(MIN) of int64 (score, index) keys; in place."""
     if is_distributed():
