@@ -145,3 +145,36 @@ def test_reference_checkpoints_load_strictly(name):
     assert set(sd) == set(fx["state_dict"])
     for k, v in fx["state_dict"].items():
         assert torch.equal(sd[k], v), k
+
+
+def test_c_abi_rejects_bad_arguments_before_touching_a_device():
+    """Error convention of include/vqb.h: negative VQB_ERR_* code, message via vqb_last_error(), no exception, no exit --
+    and argument validation comes before any CUDA call, so it can be exercised here without a GPU."""
+    from vqb200 import _lib as L
+    lib = L.lib()
+    P = 1 << 12     # a non-null dummy pointer: validation must fail before anything dereferences it
+
+    def err():
+        return lib.vqb_last_error().decode()
+
+    assert lib.vqb_dense_rowstats(0, 0, 0, 0, 0, 0, 1.0, 0, 0, 0, 0, 10, 4, 4, 0) == -1 and "null" in err()
+    assert lib.vqb_dense_rowstats(P, 0, 0, P, 0, 7, 1.0, 0, P, 0, 1, 10, 4, 4, 0) == -1 and "metric" in err()
+    assert lib.vqb_dense_rowstats(P, 9, P, P, P, 0, 1.0, 0, P, 0, 1, 10, 4, 4, 0) == -1 and "dtype" in err()
+    assert lib.vqb_dense_rowstats(P, 0, 0, P, 0, 0, 1.0, 0, P, 0, 1, 10, 4, 4, 0) == -1 and "norms" in err()
+    assert lib.vqb_dense_backward(P, 0, P, P, P, P, 0, 1.0, P, P, P, P, P, 1, P, 1, 10, 4, 4, 0) == -1 \
+        and "exactly one" in err()
+    assert lib.vqb_dense_avgprob(P, 0, P, P, P, 0, 1.0, P, P, 3, 1, 10, 4, 4, 0) == -1 and "multiple" in err()
+    assert lib.vqb_dense_backward_codes(P, 0, P, P, P, 0, 1.0, P, P, P, 0, 0, 1, P, 99, 1, 10, 4, 4, 0) == -1 \
+        and "n_splits" in err()
+    assert lib.vqb_search(0, 0, 0, 0, 0, 1, 10, 4, 4, 0, 0, 0, 0, 0, 0, 0) == -1 and "vqb_search" in err()
+    assert lib.vqb_ema_reduce(0, 0, 0, 0, 0, 1, 10, 4, 4, 0, 0, 0, 0) == -1
+    assert lib.vqb_gather_st_loss(0, 0, 0, 0, 0, 1, 1, 0, 0, 1, 10, 4, 4, 0, 0, 0) == -1
+    assert lib.vqb_prepare_codebook(0, 1, 4, 4, 0, 0, 0, 0) == -1
+    assert lib.vqb_minkey_pack(0, 0, 5, 0, 0) == -1
+    # the Python wrapper maps the codes to exceptions
+    with pytest.raises(ValueError, match="metric"):
+        L.check(lib.vqb_dense_rowstats(P, 0, 0, P, 0, 7, 1.0, 0, P, 0, 1, 10, 4, 4, 0), "vqb_dense_rowstats")
+    # size helpers are pure functions of the shape
+    assert lib.vqb_search_workspace_bytes(1, 1 << 20, 8192, 256) > (1 << 20) * 256 * 2
+    assert lib.vqb_dense_backward_codes_splits(1, 1 << 20, 8192, 256) >= 1
+    assert lib.vqb_dense_backward_codes_splits(1, 10, 64, 64) == 1          # never more splits than latent tiles
