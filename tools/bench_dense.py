@@ -1,5 +1,5 @@
 """Times the fp32 dense-similarity passes (csrc/dense.cu) with CUDA events: one JSON line per pass.
-    python tools/bench_dense.py [N K d]
+    python tools/bench_dense.py [N K d [passes [iters]]]      # passes: comma-separated subset, e.g. rowstats,backward_ce
 Algorithmic work: 2 N K d flops per score pass; the backward pass does two contractions (scores + combination)."""
 import json
 import os
@@ -12,7 +12,7 @@ sys.path.insert(0, os.path.join(ROOT, "vector-quantization-by-ml_b200"))
 from vqb200 import ops  # noqa: E402
 
 
-def timed(fn, iters=5):
+def timed(fn, iters):
     fn()
     torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -26,6 +26,8 @@ def timed(fn, iters=5):
 
 def main():
     N, K, d = (int(v) for v in sys.argv[1:4]) if len(sys.argv) >= 4 else (65536, 8192, 256)
+    only = sys.argv[4].split(",") if len(sys.argv) >= 5 else None
+    iters = int(sys.argv[5]) if len(sys.argv) >= 6 else 5
     dev = torch.device("cuda:0")
     g = torch.Generator().manual_seed(0)
     x = torch.randn(1, N, d, generator=g).to(dev)
@@ -45,7 +47,9 @@ def main():
         "backward_codes_ce": (lambda: ops.dense_backward_codes(x, xn2, c, cn2, False, 1.0, lse, coef, target=tgt), 2),
     }
     for name, (fn, passes) in runs.items():
-        ms = timed(fn)
+        if only is not None and name not in only:
+            continue
+        ms = timed(fn, iters)
         print(json.dumps({"pass": name, "bk": int(os.environ.get("VQB_DENSE_BK", "0")) or "default", "N": N, "K": K, "d": d,
                           "ms": round(ms, 3),
                           "fp32_tflops": round(passes * flops / ms / 1e9, 2)}))
