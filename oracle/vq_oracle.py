@@ -392,7 +392,7 @@ def vq_forward_learnable(embeddings: torch.Tensor, x: torch.Tensor, *, commitmen
     inplace_loss = None
     if inplace_optimizer is not None:
         xd = x.detach().float()
-        sim0 = similarities(xd.reshape(1, -1, d), embeddings.detach(), False)
+        sim0 = similarities(xd.reshape(1, -1, d), embeddings.detach(), use_cosine_sim)
         oh0 = F.one_hot(sim0.argmax(-1).reshape(1, B, n), embeddings.shape[1]).type(xd.dtype)
         q0 = torch.einsum("h b n c, h c d -> h b n d", oh0, embeddings)[0]
         if mask is not None:
@@ -451,7 +451,8 @@ def _log_eps(t: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:
 
 def vq_forward_dense(state: CodebookState, x: torch.Tensor, opts: VQOpts, *, training: bool = True,
                      mask: Optional[torch.Tensor] = None, targets: Optional[torch.Tensor] = None,
-                     ce_commit: bool = False, diversity_weight: float = 0.0, diversity_temperature: float = 100.0):
+                     ce_commit: bool = False, diversity_weight: float = 0.0, diversity_temperature: float = 100.0,
+                     freeze_codebook: bool = False):
     """``x`` may require grad.  With ``targets``: returns (quantize, ce) like the reference's ``return_loss`` branch
     (:298-299).  Otherwise (quantize, indices, loss[1], {"commitment", "codebook_diversity"}).
 
@@ -486,7 +487,8 @@ def vq_forward_dense(state: CodebookState, x: torch.Tensor, opts: VQOpts, *, tra
 
     alias = CodebookState(state.embeddings.data, state.embed_avg.data, state.cluster_size.data, state.is_initialized)
     with torch.no_grad():
-        quant, ind, _ = codebook_forward(alias, x.detach(), opts.codebook, training=training, mask=mask)
+        quant, ind, _ = codebook_forward(alias, x.detach(), opts.codebook, training=training, mask=mask,
+                                         freeze_codebook=freeze_codebook)
     codes_q = quant                                                     # :262-268 (detached: no learnable codebook here)
     if training:
         quant = x + (quant - x).detach()                                # :273

@@ -41,7 +41,12 @@ def _patch(monkeypatch):
         with torch.no_grad():
             q, ind, _ = O.codebook_forward(st, xf.detach(), opts, training=self.training, mask=mask,
                                            freeze_codebook=freeze_codebook)
-        commit = torch.nn.functional.mse_loss(q, xf) if want_commit else None
+        commit = None
+        if want_commit and mask is not None:      # vqb_gather_st_loss: mean over the rows with mask != 0
+            keep = self._expand_mask(mask, flat.shape[1]).bool()
+            commit = torch.nn.functional.mse_loss(q.reshape(H, -1, d), flat.float(), reduction="none")[:, keep].mean()
+        elif want_commit:
+            commit = torch.nn.functional.mse_loss(q, xf.float())
         if fuse_st and self.training:
             q = xf + (q - xf).detach()
         return q, ind, commit
