@@ -245,3 +245,156 @@ def test_learnable_restatement_equals_live_reference_on_random_options(seed):
     assert torch.allclose(x.grad, xo.grad, rtol=1e-6, atol=1e-9, equal_nan=True)
     assert torch.allclose(vq._codebook.embeddings.grad, emb.grad, rtol=1e-6, atol=1e-9, equal_nan=True)
     assert torch.equal(vq._codebook.embeddings.detach(), emb.detach())
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# ResidualVQ / GroupedResidualVQ host logic (vqb200/rvq.py generic level loop: quantize-dropout, shared codebook,
+# projections, masks, return_all_codes, channel-first, codes-from-indices) against the LIVE reference, the kernels
+# replaced as above.  The reference's state_dict is loaded into the product module (strict).
+# ---------------------------------------------------------------------------------------------------------------
+def make_rvq_case(seed):
+    r = random.Random(900 + seed)
+    grouped = r.random() < 0.3
+    groups = r.choice([2, 3]) if grouped else 1
+    cb_dim = r.choice([4, 8])
+    proj = (not grouped) and r.random() < 0.3
+    dim = (cb_dim + 3 if proj else cb_dim) * groups
+    dropout = r.random() < 0.4
+    Q = r.choice([2, 3, 4])
+    channel_first = (not proj) and r.random() < 0.25
+    cfg = dict(grouped=grouped, groups=groups, cb_dim=cb_dim, dim=dim, proj=proj, Q=Q, K=r.choice([6, 15]),
+               shared=r.random() < 0.3, dropout=dropout, cutoff=r.randrange(0, Q) if dropout else 0,
+               mult=r.choice([1, 1, 2]) if dropout else 1, training=r.random() < 0.8,
+               all_codes=r.random() < 0.4, channel_first=channel_first,
+               mask=(not channel_first) and r.random() < 0.3, b=r.choice([1, 2]), n=r.choice([4, 7]),
+               drop_seed=r.randrange(100), seed=seed)
+    return cfg
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "vector_quantization")),
+                    reason="the live reference is only present in the build container")
+@pytest.mark.parametrize("seed", list(range(24)))
+def test_rvq_host_logic_equals_live_reference_on_random_options(seed, monkeypatch):
+    _reference_api()
+    from vector_quantization.codebooks import CodebookParams as RefParams
+    from vector_quantization.residual_vq import GroupedResidualVQ as RefGrouped, ResidualVQ as RefRVQ
+    import vqb200
+    _patch(monkeypatch)
+    cfg = make_rvq_case(seed)
+
+    def build(RVQ, Grouped, Params):
+        cp = Params(dim=cfg["cb_dim"], codebook_size=cfg["K"], threshold_ema_dead_code=0)
+        kw = dict(num_quantizers=cfg["Q"], codebook_params=cp, shared_codebook=cfg["shared"], sync_codebook=False,
+                  quantize_dropout=cfg["dropout"], quantize_dropout_cutoff_index=cfg["cutoff"],
+                  quantize_dropout_multiple_of=cfg["mult"])
+        if cfg["grouped"]:
+            return Grouped(dim=cfg["dim"], groups=cfg["groups"], channel_last=not cfg["channel_first"], **kw) \
+                if not cfg["channel_first"] else \
+                Grouped(dim=cfg["dim"], groups=cfg["groups"], channel_last=False, **kw)
+        if cfg["proj"]:
+            kw["codebook_dim"] = cfg["cb_dim"]
+        if cfg["channel_first"]:
+            kw["channel_last"] = False
+        return RVQ(dim=cfg["dim"], **kw)
+
+    torch.manual_seed(seed)
+    ref = build(RefRVQ, RefGrouped, RefParams)
+    g = torch.Generator().manual_seed(3000 + seed)
+    with torch.no_grad():
+        for name, buf in ref.named_buffers():
+            if name.endswith("embeddings"):
+                buf.copy_(torch.randn(buf.shape, generator=g) * 0.6)
+        sd = ref.state_dict()
+        for name in sd:
+            if name.endswith("embed_avg"):
+                sd[name].copy_(sd[name.replace("embed_avg", "embeddings")])
+            if name.endswith("cluster_size"):
+                sd[name].fill_(1.0)
+    ours = build(vqb200.ResidualVQ, vqb200.GroupedResidualVQ, vqb200.CodebookParams)
+    if cfg["grouped"] and cfg["channel_first"]:
+        pytest.skip("GroupedResidualVQ(channel_last=False) does not forward channel_last to its ResidualVQs in the "
+                    "reference: each group would see a channel-last view of channel-first data")
+    ours.load_state_dict(ref.state_dict(), strict=True)
+    ref.train(cfg["training"]); ours.train(cfg["training"])
+    shape = (cfg["b"], cfg["dim"], cfg["n"]) if cfg["channel_first"] else (cfg["b"], cfg["n"], cfg["dim"])
+    x0 = torch.randn(*shape, generator=g)
+    w = torch.randn(*shape, generator=g)
+    mask = (torch.rand(cfg["b"], cfg["n"], generator=g) > 0.3) if cfg["mask"] else None
+    outs = []
+    for mod in (ref, ours):
+        x = x0.clone().requires_grad_(True)
+        kw = dict(mask=mask, return_all_codes=cfg["all_codes"])
+        if cfg["grouped"]:
+            random.seed(cfg["drop_seed"])             # GroupedResidualVQ draws the dropout seed from python's RNG
+        else:
+            kw["rand_quantize_dropout_fixed_seed"] = cfg["drop_seed"]
+        out = mod(x, **kw)
+        out = [o if torch.is_tensor(o) else torch.stack(list(o)) for o in out]
+        scalar = (out[0] * w).sum() + out[2].sum() * 1.7
+        if scalar.requires_grad:
+            scalar.backward()
+        outs.append((out, x.grad, {k: v.detach().clone() for k, v in mod.state_dict().items()}))
+    (ro, rg, rs), (oo, og, os_) = outs
+    assert len(ro) == len(oo)
+    for a, b in zip(ro, oo):
+        assert a.shape == b.shape and a.dtype == b.dtype
+    assert torch.equal(ro[1], oo[1]), "indices"
+    assert torch.allclose(ro[0], oo[0], rtol=1e-6, atol=1e-7, equal_nan=True)
+    assert torch.allclose(ro[2], oo[2], rtol=1e-6, atol=1e-8, equal_nan=True)
+    if len(ro) > 3:
+        assert torch.allclose(ro[3], oo[3], rtol=1e-6, atol=1e-7)
+    assert (rg is None) == (og is None)
+    if rg is not None:
+        assert torch.allclose(rg, og, rtol=1e-5, atol=1e-7, equal_nan=True)
+    for k in rs:
+        assert torch.allclose(rs[k], os_[k], rtol=1e-6, atol=1e-7), k
+    # codes / output from indices (the reference uses einx there; the stand-in of tests/golden/make_golden.py)
+    if not cfg["dropout"] or not cfg["training"]:
+        ind = ro[1]
+        assert torch.allclose(ref.get_codes_from_indices(ind), ours.get_codes_from_indices(ind), rtol=1e-6, atol=1e-7)
+        if not cfg["grouped"]:      # the reference's grouped variant reads an undefined `self.split_dim` here
+            assert torch.allclose(ref.get_output_from_indices(ind), ours.get_output_from_indices(ind), rtol=1e-6,
+                                  atol=1e-7)
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "vector_quantization")),
+                    reason="the live reference is only present in the build container")
+@pytest.mark.parametrize("seed", list(range(16)))
+def test_projected_vq_host_logic_equals_live_reference_on_random_options(seed, monkeypatch):
+    """VectorQuantize with project_in / project_out (+ LayerNorm) on top of the random option combinations above:
+    the product (kernels replaced, reference state_dict loaded) against the live reference, incl. input gradients."""
+    RefVQ, RefParams = _reference_api()
+    import vqb200
+    _patch(monkeypatch)
+    cfg = make_case(100 + seed)
+    r = random.Random(7000 + seed)
+    cfg["dim"] = cfg["dim"] + r.choice([1, 3])           # codebook_input_dim != dim -> projections
+    ln = r.random() < 0.5
+    shape = {"series": lambda s: (s[0], s[1], cfg["dim"]), "image": lambda s: (s[0], 2, 3, cfg["dim"]),
+             "channel_first": lambda s: (s[0], cfg["dim"], 3, 2), "one": lambda s: (s[0], cfg["dim"])}[cfg["kind"]]
+    cfg["shape"] = shape(cfg["shape"])
+    mods = []
+    for VQ, Params in ((RefVQ, RefParams), (vqb200.VectorQuantize, vqb200.CodebookParams)):
+        kw = module_kwargs(cfg, Params)
+        kw["codebook_dim"] = cfg["cb_dim"]
+        kw["layernorm_after_project_in"] = ln
+        torch.manual_seed(seed)
+        mods.append(VQ(**kw))
+    ref, ours = mods
+    emb, x0, w, mask, targets = inputs(cfg)
+    with torch.no_grad():
+        ref._codebook.embeddings.copy_(emb); ref._codebook.embed_avg.copy_(emb); ref._codebook.cluster_size.fill_(1.0)
+    ours.load_state_dict(ref.state_dict(), strict=True)
+    res = []
+    for mod in (ref, ours):
+        mod.train(cfg["training"])
+        x = x0.clone().requires_grad_(True)
+        if targets is not None:
+            out = mod(x, indices=targets, freeze_codebook=cfg["freeze"])
+        else:
+            out = mod(x, mask=mask, freeze_codebook=cfg["freeze"])
+        res.append(finish(cfg, out, x, w, mod._codebook.embeddings, mod._codebook.cluster_size))
+        res[-1]["proj_grad"] = mod.project_in[0].weight.grad.clone() if ln and mod.project_in[0].weight.grad is not None \
+            else (mod.project_in.weight.grad.clone() if not ln and mod.project_in.weight.grad is not None
+                  else torch.zeros(1))
+    compare(res[0], res[1], exact=False, cfg=cfg)
