@@ -1,0 +1,79 @@
+"""Plain-torch CPU stand-ins for the tensor-level wrappers of vqb200/ops.py (each states what the C entry point behind
+it computes, include/vqb.h).  TEST INFRASTRUCTURE: they let the orchestration in vqb200/codebook.py -- branch selection
+in `_run`, the packed statistics all_reduce, dead-code expiry and kmeans init under data parallel -- run in the
+world_size-2 Gloo tests on CPU.  The kernels themselves are tested on the GPU."""
+import torch
+import torch.nn.functional as F
+
+
+def _sims(x, emb, cosine):
+    x = x.float()
+    return torch.einsum("hnd,hkd->hnk", x, emb) if cosine else -torch.cdist(x, emb)
+
+
+def prepare_codebook(embeddings, use_cosine_sim, out=None):
+    return torch.zeros(8, dtype=torch.uint8)
+
+
+def search(x, embeddings, cache, use_cosine_sim, *, idx_offset=0, want_score=False, latents_prepared=False,
+           force_exact=False):
+    s = _sims(x, embeddings, use_cosine_sim)
+    best, idx = s.max(-1)
+    return idx + idx_offset, (-best if want_score else None), torch.zeros(8, dtype=torch.uint8)
+
+
+def l2norm_rows(x):
+    return F.normalize(x.float(), p=2, dim=-1)
+
+
+def gather_st_loss(x, embeddings, idx, mask_u8, training, want_loss):
+    H, N, d = x.shape
+    xf = x.float()
+    c = torch.stack([embeddings[h][idx[h]] for h in range(H)], 0)
+    q = xf + (c - xf) if training else c
+    loss = None
+    if want_loss:
+        keep = torch.ones(N, dtype=torch.bool) if mask_u8 is None else mask_u8.bool()
+        rows = int(keep.sum()) * H
+        err = ((c - xf) ** 2)[:, keep]
+        loss = torch.stack([err.mean() if rows else torch.tensor(float("nan")), torch.tensor(float(rows))])
+    return q, loss
+
+
+def ema_reduce(x, idx, mask_u8, K, bound_ws=None):
+    H, N, d = x.shape
+    onehot = F.one_hot(idx, K).float()
+    if mask_u8 is not None:
+        onehot = onehot * mask_u8.bool()[None, :, None]
+    sums = torch.einsum("hnd,hnk->hkd", x.float(), onehot)
+    return torch.cat([sums, onehot.sum(1)[..., None]], -1).contiguous()
+
+
+def ema_apply(stats, cluster_size, embed_avg, embeddings, weight, eps, weights_l2norm):
+    K = stats.shape[1]
+    cluster_size.lerp_(stats[..., -1], weight)
+    embed_avg.lerp_(stats[..., :-1], weight)
+    total = cluster_size.sum(-1, keepdim=True)
+    smoothed = (cluster_size + eps) / (total + K * eps) * total
+    new = embed_avg / smoothed[..., None]
+    embeddings.copy_(F.normalize(new, dim=-1) if weights_l2norm else new)
+
+
+def expire_scatter(x_rows, sample_rows, threshold, reset, weights_l2norm, cluster_size, embed_avg, embeddings):
+    dead = cluster_size < threshold
+    picked = x_rows[sample_rows.to(torch.int64)].float()
+    if weights_l2norm:
+        picked = F.normalize(picked, dim=-1)
+    embeddings[dead] = picked
+    cluster_size[dead] = reset
+    embed_avg[dead] = picked * reset
+
+
+def install(ops, lib):
+    """Replace the wrappers on the `vqb200.ops` module object and the device guard of `vqb200._lib`."""
+    for name in ("prepare_codebook", "search", "l2norm_rows", "gather_st_loss", "ema_reduce", "ema_apply",
+                 "expire_scatter"):
+        setattr(ops, name, globals()[name])
+    ops.l2norm_prepare_supported = lambda d: False
+    ops.quantize_ema_supported = lambda d: False
+    lib.require_device = lambda x: None

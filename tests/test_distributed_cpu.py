@@ -90,3 +90,108 @@ def test_two_rank_gloo_host_logic(tmp_path):
     # scores: equal 1.5 -> lower index 3; -2.5 < -2.0 -> 8; 0.0 tie -> 4; 2.0 < 3.0 -> 10; -0.0 vs 0.0: -0.0 sorts first -> 2; 7 tie -> 5
     assert res["win_idx"] == [3, 8, 4, 10, 2, 5]
     assert res["mean"] == [[1.5] * 4] * 3
+
+
+def _dp_worker(rank, world, port, out):
+    """Data parallel through the PRODUCT's orchestration (Codebook._run, expire_codes_, _kmeans_init) on Gloo, with the
+    tensor-level wrappers replaced by plain-torch statements (tests/cpu_kernels.py)."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for p in (root, os.path.join(root, "tests"), os.path.join(root, "vector-quantization-by-ml_b200")):
+        sys.path.insert(0, p)
+    import cpu_kernels
+    from oracle import vq_oracle as O
+    from vqb200 import CodebookParams, KmeansParameters, VectorQuantize, _lib, ops
+    cpu_kernels.install(ops, _lib)
+    res = {}
+    K, d, n_per = 48, 8, 160
+    g = torch.Generator().manual_seed(3)
+    x_all = torch.randn(world, n_per, d, generator=g)
+    c0 = torch.randn(1, K, d, generator=g) * 0.5
+
+    def replicas_identical(cb):
+        ok = True
+        for name in ("embeddings", "embed_avg", "cluster_size"):
+            mine = getattr(cb, name).detach().clone().contiguous()
+            ref = mine.clone()
+            dist.broadcast(ref, src=0)
+            ok &= torch.equal(mine, ref)
+        return ok
+
+    def make(thr, cs0=None, **cp):
+        torch.manual_seed(0)
+        vq = VectorQuantize(dim=d, codebook_params=CodebookParams(dim=d, codebook_size=K, threshold_ema_dead_code=thr,
+                                                                  kmeans_params=KmeansParameters(), **cp),
+                            sync_codebook=True).train()
+        cb = vq._codebook
+        with torch.no_grad():
+            cb.embeddings.copy_(c0); cb.embed_avg.copy_(c0)
+            cb.cluster_size.fill_(cs0 if cs0 is not None else (1.0 if thr == 0 else 0.5))
+        return vq, cb
+
+    # 1. EMA step without expiry: every rank ends with the codebook a single process gets on the concatenated batch
+    vq, cb = make(0)
+    assert cb.use_ddp
+    with torch.no_grad():
+        q, ind, loss = vq(x_all[rank][None])
+    st = O.CodebookState(c0.clone(), c0.clone(), torch.ones(1, K))
+    _, ind_all, _, _ = O.vq_forward(st, x_all.reshape(1, -1, d), O.VQOpts(codebook=O.CodebookOpts(threshold_ema_dead_code=0)))
+    res["ind"] = torch.equal(ind[0], ind_all[0, rank * n_per:(rank + 1) * n_per])
+    res["cs"] = torch.equal(cb.cluster_size, st.cluster_size)
+    res["emb"] = float((cb.embeddings - st.embeddings).abs().max() / st.embeddings.abs().max()) < 1e-6
+    res["same0"] = replicas_identical(cb)
+    # which codes die in cases 2 and 3: the same step without expiry, from the same start
+    twin, cbt = make(0, cs0=0.5)
+    with torch.no_grad():
+        twin(x_all[rank][None])
+    dead = cbt.cluster_size[0] < 2
+    # 2. expiry, replacements sampled from the union of the ranks' batches (distributed_replace_codes=True)
+    vq, cb = make(2)
+    torch.manual_seed(11)
+    with torch.no_grad():
+        vq(x_all[rank][None])
+    replaced = dead
+    res["reset2"] = bool((cb.cluster_size[0][dead] == 2.0).all()) and \
+        torch.equal(cb.embeddings[0][~dead], cbt.embeddings[0][~dead])
+    res["n_replaced"] = int(replaced.sum())
+    res["same2"] = replicas_identical(cb)
+    union = x_all.reshape(-1, d)
+    res["member2"] = bool((cb.embeddings[0][replaced][:, None, :] == union[None]).all(-1).any(-1).all())
+    # 3. distributed_replace_codes=False: locally sampled rows, averaged over the ranks (reference codebooks.py:238-239)
+    vq, cb = make(2, distributed_replace_codes=False)
+    torch.manual_seed(100 + rank)                      # the local draws differ between the ranks
+    with torch.no_grad():
+        vq(x_all[rank][None])
+    replaced = dead
+    res["same3"] = replicas_identical(cb)
+    res["n_replaced3"] = int(replaced.sum())
+    rows = cb.embeddings[0][replaced]
+    res["member3"] = bool((rows[:, None, :] == union[None]).all(-1).any(-1).any())     # means of two rows: not rows
+    halves = (x_all[0][:, None, :] + x_all[1][None, :, :]) / 2                        # all pair means (world = 2)
+    res["pairmean3"] = bool(((rows[:, None, None, :] - halves[None]).abs().amax(-1) < 1e-6).flatten(1).any(-1).all())
+    # 4. kmeans init under data parallel (sync'd): identical centroids on every rank
+    torch.manual_seed(0)
+    vqk = VectorQuantize(dim=d, codebook_params=CodebookParams(dim=d, codebook_size=12, threshold_ema_dead_code=0,
+                                                               initialization_by_kmeans=True,
+                                                               kmeans_params=KmeansParameters()),
+                         sync_codebook=True).train()
+    torch.manual_seed(5)
+    with torch.no_grad():
+        vqk(x_all[rank][None])
+    res["same_kmeans"] = replicas_identical(vqk._codebook) and bool(vqk._codebook.is_initialized)
+    if rank == 0:
+        torch.save(res, out)
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_data_parallel_orchestration(tmp_path):
+    out = str(tmp_path / "dp.pt")
+    mp.spawn(_dp_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    res = torch.load(out)
+    assert res["ind"] and res["cs"] and res["emb"] and res["same0"], res
+    assert res["n_replaced"] > 0 and res["same2"] and res["member2"] and res["reset2"], res
+    assert res["n_replaced3"] > 0 and res["same3"] and not res["member3"] and res["pairmean3"], res
+    assert res["same_kmeans"], res

@@ -109,6 +109,12 @@ def require_cuda(t: torch.Tensor, name: str) -> None:
         raise RuntimeError(f"vqb200: `{name}` must be contiguous")
 
 
+def require_device(x: torch.Tensor) -> None:
+    if not x.is_cuda:
+        raise RuntimeError(f"vqb200.Codebook: input must be on a CUDA device (got {x.device}); "
+                           "there is no CPU implementation")
+
+
 def aligned(t: torch.Tensor) -> torch.Tensor:
     """Contiguous and 16-byte aligned (the kernels use 128-bit loads); copies only when needed."""
     if not t.is_contiguous() or t.data_ptr() % 16:

@@ -226,9 +226,7 @@ class Codebook(nn.Module):
         commit scalar | None).  `keep_dense`: leave in `self.dense_ctx` what the consumers of the dense similarities
         (cross-entropy to indices, CE commitment, diversity loss) need: the (H,N,d) latents the search saw and the
         codebook as it was BEFORE this forward's EMA step (reference codebooks.py:386 runs before :425)."""
-        if not x.is_cuda:
-            raise RuntimeError(f"vqb200.Codebook: input must be on a CUDA device (got {x.device}); "
-                               "there is no CPU implementation")
+        _lib.require_device(x)        # raises for a CPU tensor: there is no CPU implementation
         flat, lead = self._flatten(x)
         H, N, d = flat.shape
         if H != self.num_codebooks or d != self.embeddings.shape[-1]:
