@@ -40,6 +40,13 @@ def gather_st_loss(x, embeddings, idx, mask_u8, training, want_loss):
     return q, loss
 
 
+def st_commit_backward(grad_q, g, x, embeddings, idx, mask_u8):
+    H, N, d = x.shape
+    c = torch.stack([embeddings[h][idx[h]] for h in range(H)], 0)
+    keep = torch.ones(N, dtype=torch.bool) if mask_u8 is None else mask_u8.bool()
+    return grad_q + g[0] * (x.float() - c) * keep[None, :, None]
+
+
 def ema_reduce(x, idx, mask_u8, K, bound_ws=None):
     H, N, d = x.shape
     onehot = F.one_hot(idx, K).float()
@@ -71,8 +78,8 @@ def expire_scatter(x_rows, sample_rows, threshold, reset, weights_l2norm, cluste
 
 def install(ops, lib):
     """Replace the wrappers on the `vqb200.ops` module object and the device guard of `vqb200._lib`."""
-    for name in ("prepare_codebook", "search", "l2norm_rows", "gather_st_loss", "ema_reduce", "ema_apply",
-                 "expire_scatter"):
+    for name in ("prepare_codebook", "search", "l2norm_rows", "gather_st_loss", "st_commit_backward", "ema_reduce",
+                 "ema_apply", "expire_scatter"):
         setattr(ops, name, globals()[name])
     ops.l2norm_prepare_supported = lambda d: False
     ops.quantize_ema_supported = lambda d: False

@@ -18,9 +18,9 @@ def _cpu_draw(num_rows, m, device):
 @pytest.fixture()
 def cpu_ops(monkeypatch):
     from vqb200 import _lib, codebook, ops
-    saved = {n: getattr(ops, n) for n in ("prepare_codebook", "search", "l2norm_rows", "gather_st_loss", "ema_reduce",
-                                          "ema_apply", "expire_scatter", "l2norm_prepare_supported",
-                                          "quantize_ema_supported")}
+    saved = {n: getattr(ops, n) for n in ("prepare_codebook", "search", "l2norm_rows", "gather_st_loss",
+                                          "st_commit_backward", "ema_reduce", "ema_apply", "expire_scatter",
+                                          "l2norm_prepare_supported", "quantize_ema_supported")}
     saved_guard = _lib.require_device
     cpu_kernels.install(ops, _lib)
     monkeypatch.setattr(codebook.Codebook, "_draw_rows", staticmethod(_cpu_draw))
@@ -28,6 +28,120 @@ def cpu_ops(monkeypatch):
     for n, f in saved.items():
         setattr(ops, n, f)
     _lib.require_device = saved_guard
+
+
+@pytest.fixture()
+def cpu_dense_ops(cpu_ops, monkeypatch):
+    """... plus the dense-similarity entry points as their plain-torch statements (tests/dense_ref.py)."""
+    import dense_ref as R
+    from vqb200 import ops
+    f = lambda t: t.detach().float()  # noqa: E731
+    monkeypatch.setattr(ops, "dense_row_norms", lambda t: (f(t) * f(t)).sum(-1))
+    monkeypatch.setattr(ops, "dense_rowstats", lambda x, xn2, e, cn2, cos, a, t: R.rowstats(f(x), e, cos, a, t))
+    monkeypatch.setattr(ops, "dense_avgprob", lambda x, xn2, e, cn2, cos, a, lse, n: R.avgprob(f(x), e, cos, a, lse, n))
+    monkeypatch.setattr(ops, "dense_rowdot",
+                        lambda x, xn2, e, cn2, cos, a, lse, tab, n: R.rowdot(f(x), e, cos, a, lse, tab, n))
+    monkeypatch.setattr(ops, "dense_backward",
+                        lambda x, xn2, ed, cn2, ec, cos, a, lse, coef, target=None, table=None, rdot=None, n_pos=1:
+                        R.backward(f(x), ed, ec, cos, a, lse, coef, target, table, rdot, n_pos))
+    monkeypatch.setattr(ops, "dense_backward_codes",
+                        lambda x, xn2, e, cn2, cos, a, lse, coef, target=None, table=None, rdot=None, n_pos=1:
+                        R.backward_codes(f(x), e.detach(), cos, a, lse, coef, target, table, rdot, n_pos))
+
+
+@pytest.mark.parametrize("name", gu.grad_fixture_names())
+def test_orchestration_input_gradient_matches_reference_fixture(name, cpu_ops):
+    """The autograd wiring of the real `_run` (`_QuantizeST`, the pre-update codebook snapshot, `_L2NormRows`, the
+    ResidualVQ loop) against the gradients recorded from the live reference on the EMA path."""
+    from test_gpu_parity import build_module, load_state
+    fx = gu.load_grad(name)
+    cfg = fx["cfg"]
+    mod, books = build_module(cfg)
+    with torch.no_grad():
+        load_state(books, fx)
+    mod.train()
+    x = fx["x"].clone().requires_grad_(True)
+    q, ind, loss = mod(x, mask=fx["mask"])
+    ((q * fx["w"]).sum() + loss.sum() * 1.7).backward()
+    assert torch.equal(ind, fx["indices"])
+    assert gu.rel_err(q.detach(), fx["quantize"]) <= 1e-6
+    assert torch.allclose(loss.detach(), fx["loss"], rtol=1e-5)
+    assert gu.rel_err(x.grad - fx["w"], fx["grad_x"] - fx["w"]) <= 1e-3
+    assert gu.rel_err(x.grad, fx["grad_x"]) <= 1e-6
+    for cb, after in zip(books, fx["after"]):
+        assert torch.equal(cb.cluster_size, after["cluster_size"])
+        assert gu.rel_err(cb.embeddings, after["embeddings"]) <= 1e-5
+
+
+@pytest.mark.parametrize("name", gu.dense_fixture_names())
+def test_orchestration_dense_losses_match_reference_fixture(name, cpu_dense_ops):
+    """The dense-similarity losses through the REAL `_run` (keep_dense context, pre-update snapshot shared with the
+    commitment term) -- tests/test_dense_host_cpu.py covers vq.py with `_run` replaced."""
+    from test_dense_host_cpu import build_module, load_state
+    fx = gu.load_dense(name)
+    cfg = fx["cfg"]
+    vq = build_module(cfg)
+    vq.train(cfg["training"])
+    load_state(vq, fx)
+    x = fx["x"].clone().requires_grad_(True)
+    if cfg["kind"] == "indices":
+        q, ce = vq(x, indices=fx["targets"])
+        (q.sum() * 0.01 + ce * 1.3 if cfg["training"] else ce * 1.3).backward()
+        assert torch.allclose(ce.detach(), fx["ce"], rtol=1e-6)
+    else:
+        q, ind, loss, bd = vq(x, mask=fx["mask"], return_loss_breakdown=True)
+        ((q * fx["w"]).sum() + loss.sum() * 1.7).backward()
+        assert torch.equal(ind, fx["indices"])
+        assert torch.allclose(loss.detach(), fx["loss"], rtol=1e-6, atol=1e-7)
+        assert torch.allclose(bd.commitment.detach(), fx["commitment"], rtol=1e-6)
+        assert torch.allclose(bd.codebook_diversity.detach(), fx["codebook_diversity"], rtol=1e-6)
+    assert gu.rel_err(q.detach(), fx["quantize"]) <= 1e-6
+    assert gu.rel_err(x.grad, fx["grad_x"]) <= 2e-6
+    assert torch.equal(vq._codebook.cluster_size, fx["after"]["cluster_size"])
+    assert gu.rel_err(vq._codebook.embeddings, fx["after"]["embeddings"]) <= 1e-6
+
+
+LEARNABLE = ["learnable_plain", "learnable_masked_v", "inplace_sgd", "inplace_sgd_masked", "learnable_ce_commit",
+             "learnable_ce_commit_dot", "learnable_diversity", "learnable_ce_indices"]
+
+
+@pytest.mark.parametrize("name", LEARNABLE)
+def test_orchestration_learnable_codebook_matches_reference_fixture(name, cpu_dense_ops):
+    """Learnable codebook through the real `_run`: codebook gradients of the commitment loss (segmented sums), of the
+    dense losses, sync_update_v, the in-place optimizer step."""
+    import os
+    from vqb200 import CodebookParams, VectorQuantize
+    fx = torch.load(os.path.join(gu.GOLDEN_DIR, "learnable", name + ".pt"), weights_only=False)
+    cfg = fx["cfg"]
+    cp = CodebookParams(dim=cfg["dim"], codebook_size=cfg["K"], learnable_codebook=True, ema_update=False,
+                        threshold_ema_dead_code=0, use_cosine_sim=cfg.get("cosine", False))
+    extra = {}
+    if cfg.get("ce"):
+        extra["commitment_use_cross_entropy_loss"] = True
+    if cfg.get("dw"):
+        extra.update(codebook_diversity_loss_weight=cfg["dw"], codebook_diversity_temperature=cfg["temp"])
+    if "lr" in cfg:
+        extra["in_place_codebook_optimizer"] = lambda p: torch.optim.SGD(p, lr=cfg["lr"])
+    vq = VectorQuantize(dim=cfg["dim"], codebook_params=cp, commitment_weight=cfg["cw"], sync_update_v=cfg["v"],
+                        sync_codebook=False, **extra).train()
+    with torch.no_grad():
+        vq._codebook.embeddings.copy_(fx["init_embeddings"])
+    x = fx["x"].clone().requires_grad_(True)
+    if cfg.get("indices"):
+        q, ce = vq(x, indices=fx["targets"])
+        (q.sum() * 0.01 + ce * 1.3).backward()
+        assert torch.allclose(ce.detach(), fx["ce"], rtol=1e-6)
+    else:
+        q, ind, loss, bd = vq(x, mask=fx["mask"], return_loss_breakdown=True)
+        (q * fx["w"]).sum().add(loss.sum() * 1.7).backward()
+        assert torch.equal(ind, fx["indices"])
+        assert torch.allclose(loss.detach(), fx["loss"], rtol=1e-6)
+        if "lr" in cfg:
+            assert torch.allclose(bd.inplace_optimize, fx["inplace_optimize"], rtol=1e-6)
+            assert gu.rel_err(vq._codebook.embeddings.detach(), fx["after_embeddings"]) <= 1e-6
+    assert gu.rel_err(q.detach(), fx["quantize"]) <= 1e-6
+    assert gu.rel_err(x.grad, fx["grad_x"]) <= 2e-6
+    assert gu.rel_err(vq._codebook.embeddings.grad, fx["grad_embeddings"]) <= 2e-6
 
 
 @pytest.mark.parametrize("name", gu.fixture_names())

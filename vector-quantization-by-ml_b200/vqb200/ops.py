@@ -198,6 +198,18 @@ def quantize_ema(x: torch.Tensor, embeddings: torch.Tensor, idx: torch.Tensor, t
     return q, loss, stats
 
 
+def st_commit_backward(grad_q: torch.Tensor, g: torch.Tensor, x: torch.Tensor, embeddings: torch.Tensor,
+                       idx: torch.Tensor, mask_u8: Optional[torch.Tensor]) -> torch.Tensor:
+    """grad_x (H,N,d) fp32 = grad_q + g[0] * (x - C[idx]) on the rows with mask != 0, grad_q on the others."""
+    H, N, d = x.shape
+    K = embeddings.shape[1]
+    gx = torch.empty((H, N, d), dtype=torch.float32, device=x.device)
+    L.check(L.lib().vqb_st_commit_backward(L.ptr(grad_q), L.ptr(g), L.ptr(x), L.dtype_code(x), L.ptr(embeddings),
+                                           L.ptr(idx), L.ptr(mask_u8), 1.0, L.ptr(gx), H, N, K, d,
+                                           L.stream_ptr(x.device)), "vqb_st_commit_backward")
+    return gx
+
+
 class _QuantizeST(torch.autograd.Function):
     """Training-mode quantize: returns (x + (c - x).detach(), mse(c.detach(), x), stats | None).
 
@@ -243,10 +255,7 @@ class _QuantizeST(torch.autograd.Function):
             return (grad_q.to(x.dtype),) + none
         # device scalar: grad_commit * 2 / (rows_used * d)   (no host sync)
         g = (grad_commit.float() * (2.0 / d) / loss[1]).reshape(1).contiguous()
-        gx = torch.empty((H, N, d), dtype=torch.float32, device=x.device)
-        L.check(L.lib().vqb_st_commit_backward(L.ptr(grad_q), L.ptr(g), L.ptr(x), L.dtype_code(x), L.ptr(embeddings),
-                                               L.ptr(idx), L.ptr(mask_u8) if ctx.has_mask else 0, 1.0, L.ptr(gx),
-                                               H, N, K, d, L.stream_ptr(x.device)), "vqb_st_commit_backward")
+        gx = st_commit_backward(grad_q, g, x, embeddings, idx, mask_u8 if ctx.has_mask else None)
         return (gx.to(x.dtype),) + none
 
 
