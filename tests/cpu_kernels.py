@@ -44,7 +44,7 @@ def st_commit_backward(grad_q, g, x, embeddings, idx, mask_u8):
     H, N, d = x.shape
     c = torch.stack([embeddings[h][idx[h]] for h in range(H)], 0)
     keep = torch.ones(N, dtype=torch.bool) if mask_u8 is None else mask_u8.bool()
-    return grad_q + g[0] * (x.float() - c) * keep[None, :, None]
+    return torch.where(keep[None, :, None], grad_q + g[0] * (x.float() - c), grad_q)     # masked rows: grad_q only
 
 
 def ema_reduce(x, idx, mask_u8, K, bound_ws=None):

@@ -172,3 +172,12 @@ def test_device_guard_is_back_after_the_stand_ins():
     vq = VectorQuantize(dim=8, codebook_params=CodebookParams(dim=8, codebook_size=4))
     with pytest.raises(RuntimeError, match="CUDA"):
         vq(torch.randn(1, 3, 8))
+
+
+@pytest.mark.parametrize("seed", list(range(40)))
+def test_orchestration_equals_restatement_on_random_options(seed, cpu_dense_ops):
+    """The seeded random option combinations of tests/test_random_configs_cpu.py through the REAL `_run`."""
+    import test_random_configs_cpu as T
+    from vqb200 import CodebookParams, VectorQuantize
+    cfg = T.make_case(seed)
+    T.compare(T.run_module(cfg, VectorQuantize, CodebookParams), T.run_oracle(cfg), exact=False, cfg=cfg)
