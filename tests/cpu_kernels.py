@@ -76,10 +76,35 @@ def expire_scatter(x_rows, sample_rows, threshold, reset, weights_l2norm, cluste
     embed_avg[dead] = picked * reset
 
 
+def minkey_pack(score, idx):
+    """(orderable fp32 score << 32) | index as int64: smaller score first, lowest index on ties (vqb_minkey_pack)."""
+    u = score.contiguous().view(torch.int32).to(torch.int64) & 0xFFFFFFFF
+    neg = (u >> 31) == 1
+    u = torch.where(neg, (~u) & 0xFFFFFFFF, u | 0x80000000)
+    u = u ^ 0x80000000                                   # keep the sign bit of the int64 key clear
+    key = (u << 32) | (idx & 0xFFFFFFFF)
+    return key - ((key >> 63) << 64)
+
+
+def minkey_unpack(keys, want_score=False):
+    return keys & 0xFFFFFFFF, None
+
+
+def ema_apply_sharded(stats, cluster_size, embed_avg, embeddings, weight, eps, weights_l2norm, k_total, all_reduce):
+    cluster_size.lerp_(stats[..., -1], weight)
+    totals = cluster_size.sum(-1)
+    all_reduce(totals)                                   # sum(cluster_size) over the shards
+    embed_avg.lerp_(stats[..., :-1], weight)
+    total = totals[..., None]
+    smoothed = (cluster_size + eps) / (total + k_total * eps) * total
+    new = embed_avg / smoothed[..., None]
+    embeddings.copy_(F.normalize(new, dim=-1) if weights_l2norm else new)
+
+
 def install(ops, lib):
     """Replace the wrappers on the `vqb200.ops` module object and the device guard of `vqb200._lib`."""
     for name in ("prepare_codebook", "search", "l2norm_rows", "gather_st_loss", "st_commit_backward", "ema_reduce",
-                 "ema_apply", "expire_scatter"):
+                 "ema_apply", "expire_scatter", "minkey_pack", "minkey_unpack", "ema_apply_sharded"):
         setattr(ops, name, globals()[name])
     ops.l2norm_prepare_supported = lambda d: False
     ops.quantize_ema_supported = lambda d: False

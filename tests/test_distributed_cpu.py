@@ -182,6 +182,26 @@ def _dp_worker(rank, world, port, out):
     with torch.no_grad():
         vqk(x_all[rank][None])
     res["same_kmeans"] = replicas_identical(vqk._codebook) and bool(vqk._codebook.is_initialized)
+    # 5. sharded codebook (rows split over the ranks, cross-rank (score, index) min-key merge): indices equal the
+    #    un-sharded search, every shard's EMA result equals the matching rows of the un-sharded update
+    from vqb200 import ShardedCodebook
+    Ks, Ns = 64, 300
+    gs = torch.Generator().manual_seed(9)
+    xs = torch.randn(Ns, d, generator=gs)
+    full = torch.randn(Ks, d, generator=gs) * 0.5
+    full[40] = full[7]                                   # a duplicated code across the two shards: lowest index wins
+    sh = ShardedCodebook(d, Ks)
+    sh.load_full_codebook(full)
+    sh.train()
+    qs, gidx, commit = sh(xs)
+    st5 = O.CodebookState(full[None].clone(), full[None].clone(), torch.ones(1, Ks))
+    q5, i5, l5, _ = O.vq_forward(st5, xs[None], O.VQOpts(codebook=O.CodebookOpts(threshold_ema_dead_code=0)))
+    sl = slice(sh.offset, sh.offset + sh.shard_size)
+    res["sh_idx"] = torch.equal(gidx, i5[0]) and bool((gidx != 40).all())
+    res["sh_q"] = torch.equal(qs, q5[0]) and bool(torch.allclose(commit, l5[0], rtol=1e-6))
+    res["sh_cs"] = torch.equal(sh.cluster_size[0], st5.cluster_size[0, sl])
+    res["sh_emb"] = float((sh.embeddings[0] - st5.embeddings[0, sl]).abs().max()) < 1e-5 and \
+        float((sh.embed_avg[0] - st5.embed_avg[0, sl]).abs().max()) < 1e-5
     if rank == 0:
         torch.save(res, out)
     dist.destroy_process_group()
@@ -195,3 +215,4 @@ def test_two_rank_gloo_data_parallel_orchestration(tmp_path):
     assert res["n_replaced"] > 0 and res["same2"] and res["member2"] and res["reset2"], res
     assert res["n_replaced3"] > 0 and res["same3"] and not res["member3"] and res["pairmean3"], res
     assert res["same_kmeans"], res
+    assert res["sh_idx"] and res["sh_q"] and res["sh_cs"] and res["sh_emb"], res
