@@ -76,6 +76,32 @@ def expire_scatter(x_rows, sample_rows, threshold, reset, weights_l2norm, cluste
     embed_avg[dead] = picked * reset
 
 
+def rvq_level(residual, residual_next, embeddings, idx, mask_u8, training, first_level, quantized_out, next_cache,
+              q_out=None):
+    """One ResidualVQ level on (N,d) fp32 residuals (vqb_rvq_level): gather + straight-through + loss +
+    residual_next = residual - q + quantized_out (+)= q; masked-out rows pass the residual through (q = residual)."""
+    r = residual
+    c = embeddings[idx]
+    q = r + (c - r) if training else c
+    keep = torch.ones(r.shape[0], dtype=torch.bool) if mask_u8 is None else mask_u8.bool()
+    q = torch.where(keep[:, None], q, r)
+    residual_next.copy_(r - q)
+    quantized_out.copy_(0.0 + q if first_level else quantized_out + q)
+    if q_out is not None:
+        q_out.copy_(q)
+    rows = int(keep.sum())
+    err = ((c - r) ** 2)[keep]
+    return torch.stack([err.mean() if rows else torch.tensor(float("nan")), torch.tensor(float(rows))])
+
+
+def rvq_level_ema(residual, residual_next, embeddings, idx, training, first_level, quantized_out, next_cache,
+                  bound_ws=None, q_out=None):
+    stats = ema_reduce(residual[None], idx[None], None, embeddings.shape[0])
+    loss = rvq_level(residual, residual_next, embeddings, idx, None, training, first_level, quantized_out, next_cache,
+                     q_out)
+    return loss, stats
+
+
 def minkey_pack(score, idx):
     """(orderable fp32 score << 32) | index as int64: smaller score first, lowest index on ties (vqb_minkey_pack)."""
     u = score.contiguous().view(torch.int32).to(torch.int64) & 0xFFFFFFFF
@@ -104,8 +130,9 @@ def ema_apply_sharded(stats, cluster_size, embed_avg, embeddings, weight, eps, w
 def install(ops, lib):
     """Replace the wrappers on the `vqb200.ops` module object and the device guard of `vqb200._lib`."""
     for name in ("prepare_codebook", "search", "l2norm_rows", "gather_st_loss", "st_commit_backward", "ema_reduce",
-                 "ema_apply", "expire_scatter", "minkey_pack", "minkey_unpack", "ema_apply_sharded"):
+                 "ema_apply", "expire_scatter", "minkey_pack", "minkey_unpack", "ema_apply_sharded", "rvq_level", "rvq_level_ema"):
         setattr(ops, name, globals()[name])
     ops.l2norm_prepare_supported = lambda d: False
     ops.quantize_ema_supported = lambda d: False
+    ops.rvq_level_ema_supported = lambda d: False
     lib.require_device = lambda x: None

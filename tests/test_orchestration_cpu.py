@@ -20,7 +20,9 @@ def cpu_ops(monkeypatch):
     from vqb200 import _lib, codebook, ops
     saved = {n: getattr(ops, n) for n in ("prepare_codebook", "search", "l2norm_rows", "gather_st_loss",
                                           "st_commit_backward", "ema_reduce", "ema_apply", "expire_scatter",
-                                          "l2norm_prepare_supported", "quantize_ema_supported")}
+                                          "l2norm_prepare_supported", "quantize_ema_supported", "rvq_level",
+                                          "rvq_level_ema", "rvq_level_ema_supported", "minkey_pack", "minkey_unpack",
+                                          "ema_apply_sharded")}
     saved_guard = _lib.require_device
     cpu_kernels.install(ops, _lib)
     monkeypatch.setattr(codebook.Codebook, "_draw_rows", staticmethod(_cpu_draw))
@@ -181,3 +183,44 @@ def test_orchestration_equals_restatement_on_random_options(seed, cpu_dense_ops)
     from vqb200 import CodebookParams, VectorQuantize
     cfg = T.make_case(seed)
     T.compare(T.run_module(cfg, VectorQuantize, CodebookParams), T.run_oracle(cfg), exact=False, cfg=cfg)
+
+
+@pytest.mark.parametrize("fused_ema", [False, True])
+@pytest.mark.parametrize("name", [n for n in gu.fixture_names() if n.startswith("rvq")])
+def test_fused_rvq_level_loop_matches_reference_fixture(name, fused_ema, cpu_ops, monkeypatch):
+    """`ResidualVQ._forward_fused` (one pass per level, operands of the next level prepared on the way, the dead-code
+    checks of all levels answered by one sync and replayed in level order) against the reference fixtures, both with
+    the level step and the EMA sums in one call (`rvq_level_ema`) and as separate calls."""
+    from test_gpu_parity import build_module, load_state
+    from vqb200 import ops, rvq
+    monkeypatch.setattr(ops, "rvq_level_ema_supported", lambda d: fused_ema)
+    real_can_fuse = rvq.ResidualVQ._can_fuse
+    calls = {"fused": 0}
+
+    class _OnDevice:          # what `_can_fuse` asks of its input, answered as for a CUDA tensor
+        def __init__(self, t):
+            self.is_cuda, self.ndim, self.requires_grad = True, t.ndim, t.requires_grad
+
+    def can_fuse(self, x, dropout_active):
+        ok = real_can_fuse(self, _OnDevice(x), dropout_active)
+        calls["fused"] += int(ok)
+        return ok
+
+    monkeypatch.setattr(rvq.ResidualVQ, "_can_fuse", can_fuse)
+    fx = gu.load(name)
+    cfg = fx["cfg"]
+    mod, books = build_module(cfg)
+    with torch.no_grad():
+        load_state(books, fx)
+    mod.train(cfg.get("training", True))
+    for s, step in enumerate(fx["steps"]):
+        torch.manual_seed(fx["rng_seed"] + s)
+        with torch.no_grad():
+            q, ind, loss = mod(fx["x"] + 0.01 * s, mask=fx["mask"])
+        assert torch.equal(ind, step["indices"]), f"{name} step {s}: indices"
+        assert gu.rel_err(q, step["quantize"]) <= 1e-6
+        assert torch.allclose(loss, step["loss"], rtol=1e-5, atol=1e-12)
+        for cb, after in zip(books, step["after"]):
+            assert torch.equal(cb.cluster_size, after["cluster_size"])
+            assert gu.rel_err(cb.embeddings, after["embeddings"]) <= 1e-5
+    assert calls["fused"] == len(fx["steps"])          # the fused loop is what ran
