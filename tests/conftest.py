@@ -13,6 +13,8 @@ for p in (ROOT, PKG, os.path.dirname(os.path.abspath(__file__))):
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    config.addinivalue_line("markers", "slow_oracle: full-size parity against the row-chunked CPU oracle (tens of "
+                                       "seconds of host CPU per step)")
 
 
 def pytest_collection_modifyitems(config, items):

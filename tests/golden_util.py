@@ -84,3 +84,40 @@ def build_from_description(cfg):
     import vqb200
     return getattr(vqb200, cfg["cls"])(codebook_params=vqb200.CodebookParams(**cfg["cp"]), sync_codebook=False,
                                        **cfg["kw"])
+
+
+def rvq_learnable_fixture_names():
+    return sorted(os.path.splitext(os.path.basename(p))[0]
+                  for p in glob.glob(os.path.join(GOLDEN_DIR, "rvq_learnable", "*.pt")))
+
+
+def check_rvq_learnable(name, device):
+    """ResidualVQ over learnable codebooks (tests/golden/make_golden_rvq_learnable.py): outputs, per-level losses and
+    the gradient every level's codebook Parameter receives -- also when the input carries no gradient."""
+    from vqb200 import CodebookParams, ResidualVQ
+    fx = torch.load(os.path.join(GOLDEN_DIR, "rvq_learnable", name + ".pt"), weights_only=False)
+    cfg = fx["cfg"]
+    cp = CodebookParams(dim=cfg["dim"], codebook_size=cfg["K"], learnable_codebook=True, ema_update=False,
+                        threshold_ema_dead_code=0)
+    rvq = ResidualVQ(dim=cfg["dim"], num_quantizers=cfg["Q"], codebook_params=cp, commitment_weight=cfg["cw"],
+                     sync_codebook=False).to(device).train()
+    with torch.no_grad():
+        for layer, e in zip(rvq.layers, fx["init_embeddings"]):
+            layer._codebook.embeddings.copy_(e)
+            layer._codebook.invalidate_cache()
+    x = fx["x"].to(device)
+    if cfg["x_grad"]:
+        x.requires_grad_(True)
+    mask = fx["mask"].to(device) if fx["mask"] is not None else None
+    q, ind, losses = rvq(x, mask=mask)
+    scale = torch.arange(1, cfg["Q"] + 1, device=device)
+    ((q * fx["w"].to(device)).sum() * (1.0 if cfg["x_grad"] else 0.0) + (losses * scale).sum()).backward()
+    assert torch.equal(ind.cpu(), fx["indices"])
+    assert rel_err(q.detach().cpu(), fx["quantize"]) <= 1e-6
+    assert torch.allclose(losses.detach().cpu(), fx["losses"], rtol=1e-5)
+    for li, (layer, ge) in enumerate(zip(rvq.layers, fx["grad_embeddings"])):
+        got = layer._codebook.embeddings.grad
+        assert got is not None, f"{name}: level {li} codebook received no gradient"
+        assert rel_err(got.cpu(), ge) <= 1e-5, f"{name}: level {li} codebook gradient"
+    if cfg["x_grad"]:
+        assert rel_err(x.grad.cpu(), fx["grad_x"]) <= 1e-5

@@ -24,30 +24,27 @@ def _sample_check(x, c, idx, cos, n_sample=2048, seed=0):
     got = idx[0, rows.to(idx.device)].cpu()
     bad = (got != ref) & (gap >= 1e-6)
     if bool(bad.any()):
-        # The oracle is the reference's fp32 recipe: its own rounding noise on |x|^2 + |c|^2 - 2 x.c (d + 2 fp32
-        # additions at magnitude ~|x|^2) reaches ~1e-6 relative on the distance in the tail and depends on the host
-        # BLAS blocking (CPU model, thread count).  A row just outside the 1e-6 window may therefore be mis-ordered
-        # by the ORACLE.  Arbitrate with fp64 ground truth: a differing row is accepted only if the CUDA index is the
-        # fp64 argmin and the fp64 gap is still a near-tie (< 1e-5 relative); anything else fails with details.
+        # STRICT (north star): a row may differ from the reference only inside the reference's own fp32 1e-6 window.
+        # Round 1 accepted rows just outside it when the CUDA index was the fp64 argmin, on the hypothesis that the
+        # oracle's own fp32 noise mis-orders them; tools/oracle_noise.py measured that noise on the CPU
+        # (profiles/r02_oracle_noise.jsonl: at every named shape, under 6 thread / MKL-kernel settings, each row where
+        # the oracle differs from fp64 has an oracle gap < 1e-6 and misses the true winner by <= 1.6e-7) -- the
+        # hypothesis does not hold, so there is no arbitration any more.  Everything needed to diagnose is printed.
         br = rows[bad]
         xs64, c64 = x[0, br.to(x.device)].double().cpu(), c[0].double().cpu()
         s64 = xs64 @ c64.T if cos else -torch.cdist(xs64, c64)
         arg64 = s64.argmax(-1)
         t2 = s64.topk(2, -1).values
         gap64 = (t2[:, 0] - t2[:, 1]).abs() / t2[:, 0].abs().clamp_min(1e-30)
-        wrong = (got[bad] != arg64) | (gap64 >= 1e-5)
-        if bool(wrong.any()):
-            from vqb200 import ops
-            ex, _, _ = ops.search(x[:, br.to(x.device)].contiguous(), c, None, cos, force_exact=True)
-            again, _, ws = ops.search(x, c, ops.prepare_codebook(c, cos), cos)
-            detail = [(int(r), int(got[bad][i]), int(ref[bad][i]), int(arg64[i]), int(ex[0, i]), int(again[0, int(r)]),
-                       float(gap[bad][i]), float(gap64[i])) for i, r in enumerate(br[:8])]
-            raise AssertionError(f"{int(wrong.sum())} sampled rows differ from the oracle AND from fp64 ground truth; "
-                                 f"(row, got, oracle, fp64 argmin, exact scan, second search, oracle gap, fp64 gap): "
-                                 f"{detail}; whole batch vs second search: {int((again != idx).sum())} rows differ; "
-                                 f"stats {ops.search_stats(ws)}")
-        print(f"note: {int(bad.sum())} sampled rows where the fp32 oracle mis-orders a near-tie just outside the "
-              f"1e-6 window (CUDA index == fp64 argmin, fp64 gaps {[float(v) for v in gap64]})")
+        from vqb200 import ops
+        ex, _, _ = ops.search(x[:, br.to(x.device)].contiguous(), c, None, cos, force_exact=True)
+        again, _, ws = ops.search(x, c, ops.prepare_codebook(c, cos), cos)
+        detail = [(int(r), int(got[bad][i]), int(ref[bad][i]), int(arg64[i]), int(ex[0, i]), int(again[0, int(r)]),
+                   float(gap[bad][i]), float(gap64[i])) for i, r in enumerate(br[:8])]
+        raise AssertionError(f"{int(bad.sum())} sampled rows differ from the oracle outside its 1e-6 window; "
+                             f"(row, got, oracle, fp64 argmin, exact scan, second search, oracle gap, fp64 gap): "
+                             f"{detail}; whole batch vs second search: {int((again != idx).sum())} rows differ; "
+                             f"stats {ops.search_stats(ws)}")
     return int((got != ref).sum())
 
 

@@ -174,16 +174,18 @@ def test_search_matches_oracle(H, N, K, d, cos, scale, dtype):
         gap = torch.full(ref.shape, float("inf"))
     bad = (idx.cpu() != ref) & (gap >= 1e-6)
     if bool(bad.any()):
-        # the fp32 oracle's own rounding can mis-order a near-tie just outside the window (host-BLAS dependent):
-        # accept such a row only if the CUDA index is the fp64 argmin and the fp64 gap is still a near-tie
+        # strict: only rows inside the reference's own fp32 1e-6 window may differ (tools/oracle_noise.py: the oracle's
+        # rounding noise never reaches outside it); print what is needed to diagnose
         hh, nn = bad.nonzero(as_tuple=True)
-        for h_, n_ in zip(hh.tolist(), nn.tolist()):
+        detail = []
+        for h_, n_ in list(zip(hh.tolist(), nn.tolist()))[:8]:
             x64, c64 = x[h_, n_].double(), c[h_].double()
             s64 = c64 @ x64 if cos else -(c64 - x64).pow(2).sum(-1).sqrt()
             t2 = s64.topk(2).values
             g64 = float((t2[0] - t2[1]).abs() / t2[0].abs().clamp_min(1e-30))
-            assert int(idx[h_, n_]) == int(s64.argmax()) and g64 < 1e-5, \
-                f"row ({h_},{n_}): got {int(idx[h_, n_])}, oracle {int(ref[h_, n_])}, fp64 argmin {int(s64.argmax())}, fp64 gap {g64}"
+            detail.append((h_, n_, int(idx[h_, n_]), int(ref[h_, n_]), int(s64.argmax()), float(gap[h_, n_]), g64))
+        raise AssertionError(f"{int(bad.sum())} rows differ from the oracle outside its 1e-6 window; (h, row, got, "
+                             f"oracle, fp64 argmin, oracle gap, fp64 gap): {detail}; stats {stats}")
     # score: distance (euclid) or -similarity (dot) of the winner
     ref_score = -sim.gather(-1, idx.cpu()[..., None])[..., 0]
     assert torch.allclose(score.cpu(), ref_score, rtol=2e-5, atol=2e-5 * float(ref_score.abs().max()) + 1e-7)
@@ -613,3 +615,8 @@ print("MODE OK")
     env = dict(os.environ, VQB_CLUSTER=mode)
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, env=env)
     assert out.returncode == 0 and "MODE OK" in out.stdout, out.stdout[-1500:] + out.stderr[-3000:]
+
+
+@pytest.mark.parametrize("name", gu.rvq_learnable_fixture_names())
+def test_rvq_learnable_codebooks_get_their_gradient(name):
+    gu.check_rvq_learnable(name, _dev())

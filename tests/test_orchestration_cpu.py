@@ -224,3 +224,10 @@ def test_fused_rvq_level_loop_matches_reference_fixture(name, fused_ema, cpu_ops
             assert torch.equal(cb.cluster_size, after["cluster_size"])
             assert gu.rel_err(cb.embeddings, after["embeddings"]) <= 1e-5
     assert calls["fused"] == len(fx["steps"])          # the fused loop is what ran
+
+
+@pytest.mark.parametrize("name", gu.rvq_learnable_fixture_names())
+def test_orchestration_rvq_learnable_codebooks_get_their_gradient(name, cpu_ops):
+    """ResidualVQ over learnable codebooks: the fused (no_grad) level loop must NOT be taken while a codebook Parameter
+    wants a gradient, even if the input carries none (reference vector_quantize_pytorch.py:263-269)."""
+    gu.check_rvq_learnable(name, torch.device("cpu"))

@@ -11,6 +11,24 @@ import torch
 
 from . import _lib as L
 
+
+def _on_device(fn):
+    """Run `fn` with the CUDA device of its first tensor argument current.  The library launches on the stream it is
+    given and creates TMA descriptors / queries attributes on the CURRENT device, so a module living on cuda:1 while
+    the process's current device is cuda:0 must switch for the duration of the call (torch ops do the same)."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        for a in args:
+            if isinstance(a, torch.Tensor):
+                if a.is_cuda and a.device.index != torch.cuda.current_device():
+                    with torch.cuda.device(a.device):
+                        return fn(*args, **kwargs)
+                break
+        return fn(*args, **kwargs)
+    return wrapper
+
 # ---------------------------------------------------------------------------------------------
 # workspaces: caller-owned scratch, one growing buffer per (kind, device, stream)
 # ---------------------------------------------------------------------------------------------
@@ -64,6 +82,7 @@ def _mask_u8(mask: Optional[torch.Tensor], n: int) -> Optional[torch.Tensor]:
 # ---------------------------------------------------------------------------------------------
 # codebook cache + search
 # ---------------------------------------------------------------------------------------------
+@_on_device
 def prepare_codebook(embeddings: torch.Tensor, use_cosine_sim: bool,
                      out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Scaled fp16 copy + norms + rounding bounds of `embeddings` for the tensor-core search."""
@@ -78,6 +97,7 @@ def prepare_codebook(embeddings: torch.Tensor, use_cosine_sim: bool,
     return out
 
 
+@_on_device
 def search(x: torch.Tensor, embeddings: torch.Tensor, cache: Optional[torch.Tensor], use_cosine_sim: bool, *,
            idx_offset: int = 0, want_score: bool = False, latents_prepared: bool = False,
            force_exact: bool = False) -> Tuple[torch.Tensor, Optional[torch.Tensor], torch.Tensor]:
@@ -100,6 +120,7 @@ def search(x: torch.Tensor, embeddings: torch.Tensor, cache: Optional[torch.Tens
     return idx, score, ws
 
 
+@_on_device
 def search_stats(ws: torch.Tensor) -> Dict[str, int]:
     import ctypes as C
     out = (C.c_int64 * 3)()
@@ -107,6 +128,7 @@ def search_stats(ws: torch.Tensor) -> Dict[str, int]:
     return {"reranked_rows": int(out[0]), "rescanned_rows": int(out[1]), "tensor_core_pass": int(out[2])}
 
 
+@_on_device
 def l2norm_rows(x: torch.Tensor) -> torch.Tensor:
     L.require_cuda(x, "x")
     d = x.shape[-1]
@@ -146,6 +168,7 @@ def l2norm_prepare_supported(d: int) -> bool:
     return bool(L.lib().vqb_l2norm_prepare_supported(int(d)))
 
 
+@_on_device
 def l2norm_prepare(x: torch.Tensor, K: int, cache: torch.Tensor) -> torch.Tensor:
     """x (H,N,d) -> x / |x| (fp32) and, in the shared search workspace, everything the next
     `search(out, ..., latents_prepared=True)` with this codebook cache needs."""
@@ -161,6 +184,7 @@ def l2norm_prepare(x: torch.Tensor, K: int, cache: torch.Tensor) -> torch.Tensor
 # ---------------------------------------------------------------------------------------------
 # gather + straight-through + commitment loss (autograd-aware)
 # ---------------------------------------------------------------------------------------------
+@_on_device
 def gather_st_loss(x: torch.Tensor, embeddings: torch.Tensor, idx: torch.Tensor, mask_u8: Optional[torch.Tensor],
                    training: bool, want_loss: bool) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
     """q (H,N,d) fp32 and loss_buf = [mean((c-x)^2), rows_used] (device) or None."""
@@ -181,6 +205,7 @@ def quantize_ema_supported(d: int) -> bool:
     return bool(L.lib().vqb_quantize_ema_supported(int(d)))
 
 
+@_on_device
 def quantize_ema(x: torch.Tensor, embeddings: torch.Tensor, idx: torch.Tensor, training: bool, want_loss: bool,
                  bound_ws: Optional[torch.Tensor] = None):
     """Fused gather/ST/loss + EMA sums (no mask): returns (q (H,N,d) fp32, loss_buf | None, stats (H,K,d+1))."""
@@ -198,6 +223,7 @@ def quantize_ema(x: torch.Tensor, embeddings: torch.Tensor, idx: torch.Tensor, t
     return q, loss, stats
 
 
+@_on_device
 def st_commit_backward(grad_q: torch.Tensor, g: torch.Tensor, x: torch.Tensor, embeddings: torch.Tensor,
                        idx: torch.Tensor, mask_u8: Optional[torch.Tensor]) -> torch.Tensor:
     """grad_x (H,N,d) fp32 = grad_q + g[0] * (x - C[idx]) on the rows with mask != 0, grad_q on the others."""
@@ -292,6 +318,7 @@ def quantize_training(x, embeddings, idx, mask_u8, want_loss, ema: bool = False,
 # ---------------------------------------------------------------------------------------------
 # EMA statistics / refresh / expiry
 # ---------------------------------------------------------------------------------------------
+@_on_device
 def ema_reduce(x: torch.Tensor, idx: torch.Tensor, mask_u8: Optional[torch.Tensor], K: int,
                bound_ws: Optional[torch.Tensor] = None) -> torch.Tensor:
     """stats (H,K,d+1): per-code sums of assigned rows and counts.  Bitwise reproducible."""
@@ -305,6 +332,7 @@ def ema_reduce(x: torch.Tensor, idx: torch.Tensor, mask_u8: Optional[torch.Tenso
     return stats
 
 
+@_on_device
 def ema_apply(stats: torch.Tensor, cluster_size: torch.Tensor, embed_avg: torch.Tensor, embeddings: torch.Tensor,
               weight: float, eps: float, weights_l2norm: bool) -> None:
     H, K, d1 = stats.shape
@@ -318,6 +346,7 @@ def ema_apply(stats: torch.Tensor, cluster_size: torch.Tensor, embed_avg: torch.
                                   L.stream_ptr(dev)), "vqb_ema_apply")
 
 
+@_on_device
 def ema_apply_sharded(stats: torch.Tensor, cluster_size: torch.Tensor, embed_avg: torch.Tensor,
                       embeddings: torch.Tensor, weight: float, eps: float, weights_l2norm: bool, k_total: int,
                       all_reduce) -> None:
@@ -335,6 +364,7 @@ def ema_apply_sharded(stats: torch.Tensor, cluster_size: torch.Tensor, embed_avg
                                        L.ptr(totals), st), "vqb_ema_apply_rows")
 
 
+@_on_device
 def expire_scatter(x_rows: torch.Tensor, sample_rows: torch.Tensor, threshold: float, reset: float,
                    weights_l2norm: bool, cluster_size: torch.Tensor, embed_avg: torch.Tensor,
                    embeddings: torch.Tensor) -> None:
@@ -354,6 +384,7 @@ def expire_scatter(x_rows: torch.Tensor, sample_rows: torch.Tensor, threshold: f
 # ---------------------------------------------------------------------------------------------
 # ResidualVQ level step and sharded-codebook keys
 # ---------------------------------------------------------------------------------------------
+@_on_device
 def rvq_level(residual: torch.Tensor, residual_next: torch.Tensor, embeddings: torch.Tensor, idx: torch.Tensor,
               mask_u8: Optional[torch.Tensor], training: bool, first_level: bool, quantized_out: torch.Tensor,
               next_cache: Optional[torch.Tensor], q_out: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -381,6 +412,7 @@ def rvq_level_ema_supported(d: int) -> bool:
     return bool(L.lib().vqb_rvq_level_ema_supported(int(d)))
 
 
+@_on_device
 def rvq_level_ema(residual: torch.Tensor, residual_next: torch.Tensor, embeddings: torch.Tensor, idx: torch.Tensor,
                   training: bool, first_level: bool, quantized_out: torch.Tensor, next_cache: Optional[torch.Tensor],
                   bound_ws: Optional[torch.Tensor] = None, q_out: Optional[torch.Tensor] = None):
@@ -403,6 +435,7 @@ def rvq_level_ema(residual: torch.Tensor, residual_next: torch.Tensor, embedding
     return loss, stats
 
 
+@_on_device
 def minkey_pack(score: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
     L.require_cuda(score, "score")
     keys = torch.empty(score.numel(), dtype=torch.int64, device=score.device)
@@ -411,6 +444,7 @@ def minkey_pack(score: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
     return keys
 
 
+@_on_device
 def minkey_unpack(keys: torch.Tensor, want_score: bool = False):
     L.require_cuda(keys, "keys")
     idx = torch.empty(keys.numel(), dtype=torch.int64, device=keys.device)
@@ -424,6 +458,7 @@ def minkey_unpack(keys: torch.Tensor, want_score: bool = False):
 # consumers of the dense N x K similarities (cross-entropy to indices, CE commitment, diversity loss):
 # fp32 CUDA-core passes with an online softmax, nothing of size N x K is written (csrc/dense.cu)
 # ---------------------------------------------------------------------------------------------
+@_on_device
 def dense_row_norms(t: torch.Tensor) -> torch.Tensor:
     """|row|^2 of a (..., d) tensor -> (...,) fp32."""
     L.require_cuda(t, "t")
@@ -434,6 +469,7 @@ def dense_row_norms(t: torch.Tensor) -> torch.Tensor:
     return out
 
 
+@_on_device
 def dense_rowstats(x, xn2, emb, cn2, use_cosine_sim: bool, alpha: float, target: Optional[torch.Tensor]):
     """lse (H,N) = log sum_k exp(alpha s_k) and, with `target` (H,N) int64 (-1 = ignore), the score of the target."""
     L.require_cuda(x, "x")
@@ -447,6 +483,7 @@ def dense_rowstats(x, xn2, emb, cn2, use_cosine_sim: bool, alpha: float, target:
     return lse, st
 
 
+@_on_device
 def dense_avgprob(x, xn2, emb, cn2, use_cosine_sim: bool, alpha: float, lse, n_pos: int) -> torch.Tensor:
     """(n_pos, K): softmax(alpha s) averaged over the codebooks and the N / n_pos batch entries of each position."""
     H, N, d = x.shape
@@ -458,6 +495,7 @@ def dense_avgprob(x, xn2, emb, cn2, use_cosine_sim: bool, alpha: float, lse, n_p
     return avg
 
 
+@_on_device
 def dense_rowdot(x, xn2, emb, cn2, use_cosine_sim: bool, alpha: float, lse, table, n_pos: int) -> torch.Tensor:
     """(H,N): sum_k softmax(alpha s)_k * table[row % n_pos, k]."""
     H, N, d = x.shape
@@ -469,6 +507,7 @@ def dense_rowdot(x, xn2, emb, cn2, use_cosine_sim: bool, alpha: float, lse, tabl
     return out
 
 
+@_on_device
 def dense_backward(x, xn2, emb_dist, cn2, emb_comb, use_cosine_sim: bool, alpha: float, lse, coef, target=None,
                    table=None, rdot=None, n_pos: int = 1) -> torch.Tensor:
     """Input gradient (H,N,d) fp32 of a loss on the similarities (see include/vqb.h: vqb_dense_backward)."""
@@ -482,6 +521,7 @@ def dense_backward(x, xn2, emb_dist, cn2, emb_comb, use_cosine_sim: bool, alpha:
     return gx
 
 
+@_on_device
 def dense_backward_codes(x, xn2, emb, cn2, use_cosine_sim: bool, alpha: float, lse, coef, target=None, table=None,
                          rdot=None, n_pos: int = 1) -> torch.Tensor:
     """Codebook gradient (H,K,d) fp32 of a loss on the similarities (learnable codebook): the transposed contraction

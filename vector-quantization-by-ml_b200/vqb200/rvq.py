@@ -80,6 +80,13 @@ class ResidualVQ(nn.Module):
         l0 = self.layers[0]
         if self.training and (l0.commitment_use_cross_entropy_loss or l0.has_codebook_diversity_loss):
             return False        # losses on the dense similarities: the generic per-level loop computes them
+        if l0.in_place_codebook_optimizer is not None:
+            return False        # the optimizer step inside forward (reference vector_quantize_pytorch.py:233-256)
+        if l0._codebook.learnable_codebook and self.training and torch.is_grad_enabled() and \
+                any(l._codebook.embeddings.requires_grad for l in self.layers):
+            # the commitment loss must reach the codebook Parameters (reference :263-269) even when the input carries
+            # no gradient (frozen encoder): the fused loop runs under no_grad
+            return False
         return l0.channel_last and not l0._codebook.input_l2norm and l0.heads == 1
 
     @torch.no_grad()
