@@ -182,26 +182,64 @@ def _dp_worker(rank, world, port, out):
     with torch.no_grad():
         vqk(x_all[rank][None])
     res["same_kmeans"] = replicas_identical(vqk._codebook) and bool(vqk._codebook.is_initialized)
-    # 5. sharded codebook (rows split over the ranks, cross-rank (score, index) min-key merge): indices equal the
-    #    un-sharded search, every shard's EMA result equals the matching rows of the un-sharded update
-    from vqb200 import ShardedCodebook
+    # 5. sharded codebook THROUGH THE MODULE API (Codebook.sharded: rows split over the ranks, cross-rank (score, index)
+    #    min-key merge): indices equal the un-sharded reference path, every shard's EMA + expiry result equals the
+    #    matching rows of the un-sharded update, kmeans init on shards, state_dict round trip with full-size tensors
+    from vqb200 import distributed as D
+    D.SHARD_MIN_CODES = 32
     Ks, Ns = 64, 300
     gs = torch.Generator().manual_seed(9)
-    xs = torch.randn(Ns, d, generator=gs)
+    xs = torch.randn(world, Ns, d, generator=gs)
     full = torch.randn(Ks, d, generator=gs) * 0.5
     full[40] = full[7]                                   # a duplicated code across the two shards: lowest index wins
-    sh = ShardedCodebook(d, Ks)
-    sh.load_full_codebook(full)
-    sh.train()
-    qs, gidx, commit = sh(xs)
-    st5 = O.CodebookState(full[None].clone(), full[None].clone(), torch.ones(1, Ks))
-    q5, i5, l5, _ = O.vq_forward(st5, xs[None], O.VQOpts(codebook=O.CodebookOpts(threshold_ema_dead_code=0)))
-    sl = slice(sh.offset, sh.offset + sh.shard_size)
-    res["sh_idx"] = torch.equal(gidx, i5[0]) and bool((gidx != 40).all())
-    res["sh_q"] = torch.equal(qs, q5[0]) and bool(torch.allclose(commit, l5[0], rtol=1e-6))
-    res["sh_cs"] = torch.equal(sh.cluster_size[0], st5.cluster_size[0, sl])
-    res["sh_emb"] = float((sh.embeddings[0] - st5.embeddings[0, sl]).abs().max()) < 1e-5 and \
-        float((sh.embed_avg[0] - st5.embed_avg[0, sl]).abs().max()) < 1e-5
+    full[50:53] *= 30.0                                  # never chosen: these die and are replaced (expiry on a shard)
+
+    def sharded_vq(thr, mode, **cp):
+        torch.manual_seed(0)
+        vq = VectorQuantize(dim=d, codebook_params=CodebookParams(dim=d, codebook_size=Ks, threshold_ema_dead_code=thr,
+                                                                  **cp), sync_codebook=True).train()
+        vq._codebook.sharded_input = mode
+        return vq, vq._codebook
+
+    for mode in ("replicated", "all_gather"):
+        vq, cb = sharded_vq(2, mode)
+        res[f"sh_is_sharded_{mode}"] = bool(cb.sharded) and cb.embeddings.shape == (1, Ks // world, d)
+        cb.load_full_codebook(full)
+        x_in = xs[0][None] if mode == "replicated" else xs[rank][None]
+        x_ref = xs[0][None] if mode == "replicated" else xs.reshape(1, -1, d)
+        torch.manual_seed(21)
+        with torch.no_grad():
+            qs, gidx, loss = vq(x_in)
+        st5 = O.CodebookState(full[None].clone(), full[None].clone(), torch.ones(1, Ks))
+        torch.manual_seed(21)
+        q5, i5, l5, _ = O.vq_forward(st5, x_ref, O.VQOpts(codebook=O.CodebookOpts(threshold_ema_dead_code=2)))
+        rows = slice(0, Ns) if mode == "replicated" else slice(rank * Ns, (rank + 1) * Ns)
+        sl = slice(cb.shard_offset, cb.shard_offset + cb.shard_size)
+        res[f"sh_idx_{mode}"] = torch.equal(gidx[0], i5[0, rows]) and bool((gidx != 40).all())
+        res[f"sh_q_{mode}"] = torch.equal(qs[0], q5[0, rows])
+        if mode == "replicated":
+            res["sh_loss"] = bool(torch.allclose(loss, l5, rtol=1e-6))
+        res[f"sh_cs_{mode}"] = torch.equal(cb.cluster_size[0], st5.cluster_size[0, sl])
+        res[f"sh_emb_{mode}"] = float((cb.embeddings[0] - st5.embeddings[0, sl]).abs().max()) < 1e-5 and \
+            float((cb.embed_avg[0] - st5.embed_avg[0, sl]).abs().max()) < 1e-5
+        res[f"sh_expired_{mode}"] = int((st5.cluster_size[0] == 2.0).sum())
+        sd = vq.state_dict()
+        res[f"sh_sd_{mode}"] = tuple(sd["_codebook.embeddings"].shape) == (1, Ks, d) and \
+            float((sd["_codebook.embeddings"] - st5.embeddings).abs().max()) < 1e-5
+        vq2, cb2 = sharded_vq(2, mode)
+        vq2.load_state_dict(sd)
+        res[f"sh_load_{mode}"] = torch.equal(cb2.embeddings, cb.embeddings) and torch.equal(cb2.cluster_size, cb.cluster_size)
+    # kmeans init on shards == the reference's kmeans on the un-sharded centroids (rank 0's draw)
+    vqk, cbk = sharded_vq(0, "replicated", initialization_by_kmeans=True, kmeans_params=KmeansParameters())
+    torch.manual_seed(33)
+    with torch.no_grad():
+        _, ik, _ = vqk(xs[0][None])
+    stk = O.CodebookState.fresh(1, Ks, d, kmeans_init=True)
+    torch.manual_seed(33)
+    _, iko, _, _ = O.vq_forward(stk, xs[0][None], O.VQOpts(codebook=O.CodebookOpts(threshold_ema_dead_code=0)))
+    sl = slice(cbk.shard_offset, cbk.shard_offset + cbk.shard_size)
+    res["sh_kmeans"] = torch.equal(ik, iko) and torch.equal(cbk.cluster_size[0], stk.cluster_size[0, sl]) and \
+        float((cbk.embeddings[0] - stk.embeddings[0, sl]).abs().max()) < 1e-5
     if rank == 0:
         torch.save(res, out)
     dist.destroy_process_group()
@@ -215,4 +253,8 @@ def test_two_rank_gloo_data_parallel_orchestration(tmp_path):
     assert res["n_replaced"] > 0 and res["same2"] and res["member2"] and res["reset2"], res
     assert res["n_replaced3"] > 0 and res["same3"] and not res["member3"] and res["pairmean3"], res
     assert res["same_kmeans"], res
-    assert res["sh_idx"] and res["sh_q"] and res["sh_cs"] and res["sh_emb"], res
+    for mode in ("replicated", "all_gather"):
+        for key in ("is_sharded", "idx", "q", "cs", "emb", "sd", "load"):
+            assert res[f"sh_{key}_{mode}"], (key, mode, res)
+        assert res[f"sh_expired_{mode}"] >= 3, res
+    assert res["sh_loss"] and res["sh_kmeans"], res

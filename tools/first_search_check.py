@@ -18,11 +18,13 @@ for seed in (11, 12, 13, 14):
     cache = ops.prepare_codebook(c, False)
     idx, _, ws = ops.search(x, c, cache, False)
     st = ops.search_stats(ws)
-    rows = torch.randperm(N, generator=torch.Generator().manual_seed(seed))[:65536].to(dev)
+    # seed 11 (the full-size test's inputs): EVERY row against the exact scan; the others: a 65536-row sample
+    n_chk = N if seed == 11 else 65536
+    rows = torch.randperm(N, generator=torch.Generator().manual_seed(seed))[:n_chk].to(dev)
     ex, es, _ = ops.search(x[:, rows].contiguous(), c, None, False, force_exact=True, want_score=True)
     bad = (idx[0, rows] != ex[0]).nonzero().flatten()
     total_bad += int(bad.numel())
-    print(f"seed {seed}: {int(bad.numel())} of 65536 sampled rows differ from the exact scan; stats {st}", flush=True)
+    print(f"seed {seed}: {int(bad.numel())} of {n_chk} rows differ from the exact scan; stats {st}", flush=True)
     for b in bad[:6].tolist():
         r = int(rows[b])
         _, s_got, _ = ops.search(x[:, r:r + 1].contiguous(), c[:, int(idx[0, r]):int(idx[0, r]) + 1].contiguous(), None, False,

@@ -1,8 +1,10 @@
 """Multi-GPU parity check, launched as: torchrun --nproc-per-node W --master-addr 127.0.0.1 tools/mgpu_check.py
  1. data parallel: W ranks, each quantising its slice, end up with the codebook a single process gets on the
     concatenated batch (cluster_size exact, embeddings/embed_avg 1e-6), identical on every rank, incl. expiry.
- 2. sharded codebook: indices equal the un-sharded search; each shard's EMA result equals the matching rows of the
-    un-sharded update.
+ 1c. the same data-parallel step against the CPU ORACLE on the rank-concatenated batch.
+ 2. sharded codebook through the module API (Codebook.sharded; replicated and all_gather inputs) against the CPU
+    ORACLE on the un-sharded codebook: indices, bit-exact quantize, every shard's EMA + dead-code expiry result equals
+    the matching rows of the reference update, state_dict holds the full tensors.
 Prints 'MGPU OK' from rank 0 on success."""
 import os
 import sys
@@ -13,7 +15,8 @@ sys.path.insert(0, os.path.join(ROOT, "vector-quantization-by-ml_b200"))
 import torch
 import torch.distributed as dist
 
-from vqb200 import CodebookParams, KmeansParameters, ShardedCodebook, VectorQuantize, ops
+from oracle import vq_oracle as O  # noqa: E402  (test tool: the oracle is the checker)
+from vqb200 import CodebookParams, KmeansParameters, VectorQuantize, distributed as D, ops
 
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
@@ -81,25 +84,73 @@ for name in ("embeddings", "embed_avg", "cluster_size"):
     dist.broadcast(ref, src=0)
     check(torch.equal(mine, ref), f"replicas diverged with distributed_replace_codes=False: {name}")
 
-# ---------------- 2. sharded codebook ----------------
+# ---------------- 1c. data parallel against the ORACLE (single process on the rank-concatenated batch) ----------------
+torch.manual_seed(0)
+dpo = VectorQuantize(dim=d, codebook_params=CodebookParams(dim=d, codebook_size=K, threshold_ema_dead_code=0),
+                     sync_codebook=True).to(dev).train()
+cbo = dpo._codebook
+cbo.embeddings.copy_(c0); cbo.embed_avg.copy_(c0); cbo.cluster_size.fill_(1.0); cbo.invalidate_cache()
+with torch.no_grad():
+    qd, indd, _ = dpo(x_all[rank][None].to(dev))
+sto = O.CodebookState(c0.clone(), c0.clone(), torch.ones(1, K))
+qo, io, lo, exo = O.vq_forward(sto, x_all.reshape(1, -1, d), O.VQOpts(codebook=O.CodebookOpts(threshold_ema_dead_code=0)),
+                               want_gap=True)
+rows = slice(rank * n_per, (rank + 1) * n_per)
+diff = indd[0].cpu() != io[0, rows]
+check(bool((exo["top2_rel_gap"][0, rows][diff] < 1e-6).all()), "DP indices differ from the ORACLE outside its 1e-6 window")
+if not bool(diff.any()):
+    check(torch.equal(qd[0].cpu(), qo[0, rows]), "DP quantize vs oracle")
+    check(torch.equal(cbo.cluster_size.cpu(), sto.cluster_size), "DP cluster_size vs oracle")
+    check(rel(cbo.embeddings.cpu(), sto.embeddings) < 1e-5, "DP embeddings vs oracle")
+
+# ---------------- 2. sharded codebook, through the module API, against the ORACLE (un-sharded reference path) -------
+# codebooks.py:350-435 on the whole codebook is the oracle; the sharded path must give its indices (outside the
+# reference's own 1e-6 ties), bit-exact quantize, and on every rank the matching rows of its EMA + expiry result
+D.SHARD_MIN_CODES = 4096
 K, d, N = 4096, 64, 20000
 g = torch.Generator().manual_seed(9)
-x = torch.randn(N, d, generator=g).to(dev)
-full = (torch.randn(K, d, generator=g) * 0.5).to(dev)
-sh = ShardedCodebook(d, K).to(dev)
-sh.load_full_codebook(full)
-sh.train()
-q, gidx, commit = sh(x)
-cache = ops.prepare_codebook(full[None].contiguous(), False)
-ref_idx, _, ws = ops.search(x[None], full[None].contiguous(), cache, False)
-check(torch.equal(gidx, ref_idx[0]), f"sharded indices differ: {int((gidx != ref_idx[0]).sum())}")
-check(torch.equal(q, x + (full[ref_idx[0]] - x)), "sharded quantize not bit-exact")
-stats = ops.ema_reduce(x[None], ref_idx, None, K, bound_ws=ws)
-cs, ea, em = torch.ones(1, K, device=dev), full[None].clone(), full[None].clone()
-ops.ema_apply(stats, cs, ea, em, 1 - 0.8, 1e-5, False)
-sl = slice(sh.offset, sh.offset + sh.shard_size)
-check(torch.equal(sh.cluster_size[0], cs[0, sl]), "sharded cluster_size")
-check(rel(sh.embed_avg[0], ea[0, sl]) < 1e-6 and rel(sh.embeddings[0], em[0, sl]) < 1e-5, "sharded EMA buffers")
+x = torch.randn(N, d, generator=g)
+full = torch.randn(K, d, generator=g) * 0.5
+full[3000] = full[11]                 # duplicate in another shard: the lowest index must win every row
+full[100:104] *= 30.0                 # never chosen -> die -> replaced by the rows rank 0 draws
+for mode in ("replicated", "all_gather"):
+    torch.manual_seed(0)
+    vq = VectorQuantize(dim=d, codebook_params=CodebookParams(dim=d, codebook_size=K, threshold_ema_dead_code=2),
+                        sync_codebook=True).to(dev).train()
+    cb = vq._codebook
+    check(cb.sharded and cb.embeddings.shape[1] == K // world, "Codebook did not shard")
+    cb.sharded_input = mode
+    cb.load_full_codebook(full)
+    n_loc = N // world
+    x_in = x if mode == "replicated" else x[rank * n_loc:(rank + 1) * n_loc]
+    x_ref = x if mode == "replicated" else x[:n_loc * world]
+    from vqb200.codebook import Codebook
+    Codebook._draw_rows = staticmethod(lambda n, m, device: (torch.randperm(n)[:m] if n >= m else torch.randint(0, n, (m,))).to(device))
+    torch.manual_seed(21)
+    with torch.no_grad():
+        q, gidx, loss = vq(x_in[None].to(dev))
+    st = O.CodebookState(full[None].clone(), full[None].clone(), torch.ones(1, K))
+    torch.manual_seed(21)
+    qo, io, lo, ex = O.vq_forward(st, x_ref[None], O.VQOpts(codebook=O.CodebookOpts(threshold_ema_dead_code=2)), want_gap=True)
+    rows = slice(0, N) if mode == "replicated" else slice(rank * n_loc, (rank + 1) * n_loc)
+    diff = gidx[0].cpu() != io[0, rows]
+    check(bool((ex["top2_rel_gap"][0, rows][diff] < 1e-6).all()),
+          f"sharded ({mode}) indices differ from the oracle outside its 1e-6 window: {int(diff.sum())}")
+    check(bool((gidx != 3000).all()), "duplicate code: the higher index won")
+    same = ~diff
+    check(torch.equal(q[0].cpu()[same], qo[0, rows][same]), f"sharded ({mode}) quantize not bit-exact")
+    sl = slice(cb.shard_offset, cb.shard_offset + cb.shard_size)
+    n_flip = torch.tensor([int(diff.sum())], device=dev)
+    dist.all_reduce(n_flip)
+    if int(n_flip) == 0:
+        if mode == "replicated":
+            check(abs(float(loss) - float(lo)) <= 1e-5 * float(lo), "sharded loss")
+        check(torch.equal(cb.cluster_size[0].cpu(), st.cluster_size[0, sl]), f"sharded ({mode}) cluster_size")
+        check(rel(cb.embed_avg[0].cpu(), st.embed_avg[0, sl]) < 1e-5 and rel(cb.embeddings[0].cpu(), st.embeddings[0, sl]) < 1e-5,
+              f"sharded ({mode}) EMA buffers / expiry")
+        check(int((st.cluster_size[0] == 2.0).sum()) >= 4, "expiry did not fire in the sharded scenario")
+    sd = vq.state_dict()
+    check(tuple(sd["_codebook.embeddings"].shape) == (1, K, d), "state_dict must hold the full codebook")
 if rank == 0:
     print("MGPU OK", flush=True)
 dist.destroy_process_group()

@@ -9,10 +9,9 @@ replaces
     from vector_quantization.codebooks import Codebook, CodebookParams, KmeansParameters
 """
 from .codebook import Codebook, CosineSimCodebook, EuclideanCodebook
-from .distributed import ShardedCodebook
 from .params import AffineParameters, CodebookParams, GumbelParams, KmeansParameters
 from .rvq import GroupedResidualVQ, ResidualVQ
 from .vq import LossBreakdown, VectorQuantize
 
 __all__ = ["Codebook", "EuclideanCodebook", "CosineSimCodebook", "CodebookParams", "KmeansParameters", "GumbelParams",
-           "AffineParameters", "VectorQuantize", "LossBreakdown", "ResidualVQ", "GroupedResidualVQ", "ShardedCodebook"]
+           "AffineParameters", "VectorQuantize", "LossBreakdown", "ResidualVQ", "GroupedResidualVQ"]

@@ -79,8 +79,33 @@ class Codebook(nn.Module):
             _uniform_init(num_codebooks, codebook_size, dim)
         if self.weights_l2norm:
             init = _l2norm_cpu_or_cuda(init)
+
+        # Sharded codebook (north star config 5; no reference counterpart): with >= SHARD_MIN_CODES codes, a process
+        # group up and `use_ddp` set, rank r owns rows [r K/W, (r+1) K/W) of the three buffers.  Every rank draws the
+        # same full initialisation (the ranks share the module seed, as replicated data parallel requires too) and
+        # keeps its rows; `state_dict()` gathers the full (H,K,d) tensors under the reference's keys and
+        # `load_state_dict()` takes this rank's rows of them (both collective-free on load, one all_gather on save).
+        from . import distributed as D
+        self.sharded = bool(use_ddp and D.is_distributed() and codebook_size >= D.SHARD_MIN_CODES
+                            and codebook_size % D.world_size() == 0)
+        self.shard_world = D.world_size() if self.sharded else 1
+        self.shard_rank = D.rank() if self.sharded else 0
+        self.shard_size = codebook_size // self.shard_world
+        # "replicated": every rank passes the SAME latents (BASELINE config 5); "all_gather": every rank passes its own
+        # batch and the ranks' batches are concatenated before the search (data parallel over a sharded codebook)
+        self.sharded_input = "all_gather"
+        self._replica: Optional[torch.Tensor] = None
+        self._replica_dirty = True
+        if self.sharded:
+            if learnable_codebook:
+                raise NotImplementedError("vqb200: a sharded codebook (>= %d codes under a process group) is EMA-only"
+                                          % D.SHARD_MIN_CODES)
+            lo = self.shard_rank * self.shard_size
+            init = init[:, lo:lo + self.shard_size].contiguous()
+            self._register_state_dict_hook(Codebook._gather_state_hook)
+            self._register_load_state_dict_pre_hook(self._slice_state_pre_hook)
         self.is_initialized = not initialization_by_kmeans
-        self.register_buffer("cluster_size", torch.zeros(num_codebooks, codebook_size))
+        self.register_buffer("cluster_size", torch.zeros(num_codebooks, self.shard_size))
         self.register_buffer("embed_avg", init.clone())
         if self.learnable_codebook:          # reference codebooks.py:186-190: a Parameter, trained by the user's optimizer
             self.embeddings = nn.Parameter(init)
@@ -219,6 +244,191 @@ class Codebook(nn.Module):
                                self.embeddings.data[h])
         self._dirty = True
 
+    # ------------------------------------------------------------------ sharded codebook (config 5)
+    @property
+    def shard_offset(self) -> int:
+        return self.shard_rank * self.shard_size
+
+    @staticmethod
+    def _gather_state_hook(module, state_dict, prefix, local_metadata):
+        from . import distributed as D
+        for name in ("embeddings", "embed_avg", "cluster_size"):
+            state_dict[prefix + name] = D.all_gather_codes(getattr(module, name).detach(), dim=1)
+
+    def _slice_state_pre_hook(self, state_dict, prefix, *args):
+        lo = self.shard_offset
+        for name in ("embeddings", "embed_avg", "cluster_size"):
+            t = state_dict.get(prefix + name)
+            if t is not None and t.shape[1] == self.codebook_size:
+                state_dict[prefix + name] = t[:, lo:lo + self.shard_size]
+        self._dirty = self._replica_dirty = True
+
+    def load_full_codebook(self, full: torch.Tensor, cluster_size: float = 1.0) -> None:
+        """(H,K,d) or (K,d) codebook -> this rank's rows (or all of them when not sharded); embed_avg = embeddings."""
+        full = full if full.ndim == 3 else full[None]
+        lo = self.shard_offset
+        rows = full[:, lo:lo + self.shard_size].to(self.embeddings.device, torch.float32)
+        with torch.no_grad():
+            self.embeddings.copy_(rows); self.embed_avg.copy_(rows); self.cluster_size.fill_(cluster_size)
+        self._dirty = self._replica_dirty = True
+
+    def full_codebook(self) -> torch.Tensor:
+        """(H,K,d) replica of the sharded `embeddings` (one all_gather when a shard changed since the last call)."""
+        if not self.sharded:
+            return self.embeddings.detach()
+        if self._replica_dirty or self._replica is None:
+            from . import distributed as D
+            self._replica = D.all_gather_codes(self.embeddings.detach(), dim=1, out=self._replica)
+            self._replica_dirty = False
+        return self._replica
+
+    def _shard_search(self, flat: torch.Tensor, emb: torch.Tensor, cache) -> torch.Tensor:
+        """Global nearest code of every row: local shard search -> (fp32 score of the reference recipe, global index)
+        packed into int64 keys -> all_reduce(MIN): smallest score, lowest index on ties = torch.argmax on the
+        un-sharded similarities.  Every rank evaluates the score with the same fp64-accumulated recipe, so the
+        cross-shard comparison is consistent."""
+        from . import distributed as D
+        H, N, _ = flat.shape
+        idx, score, ws = ops.search(flat, emb, cache, self.use_cosine_sim, idx_offset=self.shard_offset,
+                                    want_score=True)
+        self.last_search_ws = ws
+        keys = ops.minkey_pack(score.reshape(-1), idx.reshape(-1))
+        D.merge_min_keys(keys)
+        gidx, _ = ops.minkey_unpack(keys)
+        return gidx.reshape(H, N)
+
+    @torch.no_grad()
+    def _kmeans_init_sharded(self, flat: torch.Tensor, mask_u8: Optional[torch.Tensor]) -> None:
+        """reference utils/kmeans.py:38-120 on a row-sharded set of K centroids: rank 0's draw picks the K start rows
+        (all ranks hold the same latents), every iteration is a sharded search + segment means on the owned rows."""
+        from . import distributed as D
+        H, N, d = flat.shape
+        data = flat.float()
+        if mask_u8 is not None:
+            data = data[:, mask_u8.bool()].contiguous()
+            N = data.shape[1]
+        iters = int((self.kmeans_params or {"iter": 10})["iter"])
+        lo, Ks = self.shard_offset, self.shard_size
+        cents = []
+        for h in range(H):
+            rows = D.broadcast_from_rank0(self._draw_rows(N, self.codebook_size, data.device).to(torch.long))
+            cents.append(data[h][rows[lo:lo + Ks]])
+        cents = torch.stack(cents, 0).contiguous()
+        counts = torch.zeros(H, Ks, device=data.device)
+        for _ in range(iters):
+            cache = ops.prepare_codebook(cents, self.use_cosine_sim)
+            gidx = self._shard_search(data, cents, cache)
+            mine = (gidx >= lo) & (gidx < lo + Ks)
+            stats = torch.stack([ops.ema_reduce(data[h:h + 1], (gidx[h:h + 1] - lo).clamp_(0, Ks - 1),
+                                                mine[h].to(torch.uint8), Ks)[0] for h in range(H)], 0)
+            counts = stats[..., d].clone()
+            empty = counts == 0
+            means = stats[..., :d] / counts.masked_fill(empty, 1.0)[..., None]
+            if self.use_cosine_sim:
+                means = ops.l2norm_rows(means.contiguous())
+            cents = torch.where(empty[..., None], cents, means).contiguous()
+        self.embeddings.data.copy_(cents)
+        self.embed_avg.data.copy_(cents * counts[..., None])
+        self.cluster_size.data.copy_(counts)
+        self._dirty = self._replica_dirty = True
+
+    @torch.no_grad()
+    def _expire_codes_sharded(self, flat: torch.Tensor) -> None:
+        """reference codebooks.py:230-255 on shards: the dead codes of all shards, in ascending GLOBAL code order, take
+        the rows rank 0 draws with the reference's calls (utils/general.py:62-66) -- exactly what one process does on
+        the un-sharded codebook with rank 0's generator.  One all_gather of the per-shard dead counts (the host sync
+        the reference has too) and one broadcast of the drawn row ids."""
+        if self.threshold_ema_dead_code == 0:
+            return
+        from . import distributed as D
+        H, N, d = flat.shape
+        dead = self.cluster_size < self.threshold_ema_dead_code
+        counts = D.all_gather_small(dead.sum(dim=-1))                  # (W, H) on the host
+        if int(counts.sum()) == 0:
+            return
+        for h in range(H):
+            m_total = int(counts[:, h].sum())
+            if m_total == 0:
+                continue
+            rows = D.broadcast_from_rank0(self._draw_rows(N, m_total, flat.device).to(torch.long))
+            first = int(counts[:self.shard_rank, h].sum())
+            m = int(counts[self.shard_rank, h])
+            if m:
+                ops.expire_scatter(flat[h], rows[first:first + m], float(self.threshold_ema_dead_code),
+                                   float(self.reset_cluster_size), self.weights_l2norm, self.cluster_size.data[h],
+                                   self.embed_avg.data[h], self.embeddings.data[h])
+        self._dirty = self._replica_dirty = True
+
+    def _run_sharded(self, x, mask, freeze_codebook, fuse_st, want_commit, normalize_input):
+        """`_run` for a row-sharded codebook.  Every rank ends up with the quantised vectors / indices of ITS latents
+        (all of them when the input is replicated) and updates ITS rows of the EMA buffers from the rows they won --
+        no statistics all_reduce; the only exchanges are the min-key all_reduce, one scalar all_reduce for the Laplace
+        normaliser and the all_gather that refreshes the codebook replica the gather reads."""
+        from . import distributed as D
+        _lib.require_device(x)
+        flat, lead = self._flatten(x)
+        H, n_local, d = flat.shape
+        if H != self.num_codebooks or d != self.embeddings.shape[-1]:
+            raise ValueError(f"vqb200.Codebook: input {tuple(x.shape)} does not match codebook "
+                             f"(H={self.num_codebooks}, d={self.embeddings.shape[-1]})")
+        if torch.is_grad_enabled() and flat.requires_grad and normalize_input:
+            flat = ops.l2norm_rows_autograd(flat)
+        elif normalize_input:
+            flat = ops.l2norm_rows(flat)
+        mask_u8 = self._expand_mask(mask, n_local)
+        gathered = self.sharded_input == "all_gather"
+        rows_all, mask_all = flat.detach(), mask_u8
+        if gathered:
+            rows_all = D.all_gather_rows(flat.detach(), dim=1)
+            if mask_u8 is not None:
+                mask_all = D.all_gather_rows(mask_u8, dim=0)
+        N = rows_all.shape[1]
+        if not self.is_initialized:
+            self._kmeans_init_sharded(rows_all, mask_all)
+            self.is_initialized = True
+
+        gidx_all = self._shard_search(rows_all, self.embeddings.detach(), self._codebook_cache())
+        replica = self.full_codebook()
+        training = self.training
+        update = training and self.ema_update and not freeze_codebook
+        if update and torch.is_grad_enabled() and flat.requires_grad:
+            replica = replica.clone()          # backward reads the PRE-update codes (see _run)
+        lo_r = self.shard_rank * n_local if gathered else 0
+        gidx = gidx_all[:, lo_r:lo_r + n_local] if gathered else gidx_all
+        commit = None
+        stats_full = None
+        whole = update and not gathered and mask_u8 is None and self.fused_quantize_ema and ops.quantize_ema_supported(d)
+        if whole and fuse_st:
+            # replicated input: gather/ST/loss over all rows and the EMA sums of ALL codes in one pass; this rank
+            # keeps the statistics of its own rows of the codebook
+            quant, commit, stats_full = ops.quantize_training(flat, replica, gidx, None, want_commit, ema=True,
+                                                              bound_ws=self.last_search_ws)
+        elif whole:
+            with torch.no_grad():
+                quant, _, stats_full = ops.quantize_ema(flat, replica, gidx, False, False, bound_ws=self.last_search_ws)
+        elif fuse_st and training:
+            quant, commit, _ = ops.quantize_training(flat, replica, gidx.contiguous(), mask_u8, want_commit)
+        else:
+            with torch.no_grad():
+                quant, _ = ops.gather_st_loss(flat, replica, gidx.contiguous(), None, False, False)
+        if update:
+            with torch.no_grad():
+                lo, Ks = self.shard_offset, self.shard_size
+                if stats_full is not None:
+                    stats = stats_full[:, lo:lo + Ks].contiguous()
+                else:
+                    mine = (gidx_all >= lo) & (gidx_all < lo + Ks)
+                    if mask_all is not None:
+                        mine = mine & mask_all.bool()[None]
+                    stats = torch.stack([ops.ema_reduce(rows_all[h:h + 1], (gidx_all[h:h + 1] - lo).clamp_(0, Ks - 1),
+                                                        mine[h].to(torch.uint8), Ks)[0] for h in range(H)], 0)
+                ops.ema_apply_sharded(stats, self.cluster_size.data, self.embed_avg.data, self.embeddings.data,
+                                      1 - self.decay, self.eps_for_smoothing, self.weights_l2norm, self.codebook_size,
+                                      D.all_reduce_sum)
+                self._dirty = self._replica_dirty = True
+                self._expire_codes_sharded(rows_all)
+        return quant.reshape(H, *lead, d), gidx.reshape(H, *lead), commit
+
     # ------------------------------------------------------------------ core
     def _run(self, x: torch.Tensor, mask: Optional[torch.Tensor], freeze_codebook: bool, fuse_st: bool,
              want_commit: bool, normalize_input: bool = False, keep_dense: bool = False):
@@ -226,6 +436,10 @@ class Codebook(nn.Module):
         commit scalar | None).  `keep_dense`: leave in `self.dense_ctx` what the consumers of the dense similarities
         (cross-entropy to indices, CE commitment, diversity loss) need: the (H,N,d) latents the search saw and the
         codebook as it was BEFORE this forward's EMA step (reference codebooks.py:386 runs before :425)."""
+        if self.sharded:
+            if keep_dense:
+                raise NotImplementedError("vqb200: the dense-similarity losses are not available on a sharded codebook")
+            return self._run_sharded(x, mask, freeze_codebook, fuse_st, want_commit, normalize_input)
         _lib.require_device(x)        # raises for a CPU tensor: there is no CPU implementation
         flat, lead = self._flatten(x)
         H, N, d = flat.shape

@@ -7,7 +7,10 @@ reference does that with `sample_vectors_distributed` (utils/distributed.py:55-7
 
 Sharded codebook (no reference counterpart; BASELINE config 5): rank r owns codes [r*K/W, (r+1)*K/W); every rank
 searches its shard for all latents and an all_reduce(MIN) over packed (score, global index) int64 keys picks the
-winner -- smallest score, lowest index on ties, i.e. torch.argmax semantics on the un-sharded codebook.
+winner -- smallest score, lowest index on ties, i.e. torch.argmax semantics on the un-sharded codebook.  The path
+lives in `Codebook` itself (`Codebook.sharded`, chosen at construction when `codebook_size >= SHARD_MIN_CODES`, a
+process group is up and `use_ddp` is set), so `VectorQuantize` / `ResidualVQ` reach it unchanged; this module holds
+the collectives it uses.
 """
 from __future__ import annotations
 
@@ -17,8 +20,55 @@ import torch
 import torch.distributed as dist
 
 
+SHARD_MIN_CODES = 65536      # north star: "codebooks of 64K entries or more are sharded across GPUs"
+
+
 def is_distributed() -> bool:
     return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+
+
+def world_size() -> int:
+    return dist.get_world_size() if is_distributed() else 1
+
+
+def rank() -> int:
+    return dist.get_rank() if is_distributed() else 0
+
+
+def all_gather_codes(shard: torch.Tensor, dim: int = 1, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Concatenate the ranks' shards along `dim` (rank order) -- the replica of a row-sharded codebook buffer."""
+    if not is_distributed():
+        return shard
+    W = dist.get_world_size()
+    shard = shard.contiguous()
+    stacked = torch.empty((W,) + tuple(shard.shape), dtype=shard.dtype, device=shard.device)
+    dist.all_gather_into_tensor(stacked.view(-1), shard.view(-1))
+    full = stacked.movedim(0, dim).reshape(*shard.shape[:dim], W * shard.shape[dim], *shard.shape[dim + 1:])
+    if out is not None and out.shape == full.shape and out.dtype == full.dtype:
+        out.copy_(full)
+        return out
+    return full.contiguous()
+
+
+def all_gather_rows(local: torch.Tensor, dim: int) -> torch.Tensor:
+    """Concatenate equally sized per-rank batches along `dim` (rank order)."""
+    return all_gather_codes(local, dim=dim)
+
+
+def all_gather_small(t: torch.Tensor) -> torch.Tensor:
+    """(W, *t.shape) on the HOST: the ranks' copies of a tiny tensor (one collective + one host sync)."""
+    if not is_distributed():
+        return t[None].cpu()
+    W = dist.get_world_size()
+    out = torch.empty((W,) + tuple(t.shape), dtype=t.dtype, device=t.device)
+    dist.all_gather_into_tensor(out.view(-1), t.contiguous().view(-1))
+    return out.cpu()
+
+
+def broadcast_from_rank0(t: torch.Tensor) -> torch.Tensor:
+    if is_distributed():
+        dist.broadcast(t, src=0)
+    return t
 
 
 def all_reduce_sum(t: torch.Tensor, group=None) -> None:
@@ -72,72 +122,3 @@ def sample_vectors_distributed(local: torch.Tensor, num: int, draw_rows: Callabl
     out = torch.where(mine[:, None], picked, torch.zeros((), dtype=torch.float32, device=dev))
     dist.all_reduce(out, op=dist.ReduceOp.SUM, group=group)
     return out
-
-
-# ---- sharded codebook -----------------------------------------------------------------------------------------
-class ShardedCodebook(torch.nn.Module):
-    """Codebook of `codebook_size` codes whose rows are split contiguously over the ranks of `group`.
-
-    forward(x): x (N,d) or (B,n,d) replicated on every rank (all_gather it first if it is sharded).  Returns
-    (quantize fp32, indices int64 -- global code ids, commit loss) like a single-device codebook in eval/training
-    mode; in training mode each rank applies the EMA update to ITS shard from the rows it won.
-    """
-
-    def __init__(self, dim: int, codebook_size: int, decay: float = 0.8, eps_for_smoothing: float = 1e-5,
-                 use_cosine_sim: bool = False, group=None, rank: Optional[int] = None, world: Optional[int] = None):
-        super().__init__()
-        self.group = group
-        self.world = world if world is not None else (dist.get_world_size(group) if is_distributed() else 1)
-        self.rank = rank if rank is not None else (dist.get_rank(group) if is_distributed() else 0)
-        assert codebook_size % self.world == 0, "codebook_size must divide evenly over the ranks"
-        self.codebook_size, self.shard_size, self.dim = codebook_size, codebook_size // self.world, dim
-        self.decay, self.eps, self.use_cosine_sim = decay, eps_for_smoothing, use_cosine_sim
-        self.register_buffer("embeddings", torch.zeros(1, self.shard_size, dim))
-        self.register_buffer("embed_avg", torch.zeros(1, self.shard_size, dim))
-        self.register_buffer("cluster_size", torch.zeros(1, self.shard_size))
-        self._cache = None
-        self._dirty = True
-
-    @property
-    def offset(self) -> int:
-        return self.rank * self.shard_size
-
-    def load_full_codebook(self, full: torch.Tensor) -> None:
-        """Take this rank's rows of a (K,d) codebook; embed_avg = embeddings, cluster_size = 1."""
-        rows = full[self.offset:self.offset + self.shard_size].to(self.embeddings.device, torch.float32)
-        self.embeddings.copy_(rows[None]); self.embed_avg.copy_(rows[None]); self.cluster_size.fill_(1.0)
-        self._dirty = True
-
-    def gather_full_codebook(self) -> torch.Tensor:
-        if self.world == 1:
-            return self.embeddings[0]
-        parts = [torch.empty_like(self.embeddings[0]) for _ in range(self.world)]
-        dist.all_gather(parts, self.embeddings[0].contiguous(), group=self.group)
-        return torch.cat(parts, 0)
-
-    @torch.no_grad()
-    def forward(self, x: torch.Tensor):
-        from . import ops
-        shape = x.shape
-        flat = x.reshape(1, -1, shape[-1]).contiguous()
-        if self._dirty or self._cache is None:
-            self._cache = ops.prepare_codebook(self.embeddings, self.use_cosine_sim, self._cache)
-            self._dirty = False
-        # local shard search -> (exact score, global index) -> cross-GPU min
-        idx, score, ws = ops.search(flat, self.embeddings, self._cache, self.use_cosine_sim, idx_offset=self.offset,
-                                    want_score=True)
-        keys = ops.minkey_pack(score.reshape(-1), idx.reshape(-1))
-        merge_min_keys(keys, self.group)
-        gidx, _ = ops.minkey_unpack(keys)
-        gidx = gidx.reshape(1, -1)
-        full = self.gather_full_codebook()[None].contiguous()            # (1,K,d) replica for the gather
-        quant, loss = ops.gather_st_loss(flat, full, gidx, None, self.training, self.training)
-        if self.training:
-            mine = ((gidx >= self.offset) & (gidx < self.offset + self.shard_size)).reshape(-1)
-            local_idx = (gidx - self.offset).clamp_(0, self.shard_size - 1)
-            stats = ops.ema_reduce(flat, local_idx, mine.to(torch.uint8), self.shard_size, bound_ws=ws)
-            ops.ema_apply_sharded(stats, self.cluster_size, self.embed_avg, self.embeddings, 1 - self.decay, self.eps,
-                                  False, self.codebook_size, lambda t: all_reduce_sum(t, self.group))
-            self._dirty = True
-        commit = loss[0] if loss is not None else torch.zeros((), device=x.device)
-        return quant.reshape(shape), gidx.reshape(shape[:-1]), commit
