@@ -184,7 +184,8 @@ int    vqb_expire_scatter(const void* x, int x_dtype, const int64_t* sample_rows
  * Replaces, for one level, codebooks.py:393-397 + vector_quantize_pytorch.py:273,362 +
  * residual_vq.py:232-233, and prepares the next level's search operand in the same pass:
  *   q        = training ? fl(r + fl(c - r)) : c      (rows with mask==0: q = r, as torch.where does at :415-418)
- *   out      = first_level ? fl(0.0f + q) : fl(out + q)
+ *   out      = first_level ? fl(0.0f + q) : fl(out + q)     (quantized_out; NULL: not accumulated here, see
+ *                                                            vqb_rvq_replay_out)
  *   r_next   = fl(r - q)                  (residual_out; may alias residual_in, but the caller normally
  *                                          ping-pongs two buffers so the level input survives for expiry sampling)
  *   loss_out = [mean((c - r)^2) over rows with mask!=0, rows used]   (as vqb_gather_st_loss)
@@ -210,6 +211,18 @@ int    vqb_rvq_level_ema(const float* residual_in, float* residual_out, const fl
                          float* q_out, float* loss_out, float* stats, int64_t N, int K, int d,
                          void* ws, size_t ws_bytes, void* next_ws, size_t next_ws_bytes, const void* next_cache,
                          void* stream);
+
+/* Sum of the levels' outputs of one ResidualVQ forward (residual_vq.py:233 `quantized_out = quantized_out + quantized`
+ * over the levels), replayed from the level-0 input and the chosen codes with the IEEE operations of vqb_rvq_level:
+ *   r_0 = x;  q_l as in vqb_rvq_level with codebooks[l] (K,d), idx[l] (N,), training[l];  out = fl(..fl(0 + q_0) + ..);
+ * bit-identical to accumulating `quantized_out` level by level.  A caller that passes quantized_out = NULL to
+ * vqb_rvq_level[_ema] saves the read-modify-write of that buffer in every level and calls this once at the end.
+ * codebooks[l] must be the codebook level l gathered from (a copy taken before its EMA refresh).  d % 4 == 0,
+ * d <= 512, num_levels <= 32 (vqb_rvq_replay_out_supported).  mask (N) nullable as in vqb_rvq_level. */
+int    vqb_rvq_replay_out_supported(int d, int num_levels);
+int    vqb_rvq_replay_out(const float* x, const float* const* codebooks, const int64_t* const* idx,
+                          const int* training, int num_levels, const uint8_t* mask, float* out, int64_t N, int d,
+                          void* stream);
 
 /* ---- sharded-codebook merge (K >= 64K split across GPUs) ------------------------------
  * No reference counterpart.  key = (orderable(score) << 32) | index, so an

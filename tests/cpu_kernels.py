@@ -86,7 +86,8 @@ def rvq_level(residual, residual_next, embeddings, idx, mask_u8, training, first
     keep = torch.ones(r.shape[0], dtype=torch.bool) if mask_u8 is None else mask_u8.bool()
     q = torch.where(keep[:, None], q, r)
     residual_next.copy_(r - q)
-    quantized_out.copy_(0.0 + q if first_level else quantized_out + q)
+    if quantized_out is not None:
+        quantized_out.copy_(0.0 + q if first_level else quantized_out + q)
     if q_out is not None:
         q_out.copy_(q)
     rows = int(keep.sum())
@@ -100,6 +101,22 @@ def rvq_level_ema(residual, residual_next, embeddings, idx, training, first_leve
     loss = rvq_level(residual, residual_next, embeddings, idx, None, training, first_level, quantized_out, next_cache,
                      q_out)
     return loss, stats
+
+
+def rvq_replay_out(x, codebooks, idxs, training, mask_u8, out=None):
+    """vqb_rvq_replay_out: the running sum of the levels' outputs, replayed from the input and the indices."""
+    keep = torch.ones(x.shape[0], dtype=torch.bool) if mask_u8 is None else mask_u8.bool()
+    r, acc = x, torch.zeros_like(x)
+    for c, i, tr in zip(codebooks, idxs, training):
+        cq = c[i]
+        q = r + (cq - r) if tr else cq
+        q = torch.where(keep[:, None], q, r)
+        acc = acc + q
+        r = r - q
+    if out is not None:
+        out.copy_(acc)
+        return out
+    return acc
 
 
 def minkey_pack(score, idx):
@@ -130,9 +147,11 @@ def ema_apply_sharded(stats, cluster_size, embed_avg, embeddings, weight, eps, w
 def install(ops, lib):
     """Replace the wrappers on the `vqb200.ops` module object and the device guard of `vqb200._lib`."""
     for name in ("prepare_codebook", "search", "l2norm_rows", "gather_st_loss", "st_commit_backward", "ema_reduce",
-                 "ema_apply", "expire_scatter", "minkey_pack", "minkey_unpack", "ema_apply_sharded", "rvq_level", "rvq_level_ema"):
+                 "ema_apply", "expire_scatter", "minkey_pack", "minkey_unpack", "ema_apply_sharded", "rvq_level", "rvq_level_ema",
+                 "rvq_replay_out"):
         setattr(ops, name, globals()[name])
     ops.l2norm_prepare_supported = lambda d: False
     ops.quantize_ema_supported = lambda d: False
     ops.rvq_level_ema_supported = lambda d: False
+    ops.rvq_replay_out_supported = lambda d, q: True
     lib.require_device = lambda x: None

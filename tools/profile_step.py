@@ -1,5 +1,7 @@
 """Per-kernel breakdown of one full training step (VectorQuantize.forward) at a named config.
-usage: python tools/profile_step.py [c2|c3|c4|c1]"""
+usage: python tools/profile_step.py [c2|c3|c4|c5|c1]
+       python -m torch.distributed.run --nproc-per-node W --master-addr 127.0.0.1 tools/profile_step.py c5
+(under torchrun the codebook of c5 is sharded over the ranks and rank 0 prints its own kernel table, NCCL included)"""
 import os
 import sys
 
@@ -12,7 +14,13 @@ from torch.profiler import ProfilerActivity, profile
 from vqb200 import CodebookParams, KmeansParameters, ResidualVQ, VectorQuantize, ops
 
 cfg = sys.argv[1] if len(sys.argv) > 1 else "c2"
-dev = torch.device("cuda:0")
+world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
+local = int(os.environ.get("LOCAL_RANK", "0"))
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+if world > 1:
+    import torch.distributed as dist
+    dist.init_process_group("nccl", device_id=dev)
 torch.manual_seed(0)
 g = torch.Generator(device=dev).manual_seed(1)
 
@@ -38,6 +46,12 @@ elif cfg == "c4":
     for i, l in enumerate(mod.layers):
         seed_codebook(l._codebook, scale=0.5 / (1.5 ** i))
     x = torch.randn(64, 4096, 512, generator=g, device=dev)
+elif cfg == "c5":
+    mod = VectorQuantize(dim=64, codebook_params=CodebookParams(dim=64, codebook_size=65536, threshold_ema_dead_code=0),
+                         sync_codebook=world > 1).to(dev)
+    mod._codebook.load_full_codebook(torch.randn(1, 65536, 64, generator=torch.Generator().manual_seed(0)) * 0.5)
+    mod._codebook.sharded_input = "replicated"
+    x = torch.randn(4096, 1024, 64, generator=torch.Generator(device=dev).manual_seed(4321), device=dev)
 else:
     mod = VectorQuantize(dim=256, codebook_params=CodebookParams(dim=256, codebook_size=512, threshold_ema_dead_code=0)).to(dev)
     x = torch.randn(1, 1024, 256, generator=g, device=dev)
@@ -52,9 +66,14 @@ with torch.no_grad():
         mod(x)
     e1.record()
     torch.cuda.synchronize()
-    print(f"{cfg}: {e0.elapsed_time(e1) / 5:.3f} ms per step", flush=True)
+    if rank == 0:
+        print(f"{cfg} (world {world}): {e0.elapsed_time(e1) / 5:.3f} ms per step", flush=True)
     with profile(activities=[ProfilerActivity.CUDA]) as prof:
         for _ in range(3):
             mod(x)
         torch.cuda.synchronize()
-print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=25, max_name_column_width=64), flush=True)
+if rank == 0:
+    print("(3 profiled steps: divide the totals by 3)")
+    print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=40, max_name_column_width=64), flush=True)
+if world > 1:
+    dist.destroy_process_group()

@@ -465,6 +465,7 @@ quantize_ema_kernel(const T* __restrict__ x, const float* __restrict__ cb, const
             __stcs(reinterpret_cast<float4*>(qh + off), make_float4(o[0], o[1], o[2], o[3]));
             __stcs(reinterpret_cast<float4*>(qh + off) + 1, make_float4(o[4], o[5], o[6], o[7]));
           } else {
+            if (R.out) {                          // NULL: the caller sums the levels afterwards (vqb_rvq_replay_out)
             float acc8[8];
             if (R.first) {
 #pragma unroll
@@ -477,6 +478,7 @@ quantize_ema_kernel(const T* __restrict__ x, const float* __restrict__ cb, const
             }
             *reinterpret_cast<float4*>(R.out + off) = make_float4(acc8[0], acc8[1], acc8[2], acc8[3]);
             *(reinterpret_cast<float4*>(R.out + off) + 1) = make_float4(acc8[4], acc8[5], acc8[6], acc8[7]);
+            }
 #pragma unroll
             for (int t = 0; t < 8; ++t) {
               rn[b].v[t] = __fsub_rn(v.v[t], o[t]);
@@ -904,7 +906,7 @@ extern "C" int vqb_rvq_level_ema(const float* residual_in, float* residual_out, 
                                  float* quantized_out, float* q_out, float* loss_out, float* stats, int64_t N, int K,
                                  int d, void* ws, size_t ws_bytes, void* next_ws, size_t next_ws_bytes,
                                  const void* next_cache, void* stream) {
-  VQB_REQUIRE(residual_in && residual_out && quantized_out && loss_out, VQB_ERR_INVALID, "vqb_rvq_level_ema: null pointer");
+  VQB_REQUIRE(residual_in && residual_out && loss_out, VQB_ERR_INVALID, "vqb_rvq_level_ema: null pointer");
   VQB_REQUIRE(vqb_rvq_level_ema_supported(d), VQB_ERR_UNSUPPORTED, "vqb_rvq_level_ema: d=%d (64, 128, 256 or 512)", d);
   VQB_REQUIRE(residual_in != residual_out, VQB_ERR_INVALID, "vqb_rvq_level_ema: rows are visited in code order, the "
               "residual cannot be updated in place");

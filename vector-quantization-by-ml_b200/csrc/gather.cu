@@ -256,13 +256,15 @@ rvq_level_kernel(const float* res_in, float* res_out, const float* __restrict__ 
         if (!live) qv = r;
         else if (training) qv = make_float4(__fadd_rn(r.x, df.x), __fadd_rn(r.y, df.y), __fadd_rn(r.z, df.z), __fadd_rn(r.w, df.w));
         else qv = c;
-        float4 o;
-        if (first) o = make_float4(__fadd_rn(0.f, qv.x), __fadd_rn(0.f, qv.y), __fadd_rn(0.f, qv.z), __fadd_rn(0.f, qv.w));
-        else {
-          const float4 p = *reinterpret_cast<const float4*>(orow + j);
-          o = make_float4(__fadd_rn(p.x, qv.x), __fadd_rn(p.y, qv.y), __fadd_rn(p.z, qv.z), __fadd_rn(p.w, qv.w));
+        if (out) {                         // NULL: the caller sums the levels afterwards (vqb_rvq_replay_out)
+          float4 o;
+          if (first) o = make_float4(__fadd_rn(0.f, qv.x), __fadd_rn(0.f, qv.y), __fadd_rn(0.f, qv.z), __fadd_rn(0.f, qv.w));
+          else {
+            const float4 p = *reinterpret_cast<const float4*>(orow + j);
+            o = make_float4(__fadd_rn(p.x, qv.x), __fadd_rn(p.y, qv.y), __fadd_rn(p.z, qv.z), __fadd_rn(p.w, qv.w));
+          }
+          *reinterpret_cast<float4*>(orow + j) = o;
         }
-        *reinterpret_cast<float4*>(orow + j) = o;
         const float4 rn = make_float4(__fsub_rn(r.x, qv.x), __fsub_rn(r.y, qv.y), __fsub_rn(r.z, qv.z), __fsub_rn(r.w, qv.w));
         *reinterpret_cast<float4*>(ro + j) = rn;
         if (qout) *reinterpret_cast<float4*>(qout + row * (int64_t)d + j) = qv;
@@ -275,7 +277,7 @@ rvq_level_kernel(const float* res_in, float* res_out, const float* __restrict__ 
         const float r = rr[j], c = cr[j];
         const float df = __fsub_rn(c, r);
         const float qv = live ? (training ? __fadd_rn(r, df) : c) : r;
-        orow[j] = first ? __fadd_rn(0.0f, qv) : __fadd_rn(orow[j], qv);
+        if (out) orow[j] = first ? __fadd_rn(0.0f, qv) : __fadd_rn(orow[j], qv);
         const float rn = __fsub_rn(r, qv);
         ro[j] = rn;
         if (qout) qout[row * (int64_t)d + j] = qv;
@@ -362,6 +364,83 @@ int launch_loss_finalize(const double* part, const long long* cntp, int nblocks,
   return VQB_OK;
 }
 
+
+// Sum of the levels' outputs of a ResidualVQ forward, replayed from the input and the chosen codes with the very IEEE
+// operations of the level kernels (residual_vq.py:232-233):
+//   r_0 = x;  q_l = live ? (training_l ? fl(r_l + fl(c_l - r_l)) : c_l) : r_l;  out = fl(..fl(fl(0 + q_0) + q_1)..);
+//   r_{l+1} = fl(r_l - q_l)
+// The level passes then do not read-modify-write `out` (2 x 4d bytes per row and level): one pass at the end reads x
+// and writes out once; the Q code rows per latent come from L2 (the codebooks of a ResidualVQ are small).
+constexpr int kMaxReplayLevels = 32;
+struct ReplayArgs {
+  const float* cb[kMaxReplayLevels];        // (K,d) codebook each level GATHERED from (before its EMA refresh)
+  const int64_t* idx[kMaxReplayLevels];     // (N,)
+  int training[kMaxReplayLevels];
+  int Q;
+};
+template <int VEC>     // float4 groups per lane: d <= 128 * VEC
+__global__ void __launch_bounds__(kGatherThreads)
+rvq_replay_out_kernel(const float* __restrict__ x, const uint8_t* __restrict__ mask, float* __restrict__ out,
+                      int64_t N, int d, const __grid_constant__ ReplayArgs A) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int wpb = kGatherThreads / 32;
+  for (int64_t row = (int64_t)blockIdx.x * wpb + warp; row < N; row += (int64_t)gridDim.x * wpb) {
+    const bool live = mask == nullptr || mask[row] != 0;
+    float4 r[VEC], acc[VEC];
+#pragma unroll
+    for (int t = 0; t < VEC; ++t) {
+      const int j = lane * 4 + 128 * t;
+      r[t] = j < d ? __ldcs(reinterpret_cast<const float4*>(x + row * (int64_t)d + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      acc[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    // lane l fetches level l's code id: the Q index loads are in flight together, only the code rows are chained
+    const long long my_k = lane < A.Q ? (long long)A.idx[lane][row] : 0ll;
+    float4 cnext[VEC];                   // code row of the next level: loaded while this level is computed
+    {
+      const float* cr = A.cb[0] + __shfl_sync(0xffffffffu, my_k, 0) * (int64_t)d;
+#pragma unroll
+      for (int t = 0; t < VEC; ++t) {
+        const int j = lane * 4 + 128 * t;
+        cnext[t] = j < d ? __ldg(reinterpret_cast<const float4*>(cr + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    for (int l = 0; l < A.Q; ++l) {
+      float4 ccur[VEC];
+#pragma unroll
+      for (int t = 0; t < VEC; ++t) ccur[t] = cnext[t];
+      if (l + 1 < A.Q) {
+        const float* cr = A.cb[l + 1] + __shfl_sync(0xffffffffu, my_k, l + 1) * (int64_t)d;
+#pragma unroll
+        for (int t = 0; t < VEC; ++t) {
+          const int j = lane * 4 + 128 * t;
+          if (j < d) cnext[t] = __ldg(reinterpret_cast<const float4*>(cr + j));
+        }
+      }
+      const bool tr = A.training[l] != 0;
+#pragma unroll
+      for (int t = 0; t < VEC; ++t) {
+        const int j = lane * 4 + 128 * t;
+        if (j >= d) continue;
+        const float4 c = ccur[t];
+        const float4 v = r[t];
+        float4 qv;
+        if (!live) qv = v;
+        else if (tr) qv = make_float4(__fadd_rn(v.x, __fsub_rn(c.x, v.x)), __fadd_rn(v.y, __fsub_rn(c.y, v.y)),
+                                      __fadd_rn(v.z, __fsub_rn(c.z, v.z)), __fadd_rn(v.w, __fsub_rn(c.w, v.w)));
+        else qv = c;
+        const float4 p = acc[t];             // level 0: fl(0.0f + q), as the level kernels do
+        acc[t] = make_float4(__fadd_rn(p.x, qv.x), __fadd_rn(p.y, qv.y), __fadd_rn(p.z, qv.z), __fadd_rn(p.w, qv.w));
+        r[t] = make_float4(__fsub_rn(v.x, qv.x), __fsub_rn(v.y, qv.y), __fsub_rn(v.z, qv.z), __fsub_rn(v.w, qv.w));
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < VEC; ++t) {
+      const int j = lane * 4 + 128 * t;
+      if (j < d) __stcs(reinterpret_cast<float4*>(out + row * (int64_t)d + j), acc[t]);
+    }
+  }
+}
+
 }  // namespace vqb
 
 using namespace vqb;
@@ -436,7 +515,7 @@ extern "C" int vqb_rvq_level(const float* residual_in, float* residual_out, cons
                              float* quantized_out, float* q_out, float* loss_out, int64_t N, int K, int d,
                              void* gather_ws, size_t gather_ws_bytes, void* next_ws, size_t next_ws_bytes,
                              const void* next_cache, void* stream) {
-  VQB_REQUIRE(residual_in && residual_out && codebook && idx && quantized_out && loss_out && gather_ws,
+  VQB_REQUIRE(residual_in && residual_out && codebook && idx && loss_out && gather_ws,
               VQB_ERR_INVALID, "vqb_rvq_level: null pointer");
   GatherLayout L = gather_layout();
   VQB_REQUIRE(gather_ws_bytes >= L.total, VQB_ERR_WORKSPACE, "gather workspace too small");
@@ -472,6 +551,32 @@ extern "C" int vqb_rvq_level(const float* residual_in, float* residual_out, cons
     VQB_LAUNCH_CHECK();
   }
   loss_finalize_kernel<<<1, 256, 0, st>>>(part, cntp, N > 0 ? grid : 0, d, loss_out);
+  VQB_LAUNCH_CHECK();
+  return VQB_OK;
+}
+
+extern "C" int vqb_rvq_replay_out_supported(int d, int num_levels) {
+  return (d > 0 && d % 4 == 0 && d <= 512 && num_levels >= 1 && num_levels <= kMaxReplayLevels) ? 1 : 0;
+}
+
+extern "C" int vqb_rvq_replay_out(const float* x, const float* const* codebooks, const int64_t* const* idx,
+                                  const int* training, int num_levels, const uint8_t* mask, float* out, int64_t N,
+                                  int d, void* stream) {
+  VQB_REQUIRE(x && codebooks && idx && training && out, VQB_ERR_INVALID, "vqb_rvq_replay_out: null pointer");
+  VQB_REQUIRE(vqb_rvq_replay_out_supported(d, num_levels), VQB_ERR_UNSUPPORTED,
+              "vqb_rvq_replay_out: d=%d (multiple of 4, <= 512), levels=%d (<= %d)", d, num_levels, kMaxReplayLevels);
+  if (N <= 0) return VQB_OK;
+  ReplayArgs A = {};
+  A.Q = num_levels;
+  for (int l = 0; l < num_levels; ++l) {
+    VQB_REQUIRE(codebooks[l] && idx[l], VQB_ERR_INVALID, "vqb_rvq_replay_out: null level pointer");
+    A.cb[l] = codebooks[l]; A.idx[l] = idx[l]; A.training[l] = training[l];
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = gather_grid(N);
+  if (d <= 128) rvq_replay_out_kernel<1><<<grid, kGatherThreads, 0, st>>>(x, mask, out, N, d, A);
+  else if (d <= 256) rvq_replay_out_kernel<2><<<grid, kGatherThreads, 0, st>>>(x, mask, out, N, d, A);
+  else rvq_replay_out_kernel<4><<<grid, kGatherThreads, 0, st>>>(x, mask, out, N, d, A);
   VQB_LAUNCH_CHECK();
   return VQB_OK;
 }

@@ -121,13 +121,19 @@ __device__ __forceinline__ void load_cands(const uint2* __restrict__ cand, int64
 
 // phase 1, one thread per row, pure streaming: accept the unique candidate, or queue the row for the
 // warp-per-row re-rank (phase 2), or flag it for the exact rescan
+// SCORE (the caller wants the exact score of every row: sharded codebooks merge (score, index) keys across GPUs): a row
+// with a single candidate evaluates that one exact score right here -- same functions, same fma order as the pair
+// scorer -- instead of going through the queue: with every row queued the one-atomic-per-row append of
+// rerank_emit_kernel alone cost 5 ms for the 4M rows of config 5.
+template <typename T, bool SCORE>
 __global__ void __launch_bounds__(256)
 resolve_classify_kernel(const uint2* __restrict__ cand, const float* __restrict__ err, int64_t H, int64_t N, int K,
-                        int Kp, int64_t idx_offset, int want_score, int64_t* __restrict__ idx_out,
+                        int Kp, int64_t idx_offset, int64_t* __restrict__ idx_out,
                         int* __restrict__ rr_list, int* __restrict__ flag_list, uint32_t* __restrict__ flag_cnt,
                         unsigned long long* __restrict__ keys, uint32_t* __restrict__ scal,
                         const float* __restrict__ xinv, const float* __restrict__ chdr, int aug,
-                        const float* __restrict__ xn2, float tie) {
+                        const float* __restrict__ xn2, float tie, const T* __restrict__ x,
+                        const float* __restrict__ cb, int d, int metric, float* __restrict__ score_out) {
   const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   bool queue = false;
   if (gid < H * N) {
@@ -142,8 +148,13 @@ resolve_classify_kernel(const uint2* __restrict__ cand, const float* __restrict_
       const uint32_t pos = atomicAdd(flag_cnt + h, 1u);
       flag_list[h * N + pos] = (int)(gid - h * N);
       keys[gid] = ~0ull;                      // min-key accumulator of the K-split rescan
-    } else if (R.ncand == 1 && !R.local_rescan && !want_score) {
+    } else if (R.ncand == 1 && !R.local_rescan) {
       idx_out[gid] = (int64_t)R.c1 + idx_offset;
+      if (SCORE) {
+        const T* xr = x + gid * (int64_t)d;
+        const double n2 = metric == VQB_EUCLID ? row_norm2<T>(xr, d) : 0.0;
+        score_out[gid] = exact_score<T>(xr, cb + (h * K + (int64_t)R.c1) * d, d, metric, n2);
+      }
     } else {
       queue = true;
       keys[gid] = ~0ull;                      // min-key accumulator of the pair scoring
@@ -514,14 +525,21 @@ extern "C" int vqb_search(const void* x, int x_dtype, const float* codebook, con
   if (rc) return rc;
   const int64_t total = H * N;
   int* rr_list = (int*)(w + SL.off_rr);
-  resolve_classify_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
-      (const uint2*)(w + SL.off_cand), err, H, N, K, CL.Kp, idx_offset, score_out != nullptr, idx_out, rr_list,
-      flag_list, cnt, keys, scal, xinv, chdr, aug, xn2, tie);
+  if (score_out) {
+    VQB_DISPATCH_DTYPE(x_dtype, T,
+      (resolve_classify_kernel<T, true><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
+          (const uint2*)(w + SL.off_cand), err, H, N, K, CL.Kp, idx_offset, idx_out, rr_list, flag_list, cnt, keys, scal,
+          xinv, chdr, aug, xn2, tie, (const T*)x, codebook, d, metric, score_out)));
+  } else {
+    resolve_classify_kernel<float, false><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
+        (const uint2*)(w + SL.off_cand), err, H, N, K, CL.Kp, idx_offset, idx_out, rr_list, flag_list, cnt, keys, scal,
+        xinv, chdr, aug, xn2, tie, nullptr, codebook, d, metric, nullptr);
+  }
   VQB_LAUNCH_CHECK();
   {
     uint2* pairs = (uint2*)(w + SL.off_pairs);
     const uint32_t pair_cap = (uint32_t)(SL.pair_cap < 0xffffff00ull ? SL.pair_cap : 0xffffff00ull);
-    int64_t want = score_out ? (total + 7) / 8 : (total / 16 + 7) / 8 + 1;   // blocks of 8 warps
+    int64_t want = (total / 16 + 7) / 8 + 1;   // blocks of 8 warps
     const int64_t cap = (int64_t)num_sms() * 8;
     const int grid_rr = (int)(want < cap ? want : cap);
     rerank_emit_kernel<<<grid_rr, 256, 0, st>>>((const uint2*)(w + SL.off_cand), err, N, K, CL.Kp, rr_list, scal, aug,
@@ -531,7 +549,7 @@ extern "C" int vqb_search(const void* x, int x_dtype, const float* codebook, con
     VQB_LAUNCH_CHECK();
     flag_emit_kernel<<<dim3(64, (unsigned)H), 256, 0, st>>>(flag_list, cnt, plan, N, K, pairs);
     VQB_LAUNCH_CHECK();
-    int64_t wantp = score_out ? (total + 255) / 256 : (total / 8 + 255) / 256 + 1;
+    int64_t wantp = (total / 8 + 255) / 256 + 1;
     const int grid_ps = (int)(wantp < cap ? wantp : cap);
     VQB_DISPATCH_DTYPE(x_dtype, T,
       pair_score_kernel<T><<<grid_ps, 256, 0, st>>>((const T*)x, codebook, pairs, scal, pair_cap, total, N, K, d, metric,

@@ -408,6 +408,32 @@ def rvq_level(residual: torch.Tensor, residual_next: torch.Tensor, embeddings: t
     return loss
 
 
+def rvq_replay_out_supported(d: int, num_levels: int) -> bool:
+    return bool(L.lib().vqb_rvq_replay_out_supported(int(d), int(num_levels)))
+
+
+@_on_device
+def rvq_replay_out(x: torch.Tensor, codebooks, idxs, training, mask_u8: Optional[torch.Tensor],
+                   out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Sum of the levels' outputs of a ResidualVQ forward (what `quantized_out` accumulates level by level), replayed
+    bit-exactly from the level-0 input x (N,d) fp32, the (K,d) codebook each level gathered from and its (N,) indices."""
+    import ctypes as C
+    L.require_cuda(x, "x")
+    assert x.dtype == torch.float32 and x.ndim == 2
+    N, d = x.shape
+    Q = len(codebooks)
+    keep = [c.contiguous() for c in codebooks] + [i.contiguous() for i in idxs]
+    cbp = (C.c_void_p * Q)(*[L.ptr(c) for c in keep[:Q]])
+    ixp = (C.c_void_p * Q)(*[L.ptr(i) for i in keep[Q:]])
+    trp = (C.c_int * Q)(*[int(bool(t)) for t in training])
+    if out is None:
+        out = torch.empty((N, d), dtype=torch.float32, device=x.device)
+    L.check(L.lib().vqb_rvq_replay_out(L.ptr(x), C.cast(cbp, C.c_void_p), C.cast(ixp, C.c_void_p),
+                                       C.cast(trp, C.c_void_p), Q, L.ptr(mask_u8), L.ptr(out), N, d,
+                                       L.stream_ptr(x.device)), "vqb_rvq_replay_out")
+    return out
+
+
 def rvq_level_ema_supported(d: int) -> bool:
     return bool(L.lib().vqb_rvq_level_ema_supported(int(d)))
 

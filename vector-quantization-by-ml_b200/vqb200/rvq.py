@@ -91,15 +91,26 @@ class ResidualVQ(nn.Module):
 
     @torch.no_grad()
     def _forward_fused(self, x, mask, freeze_codebook):
+        out, all_idx, all_loss, late = self._fused_levels(x, mask, freeze_codebook)
+        self._fused_expiry(late, mask)
+        return out, all_idx, all_loss
+
+    @torch.no_grad()
+    def _fused_levels(self, x, mask, freeze_codebook):
+        """Everything of the fused level loop that needs no host round trip (capturable in a CUDA graph)."""
         B, n, d = x.shape
         N = B * n
         dev = x.device
         # level 0 reads the input itself (never written: every level writes its residual to another buffer)
         x0 = _lib.aligned(x.reshape(N, d).float())
         bufs = [torch.empty((N, d), dtype=torch.float32, device=dev) for _ in range(min(2, len(self.layers)))]
-        out = torch.empty((N, d), dtype=torch.float32, device=dev)
         all_idx, all_loss = [], []
         Q = len(self.layers)
+        # `quantized_out` (residual_vq.py:233) is not accumulated level by level -- that is a read-modify-write of an
+        # (N,d) buffer in every level pass -- but replayed once at the end from x and the indices with the same IEEE
+        # operations (vqb_rvq_replay_out): bit-identical, 2 x 4d bytes per row and level less HBM traffic
+        replay = Q >= 2 and ops.rvq_replay_out_supported(d, Q)
+        out = None if replay else torch.empty((N, d), dtype=torch.float32, device=dev)
         prepared = False
         # Dead-code check (reference codebooks.py:245-252) costs one host sync per level (0.75 ms of an 8.8 ms C4 step).
         # A level's codebook is not read again in this forward unless it is shared, so the checks of all levels are
@@ -124,7 +135,7 @@ class ResidualVQ(nn.Module):
             idx, _, ws = ops.search(flat, emb, cb._codebook_cache(), cb.use_cosine_sim, latents_prepared=prepared)
             training = self.training and layer.training
             do_ema = training and cb.ema_update and not freeze_codebook
-            if defer:       # the codebook the gather uses (the EMA refresh below overwrites it in place)
+            if defer or replay:   # the codebook the gather uses (the EMA refresh below overwrites it in place)
                 pre_emb.append((emb.clone() if do_ema else emb, training))
             # the next level's operands are prepared in the same pass when its codebook cache is already final:
             # a different codebook object (not shared) that is initialised
@@ -155,24 +166,79 @@ class ResidualVQ(nn.Module):
                 loss = loss + loss_buf[0] * layer.commitment_weight
             all_idx.append(idx.reshape(B, n))
             all_loss.append(loss)
-        if pending:
-            dead = torch.stack([p[2] for p in pending]).tolist()        # the one host sync
-            if any(dead):
-                live = None if mask is None else books[0]._expand_mask(mask, N).bool()[:, None]
-                r, at = x0, 0
-                for (li, cb, _), m in zip(pending, dead):
-                    if not m:
-                        continue
-                    while at < li:                                       # replay levels at .. li-1 on the residual
-                        e, tr = pre_emb[at]
-                        cq = e[0][all_idx[at].reshape(-1)]
-                        q = r + (cq - r) if tr else cq
-                        if live is not None:
-                            q = torch.where(live, q, r)
-                        r = r - q
-                        at += 1
-                    cb.expire_codes_(r[None])
-        return out.reshape(B, n, d), all_idx, all_loss
+        if replay:
+            out = ops.rvq_replay_out(x0, [e[0] for e, _ in pre_emb], [i.reshape(-1) for i in all_idx],
+                                     [tr for _, tr in pre_emb], books[0]._expand_mask(mask, N))
+        dead_counts = torch.stack([p[2] for p in pending]) if pending else None
+        late = (pending, dead_counts, x0, pre_emb, all_idx)
+        return out.reshape(B, n, d), all_idx, all_loss, late
+
+    @torch.no_grad()
+    def _fused_expiry(self, late, mask):
+        """The deferred dead-code checks of all levels: ONE host sync, then (rarely) the replay described above."""
+        pending, dead_counts, x0, pre_emb, all_idx = late
+        if not pending:
+            return
+        dead = dead_counts.tolist()                                      # the one host sync
+        if not any(dead):
+            return
+        N = x0.shape[0]
+        live = None if mask is None else pending[0][1]._expand_mask(mask, N).bool()[:, None]
+        r, at = x0, 0
+        for (li, cb, _), m in zip(pending, dead):
+            if not m:
+                continue
+            while at < li:                                               # replay levels at .. li-1 on the residual
+                e, tr = pre_emb[at]
+                cq = e[0][all_idx[at].reshape(-1)]
+                q = r + (cq - r) if tr else cq
+                if live is not None:
+                    q = torch.where(live, q, r)
+                r = r - q
+                at += 1
+            cb.expire_codes_(r[None])
+
+    # ------------------------------------------------------------------ CUDA graph of the fused level loop (opt-in)
+    def enable_cuda_graph(self, flag: bool = True, max_graphs: int = 4) -> "ResidualVQ":
+        """Replay the fused level loop (~25 launches per level) as ONE CUDA graph per (input address, shape, mode).
+        Opt-in because graph outputs are STATIC buffers: the tensors returned by a forward are overwritten by the next
+        forward on the same input address (clone what must survive).  The first forward on a new input address runs
+        eagerly, the second captures, later ones replay; the dead-code check stays outside the graph (one host sync
+        per forward, as in eager mode).  Not used while a codebook still needs its kmeans init, with a mask, with
+        quantize-dropout, a shared codebook, or while `ops.TIME_SEARCH_KERNEL` brackets kernels with events."""
+        self._graph_on = bool(flag)
+        self._graph_max = int(max_graphs)
+        self._graphs = {}
+        return self
+
+    def _graph_usable(self, x, mask) -> bool:
+        if not getattr(self, "_graph_on", False) or mask is not None or ops.TIME_SEARCH_KERNEL:
+            return False
+        books = [l._codebook for l in self.layers]
+        return len({id(b) for b in books}) == len(books) and all(b.is_initialized and not b.sharded for b in books)
+
+    def _forward_graphed(self, x, freeze_codebook):
+        key = (x.data_ptr(), tuple(x.shape), x.dtype, bool(freeze_codebook), self.training, x.device.index)
+        ent = self._graphs.get(key)
+        if ent is None:
+            if len(self._graphs) >= self._graph_max:
+                return self._forward_fused(x, None, freeze_codebook)
+            self._graphs[key] = "warm"                      # this forward is the eager warm-up of the key
+            return self._forward_fused(x, None, freeze_codebook)
+        if ent == "warm":
+            g = torch.cuda.CUDAGraph()
+            for layer in self.layers:       # the graph must ALWAYS rebuild the search operands of the codebooks: what
+                layer._codebook._dirty = True   # python decides during capture is what every replay does
+            torch.cuda.synchronize(x.device)
+            with torch.cuda.graph(g):
+                res = self._fused_levels(x, None, freeze_codebook)
+            ent = self._graphs[key] = (g, res, x)           # `x` kept alive: its address is baked into the graph
+        g, (out, all_idx, all_loss, late), _ = ent
+        g.replay()
+        for layer in self.layers:                           # the replayed EMA refresh changed `embeddings` in place
+            layer._codebook._dirty = True
+        self._fused_expiry(late, None)
+        return out, all_idx, all_loss
 
     # ------------------------------------------------------------------ forward (reference :134-269)
     def forward(self, x, mask=None, indices=None, return_all_codes=False, freeze_codebook=False,
@@ -201,7 +267,10 @@ class ResidualVQ(nn.Module):
             null_loss = torch.full((1,), 0.0, device=device, dtype=x.dtype)
 
         if self._can_fuse(x, should_dropout):
-            quantized_out, all_indices, all_losses = self._forward_fused(x, mask, freeze_codebook)
+            if self._graph_usable(x, mask):
+                quantized_out, all_indices, all_losses = self._forward_graphed(x, freeze_codebook)
+            else:
+                quantized_out, all_indices, all_losses = self._forward_fused(x, mask, freeze_codebook)
         else:
             quantized_out = 0.0
             residual = x
