@@ -266,6 +266,21 @@ int vqb_dense_backward(const void* x, int x_dtype, const float* xn2, const float
                        const int64_t* target, const float* table, const float* rdot, int64_t n_pos, float* grad_x,
                        int64_t H, int64_t N, int K, int d, void* stream);
 
+/* Stochastic sampling of the code (GumbelParams.stochastic; reference utils/general.py:107-129 at codebooks.py:388):
+ *   idx_out (H,N) = argmax_k ( fl(s_k / temperature) + g_k ),  g = -log(-log(u)) with log(t) = ln(max(t, 1e-5)),
+ * first maximum on ties, as one more epilogue of the tiled fp32 score pass (no N x K tensor in HBM).
+ * The uniforms u (H,N,K) are either given (`uniforms`, fp32 in [0,1)) or generated in place: Philox4x32-10 laid out as
+ * ATen's CUDA `uniform_` on a tensor of H*N*K elements launched with `philox_threads` threads (256 * grid), generator
+ * state (philox_seed, philox_offset): the very numbers `torch.zeros_like(similarities).uniform_(0, 1)` draws. */
+int vqb_dense_gumbel_sample(const void* x, int x_dtype, const float* xn2, const float* codebook, const float* cn2,
+                            int metric, float temperature, const float* uniforms, uint64_t philox_seed,
+                            uint64_t philox_offset, uint32_t philox_threads, int64_t* idx_out, int64_t H, int64_t N,
+                            int K, int d, void* stream);
+/* scores_out (H,N,K) fp32 = the reference's `similarities` (codebooks.py:386), materialised on request only (the third
+ * return value of Codebook.forward, codebooks.py:433-435). */
+int vqb_dense_scores(const void* x, int x_dtype, const float* xn2, const float* codebook, const float* cn2, int metric,
+                     float* scores_out, int64_t H, int64_t N, int K, int d, void* stream);
+
 /* codebook side of vqb_dense_backward (learnable codebook: codebooks.py:375-377 leaves `embeddings` attached to the
  * similarities): grad_c[k] = c_k sum_n rho_nk - sum_n rho_nk x_n with the same weights.  Writes n_splits partial sums
  * grad_c_partial (n_splits,H,K,d) over disjoint sets of latent tiles, n_splits = vqb_dense_backward_codes_splits(...);

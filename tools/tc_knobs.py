@@ -7,7 +7,9 @@ from vqb200 import ops
 dev = torch.device("cuda:0")
 N, K, d = (int(a) for a in sys.argv[1:4]) if len(sys.argv) > 3 else (1 << 20, 8192, 256)
 g = torch.Generator(device=dev).manual_seed(0)
-x = torch.randn(1, N, d, generator=g, device=dev).bfloat16()
+x = torch.randn(1, N, d, generator=g, device=dev)
+if not (len(sys.argv) > 4 and sys.argv[4] == "f32"):
+    x = x.bfloat16()
 c = torch.randn(1, K, d, generator=g, device=dev) * 0.5
 cache = ops.prepare_codebook(c, False)
 ops.TIME_SEARCH_KERNEL = True
@@ -32,5 +34,5 @@ if cy[3]:
     print(f"                          epi warp total {f(cy[7])} wait tmem_full {f(cy[8])} wait bias {f(cy[9])} tmem ld wait {f(cy[10])} try tmem_full {f(cy[11])}")
 if buf[0] + buf[1]:
     print(f"   ranked chunks {buf[0]}  skipped {buf[1]}  -> ranked fraction {buf[0] / (buf[0] + buf[1]):.3f}")
-print(f"VQB_CLUSTER={os.environ.get('VQB_CLUSTER','-')} VQB_TC_DEBUG={os.environ.get('VQB_TC_DEBUG','0')} N={N} K={K} d={d}: "
+print(f"VQB_DRAIN={os.environ.get('VQB_DRAIN','-')} VQB_CLUSTER={os.environ.get('VQB_CLUSTER','-')} VQB_TC_DEBUG={os.environ.get('VQB_TC_DEBUG','0')} N={N} K={K} d={d}: "
       f"tc kernel {ms:.3f} ms  {2*N*K*d/ms/1e9:.0f} TFLOP/s", flush=True)

@@ -575,6 +575,119 @@ __global__ void __launch_bounds__(kThreads) dense_backward_codes_kernel(
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Stochastic (gumbel) sampling of the code, reference utils/general.py:107-129 called at codebooks.py:388:
+//   ind = argmax_k ( fl(s_k / temperature) + g_k ),   g = -log(-log(u)),  log(t) = ln(max(t, 1e-5)),  u ~ U[0,1)
+// as one more epilogue of the tiled score pass: neither the N x K similarities nor the N x K noise exist in HBM.
+// The uniforms are either read from a caller-provided (H,N,K) tensor (tests: the draw a fixture was recorded with)
+// or generated in place with Philox4x32-10 in the layout of ATen's `uniform_` CUDA kernel for a tensor of H*N*K
+// elements (distribution_elementwise_grid_stride_kernel, unroll 4, T = 256 * grid threads): element `li` is output
+// (li / T) % 4 of the ((li / T) / 4)-th curand_uniform4 call of thread li % T, i.e. of the Philox block
+// ctr = {offset/4 + (li / T) / 4, subsequence = li % T}, key = seed.  With the generator's (seed, offset) and the same T
+// the kernel draws exactly what `torch.zeros_like(similarities).uniform_(0, 1)` would have drawn.
+// ---------------------------------------------------------------------------------------------------------------
+struct Philox {
+  unsigned long long seed, offset4;   // generator seed, philox offset / 4
+  unsigned int T;                     // threads of the equivalent ATen launch (0: read `u` instead)
+};
+
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+  constexpr unsigned int kA = 0xD2511F53u, kB = 0xCD9E8D57u, kW0 = 0x9E3779B9u, kW1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const unsigned int hi0 = __umulhi(kA, c.x), lo0 = kA * c.x;
+    const unsigned int hi1 = __umulhi(kB, c.z), lo1 = kB * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    k.x += kW0; k.y += kW1;
+  }
+  return c;
+}
+
+__device__ __forceinline__ float philox_uniform(const Philox& P, unsigned long long li) {
+  const unsigned long long q = li / P.T;
+  const unsigned int sub = (unsigned int)(li - q * P.T);
+  const unsigned long long blk = P.offset4 + (q >> 2);
+  const uint4 r = philox4x32_10(make_uint4((unsigned int)blk, (unsigned int)(blk >> 32), sub, 0u),
+                                make_uint2((unsigned int)P.seed, (unsigned int)(P.seed >> 32)));
+  const unsigned int w = (q & 3) == 0 ? r.x : ((q & 3) == 1 ? r.y : ((q & 3) == 2 ? r.z : r.w));
+  // curand_uniform: (0, 1];  ATen's uniform_(0, 1) maps 1.0 to 0.0
+  const float v = fmaf((float)w, 2.3283064e-10f, 2.3283064e-10f / 2.0f);
+  return v == 1.0f ? 0.0f : v;
+}
+
+__device__ __forceinline__ float gumbel_of(float u) {
+  const float a = logf(fmaxf(u, 1e-5f));
+  return -logf(fmaxf(-a, 1e-5f));
+}
+
+// MODE 0: sample (idx_out);  MODE 1: write the similarities (scores_out (H,N,K) -- the opt-in third return value of
+// Codebook.forward, codebooks.py:433-435)                                              grid (ceil(N/64), H)
+template <typename T, int MODE, int BKT>
+__global__ void __launch_bounds__(kThreads) dense_sample_kernel(
+    const T* __restrict__ x, const float* __restrict__ xn2, const float* __restrict__ cb, const float* __restrict__ cn2,
+    int metric, float temperature, const float* __restrict__ u, const Philox P, int64_t* __restrict__ idx_out,
+    float* __restrict__ scores_out, int64_t N, int K, int d, int vec) {
+  __shared__ __align__(16) float pool[2 * BKT * LD];
+  float (*As)[LD] = reinterpret_cast<float (*)[LD]>(pool);
+  float (*Bs)[LD] = reinterpret_cast<float (*)[LD]>(pool + BKT * LD);
+  __shared__ float s_xn2[BM], s_cn2[BN];
+  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+  const int64_t h = blockIdx.y, row0 = (int64_t)blockIdx.x * BM;
+  const T* x_h = x + h * N * d;
+  const float* cb_h = cb + h * (int64_t)K * d;
+  if (tid < BM) {
+    const int64_t row = row0 + tid;
+    s_xn2[tid] = (row < N && xn2 != nullptr) ? xn2[h * N + row] : 0.f;
+  }
+  float best[4];
+  int bidx[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { best[i] = neg_inf(); bidx[i] = 0x7fffffff; }
+
+  for (int64_t col0 = 0; col0 < K; col0 += BN) {
+    __syncthreads();
+    if (tid < BN) s_cn2[tid] = (cn2 != nullptr && col0 + tid < K) ? cn2[h * K + col0 + tid] : 0.f;
+    float acc[4][4];
+    score_tile<BKT, T, float>(x_h, row0, N, cb_h, col0, K, d, vec != 0, As, Bs, acc);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = ty * 4 + i;
+      const int64_t row = row0 + r;
+      if (row >= N) continue;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int64_t col = col0 + tx * 4 + j;
+        if (col >= K) continue;
+        const float sc = sim_of(acc[i][j], s_xn2[r], s_cn2[tx * 4 + j], metric);
+        const unsigned long long li = (unsigned long long)((h * N + row) * (int64_t)K + col);
+        if (MODE == 1) {
+          scores_out[li] = sc;
+        } else {
+          const float uu = P.T ? philox_uniform(P, li) : __ldg(u + li);
+          const float v = __fadd_rn(__fdiv_rn(sc, temperature), gumbel_of(uu));
+          // first maximum wins (torch.argmax); columns are visited in increasing order per thread
+          if (v > best[i] || (v == best[i] && (int)col < bidx[i]) || bidx[i] == 0x7fffffff) { best[i] = v; bidx[i] = (int)col; }
+        }
+      }
+    }
+  }
+  if (MODE == 1) return;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float bv = best[i];
+    int bi = bidx[i];
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (oi != 0x7fffffff && (bi == 0x7fffffff || ov > bv || (ov == bv && oi < bi))) { bv = ov; bi = oi; }
+    }
+    const int64_t row = row0 + ty * 4 + i;
+    if (tx == 0 && row < N) idx_out[h * N + row] = (int64_t)bi;
+  }
+}
+
 int check_common(const void* x, const void* cb, int64_t H, int64_t N, int K, int d, int metric) {
   VQB_REQUIRE((x != nullptr || N == 0) && cb != nullptr, VQB_ERR_INVALID, "dense: null pointer");
   VQB_REQUIRE(H >= 1 && H <= 65535 && N >= 0 && K >= 1 && d >= 1, VQB_ERR_INVALID,
@@ -765,6 +878,48 @@ extern "C" int vqb_dense_backward_codes(const void* x, int x_dtype, const float*
     if (nsub == 1) { VQB_DENSE_BWDC(1, 16); } else if (nsub == 2) { VQB_DENSE_BWDC(2, 16); } else { VQB_DENSE_BWDC(4, 16); }
   }
 #undef VQB_DENSE_BWDC
+  VQB_LAUNCH_CHECK();
+  return VQB_OK;
+}
+
+
+extern "C" int vqb_dense_gumbel_sample(const void* x, int x_dtype, const float* xn2, const float* codebook,
+                                       const float* cn2, int metric, float temperature, const float* uniforms,
+                                       uint64_t philox_seed, uint64_t philox_offset, uint32_t philox_threads,
+                                       int64_t* idx_out, int64_t H, int64_t N, int K, int d, void* stream) {
+  if (int rc = check_common(x, codebook, H, N, K, d, metric)) return rc;
+  VQB_REQUIRE(idx_out != nullptr || N == 0, VQB_ERR_INVALID, "vqb_dense_gumbel_sample: idx_out is null");
+  VQB_REQUIRE(temperature > 0.f, VQB_ERR_INVALID, "vqb_dense_gumbel_sample: temperature must be > 0");
+  VQB_REQUIRE(uniforms != nullptr || philox_threads > 0, VQB_ERR_INVALID,
+              "vqb_dense_gumbel_sample: pass the uniforms or the Philox stream (seed, offset, threads)");
+  VQB_REQUIRE(philox_offset % 4 == 0, VQB_ERR_INVALID, "vqb_dense_gumbel_sample: philox offset must be a multiple of 4");
+  VQB_REQUIRE(metric == VQB_DOT || N == 0 || (xn2 != nullptr && cn2 != nullptr), VQB_ERR_INVALID,
+              "vqb_dense_gumbel_sample: the Euclidean metric needs the row norms");
+  if (N == 0) return VQB_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const dim3 grid((unsigned)((N + BM - 1) / BM), (unsigned)H);
+  const int vec = vec_ok(x, codebook, codebook, d);
+  Philox P;
+  P.seed = philox_seed; P.offset4 = philox_offset / 4; P.T = uniforms ? 0u : philox_threads;
+  VQB_DISPATCH_DTYPE(x_dtype, T, (dense_sample_kernel<T, 0, 16><<<grid, kThreads, 0, st>>>(
+      (const T*)x, xn2, codebook, cn2, metric, temperature, uniforms, P, idx_out, nullptr, N, K, d, vec)));
+  VQB_LAUNCH_CHECK();
+  return VQB_OK;
+}
+
+extern "C" int vqb_dense_scores(const void* x, int x_dtype, const float* xn2, const float* codebook, const float* cn2,
+                                int metric, float* scores_out, int64_t H, int64_t N, int K, int d, void* stream) {
+  if (int rc = check_common(x, codebook, H, N, K, d, metric)) return rc;
+  VQB_REQUIRE(scores_out != nullptr || N == 0, VQB_ERR_INVALID, "vqb_dense_scores: scores_out is null");
+  VQB_REQUIRE(metric == VQB_DOT || N == 0 || (xn2 != nullptr && cn2 != nullptr), VQB_ERR_INVALID,
+              "vqb_dense_scores: the Euclidean metric needs the row norms");
+  if (N == 0) return VQB_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const dim3 grid((unsigned)((N + BM - 1) / BM), (unsigned)H);
+  const int vec = vec_ok(x, codebook, codebook, d);
+  Philox P = {};
+  VQB_DISPATCH_DTYPE(x_dtype, T, (dense_sample_kernel<T, 1, 16><<<grid, kThreads, 0, st>>>(
+      (const T*)x, xn2, codebook, cn2, metric, 1.f, nullptr, P, nullptr, scores_out, N, K, d, vec)));
   VQB_LAUNCH_CHECK();
   return VQB_OK;
 }
