@@ -224,6 +224,13 @@ int    vqb_rvq_replay_out(const float* x, const float* const* codebooks, const i
                           const int* training, int num_levels, const uint8_t* mask, float* out, int64_t N, int d,
                           void* stream);
 
+/* Column moments of the latents for the affine re-parametrisation (reference codebooks.py:300-347, `use_affine`):
+ * sums_out (H,d,2) fp64 = per codebook and column {sum, sum of squares} over the rows with mask != 0 (mask (N) u8,
+ * nullable), rows_used_out (H) int64 = rows counted; one pass over x, fp64 accumulation.  mean = sum / n,
+ * biased variance = sumsq / n - mean^2 (what torch.var(unbiased=False) returns, to fp32 rounding). */
+int    vqb_column_moments(const void* x, int x_dtype, const uint8_t* mask, int64_t H, int64_t N, int d,
+                          double* sums_out, int64_t* rows_used_out, void* stream);
+
 /* ---- sharded-codebook merge (K >= 64K split across GPUs) ------------------------------
  * No reference counterpart.  key = (orderable(score) << 32) | index, so an
  * all_reduce(MIN) over uint64 (as int64 with the sign bit clear) picks the smallest score and,

@@ -119,6 +119,28 @@ def rvq_replay_out(x, codebooks, idxs, training, mask_u8, out=None):
     return acc
 
 
+def dense_gumbel_sample(x, emb, use_cosine_sim, temperature, uniforms=None, generator=None):
+    """vqb_dense_gumbel_sample with the reference's own torch calls (utils/general.py:107-129)."""
+    sim = torch.einsum("hnd,hcd->hnc", x.float(), emb) if use_cosine_sim else -torch.cdist(x.float(), emb)
+    u = uniforms.reshape(sim.shape) if uniforms is not None else torch.zeros_like(sim).uniform_(0, 1)
+    g = -torch.log((-torch.log(u.clamp(min=1e-5))).clamp(min=1e-5))
+    return (sim / temperature + g).argmax(dim=-1)
+
+
+def dense_scores(x, emb, use_cosine_sim):
+    return torch.einsum("hnd,hcd->hnc", x.float(), emb) if use_cosine_sim else -torch.cdist(x.float(), emb)
+
+
+def column_moments(x, mask_u8):
+    xd = x.double()
+    if mask_u8 is not None:
+        xd = xd * mask_u8.bool()[None, :, None]
+        rows = torch.full((x.shape[0],), int(mask_u8.bool().sum()), dtype=torch.int64)
+    else:
+        rows = torch.full((x.shape[0],), x.shape[1], dtype=torch.int64)
+    return torch.stack([xd.sum(dim=1), (xd * xd).sum(dim=1)], dim=-1), rows
+
+
 def minkey_pack(score, idx):
     """(orderable fp32 score << 32) | index as int64: smaller score first, lowest index on ties (vqb_minkey_pack)."""
     u = score.contiguous().view(torch.int32).to(torch.int64) & 0xFFFFFFFF
@@ -144,11 +166,18 @@ def ema_apply_sharded(stats, cluster_size, embed_avg, embeddings, weight, eps, w
     embeddings.copy_(F.normalize(new, dim=-1) if weights_l2norm else new)
 
 
+REPLACED = ("prepare_codebook", "search", "l2norm_rows", "gather_st_loss", "st_commit_backward", "ema_reduce",
+            "ema_apply", "expire_scatter", "minkey_pack", "minkey_unpack", "ema_apply_sharded", "rvq_level",
+            "rvq_level_ema", "rvq_replay_out", "dense_gumbel_sample", "dense_scores", "column_moments",
+            "l2norm_prepare_supported", "quantize_ema_supported", "rvq_level_ema_supported",
+            "rvq_replay_out_supported")
+
+
 def install(ops, lib):
     """Replace the wrappers on the `vqb200.ops` module object and the device guard of `vqb200._lib`."""
     for name in ("prepare_codebook", "search", "l2norm_rows", "gather_st_loss", "st_commit_backward", "ema_reduce",
                  "ema_apply", "expire_scatter", "minkey_pack", "minkey_unpack", "ema_apply_sharded", "rvq_level", "rvq_level_ema",
-                 "rvq_replay_out"):
+                 "rvq_replay_out", "dense_gumbel_sample", "dense_scores", "column_moments"):
         setattr(ops, name, globals()[name])
     ops.l2norm_prepare_supported = lambda d: False
     ops.quantize_ema_supported = lambda d: False

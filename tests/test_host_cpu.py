@@ -94,14 +94,22 @@ def test_no_cpu_fallback_and_unsupported_options_fail_loudly():
         vq(torch.randn(1, 3, 8))
     cb = Codebook(8, 4, learnable_codebook=True, ema_update=False)       # supported: embeddings is a Parameter
     assert isinstance(cb.embeddings, torch.nn.Parameter) and "embeddings" in cb.state_dict()
-    with pytest.raises(NotImplementedError):
-        Codebook(8, 4, use_affine=True)
-    with pytest.raises(NotImplementedError):
-        Codebook(8, 4, gumbel_params=GumbelParams(stochastic=True))
+    with pytest.raises(ValueError):
+        Codebook(8, 4, use_affine=True)            # needs affine_params (the reference dereferences None later)
+    from vqb200.params import AffineParameters
+    aff = Codebook(8, 4, use_affine=True, affine_params=AffineParameters(sync=False))
+    assert {"codebook_mean", "codebook_variance", "codebook_mean_needs_init"} <= set(aff.state_dict())
+    cbg = Codebook(8, 4, gumbel_params=GumbelParams(stochastic=True, temperature=0.5))
+    assert cbg._variants_active() and cbg._variant_sampling() == (True, False)
+    assert not Codebook(8, 4, gumbel_params=GumbelParams(stochastic=True, temperature=0.0))._variants_active()
+    with pytest.raises(RuntimeError, match="CUDA"):  # the variants have no CPU implementation either
+        cbg(torch.randn(1, 3, 8))
     with pytest.raises(ValueError):
         Codebook(8, 4, transform_input="tanh")
-    with pytest.raises(NotImplementedError):
-        VectorQuantize(dim=8, codebook_params=CodebookParams(dim=8, codebook_size=4), orthogonal_reg_weight=1.0)
+    vqorth = VectorQuantize(dim=8, codebook_params=CodebookParams(dim=8, codebook_size=4), orthogonal_reg_weight=1.0)
+    # reference :95-102: the orthogonal loss makes the codebook a Parameter; the EMA update stays on
+    assert isinstance(vqorth._codebook.embeddings, torch.nn.Parameter) and vqorth._codebook.ema_update
+    assert not vqorth._codebook.commit_grad_to_codebook
     # in_place_codebook_optimizer: a factory over the codebook's parameters, so it needs a learnable codebook
     # (with the default EMA codebook torch raises on the empty parameter list, as in the reference)
     with pytest.raises(ValueError):

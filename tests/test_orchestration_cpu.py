@@ -18,11 +18,7 @@ def _cpu_draw(num_rows, m, device):
 @pytest.fixture()
 def cpu_ops(monkeypatch):
     from vqb200 import _lib, codebook, ops
-    saved = {n: getattr(ops, n) for n in ("prepare_codebook", "search", "l2norm_rows", "gather_st_loss",
-                                          "st_commit_backward", "ema_reduce", "ema_apply", "expire_scatter",
-                                          "l2norm_prepare_supported", "quantize_ema_supported", "rvq_level",
-                                          "rvq_level_ema", "rvq_level_ema_supported", "minkey_pack", "minkey_unpack",
-                                          "ema_apply_sharded")}
+    saved = {n: getattr(ops, n) for n in cpu_kernels.REPLACED}
     saved_guard = _lib.require_device
     cpu_kernels.install(ops, _lib)
     monkeypatch.setattr(codebook.Codebook, "_draw_rows", staticmethod(_cpu_draw))

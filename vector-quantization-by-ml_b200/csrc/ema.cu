@@ -590,6 +590,39 @@ inline FusedLayout fused_layout(int64_t H, int64_t N, int K, int d) {
 }
 inline bool fused_width_ok(int d) { return d == 512 || (d >= 8 && d <= 256 && (d & (d - 1)) == 0); }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Column moments of the latents (affine re-parametrisation, reference codebooks.py:300-347: batch mean and biased
+// variance over the rows of each codebook's batch): per (h, column) sum and sum of squares over the rows with
+// mask != 0, accumulated in fp64 in ONE pass over the latents.  out (H, d, 2) fp64 must be zero; rows_used (H) int64.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kMomentRows = 256;          // rows per block
+template <typename T>
+__global__ void __launch_bounds__(256)
+column_moments_kernel(const T* __restrict__ x, const uint8_t* __restrict__ mask, int64_t N, int d,
+                      double* __restrict__ out, long long* __restrict__ rows_used) {
+  const int h = blockIdx.y;
+  const int64_t r0 = (int64_t)blockIdx.x * kMomentRows;
+  const int64_t r1 = r0 + kMomentRows < N ? r0 + kMomentRows : N;
+  const T* xh = x + (int64_t)h * N * d;
+  for (int c = threadIdx.x; c < d; c += blockDim.x) {
+    double s = 0.0, ss = 0.0;
+    for (int64_t r = r0; r < r1; ++r) {
+      if (mask && !mask[r]) continue;
+      const double v = (double)to_f32<T>(xh[r * d + c]);
+      s += v;
+      ss = fma(v, v, ss);
+    }
+    atomicAdd(out + ((int64_t)h * d + c) * 2, s);
+    atomicAdd(out + ((int64_t)h * d + c) * 2 + 1, ss);
+  }
+  if (threadIdx.x == 0) {
+    long long n = 0;
+    for (int64_t r = r0; r < r1; ++r) n += (!mask || mask[r]) ? 1 : 0;
+    atomicAdd(reinterpret_cast<unsigned long long*>(rows_used + h), (unsigned long long)n);
+  }
+}
+
 // --- apply ------------------------------------------------------------------------------------------
 __device__ __forceinline__ float torch_lerp(float a, float b, float w) {
   // ATen lerp: |w| < 0.5 ? a + w*(b-a) : b - (b-a)*(1-w), evaluated with one fma (both the CPU vector
@@ -987,6 +1020,21 @@ extern "C" int vqb_minkey_unpack(const int64_t* keys, int64_t n, int64_t* idx, f
   if (n == 0) return VQB_OK;
   minkey_unpack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const long long*)keys, n, idx,
                                                                                        score);
+  VQB_LAUNCH_CHECK();
+  return VQB_OK;
+}
+
+extern "C" int vqb_column_moments(const void* x, int x_dtype, const uint8_t* mask, int64_t H, int64_t N, int d,
+                                  double* sums_out, int64_t* rows_used_out, void* stream) {
+  VQB_REQUIRE(H >= 1 && H <= 65535 && N >= 0 && d >= 1, VQB_ERR_INVALID, "vqb_column_moments: bad shape");
+  VQB_REQUIRE(sums_out && rows_used_out && (x || N == 0), VQB_ERR_INVALID, "vqb_column_moments: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  VQB_CUDA_TRY(cudaMemsetAsync(sums_out, 0, (size_t)H * d * 2 * sizeof(double), st));
+  VQB_CUDA_TRY(cudaMemsetAsync(rows_used_out, 0, (size_t)H * sizeof(int64_t), st));
+  if (N == 0) return VQB_OK;
+  const dim3 grid((unsigned)((N + kMomentRows - 1) / kMomentRows), (unsigned)H);
+  VQB_DISPATCH_DTYPE(x_dtype, T, (column_moments_kernel<T><<<grid, 256, 0, st>>>(
+      (const T*)x, mask, N, d, sums_out, (long long*)rows_used_out)));
   VQB_LAUNCH_CHECK();
   return VQB_OK;
 }

@@ -3,10 +3,19 @@
 Same constructor, same persistent buffers (``embeddings`` (H,K,d), ``embed_avg`` (H,K,d),
 ``cluster_size`` (H,K), fp32) and the same ``forward(x, mask, freeze_codebook)`` contract;
 the numeric work (search, gather, EMA statistics, refresh, expiry scatter) runs in
-libvqb200.so.  Options that are off the named hot path (affine re-parametrisation,
-stochastic gumbel sampling) raise NotImplementedError -- there is
-no silent fallback.  ``learnable_codebook=True`` makes ``embeddings`` a Parameter that receives the gradient
+libvqb200.so.  ``learnable_codebook=True`` makes ``embeddings`` a Parameter that receives the gradient
 of the commitment loss / of the gathered codes (a segmented sum over the rows of each code).
+
+Variants off the named hot path take `_run_variants` (same kernels, no fused passes):
+  * gumbel sampling (reference utils/general.py:107-151, codebooks.py:388): `stochastic` = argmax of
+    similarities / temperature + gumbel noise as an epilogue of the tiled fp32 score pass (vqb_dense_gumbel_sample;
+    the noise is generated in the kernel from torch's Philox stream, no N x K tensor exists);
+    `straight_through` / `reinmax` change only the GRADIENT through the one-hot (their forward value is the hard
+    one-hot to 2^-24), which the reference drops unless the codebook is learnable or `Codebook.forward` is used
+    directly under autograd -- that corner runs the reference's formulas as row-chunked torch ops (library code, not
+    kernels of this package);
+  * affine re-parametrisation (codebooks.py:274-348,373-384,400-403): batch moments from one fp64 pass over the latents
+    (vqb_column_moments), search / gather on the transformed codebook, EMA sums transformed per code instead of per row.
 """
 from __future__ import annotations
 
@@ -46,12 +55,11 @@ class Codebook(nn.Module):
             if val not in ("identity", "l2norm"):
                 # the reference does `raise f"..."` here (a TypeError); keep the intent, not the bug
                 raise ValueError(f"The option {val} for {name} is not implemented")
-        if use_affine:
-            raise NotImplementedError("vqb200: use_affine is outside the accelerated EMA path")
         gp = asdict(gumbel_params) if is_dataclass(gumbel_params) else dict(gumbel_params)
-        if gp.get("stochastic") or gp.get("straight_through") or gp.get("reinmax"):
-            raise NotImplementedError("vqb200: stochastic / straight-through gumbel sampling is outside the "
-                                      "accelerated path (deterministic argmax only)")
+        # reference codebooks.py:154-158: `sample_fn_training` (the only one forward() calls) = gumbel_sample(**params)
+        self.gumbel = {"temperature": 1.0, "stochastic": False, "reinmax": False, "straight_through": False, "dim": -1,
+                       "training": True, **gp}
+        self._uniform_queue: list = []       # tests: the (H,N,K) draws a fixture was recorded with, in call order
 
         self.input_l2norm = transform_input == "l2norm"
         self.weights_l2norm = weights_regularization == "l2norm"
@@ -73,7 +81,16 @@ class Codebook(nn.Module):
         self._kmeans_sync = bool((self.kmeans_params or {"sync": True})["sync"])
         self.distributed_replace_codes = distributed_replace_codes
         self.learnable_codebook = bool(learnable_codebook)
-        self.use_affine = False
+        # VectorQuantize clears this when ITS learnable_codebook is off while the codebook is a Parameter only because of
+        # the orthogonal regularisation (reference vector_quantize_pytorch.py:99-104,262-268: commit_quantize is detached)
+        self.commit_grad_to_codebook = True
+        self.return_similarities = False       # opt in to the dense (H, ..., K) third return value of forward()
+        self._sim: Optional[torch.Tensor] = None
+        self.use_affine = bool(use_affine)
+        if self.use_affine:
+            if affine_params is None:
+                raise ValueError("vqb200.Codebook: use_affine=True needs affine_params")
+            self.affine_params = asdict(affine_params) if is_dataclass(affine_params) else dict(affine_params)
 
         init = torch.zeros(num_codebooks, codebook_size, dim) if initialization_by_kmeans else \
             _uniform_init(num_codebooks, codebook_size, dim)
@@ -97,8 +114,9 @@ class Codebook(nn.Module):
         self._replica: Optional[torch.Tensor] = None
         self._replica_dirty = True
         if self.sharded:
-            if learnable_codebook:
-                raise NotImplementedError("vqb200: a sharded codebook (>= %d codes under a process group) is EMA-only"
+            if learnable_codebook or self.use_affine or any(self._variant_sampling()):
+                raise NotImplementedError("vqb200: a sharded codebook (>= %d codes under a process group) is EMA-only "
+                                          "with deterministic sampling and no affine re-parametrisation"
                                           % D.SHARD_MIN_CODES)
             lo = self.shard_rank * self.shard_size
             init = init[:, lo:lo + self.shard_size].contiguous()
@@ -111,6 +129,14 @@ class Codebook(nn.Module):
             self.embeddings = nn.Parameter(init)
         else:
             self.register_buffer("embeddings", init)
+
+        if self.use_affine:                    # reference codebooks.py:194-206, same buffer names
+            self.register_buffer("batch_mean", None)
+            self.register_buffer("batch_variance", None)
+            self.register_buffer("codebook_mean_needs_init", torch.Tensor([True]))
+            self.register_buffer("codebook_mean", torch.empty(num_codebooks, 1, dim))
+            self.register_buffer("codebook_variance_needs_init", torch.Tensor([True]))
+            self.register_buffer("codebook_variance", torch.empty(num_codebooks, 1, dim))
 
         # derived, non-persistent: scaled fp16 copy + norms for the tensor-core search
         self._cache: Optional[torch.Tensor] = None
@@ -429,6 +455,186 @@ class Codebook(nn.Module):
                 self._expire_codes_sharded(rows_all)
         return quant.reshape(H, *lead, d), gidx.reshape(H, *lead), commit
 
+    # ------------------------------------------------------------------ variants: gumbel sampling, affine
+    def _variant_sampling(self):
+        """(stochastic, straight_through) as reference gumbel_sample applies them (utils/general.py:121-137)."""
+        g = self.gumbel
+        active = bool(g["training"]) and g["temperature"] > 0
+        return (active and bool(g["stochastic"])), (active and bool(g["straight_through"]))
+
+    def _variants_active(self) -> bool:
+        stochastic, st = self._variant_sampling()
+        return self.use_affine or stochastic or st
+
+    def _update_with_decay(self, name: str, new_value: torch.Tensor, decay: float) -> None:
+        # reference codebooks.py:258-272
+        old = getattr(self, name)
+        needs_init = getattr(self, name + "_needs_init", None)
+        first = needs_init is not None and bool(needs_init.item())
+        if first:
+            needs_init.fill_(0.0)
+        if old is None or first:
+            setattr(self, name, new_value.detach().clone())
+            return
+        setattr(self, name, old * decay + new_value.detach() * (1 - decay))
+
+    @torch.no_grad()
+    def _update_affine(self, flat: torch.Tensor, mask_u8: Optional[torch.Tensor]) -> None:
+        """reference codebooks.py:274-348.  The batch moments come from ONE fp64 pass over the latents; with
+        `affine_params.sync` the per-rank sums are all-reduced (mean and variance of the union of the batches, as the
+        reference's three all_reduce calls compute)."""
+        ap = self.affine_params
+        emb = self.embeddings.detach()
+        if self.training:
+            self._update_with_decay("codebook_mean", emb.mean(dim=1, keepdim=True), ap["codebook_decay"])
+            self._update_with_decay("codebook_variance", emb.var(dim=1, unbiased=False, keepdim=True),
+                                    ap["codebook_decay"])
+        sums, rows = ops.column_moments(flat.detach(), mask_u8)
+        if ap["sync"]:
+            from . import distributed as D
+            packed = torch.cat([sums.reshape(-1), rows.double()])
+            D.all_reduce_sum(packed)
+            sums, rows = packed[:sums.numel()].reshape(sums.shape), packed[sums.numel():]
+        n = rows.double()[:, None]
+        mean = sums[..., 0] / n
+        var = (sums[..., 1] / n - mean * mean).clamp_min(0.0)
+        self._update_with_decay("batch_mean", mean.float()[:, None, :], ap["batch_decay"])
+        self._update_with_decay("batch_variance", var.float()[:, None, :], ap["batch_decay"])
+
+    def _gumbel_st_quantize(self, flat: torch.Tensor, emb_g: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+        """quantize = one_hot' @ embeddings with the straight-through / reinmax one-hot of reference
+        utils/general.py:139-149, as torch ops under autograd (library code): only the gradient through the one-hot
+        differs from a gather.  Row-chunked (bounds the size of each temporary, not the total the graph keeps);
+        `reinmax` cannot be chunked because the reference normalises `prob1` over dim=1 -- the ROW axis of (h, n, c) --
+        which couples all rows.  No recomputation in backward: with an EMA codebook `emb_g` aliases the live buffer,
+        which this forward's EMA step overwrites in place before backward runs -- the reference's graph has exactly that
+        aliasing (its saved `embeddings.detach()` shares the buffer's storage, codebooks.py:375-377,425), so the same
+        torch ops on the same alias reproduce its gradient: pre-update distances and probabilities, post-update code
+        vectors."""
+        import torch.nn.functional as F
+        g = self.gumbel
+        tau, K, cos = float(g["temperature"]), emb_g.shape[1], self.use_cosine_sim
+
+        def log_eps(t):
+            return t.clamp(min=1e-5).log()
+
+        def piece(xc, e, ic):
+            xc = xc.float()
+            logits = torch.einsum("hnd,hcd->hnc", xc, e) if cos else -torch.cdist(xc, e)
+            one_hot = F.one_hot(ic, K).type(logits.dtype)
+            if g["reinmax"]:
+                prob0 = logits.softmax(dim=-1)
+                prob1 = (one_hot + (logits / tau).softmax(dim=-1)) / 2
+                prob1 = ((log_eps(prob1) - logits).detach() + logits).softmax(dim=1)
+                prob2 = 2 * prob1 - 0.5 * prob0
+                one_hot = prob2 - prob2.detach() + one_hot
+            else:
+                prob1 = (logits / tau).softmax(dim=-1)
+                one_hot = one_hot + prob1 - prob1.detach()
+            return torch.einsum("hnc,hcd->hnd", one_hot, e)
+
+        N = flat.shape[1]
+        rows = N if g["reinmax"] else max(1, (1 << 24) // max(K, 1))
+        if rows >= N:
+            return piece(flat, emb_g, idx)
+        outs = [piece(flat[:, lo:lo + rows], emb_g, idx[:, lo:lo + rows]) for lo in range(0, N, rows)]
+        return torch.cat(outs, dim=1)
+
+    def _run_variants(self, x, mask, freeze_codebook, fuse_st, want_commit, normalize_input, keep_dense):
+        """`_run` with the affine re-parametrisation and / or gumbel sampling (see the module docstring): the same
+        kernels, un-fused; returns what `_run` returns."""
+        g = self.gumbel
+        assert not (g["reinmax"] and not g["straight_through"]), \
+            "reinmax can only be turned on if using straight through gumbel softmax"
+        _lib.require_device(x)
+        flat, lead = self._flatten(x)
+        H, N, d = flat.shape
+        K = self.codebook_size
+        if H != self.num_codebooks or d != self.embeddings.shape[-1]:
+            raise ValueError(f"vqb200.Codebook: input {tuple(x.shape)} does not match codebook "
+                             f"{tuple(self.embeddings.shape)}")
+        mask_u8 = self._expand_mask(mask, N)
+        if normalize_input:
+            flat = ops.l2norm_rows_autograd(flat) if (torch.is_grad_enabled() and flat.requires_grad) \
+                else ops.l2norm_rows(flat)
+        if not self.is_initialized:
+            self._kmeans_init(flat, mask_u8)
+            self.is_initialized = True
+
+        training = self.training
+        update = training and self.ema_update and not freeze_codebook
+        grad_on = torch.is_grad_enabled()
+        emb_param = self.embeddings if (self.learnable_codebook and self.commit_grad_to_codebook and training
+                                        and not freeze_codebook and grad_on and self.embeddings.requires_grad) else None
+        base = emb_param if emb_param is not None else self.embeddings.detach()
+        inv_scale = cm = bm = None
+        if self.use_affine:
+            self._update_affine(flat, mask_u8)
+            codebook_std = self.codebook_variance.clamp(min=1e-5).sqrt()
+            batch_std = self.batch_variance.clamp(min=1e-5).sqrt()
+            cm, bm, inv_scale = self.codebook_mean, self.batch_mean, codebook_std / batch_std
+            emb_eff = (base - cm) * (batch_std / codebook_std) + bm          # reference :381-384
+        else:
+            emb_eff = base
+        emb_val = emb_eff.detach().contiguous()
+        if update and emb_val.data_ptr() == self.embeddings.data_ptr() and (keep_dense or (grad_on and flat.requires_grad)):
+            emb_val = emb_val.clone()          # backward reads the PRE-update codes (see _run)
+        if keep_dense:
+            self.dense_ctx = ops._DenseCtx(flat, emb_val, emb_val if self.use_affine else self.embeddings,
+                                           self.use_cosine_sim)
+
+        stochastic, st = self._variant_sampling()
+        x_det = flat.detach()
+        if stochastic:
+            u = self._uniform_queue.pop(0) if self._uniform_queue else None
+            idx = ops.dense_gumbel_sample(x_det, emb_val, self.use_cosine_sim, float(g["temperature"]), uniforms=u)
+            self.last_search_ws = None
+        else:
+            cache = ops.prepare_codebook(emb_val, self.use_cosine_sim) if self.use_affine else self._codebook_cache()
+            idx, _, ws = ops.search(x_det, emb_val, cache, self.use_cosine_sim)
+            self.last_search_ws = ws
+        if self.return_similarities and not fuse_st:
+            self._sim = ops.dense_scores(x_det, emb_val, self.use_cosine_sim)
+
+        commit = None
+        wants_x = grad_on and flat.requires_grad
+        need_graph = st and training and grad_on and (emb_param is not None if fuse_st
+                                                      else (wants_x or emb_param is not None))
+        if need_graph:
+            emb_graph = emb_eff if (emb_param is not None or self.use_affine) else self.embeddings.detach()
+            q_graph = self._gumbel_st_quantize(flat, emb_graph, idx)
+            if fuse_st:     # reference vector_quantize_pytorch.py:262-273,335-362 with commit_quantize attached
+                xf = flat.float()
+                if want_commit:
+                    per = (q_graph - xf) ** 2
+                    commit = per[:, mask_u8.bool()].mean() if mask_u8 is not None else per.mean()
+                quant = xf + (q_graph - xf).detach()
+            else:
+                quant = q_graph
+        elif fuse_st and training:
+            quant, commit, _ = ops.quantize_training(flat, emb_val if emb_param is None else emb_eff.contiguous(), idx,
+                                                     mask_u8, want_commit)
+        elif emb_param is not None:
+            quant = ops.gather_codes(emb_eff.contiguous(), idx)
+        else:
+            with torch.no_grad():
+                quant, _ = ops.gather_st_loss(x_det, emb_val, idx, None, False, False)
+
+        if update:
+            with torch.no_grad():
+                stats = ops.ema_reduce(x_det, idx, mask_u8, K)
+                if self.use_affine:
+                    # reference :400-403 transforms every latent, (x - batch_mean) * (codebook_std / batch_std) +
+                    # codebook_mean, before the sums; the map is affine, so the per-code sums transform the same way
+                    cnt = stats[..., d:]
+                    stats[..., :d] = (stats[..., :d] - cnt * bm) * inv_scale + cnt * cm
+                self._all_reduce(stats)
+                ops.ema_apply(stats, self.cluster_size.data, self.embed_avg.data, self.embeddings.data,
+                              1 - self.decay, self.eps_for_smoothing, self.weights_l2norm)
+                self._dirty = True
+                self.expire_codes_(x_det)
+        return quant.reshape(H, *lead, d), idx.reshape(H, *lead), commit
+
     # ------------------------------------------------------------------ core
     def _run(self, x: torch.Tensor, mask: Optional[torch.Tensor], freeze_codebook: bool, fuse_st: bool,
              want_commit: bool, normalize_input: bool = False, keep_dense: bool = False):
@@ -440,6 +646,8 @@ class Codebook(nn.Module):
             if keep_dense:
                 raise NotImplementedError("vqb200: the dense-similarity losses are not available on a sharded codebook")
             return self._run_sharded(x, mask, freeze_codebook, fuse_st, want_commit, normalize_input)
+        if self._variants_active():
+            return self._run_variants(x, mask, freeze_codebook, fuse_st, want_commit, normalize_input, keep_dense)
         _lib.require_device(x)        # raises for a CPU tensor: there is no CPU implementation
         flat, lead = self._flatten(x)
         H, N, d = flat.shape
@@ -477,14 +685,17 @@ class Codebook(nn.Module):
             self.dense_ctx = ops._DenseCtx(flat, emb, self.embeddings, self.use_cosine_sim)
         idx, _, ws = ops.search(flat, emb, self._codebook_cache(), self.use_cosine_sim, latents_prepared=prepared)
         self.last_search_ws = ws
+        if self.return_similarities and not fuse_st:
+            self._sim = ops.dense_scores(flat.detach(), emb, self.use_cosine_sim)   # before the EMA step, as :386
 
         training = self.training
         commit = None
         update = training and self.ema_update and not freeze_codebook
         # learnable codebook (reference codebooks.py:375-377, vector_quantize_pytorch.py:262-268): the commitment loss
         # and the gathered codes are differentiable with respect to `embeddings`
-        emb_param = self.embeddings if (self.learnable_codebook and training and not freeze_codebook
-                                        and torch.is_grad_enabled() and self.embeddings.requires_grad) else None
+        emb_param = self.embeddings if (self.learnable_codebook and self.commit_grad_to_codebook and training
+                                        and not freeze_codebook and torch.is_grad_enabled()
+                                        and self.embeddings.requires_grad) else None
         # un-masked training step: gather/ST/loss and the EMA sums share ONE pass over the latents
         fused = update and mask_u8 is None and self.fused_quantize_ema and ops.quantize_ema_supported(d) \
             and emb_param is None
@@ -517,15 +728,21 @@ class Codebook(nn.Module):
 
     @torch.amp.autocast(device_type="cuda", enabled=False)
     def forward(self, x, mask=None, freeze_codebook=False):
-        """reference codebooks.py:350-435.  Returns (quantize, embed_ind, similarities) with
-        similarities=None: the N x K matrix is never materialised on this path."""
+        """reference codebooks.py:350-435.  Returns (quantize, embed_ind, similarities).  `similarities` is None unless
+        `self.return_similarities` is set: the (H, ..., K) matrix is not needed by anything on this path and is only
+        materialised on request (one extra fp32 score pass, vqb_dense_scores); like the reference's it keeps the leading
+        codebook axis even when the input had none (:431-433)."""
         needs_codebook_dim = x.ndim < 4
         if needs_codebook_dim:
             x = x[None]
+        self._sim = None
         quant, ind, _ = self._run(x, mask, freeze_codebook, fuse_st=False, want_commit=False)
+        sim, self._sim = self._sim, None
+        if sim is not None:
+            sim = sim.reshape(*ind.shape, sim.shape[-1])
         if needs_codebook_dim:
             quant, ind = quant[0], ind[0]
-        return quant, ind, None
+        return quant, ind, sim
 
 
 class EuclideanCodebook(Codebook):

@@ -638,3 +638,90 @@ class _DenseAvgProb(torch.autograd.Function):
 
 def dense_avg_prob(dc: "_DenseCtx", n_pos: int, temperature: float, emb_param=None) -> torch.Tensor:
     return _DenseAvgProb.apply(dc.x, emb_param, dc, int(n_pos), -float(temperature))
+
+
+# ---------------------------------------------------------------------------------------------
+# f4 variants: gumbel sampling, materialised similarities, column moments (affine)
+# ---------------------------------------------------------------------------------------------
+def _aten_uniform_launch(numel: int, device: torch.device):
+    """(threads, counter_offset) of ATen's CUDA `uniform_` on `numel` elements (DistributionTemplates.h,
+    calc_execution_policy: block 256, unroll 4, grid = min(SMs * maxThreadsPerSM / 256, ceil(numel / 256)))."""
+    props = torch.cuda.get_device_properties(device)
+    block, unroll = 256, 4
+    grid = (numel + block - 1) // block
+    grid = min(props.multi_processor_count * (props.max_threads_per_multi_processor // block), grid)
+    grid = max(grid, 1)
+    counter_offset = ((numel - 1) // (block * grid * unroll) + 1) * 4
+    return block * grid, counter_offset
+
+
+@_on_device
+def dense_gumbel_sample(x: torch.Tensor, emb: torch.Tensor, use_cosine_sim: bool, temperature: float,
+                        uniforms: Optional[torch.Tensor] = None, generator: Optional[torch.Generator] = None):
+    """idx (H,N) = argmax_k(s_k / temperature - log(-log(u_k))) (reference utils/general.py:107-129).  `uniforms`
+    (H,N,K) fp32 injects the draw; otherwise the kernel generates, in place, the numbers that
+    `torch.zeros(H,N,K, device=...).uniform_(0, 1)` would draw from `generator` (default: the device's default
+    generator) and advances that generator by the same amount (bitwise the same stream while H*N*K < 2^31, where ATen
+    uses one launch)."""
+    L.require_cuda(x, "x")
+    H, N, d = x.shape
+    K = emb.shape[1]
+    dev = x.device
+    xn2 = None if use_cosine_sim else dense_row_norms(x)
+    cn2 = None if use_cosine_sim else dense_row_norms(emb)
+    idx = torch.empty((H, N), dtype=torch.int64, device=dev)
+    seed = offset = threads = 0
+    if uniforms is not None:
+        uniforms = uniforms.to(device=dev, dtype=torch.float32).contiguous()
+        assert uniforms.numel() == H * N * K, "uniforms must be (H,N,K)"
+    elif H * N * K > 0:
+        gen = generator if generator is not None else torch.cuda.default_generators[dev.index]
+        threads, counter = _aten_uniform_launch(H * N * K, dev)
+        seed, offset = int(gen.initial_seed()), int(gen.get_offset())
+        gen.set_offset(offset + counter)
+    L.check(L.lib().vqb_dense_gumbel_sample(L.ptr(x), L.dtype_code(x), L.ptr(xn2), L.ptr(emb), L.ptr(cn2),
+                                            _metric(use_cosine_sim), float(temperature), L.ptr(uniforms),
+                                            seed & 0xFFFFFFFFFFFFFFFF, offset, threads, L.ptr(idx), H, N, K, d,
+                                            L.stream_ptr(dev)), "vqb_dense_gumbel_sample")
+    return idx
+
+
+@_on_device
+def dense_scores(x: torch.Tensor, emb: torch.Tensor, use_cosine_sim: bool) -> torch.Tensor:
+    """The reference's `similarities` (H,N,K) fp32, materialised (opt-in third return value of Codebook.forward)."""
+    L.require_cuda(x, "x")
+    H, N, d = x.shape
+    K = emb.shape[1]
+    xn2 = None if use_cosine_sim else dense_row_norms(x)
+    cn2 = None if use_cosine_sim else dense_row_norms(emb)
+    out = torch.empty((H, N, K), dtype=torch.float32, device=x.device)
+    L.check(L.lib().vqb_dense_scores(L.ptr(x), L.dtype_code(x), L.ptr(xn2), L.ptr(emb), L.ptr(cn2),
+                                     _metric(use_cosine_sim), L.ptr(out), H, N, K, d, L.stream_ptr(x.device)),
+            "vqb_dense_scores")
+    return out
+
+
+@_on_device
+def column_moments(x: torch.Tensor, mask_u8: Optional[torch.Tensor]):
+    """x (H,N,d): per codebook and column (sum, sum of squares) fp64 (H,d,2) over the rows with mask != 0, and the
+    number of rows counted (H,) int64 -- one pass (vqb_column_moments)."""
+    L.require_cuda(x, "x")
+    H, N, d = x.shape
+    sums = torch.empty((H, d, 2), dtype=torch.float64, device=x.device)
+    rows = torch.empty((H,), dtype=torch.int64, device=x.device)
+    L.check(L.lib().vqb_column_moments(L.ptr(x), L.dtype_code(x), L.ptr(mask_u8), H, N, d, L.ptr(sums), L.ptr(rows),
+                                       L.stream_ptr(x.device)), "vqb_column_moments")
+    return sums, rows
+
+
+def orthogonal_loss(t: torch.Tensor) -> torch.Tensor:
+    """reference utils/losses.py:22-27 (eq. 2 of arXiv:2112.00384): mean squared cosine similarity between the codes of
+    each codebook, minus 1/n.  sum_ij (n_i . n_j)^2 = |N^T N|_F^2 = |N N^T|_F^2: the smaller of the (d,d) and (n,n) Gram
+    matrices is formed (a K = 65536 codebook never allocates K x K).  Plain library GEMM on codebook-sized operands."""
+    h, n = t.shape[:2]
+    normed = torch.nn.functional.normalize(t, p=2, dim=-1)
+    if t.shape[-1] < n:
+        gram = torch.einsum("hnd,hne->hde", normed, normed)
+    else:
+        gram = torch.einsum("hid,hjd->hij", normed, normed)
+    return (gram ** 2).sum() / (h * n ** 2) - (1 / n)

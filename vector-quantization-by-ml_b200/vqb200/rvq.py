@@ -82,6 +82,8 @@ class ResidualVQ(nn.Module):
             return False        # losses on the dense similarities: the generic per-level loop computes them
         if l0.in_place_codebook_optimizer is not None:
             return False        # the optimizer step inside forward (reference vector_quantize_pytorch.py:233-256)
+        if any(l._codebook._variants_active() or l.has_codebook_orthogonal_loss for l in self.layers):
+            return False        # gumbel sampling / affine / orthogonal loss: the generic per-level loop
         if l0._codebook.learnable_codebook and self.training and torch.is_grad_enabled() and \
                 any(l._codebook.embeddings.requires_grad for l in self.layers):
             # the commitment loss must reach the codebook Parameters (reference :263-269) even when the input carries

@@ -6,9 +6,10 @@ and the EMA update are CUDA kernels behind ``Codebook``.  The consumers of the d
 matrix -- cross-entropy to given indices (reference :284-299), the cross-entropy commitment loss (:338-346)
 and the codebook diversity loss (:324-333) -- run as fp32 online-softmax passes that never write the
 matrix (csrc/dense.cu), forward, input gradient and -- with a learnable codebook -- codebook gradient.
-Orthogonal regularisation (broken in the reference itself) raises NotImplementedError; a learnable codebook
-(`learnable_codebook=True, ema_update=False`, optionally `sync_update_v` and `in_place_codebook_optimizer`)
-is supported.
+A learnable codebook (`learnable_codebook=True, ema_update=False`, optionally `sync_update_v` and
+`in_place_codebook_optimizer`) is supported, and so is the orthogonal regularisation of the codebook (reference
+:366-390, utils/losses.py:22-27; the reference reads the non-existent `_codebook.embed` there and raises
+AttributeError -- implemented on `embeddings`, as SURVEY 8(b) prescribes).
 """
 from __future__ import annotations
 
@@ -62,19 +63,21 @@ class VectorQuantize(nn.Module):
         self.codebook_diversity_temperature = codebook_diversity_temperature
         self.has_codebook_diversity_loss = codebook_diversity_loss_weight > 0.0
 
-        unsupported = []
-        if orthogonal_reg_weight > 0.0:
-            unsupported.append("orthogonal_reg_weight (the reference itself raises AttributeError on this path: "
-                               "vector_quantize_pytorch.py:367 reads the non-existent `_codebook.embed`)")
-        if unsupported:
-            raise NotImplementedError("vqb200.VectorQuantize: outside the accelerated path: " + "; ".join(unsupported))
+        has_codebook_orthogonal_loss = orthogonal_reg_weight > 0.0
+        self.has_codebook_orthogonal_loss = has_codebook_orthogonal_loss
+        self.orthogonal_reg_weight = orthogonal_reg_weight
+        self.orthogonal_reg_active_codes_only = orthogonal_reg_active_codes_only
+        self.orthogonal_reg_max_codes = orthogonal_reg_max_codes
 
         if sync_codebook is None:
             sync_codebook = _is_distributed()
 
+        # reference :95-102: the orthogonal loss needs a gradient to the codebook, so it turns the codebook into a
+        # Parameter even when `learnable_codebook` is off (the EMA update then still runs, through `.data`)
         self.codebook_params = replace(codebook_params, dim=codebook_dim,
                                        num_codebooks=heads if separate_codebook_per_head else 1,
-                                       learnable_codebook=codebook_params.learnable_codebook,
+                                       learnable_codebook=has_codebook_orthogonal_loss
+                                       or codebook_params.learnable_codebook,
                                        use_ddp=sync_codebook)
         self.learnable_codebook = codebook_params.learnable_codebook
         assert not (codebook_params.ema_update and codebook_params.learnable_codebook), \
@@ -84,6 +87,8 @@ class VectorQuantize(nn.Module):
         self.sync_update_v = sync_update_v
         kw = asdict(self.codebook_params)
         self._codebook = Codebook(**kw)
+        # commit_quantize is detached unless VectorQuantize's OWN learnable_codebook is set (reference :262-268)
+        self._codebook.commit_grad_to_codebook = bool(self.learnable_codebook)
         # reference :132-136: an optimizer factory over the codebook's parameters (needs a learnable codebook)
         self.in_place_codebook_optimizer = in_place_codebook_optimizer(self._codebook.parameters()) \
             if in_place_codebook_optimizer is not None else None
@@ -120,6 +125,11 @@ class VectorQuantize(nn.Module):
 
     def get_output_from_indices(self, indices):
         return self.project_out(self.get_codes_from_indices(indices))
+
+    @staticmethod
+    def _draw_perm(n: int, device) -> torch.Tensor:
+        # reference :384: torch.randperm(num_codes, device=device) on the global generator
+        return torch.randperm(n, device=device)
 
     def _rows_of(self, t, B, multi):
         """(b, n[, h]) per-position integers -> the (H, N) row layout of the codebook's latents (reference
@@ -197,7 +207,7 @@ class VectorQuantize(nn.Module):
         self._codebook.dense_ctx = None
         # learnable codebook: the similarities stay attached to `embeddings` (reference codebooks.py:375-377, whatever
         # freeze_codebook says), so the dense losses also send a gradient to the codebook
-        emb_param = self._codebook.embeddings if (self.learnable_codebook and torch.is_grad_enabled()
+        emb_param = self._codebook.embeddings if (self._codebook.learnable_codebook and torch.is_grad_enabled()
                                                   and self._codebook.embeddings.requires_grad) else None
         rows_idx = embed_ind.reshape(embed_ind.shape[0], -1)          # (H, N): the row layout of the dense passes
         if x.ndim < 4:
@@ -212,7 +222,7 @@ class VectorQuantize(nn.Module):
             target = self._rows_of(indices.to(device=device, dtype=torch.int64), B, multi)
             return quantize, ops.dense_cross_entropy(dense, target, emb_param)
 
-        commit_loss = diversity_loss = self.zero
+        commit_loss = diversity_loss = orthogonal_reg_loss = self.zero
         if multi:
             if self.separate_codebook_per_head:
                 embed_ind = embed_ind.permute(1, 2, 0)
@@ -245,6 +255,19 @@ class VectorQuantize(nn.Module):
         elif want_commit:
             commit_loss = commit
             loss = loss + commit_loss * self.commitment_weight
+        if training and self.has_codebook_orthogonal_loss:
+            # reference :366-390 on `embeddings` (K- or d-sized torch glue on the codebook, no latents involved)
+            codebook = self._codebook.embeddings
+            if self.orthogonal_reg_active_codes_only:
+                assert not (multi and self.separate_codebook_per_head), \
+                    "orthogonal regularization for only active codes not compatible with multi-headed with " \
+                    "separate codebooks yet"
+                codebook = codebook[:, torch.unique(embed_ind)]
+            num_codes = codebook.shape[-2]
+            if self.orthogonal_reg_max_codes is not None and num_codes > self.orthogonal_reg_max_codes:
+                codebook = codebook[:, self._draw_perm(num_codes, device)[:self.orthogonal_reg_max_codes]]
+            orthogonal_reg_loss = ops.orthogonal_loss(codebook)
+            loss = loss + orthogonal_reg_loss * self.orthogonal_reg_weight
 
         if multi:
             if self.separate_codebook_per_head:
@@ -264,4 +287,4 @@ class VectorQuantize(nn.Module):
 
         if not return_loss_breakdown:
             return quantize, embed_ind, loss
-        return quantize, embed_ind, loss, LossBreakdown(commit_loss, diversity_loss, self.zero, inplace_loss)
+        return quantize, embed_ind, loss, LossBreakdown(commit_loss, diversity_loss, orthogonal_reg_loss, inplace_loss)
