@@ -596,3 +596,189 @@ def rvq_forward(states: List[CodebookState], x: torch.Tensor, opts: VQOpts, *, t
         all_loss.append(loss)
         all_extras.append(ex)
     return out, torch.stack(all_ind, -1), torch.stack(all_loss, -1), all_extras
+
+
+# --------------------------------------------------------------------------- #
+# f4 variants: gumbel sampling, affine re-parametrisation, orthogonal regularisation.
+# Autograd-carrying restatement on the reference's own torch ops; pinned by tests/golden/f4 (recorded from the live
+# reference by tests/golden/make_golden_f4.py) in tests/test_oracle_f4.py.
+# --------------------------------------------------------------------------- #
+
+def gumbel_noise(u: torch.Tensor) -> torch.Tensor:
+    """utils/general.py:107-109 for a given uniform draw u (the reference draws `zeros_like(t).uniform_(0, 1)`)."""
+    return -_log_eps(-_log_eps(u))
+
+
+def gumbel_sample(logits: torch.Tensor, *, temperature: float = 1.0, stochastic: bool = False,
+                  straight_through: bool = False, reinmax: bool = False, training: bool = True,
+                  uniforms: Optional[torch.Tensor] = None):
+    """utils/general.py:112-151 (dim = -1).  Returns (ind, one_hot); the one-hot carries the straight-through / reinmax
+    graph when those are on.  `uniforms`: the (h,n,c) draw to use instead of a fresh one."""
+    size = logits.shape[-1]
+    if training and stochastic and temperature > 0:                       # :123-126
+        u = uniforms if uniforms is not None else torch.zeros_like(logits).uniform_(0, 1)
+        sampling_logits = (logits / temperature) + gumbel_noise(u)
+    else:
+        sampling_logits = logits
+    ind = sampling_logits.argmax(dim=-1)                                  # :128
+    one_hot = F.one_hot(ind, size).type(logits.dtype)                     # :129
+    assert not (reinmax and not straight_through)                         # :131-133
+    if not straight_through or temperature <= 0.0 or not training:        # :135-136
+        return ind, one_hot
+    if reinmax:                                                           # :141-146 (softmax over dim=1 as written there)
+        prob0 = logits.softmax(dim=-1)
+        prob1 = (one_hot + (logits / temperature).softmax(dim=-1)) / 2
+        prob1 = ((_log_eps(prob1) - logits).detach() + logits).softmax(dim=1)
+        prob2 = 2 * prob1 - 0.5 * prob0
+        one_hot = prob2 - prob2.detach() + one_hot
+    else:                                                                 # :147-149
+        prob1 = (logits / temperature).softmax(dim=-1)
+        one_hot = one_hot + prob1 - prob1.detach()
+    return ind, one_hot
+
+
+def orthogonal_loss(t: torch.Tensor) -> torch.Tensor:
+    """utils/losses.py:22-27."""
+    h, n = t.shape[:2]
+    normed = l2norm(t)
+    cosine_sim = torch.einsum("h i d, h j d -> h i j", normed, normed)
+    return (cosine_sim ** 2).sum() / (h * n ** 2) - (1 / n)
+
+
+@dataclass
+class AffineState:
+    """The affine buffers of reference Codebook (codebooks.py:194-206) + AffineParameters (:31-37)."""
+    sync: bool = False
+    batch_decay: float = 0.99
+    codebook_decay: float = 0.9
+    batch_mean: Optional[torch.Tensor] = None
+    batch_variance: Optional[torch.Tensor] = None
+    codebook_mean: Optional[torch.Tensor] = None
+    codebook_variance: Optional[torch.Tensor] = None
+
+    def _decay(self, name: str, new: torch.Tensor, decay: float) -> None:      # :258-272
+        old = getattr(self, name)
+        setattr(self, name, new.detach() if old is None else old * decay + new.detach() * (1 - decay))
+
+    def update(self, data: torch.Tensor, embeddings: torch.Tensor, training: bool,
+               flat_mask: Optional[torch.Tensor]) -> None:                     # :274-348, sync off / single process
+        if training:
+            self._decay("codebook_mean", embeddings.mean(dim=1, keepdim=True), self.codebook_decay)
+            self._decay("codebook_variance", embeddings.var(dim=1, unbiased=False, keepdim=True), self.codebook_decay)
+        if flat_mask is not None:
+            data = data[flat_mask].reshape(data.shape[0], -1, data.shape[-1])
+        self._decay("batch_mean", data.mean(dim=1, keepdim=True), self.batch_decay)
+        self._decay("batch_variance", data.var(dim=1, unbiased=False, keepdim=True), self.batch_decay)
+
+
+def codebook_forward_variants(state: CodebookState, x: torch.Tensor, opts: CodebookOpts, *, gumbel: Optional[dict] = None,
+                              affine: Optional[AffineState] = None, training: bool = True,
+                              mask: Optional[torch.Tensor] = None, freeze_codebook: bool = False,
+                              learnable: bool = False, uniforms: Optional[torch.Tensor] = None):
+    """reference Codebook.forward (codebooks.py:350-435) with gumbel sampling and the affine re-parametrisation, under
+    autograd.  `state.embeddings` may require grad (`learnable`).  Returns (quantize, ind, similarities) shaped as the
+    reference returns them; mutates `state` (EMA step, expiry) and `affine`."""
+    gumbel = {"training": True, **(gumbel or {})}
+    needs_h = x.ndim < 4
+    x = x.float()
+    if needs_h:
+        x = x.unsqueeze(0)
+    H, d = x.shape[0], x.shape[-1]
+    lead = x.shape[1:-1]
+    flat = x.reshape(H, -1, d)
+    N, K = flat.shape[1], state.embeddings.shape[1]
+    flat_mask = None
+    if mask is not None:
+        rep = N // (mask.shape[0] * mask.shape[1])
+        flat_mask = mask[:, None, :].expand(mask.shape[0], rep, mask.shape[1]).reshape(1, -1).expand(H, -1)
+    if affine is not None:
+        affine.update(flat, state.embeddings.detach(), training, flat_mask)   # :372-373
+    emb = state.embeddings if learnable else state.embeddings.detach()    # :375-377 (an alias of the buffer)
+    codebook_std = batch_std = None
+    if affine is not None:                                                # :379-384
+        codebook_std = affine.codebook_variance.clamp(min=1e-5).sqrt()
+        batch_std = affine.batch_variance.clamp(min=1e-5).sqrt()
+        emb = (emb - affine.codebook_mean) * (batch_std / codebook_std) + affine.batch_mean
+    sim = similarities(flat, emb, opts.use_cosine_sim)                    # :386
+    ind, onehot = gumbel_sample(sim, uniforms=uniforms, **{k: v for k, v in gumbel.items() if k != "dim"})   # :388-390
+    if training:
+        quant = torch.einsum("h n c, h c d -> h n d", onehot, emb)        # :393-395
+    else:
+        quant = emb.gather(1, ind[..., None].expand(-1, -1, d)) if not emb.requires_grad else \
+            torch.stack([emb[h][ind[h]] for h in range(H)], 0)            # :397
+    if training and opts.ema_update and not freeze_codebook:              # :399-426
+        with torch.no_grad():
+            rows = flat.detach()
+            if affine is not None:
+                rows = (rows - affine.batch_mean) * (codebook_std / batch_std) + affine.codebook_mean
+            oh = onehot.detach().clone()
+            if flat_mask is not None:
+                oh[~flat_mask] = 0.0
+            w = 1 - opts.decay
+            state.cluster_size.data.lerp_(oh.sum(dim=1), w)
+            state.embed_avg.data.lerp_(torch.einsum("h n d, h n c -> h c d", rows, oh).contiguous(), w)
+            total = state.cluster_size.sum(dim=-1, keepdim=True)
+            smoothed = (state.cluster_size + opts.eps) / (total + K * opts.eps) * total
+            new_emb = state.embed_avg / smoothed[..., None]
+            if opts.weights_l2norm:
+                new_emb = l2norm(new_emb)
+            state.embeddings.data.copy_(new_emb)                          # in place: graph aliases see the new values
+            expire_codes(state, x.detach(), opts)
+    quant = quant.reshape(H, *lead, d)
+    ind = ind.reshape(H, *lead)
+    if needs_h:
+        quant, ind = quant[0], ind[0]
+    return quant, ind, sim.reshape(H, *lead, K)                           # :431-435
+
+
+def vq_forward_variants(state: CodebookState, x: torch.Tensor, opts: VQOpts, *, gumbel: Optional[dict] = None,
+                        affine: Optional[AffineState] = None, training: bool = True, mask: Optional[torch.Tensor] = None,
+                        learnable: bool = False, codebook_is_parameter: bool = False,
+                        uniforms: Optional[torch.Tensor] = None, orthogonal_reg_weight: float = 0.0,
+                        orthogonal_reg_active_codes_only: bool = False,
+                        orthogonal_reg_max_codes: Optional[int] = None):
+    """VectorQuantize.forward (vector_quantize_pytorch.py:182-430) around `codebook_forward_variants`: channel-last,
+    no projections, shared-codebook heads.  `learnable` is VectorQuantize's own flag (commit_quantize stays attached,
+    :262-268); `codebook_is_parameter` is the Codebook's (the similarities stay attached, codebooks.py:375-377 -- also
+    set by the orthogonal loss alone, :95-102).  Returns (quantize, ind, loss[1], (commit, orthogonal))."""
+    B, n, D = x.shape
+    heads = opts.heads
+    xin = x
+    if heads > 1:                                                         # :213-219 "b n (h d) -> 1 (b h) n d"
+        xin = x.reshape(B, n, heads, D // heads).permute(0, 2, 1, 3).reshape(1, B * heads, n, D // heads)
+    if opts.input_l2norm:
+        xin = l2norm(xin)                                                 # :221
+    quant, ind, _ = codebook_forward_variants(state, xin, opts.codebook, gumbel=gumbel, affine=affine,
+                                              training=training, mask=mask, learnable=codebook_is_parameter,
+                                              uniforms=uniforms)
+    loss = torch.tensor([0.0])
+    commit = orth = torch.tensor(0.0)
+    if training:
+        commit_q = quant if learnable else quant.detach()                 # :262-268
+        quant = xin + (quant - xin).detach()                              # :273
+    if heads > 1:                                                         # :302-308 "1 (b h) n -> b n h"
+        ind = ind.reshape(B, heads, n).permute(0, 2, 1)
+    if training:
+        if opts.commitment_weight > 0:                                    # :335-364
+            if mask is not None:
+                per = F.mse_loss(commit_q, xin.float(), reduction="none")
+                lm = mask if heads == 1 else mask[None, :, None, :].expand(per.shape[0], B, per.shape[1] // B, n) \
+                    .reshape(per.shape[0], per.shape[1], n)
+                commit = per[lm].mean()
+            else:
+                commit = F.mse_loss(commit_q, xin.float())
+            loss = loss + commit * opts.commitment_weight
+        if orthogonal_reg_weight > 0:                                     # :366-390 (on `embeddings`)
+            codebook = state.embeddings
+            if orthogonal_reg_active_codes_only:
+                codebook = codebook[:, torch.unique(ind)]
+            num_codes = codebook.shape[-2]
+            if orthogonal_reg_max_codes is not None and num_codes > orthogonal_reg_max_codes:
+                codebook = codebook[:, torch.randperm(num_codes)[:orthogonal_reg_max_codes]]
+            orth = orthogonal_loss(codebook)
+            loss = loss + orth * orthogonal_reg_weight
+    if heads > 1:                                                         # :394-404 "1 (b h) n d -> b n (h d)"
+        quant = quant.reshape(B, heads, n, D // heads).permute(0, 2, 1, 3).reshape(B, n, D)
+    if mask is not None:
+        quant = torch.where(mask[..., None], quant, x)                    # :415-418
+    return quant, ind, loss, (commit, orth)
