@@ -20,7 +20,7 @@ for r in rows[hi + 1:]:
     ns = v * {"ns": 1, "us": 1e3, "ms": 1e6, "s": 1e9}.get(r[idx["Metric Unit"]], 1)
     L.append((r[idx["Kernel Name"]], ns))
 tc = [i for i, (n, _) in enumerate(L) if "search_aug_kernel" in n or "search_tc_kernel" in n]
-a, b = tc[4], tc[5]                      # one timed step: from the codebook refresh before one search to the next
+a, b = tc[3], tc[4]                      # one timed step: from the codebook refresh before one search to the next
 first = [i for i, (n, _) in enumerate(L) if "codebook_absmax_kernel" in n]
 sa, sb = max(i for i in first if i < a), max(i for i in first if i < b)
 step = L[sa:sb]
@@ -30,7 +30,7 @@ for n, ns in step:
     n = re.sub(r"\(.*", "", n).replace("void ", "")
     agg[n] = agg.get(n, 0) + ns
 kern = [{"name": n, "us": ns / 1e3, "share_pct": 100 * ns / tot} for n, ns in sorted(agg.items(), key=lambda kv: -kv[1])]
-raw = subprocess.run(["ncu", "-i", "gpurun_out/prof_r01.ncu-rep", "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+raw = subprocess.run(["ncu", "-i", f"gpurun_out/prof_{tag}.ncu-rep", "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rr = list(csv.reader(raw.splitlines()))
 h2, units, data = rr[0], rr[1], rr[2:]
 ix = {h: i for i, h in enumerate(h2)}
