@@ -30,8 +30,11 @@ struct EmaLayout {
   size_t zero_bytes;   // counts + cursor + start + scale + acc are zeroed together
   size_t off_sorted;   // i32 [H][N]
   size_t off_total;    // f32 [H]   (ema_apply scratch)
+  size_t off_table;    // u32 [H][kSortBlocks][K]  per-block histograms / offsets of the counting sort (K <= kSortMaxK)
   size_t total;
 };
+constexpr int kSortBlocks = 148;       // one block per SM
+constexpr int kSortMaxK = 12288;       // 48 KB of shared-memory counters per block
 inline EmaLayout ema_layout(int64_t H, int64_t N, int K, int d) {
   EmaLayout L;
   size_t o = 0;
@@ -43,6 +46,7 @@ inline EmaLayout ema_layout(int64_t H, int64_t N, int K, int d) {
   L.zero_bytes = o;
   L.off_sorted = o; o += align_up((size_t)(H * N > 0 ? H * N : 1) * 4);
   L.off_total = o;  o += align_up((size_t)H * 4);
+  L.off_table = o;  o += K <= kSortMaxK ? align_up((size_t)H * kSortBlocks * K * 4) : 0;
   L.total = o;
   return L;
 }
@@ -134,6 +138,97 @@ __global__ void ema_place_kernel(const int64_t* __restrict__ idx, const uint8_t*
   if (k < 0 || k >= K) return;
   const uint32_t pos = start[(int64_t)h * (K + 1) + k] + atomicAdd(cursor + (int64_t)h * K + k, 1u);
   sorted[(int64_t)h * N + pos] = (int)n;
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// Counting sort of the rows by code WITHOUT global atomics (K <= kSortMaxK): block b of kSortBlocks owns a contiguous
+// range of rows; (1) histogram of its rows in shared memory -> table[b][k]; (2) per code, an exclusive prefix over the
+// blocks (table[b][k] becomes the offset of block b inside the code's segment), then the usual exclusive scan over the
+// codes (start[k]); (3) each block places its rows with shared-memory cursors starting at start[k] + table[b][k].
+// The global-atomic form (ema_hist / ema_place: one atomic per row on K addresses) took 45 us of a C2 step and of
+// every C4 level; larger codebooks keep it.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024)
+sort_hist_kernel(const int64_t* __restrict__ idx, const uint8_t* __restrict__ mask, int64_t N, int K,
+                 uint32_t* __restrict__ table) {
+  extern __shared__ uint32_t s_cnt[];
+  const int h = blockIdx.y, b = blockIdx.x, B = gridDim.x;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) s_cnt[k] = 0u;
+  __syncthreads();
+  const int64_t span = (N + B - 1) / B, r0 = (int64_t)b * span, r1 = r0 + span < N ? r0 + span : N;
+  for (int64_t n = r0 + threadIdx.x; n < r1; n += blockDim.x) {
+    if (mask && !mask[n]) continue;
+    const int64_t k = idx[(int64_t)h * N + n];
+    if (k >= 0 && k < K) atomicAdd(s_cnt + k, 1u);
+  }
+  __syncthreads();
+  uint32_t* t = table + ((int64_t)h * B + b) * K;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) t[k] = s_cnt[k];
+}
+
+// one thread per code: table[b][k] -> exclusive prefix over the blocks b; counts[k] = total          grid (ceil(K/256), H)
+__global__ void __launch_bounds__(256)
+sort_prefix_kernel(uint32_t* __restrict__ table, int B, int K, uint32_t* __restrict__ counts) {
+  const int h = blockIdx.y;
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  uint32_t* t = table + (int64_t)h * B * K + k;
+  uint32_t v = 0u;
+  int b = 0;
+  for (; b + 8 <= B; b += 8) {                     // 8 independent loads in flight
+    uint32_t x[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) x[u] = t[(int64_t)(b + u) * K];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { t[(int64_t)(b + u) * K] = v; v += x[u]; }
+  }
+  for (; b < B; ++b) { const uint32_t x = t[(int64_t)b * K]; t[(int64_t)b * K] = v; v += x; }
+  counts[(int64_t)h * K + k] = v;
+}
+
+__global__ void __launch_bounds__(1024)
+sort_place_kernel(const int64_t* __restrict__ idx, const uint8_t* __restrict__ mask, int64_t N, int K,
+                  const uint32_t* __restrict__ start, const uint32_t* __restrict__ table, int* __restrict__ sorted) {
+  extern __shared__ uint32_t s_cur[];
+  const int h = blockIdx.y, b = blockIdx.x, B = gridDim.x;
+  const uint32_t* t = table + ((int64_t)h * B + b) * K;
+  const uint32_t* st = start + (int64_t)h * (K + 1);
+  for (int k = threadIdx.x; k < K; k += blockDim.x) s_cur[k] = st[k] + t[k];
+  __syncthreads();
+  const int64_t span = (N + B - 1) / B, r0 = (int64_t)b * span, r1 = r0 + span < N ? r0 + span : N;
+  for (int64_t n = r0 + threadIdx.x; n < r1; n += blockDim.x) {
+    if (mask && !mask[n]) continue;
+    const int64_t k = idx[(int64_t)h * N + n];
+    if (k < 0 || k >= K) continue;
+    sorted[(int64_t)h * N + atomicAdd(s_cur + k, 1u)] = (int)n;
+  }
+}
+
+// rows of every codebook sorted by code: counts, start (exclusive scan) and the permutation `sorted`
+static int launch_code_sort(const int64_t* idx, const uint8_t* mask, int64_t H, int64_t N, int K, uint32_t* counts,
+                            uint32_t* cursor, uint32_t* start, int* sorted, uint32_t* table, cudaStream_t st) {
+  if (K <= kSortMaxK && table != nullptr && N >= 4096) {
+    const dim3 g((unsigned)kSortBlocks, (unsigned)H);
+    const size_t smem = (size_t)K * 4;
+    sort_hist_kernel<<<g, 1024, smem, st>>>(idx, mask, N, K, table);
+    VQB_LAUNCH_CHECK();
+    sort_prefix_kernel<<<dim3((unsigned)((K + 255) / 256), (unsigned)H), 256, 0, st>>>(table, kSortBlocks, K, counts);
+    VQB_LAUNCH_CHECK();
+    ema_scan_kernel<<<(unsigned)H, 1024, 0, st>>>(counts, K, start);
+    VQB_LAUNCH_CHECK();
+    sort_place_kernel<<<g, 1024, smem, st>>>(idx, mask, N, K, start, table, sorted);
+    VQB_LAUNCH_CHECK();
+    return VQB_OK;
+  }
+  dim3 g1((unsigned)((N + 255) / 256), (unsigned)H);
+  ema_hist_kernel<<<g1, 256, 0, st>>>(idx, mask, N, K, counts);
+  VQB_LAUNCH_CHECK();
+  ema_scan_kernel<<<(unsigned)H, 1024, 0, st>>>(counts, K, start);
+  VQB_LAUNCH_CHECK();
+  ema_place_kernel<<<g1, 256, 0, st>>>(idx, mask, N, K, start, cursor, sorted);
+  VQB_LAUNCH_CHECK();
+  return VQB_OK;
 }
 
 // one warp per 64 consecutive positions of the sorted order; lanes own columns {cb*128 + lane*4 .. +3}
@@ -808,13 +903,8 @@ extern "C" int vqb_ema_reduce(const void* x, int x_dtype, const int64_t* idx, co
     }
     ema_scale_kernel<<<1, 1, 0, st>>>(absmax_bound2, (const uint32_t*)(scale + 1), N, scale);
     VQB_LAUNCH_CHECK();
-    dim3 g1((unsigned)((N + 255) / 256), (unsigned)H);
-    ema_hist_kernel<<<g1, 256, 0, st>>>(idx, mask, N, K, counts);
-    VQB_LAUNCH_CHECK();
-    ema_scan_kernel<<<(unsigned)H, 1024, 0, st>>>(counts, K, start);
-    VQB_LAUNCH_CHECK();
-    ema_place_kernel<<<g1, 256, 0, st>>>(idx, mask, N, K, start, cursor, sorted);
-    VQB_LAUNCH_CHECK();
+    if (int rc = launch_code_sort(idx, mask, H, N, K, counts, cursor, start, sorted,
+                                  K <= kSortMaxK ? (uint32_t*)(w + L.off_table) : nullptr, st)) return rc;
     const int64_t chunks = (N + kChunkRows - 1) / kChunkRows;
     dim3 g2((unsigned)((chunks + 7) / 8), (unsigned)H);
     VQB_DISPATCH_DTYPE(x_dtype, T,
@@ -870,13 +960,8 @@ static int quantize_ema_impl(const void* x, int x_dtype, const float* codebook, 
     VQB_LAUNCH_CHECK();
     // the next level's statistics usually live in the workspace absmax_bound2 points into: zero them only now
     if (rvq && rvq->next_scal) VQB_CUDA_TRY(cudaMemsetAsync(rvq->next_scal, 0, 8, st));
-    dim3 g1((unsigned)((N + 255) / 256), (unsigned)H);
-    ema_hist_kernel<<<g1, 256, 0, st>>>(idx, nullptr, N, K, counts);
-    VQB_LAUNCH_CHECK();
-    ema_scan_kernel<<<(unsigned)H, 1024, 0, st>>>(counts, K, start);
-    VQB_LAUNCH_CHECK();
-    ema_place_kernel<<<g1, 256, 0, st>>>(idx, nullptr, N, K, start, cursor, sorted);
-    VQB_LAUNCH_CHECK();
+    if (int rc = launch_code_sort(idx, nullptr, H, N, K, counts, cursor, start, sorted,
+                                  K <= kSortMaxK ? (uint32_t*)(w + L.E.off_table) : nullptr, st)) return rc;
     const int64_t chunks = (N + kFusedChunkRows - 1) / kFusedChunkRows;
     dim3 g2((unsigned)((chunks + 7) / 8), (unsigned)H);
 #define VQB_QE_LAUNCH(T, NB, TERMS)                                                                          \

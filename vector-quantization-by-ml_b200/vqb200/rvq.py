@@ -207,7 +207,8 @@ class ResidualVQ(nn.Module):
         forward on the same input address (clone what must survive).  The first forward on a new input address runs
         eagerly, the second captures, later ones replay; the dead-code check stays outside the graph (one host sync
         per forward, as in eager mode).  Not used while a codebook still needs its kmeans init, with a mask, with
-        quantize-dropout, a shared codebook, or while `ops.TIME_SEARCH_KERNEL` brackets kernels with events."""
+        quantize-dropout, a shared codebook, under data parallelism (the per-level all_reduce is not captured), or while
+        `ops.TIME_SEARCH_KERNEL` brackets kernels with events."""
         self._graph_on = bool(flag)
         self._graph_max = int(max_graphs)
         self._graphs = {}
@@ -217,6 +218,8 @@ class ResidualVQ(nn.Module):
         if not getattr(self, "_graph_on", False) or mask is not None or ops.TIME_SEARCH_KERNEL:
             return False
         books = [l._codebook for l in self.layers]
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1 and any(b.use_ddp for b in books):
+            return False        # the statistics all_reduce of every level would have to be captured on all ranks at once
         return len({id(b) for b in books}) == len(books) and all(b.is_initialized and not b.sharded for b in books)
 
     def _forward_graphed(self, x, freeze_codebook):
@@ -232,7 +235,7 @@ class ResidualVQ(nn.Module):
             for layer in self.layers:       # the graph must ALWAYS rebuild the search operands of the codebooks: what
                 layer._codebook._dirty = True   # python decides during capture is what every replay does
             torch.cuda.synchronize(x.device)
-            with torch.cuda.graph(g):
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
                 res = self._fused_levels(x, None, freeze_codebook)
             ent = self._graphs[key] = (g, res, x)           # `x` kept alive: its address is baked into the graph
         g, (out, all_idx, all_loss, late), _ = ent
