@@ -375,6 +375,18 @@ def bench_c4(ctx, steps, warmup, pk, strong):
     ms, _, _ = timed_loop(ctx, step, steps, max(warmup, 4) + 2, time_kernels=False)
     launches = launches * steps / eager_steps
     per_level = sum(tc) / max(len(tc), 1)
+    # the same step with a gradient to the input (an encoder trained through the quantiser): fused loop forward + ONE
+    # replay pass backward (vqb_rvq_backward)
+    xg = [t.clone().requires_grad_(True) for t in xs]
+
+    def grad_step(i):
+        x = xg[i % 2]
+        x.grad = None
+        q, _, loss = rvq(x)
+        (q.sum() * 1e-6 + loss.sum()).backward()
+    ms_grad, _, _ = timed_loop(ctx, grad_step, max(2, min(steps, 5)), 2, time_kernels=False)
+    grad_steps = max(2, min(steps, 5))
+    del xg
     flops = 2.0 * N * K * d
     total_rows = N * ctx.world
     out = {"workload": f"C4: ResidualVQ 8 x K=1024 x d=512, {'64 sequences split over the ranks' if strong else '64 sequences per rank'}"
@@ -384,8 +396,10 @@ def bench_c4(ctx, steps, warmup, pk, strong):
            "steps": steps, "search_kernel_ms_per_level": per_level,
            "search_frac_of_tensor_peak": flops / (per_level / 1e3) / 1e12 / pk["tflops"] if per_level else None,
            "search_kernels_share_of_step": per_level * Q / (ms / steps) if per_level else None,
-           "gpu_launches_per_step": launches / steps, "cuda_graph": True,
-           "eager_ms_per_step": ms_eager / eager_steps}
+           "gpu_launches_per_step": launches / steps, "cuda_graph": ctx.world == 1,
+           "eager_ms_per_step": ms_eager / eager_steps, "autograd_ms_per_step": ms_grad / grad_steps,
+           "note": "ms_per_step: no-grad forward replayed as one CUDA graph on one GPU (eager under data parallelism); "
+                   "autograd_ms_per_step: forward with requires_grad + backward"}
     del rvq, xs
     free_all()
     return out

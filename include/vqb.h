@@ -231,6 +231,15 @@ int    vqb_rvq_replay_out(const float* x, const float* const* codebooks, const i
 int    vqb_column_moments(const void* x, int x_dtype, const uint8_t* mask, int64_t H, int64_t N, int d,
                           double* sums_out, int64_t* rows_used_out, void* stream);
 
+/* Input gradient of one ResidualVQ forward in training mode with EMA codebooks (reference autograd through
+ * residual_vq.py:212-243 and vector_quantize_pytorch.py:273,335-362), in one pass over the level-0 input:
+ *   grad_x = num_levels * g_out + sum_l [mask != 0] coef[l] * (r_l - c_l),   r_l replayed as in vqb_rvq_replay_out,
+ * c_l = codebooks[l][idx[l]] (the codebook BEFORE level l's EMA step), coef (num_levels) fp32 on the device =
+ * grad of the level's commitment loss * commitment_weight * 2 / (rows used * d).  g_out (N,d) nullable (= 0). */
+int    vqb_rvq_backward(const float* x, const float* const* codebooks, const int64_t* const* idx, const int* training,
+                        int num_levels, const float* coef, const float* g_out, const uint8_t* mask, float* grad_x,
+                        int64_t N, int d, void* stream);
+
 /* ---- sharded-codebook merge (K >= 64K split across GPUs) ------------------------------
  * No reference counterpart.  key = (orderable(score) << 32) | index, so an
  * all_reduce(MIN) over uint64 (as int64 with the sign bit clear) picks the smallest score and,

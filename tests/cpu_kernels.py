@@ -141,6 +141,20 @@ def column_moments(x, mask_u8):
     return torch.stack([xd.sum(dim=1), (xd * xd).sum(dim=1)], dim=-1), rows
 
 
+def rvq_backward(x, codebooks, idxs, training, coef, g_out, mask_u8):
+    """vqb_rvq_backward: Q * g_out + sum_l live * coef[l] * (r_l - c_l), residuals replayed from x."""
+    keep = torch.ones(x.shape[0], dtype=torch.bool) if mask_u8 is None else mask_u8.bool()
+    r = x
+    acc = len(codebooks) * (g_out.float() if g_out is not None else torch.zeros_like(x))
+    for l, (c, i, tr) in enumerate(zip(codebooks, idxs, training)):
+        cq = c[i]
+        acc = acc + torch.where(keep[:, None], coef[l] * (r - cq), torch.zeros_like(r))
+        q = r + (cq - r) if tr else cq
+        q = torch.where(keep[:, None], q, r)
+        r = r - q
+    return acc
+
+
 def minkey_pack(score, idx):
     """(orderable fp32 score << 32) | index as int64: smaller score first, lowest index on ties (vqb_minkey_pack)."""
     u = score.contiguous().view(torch.int32).to(torch.int64) & 0xFFFFFFFF
@@ -168,7 +182,7 @@ def ema_apply_sharded(stats, cluster_size, embed_avg, embeddings, weight, eps, w
 
 REPLACED = ("prepare_codebook", "search", "l2norm_rows", "gather_st_loss", "st_commit_backward", "ema_reduce",
             "ema_apply", "expire_scatter", "minkey_pack", "minkey_unpack", "ema_apply_sharded", "rvq_level",
-            "rvq_level_ema", "rvq_replay_out", "dense_gumbel_sample", "dense_scores", "column_moments",
+            "rvq_level_ema", "rvq_replay_out", "rvq_backward", "dense_gumbel_sample", "dense_scores", "column_moments",
             "l2norm_prepare_supported", "quantize_ema_supported", "rvq_level_ema_supported",
             "rvq_replay_out_supported")
 
@@ -177,7 +191,7 @@ def install(ops, lib):
     """Replace the wrappers on the `vqb200.ops` module object and the device guard of `vqb200._lib`."""
     for name in ("prepare_codebook", "search", "l2norm_rows", "gather_st_loss", "st_commit_backward", "ema_reduce",
                  "ema_apply", "expire_scatter", "minkey_pack", "minkey_unpack", "ema_apply_sharded", "rvq_level", "rvq_level_ema",
-                 "rvq_replay_out", "dense_gumbel_sample", "dense_scores", "column_moments"):
+                 "rvq_replay_out", "rvq_backward", "dense_gumbel_sample", "dense_scores", "column_moments"):
         setattr(ops, name, globals()[name])
     ops.l2norm_prepare_supported = lambda d: False
     ops.quantize_ema_supported = lambda d: False

@@ -227,3 +227,40 @@ def test_orchestration_rvq_learnable_codebooks_get_their_gradient(name, cpu_ops)
     """ResidualVQ over learnable codebooks: the fused (no_grad) level loop must NOT be taken while a codebook Parameter
     wants a gradient, even if the input carries none (reference vector_quantize_pytorch.py:263-269)."""
     gu.check_rvq_learnable(name, torch.device("cpu"))
+
+
+@pytest.mark.parametrize("name", [n for n in gu.grad_fixture_names() if "rvq" in n])
+def test_fused_rvq_loop_under_autograd_matches_reference_gradient(name, cpu_ops, monkeypatch):
+    """`_FusedRVQ`: the fused level loop with a gradient to the input (one replay pass backward, `rvq_backward`) against
+    the input gradients recorded from the live reference (3 levels; shared codebook + mask)."""
+    from test_gpu_parity import build_module, load_state
+    from vqb200 import rvq
+    real_can_fuse = rvq.ResidualVQ._can_fuse
+    calls = {"fused": 0}
+
+    class _OnDevice:
+        def __init__(self, t):
+            self.is_cuda, self.ndim, self.requires_grad, self.shape = True, t.ndim, t.requires_grad, t.shape
+
+    def can_fuse(self, x, dropout_active):
+        ok = real_can_fuse(self, _OnDevice(x), dropout_active)
+        calls["fused"] += int(ok)
+        return ok
+
+    monkeypatch.setattr(rvq.ResidualVQ, "_can_fuse", can_fuse)
+    fx = gu.load_grad(name)
+    mod, books = build_module(fx["cfg"])
+    with torch.no_grad():
+        load_state(books, fx)
+    mod.train()
+    x = fx["x"].clone().requires_grad_(True)
+    q, ind, loss = mod(x, mask=fx["mask"])
+    assert calls["fused"] == 1 and q.grad_fn is not None
+    ((q * fx["w"]).sum() + loss.sum() * 1.7).backward()
+    assert torch.equal(ind, fx["indices"])
+    assert gu.rel_err(q.detach(), fx["quantize"]) <= 1e-6
+    assert torch.allclose(loss.detach(), fx["loss"], rtol=1e-5)
+    assert gu.rel_err(x.grad, fx["grad_x"]) <= 1e-6
+    for cb, after in zip(books, fx["after"]):
+        assert torch.equal(cb.cluster_size, after["cluster_size"])
+        assert gu.rel_err(cb.embeddings, after["embeddings"]) <= 1e-5

@@ -441,6 +441,69 @@ rvq_replay_out_kernel(const float* __restrict__ x, const uint8_t* __restrict__ m
   }
 }
 
+
+// Input gradient of a whole ResidualVQ forward (training, EMA codebooks) in ONE pass, replayed from the level-0 input
+// and the chosen codes like rvq_replay_out_kernel.  Reference autograd through residual_vq.py:212-243 and
+// vector_quantize_pytorch.py:273,335-362: every level's output is r_l + (q_l - r_l).detach() (identity Jacobian), the
+// next residual subtracts a DETACHED quantity (identity again), so d out / d x = Q I, and the commitment loss of level
+// l, mean((c_l - r_l)^2) over the live rows, contributes coef_l (r_l - c_l) with coef_l = g_loss_l w_l 2 / (rows_l d):
+//   grad_x = Q g_out + sum_l live coef_l (r_l - c_l)        (c_l from the codebook as it was BEFORE level l's EMA step)
+struct BackwardArgs {
+  ReplayArgs R;
+  const float* coef;       // (Q) device
+};
+template <int VEC>
+__global__ void __launch_bounds__(kGatherThreads)
+rvq_backward_kernel(const float* __restrict__ x, const float* __restrict__ g_out, const uint8_t* __restrict__ mask,
+                    float* __restrict__ grad_x, int64_t N, int d, const __grid_constant__ BackwardArgs B) {
+  const ReplayArgs& A = B.R;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int wpb = kGatherThreads / 32;
+  const float my_coef = lane < A.Q ? B.coef[lane] : 0.f;
+  for (int64_t row = (int64_t)blockIdx.x * wpb + warp; row < N; row += (int64_t)gridDim.x * wpb) {
+    const bool live = mask == nullptr || mask[row] != 0;
+    float4 r[VEC], acc[VEC];
+#pragma unroll
+    for (int t = 0; t < VEC; ++t) {
+      const int j = lane * 4 + 128 * t;
+      r[t] = acc[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (j < d) {
+        r[t] = __ldcs(reinterpret_cast<const float4*>(x + row * (int64_t)d + j));
+        const float4 g = g_out ? __ldcs(reinterpret_cast<const float4*>(g_out + row * (int64_t)d + j))
+                               : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float q = (float)A.Q;
+        acc[t] = make_float4(q * g.x, q * g.y, q * g.z, q * g.w);
+      }
+    }
+    const long long my_k = lane < A.Q ? (long long)A.idx[lane][row] : 0ll;
+    for (int l = 0; l < A.Q; ++l) {
+      const float* cr = A.cb[l] + __shfl_sync(0xffffffffu, my_k, l) * (int64_t)d;
+      const float cf = live ? __shfl_sync(0xffffffffu, my_coef, l) : 0.f;
+      const bool tr = A.training[l] != 0;
+#pragma unroll
+      for (int t = 0; t < VEC; ++t) {
+        const int j = lane * 4 + 128 * t;
+        if (j >= d) continue;
+        const float4 c = __ldg(reinterpret_cast<const float4*>(cr + j));
+        const float4 v = r[t];
+        acc[t].x = fmaf(cf, v.x - c.x, acc[t].x); acc[t].y = fmaf(cf, v.y - c.y, acc[t].y);
+        acc[t].z = fmaf(cf, v.z - c.z, acc[t].z); acc[t].w = fmaf(cf, v.w - c.w, acc[t].w);
+        float4 qv;
+        if (!live) qv = v;
+        else if (tr) qv = make_float4(__fadd_rn(v.x, __fsub_rn(c.x, v.x)), __fadd_rn(v.y, __fsub_rn(c.y, v.y)),
+                                      __fadd_rn(v.z, __fsub_rn(c.z, v.z)), __fadd_rn(v.w, __fsub_rn(c.w, v.w)));
+        else qv = c;
+        r[t] = make_float4(__fsub_rn(v.x, qv.x), __fsub_rn(v.y, qv.y), __fsub_rn(v.z, qv.z), __fsub_rn(v.w, qv.w));
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < VEC; ++t) {
+      const int j = lane * 4 + 128 * t;
+      if (j < d) __stcs(reinterpret_cast<float4*>(grad_x + row * (int64_t)d + j), acc[t]);
+    }
+  }
+}
+
 }  // namespace vqb
 
 using namespace vqb;
@@ -577,6 +640,29 @@ extern "C" int vqb_rvq_replay_out(const float* x, const float* const* codebooks,
   if (d <= 128) rvq_replay_out_kernel<1><<<grid, kGatherThreads, 0, st>>>(x, mask, out, N, d, A);
   else if (d <= 256) rvq_replay_out_kernel<2><<<grid, kGatherThreads, 0, st>>>(x, mask, out, N, d, A);
   else rvq_replay_out_kernel<4><<<grid, kGatherThreads, 0, st>>>(x, mask, out, N, d, A);
+  VQB_LAUNCH_CHECK();
+  return VQB_OK;
+}
+
+extern "C" int vqb_rvq_backward(const float* x, const float* const* codebooks, const int64_t* const* idx,
+                                const int* training, int num_levels, const float* coef, const float* g_out,
+                                const uint8_t* mask, float* grad_x, int64_t N, int d, void* stream) {
+  VQB_REQUIRE(x && codebooks && idx && training && coef && grad_x, VQB_ERR_INVALID, "vqb_rvq_backward: null pointer");
+  VQB_REQUIRE(vqb_rvq_replay_out_supported(d, num_levels), VQB_ERR_UNSUPPORTED,
+              "vqb_rvq_backward: d=%d (multiple of 4, <= 512), levels=%d (<= %d)", d, num_levels, kMaxReplayLevels);
+  if (N <= 0) return VQB_OK;
+  BackwardArgs B = {};
+  B.R.Q = num_levels;
+  B.coef = coef;
+  for (int l = 0; l < num_levels; ++l) {
+    VQB_REQUIRE(codebooks[l] && idx[l], VQB_ERR_INVALID, "vqb_rvq_backward: null level pointer");
+    B.R.cb[l] = codebooks[l]; B.R.idx[l] = idx[l]; B.R.training[l] = training[l];
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = gather_grid(N);
+  if (d <= 128) rvq_backward_kernel<1><<<grid, kGatherThreads, 0, st>>>(x, g_out, mask, grad_x, N, d, B);
+  else if (d <= 256) rvq_backward_kernel<2><<<grid, kGatherThreads, 0, st>>>(x, g_out, mask, grad_x, N, d, B);
+  else rvq_backward_kernel<4><<<grid, kGatherThreads, 0, st>>>(x, g_out, mask, grad_x, N, d, B);
   VQB_LAUNCH_CHECK();
   return VQB_OK;
 }

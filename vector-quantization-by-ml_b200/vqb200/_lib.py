@@ -54,6 +54,7 @@ SIGNATURES = {
     "vqb_dense_gumbel_sample": (_i32, [_p, _i32, _p, _p, _p, _i32, _f32, _p, C.c_uint64, C.c_uint64, C.c_uint32, _p,
                                        _i64, _i64, _i32, _i32, _p]),
     "vqb_dense_scores": (_i32, [_p, _i32, _p, _p, _p, _i32, _p, _i64, _i64, _i32, _i32, _p]),
+    "vqb_rvq_backward": (_i32, [_p, _p, _p, _p, _i32, _p, _p, _p, _p, _i64, _i32, _p]),
     "vqb_rvq_replay_out_supported": (_i32, [_i32, _i32]),
     "vqb_rvq_replay_out": (_i32, [_p, _p, _p, _p, _i32, _p, _p, _i64, _i32, _p]),
     "vqb_rvq_level_ema_supported": (_i32, [_i32]),

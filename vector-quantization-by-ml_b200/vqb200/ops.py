@@ -434,6 +434,28 @@ def rvq_replay_out(x: torch.Tensor, codebooks, idxs, training, mask_u8: Optional
     return out
 
 
+@_on_device
+def rvq_backward(x: torch.Tensor, codebooks, idxs, training, coef: torch.Tensor, g_out: Optional[torch.Tensor],
+                 mask_u8: Optional[torch.Tensor]) -> torch.Tensor:
+    """Input gradient (N,d) of a ResidualVQ training forward: Q * g_out + sum_l coef[l] * (r_l - C_l[idx_l]) on the
+    rows with mask != 0 (vqb_rvq_backward); the residuals are replayed from x and the indices."""
+    import ctypes as C
+    L.require_cuda(x, "x")
+    N, d = x.shape
+    Q = len(codebooks)
+    keep = [c.contiguous() for c in codebooks] + [i.contiguous() for i in idxs]
+    cbp = (C.c_void_p * Q)(*[L.ptr(c) for c in keep[:Q]])
+    ixp = (C.c_void_p * Q)(*[L.ptr(i) for i in keep[Q:]])
+    trp = (C.c_int * Q)(*[int(bool(t)) for t in training])
+    coef = coef.to(device=x.device, dtype=torch.float32).contiguous()
+    g = g_out.contiguous().float() if g_out is not None else None
+    gx = torch.empty((N, d), dtype=torch.float32, device=x.device)
+    L.check(L.lib().vqb_rvq_backward(L.ptr(x), C.cast(cbp, C.c_void_p), C.cast(ixp, C.c_void_p),
+                                     C.cast(trp, C.c_void_p), Q, L.ptr(coef), L.ptr(g), L.ptr(mask_u8), L.ptr(gx), N, d,
+                                     L.stream_ptr(x.device)), "vqb_rvq_backward")
+    return gx
+
+
 def rvq_level_ema_supported(d: int) -> bool:
     return bool(L.lib().vqb_rvq_level_ema_supported(int(d)))
 

@@ -75,7 +75,7 @@ class ResidualVQ(nn.Module):
     def _can_fuse(self, x, dropout_active) -> bool:
         if not self.use_fused_levels or dropout_active or not x.is_cuda or x.ndim != 3:
             return False
-        if torch.is_grad_enabled() and x.requires_grad:
+        if torch.is_grad_enabled() and x.requires_grad and not self._can_fuse_autograd(x):
             return False
         l0 = self.layers[0]
         if self.training and (l0.commitment_use_cross_entropy_loss or l0.has_codebook_diversity_loss):
@@ -91,10 +91,22 @@ class ResidualVQ(nn.Module):
             return False
         return l0.channel_last and not l0._codebook.input_l2norm and l0.heads == 1
 
-    @torch.no_grad()
+    def _can_fuse_autograd(self, x) -> bool:
+        """The fused loop under autograd (`_FusedRVQ`): training mode, EMA codebooks (the gradient to the input is all
+        there is), at least two levels and a width the replay kernels take."""
+        d = x.shape[-1]
+        return bool(self.training and all(l.training for l in self.layers)
+                    and not any(l._codebook.learnable_codebook for l in self.layers)
+                    and len(self.layers) >= 2 and ops.rvq_replay_out_supported(d, len(self.layers)))
+
     def _forward_fused(self, x, mask, freeze_codebook):
-        out, all_idx, all_loss, late = self._fused_levels(x, mask, freeze_codebook)
-        self._fused_expiry(late, mask)
+        if torch.is_grad_enabled() and x.requires_grad:
+            out, idx, losses = _FusedRVQ.apply(x, self, mask, freeze_codebook)
+            Q = idx.shape[0]
+            return out, [idx[i] for i in range(Q)], [losses[i:i + 1] for i in range(Q)]
+        with torch.no_grad():
+            out, all_idx, all_loss, late = self._fused_levels(x, mask, freeze_codebook)
+            self._fused_expiry(late, mask)
         return out, all_idx, all_loss
 
     @torch.no_grad()
@@ -106,7 +118,7 @@ class ResidualVQ(nn.Module):
         # level 0 reads the input itself (never written: every level writes its residual to another buffer)
         x0 = _lib.aligned(x.reshape(N, d).float())
         bufs = [torch.empty((N, d), dtype=torch.float32, device=dev) for _ in range(min(2, len(self.layers)))]
-        all_idx, all_loss = [], []
+        all_idx, all_loss, loss_bufs = [], [], []
         Q = len(self.layers)
         # `quantized_out` (residual_vq.py:233) is not accumulated level by level -- that is a read-modify-write of an
         # (N,d) buffer in every level pass -- but replayed once at the end from x and the indices with the same IEEE
@@ -164,6 +176,7 @@ class ResidualVQ(nn.Module):
                 elif cb.threshold_ema_dead_code != 0:
                     pending.append((li, cb, (cb.cluster_size < cb.threshold_ema_dead_code).sum()))
             loss = torch.zeros(1, device=dev)
+            loss_bufs.append((loss_buf, layer.commitment_weight if (training and layer.has_commitment_loss) else 0.0))
             if training and layer.has_commitment_loss:
                 loss = loss + loss_buf[0] * layer.commitment_weight
             all_idx.append(idx.reshape(B, n))
@@ -172,13 +185,13 @@ class ResidualVQ(nn.Module):
             out = ops.rvq_replay_out(x0, [e[0] for e, _ in pre_emb], [i.reshape(-1) for i in all_idx],
                                      [tr for _, tr in pre_emb], books[0]._expand_mask(mask, N))
         dead_counts = torch.stack([p[2] for p in pending]) if pending else None
-        late = (pending, dead_counts, x0, pre_emb, all_idx)
+        late = (pending, dead_counts, x0, pre_emb, all_idx, loss_bufs)
         return out.reshape(B, n, d), all_idx, all_loss, late
 
     @torch.no_grad()
     def _fused_expiry(self, late, mask):
         """The deferred dead-code checks of all levels: ONE host sync, then (rarely) the replay described above."""
-        pending, dead_counts, x0, pre_emb, all_idx = late
+        pending, dead_counts, x0, pre_emb, all_idx = late[:5]
         if not pending:
             return
         dead = dead_counts.tolist()                                      # the one host sync
@@ -217,6 +230,8 @@ class ResidualVQ(nn.Module):
     def _graph_usable(self, x, mask) -> bool:
         if not getattr(self, "_graph_on", False) or mask is not None or ops.TIME_SEARCH_KERNEL:
             return False
+        if torch.is_grad_enabled() and x.requires_grad:
+            return False        # the autograd form of the fused loop (`_FusedRVQ`) runs eagerly
         books = [l._codebook for l in self.layers]
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1 and any(b.use_ddp for b in books):
             return False        # the statistics all_reduce of every level would have to be captured on all ranks at once
@@ -297,6 +312,41 @@ class ResidualVQ(nn.Module):
         if return_all_codes:
             ret = (*ret, self.get_codes_from_indices(all_indices))
         return ret
+
+
+class _FusedRVQ(torch.autograd.Function):
+    """The fused level loop with a gradient to the input.  Reference autograd through residual_vq.py:212-243: every
+    level returns r_l + (q_l - r_l).detach() and the next residual subtracts a detached quantity, so d out / d x = Q I;
+    the commitment loss of level l, mse(c_l.detach(), r_l), adds w_l 2 (r_l - c_l) / (rows d).  Backward is ONE pass
+    that replays the residuals from x and the indices (vqb_rvq_backward) against the codebooks as they were before each
+    level's EMA step -- the generic per-level loop instead keeps Q (N,d) residuals alive for autograd."""
+
+    @staticmethod
+    def forward(ctx, x, rvq, mask, freeze_codebook):
+        with torch.no_grad():
+            out, all_idx, all_loss, late = rvq._fused_levels(x.detach(), mask, freeze_codebook)
+            rvq._fused_expiry(late, mask)
+        _, _, x0, pre_emb, _, loss_bufs = late
+        ctx.x0, ctx.pre_emb, ctx.loss_bufs = x0, pre_emb, loss_bufs
+        ctx.idx = [i.reshape(-1) for i in all_idx]
+        ctx.mask_u8 = rvq.layers[0]._codebook._expand_mask(mask, x0.shape[0])
+        ctx.shape, ctx.dtype = x.shape, x.dtype
+        idx = torch.stack(all_idx, 0)
+        ctx.mark_non_differentiable(idx)
+        return out, idx, torch.cat(all_loss, 0)
+
+    @staticmethod
+    def backward(ctx, g_out, _g_idx, g_losses):
+        N, d = ctx.x0.shape
+        if g_losses is None:
+            coef = torch.zeros(len(ctx.idx), device=ctx.x0.device)
+        else:
+            # grad of level l's loss * commitment weight * 2 / (rows used * d), all on the device
+            coef = torch.stack([g_losses[l].float() * (w * 2.0 / d) / lb[1] for l, (lb, w) in enumerate(ctx.loss_bufs)])
+        g = g_out.reshape(N, d) if g_out is not None else None
+        gx = ops.rvq_backward(ctx.x0, [e[0] for e, _ in ctx.pre_emb], ctx.idx, [tr for _, tr in ctx.pre_emb], coef, g,
+                              ctx.mask_u8)
+        return gx.reshape(ctx.shape).to(ctx.dtype), None, None, None
 
 
 class GroupedResidualVQ(nn.Module):
