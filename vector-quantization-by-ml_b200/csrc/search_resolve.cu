@@ -136,6 +136,7 @@ resolve_classify_kernel(const uint2* __restrict__ cand, const float* __restrict_
                         const float* __restrict__ cb, int d, int metric, float* __restrict__ score_out) {
   const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   bool queue = false;
+  int64_t direct_code = -1;                   // SCORE: flat index (h K + code) of the accepted single candidate
   if (gid < H * N) {
     const int64_t h = gid / N;
     RowCands R;
@@ -150,15 +151,44 @@ resolve_classify_kernel(const uint2* __restrict__ cand, const float* __restrict_
       keys[gid] = ~0ull;                      // min-key accumulator of the K-split rescan
     } else if (R.ncand == 1 && !R.local_rescan) {
       idx_out[gid] = (int64_t)R.c1 + idx_offset;
-      if (SCORE) {
-        const T* xr = x + gid * (int64_t)d;
-        const double n2 = metric == VQB_EUCLID ? row_norm2<T>(xr, d) : 0.0;
-        score_out[gid] = exact_score<T>(xr, cb + (h * K + (int64_t)R.c1) * d, d, metric, n2);
-      }
+      if (SCORE) direct_code = (h * K + (int64_t)R.c1);
     } else {
       queue = true;
       keys[gid] = ~0ull;                      // min-key accumulator of the pair scoring
     }
+  }
+  if (SCORE) {
+    // Exact score of the accepted candidate, same fma chains in the same order as exact_score() / row_norm2() (the
+    // sharded merge compares scores across GPUs and across resolve paths).  A thread walking its own 4d-byte row
+    // touches 32 different lines per warp-load; the block's rows are staged through shared memory instead, 32
+    // dimensions at a time with fully coalesced loads (stride 33: conflict-free reads), and only the code row --
+    // a gather in any case, served by L2 -- is read directly.
+    __shared__ float xs[256][33];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t row0 = (int64_t)blockIdx.x * blockDim.x;
+    const int64_t total = H * N;
+    const float* cr = direct_code >= 0 ? cb + direct_code * (int64_t)d : cb;
+    double dot = 0.0, cn2 = 0.0, n2 = 0.0;
+    for (int d0 = 0; d0 < d; d0 += 32) {
+      __syncthreads();
+#pragma unroll 8
+      for (int r = 0; r < 32; ++r) {
+        const int64_t row = row0 + warp * 32 + r;
+        xs[warp * 32 + r][lane] = (row < total && d0 + lane < d) ? to_f32<T>(x[row * (int64_t)d + d0 + lane]) : 0.f;
+      }
+      __syncthreads();
+      if (direct_code >= 0) {
+        const int lim = d - d0 < 32 ? d - d0 : 32;
+        for (int c = 0; c < lim; ++c) {
+          const double a = (double)xs[threadIdx.x][c], cv = (double)__ldg(cr + d0 + c);
+          n2 = fma(a, a, n2);
+          dot = fma(a, cv, dot);
+          cn2 = fma(cv, cv, cn2);
+        }
+      }
+    }
+    if (direct_code >= 0)
+      score_out[gid] = metric == VQB_DOT ? (float)(-dot) : sqrtf(fmaxf((float)(n2 + cn2 - 2.0 * dot), 0.f));
   }
   // warp-aggregated append to the re-rank list (scal[3] is its length)
   const uint32_t m = __ballot_sync(0xffffffffu, queue);
@@ -187,11 +217,16 @@ rerank_emit_kernel(const uint2* __restrict__ cand, const float* __restrict__ err
                    const int* __restrict__ rr_list, uint32_t* __restrict__ scal, int aug, uint2* __restrict__ pairs,
                    uint32_t pair_cap, int* __restrict__ flag_list, uint32_t* __restrict__ flag_cnt,
                    const float* __restrict__ xn2, float tie) {
-  const int lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
   const int64_t count = scal[3];
-  for (int64_t it = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); it < count; it += nwarps) {
-    const int64_t gid = rr_list[it];
+  // the pair slots of the 8 rows a block handles per iteration are reserved with ONE atomic (a row at a time, 250 k
+  // queued rows of a d = 64 search serialised on that one counter for 0.24 ms)
+  __shared__ uint32_t s_n[8], s_base;
+  for (int64_t it0 = (int64_t)blockIdx.x * (blockDim.x >> 5); it0 < count; it0 += nwarps) {   // block-uniform trip count
+    const int64_t it = it0 + warp;
+    const bool have = it < count;
+    const int64_t gid = rr_list[have ? it : it0];
     const int64_t h = gid / N;
     float key = __int_as_float(0x7f800000);
     int code = -1;
@@ -218,10 +253,19 @@ rerank_emit_kernel(const uint2* __restrict__ cand, const float* __restrict__ err
                      code_next >= 0 && (code >> 9) == (code_next >> 9);
     const uint32_t acts = __ballot_sync(0xffffffffu, act);
     uint32_t reqs = __ballot_sync(0xffffffffu, req);
-    const uint32_t n = (uint32_t)__popc(acts) + 64u * (uint32_t)__popc(reqs);
-    uint32_t base = 0;
-    if (lane == 0) base = atomicAdd(scal + 9, n);
-    base = __shfl_sync(0xffffffffu, base, 0);
+    const uint32_t n = have ? (uint32_t)__popc(acts) + 64u * (uint32_t)__popc(reqs) : 0u;
+    if (lane == 0) s_n[warp] = n;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      uint32_t t = 0;
+      for (int w2 = 0; w2 < (int)(blockDim.x >> 5); ++w2) t += s_n[w2];
+      s_base = t ? atomicAdd(scal + 9, t) : 0u;
+    }
+    __syncthreads();
+    uint32_t base = s_base;
+    for (int w2 = 0; w2 < warp; ++w2) base += s_n[w2];
+    __syncthreads();                    // s_n / s_base are rewritten in the next iteration
+    if (!have) continue;
     if (base + n > pair_cap) {          // no room: the exact rescan takes the row (its key is already ~0)
       if (lane == 0) flag_list[h * N + atomicAdd(flag_cnt + h, 1u)] = (int)(gid - h * N);
       for (uint32_t i = base + lane; i < base + n && i < pair_cap; i += 32)   // void the reserved slots
