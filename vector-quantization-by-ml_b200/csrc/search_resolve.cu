@@ -179,11 +179,26 @@ resolve_classify_kernel(const uint2* __restrict__ cand, const float* __restrict_
       __syncthreads();
       if (direct_code >= 0) {
         const int lim = d - d0 < 32 ? d - d0 : 32;
-        for (int c = 0; c < lim; ++c) {
-          const double a = (double)xs[threadIdx.x][c], cv = (double)__ldg(cr + d0 + c);
-          n2 = fma(a, a, n2);
-          dot = fma(a, cv, dot);
-          cn2 = fma(cv, cv, cn2);
+        if ((d & 3) == 0) {              // code row as float4: a warp-load of 32 different rows costs 32 L1 wavefronts
+#pragma unroll 2
+          for (int c = 0; c < lim; c += 4) {
+            const float4 c4 = __ldg(reinterpret_cast<const float4*>(cr + d0 + c));
+            const float cvs[4] = {c4.x, c4.y, c4.z, c4.w};
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const double a = (double)xs[threadIdx.x][c + t], cv = (double)cvs[t];
+              n2 = fma(a, a, n2);
+              dot = fma(a, cv, dot);
+              cn2 = fma(cv, cv, cn2);
+            }
+          }
+        } else {
+          for (int c = 0; c < lim; ++c) {
+            const double a = (double)xs[threadIdx.x][c], cv = (double)__ldg(cr + d0 + c);
+            n2 = fma(a, a, n2);
+            dot = fma(a, cv, dot);
+            cn2 = fma(cv, cv, cn2);
+          }
         }
       }
     }
