@@ -503,6 +503,29 @@ def main():
     clocks = sampler.stop(t_warm, t_end) if rank == 0 else None
     stats = ops.search_stats(cb.last_search_ws)
 
+    # ---- the bandwidth-bound part of the step on its own: gather + straight-through + loss + EMA sums in one pass over
+    #      the latents (counting sort included), against its ALGORITHMIC bytes (sz(x) d + 12 read,
+    #      4 d + 4 write per row) and the measured HBM copy peak ----
+    with torch.no_grad():
+        flat = xs[0].reshape(1, -1, DIM)
+        idx_b, _, ws_b = ops.search(flat, cb.embeddings, cb._codebook_cache(), False)
+        for _ in range(3):
+            ops.quantize_ema(flat, cb.embeddings, idx_b, True, True, bound_ws=ws_b)
+        eb0, eb1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        eb0.record()
+        for i in range(10):
+            ops.quantize_ema(xs[i % n_bufs].reshape(1, -1, DIM), cb.embeddings, idx_b, True, True, bound_ws=ws_b)
+        eb1.record()
+        torch.cuda.synchronize()
+    gather_ms = eb0.elapsed_time(eb1) / 10
+    gather_bytes = N_ROWS * (2 * DIM + 12 + 4 * DIM + 4)
+    hbm = {"kernel": "vqb_quantize_ema: counting sort + quantize_ema_kernel + finalize (gather, straight-through, "
+                     "commitment loss and EMA sums in one pass)",
+           "ms": gather_ms, "algorithmic_bytes": gather_bytes, "achieved_gbs": gather_bytes / (gather_ms / 1e3) / 1e9,
+           "peak_gbs": pk["hbm_gbs"], "frac": gather_bytes / (gather_ms / 1e3) / 1e9 / pk["hbm_gbs"]}
+    del idx_b, flat
+
     # ---- the step a training loop takes: input requires grad, forward + backward (codebook snapshot, _QuantizeST,
     #      vqb_st_commit_backward); fp32 latents (the reference's own backward rejects bf16 inputs) ----
     x_grad = xs[0].float().requires_grad_(True)
@@ -662,6 +685,7 @@ def main():
                                  "what": "fp32 latents with requires_grad: forward (search, codebook snapshot, fused "
                                          "gather/ST/loss+EMA) + backward (vqb_st_commit_backward)",
                                  "gpu_launches_per_step": ag_launches / ag_steps},
+               "roofline_hbm": hbm,
                "configs": configs,
                "gpu_launches": int(launches), "clocks": clocks}
         print(json.dumps(out), flush=True)

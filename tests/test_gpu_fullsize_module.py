@@ -218,3 +218,39 @@ def test_c4_residual_vq_slice_matches_oracle():
             for li, (layer, st) in enumerate(zip(rvq.layers, sts)):
                 _compare_buffers(layer._codebook, st, torch.empty(0, dtype=torch.long), f"C4 level {li} fused={fused}")
         print(f"C4 slice fused={fused}: {n_flips} exempt ties of {got.numel()} lookups")
+
+
+def test_c4_slice_fused_backward_equals_per_level_autograd():
+    """`_FusedRVQ` (fused level loop forward, ONE replay pass backward: vqb_rvq_backward) against the generic per-level
+    loop under torch autograd at the C4 slice (8 x 1024 x 512): same outputs and losses, input gradient to fp32
+    rounding.  The per-level loop itself is pinned to the reference's gradients by the `grads/` fixtures."""
+    from vqb200 import CodebookParams, ResidualVQ
+    Q, K, d = 8, 1024, 512
+    g = torch.Generator().manual_seed(43)
+    cbs = [torch.randn(1, K, d, generator=g) * (0.5 / 1.4 ** li) for li in range(Q)]
+    x0 = torch.randn(4, 4096, d, generator=g)
+    w = torch.randn(4, 4096, d, generator=g)
+    res = {}
+    for fused in (True, False):
+        torch.manual_seed(0)
+        rvq = ResidualVQ(dim=d, num_quantizers=Q,
+                         codebook_params=CodebookParams(dim=d, codebook_size=K, threshold_ema_dead_code=0)).to(DEV).train()
+        for layer, c in zip(rvq.layers, cbs):
+            cb = layer._codebook
+            with torch.no_grad():
+                cb.embeddings.copy_(c); cb.embed_avg.copy_(c); cb.cluster_size.fill_(1.0)
+            cb.invalidate_cache()
+        rvq.use_fused_levels = fused
+        x = x0.to(DEV).requires_grad_(True)
+        q, ind, losses = rvq(x)
+        ((q * w.to(DEV)).sum() + (losses * torch.arange(1, Q + 1, device=DEV)).sum() * 3.0).backward()
+        res[fused] = (q.detach(), ind, losses.detach(), x.grad.clone(),
+                      [l._codebook.embeddings.clone() for l in rvq.layers])
+    qf, indf, lf, gf, ef = res[True]
+    qg, indg, lg, gg, eg = res[False]
+    assert torch.equal(indf, indg)
+    assert torch.equal(qf, qg), "quantized_out differs between the fused and the per-level loop"
+    assert torch.allclose(lf, lg, rtol=1e-6)
+    assert _rel(gf.cpu(), gg.cpu()) <= 1e-6, _rel(gf.cpu(), gg.cpu())
+    for a, b in zip(ef, eg):
+        assert _rel(a.cpu(), b.cpu()) <= 1e-6
