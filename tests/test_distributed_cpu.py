@@ -258,3 +258,79 @@ def test_two_rank_gloo_data_parallel_orchestration(tmp_path):
             assert res[f"sh_{key}_{mode}"], (key, mode, res)
         assert res[f"sh_expired_{mode}"] >= 3, res
     assert res["sh_loss"] and res["sh_kmeans"], res
+
+
+def _rvq_dp_worker(rank, world, port, out):
+    """ResidualVQ data parallel through the FUSED level loop (`_fused_levels`: per-level statistics all_reduce launched
+    asynchronously, refreshes applied after the loop) on Gloo: every rank must end with the codebooks one process gets on
+    the rank-concatenated batch (the oracle's rvq_forward), with and without dead-code expiry."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for p in (root, os.path.join(root, "tests"), os.path.join(root, "vector-quantization-by-ml_b200")):
+        sys.path.insert(0, p)
+    import cpu_kernels
+    from oracle import vq_oracle as O
+    from vqb200 import CodebookParams, ResidualVQ, _lib, ops, rvq as RVQ
+    cpu_kernels.install(ops, _lib)
+    real_can_fuse = RVQ.ResidualVQ._can_fuse
+    fused_calls = []
+
+    class _OnDevice:
+        def __init__(self, t):
+            self.is_cuda, self.ndim, self.requires_grad, self.shape = True, t.ndim, t.requires_grad, t.shape
+
+    def can_fuse(self, x, dropout_active):
+        ok = real_can_fuse(self, _OnDevice(x), dropout_active)
+        fused_calls.append(ok)
+        return ok
+    RVQ.ResidualVQ._can_fuse = can_fuse
+    res = {}
+    Q, K, d, b, n = 3, 40, 8, 2, 90
+    g = torch.Generator().manual_seed(4)
+    x_all = torch.randn(world * b, n, d, generator=g)
+    cbs = [torch.randn(1, K, d, generator=g) * (0.6 / 1.5 ** li) for li in range(Q)]
+    for thr in (0, 2):
+        torch.manual_seed(0)
+        m = ResidualVQ(dim=d, num_quantizers=Q, codebook_params=CodebookParams(dim=d, codebook_size=K,
+                                                                               threshold_ema_dead_code=thr),
+                       sync_codebook=True).train()
+        sts = []
+        for layer, c in zip(m.layers, cbs):
+            cb = layer._codebook
+            with torch.no_grad():
+                cb.embeddings.copy_(c); cb.embed_avg.copy_(c); cb.cluster_size.fill_(1.0)
+            sts.append(O.CodebookState(c.clone(), c.clone(), torch.ones(1, K)))
+        with torch.no_grad():
+            q, ind, loss = m(x_all[rank * b:(rank + 1) * b])
+        opts = O.VQOpts(codebook=O.CodebookOpts(threshold_ema_dead_code=0))
+        qo, io, lo, _ = O.rvq_forward(sts, x_all, opts, training=True)
+        res[f"ind{thr}"] = torch.equal(ind, io[rank * b:(rank + 1) * b])
+        res[f"q{thr}"] = torch.equal(q, qo[rank * b:(rank + 1) * b])
+        same = True
+        for layer, st in zip(m.layers, sts):
+            cb = layer._codebook
+            if thr == 0:
+                same &= torch.equal(cb.cluster_size, st.cluster_size)
+                same &= float((cb.embeddings - st.embeddings).abs().max() / st.embeddings.abs().max()) < 1e-6
+            for name in ("embeddings", "embed_avg", "cluster_size"):      # replicas identical, expiry included
+                mine = getattr(cb, name).detach().clone().contiguous()
+                ref = mine.clone()
+                dist.broadcast(ref, src=0)
+                same &= torch.equal(mine, ref)
+            if thr == 2:
+                same &= bool((cb.cluster_size >= 2.0 - 1e-6).all())       # every dead code was replaced
+        res[f"books{thr}"] = same
+    res["fused"] = all(fused_calls) and len(fused_calls) == 2
+    if rank == 0:
+        torch.save(res, out)
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_residual_vq_fused_loop_data_parallel(tmp_path):
+    out = str(tmp_path / "rvq_dp.pt")
+    mp.spawn(_rvq_dp_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    res = torch.load(out)
+    assert all(res.values()), res

@@ -134,7 +134,8 @@ class ResidualVQ(nn.Module):
         # kmeans init (that draws too) or when the codebook is shared.
         books = [l._codebook for l in self.layers]
         defer = len({id(b) for b in books}) == Q and all(b.is_initialized for b in books)
-        pending, pre_emb = [], []
+        pending, pre_emb, late_apply = [], [], []
+        overlap = defer and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
         for li, layer in enumerate(self.layers):
             cb = layer._codebook
             cur = x0 if li == 0 else bufs[(li - 1) % len(bufs)]
@@ -166,7 +167,13 @@ class ResidualVQ(nn.Module):
                 stats = ops.ema_reduce(flat, idx, mask_u8, cb.codebook_size, bound_ws=ws) if do_ema else None
                 loss_buf = ops.rvq_level(cur, nxt, emb[0], idx[0], mask_u8, training, li == 0, out, next_cache)
             prepared = next_cache is not None
-            if do_ema:
+            if do_ema and overlap and cb.use_ddp:
+                # data parallel, distinct codebooks: nothing later in this forward reads codebook `li` (the gather's
+                # copy was taken above), so the statistics all_reduce of this level runs beside the next levels'
+                # searches and its refresh is applied after the loop (reference residual_vq.py:212-243 with
+                # codebooks.py:410,415 per level: same values, other order of independent operations)
+                late_apply.append((dist.all_reduce(stats, async_op=True), stats, cb, li))
+            elif do_ema:
                 cb._all_reduce(stats)
                 ops.ema_apply(stats, cb.cluster_size.data, cb.embed_avg.data, cb.embeddings.data, 1 - cb.decay,
                               cb.eps_for_smoothing, cb.weights_l2norm)
@@ -184,6 +191,13 @@ class ResidualVQ(nn.Module):
         if replay:
             out = ops.rvq_replay_out(x0, [e[0] for e, _ in pre_emb], [i.reshape(-1) for i in all_idx],
                                      [tr for _, tr in pre_emb], books[0]._expand_mask(mask, N))
+        for work, stats, cb, li in late_apply:
+            work.wait()
+            ops.ema_apply(stats, cb.cluster_size.data, cb.embed_avg.data, cb.embeddings.data, 1 - cb.decay,
+                          cb.eps_for_smoothing, cb.weights_l2norm)
+            cb._dirty = True
+            if cb.threshold_ema_dead_code != 0:
+                pending.append((li, cb, (cb.cluster_size < cb.threshold_ema_dead_code).sum()))
         dead_counts = torch.stack([p[2] for p in pending]) if pending else None
         late = (pending, dead_counts, x0, pre_emb, all_idx, loss_bufs)
         return out.reshape(B, n, d), all_idx, all_loss, late
