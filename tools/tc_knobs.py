@@ -3,7 +3,9 @@ import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "vector-quantization-by-ml_b200"))
 import torch
-from vqb200 import ops
+from vqb200 import ops, _lib as _L
+if os.environ.get("VQB_LIB_OVERRIDE"):
+    _L.LIB_PATH = os.path.join(ROOT, os.environ["VQB_LIB_OVERRIDE"])
 dev = torch.device("cuda:0")
 N, K, d = (int(a) for a in sys.argv[1:4]) if len(sys.argv) > 3 else (1 << 20, 8192, 256)
 g = torch.Generator(device=dev).manual_seed(0)
@@ -34,5 +36,6 @@ if cy[3]:
     print(f"                          epi warp total {f(cy[7])} wait tmem_full {f(cy[8])} wait bias {f(cy[9])} tmem ld wait {f(cy[10])} try tmem_full {f(cy[11])}")
 if buf[0] + buf[1]:
     print(f"   ranked chunks {buf[0]}  skipped {buf[1]}  -> ranked fraction {buf[0] / (buf[0] + buf[1]):.3f}")
+print(os.environ.get('VQB_LIB_OVERRIDE','shipped'), end=' ')
 print(f"VQB_DRAIN={os.environ.get('VQB_DRAIN','-')} VQB_CLUSTER={os.environ.get('VQB_CLUSTER','-')} VQB_TC_DEBUG={os.environ.get('VQB_TC_DEBUG','0')} N={N} K={K} d={d}: "
       f"tc kernel {ms:.3f} ms  {2*N*K*d/ms/1e9:.0f} TFLOP/s", flush=True)

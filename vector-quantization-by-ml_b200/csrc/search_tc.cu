@@ -206,6 +206,17 @@ __device__ __forceinline__ void top2_pair(float& m1, float& m2, float a, float b
 
 __device__ unsigned long long g_dbg_cycles[16];    // bring-up only (VQB_TC_DEBUG & 32): where each role waits
 __device__ unsigned long long g_dbg_counters[2];   // bring-up only (VQB_TC_DEBUG & 16): ranked / skipped chunks
+#ifdef VQB_TRACE
+// bring-up only (-DVQB_TRACE): cluster 0 stamps clock64 per tile.  g_trace_mma[role][tile]: 0 tmem_empty seen,
+// 1 MMAs + commits issued, 2 (with -DVQB_TRACE_MMA_LAT) tmem_full seen by the issuing warp itself.
+// g_trace_epi[role][cta rank * 16 + warp][tile]: 0 tmem_full seen, 1 loads done + arrive sent, 2 ranked.
+// The two CTAs of the pair run on different SMs: their clocks are not comparable, intervals are.
+constexpr int kTraceTiles = 256;
+__device__ long long g_trace_mma[3][kTraceTiles];
+__device__ long long g_trace_epi[3][32][kTraceTiles];
+#define VQB_STAMP_MMA(role, t) do { if ((t) < kTraceTiles) g_trace_mma[role][t] = clock64(); } while (0)
+#define VQB_STAMP_EPI(role, w, t) do { if ((t) < kTraceTiles) g_trace_epi[role][w][t] = clock64(); } while (0)
+#endif
 constexpr float kPackSlackTC = 6.2e-5f;   // must equal kPackSlack in search_resolve.cu
 
 // order-preserving float <-> int (involution): lets shared-memory atomicMin work on scores of either sign
@@ -877,35 +888,80 @@ search_aug_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     // =============================== MMA issuer (leader CTA) ===============================
     if (rank == 0) {
       uint32_t stage = 0, ph = 0, a_ph = 0, acc = 0, acc_ph = 0;
+#ifdef VQB_TRACE
+      int tr_t = 0;
+#endif
       for (int g = cid; g < G; g += num_clusters) {
         for (int nt = 0; nt < P.NT; ++nt) {
-          mbar_wait(smem_u32(&bars->tmem_empty[acc]), acc_ph ^ 1u);
-          tc_fence_after();
           const uint32_t d_tmem = tmem_base + acc * (uint32_t)kBlockN;
-          for (int kb = 0; kb < P.KB; ++kb) {
-            if (nt == 0) mbar_wait(smem_u32(&bars->a_full[kb]), a_ph);
+          if (P.KB == 1) {
+            // d_pad = 64: one stage per N tile, and the accumulator hand-off is the critical path (clock stamps,
+            // tools/trace_d64.py: buffer free -> MMAs issued took 760 cycles with the stage wait and the descriptor
+            // arithmetic after the `tmem_empty` wait, 350 with them before it).  The stage has been full for a long
+            // time (the ring runs ahead), so everything that does not need the accumulator goes first.
+            if (nt == 0) mbar_wait(smem_u32(&bars->a_full[0]), a_ph);
             mbar_wait(smem_u32(&bars->full[stage]), ph);
+            const uint32_t b_addr = b_base + stage * kStageStrideAug;
+            const uint32_t ca = b_addr + kStageBytes / 2;
+            const uint64_t adesc = make_sw128_desc(a_base);
+            const uint64_t bdesc = make_sw128_desc(b_addr);
+            const uint64_t xdesc = make_nosw_desc(xa_base, zero_base - xa_base, 128);
+            const uint64_t cdesc = make_nosw_desc(ca, zero_base - ca, 128);
+            asm volatile("" ::"l"(adesc), "l"(bdesc), "l"(xdesc), "l"(cdesc));   // materialised here, not after the wait
+            mbar_wait(smem_u32(&bars->tmem_empty[acc]), acc_ph ^ 1u);   // epilogues of both CTAs drained this buffer
+#ifdef VQB_TRACE
+            if (cid == 0 && lane == 0) VQB_STAMP_MMA(0, tr_t);
+#endif
             tc_fence_after();
             if (elect_one()) {
-              const uint32_t b_addr = b_base + stage * kStageStrideAug;
-              const uint64_t adesc = make_sw128_desc(a_base + kb * kSlabBytes);
-              const uint64_t bdesc = make_sw128_desc(b_addr);
 #pragma unroll
               for (int kk = 0; kk < kBlockK / 16; ++kk)
-                umma_f16_pair(d_tmem, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), kIdescPair,
-                              (kb | kk) != 0 ? 1u : 0u);
-              if (kb == P.KB - 1 && aug) {        // + a (b1 + b2 + b3) = s_row s_c |c|^2/2
-                const uint32_t ca = b_addr + kStageBytes / 2;
-                umma_f16_pair(d_tmem, make_nosw_desc(xa_base, zero_base - xa_base, 128),
-                              make_nosw_desc(ca, zero_base - ca, 128), kIdescPair, 1u);
-              }
+                umma_f16_pair(d_tmem, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), kIdescPair, kk != 0 ? 1u : 0u);
+              if (aug) umma_f16_pair(d_tmem, xdesc, cdesc, kIdescPair, 1u);   // + a (b1 + b2 + b3) = s_row s_c |c|^2/2
+              umma_commit_pair(smem_u32(&bars->tmem_full[acc]));              // the hand-off first
               umma_commit_pair(smem_u32(&bars->empty[stage]));
-              if (nt == P.NT - 1) umma_commit_pair(smem_u32(&bars->a_empty[kb]));
-              if (kb == P.KB - 1) umma_commit_pair(smem_u32(&bars->tmem_full[acc]));
+              if (nt == P.NT - 1) umma_commit_pair(smem_u32(&bars->a_empty[0]));
             }
             __syncwarp();
             if (++stage == (uint32_t)P.S) { stage = 0; ph ^= 1u; }
+          } else {
+            mbar_wait(smem_u32(&bars->tmem_empty[acc]), acc_ph ^ 1u);
+            tc_fence_after();
+            for (int kb = 0; kb < P.KB; ++kb) {
+              if (nt == 0) mbar_wait(smem_u32(&bars->a_full[kb]), a_ph);
+              mbar_wait(smem_u32(&bars->full[stage]), ph);
+              tc_fence_after();
+              if (elect_one()) {
+                const uint32_t b_addr = b_base + stage * kStageStrideAug;
+                const uint64_t adesc = make_sw128_desc(a_base + kb * kSlabBytes);
+                const uint64_t bdesc = make_sw128_desc(b_addr);
+#pragma unroll
+                for (int kk = 0; kk < kBlockK / 16; ++kk)
+                  umma_f16_pair(d_tmem, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), kIdescPair,
+                                (kb | kk) != 0 ? 1u : 0u);
+                if (kb == P.KB - 1 && aug) {        // + a (b1 + b2 + b3) = s_row s_c |c|^2/2
+                  const uint32_t ca = b_addr + kStageBytes / 2;
+                  umma_f16_pair(d_tmem, make_nosw_desc(xa_base, zero_base - xa_base, 128),
+                                make_nosw_desc(ca, zero_base - ca, 128), kIdescPair, 1u);
+                }
+                umma_commit_pair(smem_u32(&bars->empty[stage]));
+                if (nt == P.NT - 1) umma_commit_pair(smem_u32(&bars->a_empty[kb]));
+                if (kb == P.KB - 1) umma_commit_pair(smem_u32(&bars->tmem_full[acc]));
+              }
+              __syncwarp();
+              if (++stage == (uint32_t)P.S) { stage = 0; ph ^= 1u; }
+            }
           }
+#ifdef VQB_TRACE
+          if (cid == 0 && lane == 0) VQB_STAMP_MMA(1, tr_t);
+#ifdef VQB_TRACE_MMA_LAT
+          mbar_wait(smem_u32(&bars->tmem_full[acc]), acc_ph);   // the issuing warp itself watches the accumulator complete
+#endif
+#endif
+#ifdef VQB_TRACE
+          if (cid == 0 && lane == 0) VQB_STAMP_MMA(2, tr_t);
+          ++tr_t;
+#endif
           if (++acc == 2) { acc = 0; acc_ph ^= 1u; }
         }
         a_ph ^= 1u;
@@ -963,6 +1019,12 @@ search_aug_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
             if (nt + par < P.NT) {
               const uint32_t taddr = lane_addr + acc * (uint32_t)kBlockN;
               mbar_wait(smem_u32(&bars->tmem_full[acc]), acc_ph);
+#ifdef VQB_TRACE
+              const int tr_t = (int)(tile_it - 1) * P.NT + nt + par;
+              const bool tr_on = cid == 0 && lane == 0;
+              const int tr_w = (int)rank * 16 + warp;
+              if (tr_on) VQB_STAMP_EPI(0, tr_w, tr_t);
+#endif
               tc_fence_after();
               TMEM_LD16(taddr, rD[0]);
               TMEM_LD16(taddr + 16, rD[DRAIN ? 1 : 0]);
@@ -972,6 +1034,9 @@ search_aug_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
               tc_fence_before();
               __syncwarp();
               if (lane == 0) mbar_arrive_leader(smem_u32(&bars->tmem_empty[acc]));   // buffer handed back: rank from registers
+#ifdef VQB_TRACE
+              if (tr_on) VQB_STAMP_EPI(1, tr_w, tr_t);
+#endif
               if (++acc == 2) { acc = 0; acc_ph ^= 1u; }
               float cmin;
 #define VQB_DRAIN_CHUNK(CH)                                                                                 \
@@ -982,6 +1047,9 @@ search_aug_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
                                           m_run, t_run, row_slot, a1, a2, any_slow, 0);
               VQB_DRAIN_CHUNK(0) VQB_DRAIN_CHUNK(1) VQB_DRAIN_CHUNK(2) VQB_DRAIN_CHUNK(3)
 #undef VQB_DRAIN_CHUNK
+#ifdef VQB_TRACE
+              if (tr_on) VQB_STAMP_EPI(2, tr_w, tr_t);
+#endif
             }
           } else if (nt + par < P.NT) {
             const uint32_t taddr = lane_addr + acc * (uint32_t)kBlockN;
@@ -1325,6 +1393,12 @@ int search_timing(float* host_ms, int cap) {
 
 }  // namespace vqb
 
+#ifdef VQB_TRACE
+extern "C" int vqb_debug_trace(long long* mma, long long* epi) {   // [3][kTraceTiles], [3][32][kTraceTiles]
+  if (cudaMemcpyFromSymbol(mma, vqb::g_trace_mma, sizeof(long long) * 3 * vqb::kTraceTiles) != cudaSuccess) return -1;
+  return cudaMemcpyFromSymbol(epi, vqb::g_trace_epi, sizeof(long long) * 96 * vqb::kTraceTiles) == cudaSuccess ? 0 : -1;
+}
+#endif
 extern "C" int vqb_search_timing(float* host_ms, int cap) { return vqb::search_timing(host_ms, cap); }
 // bring-up aid, not part of include/vqb.h
 extern "C" int vqb_debug_counters(unsigned long long* out2) { return vqb::debug_counters(out2); }
