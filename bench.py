@@ -371,7 +371,7 @@ def bench_c4(ctx, steps, warmup, pk, strong):
     eager_steps = max(2, min(steps, 4))
     # the timed number: the 8-level loop replayed as one CUDA graph per input buffer (ResidualVQ.enable_cuda_graph);
     # warm-up covers the eager pass and the capture of both rotating buffers
-    rvq.enable_cuda_graph()
+    rvq.enable_cuda_graph(data_parallel=True)   # every rank runs this same sequence of forwards
     ms, _, _ = timed_loop(ctx, step, steps, max(warmup, 4) + 2, time_kernels=False)
     launches = launches * steps / eager_steps
     per_level = sum(tc) / max(len(tc), 1)
@@ -396,9 +396,10 @@ def bench_c4(ctx, steps, warmup, pk, strong):
            "steps": steps, "search_kernel_ms_per_level": per_level,
            "search_frac_of_tensor_peak": flops / (per_level / 1e3) / 1e12 / pk["tflops"] if per_level else None,
            "search_kernels_share_of_step": per_level * Q / (ms / steps) if per_level else None,
-           "gpu_launches_per_step": launches / steps, "cuda_graph": ctx.world == 1,
+           "gpu_launches_per_step": launches / steps, "cuda_graph": True,
            "eager_ms_per_step": ms_eager / eager_steps, "autograd_ms_per_step": ms_grad / grad_steps,
-           "note": "ms_per_step: no-grad forward replayed as one CUDA graph on one GPU (eager under data parallelism); "
+           "note": "ms_per_step: no-grad forward replayed as one CUDA graph (under data parallelism the graph holds the "
+                   "per-level statistics all_reduce, launched beside the next level's search); "
                    "autograd_ms_per_step: forward with requires_grad + backward"}
     del rvq, xs
     free_all()

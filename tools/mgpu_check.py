@@ -103,6 +103,54 @@ if not bool(diff.any()):
     check(torch.equal(cbo.cluster_size.cpu(), sto.cluster_size), "DP cluster_size vs oracle")
     check(rel(cbo.embeddings.cpu(), sto.embeddings) < 1e-5, "DP embeddings vs oracle")
 
+# ---------------- 1d. ResidualVQ data parallel: CUDA graph (with the captured statistics all_reduce) == eager ----------------
+from vqb200 import ResidualVQ  # noqa: E402
+
+
+def _make_rvq(thr):
+    torch.manual_seed(0)
+    m = ResidualVQ(dim=64, num_quantizers=4, codebook_params=CodebookParams(dim=64, codebook_size=96,
+                                                                            threshold_ema_dead_code=thr),
+                   sync_codebook=True).to(dev).train()
+    gg = torch.Generator().manual_seed(3)
+    for li, layer in enumerate(m.layers):
+        c = (torch.randn(1, 96, 64, generator=gg) * (0.6 / 1.5 ** li)).to(dev)
+        cb = layer._codebook
+        cb.embeddings.copy_(c); cb.embed_avg.copy_(c); cb.cluster_size.fill_(1.0); cb.invalidate_cache()
+    return m
+
+
+for thr in (0, 2):
+    eager, graphed = _make_rvq(thr), _make_rvq(thr)
+    graphed.enable_cuda_graph(data_parallel=True)
+    gg = torch.Generator().manual_seed(11 + rank)
+    x_e = torch.empty(3, 700, 64, device=dev)
+    x_g = torch.empty(3, 700, 64, device=dev)
+    for step in range(5):
+        xx = torch.randn(3, 700, 64, generator=gg)
+        x_e.copy_(xx); x_g.copy_(xx)
+        torch.manual_seed(100 + step)
+        with torch.no_grad():
+            qe, ie, le = eager(x_e)
+        torch.manual_seed(100 + step)
+        with torch.no_grad():
+            qg, ig, lg = graphed(x_g)
+        check(torch.equal(qe, qg) and torch.equal(ie, ig) and torch.equal(le, lg), f"RVQ DP graph step {step} thr {thr}: outputs")
+        for le_, lg_ in zip(eager.layers, graphed.layers):
+            for name in ("embeddings", "embed_avg", "cluster_size"):
+                check(torch.equal(getattr(le_._codebook, name), getattr(lg_._codebook, name)),
+                      f"RVQ DP graph step {step} thr {thr}: {name}")
+    check(any(isinstance(v, tuple) for v in graphed._graphs.values()), "RVQ DP graph was never captured")
+    # a captured graph holds NCCL kernels of this communicator: release it before the process group goes away
+    # (destroy_process_group with such a graph alive never returned on two B200s)
+    graphed.enable_cuda_graph(False)
+    del eager, graphed
+import gc  # noqa: E402
+gc.collect()
+torch.cuda.synchronize()
+if rank == 0:
+    print("1d. ResidualVQ data-parallel CUDA graph == eager: ok", flush=True)
+
 # ---------------- 2. sharded codebook, through the module API, against the ORACLE (un-sharded reference path) -------
 # codebooks.py:350-435 on the whole codebook is the oracle; the sharded path must give its indices (outside the
 # reference's own 1e-6 ties), bit-exact quantize, and on every rank the matching rows of its EMA + expiry result
@@ -153,4 +201,6 @@ for mode in ("replicated", "all_gather"):
     check(tuple(sd["_codebook.embeddings"].shape) == (1, K, d), "state_dict must hold the full codebook")
 if rank == 0:
     print("MGPU OK", flush=True)
+torch.cuda.synchronize()
+dist.barrier()
 dist.destroy_process_group()

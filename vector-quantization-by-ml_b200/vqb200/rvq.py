@@ -228,15 +228,20 @@ class ResidualVQ(nn.Module):
             cb.expire_codes_(r[None])
 
     # ------------------------------------------------------------------ CUDA graph of the fused level loop (opt-in)
-    def enable_cuda_graph(self, flag: bool = True, max_graphs: int = 4) -> "ResidualVQ":
+    def enable_cuda_graph(self, flag: bool = True, max_graphs: int = 4, data_parallel: bool = False) -> "ResidualVQ":
         """Replay the fused level loop (~25 launches per level) as ONE CUDA graph per (input address, shape, mode).
         Opt-in because graph outputs are STATIC buffers: the tensors returned by a forward are overwritten by the next
         forward on the same input address (clone what must survive).  The first forward on a new input address runs
         eagerly, the second captures, later ones replay; the dead-code check stays outside the graph (one host sync
         per forward, as in eager mode).  Not used while a codebook still needs its kmeans init, with a mask, with
-        quantize-dropout, a shared codebook, under data parallelism (the per-level all_reduce is not captured), or while
-        `ops.TIME_SEARCH_KERNEL` brackets kernels with events."""
+        quantize-dropout, a shared codebook, or while `ops.TIME_SEARCH_KERNEL` brackets kernels with events.
+        Under data parallelism the graph holds the per-level statistics all_reduce (NCCL collectives are capturable);
+        that needs `data_parallel=True` as a promise that EVERY rank enables the graph and calls forward with the same
+        sequence of (shape, mode) keys -- a rank that replays while another captures or runs eagerly would dead-lock
+        in the collective.  Call `enable_cuda_graph(False)` before `destroy_process_group()`: a live graph keeps
+        kernels of the communicator."""
         self._graph_on = bool(flag)
+        self._graph_ddp = bool(data_parallel)
         self._graph_max = int(max_graphs)
         self._graphs = {}
         return self
@@ -247,11 +252,14 @@ class ResidualVQ(nn.Module):
         if torch.is_grad_enabled() and x.requires_grad:
             return False        # the autograd form of the fused loop (`_FusedRVQ`) runs eagerly
         books = [l._codebook for l in self.layers]
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1 and any(b.use_ddp for b in books):
-            return False        # the statistics all_reduce of every level would have to be captured on all ranks at once
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1 and any(b.use_ddp for b in books) \
+                and not getattr(self, "_graph_ddp", False):
+            return False        # the statistics all_reduce of every level has to be captured on all ranks at once
         return len({id(b) for b in books}) == len(books) and all(b.is_initialized and not b.sharded for b in books)
 
     def _forward_graphed(self, x, freeze_codebook):
+        # under data parallelism the ranks' input addresses differ, their SEQUENCE of keys must not: the k-th distinct
+        # address of a rank stands for the k-th of every other rank
         key = (x.data_ptr(), tuple(x.shape), x.dtype, bool(freeze_codebook), self.training, x.device.index)
         ent = self._graphs.get(key)
         if ent is None:
