@@ -52,6 +52,7 @@ extern "C" {
 #define VQB_SEARCH_LATENTS_PREPARED 1  /* ws already holds the scaled fp16 latents, row scales, bias operands and row stats (written by vqb_rvq_level[_ema] or vqb_l2norm_prepare against the SAME codebook cache) */
 #define VQB_SEARCH_FORCE_EXACT      2  /* skip the tensor-core pass: fp32/fp64 CUDA-core scan of every code */
 #define VQB_SEARCH_TIMING           4  /* bracket the tensor-core kernel with CUDA events (see vqb_search_timing) */
+#define VQB_SEARCH_FUSED_PREP       8  /* opt-in: 16-bit latents are converted to the fp16 operands INSIDE the tensor-core kernel (two extra warps per CTA, behind a sampled bound of the row norms; rows above it are rescanned exactly) instead of by a separate pass.  Same results; on B200 the converter warps cost the kernel what the separate pass costs, so it is off by default.  Ignored when the problem does not qualify (fp32 latents, d > 256 or d % 8, little tensor work per row tile). */
 
 int         vqb_version(void);
 const char* vqb_last_error(void);

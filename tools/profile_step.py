@@ -75,5 +75,19 @@ with torch.no_grad():
 if rank == 0:
     print("(3 profiled steps: divide the totals by 3)")
     print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=40, max_name_column_width=64), flush=True)
+if rank == 0 and os.environ.get("VQB_TIMELINE"):
+    # device timeline of the LAST profiled step: every kernel with its start offset, duration and the idle gap before it
+    from torch.autograd import DeviceType
+    evs = sorted((e for e in prof.events() if e.device_type == DeviceType.CUDA), key=lambda e: e.time_range.start)
+    per = len(evs) // 3
+    last = evs[-per:]
+    t0, prev_end, idle = last[0].time_range.start, last[0].time_range.start, 0.0
+    print(f"timeline of one step ({per} device activities): start_us  dur_us  gap_before_us  name")
+    for e in last:
+        gap = e.time_range.start - prev_end
+        idle += max(gap, 0.0)
+        print(f"  {e.time_range.start - t0:9.1f} {e.time_range.end - e.time_range.start:9.1f} {gap:7.1f}  {e.name[:90]}")
+        prev_end = max(prev_end, e.time_range.end)
+    print(f"span {prev_end - t0:.1f} us, idle between kernels {idle:.1f} us")
 if world > 1:
     dist.destroy_process_group()

@@ -240,16 +240,30 @@ inline int dtype_size(int dt) { return dt == VQB_F32 ? 4 : 2; }
 int launch_prepare_latents(const void* x, int x_dtype, int64_t rows, int64_t rows_per_head, int d, int dp,
                            const float* chdr, __half* xb, float* xinv, float* xn2, __half* xaug, uint32_t* scal,
                            cudaStream_t st);
+// derive_dx_dp > 0: the residual bound |x - x~| is not in scal[1] but derived from scal[0] by dx_bound_16bit()
+// (16-bit latents converted inside the search kernel: search_tc.cu, CONV)
 int launch_make_bias(const void* cache, const CacheLayout& CL, int64_t H, int K, int metric,
-                     uint32_t* scal, float* bias, float* err, __half* caug, cudaStream_t st);
+                     uint32_t* scal, float* bias, float* err, __half* caug, cudaStream_t st, int derive_dx_dp = 0);
+// In-kernel conversion of 16-bit latents (search_tc.cu, CONV): scal[0] = bound of the row norms from a strided sample
+// (times kSampleGuard); the search kernel converts every row itself and sends rows that exceed the bound to the exact
+// rescan (negative xinv), so the bound only has to be right for the rows that keep their tensor-core candidates.
+int launch_sample_bound(const void* x, int x_dtype, int64_t rows, int d, uint32_t* scal, cudaStream_t st);
+struct ConvArgs {
+  const void* x = nullptr;   // raw latents [H][N][d], bf16 or fp16; nullptr: operands were prepared by a separate pass
+  int x_dtype = 0;
+  int d = 0;
+};
 // xaug / caug: the bias k-step operands (both NULL: bias added in the epilogue from `bias`)
 // aug_mode (search_tc_aug_mode): 0 = bias added in the epilogue from `bias`; 1 = bias as an extra MMA k-step;
 // 2 = same kernel without the k-step (dot metric, no padded codes)
 // xn2 / tie: per-row bound of |x|^2 and the tie-window coefficient (kTieSlack for the Euclidean metric, 0 for dot)
 int launch_search_tc(const __half* xb, const float* xinv, const float* xn2, float tie, const __half* xaug,
                      const __half* cb, const __half* caug, const float* chdr, const float* bias, int aug_mode,
-                     int64_t H, int64_t N, int K, int dp, void* cand, uint32_t* scal, bool timing, cudaStream_t st);
+                     int64_t H, int64_t N, int K, int dp, void* cand, uint32_t* scal, bool timing, cudaStream_t st,
+                     const ConvArgs& conv = ConvArgs());
 int search_tc_aug_mode(int64_t N, int K, int metric);
+// 1 when the search kernel converts 16-bit latents itself (no separate prepare pass) for this problem
+int search_tc_conv_ok(int64_t N, int K, int d, int x_dtype, int aug_mode, int requested);
 
 int launch_loss_finalize(const double* part, const long long* cntp, int nblocks, int d, float* loss_out,
                          cudaStream_t st);
@@ -273,6 +287,15 @@ constexpr float kTieSlack = 5.0e-7f;
 // upper bound of |x|^2 from |x~|^2 and |x - x~|^2
 __device__ __forceinline__ float row_norm2_bound(float n2, float r2) {
   return (n2 + 2.f * sqrtf(n2 * r2) + r2) * 1.0001f;
+}
+
+// 16-bit latents times a power of two are fp16 numbers unless they land in fp16's subnormal range, where the rounding
+// error is at most 2^-25 per element: |x - x~| <= sqrt(dp) 2^-25 / s_row, and 1 / s_row <= max(|x|_max 2^-13,
+// 1 / cap) with cap = 2^15 2^q the clamp of clamp_row_scale (two_mq = 2^-q).  Bound for every row with |x| <= xmax.
+constexpr float kSampleGuard = 1.125f;
+__device__ __forceinline__ float dx_bound_16bit(float xmax, int dp, float two_mq) {
+  const float inv_s = fmaxf(xmax * 1.220703125e-4f, two_mq * 3.0517578125e-5f);     // 2^-13, 2^-15
+  return sqrtf((float)dp) * 2.9802322e-8f * inv_s * 1.01f;
 }
 
 // pow2_scale(m) from the exponent field (same value for every input, a handful of integer instructions)

@@ -421,11 +421,53 @@ int launch_prepare_latents(const void* x, int x_dtype, int64_t rows, int64_t row
   return VQB_OK;
 }
 
+// Strided sample of the rows: scal[0] = kSampleGuard * max |x_row| over the sample (in-kernel conversion, search_tc.cu).
+// One warp per sampled row, d % 8 == 0, d <= 256.
+template <typename T>
+__global__ void __launch_bounds__(256)
+sample_bound_kernel(const T* __restrict__ x, int64_t rows, int64_t stride, int64_t nsample, int d,
+                    uint32_t* __restrict__ scal) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int64_t i = (int64_t)blockIdx.x * 8 + w;
+  float n2 = 0.f;
+  if (i < nsample) {
+    const int64_t row = i * stride < rows ? i * stride : rows - 1;
+    const int j = lane * 8;
+    if (j < d) {
+      const F8 vv = raw_to_f8(load_raw8<T>(x + row * (int64_t)d + j));
+#pragma unroll
+      for (int e = 0; e < 8; ++e) n2 = fmaf(vv.v[e], vv.v[e], n2);
+    }
+    n2 = warp_sum(n2);
+  }
+  __shared__ float s_n[8];
+  if (lane == 0) s_n[w] = n2;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float mn = 0.f;
+    for (int k = 0; k < 8; ++k) mn = fmaxf(mn, s_n[k]);
+    if (mn > 0.f && mn < 3.0e38f) atomicMax(scal + 0, __float_as_uint(sqrtf(mn) * kSampleGuard));
+  }
+}
+
+int launch_sample_bound(const void* x, int x_dtype, int64_t rows, int d, uint32_t* scal, cudaStream_t st) {
+  VQB_REQUIRE(x_dtype != VQB_F32 && d % 8 == 0 && d <= 256, VQB_ERR_UNSUPPORTED, "sample_bound: 16-bit rows of d <= 256");
+  const int64_t nsample = rows < 16384 ? rows : 16384;
+  const int64_t stride = rows / nsample;
+  const unsigned blocks = (unsigned)((nsample + 7) / 8);
+  if (x_dtype == VQB_BF16)
+    sample_bound_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)x, rows, stride, nsample, d, scal);
+  else
+    sample_bound_kernel<__half><<<blocks, 256, 0, st>>>((const __half*)x, rows, stride, nsample, d, scal);
+  VQB_LAUNCH_CHECK();
+  return VQB_OK;
+}
+
 // E_k = Xmax*|c_k - c~_k| + DXmax*|c_k| + accumulation slack;  bias_k = |c_k|^2/2 - E_k
 __global__ void make_bias_kernel(const float* __restrict__ cn2h, const float* __restrict__ cn,
                                  const float* __restrict__ dcn, int64_t total, int Kp, int K,
                                  const float* __restrict__ hdr, uint32_t* __restrict__ scal,
-                                 float* __restrict__ bias, float* __restrict__ err) {
+                                 float* __restrict__ bias, float* __restrict__ err, int derive_dx_dp) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   float e = 0.f;
   if (i < total) {
@@ -435,7 +477,9 @@ __global__ void make_bias_kernel(const float* __restrict__ cn2h, const float* __
       bias[i] = kPadBias;
       err[i] = 0.f;
     } else {
-      const float xmax = __uint_as_float(scal[0]), dxmax = __uint_as_float(scal[1]);
+      const float xmax = __uint_as_float(scal[0]);
+      const float dxmax = derive_dx_dp > 0 ? dx_bound_16bit(xmax, derive_dx_dp, hdr[(i / Kp) * kHdrFloats + 5])
+                                           : __uint_as_float(scal[1]);
       const float c = cn[i], h = cn2h[i];
       // products are exact in the tensor core (fp16 x fp16 = 22 bits, fits fp32); accumulation is fp32-ish:
       // allow 2^-16 of the largest possible |sum| plus the fp32 rounding of |c|^2/2.
@@ -487,13 +531,13 @@ __global__ void make_bias_operand_kernel(const float* __restrict__ cn2h, const f
 }
 
 int launch_make_bias(const void* cache, const CacheLayout& CL, int64_t H, int K, int metric,
-                     uint32_t* scal, float* bias, float* err, __half* caug, cudaStream_t st) {
+                     uint32_t* scal, float* bias, float* err, __half* caug, cudaStream_t st, int derive_dx_dp) {
   (void)metric;
   const char* base = (const char*)cache;
   int64_t total = H * (int64_t)CL.Kp;
   make_bias_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
       (const float*)(base + CL.off_cn2h), (const float*)(base + CL.off_cn), (const float*)(base + CL.off_dcn),
-      total, CL.Kp, K, (const float*)(base + CL.off_hdr), scal, bias, err);
+      total, CL.Kp, K, (const float*)(base + CL.off_hdr), scal, bias, err, derive_dx_dp);
   VQB_LAUNCH_CHECK();
   if (caug) {
     make_bias_operand_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(

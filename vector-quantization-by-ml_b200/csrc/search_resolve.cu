@@ -571,16 +571,28 @@ extern "C" int vqb_search(const void* x, int x_dtype, const float* codebook, con
   int rc;
   __half* xaug = (__half*)(w + SL.off_xaug);
   const float* chdr = (const float*)(cbase + CL.off_hdr);
-  if (!prepared) {
+  const int aug = search_tc_aug_mode(N, K, metric);
+  // 16-bit latents and enough tensor work per row tile: the search kernel converts the rows itself, overlapped with
+  // its MMAs (search_tc.cu, CONV); all that runs ahead of it is a strided sample that bounds the row norms
+  ConvArgs conv;
+  const int conv_mode = prepared ? 0 : search_tc_conv_ok(N, K, d, x_dtype, aug, (flags & VQB_SEARCH_FUSED_PREP) != 0);
+  if (conv_mode == 2) {
+    rc = launch_prepare_latents(x, x_dtype, H * N, N, d, SL.dp, chdr, xb, xinv, xn2, xaug, scal, st);
+    if (rc) return rc;
+    conv.x = x; conv.x_dtype = -1; conv.d = d;
+  } else if (conv_mode == 1) {
+    conv.x = x; conv.x_dtype = x_dtype; conv.d = d;
+    rc = launch_sample_bound(x, x_dtype, H * N, d, scal, st);
+    if (rc) return rc;
+  } else if (!prepared) {
     rc = launch_prepare_latents(x, x_dtype, H * N, N, d, SL.dp, chdr, xb, xinv, xn2, xaug, scal, st);
     if (rc) return rc;
   }
-  const int aug = search_tc_aug_mode(N, K, metric);
   __half* caug = (__half*)(w + SL.off_caug);
-  rc = launch_make_bias(cache, CL, H, K, metric, scal, bias, err, aug == 1 ? caug : nullptr, st);
+  rc = launch_make_bias(cache, CL, H, K, metric, scal, bias, err, aug == 1 ? caug : nullptr, st, conv_mode == 1 ? SL.dp : 0);
   if (rc) return rc;
   rc = launch_search_tc(xb, xinv, xn2, tie, xaug, (const __half*)(cbase + CL.off_cb), caug, chdr,
-                        bias, aug, H, N, K, SL.dp, w + SL.off_cand, scal, (flags & VQB_SEARCH_TIMING) != 0, st);
+                        bias, aug, H, N, K, SL.dp, w + SL.off_cand, scal, (flags & VQB_SEARCH_TIMING) != 0, st, conv);
   if (rc) return rc;
   const int64_t total = H * N;
   int* rr_list = (int*)(w + SL.off_rr);

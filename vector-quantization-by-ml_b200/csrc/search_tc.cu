@@ -754,6 +754,12 @@ struct AugParams {
   int64_t N;
   int Kp, H, KB, NT, S, GPH;
   int aug;             // 0: dot metric with K % 256 == 0 -- no bias k-step at all
+  // CONV: the kernel converts the caller's 16-bit latents itself (two extra warps, a row tile or two ahead of the
+  // TMA producer) into the fp16 operand arrays that the pointers above name
+  const void* xraw;    // [H][N][d] bf16 / fp16
+  const __half* xb_w;  // [H][N][dp] the A operand array behind map_x
+  const __half* xaug_w;
+  int xdtype, d, dp;
 };
 
 struct AugBarriers {
@@ -763,10 +769,79 @@ struct AugBarriers {
   uint64_t a_empty[kMaxKB];
   uint64_t tmem_full[2];
   uint64_t tmem_empty[2];
+  uint64_t conv_full[2];      // CONV: both converter warps wrote the operands of a row tile (count 2)
+  uint64_t conv_empty[2];     // CONV: the producer took that row tile: the converters may run two tiles ahead
   uint32_t tmem_base;
   uint32_t pad;
   int rowmin[3][kBlockM];     // see Barriers::rowmin
 };
+
+// One warp converts rows [r0, r1) of codebook `h` exactly as prepare_latents4_kernel does for 16-bit latents (same
+// scale, same fp16 values, same bounds), 8 rows in flight.  A row whose statistics exceed the bounds the bias
+// operand was built with (scal[0] from the strided sample, the residual bound derived from it) gets a NEGATIVE xinv:
+// resolve rescans it exactly.
+template <typename T>
+__device__ __forceinline__ void convert_rows16(const T* __restrict__ x, int64_t base, int64_t r0, int64_t r1, int d,
+                                               int dp, float two_q, float two_mq, float x0sq, float x1sq,
+                                               __half* __restrict__ xb, float* __restrict__ xinv,
+                                               float* __restrict__ xn2, __half* __restrict__ xaug, int lane) {
+  // Few registers on purpose: this code shares the kernel's 96-register budget with the epilogue; when it spilled,
+  // its local-memory traffic went through the 13 KB of L1 that the kernel leaves and slowed the epilogue warps too.
+  constexpr int U = 4;
+  const int j = lane * 8;
+  const bool on = j < d;
+  const float infl = (1.f + (float)dp * 2.4e-7f) * 1.00003f;
+  for (int64_t row0 = r0; row0 < r1; row0 += U) {
+    Raw8<T> raw[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      raw[u] = load_raw8<T>(x + (on && row0 + u < r1 ? (base + row0 + u) * (int64_t)d + j : 0));
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (row0 + u >= r1) break;                 // warp-uniform
+      F8 vv = raw_to_f8(raw[u]);
+      if (!on) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) vv.v[e] = 0.f;
+      }
+      float m = 0.f;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) m = fmaxf(m, fabsf(vv.v[e]));
+      // non-negative floats order like their bit patterns: one REDUX instead of five shuffle + max steps
+      m = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(m)));
+      float s = pow2_scale_bits(m);
+      const float a = clamp_row_scale(s, two_q, two_mq);
+      const float is = pow2_recip(s);
+      float n2 = 0.f;
+      uint32_t pk[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float v0 = vv.v[2 * e], v1 = vv.v[2 * e + 1];
+        const __half2 hh = __floats2half2_rn(v0 * s, v1 * s);
+        pk[e] = *reinterpret_cast<const uint32_t*>(&hh);
+        n2 = fmaf(v0, v0, n2);
+        n2 = fmaf(v1, v1, n2);
+      }
+      if (j < dp)
+        *reinterpret_cast<uint4*>(xb + (base + row0 + u) * (int64_t)dp + j) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      // |x|^2 as an integer sum (one REDUX): the lane's part in units of m^2 2^-20, rounded UP; 8 m^2 per lane at most
+      // -> < 2^24 per lane, < 2^29 per row.  An upper bound of the fp32 sum prepare_latents4 forms, within 2^-15.
+      const float unit = m * m * 9.5367431640625e-7f;     // m^2 2^-20
+      const uint32_t q = unit > 0.f ? (uint32_t)__float2uint_ru(__fdividef(n2, unit) * 1.000001f) + 1u : 0u;
+      n2 = (float)__reduce_add_sync(0xffffffffu, q) * unit * 1.000001f;
+      const float rb = 2.9802322e-8f * is;                       // 2^-25 / s
+      const float r2 = m > 0.f ? (float)dp * rb * rb * 1.0001f : 0.f;   // an all-zero row converts exactly
+      n2 = n2 * 1.000001f + r2 * 1.0001e6f;
+      const bool ok = n2 * infl <= x0sq && r2 * infl <= x1sq;      // squares of the bounds: no square roots here
+      if (lane == 0) {
+        xinv[base + row0 + u] = (a > 0.f && ok) ? is : -is;
+        xn2[base + row0 + u] = n2 * 1.0001f + r2 * 10002.f;        // (|x~| + |x - x~|)^2 <= n2 (1 + e) + r2 (1 + 1/e)
+        const uint32_t aa = (uint32_t)__half_as_ushort(__float2half_rn(a));
+        *reinterpret_cast<uint4*>(xaug + (base + row0 + u) * 8) = make_uint4(aa | (aa << 16), aa, 0u, 0u);
+      }
+    }
+  }
+}
 
 template <bool WAIT = true>
 __device__ __forceinline__ float chunk_min16(const uint32_t (&r)[16]) {
@@ -787,8 +862,9 @@ __device__ __forceinline__ float chunk_min16(const uint32_t (&r)[16]) {
 // latency.  Costs 64 live accumulator registers: 18 warps (the TMA warp also allocates TMEM and writes the zero
 // chunk) x 32 x 112 registers.
 constexpr int kThreadsDrain = 576;
-template <bool DRAIN>
-__global__ void __launch_bounds__(DRAIN ? kThreadsDrain : kThreads, 1)
+constexpr int kThreadsConv = 640;      // + two converter warps (18, 19)
+template <bool DRAIN, bool CONV = false>
+__global__ void __launch_bounds__(CONV ? kThreadsConv : (DRAIN ? kThreadsDrain : kThreads), 1)
 search_aug_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_c,
                   const __grid_constant__ CUtensorMap map_xa, const __grid_constant__ CUtensorMap map_ca,
                   const AugParams P) {
@@ -830,6 +906,8 @@ search_aug_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     for (int i = 0; i < 2; ++i) {
       mbar_init(smem_u32(&bars->tmem_full[i]), 1);
       mbar_init(smem_u32(&bars->tmem_empty[i]), 2 * kNumEpiWarps);
+      mbar_init(smem_u32(&bars->conv_full[i]), 2);
+      mbar_init(smem_u32(&bars->conv_empty[i]), 1);
     }
     fence_barrier_init();
   }
@@ -851,11 +929,23 @@ search_aug_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
 
   if (warp == kWarpTma) {
     // =============================== TMA producer ===============================
-    uint32_t stage = 0, ph = 0, a_ph = 0;
+    uint32_t stage = 0, ph = 0, a_ph = 0, c_it = 0;
     for (int g = cid; g < G; g += num_clusters) {
       const int h = g / P.GPH;
       const int mt = (g - h * P.GPH) * 2 + (int)rank;
       const int row0 = mt * kBlockM;
+      if (CONV) {   // the operands of this row tile are in global memory (written by this CTA's converter warps)
+#ifdef VQB_TRACE
+        if (cid == 0 && rank == 0 && lane == 0) VQB_STAMP_EPI(0, 20, (int)c_it);
+#endif
+        mbar_wait(smem_u32(&bars->conv_full[c_it & 1u]), (c_it >> 1) & 1u);
+#ifdef VQB_TRACE
+        if (cid == 0 && rank == 0 && lane == 0) VQB_STAMP_EPI(1, 20, (int)c_it);
+#endif
+        if (elect_one()) mbar_arrive(smem_u32(&bars->conv_empty[c_it & 1u]));
+        __syncwarp();
+        ++c_it;
+      }
       for (int nt = 0; nt < P.NT; ++nt) {
         for (int kb = 0; kb < P.KB; ++kb) {
           const bool last = kb == P.KB - 1;
@@ -967,6 +1057,50 @@ search_aug_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
         a_ph ^= 1u;
       }
     }
+  } else if (CONV && warp >= 18) {
+    // =============================== converter warps (CONV) ===============================
+    // Each converts 64 of the CTA's 128 rows of every row tile, in the CTA's own tile order, at most two row tiles
+    // ahead of the producer: the fp16 rows are still in L2 when the TMA load comes for them.  The tensor pipe is the
+    // bound of this kernel and HBM nearly idle, so the conversion pass costs nothing on the step's critical path.
+    const int cw = warp - 18;
+    const float x0 = __uint_as_float(P.scal[0]);
+    const float x0sq = x0 * x0 * 0.99999f;
+    uint32_t c_it = 0;
+    for (int g = cid; g < G; g += num_clusters, ++c_it) {
+      const int h = g / P.GPH;
+      const int mt = (g - h * P.GPH) * 2 + (int)rank;
+#ifdef VQB_TRACE
+      if (cid == 0 && rank == 0 && lane == 0) VQB_STAMP_EPI(0, 18 + cw, (int)c_it);
+#endif
+      mbar_wait(smem_u32(&bars->conv_empty[c_it & 1u]), ((c_it >> 1) & 1u) ^ 1u);
+#ifdef VQB_TRACE
+      if (cid == 0 && rank == 0 && lane == 0) VQB_STAMP_EPI(1, 18 + cw, (int)c_it);
+#endif
+      const int64_t r0 = (int64_t)mt * kBlockM + cw * (kBlockM / 2);
+      const int64_t r1 = r0 + kBlockM / 2 < P.N ? r0 + kBlockM / 2 : P.N;
+      const float two_q = P.chdr[h * kHdrFloats + 4], two_mq = P.chdr[h * kHdrFloats + 5];
+      const float x1 = dx_bound_16bit(x0, P.dp, two_mq);
+      const float x1sq = x1 * x1 * 0.99999f;
+      const int64_t base = (int64_t)h * P.N;
+      if (r0 < r1 && P.xdtype >= 0) {
+        if (P.xdtype == VQB_BF16)
+          convert_rows16<__nv_bfloat16>((const __nv_bfloat16*)P.xraw, base, r0, r1, P.d, P.dp, two_q, two_mq, x0sq, x1sq,
+                                        const_cast<__half*>(P.xb_w), const_cast<float*>(P.xinv),
+                                        const_cast<float*>(P.xn2), const_cast<__half*>(P.xaug_w), lane);
+        else
+          convert_rows16<__half>((const __half*)P.xraw, base, r0, r1, P.d, P.dp, two_q, two_mq, x0sq, x1sq,
+                                 const_cast<__half*>(P.xb_w), const_cast<float*>(P.xinv), const_cast<float*>(P.xn2),
+                                 const_cast<__half*>(P.xaug_w), lane);
+      }
+      // generic-proxy global writes -> read by the TMA unit (async proxy) of this CTA
+      asm volatile("fence.proxy.async;" ::: "memory");
+      __threadfence_block();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&bars->conv_full[c_it & 1u]));
+#ifdef VQB_TRACE
+      if (cid == 0 && rank == 0 && lane == 0) VQB_STAMP_EPI(2, 18 + cw, (int)c_it);
+#endif
+    }
   } else if (warp < kNumEpiWarps) {
     // =============================== epilogue: packed running top-2 on raw accumulators ===============================
     const int q = warp & 3;
@@ -992,9 +1126,15 @@ search_aug_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
 #pragma unroll
       for (int c = 0; c < 2; ++c) { M1[c] = INF; M2[c] = INF; M3[c] = INF; C1[c] = -1; C2[c] = -1; C3[c] = -1; }
       // key = s_row s_c score: inv undoes it (exact, powers of two); thresholds live in the scaled units
-      const float inv = row < P.N ? fabsf(P.xinv[(size_t)h * P.N + row]) * P.chdr[h * kHdrFloats + 1] : 0.f;
-      // candidate window of this row in its scaled units: Emax part + the fp32 distance-tie part
-      const float trow = inv > 0.f ? (tconst + P.tie * P.xn2[(size_t)h * P.N + row]) / inv : 0.f;
+      // CONV: the row scalars are written by this CTA's converter warps, possibly only moments ago (first row tile of
+      // the kernel): they are read after the row tile's first `tmem_full` wait, which orders them (converter ->
+      // producer -> TMA -> MMA -> here); read at this point they could still be what an earlier search left behind
+      float inv = 0.f, trow = 0.f;
+      if (!CONV) {
+        inv = row < P.N ? fabsf(P.xinv[(size_t)h * P.N + row]) * P.chdr[h * kHdrFloats + 1] : 0.f;
+        // candidate window of this row in its scaled units: Emax part + the fp32 distance-tie part
+        trow = inv > 0.f ? (tconst + P.tie * P.xn2[(size_t)h * P.N + row]) / inv : 0.f;
+      }
       uint32_t idmask;
       asm volatile("mov.u32 %0, 0xFFFFFFC0;" : "=r"(idmask));
       float m_run = INF, t_run = INF;
@@ -1019,6 +1159,12 @@ search_aug_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
             if (nt + par < P.NT) {
               const uint32_t taddr = lane_addr + acc * (uint32_t)kBlockN;
               mbar_wait(smem_u32(&bars->tmem_full[acc]), acc_ph);
+              if (CONV && nt == 0 && par == 0) {
+                const volatile float* vx = P.xinv;
+                const volatile float* vn = P.xn2;
+                inv = row < P.N ? fabsf(vx[(size_t)h * P.N + row]) * P.chdr[h * kHdrFloats + 1] : 0.f;
+                trow = inv > 0.f ? (tconst + P.tie * vn[(size_t)h * P.N + row]) / inv : 0.f;
+              }
 #ifdef VQB_TRACE
               const int tr_t = (int)(tile_it - 1) * P.NT + nt + par;
               const bool tr_on = cid == 0 && lane == 0;
@@ -1234,10 +1380,31 @@ int search_tc_aug_mode(int64_t N, int K, int metric) {
   return (metric == VQB_DOT && K % kBlockN == 0) ? 2 : 1;
 }
 
+static int drain_env() {     // env VQB_DRAIN=0: chunk-by-chunk epilogue (the TMEM buffer is held while it is ranked)
+  static int drain = -1;
+  if (drain < 0) { const char* e = getenv("VQB_DRAIN"); drain = e ? atoi(e) : 1; }
+  return drain;
+}
+
+// In-kernel conversion of 16-bit latents (CONV, opt-in: VQB_SEARCH_FUSED_PREP): the two converter warps keep up when
+// a row tile carries enough tensor work; below that the separate prepare pass stays.
+// env VQB_FUSED_PREP: 1 = on for every qualifying search, 0 = never, 2 = bring-up (converter warps present but idle,
+// operands from the separate pass); unset: the caller's flag decides.
+int search_tc_conv_ok(int64_t N, int K, int d, int x_dtype, int aug_mode, int requested) {
+  static int env = -2;
+  if (env == -2) { const char* e = getenv("VQB_FUSED_PREP"); env = e ? atoi(e) : -1; }
+  const int on = env >= 0 ? env : (requested ? 1 : 0);
+  if (on == 2) return 2;
+  if (!on || !aug_mode || !drain_env() || x_dtype == VQB_F32 || (d & 7) || d > 256) return 0;
+  const int dp = d_pad(d);
+  const int64_t work = (int64_t)(k_pad(K) / kBlockN) * (dp / kBlockK);       // MMA k-blocks per row tile
+  return (work >= 96 && N >= 64 * kBlockM) ? 1 : 0;
+}
+
 static int launch_aug(const __half* xb, const float* xinv, const float* xn2, float tie, const __half* xaug,
                       const __half* cb, const __half* caug,
                       const float* chdr, int64_t H, int64_t N, int K, int dp, int aug_on, void* cand, uint32_t* scal,
-                      bool timing, cudaStream_t st) {
+                      bool timing, cudaStream_t st, const ConvArgs& conv) {
   const int Kp = k_pad(K);
   static int num_sms = 0;
   int dev = 0;
@@ -1247,11 +1414,15 @@ static int launch_aug(const __half* xb, const float* xinv, const float* xn2, flo
   if (dev < 0 || dev >= 64 || !configured[dev]) {
     VQB_CUDA_TRY(cudaFuncSetAttribute(search_aug_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     VQB_CUDA_TRY(cudaFuncSetAttribute(search_aug_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    VQB_CUDA_TRY(cudaFuncSetAttribute(search_aug_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      227 * 1024));
     if (dev >= 0 && dev < 64) configured[dev] = true;
   }
-  static int drain = -1;     // env VQB_DRAIN=0: chunk-by-chunk epilogue (the TMEM buffer is held while it is ranked)
-  if (drain < 0) { const char* e = getenv("VQB_DRAIN"); drain = e ? atoi(e) : 1; }
+  const int drain = drain_env();
+  const bool do_conv = conv.x != nullptr;
+  VQB_REQUIRE(!do_conv || drain, VQB_ERR_INVALID, "in-kernel latent conversion needs the draining epilogue");
   AugParams P;
+  P.xraw = conv.x; P.xdtype = conv.x_dtype; P.d = conv.d; P.dp = dp; P.xb_w = xb; P.xaug_w = xaug;
   P.xinv = xinv; P.xn2 = xn2; P.tie = tie; P.chdr = chdr; P.cand = cand; P.scal = scal; P.N = N; P.Kp = Kp;
   P.H = (int)H;
   P.KB = dp / kBlockK;
@@ -1279,7 +1450,7 @@ static int launch_aug(const __half* xb, const float* xinv, const float* xn2, flo
   if (rc) return rc;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(nclusters * 2));
-  cfg.blockDim = dim3(drain ? kThreadsDrain : kThreads);
+  cfg.blockDim = dim3(do_conv ? kThreadsConv : (drain ? kThreadsDrain : kThreads));
   cfg.dynamicSmemBytes = smem_bytes;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -1302,7 +1473,8 @@ static int launch_aug(const __half* xb, const float* xinv, const float* xn2, flo
     if (g_ev_count < kTimingSlots) slot = g_ev_count++;
   }
   if (slot >= 0) VQB_CUDA_TRY(cudaEventRecord(g_ev0[slot], st));
-  if (drain) VQB_CUDA_TRY(cudaLaunchKernelEx(&cfg, search_aug_kernel<true>, mx, mc, mxa, mca, P));
+  if (do_conv) VQB_CUDA_TRY(cudaLaunchKernelEx(&cfg, search_aug_kernel<true, true>, mx, mc, mxa, mca, P));
+  else if (drain) VQB_CUDA_TRY(cudaLaunchKernelEx(&cfg, search_aug_kernel<true>, mx, mc, mxa, mca, P));
   else VQB_CUDA_TRY(cudaLaunchKernelEx(&cfg, search_aug_kernel<false>, mx, mc, mxa, mca, P));
   ++g_launch_count;
   if (slot >= 0) VQB_CUDA_TRY(cudaEventRecord(g_ev1[slot], st));
@@ -1311,14 +1483,16 @@ static int launch_aug(const __half* xb, const float* xinv, const float* xn2, flo
 
 int launch_search_tc(const __half* xb, const float* xinv, const float* xn2, float tie, const __half* xaug,
                      const __half* cb, const __half* caug, const float* chdr, const float* bias, int aug_mode,
-                     int64_t H, int64_t N, int K, int dp, void* cand, uint32_t* scal, bool timing, cudaStream_t st) {
+                     int64_t H, int64_t N, int K, int dp, void* cand, uint32_t* scal, bool timing, cudaStream_t st,
+                     const ConvArgs& conv) {
   const int Kp = k_pad(K);
+  VQB_REQUIRE(conv.x == nullptr || aug_mode, VQB_ERR_INVALID, "in-kernel latent conversion needs the bias k-step kernel");
   if (aug_mode) {
     VQB_REQUIRE(xaug && caug, VQB_ERR_INVALID, "search: bias operands missing");
     VQB_REQUIRE(dp % kBlockK == 0 && dp / kBlockK <= kMaxKB, VQB_ERR_UNSUPPORTED, "d_pad %d unsupported by the TC path", dp);
     VQB_REQUIRE(N < (1ll << 31) - kBlockM, VQB_ERR_UNSUPPORTED, "N too large for TMA coordinates");
     return launch_aug(xb, xinv, xn2, tie, xaug, cb, caug, chdr, H, N, K, dp, aug_mode == 1 ? 1 : 0, cand, scal, timing,
-                      st);
+                      st, conv);
   }
   VQB_REQUIRE(dp % kBlockK == 0 && dp / kBlockK <= kMaxKB, VQB_ERR_UNSUPPORTED, "d_pad %d unsupported by the TC path", dp);
   VQB_REQUIRE(N < (1ll << 31) - kBlockM, VQB_ERR_UNSUPPORTED, "N too large for TMA coordinates");

@@ -18,6 +18,7 @@ VQB_EUCLID, VQB_DOT = 0, 1
 SEARCH_LATENTS_PREPARED = 1
 SEARCH_FORCE_EXACT = 2
 SEARCH_TIMING = 4
+SEARCH_FUSED_PREP = 8
 
 _DTYPES = {torch.float32: VQB_F32, torch.bfloat16: VQB_BF16, torch.float16: VQB_F16}
 

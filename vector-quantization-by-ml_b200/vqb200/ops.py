@@ -100,8 +100,9 @@ def prepare_codebook(embeddings: torch.Tensor, use_cosine_sim: bool,
 @_on_device
 def search(x: torch.Tensor, embeddings: torch.Tensor, cache: Optional[torch.Tensor], use_cosine_sim: bool, *,
            idx_offset: int = 0, want_score: bool = False, latents_prepared: bool = False,
-           force_exact: bool = False) -> Tuple[torch.Tensor, Optional[torch.Tensor], torch.Tensor]:
-    """Nearest code of every row.  Returns (idx (H,N) int64, score (H,N) fp32 | None, search workspace)."""
+           force_exact: bool = False, fused_prep: bool = False) -> Tuple[torch.Tensor, Optional[torch.Tensor], torch.Tensor]:
+    """Nearest code of every row.  Returns (idx (H,N) int64, score (H,N) fp32 | None, search workspace).
+    `fused_prep` (opt-in, include/vqb.h VQB_SEARCH_FUSED_PREP): 16-bit latents are converted inside the search kernel."""
     L.require_cuda(x, "x")
     L.require_cuda(embeddings, "embeddings")
     H, N, d = x.shape
@@ -113,7 +114,7 @@ def search(x: torch.Tensor, embeddings: torch.Tensor, cache: Optional[torch.Tens
     score = torch.empty((H, N), dtype=torch.float32, device=dev) if want_score else None
     ws = workspace("search", L.lib().vqb_search_workspace_bytes(H, N, K, d), dev)
     flags = (L.SEARCH_LATENTS_PREPARED if latents_prepared else 0) | (L.SEARCH_FORCE_EXACT if force_exact else 0) \
-        | (L.SEARCH_TIMING if TIME_SEARCH_KERNEL else 0)
+        | (L.SEARCH_TIMING if TIME_SEARCH_KERNEL else 0) | (L.SEARCH_FUSED_PREP if fused_prep else 0)
     L.check(L.lib().vqb_search(L.ptr(x), L.dtype_code(x), L.ptr(embeddings), L.ptr(cache), _metric(use_cosine_sim),
                                H, N, K, d, int(idx_offset), L.ptr(idx), L.ptr(score), flags, L.ptr(ws), ws.numel(),
                                L.stream_ptr(dev)), "vqb_search")
