@@ -7,6 +7,8 @@
 //     power-of-two scales remove fp16's range problem and are undone exactly in the epilogue.
 //   * per-search lower-bound bias  L_k = |c_k|^2/2 - E_k  (see search_resolve.cu for the proof sketch)
 //   * l2norm of rows (reference utils/losses.py:19)
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace vqb {
@@ -85,8 +87,8 @@ __global__ void codebook_aug_scale_kernel(int64_t H, float* __restrict__ hdr) {
 // Fast variant for d % 8 == 0, d <= 256 (one 8-element group per lane): a warp converts 4 (fp32) or 8 (16-bit) rows per
 // iteration with all loads issued up front -- with one 512 B row per warp in flight the kernel is latency bound (Little's law:
 // ~19 KB per SM in flight ~ 3.5 TB/s).
-template <typename T>
-__global__ void __launch_bounds__(256)
+template <typename T, int MINB>
+__global__ void __launch_bounds__(256, MINB)
 prepare_latents4_kernel(const T* __restrict__ x, int64_t rows, int64_t rows_per_head, bool single_head, int d, int dp,
                         const float* __restrict__ chdr, __half* __restrict__ xb, float* __restrict__ xinv,
                         float* __restrict__ xn2, __half* __restrict__ xaug, uint32_t* __restrict__ scal) {
@@ -119,8 +121,8 @@ prepare_latents4_kernel(const T* __restrict__ x, int64_t rows, int64_t rows_per_
       float m = 0.f;
 #pragma unroll
       for (int e = 0; e < 8; ++e) m = fmaxf(m, fabsf(vv.v[e]));
-#pragma unroll
-      for (int o2 = 16; o2 > 0; o2 >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o2));
+      // non-negative floats order like their bit patterns: one REDUX instead of five shuffle + max steps (same value)
+      m = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(m)));
       float s = pow2_scale_bits(m);
       float a = 1.f;
       if (chdr) a = clamp_row_scale(s, two_q, two_mq);
@@ -408,10 +410,21 @@ int launch_prepare_latents(const void* x, int x_dtype, int64_t rows, int64_t row
                                                                                 rows_per_head >= rows, d, dp, chdr,
                                                                                 xb, xinv, xn2, xaug, scal));
   } else if ((d & 7) == 0 && d <= 256 && (rows_per_head >= rows || (rows_per_head % 8 == 0 && rows < (1ll << 32)))) {
-    VQB_DISPATCH_DTYPE(x_dtype, T,
-      prepare_latents4_kernel<T><<<(unsigned)blocks, warps * 32, 0, st>>>((const T*)x, rows, rows_per_head,
-                                                                          rows_per_head >= rows, d, dp, chdr,
-                                                                          xb, xinv, xn2, xaug, scal));
+    static int minb = -1;     // env VQB_PREP_MINB: resident blocks per SM the kernel is compiled for (register cap)
+    if (minb < 0) { const char* e = getenv("VQB_PREP_MINB"); minb = e ? atoi(e) : 3; }
+    const int64_t want = (rows + warps - 1) / warps, cap = (int64_t)sms * 4 * (minb >= 4 ? 4 : (minb == 3 ? 3 : 2));
+    blocks = want < cap ? want : cap;      // persistent: as many blocks as fit at this register cap
+    if (blocks < 1) blocks = 1;
+    if (minb >= 4) {
+      VQB_DISPATCH_DTYPE(x_dtype, T, (prepare_latents4_kernel<T, 4><<<(unsigned)blocks, warps * 32, 0, st>>>(
+          (const T*)x, rows, rows_per_head, rows_per_head >= rows, d, dp, chdr, xb, xinv, xn2, xaug, scal)));
+    } else if (minb == 3) {
+      VQB_DISPATCH_DTYPE(x_dtype, T, (prepare_latents4_kernel<T, 3><<<(unsigned)blocks, warps * 32, 0, st>>>(
+          (const T*)x, rows, rows_per_head, rows_per_head >= rows, d, dp, chdr, xb, xinv, xn2, xaug, scal)));
+    } else {
+      VQB_DISPATCH_DTYPE(x_dtype, T, (prepare_latents4_kernel<T, 2><<<(unsigned)blocks, warps * 32, 0, st>>>(
+          (const T*)x, rows, rows_per_head, rows_per_head >= rows, d, dp, chdr, xb, xinv, xn2, xaug, scal)));
+    }
   } else {
     VQB_DISPATCH_DTYPE(x_dtype, T,
       prepare_latents_kernel<T><<<(unsigned)blocks, warps * 32, 0, st>>>((const T*)x, rows, rows_per_head, d, dp, chdr,
