@@ -67,6 +67,37 @@ __device__ __forceinline__ float exact_score(const T* __restrict__ xr, const flo
   return sqrtf(fmaxf(d2, 0.f));
 }
 
+// exact_score(xr, cr, d, metric, row_norm2(xr, d)) in ONE walk over the latent row: three independent fma chains, each in
+// the order of the two functions above, so the value is bit-identical (the pair scorer walked every row twice)
+template <typename T>
+__device__ __forceinline__ float exact_score_norm(const T* __restrict__ xr, const float* __restrict__ cr, int d,
+                                                  int metric) {
+  double dot = 0.0, cn2 = 0.0, n2 = 0.0;
+  if ((d & 3) == 0) {
+#pragma unroll 8
+    for (int j = 0; j < d; j += 4) {
+      float4 a = load4<T>(xr + j);
+      float4 c = __ldg(reinterpret_cast<const float4*>(cr + j));
+      n2 = fma((double)a.x, (double)a.x, n2); n2 = fma((double)a.y, (double)a.y, n2);
+      n2 = fma((double)a.z, (double)a.z, n2); n2 = fma((double)a.w, (double)a.w, n2);
+      dot = fma((double)a.x, (double)c.x, dot); dot = fma((double)a.y, (double)c.y, dot);
+      dot = fma((double)a.z, (double)c.z, dot); dot = fma((double)a.w, (double)c.w, dot);
+      cn2 = fma((double)c.x, (double)c.x, cn2); cn2 = fma((double)c.y, (double)c.y, cn2);
+      cn2 = fma((double)c.z, (double)c.z, cn2); cn2 = fma((double)c.w, (double)c.w, cn2);
+    }
+  } else {
+    for (int j = 0; j < d; ++j) {
+      double a = (double)to_f32<T>(xr[j]), c = (double)cr[j];
+      n2 = fma(a, a, n2);
+      dot = fma(a, c, dot);
+      cn2 = fma(c, c, cn2);
+    }
+  }
+  if (metric == VQB_DOT) return (float)(-dot);
+  float d2 = (float)(n2 + cn2 - 2.0 * dot);
+  return sqrtf(fmaxf(d2, 0.f));
+}
+
 constexpr float kPackSlack = 6.2e-5f;   // 2 keys x 2^-17 (6 id bits) + fma rounding, with margin
 
 // candidate bookkeeping shared by both resolve phases ------------------------------------------------
@@ -353,8 +384,7 @@ pair_score_kernel(const T* __restrict__ x, const float* __restrict__ cb, const u
     if (pr.y >= (uint32_t)K || gid >= total_rows) continue;
     const int64_t h = gid / N;
     const T* xr = x + gid * (int64_t)d;
-    const double xn2 = metric == VQB_EUCLID ? row_norm2<T>(xr, d) : 0.0;
-    const float s = exact_score<T>(xr, cb + (h * K + (int64_t)pr.y) * d, d, metric, xn2);
+    const float s = exact_score_norm<T>(xr, cb + (h * K + (int64_t)pr.y) * d, d, metric);
     atomicMin(keys + gid, pack_key(s, (int)pr.y));
   }
 }
