@@ -1,4 +1,4 @@
-"""Bring-up: clock stamps of the converter warps and the producer of cluster 0 (library built with -DVQB_TRACE)."""
+"""Bring-up: clock stamps of the converter warps and the producer of cluster 0 (`make -C vector-quantization-by-ml_b200/csrc trace` -> tools/micro/libvqb200_trace.so)."""
 import os, sys, ctypes as C, statistics as st
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "vector-quantization-by-ml_b200"))
@@ -13,7 +13,7 @@ c = torch.randn(1, K, d, generator=g, device=dev) * 0.5
 cache = ops.prepare_codebook(c, False)
 ops.TIME_SEARCH_KERNEL = True
 for _ in range(3):
-    ops.search(x, c, cache, False)
+    ops.search(x, c, cache, False, fused_prep=True)
 torch.cuda.synchronize()
 print("kernel ms", ops.search_kernel_times_ms())
 T = 256

@@ -1,5 +1,5 @@
-"""Bring-up: per-tile clock stamps of cluster 0 of the d = 64 search kernel (library built with `make EXTRA=-DVQB_TRACE`
-into tools/micro/).  Prints the intervals of the accumulator hand-off chain in SM cycles, per epilogue warp."""
+"""Bring-up: per-tile clock stamps of cluster 0 of the d = 64 search kernel (library built with `make -C vector-quantization-by-ml_b200/csrc trace`
+-> tools/micro/libvqb200_trace.so).  Prints the intervals of the accumulator hand-off chain in SM cycles, per epilogue warp."""
 import os, sys, ctypes as C, statistics as st
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "vector-quantization-by-ml_b200"))
