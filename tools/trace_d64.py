@@ -53,3 +53,13 @@ i = 130
 for w in range(16):
     print(f"  w{w:2d} {E[0][w][i] - M[1][i]:6d} {E[1][w][i] - M[1][i]:6d} {E[2][w][i] - M[1][i]:6d}")
 print(f"  mma: empty_seen(130) {M[0][i] - M[1][i]}, empty_seen(131) {M[0][i+1] - M[1][i]}, empty_seen(132) {M[0][i+2] - M[1][i]}, issued(131) {M[1][i+1] - M[1][i]}")
+# per-position-in-row-tile period of the MMA warp (where a row tile spends its time)
+NT = (K + 255) // 256
+if NT <= 64 and M[0][NT] != 0:      # the MMA warp's stamps exist for one-stage tiles (d_pad = 64) only
+    print(f"MMA period by N tile within a row tile (NT = {NT}; mean over the traced row tiles, cycles):")
+    per = [[] for _ in range(NT)]
+    for i in range(NT, min(T - 1, (T // NT) * NT - 1)):
+        per[i % NT].append(M[0][i + 1] - M[0][i])
+    print("  " + " ".join(f"{int(st.mean(p)):5d}" for p in per if p))
+    tot = sum(st.mean(p) for p in per if p)
+    print(f"  row tile total {tot:.0f} cycles; steady-state tile (median position) {sorted(st.mean(p) for p in per if p)[NT // 2]:.0f}")
